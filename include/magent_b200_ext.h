@@ -1,0 +1,35 @@
+/*
+ * magent_b200_ext.h -- entry points the B200 engine adds next to the reference ABI.
+ * None of them exists in the reference library; a caller that never uses them is a pure drop-in.
+ */
+#ifndef MAGENT_B200_EXT_H
+#define MAGENT_B200_EXT_H
+#include <stddef.h>
+#include "magent_runtime_api.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int magent_b200_version(void);                 /* 1000*major + minor */
+const char *magent_b200_last_error(void);
+int magent_b200_device_count(void);            /* 0 when no CUDA device is visible */
+
+/* page-locked host memory for observation / reward receive buffers (PCIe-speed copies) */
+void *magent_b200_host_alloc(size_t bytes);
+int magent_b200_host_free(void *p);
+
+int magent_b200_sync(EnvHandle game);          /* wait for all queued device work of this game */
+/* route the following setup calls (add_agents, seed) to one arena of the batch; -1 = all arenas */
+int magent_b200_select_arena(EnvHandle game, int arena);
+/* set_action with uniform random actions generated on the device (throughput runs; not part of parity).
+ * `unused` must be NULL. */
+int magent_b200_random_actions(EnvHandle game, GroupHandle group, void *unused, unsigned long long seed);
+/* int64 event counters since construction: agent_steps, attacks, hits, kills, starved, moves_ok,
+ * moves_blocked, steps.  Returns the number written. */
+int magent_b200_get_counters(EnvHandle game, long long *out, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

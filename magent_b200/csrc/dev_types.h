@@ -1,0 +1,144 @@
+// dev_types.h -- plain-old-data layout of the engine state in HBM, shared by host and device.
+//
+// Layout summary:
+//   * `occ`   int32 [A][H*W]   one cell code per grid cell: OCC_EMPTY, OCC_WALL or an agent code
+//             (group << 24 | index-in-group).  A w x l body writes its code into every cell it covers.
+//             Replaces reference MapSlot{slot_type,occ_type,occupier*} + channel_ids
+//             (src/gridworld/Map.h:23-29,72-73): channel and hp are derived from the code.
+//   * per group, arena-major SoA arrays [A][cap] in *group vector order* (the reference keeps
+//             std::vector<Agent*> per group, GridWorld.h:256-313; index == position in that vector),
+//             ping-pong double buffered so `clear_dead` is a stable parallel compaction.
+//   * per-agent step scratch [A][cap_total] addressed by flat = foff[group] + index.
+//   * per-arena header (rng state, done flag, relaxation flags) and [G][A] count arrays.
+#pragma once
+#include <stdint.h>
+#include "hd.h"
+
+namespace mg {
+
+enum { MG_MAX_GROUPS = 8, MG_MAX_RULES = 16, MG_MAX_PROG = 16, MG_MAX_RECV = 4 };
+enum { MG_N_COUNTERS = 8 };
+enum Counter { CNT_AGENT_STEPS = 0, CNT_ATTACKS, CNT_HITS, CNT_KILLS, CNT_STARVED,
+               CNT_MOVES_OK, CNT_MOVES_BLOCKED, CNT_STEPS };
+
+enum : int { OCC_EMPTY = -1, OCC_WALL = -2 };
+enum : int { RANK_NONE = -1, DEATH_NEVER = 0x7fffffff, DEATH_BEFORE = -1 };
+enum : unsigned { MVKEY_NONE = 0xffffffffu };
+
+// agent flags
+enum : unsigned char { FLAG_DEAD = 1, FLAG_ABSORBED = 2 };
+// mover states
+enum : unsigned char { MV_NONE = 0, MV_OOB = 1, MV_STATIC_FAIL = 2, MV_PENDING_FAIL = 3, MV_OK = 4 };
+
+// EventOp numbering of the reference (src/gridworld/grid_def.h:17-23)
+enum EventOp : unsigned char { OP_AND = 0, OP_OR, OP_NOT, OP_KILL, OP_AT, OP_IN, OP_COLLIDE, OP_ATTACK,
+                               OP_DIE, OP_IN_A_LINE, OP_ALIGN, OP_NULL };
+
+MG_HD int code_make(int g, int i) { return (g << 24) | i; }
+MG_HD int code_group(int c) { return c >> 24; }
+MG_HD int code_index(int c) { return c & 0xffffff; }
+
+struct AgentSoA {           // arena-major [A][cap]
+    int *x, *y;             // top-left cell of the body (reference Agent::pos)
+    float *hp;
+    int *act;               // last_action (reference Agent::last_action)
+    int *id;
+    float *next_reward, *last_reward;
+    int *op_obj;            // agent code of the object of last_op, or -1
+    unsigned char *last_op; // EventOp
+    unsigned char *flags;   // FLAG_DEAD | FLAG_ABSORBED
+    unsigned char *dir;     // Direction; always NORTH(3) while turn_mode is unsupported
+};
+
+struct GroupDev {
+    // ---- type constants (reference AgentType, src/gridworld/AgentType.h:17-48)
+    int body_w, body_l;
+    float max_hp, damage, step_recover, kill_supply;
+    float step_reward, kill_reward, dead_penalty, attack_penalty;
+    int attack_in_group;
+    int view_w, view_h, view_x1, view_y1;     // view rectangle and its left-top offset from the eye
+    int view_xoff, view_yoff;                 // eye offset from pos  (= width/2, length/2)
+    int att_xoff, att_yoff;
+    int n_move, attack_base, n_action, n_attack;
+    int channel;                              // group2channel(g)  (GridWorld.cc:915-924)
+    int feature_size;
+    const int *move_dx, *move_dy;             // [n_move]    (Range::num2delta)
+    const int *att_dx, *att_dy;               // [n_attack]
+    const unsigned char *view_mask;           // [view_h*view_w] is_in_range
+    // ---- state
+    int cap;                                  // per-arena capacity of the SoA arrays
+    int foff;                                 // flat scratch offset of this group inside an arena
+    AgentSoA soa[2];                          // ping-pong; bit g of `curmask` selects the live one
+};
+
+struct ArenaHdr {
+    uint32_t rng;            // minstd_rand0 state (reference GridWorld::random_engine)
+    uint32_t rng_next;
+    int done;
+    int n_attack;
+    int changed[3];          // rotating "something changed" flags of the relaxation loops
+    int rule_trigger;        // bitmask of rules triggered this step
+    float grp_reward[MG_MAX_GROUPS];
+};
+
+struct RuleInstr {           // postfix program over the bound (subject, object) pair
+    unsigned char op;        // EventOp
+    unsigned char role_a;    // 0 = subject, 1 = inferred object
+    unsigned char role_b;
+    unsigned char pad;
+    int i0, i1, i2, i3;      // OP_AT: x,y ; OP_IN: x1,y1,x2,y2
+};
+
+struct RuleRecv { int role; int group; float value; };   // role 0 subject, 1 object, 2 whole group
+
+struct RuleDev {
+    int kind;                // 0: scan one 'any' subject, optionally binding its op_obj
+    int sub_group;
+    int has_obj, obj_group, obj_index;      // obj_index -1 = any
+    int n_prog; RuleInstr prog[MG_MAX_PROG];
+    int n_recv; RuleRecv recv[MG_MAX_RECV];
+    int is_terminal;
+};
+
+struct EngineDev {
+    int A, W, H, G;
+    int nsep, bandwidth, large_map;           // GridWorld.cc:75-85, :407
+    int minimap_mode, embedding_size, n_channel, channel_base;
+    int cap_total, max_body;
+    uint32_t pow2[32];                        // 16807^(2^b) mod (2^31-1)
+    GroupDev grp[MG_MAX_GROUPS];
+    ArenaHdr *hdr;                            // [A]
+    int *n, *dead_ct;                         // [G][A]
+    int *off;                                 // [G][A+1] prefix of n over arenas (ABI concatenation)
+    int *done;                                // [A] done flag of the last step
+    int *occ, *claim_head;                    // [A][H*W]
+    // per-agent step scratch [A][cap_total]
+    int *att_rank, *tgt, *in_head, *in_next, *death, *mv_nx, *mv_ny;
+    unsigned *mv_key;
+    float *hp_fin;
+    unsigned char *mv_state;
+    // shuffle scratch [A][cap_total]
+    int *jv, *sh_head, *sh_next, *sh_first, *att_agent;
+    int *cl_next;                             // [A][cap_total*max_body] claimant list links
+    int n_rules; RuleDev rules[MG_MAX_RULES];
+    long long *counters;                      // [MG_N_COUNTERS]
+    int *team_scratch;                        // [2 * max CTAs] partial sums of team scans
+    int *mm_count;                            // [A][G][max_view_cells] minimap histogram scratch
+};
+
+struct StepArgs {
+    unsigned curmask;
+    int n_order;
+    int order[MG_MAX_GROUPS];                 // groups that received set_action, in call order
+};
+
+struct ObsArgs {
+    unsigned curmask;
+    int group;
+    float *view;                              // [sum_a n][view_h][view_w][n_channel]
+    float *feature;                           // [sum_a n][feature_size]
+};
+
+enum InfoKind { INFO_ID = 0, INFO_POS, INFO_ALIVE, INFO_REWARD, INFO_ACTION_SCATTER, INFO_HP };
+
+}  // namespace mg

@@ -1,0 +1,898 @@
+// engine.cc -- host side of the B200 grid-world engine.  See engine.h.
+#include "engine.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <set>
+
+#include "backend.h"
+
+namespace mg {
+
+static std::string g_last_error;
+const char *last_error() { return g_last_error.c_str(); }
+void set_last_error(const std::string &s) { g_last_error = s; }
+
+// The reference signals fatal conditions with LOG(FATAL), which throws from a destructor and ends in
+// std::terminate (src/utility/utility.h:77-80,103).  Same observable behaviour: message, then abort.
+void fatal(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    fprintf(stderr, "[magent_b200 FATAL] %s\n", buf);
+    fflush(stderr);
+    abort();
+}
+
+static bool strequ(const char *a, const char *b) { return strcmp(a, b) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// ranges  (reference src/gridworld/Range.h:149-190; same double-precision arithmetic)
+RangeTab make_circle_range(float radius, float inner_radius, int parity) {
+    const double eps = 1e-8;
+    RangeTab r;
+    r.width = 2 * int(radius + eps) + parity;
+    int center = (int)(radius);
+    if (r.width % 2 != parity) r.width++;
+    r.height = r.width;
+    r.mask.assign((size_t)r.width * r.width, 0);
+    double delta = (parity == 0 ? 0.5 : 0);
+    for (int i = 0; i < r.width; i++) {
+        for (int j = 0; j < r.width; j++) {
+            double dis_x = fabs(j - center + delta);
+            double dis_y = fabs(i - center + delta);
+            double dis = sqrt(dis_x * dis_x + dis_y * dis_y);
+            if (dis < radius + eps && dis > inner_radius - eps) {
+                r.mask[(size_t)i * r.width + j] = 1;
+                r.dx.push_back(j - center);
+                r.dy.push_back(i - center);
+                r.count++;
+            }
+        }
+    }
+    r.x1 = r.y1 = -center;
+    r.x2 = r.y2 = r.width - center - 1;
+    return r;
+}
+
+void HostGroup::clear() { resize(0); dead_ct = 0; grp_reward = 0.0f; }
+void HostGroup::resize(int n) {
+    x.resize(n); y.resize(n); id.resize(n); act.resize(n); op_obj.resize(n);
+    hp.resize(n); next_reward.resize(n); last_reward.resize(n);
+    last_op.resize(n); flags.resize(n); dir.resize(n);
+}
+
+// ---------------------------------------------------------------------------------------------
+Engine::Engine() {
+    memset(&hE_, 0, sizeof hE_);
+    arenas_.resize(1);
+    arenas_[0].rng = minstd_seed(0);                  // GridWorld.cc:29
+}
+
+Engine::~Engine() { free_device(); }
+
+void Engine::check_group(int g, const char *where) const {
+    if (g < 0 || g >= G()) fatal("invalid group handle %d in %s", g, where);
+}
+
+int Engine::group2channel(int g) const {             // GridWorld.cc:915-924
+    int base = 1, scale = 2;
+    if (food_mode_) base++;
+    if (minimap_mode_) scale++;
+    return base + g * scale;
+}
+
+int Engine::feature_size(int g) const {              // GridWorld.cc:926-934
+    int f = embedding_size_ + group_type_[g]->n_action + 1;
+    if (goal_mode_) f += 2;
+    if (minimap_mode_) f += 2;
+    return f;
+}
+
+void Engine::set_config(const char *key, void *p_value) {     // GridWorld.cc:120-149
+    int ivalue = *(int *)p_value;
+    bool bvalue = *(bool *)p_value;
+    if (strequ(key, "map_width")) W_ = ivalue;
+    else if (strequ(key, "map_height")) H_ = ivalue;
+    else if (strequ(key, "food_mode")) {
+        food_mode_ = bvalue;
+        if (bvalue) fatal("food_mode is not supported by the B200 engine yet (SURVEY.md §8f rank 4)");
+    } else if (strequ(key, "turn_mode")) {
+        turn_mode_ = bvalue;
+        if (bvalue) fatal("turn_mode is not supported by the B200 engine yet (SURVEY.md §8f rank 4)");
+    } else if (strequ(key, "minimap_mode")) minimap_mode_ = bvalue;
+    else if (strequ(key, "goal_mode")) goal_mode_ = bvalue;
+    else if (strequ(key, "embedding_size")) embedding_size_ = ivalue;
+    else if (strequ(key, "render_dir")) { /* replay dump is out of scope; accepted and ignored */ }
+    else if (strequ(key, "seed")) {
+        if (where_ == DEVICE) to_host(false);
+        for (int a = 0; a < A_; ++a)
+            if (sel_arena_ < 0 || sel_arena_ == a)
+                arenas_[a].rng = minstd_seed((long long)ivalue + (sel_arena_ < 0 ? a : 0));
+    }
+    // ---- extension keys (unknown keys are FATAL in the reference, so these cannot collide)
+    else if (strequ(key, "num_arenas")) {
+        if (was_reset_) fatal("num_arenas must be configured before the first reset");
+        if (ivalue < 1) fatal("num_arenas must be >= 1");
+        A_ = ivalue;
+        uint32_t seed0 = arenas_[0].rng;
+        arenas_.assign(A_, HostArena());
+        for (int a = 0; a < A_; ++a) arenas_[a].rng = a == 0 ? seed0 : minstd_seed(a);
+    } else if (strequ(key, "device_id")) device_id_ = ivalue;
+    else fatal("invalid argument in GridWorld::set_config : %s", key);
+}
+
+void Engine::register_agent_type(const char *name, int n, const char **keys, float *values) {
+    std::string str(name);
+    if (types_.count(str)) fatal("duplicated name of agent type in GridWorld::register_agent_type : %s", name);
+    AgentTypeDef t;
+    t.name = str;
+    float view_x_offset = 0, view_y_offset = 0, att_x_offset = 0, att_y_offset = 0, turn_x = 0, turn_y = 0;
+    for (int i = 0; i < n; i++) {                     // AgentType.cc:52-83
+        const char *k = keys[i];
+        float v = values[i];
+#define MG_SET_INT(f) if (strequ(k, #f)) { t.f = (int)(v + 0.5); continue; }
+#define MG_SET_FLT(f) if (strequ(k, #f)) { t.f = v; continue; }
+#define MG_SET_BOOL(f) if (strequ(k, #f)) { t.f = bool(int(v + 0.5)); continue; }
+        MG_SET_INT(width) MG_SET_INT(length)
+        MG_SET_FLT(speed) MG_SET_FLT(hp)
+        MG_SET_FLT(view_radius) MG_SET_FLT(view_angle) MG_SET_FLT(attack_radius) MG_SET_FLT(attack_angle)
+        MG_SET_FLT(hear_radius) MG_SET_FLT(speak_radius) MG_SET_INT(speak_ability)
+        MG_SET_FLT(damage) MG_SET_FLT(trace) MG_SET_FLT(eat_ability)
+        MG_SET_FLT(step_recover) MG_SET_FLT(kill_supply) MG_SET_FLT(food_supply)
+        MG_SET_BOOL(attack_in_group) MG_SET_BOOL(can_absorb)
+        MG_SET_FLT(step_reward) MG_SET_FLT(kill_reward) MG_SET_FLT(dead_penalty) MG_SET_FLT(attack_penalty)
+#undef MG_SET_INT
+#undef MG_SET_FLT
+#undef MG_SET_BOOL
+        if (strequ(k, "view_x_offset")) { view_x_offset = v; continue; }
+        if (strequ(k, "view_y_offset")) { view_y_offset = v; continue; }
+        if (strequ(k, "att_x_offset")) { att_x_offset = v; continue; }
+        if (strequ(k, "att_y_offset")) { att_y_offset = v; continue; }
+        if (strequ(k, "turn_x_offset")) { turn_x = v; continue; }
+        if (strequ(k, "turn_y_offset")) { turn_y = v; continue; }
+        fatal("invalid agent config in AgentType::AgentType : %s", k);
+    }
+    (void)view_x_offset; (void)view_y_offset; (void)att_x_offset; (void)att_y_offset; (void)turn_x; (void)turn_y;
+    if (t.can_absorb) fatal("can_absorb agent types are not supported by the B200 engine yet (SURVEY.md §8f rank 1)");
+    if (t.width < 1 || t.length < 1 || t.width * t.length > 16) fatal("unsupported body size %dx%d", t.width, t.length);
+
+    int parity = t.width % 2;                         // AgentType.cc:86-105
+    if (t.view_angle >= 180) {
+        if (fabs(t.view_angle - 360) > 1e-5) fatal("only supports ranges with angle = 360, when angle > 180.");
+        t.view = make_circle_range(t.view_radius, 0, parity);
+    } else fatal("SectorRange views are not supported by the B200 engine yet (SURVEY.md §8f rank 4)");
+    if (t.attack_angle >= 180) {
+        if (fabs(t.attack_angle - 360) > 1e-5) fatal("only supports ranges with angle = 360, when angle > 180.");
+        t.attack = make_circle_range(t.attack_radius, t.width / 2.0f, parity);
+    } else if (t.attack_radius == 0 && t.attack_angle == 0) {
+        // the reference default (attack_angle = 0) builds an empty SectorRange(0, 0): no attack actions
+        t.attack = RangeTab();
+    } else fatal("SectorRange attacks are not supported by the B200 engine yet (SURVEY.md §8f rank 4)");
+    t.move = make_circle_range(t.speed, 0, 1);
+    t.view_x_offset = t.width / 2; t.view_y_offset = t.length / 2;       // AgentType.cc:106-108
+    t.att_x_offset = t.width / 2;  t.att_y_offset = t.length / 2;
+    t.move_base = 0;
+    t.turn_base = t.move.count;
+    t.attack_base = t.turn_base;                      // turn_mode off
+    t.n_action = t.attack_base + t.attack.count;
+    types_.insert(std::make_pair(str, t));
+}
+
+void Engine::new_group(const char *type_name, int *handle) {            // GridWorld.cc:160-169
+    auto it = types_.find(std::string(type_name));
+    if (it == types_.end()) fatal("invalid name of agent type in new_group : %s", type_name);
+    if (G() >= MG_MAX_GROUPS) fatal("too many groups (max %d)", (int)MG_MAX_GROUPS);
+    if (where_ == DEVICE) to_host(false);
+    *handle = G();
+    group_type_.push_back(&it->second);
+    for (auto &ar : arenas_) ar.groups.resize(G());
+    refresh_host_counts();
+}
+
+void Engine::define_agent_symbol(int no, int group, int index) {        // RewardEngine.cc:28-35
+    if (no >= (int)symbols_.size()) symbols_.resize(no + 1);
+    symbols_[no].group = group;
+    symbols_[no].index = index;
+}
+
+void Engine::define_event_node(int no, int op, int *inputs, int n_inputs) {   // RewardEngine.cc:37-49
+    if (no >= (int)nodes_.size()) nodes_.resize(no + 1);
+    nodes_[no].op = op;
+    for (int i = 0; i < n_inputs; i++) nodes_[no].raw.push_back(inputs[i]);
+}
+
+void Engine::add_reward_rule(int on, int *receivers, float *values, int n_receiver,
+                             bool is_terminal, bool auto_value) {       // RewardEngine.cc:51-69
+    RuleDef r;
+    r.on = on;
+    for (int i = 0; i < n_receiver; i++) { r.recv.push_back(receivers[i]); r.values.push_back(values[i]); }
+    r.is_terminal = is_terminal;
+    r.auto_value = auto_value;
+    rules_.push_back(r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reward-rule compiler.  Re-derives the reference's binding plan (related symbols, inference map,
+// input_symbols / infer_obj; RewardEngine.cc:71-189) and lowers the shapes the device evaluator
+// handles: ONE 'any' subject symbol, optionally with its op_obj bound to a second symbol.
+namespace {
+struct NodeInfo { std::set<int> related; std::map<int, int> infer; };
+
+void collect(const std::vector<NodeDef> &nodes, int no, std::vector<NodeInfo> &info, std::vector<char> &seen) {
+    if (seen[no]) return;
+    seen[no] = 1;
+    const NodeDef &n = nodes[no];
+    NodeInfo &me = info[no];
+    switch (n.op) {
+        case OP_AND: case OP_OR:
+            for (int q = 0; q < 2; ++q) {
+                collect(nodes, n.raw[q], info, seen);
+                me.related.insert(info[n.raw[q]].related.begin(), info[n.raw[q]].related.end());
+                me.infer.insert(info[n.raw[q]].infer.begin(), info[n.raw[q]].infer.end());
+            }
+            break;
+        case OP_NOT:
+            collect(nodes, n.raw[0], info, seen);
+            me.related = info[n.raw[0]].related;
+            me.infer = info[n.raw[0]].infer;
+            break;
+        case OP_KILL: case OP_COLLIDE: case OP_ATTACK:
+            me.related.insert(n.raw[0]); me.related.insert(n.raw[1]);
+            me.infer.insert(std::make_pair(n.raw[0], n.raw[1]));
+            break;
+        case OP_AT: case OP_IN: case OP_DIE: case OP_IN_A_LINE: case OP_ALIGN:
+            me.related.insert(n.raw[0]);
+            break;
+        default:
+            fatal("invalid event op in GridWorld::collect_related_symbol");
+    }
+}
+}  // namespace
+
+void Engine::compile_rules() {
+    compiled_rules_.clear();
+    if (rules_.size() > MG_MAX_RULES) fatal("too many reward rules (max %d)", (int)MG_MAX_RULES);
+    std::vector<NodeInfo> info(nodes_.size());
+    std::vector<char> seen(nodes_.size(), 0);
+    for (size_t i = 0; i < nodes_.size(); ++i) collect(nodes_, (int)i, info, seen);
+
+    for (size_t ri = 0; ri < rules_.size(); ++ri) {
+        const RuleDef &rd = rules_[ri];
+        const NodeInfo &on = info[rd.on];
+        std::vector<int> input, infer;
+        std::set<int> added;
+        for (int s : on.related) {                    // first pass: symbols whose object can be inferred
+            if (added.count(s)) continue;
+            auto it = on.infer.find(s);
+            if (it != on.infer.end()) {
+                input.push_back(s); infer.push_back(it->second);
+                added.insert(s); added.insert(it->second);
+            }
+        }
+        for (int s : on.related)                      // second pass: the rest
+            if (!added.count(s)) { input.push_back(s); infer.push_back(-1); }
+
+        if (input.size() != 1 || symbols_[input[0]].index != -1)
+            fatal("reward rule %d: only rules with a single 'any' subject symbol are supported by the "
+                  "B200 engine yet (got %d input symbols; SURVEY.md §8f rank 1)", (int)ri, (int)input.size());
+        RuleDev R;
+        memset(&R, 0, sizeof R);
+        R.kind = 0;
+        R.sub_group = symbols_[input[0]].group;
+        check_group(R.sub_group, "reward rule subject");
+        R.has_obj = infer[0] >= 0;
+        if (R.has_obj) {
+            R.obj_group = symbols_[infer[0]].group;
+            R.obj_index = symbols_[infer[0]].index;
+            if (R.obj_index == -2) fatal("reward rule %d: the object of attack/kill/collide cannot be a group", (int)ri);
+        }
+        auto role_of = [&](int sym) -> int {
+            if (sym == input[0]) return 0;
+            if (R.has_obj && sym == infer[0]) return 1;
+            fatal("reward rule %d: symbol %d is not bound by the trigger event", (int)ri, sym);
+        };
+        // postfix lowering of the trigger tree
+        struct Lower {
+            const std::vector<NodeDef> &nodes; RuleDev &R; decltype(role_of) &role;
+            void go(int no) {
+                const NodeDef &n = nodes[no];
+                RuleInstr I; memset(&I, 0, sizeof I);
+                I.op = (unsigned char)n.op;
+                switch (n.op) {
+                    case OP_AND: case OP_OR: go(n.raw[0]); go(n.raw[1]); break;
+                    case OP_NOT: go(n.raw[0]); break;
+                    case OP_KILL: case OP_COLLIDE: case OP_ATTACK:
+                        I.role_a = (unsigned char)role(n.raw[0]); I.role_b = (unsigned char)role(n.raw[1]); break;
+                    case OP_AT: I.role_a = (unsigned char)role(n.raw[0]); I.i0 = n.raw[1]; I.i1 = n.raw[2]; break;
+                    case OP_IN: I.role_a = (unsigned char)role(n.raw[0]);
+                        I.i0 = n.raw[1]; I.i1 = n.raw[2]; I.i2 = n.raw[3]; I.i3 = n.raw[4]; break;
+                    case OP_DIE: I.role_a = (unsigned char)role(n.raw[0]); break;
+                    default: fatal("event op %d is not supported by the B200 engine yet", n.op);
+                }
+                if (R.n_prog >= MG_MAX_PROG) fatal("reward rule trigger too large");
+                R.prog[R.n_prog++] = I;
+            }
+        } lower{nodes_, R, role_of};
+        lower.go(rd.on);
+        if (rd.recv.size() > MG_MAX_RECV) fatal("too many receivers in a reward rule");
+        for (size_t q = 0; q < rd.recv.size(); ++q) {
+            RuleRecv rc;
+            const SymbolDef &sd = symbols_[rd.recv[q]];
+            if (sd.index == -2) { rc.role = 2; rc.group = sd.group; }
+            else { rc.role = role_of(rd.recv[q]); rc.group = sd.group; }
+            rc.value = rd.values[q];
+            R.recv[R.n_recv++] = rc;
+        }
+        R.is_terminal = rd.is_terminal;
+        compiled_rules_.push_back(R);
+    }
+    rules_compiled_ = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host image of the arenas: episode setup
+void Engine::refresh_host_counts() {
+    h_off_.assign((size_t)G() * (A_ + 1), 0);
+    for (int g = 0; g < G(); ++g)
+        for (int a = 0; a < A_; ++a)
+            h_off_[(size_t)g * (A_ + 1) + a + 1] = h_off_[(size_t)g * (A_ + 1) + a] +
+                (g < (int)arenas_[a].groups.size() ? arenas_[a].groups[g].size() : 0);
+}
+
+void Engine::reset() {                                // GridWorld.cc:72-118, Map.cc:23-47
+    if (W_ <= 2 || H_ <= 2) fatal("map size not configured");
+    if (where_ == DEVICE) {                           // keep the RNG streams: they persist across reset
+        std::vector<ArenaHdr> hdr(A_);
+        be::d2h(hdr.data(), hE_.hdr, sizeof(ArenaHdr) * A_);
+        for (int a = 0; a < A_; ++a) arenas_[a].rng = hdr[a].rng;
+        where_ = HOST;
+    }
+    large_map_ = (long)W_ * H_ > 99 * 99;
+    nsep_ = large_map_ ? ((long)W_ * H_ > 1000 * 1000 ? 16 : 8) : 1;
+    for (auto &ar : arenas_) {
+        ar.id_counter = 0;
+        ar.done = 0;
+        ar.occ.assign((size_t)W_ * H_, OCC_EMPTY);
+        for (int i = 0; i < W_; i++) { ar.occ[i] = OCC_WALL; ar.occ[(size_t)(H_ - 1) * W_ + i] = OCC_WALL; }
+        for (int i = 0; i < H_; i++) { ar.occ[(size_t)i * W_] = OCC_WALL; ar.occ[(size_t)i * W_ + W_ - 1] = OCC_WALL; }
+        ar.groups.resize(G());
+        for (auto &g : ar.groups) g.clear();
+    }
+    if (!rules_compiled_) compile_rules();
+    was_reset_ = true;
+    order_.clear();
+    refresh_host_counts();
+}
+
+bool Engine::host_is_blank(const HostArena &ar, int x, int y, int w, int h) const {   // Map.cc:454-470
+    if (x < 0 || y < 0 || x + w >= W_ || y + h >= H_) return false;
+    for (int i = 0; i < w; i++)
+        for (int j = 0; j < h; j++)
+            if (ar.occ[(size_t)(y + j) * W_ + x + i] != OCC_EMPTY) return false;
+    return true;
+}
+
+static inline uint32_t rng_next(uint32_t &state) { state = mulmod31(state, MINSTD_A); return state; }
+
+void Engine::host_random_blank(HostArena &ar, int w, int h, int &x, int &y) {         // Map.cc:49-63
+    int tries = 0;
+    for (;;) {
+        x = (int)rng_next(ar.rng) % (W_ - w);
+        y = (int)rng_next(ar.rng) % (H_ - h);
+        if (host_is_blank(ar, x, y, w, h)) return;
+        if (tries++ > W_ * H_) fatal("cannot find a blank position in a filled map");
+    }
+}
+
+int Engine::host_add_wall(HostArena &ar, int x, int y) {                              // Map.cc:108-115
+    if (x < 0 || y < 0 || x >= W_ || y >= H_) return 1;
+    int &c = ar.occ[(size_t)y * W_ + x];
+    if (c >= 0) return 1;
+    c = OCC_WALL;
+    return 0;
+}
+
+int Engine::host_add_agent(HostArena &ar, int g, int x, int y) {                      // Map.cc:75-97 + Agent ctor
+    const AgentTypeDef &t = *group_type_[g];
+    if (!host_is_blank(ar, x, y, t.width, t.length)) return 1;
+    HostGroup &hg = ar.groups[g];
+    int i = hg.size();
+    if (i >= (1 << 23)) fatal("too many agents in one group of one arena (max %d)", 1 << 23);
+    hg.resize(i + 1);
+    hg.x[i] = x; hg.y[i] = y; hg.id[i] = ar.id_counter++;
+    hg.act[i] = t.n_action;                           // "dangerous here !" (GridWorld.h:140)
+    hg.op_obj[i] = -1;
+    hg.hp[i] = t.hp;
+    hg.next_reward[i] = t.step_reward; hg.last_reward[i] = 0.0f;
+    hg.last_op[i] = OP_NULL; hg.flags[i] = 0; hg.dir[i] = 3;
+    int code = code_make(g, i);
+    for (int bx = 0; bx < t.width; bx++)
+        for (int by = 0; by < t.length; by++)
+            ar.occ[(size_t)(y + by) * W_ + x + bx] = code;
+    return 0;
+}
+
+void Engine::add_agents(int group, int n, const char *method,
+                        const int *pos_x, const int *pos_y, const int *pos_dir) {    // GridWorld.cc:180-290
+    if (!was_reset_) fatal("add_agents before reset");
+    if (where_ == DEVICE) to_host(false);
+    const bool is_random = strequ(method, "random"), is_custom = strequ(method, "custom"),
+               is_fill = strequ(method, "fill");
+    if (!is_random && !is_custom && !is_fill) fatal("unsupported method in GridWorld::add_agents : %s", method);
+    if (group != -1) check_group(group, "GridWorld::add_agents");
+    for (int a = 0; a < A_; ++a) {
+        if (sel_arena_ >= 0 && sel_arena_ != a) continue;
+        HostArena &ar = arenas_[a];
+        if (group == -1) {
+            if (is_random) {
+                for (int i = 0; i < n; i++) { int x, y; host_random_blank(ar, 1, 1, x, y); host_add_wall(ar, x, y); }
+            } else if (is_custom) {
+                for (int i = 0; i < n; i++) host_add_wall(ar, pos_x[i], pos_y[i]);
+            } else {
+                int x0 = pos_x[0], y0 = pos_x[1], x1 = x0 + pos_x[2], y1 = y0 + pos_x[3];
+                for (int x = x0; x < x1; x++) for (int y = y0; y < y1; y++) host_add_wall(ar, x, y);
+            }
+        } else {
+            const AgentTypeDef &t = *group_type_[group];
+            if (is_random) {
+                for (int i = 0; i < n; i++) { int x, y; host_random_blank(ar, t.width, t.length, x, y); host_add_agent(ar, group, x, y); }
+            } else if (is_custom) {
+                for (int i = 0; i < n; i++) {
+                    if (pos_dir && pos_dir[i] >= 4) fatal("invalid direction in GridWorld::add_agent");
+                    host_add_agent(ar, group, pos_x[i], pos_y[i]);
+                }
+            } else {
+                int x0 = pos_x[0], y0 = pos_x[1], x1 = x0 + pos_x[2], y1 = y0 + pos_x[3];
+                for (int x = x0; x < x1; x += t.width)
+                    for (int y = y0; y < y1; y += t.length) host_add_agent(ar, group, x, y);
+            }
+        }
+    }
+    refresh_host_counts();
+}
+
+// ---------------------------------------------------------------------------------------------
+// device image
+void Engine::ensure_backend() {
+    if (device_ready_) return;
+    std::string err;
+    if (!be::init(device_id_, &err)) fatal("no usable CUDA device for the B200 engine: %s (there is no CPU fallback)", err.c_str());
+    device_ready_ = true;
+}
+
+void *Engine::dalloc(size_t bytes) {
+    void *p = be::dmalloc(bytes ? bytes : 16);
+    dev_allocs_.push_back(p);
+    return p;
+}
+
+void Engine::free_device() {
+    for (void *p : dev_allocs_) be::dfree(p);
+    dev_allocs_.clear();
+    if (d_view_stage_) be::dfree(d_view_stage_);
+    if (d_feat_stage_) be::dfree(d_feat_stage_);
+    if (d_io_stage_) be::dfree(d_io_stage_);
+    d_view_stage_ = d_feat_stage_ = nullptr; d_io_stage_ = nullptr;
+    view_stage_bytes_ = feat_stage_bytes_ = io_stage_bytes_ = 0;
+    dE_ = nullptr;
+    cap_.clear();
+}
+
+void *Engine::io_stage(size_t bytes) {
+    if (bytes > io_stage_bytes_) {
+        if (d_io_stage_) be::dfree(d_io_stage_);
+        io_stage_bytes_ = bytes + bytes / 4 + 256;
+        d_io_stage_ = be::dmalloc(io_stage_bytes_);
+    }
+    return d_io_stage_;
+}
+
+int Engine::max_agents_per_arena() const {
+    int m = 0;
+    for (int a = 0; a < A_; ++a) {
+        int s = 0;
+        for (int g = 0; g < G(); ++g) s += count(g, a);
+        m = std::max(m, s);
+    }
+    return m;
+}
+
+template <class T>
+static T *upload_vec(Engine *, std::vector<void *> &allocs, const std::vector<T> &v) {
+    T *p = (T *)be::dmalloc(std::max<size_t>(v.size(), 1) * sizeof(T));
+    allocs.push_back(p);
+    if (!v.empty()) be::h2d(p, v.data(), v.size() * sizeof(T));
+    return p;
+}
+
+void Engine::to_device() {
+    if (where_ == DEVICE) return;
+    if (!was_reset_) fatal("environment used before reset");
+    ensure_backend();
+    const int Gn = G();
+    // capacities: grow-only while the geometry is unchanged
+    std::vector<int> need(Gn, 0);
+    for (int g = 0; g < Gn; ++g) {
+        for (int a = 0; a < A_; ++a) need[g] = std::max(need[g], count(g, a));
+        need[g] = std::max(64, (need[g] + 63) / 64 * 64);
+    }
+    bool realloc = dE_ == nullptr || hE_.A != A_ || hE_.W != W_ || hE_.H != H_ || hE_.G != Gn;
+    if (!realloc) for (int g = 0; g < Gn; ++g) if (need[g] > cap_[g]) realloc = true;
+    if (realloc) {
+        free_device();
+        memset(&hE_, 0, sizeof hE_);
+        cap_ = need;
+        hE_.A = A_; hE_.W = W_; hE_.H = H_; hE_.G = Gn;
+        int foff = 0, max_body = 1, max_cells = 1;
+        for (int g = 0; g < Gn; ++g) {
+            const AgentTypeDef &t = *group_type_[g];
+            GroupDev &D = hE_.grp[g];
+            D.body_w = t.width; D.body_l = t.length;
+            D.max_hp = t.hp; D.damage = t.damage; D.step_recover = t.step_recover; D.kill_supply = t.kill_supply;
+            D.step_reward = t.step_reward; D.kill_reward = t.kill_reward;
+            D.dead_penalty = t.dead_penalty; D.attack_penalty = t.attack_penalty;
+            D.attack_in_group = t.attack_in_group;
+            D.view_w = t.view.width; D.view_h = t.view.height; D.view_x1 = t.view.x1; D.view_y1 = t.view.y1;
+            D.view_xoff = t.view_x_offset; D.view_yoff = t.view_y_offset;
+            D.att_xoff = t.att_x_offset; D.att_yoff = t.att_y_offset;
+            D.n_move = t.move.count; D.attack_base = t.attack_base; D.n_action = t.n_action; D.n_attack = t.attack.count;
+            D.channel = group2channel(g);
+            D.feature_size = feature_size(g);
+            D.move_dx = upload_vec(this, dev_allocs_, t.move.dx); D.move_dy = upload_vec(this, dev_allocs_, t.move.dy);
+            D.att_dx = upload_vec(this, dev_allocs_, t.attack.dx); D.att_dy = upload_vec(this, dev_allocs_, t.attack.dy);
+            D.view_mask = upload_vec(this, dev_allocs_, t.view.mask);
+            D.cap = cap_[g];
+            D.foff = foff; foff += cap_[g];
+            max_body = std::max(max_body, t.width * t.length);
+            max_cells = std::max(max_cells, t.view.width * t.view.height);
+            size_t n = (size_t)A_ * cap_[g];
+            for (int b = 0; b < 2; ++b) {
+                AgentSoA &s = D.soa[b];
+                s.x = (int *)dalloc(n * 4); s.y = (int *)dalloc(n * 4); s.hp = (float *)dalloc(n * 4);
+                s.act = (int *)dalloc(n * 4); s.id = (int *)dalloc(n * 4);
+                s.next_reward = (float *)dalloc(n * 4); s.last_reward = (float *)dalloc(n * 4);
+                s.op_obj = (int *)dalloc(n * 4);
+                s.last_op = (unsigned char *)dalloc(n); s.flags = (unsigned char *)dalloc(n); s.dir = (unsigned char *)dalloc(n);
+            }
+        }
+        hE_.cap_total = foff; hE_.max_body = max_body;
+        size_t cells = (size_t)A_ * W_ * H_, sc = (size_t)A_ * foff;
+        hE_.hdr = (ArenaHdr *)dalloc(sizeof(ArenaHdr) * A_);
+        hE_.n = (int *)dalloc((size_t)Gn * A_ * 4); hE_.dead_ct = (int *)dalloc((size_t)Gn * A_ * 4);
+        hE_.off = (int *)dalloc((size_t)Gn * (A_ + 1) * 4);
+        hE_.done = (int *)dalloc((size_t)A_ * 4);
+        hE_.occ = (int *)dalloc(cells * 4); hE_.claim_head = (int *)dalloc(cells * 4);
+        hE_.att_rank = (int *)dalloc(sc * 4); hE_.tgt = (int *)dalloc(sc * 4);
+        hE_.in_head = (int *)dalloc(sc * 4); hE_.in_next = (int *)dalloc(sc * 4);
+        hE_.death = (int *)dalloc(sc * 4); hE_.mv_nx = (int *)dalloc(sc * 4); hE_.mv_ny = (int *)dalloc(sc * 4);
+        hE_.mv_key = (unsigned *)dalloc(sc * 4); hE_.hp_fin = (float *)dalloc(sc * 4);
+        hE_.mv_state = (unsigned char *)dalloc(sc);
+        hE_.jv = (int *)dalloc(sc * 4); hE_.sh_head = (int *)dalloc(sc * 4); hE_.sh_next = (int *)dalloc(sc * 4);
+        hE_.sh_first = (int *)dalloc(sc * 4); hE_.att_agent = (int *)dalloc(sc * 4);
+        hE_.cl_next = (int *)dalloc(sc * max_body * 4);
+        hE_.counters = (long long *)dalloc(sizeof(long long) * MG_N_COUNTERS);
+        be::dmemset(hE_.counters, 0, sizeof(long long) * MG_N_COUNTERS);
+        hE_.team_scratch = (int *)dalloc(sizeof(int) * 2 * 4096);
+        hE_.mm_count = (int *)dalloc((size_t)A_ * Gn * max_cells * 4);
+        d_mm_val_ = (float *)dalloc((size_t)A_ * Gn * max_cells * 4);
+        dE_ = (EngineDev *)dalloc(sizeof(EngineDev));
+    }
+    // constants that may change between episodes without a re-allocation
+    hE_.nsep = nsep_; hE_.large_map = large_map_; hE_.bandwidth = (W_ + nsep_ - 1) / nsep_;
+    hE_.minimap_mode = minimap_mode_; hE_.embedding_size = embedding_size_;
+    hE_.n_channel = n_channel(); hE_.channel_base = group2channel(0);
+    {
+        uint32_t p = MINSTD_A;
+        for (int b = 0; b < 32; ++b) { hE_.pow2[b] = p; p = mulmod31(p, p); }
+    }
+    hE_.n_rules = (int)compiled_rules_.size();
+    for (int r = 0; r < hE_.n_rules; ++r) hE_.rules[r] = compiled_rules_[r];
+    for (int g = 0; g < Gn; ++g) hE_.grp[g].feature_size = feature_size(g);
+    curmask_ = 0;
+
+    // ---- pack and upload the state
+    std::vector<int> ibuf; std::vector<float> fbuf; std::vector<unsigned char> bbuf;
+    for (int g = 0; g < Gn; ++g) {
+        const size_t cap = cap_[g], n = (size_t)A_ * cap;
+        const AgentSoA &s = hE_.grp[g].soa[0];
+        auto up_i = [&](int *dst, std::vector<int> HostGroup::*m) {
+            ibuf.assign(n, 0);
+            for (int a = 0; a < A_; ++a) { const auto &v = arenas_[a].groups[g].*m; std::copy(v.begin(), v.end(), ibuf.begin() + a * cap); }
+            be::h2d(dst, ibuf.data(), n * 4);
+        };
+        auto up_f = [&](float *dst, std::vector<float> HostGroup::*m) {
+            fbuf.assign(n, 0);
+            for (int a = 0; a < A_; ++a) { const auto &v = arenas_[a].groups[g].*m; std::copy(v.begin(), v.end(), fbuf.begin() + a * cap); }
+            be::h2d(dst, fbuf.data(), n * 4);
+        };
+        auto up_b = [&](unsigned char *dst, std::vector<unsigned char> HostGroup::*m) {
+            bbuf.assign(n, 0);
+            for (int a = 0; a < A_; ++a) { const auto &v = arenas_[a].groups[g].*m; std::copy(v.begin(), v.end(), bbuf.begin() + a * cap); }
+            be::h2d(dst, bbuf.data(), n);
+        };
+        up_i(s.x, &HostGroup::x); up_i(s.y, &HostGroup::y); up_i(s.act, &HostGroup::act);
+        up_i(s.id, &HostGroup::id); up_i(s.op_obj, &HostGroup::op_obj);
+        up_f(s.hp, &HostGroup::hp); up_f(s.next_reward, &HostGroup::next_reward); up_f(s.last_reward, &HostGroup::last_reward);
+        up_b(s.last_op, &HostGroup::last_op); up_b(s.flags, &HostGroup::flags); up_b(s.dir, &HostGroup::dir);
+    }
+    for (int a = 0; a < A_; ++a)
+        be::h2d(hE_.occ + (size_t)a * W_ * H_, arenas_[a].occ.data(), (size_t)W_ * H_ * 4);
+    be::dmemset(hE_.claim_head, 0xff, (size_t)A_ * W_ * H_ * 4);
+    {
+        std::vector<ArenaHdr> hdr(A_);
+        std::vector<int> n((size_t)Gn * A_), dc((size_t)Gn * A_), done(A_);
+        for (int a = 0; a < A_; ++a) {
+            memset(&hdr[a], 0, sizeof(ArenaHdr));
+            hdr[a].rng = hdr[a].rng_next = arenas_[a].rng;
+            hdr[a].done = done[a] = arenas_[a].done;
+            for (int g = 0; g < Gn; ++g) {
+                hdr[a].grp_reward[g] = arenas_[a].groups[g].grp_reward;
+                n[(size_t)g * A_ + a] = arenas_[a].groups[g].size();
+                dc[(size_t)g * A_ + a] = arenas_[a].groups[g].dead_ct;
+            }
+        }
+        be::h2d(hE_.hdr, hdr.data(), sizeof(ArenaHdr) * A_);
+        be::h2d(hE_.n, n.data(), n.size() * 4);
+        be::h2d(hE_.dead_ct, dc.data(), dc.size() * 4);
+        be::h2d(hE_.done, done.data(), done.size() * 4);
+        be::h2d(hE_.off, h_off_.data(), h_off_.size() * 4);
+    }
+    be::h2d(dE_, &hE_, sizeof(EngineDev));
+    where_ = DEVICE;
+}
+
+void Engine::to_host(bool keep_device_authoritative) {
+    if (where_ == HOST) return;
+    const int Gn = G();
+    std::vector<int> ibuf; std::vector<float> fbuf; std::vector<unsigned char> bbuf;
+    std::vector<int> dc((size_t)Gn * A_);
+    be::d2h(dc.data(), hE_.dead_ct, dc.size() * 4);
+    std::vector<ArenaHdr> hdr(A_);
+    be::d2h(hdr.data(), hE_.hdr, sizeof(ArenaHdr) * A_);
+    for (int g = 0; g < Gn; ++g) {
+        const size_t cap = cap_[g], n = (size_t)A_ * cap;
+        const AgentSoA &s = hE_.grp[g].soa[(curmask_ >> g) & 1u];
+        for (int a = 0; a < A_; ++a) arenas_[a].groups[g].resize(count(g, a));
+        auto dn_i = [&](const int *src, std::vector<int> HostGroup::*m) {
+            ibuf.resize(n); be::d2h(ibuf.data(), src, n * 4);
+            for (int a = 0; a < A_; ++a) { auto &v = arenas_[a].groups[g].*m; std::copy(ibuf.begin() + a * cap, ibuf.begin() + a * cap + v.size(), v.begin()); }
+        };
+        auto dn_f = [&](const float *src, std::vector<float> HostGroup::*m) {
+            fbuf.resize(n); be::d2h(fbuf.data(), src, n * 4);
+            for (int a = 0; a < A_; ++a) { auto &v = arenas_[a].groups[g].*m; std::copy(fbuf.begin() + a * cap, fbuf.begin() + a * cap + v.size(), v.begin()); }
+        };
+        auto dn_b = [&](const unsigned char *src, std::vector<unsigned char> HostGroup::*m) {
+            bbuf.resize(n); be::d2h(bbuf.data(), src, n);
+            for (int a = 0; a < A_; ++a) { auto &v = arenas_[a].groups[g].*m; std::copy(bbuf.begin() + a * cap, bbuf.begin() + a * cap + v.size(), v.begin()); }
+        };
+        dn_i(s.x, &HostGroup::x); dn_i(s.y, &HostGroup::y); dn_i(s.act, &HostGroup::act);
+        dn_i(s.id, &HostGroup::id); dn_i(s.op_obj, &HostGroup::op_obj);
+        dn_f(s.hp, &HostGroup::hp); dn_f(s.next_reward, &HostGroup::next_reward); dn_f(s.last_reward, &HostGroup::last_reward);
+        dn_b(s.last_op, &HostGroup::last_op); dn_b(s.flags, &HostGroup::flags); dn_b(s.dir, &HostGroup::dir);
+        for (int a = 0; a < A_; ++a) {
+            arenas_[a].groups[g].dead_ct = dc[(size_t)g * A_ + a];
+            arenas_[a].groups[g].grp_reward = hdr[a].grp_reward[g];
+        }
+    }
+    for (int a = 0; a < A_; ++a) {
+        arenas_[a].occ.resize((size_t)W_ * H_);
+        be::d2h(arenas_[a].occ.data(), hE_.occ + (size_t)a * W_ * H_, (size_t)W_ * H_ * 4);
+        arenas_[a].rng = hdr[a].rng;
+        arenas_[a].done = hdr[a].done;
+    }
+    if (!keep_device_authoritative) where_ = HOST;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the step loop
+void Engine::get_observation(int group, float **bufs) {               // GridWorld.cc:292-401
+    check_group(group, "GridWorld::get_observation");
+    to_device();
+    const int n = total(group);
+    if (n == 0) return;
+    const AgentTypeDef &t = *group_type_[group];
+    const size_t vbytes = (size_t)n * t.view.height * t.view.width * n_channel() * 4;
+    const size_t fbytes = (size_t)n * feature_size(group) * 4;
+    const bool vdev = be::is_device_ptr(bufs[0]), fdev = be::is_device_ptr(bufs[1]);
+    ObsArgs O;
+    O.curmask = curmask_; O.group = group;
+    if (vdev) O.view = bufs[0];
+    else {
+        if (vbytes > view_stage_bytes_) {
+            if (d_view_stage_) be::dfree(d_view_stage_);
+            view_stage_bytes_ = vbytes + vbytes / 8 + 256;
+            d_view_stage_ = (float *)be::dmalloc(view_stage_bytes_);
+        }
+        O.view = d_view_stage_;
+    }
+    if (fdev) O.feature = bufs[1];
+    else {
+        if (fbytes > feat_stage_bytes_) {
+            if (d_feat_stage_) be::dfree(d_feat_stage_);
+            feat_stage_bytes_ = fbytes + fbytes / 8 + 256;
+            d_feat_stage_ = (float *)be::dmalloc(feat_stage_bytes_);
+        }
+        O.feature = d_feat_stage_;
+    }
+    if (minimap_mode_) be::launch_minimap(dE_, hE_, curmask_, group, d_mm_val_);
+    be::launch_obs(dE_, hE_, O, minimap_mode_ ? d_mm_val_ : nullptr, n);
+    if (!vdev) be::d2h(bufs[0], d_view_stage_, vbytes);
+    if (!fdev) be::d2h(bufs[1], d_feat_stage_, fbytes);
+}
+
+void Engine::set_action(int group, const int *actions) {              // GridWorld.cc:403-454
+    check_group(group, "GridWorld::set_action");
+    to_device();
+    const int n = total(group);
+    if (std::find(order_.begin(), order_.end(), group) == order_.end()) order_.push_back(group);
+    if (n == 0) return;
+    const void *src = actions;
+    if (!be::is_device_ptr(actions)) {
+        void *st = io_stage((size_t)n * 4);
+        be::h2d(st, actions, (size_t)n * 4);
+        src = st;
+    }
+    be::launch_info(dE_, hE_, curmask_, INFO_ACTION_SCATTER, group, const_cast<void *>(src), n);
+}
+
+void Engine::random_actions(int group, unsigned long long seed) {
+    check_group(group, "random_actions");
+    to_device();
+    if (std::find(order_.begin(), order_.end(), group) == order_.end()) order_.push_back(group);
+    const int n = total(group);
+    if (n == 0) return;
+    be::launch_random_actions(dE_, hE_, curmask_, group, seed * 0x9E3779B97F4A7C15ull + (++rand_calls_), n);
+}
+
+void Engine::step(int *done) {                                        // GridWorld.cc:456-631
+    to_device();
+    StepArgs S;
+    memset(&S, 0, sizeof S);
+    S.curmask = curmask_;
+    S.n_order = (int)order_.size();
+    for (int k = 0; k < S.n_order; ++k) S.order[k] = order_[k];
+    be::launch_step(dE_, hE_, S, max_agents_per_arena());
+    order_.clear();
+    std::vector<int> d(A_);
+    be::d2h(d.data(), hE_.done, (size_t)A_ * 4);
+    int all = 1;
+    for (int a = 0; a < A_; ++a) { arenas_[a].done = d[a]; all &= d[a] != 0; }
+    *done = all;
+}
+
+void Engine::get_reward(int group, float *buf) {                      // GridWorld.cc:694-704
+    check_group(group, "GridWorld::get_reward");
+    to_device();
+    const int n = total(group);
+    if (n == 0) return;
+    if (be::is_device_ptr(buf)) { be::launch_info(dE_, hE_, curmask_, INFO_REWARD, group, buf, n); return; }
+    void *st = io_stage((size_t)n * 4);
+    be::launch_info(dE_, hE_, curmask_, INFO_REWARD, group, st, n);
+    be::d2h(buf, st, (size_t)n * 4);
+}
+
+void Engine::clear_dead() {                                           // GridWorld.cc:633-665
+    to_device();
+    be::launch_cull(dE_, hE_, curmask_, max_agents_per_arena());
+    curmask_ ^= (1u << G()) - 1u;
+    be::launch_offsets(dE_, hE_);
+    be::d2h(h_off_.data(), hE_.off, h_off_.size() * 4);
+}
+
+void Engine::set_goal(int, const char *, const int *) {
+    fatal("goal_mode is deprecated in the reference and not supported by the B200 engine");
+}
+
+void Engine::render() { /* replay dump (RenderGenerator) is out of scope: SURVEY.md §8f rank 3 */ }
+
+void Engine::sync() { if (device_ready_) be::sync(); }
+
+int Engine::get_counters(long long *out, int cap) {
+    int n = std::min<int>(cap, MG_N_COUNTERS);
+    if (where_ != DEVICE && dE_ == nullptr) { for (int i = 0; i < n; ++i) out[i] = 0; return n; }
+    std::vector<long long> c(MG_N_COUNTERS);
+    be::d2h(c.data(), hE_.counters, sizeof(long long) * MG_N_COUNTERS);
+    for (int i = 0; i < n; ++i) out[i] = c[i];
+    return n;
+}
+
+void Engine::get_info(int group, const char *name, void *void_buffer) {        // GridWorld.cc:709-894
+    int *ib = (int *)void_buffer;
+    float *fb = (float *)void_buffer;
+    if (strequ(name, "num")) {
+        check_group(group, "get_info(num)");
+        ib[0] = total(group);
+    } else if (strequ(name, "id") || strequ(name, "pos") || strequ(name, "alive") || strequ(name, "hp")) {
+        check_group(group, "get_info");
+        to_device();
+        const int n = total(group);
+        if (n == 0) return;
+        int kind = strequ(name, "id") ? INFO_ID : strequ(name, "pos") ? INFO_POS : strequ(name, "alive") ? INFO_ALIVE : INFO_HP;
+        size_t bytes = kind == INFO_POS ? (size_t)n * 8 : kind == INFO_ALIVE ? (size_t)n : (size_t)n * 4;
+        if (be::is_device_ptr(void_buffer)) { be::launch_info(dE_, hE_, curmask_, kind, group, void_buffer, n); return; }
+        void *st = io_stage(bytes);
+        be::launch_info(dE_, hE_, curmask_, kind, group, st, n);
+        be::d2h(void_buffer, st, bytes);
+    } else if (strequ(name, "arena_num")) {
+        check_group(group, "get_info(arena_num)");
+        for (int a = 0; a < A_; ++a) ib[a] = count(group, a);
+    } else if (strequ(name, "arena_done")) {
+        for (int a = 0; a < A_; ++a) ib[a] = arenas_[a].done;
+    } else if (strequ(name, "action_space")) {
+        check_group(group, "get_info"); ib[0] = group_type_[group]->n_action;
+    } else if (strequ(name, "view_space")) {
+        check_group(group, "get_info");
+        ib[0] = group_type_[group]->view.height; ib[1] = group_type_[group]->view.width; ib[2] = n_channel();
+    } else if (strequ(name, "feature_space")) {
+        check_group(group, "get_info"); ib[0] = feature_size(group);
+    } else if (strequ(name, "view2attack")) {
+        check_group(group, "get_info");
+        const AgentTypeDef &t = *group_type_[group];
+        for (int i = 0; i < t.view.height * t.view.width; ++i) ib[i] = -1;
+        for (int i = 0; i < t.attack.count; ++i)
+            ib[(t.attack.dy[i] - t.view.y1) * t.view.width + (t.attack.dx[i] - t.view.x1)] = i;
+    } else if (strequ(name, "attack_base")) {
+        check_group(group, "get_info"); ib[0] = group_type_[group]->attack_base;
+    } else if (strequ(name, "both_attack")) {
+        ib[0] = 0;                                    // `const bool stat = false` in the reference
+    } else if (strequ(name, "groups_info")) {
+        static const int colors[][3] = {{192, 64, 64}, {64, 64, 192}, {64, 192, 64}, {64, 64, 64}};
+        for (int i = 0; i < G(); i++) {
+            ib[i * 5 + 0] = group_type_[i]->width; ib[i * 5 + 1] = group_type_[i]->length;
+            for (int c = 0; c < 3; ++c) ib[i * 5 + 2 + c] = colors[i % 4][c];
+        }
+    } else if (strequ(name, "walls_info") || strequ(name, "global_minimap") || strequ(name, "mean_info") ||
+               strequ(name, "render_window_info") || strequ(name, "attack_event")) {
+        // cold getters: served from a host snapshot of arena 0 (or the selected arena)
+        to_host(true);
+        const HostArena &ar = arenas_[sel_arena_ >= 0 ? sel_arena_ : 0];
+        if (strequ(name, "walls_info")) {
+            int ct = 0;
+            for (int i = 0; i < W_ * H_; i++)
+                if (ar.occ[i] == OCC_WALL) { ++ct; ib[ct * 2] = i % W_; ib[ct * 2 + 1] = i / W_; }
+            ib[0] = ct;
+        } else if (strequ(name, "global_minimap")) {
+            int vh = (int)lround(fb[0]), vw = (int)lround(fb[1]);
+            int ng = G();
+            for (int i = 0; i < vh * vw * ng; ++i) fb[i] = 0.0f;
+            int scale_h = (H_ + vh - 1) / vh, scale_w = (W_ + vw - 1) / vw;
+            for (int i = 0; i < ng; i++) {
+                int ch = ((i - group) % ng + ng) % ng;
+                const HostGroup &hg = ar.groups[i];
+                for (int j = 0; j < hg.size(); j++) fb[((hg.y[j] / scale_h) * vw + hg.x[j] / scale_w) * ng + ch] += 1.0f;
+                for (int j = 0; j < vh * vw; j++) fb[j * ng + ch] /= (float)hg.size();
+            }
+        } else if (strequ(name, "mean_info")) {
+            check_group(group, "get_info(mean_info)");
+            const HostGroup &hg = ar.groups[group];
+            int na = group_type_[group]->n_action;
+            float sx = 0, sy = 0;
+            std::vector<int> ctr(na + 1, 0);
+            for (int i = 0; i < hg.size(); i++) { sx += hg.x[i]; sy += hg.y[i]; if (hg.act[i] >= 0 && hg.act[i] <= na) ctr[hg.act[i]]++; }
+            fb[0] = sx / hg.size(); fb[1] = sy / hg.size();
+            for (int i = 0; i < na; i++) fb[2 + i] = (float)(1.0 * ctr[i] / hg.size());
+        } else if (strequ(name, "render_window_info")) {
+            int x1 = ib[0], y1 = ib[1], x2 = ib[2], y2 = ib[3], ct = 1;
+            for (int g = 0; g < G(); g++) {
+                const HostGroup &hg = ar.groups[g];
+                for (int j = 0; j < hg.size(); j++) {
+                    if (hg.x[j] < x1 || hg.x[j] > x2 || hg.y[j] < y1 || hg.y[j] > y2) continue;
+                    ib[ct * 4] = hg.id[j]; ib[ct * 4 + 1] = hg.x[j]; ib[ct * 4 + 2] = hg.y[j]; ib[ct * 4 + 3] = g; ct++;
+                }
+            }
+            ib[0] = ct - 1; ib[1] = 0;                 // attack events are not recorded (render is out of scope)
+        }
+    } else {
+        fatal("unsupported info name in GridWorld::get_info : %s", name);
+    }
+}
+
+}  // namespace mg

@@ -1,0 +1,652 @@
+// step_phases.h -- the GridWorld step pipeline as data-parallel phases over one arena.
+//
+// Every function below is executed by a *team* of threads (Ctx: tid()/nth()/scan()/sync are provided
+// by the caller: a CTA, a cooperative grid, or the single-threaded test emulation).  Phases are
+// separated by team barriers in run_step()/run_cull(); inside a phase each thread only writes state it
+// owns (its agent, its agent's cells) or uses atomics.
+//
+// The reference executes attack and move *sequentially* (attack order = a Fisher-Yates shuffle of the
+// attack buffer, GridWorld.cc:464-506; move order = band buffers then boundary buffer in insertion
+// order, GridWorld.cc:573-613).  The phases reproduce the OUTCOME of that sequential order:
+//   * shuffle replay: closed-form position of every element after the swap loop,
+//   * attack: per-victim timelines in rank order, relaxed to the unique fixpoint of the
+//     "attacker still alive at its rank" dependency (triangular in rank => unique, reached by sweeps),
+//   * move: per-cell claimant lists + relaxation of "claimant succeeds iff every target cell is free at
+//     its turn" (triangular in order key).
+#pragma once
+#include "dev_types.h"
+
+namespace mg {
+
+struct GroupEnum {
+    int cnt, k_n;
+    int grp[MG_MAX_GROUPS];
+    int pre[MG_MAX_GROUPS + 1];
+};
+
+MG_HD void enum_all(const EngineDev &E, int a, GroupEnum &e) {
+    e.k_n = E.G; e.pre[0] = 0;
+    for (int g = 0; g < E.G; ++g) { e.grp[g] = g; e.pre[g + 1] = e.pre[g] + E.n[g * E.A + a]; }
+    e.cnt = e.pre[E.G];
+}
+MG_HD void enum_order(const EngineDev &E, const StepArgs &S, int a, GroupEnum &e) {
+    e.k_n = S.n_order; e.pre[0] = 0;
+    for (int k = 0; k < S.n_order; ++k) {
+        e.grp[k] = S.order[k];
+        e.pre[k + 1] = e.pre[k] + E.n[S.order[k] * E.A + a];
+    }
+    e.cnt = e.pre[S.n_order];
+}
+MG_HD void enum_locate(const GroupEnum &e, int idx, int &k, int &i) {
+    k = 0;
+    while (idx >= e.pre[k + 1]) ++k;
+    i = idx - e.pre[k];
+}
+
+MG_HD const AgentSoA &cur_soa(const EngineDev &E, unsigned curmask, int g) {
+    return E.grp[g].soa[(curmask >> g) & 1u];
+}
+
+// view of one arena: bases into the arena-major arrays
+struct ArenaRef {
+    int a;
+    int *occ, *claim;
+    long sb;            // base into per-agent scratch  (a * cap_total)
+    long nb;            // base into claim nodes        (a * cap_total * max_body)
+    ArenaHdr *hdr;
+};
+MG_HD ArenaRef arena_ref(const EngineDev &E, int a) {
+    ArenaRef r;
+    r.a = a;
+    r.occ = E.occ + (long)a * E.W * E.H;
+    r.claim = E.claim_head + (long)a * E.W * E.H;
+    r.sb = (long)a * E.cap_total;
+    r.nb = (long)a * E.cap_total * E.max_body;
+    r.hdr = E.hdr + a;
+    return r;
+}
+MG_HD long gidx(const EngineDev &E, int a, int g, int i) { return (long)a * E.grp[g].cap + i; }
+MG_HD int lflat(const EngineDev &E, int code) { return E.grp[code_group(code)].foff + code_index(code); }
+
+// ------------------------------------------------------------------------------------------------
+// phase 0: reset per-step scratch
+template <class Ctx>
+MG_HD void phase_init(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+    ArenaRef R = arena_ref(E, a);
+    GroupEnum all; enum_all(E, a, all);
+    for (int idx = c.tid(); idx < all.cnt; idx += c.nth()) {
+        int g, i; enum_locate(all, idx, g, i);
+        const AgentSoA &s = cur_soa(E, S.curmask, g);
+        long f = R.sb + E.grp[g].foff + i;
+        bool dead = s.flags[gidx(E, a, g, i)] & FLAG_DEAD;
+        E.att_rank[f] = RANK_NONE;
+        E.tgt[f] = -1;
+        E.in_head[f] = -1;
+        E.death[f] = dead ? DEATH_BEFORE : DEATH_NEVER;
+        E.mv_key[f] = MVKEY_NONE;
+        E.mv_state[f] = MV_NONE;
+        E.sh_head[R.sb + idx] = -1;          // shuffle scratch is indexed by buffer position < n_attack <= cnt
+        E.sh_first[R.sb + idx] = DEATH_NEVER;
+    }
+    if (c.tid() == 0) {
+        R.hdr->n_attack = 0;
+        R.hdr->rule_trigger = 0;
+        R.hdr->rng_next = R.hdr->rng;
+        R.hdr->changed[0] = R.hdr->changed[1] = R.hdr->changed[2] = 0;
+        GroupEnum ord; enum_order(E, S, a, ord);
+        atomic_add64(&E.counters[CNT_AGENT_STEPS], ord.cnt);
+        if (a == 0) atomic_add64(&E.counters[CNT_STEPS], 1);
+    }
+}
+
+// phase 1: position of every attack action in the attack buffer (reference GridWorld.cc:403-454 pushes
+// in set_action call order, then agent index order; dead-but-unculled agents are pushed too)
+template <class Ctx>
+MG_HD int phase_attack_scan(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+    ArenaRef R = arena_ref(E, a);
+    GroupEnum ord; enum_order(E, S, a, ord);
+    auto pred = [&](int idx) -> int {
+        int k, i; enum_locate(ord, idx, k, i);
+        int g = ord.grp[k];
+        int act = cur_soa(E, S.curmask, g).act[gidx(E, a, g, i)];
+        return (act >= E.grp[g].attack_base && act < E.grp[g].n_action) ? 1 : 0;
+    };
+    auto emit = [&](int idx, int e) {
+        int k, i; enum_locate(ord, idx, k, i);
+        E.att_agent[R.sb + e] = code_make(ord.grp[k], i);
+    };
+    int total = c.scan(ord.cnt, pred, emit);
+    if (c.tid() == 0) {
+        R.hdr->n_attack = total;
+        atomic_add64(&E.counters[CNT_ATTACKS], total);
+    }
+    return total;
+}
+
+// phase 2: the A random draws of the shuffle, j_e = x_e mod (e+1)  (GridWorld.cc:465-468), by jump-ahead
+template <class Ctx>
+MG_HD void phase_rng(Ctx &c, const EngineDev &E, int a, int n_attack) {
+    ArenaRef R = arena_ref(E, a);
+    uint32_t x0 = R.hdr->rng;
+    for (int e = c.tid(); e < n_attack; e += c.nth()) {
+        uint32_t x = mulmod31(minstd_pow(E.pow2, (uint32_t)e + 1u), x0);
+        int j = (int)(x % (uint32_t)(e + 1));
+        E.jv[R.sb + e] = j;
+        E.sh_next[R.sb + e] = atomic_exch(&E.sh_head[R.sb + j], e);
+        if (e > j) atomic_min(&E.sh_first[R.sb + j], e);
+        if (e == n_attack - 1) R.hdr->rng_next = x;
+    }
+}
+
+// phase 3: final buffer position (= execution rank) of each attack, and its target
+template <class Ctx>
+MG_HD void phase_rank_target(Ctx &c, const EngineDev &E, const StepArgs &S, int a, int n_attack) {
+    ArenaRef R = arena_ref(E, a);
+    for (int e = c.tid(); e < n_attack; e += c.nth()) {
+        // element e is swapped to position v=j_e at step e; afterwards it moves whenever a later step
+        // picks its current position: first to ne = next step with the same j, then along sh_first.
+        int v = E.jv[R.sb + e];
+        int ne = DEATH_NEVER;
+        for (int q = E.sh_head[R.sb + v]; q != -1; q = E.sh_next[R.sb + q])
+            if (q > e && q < ne) ne = q;
+        int pos = v;
+        if (ne != DEATH_NEVER) {
+            pos = ne;
+            for (int nx = E.sh_first[R.sb + pos]; nx != DEATH_NEVER; nx = E.sh_first[R.sb + pos]) pos = nx;
+        }
+        int code = E.att_agent[R.sb + e];
+        int g = code_group(code), i = code_index(code);
+        const GroupDev &G = E.grp[g];
+        const AgentSoA &s = cur_soa(E, S.curmask, g);
+        long gi = gidx(E, a, g, i);
+        int fs = G.foff + i;
+        E.att_rank[R.sb + fs] = pos;
+        if (s.flags[gi] & FLAG_DEAD) continue;          // skipped at execution (GridWorld.cc:479)
+        // Map::get_attack_obj (Map.cc:209-252), dir == NORTH
+        int k = s.act[gi] - G.attack_base;
+        int tx = s.x[gi] + G.att_xoff + G.att_dx[k];
+        int ty = s.y[gi] + G.att_yoff + G.att_dy[k];
+        if (tx < 0 || tx >= E.W || ty < 0 || ty >= E.H) continue;
+        int t = R.occ[ty * E.W + tx];
+        if (t < 0) continue;
+        if (!G.attack_in_group && code_group(t) == g) continue;
+        E.tgt[R.sb + fs] = t;
+        E.in_next[R.sb + fs] = atomic_exch(&E.in_head[R.sb + lflat(E, t)], fs);
+    }
+}
+
+// phase 4 (swept until stable): death rank of every agent that is hit or that attacks.
+// Sequential semantics being reproduced: GridWorld.cc:475-506 + Map::do_attack (Map.cc:255-310) +
+// Agent::be_attack/add_hp (GridWorld.h:185,203-209).
+template <class Ctx>
+MG_HD bool phase_attack_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+    ArenaRef R = arena_ref(E, a);
+    GroupEnum all; enum_all(E, a, all);
+    bool changed = false;
+    for (int idx = c.tid(); idx < all.cnt; idx += c.nth()) {
+        int g, i; enum_locate(all, idx, g, i);
+        int ft = E.grp[g].foff + i;
+        long f = R.sb + ft;
+        int head = E.in_head[f];
+        int my_tgt = E.tgt[f];
+        if (head == -1 && my_tgt < 0) continue;
+        const GroupDev &G = E.grp[g];
+        float hp = cur_soa(E, S.curmask, g).hp[gidx(E, a, g, i)];
+        int own_r = my_tgt >= 0 ? E.att_rank[f] : DEATH_NEVER;
+        bool own_done = my_tgt < 0;
+        int last = -1, dn = DEATH_NEVER;
+        for (;;) {
+            int best = DEATH_NEVER, bs = -1;
+            for (int s = head; s != -1; s = E.in_next[R.sb + s]) {
+                int r = E.att_rank[R.sb + s];
+                if (r > last && r < best) { best = r; bs = s; }
+            }
+            if (!own_done && own_r < best) {            // my own attack comes first: kill => supply
+                own_done = true;
+                if (ld_volatile(&E.death[R.sb + lflat(E, my_tgt)]) == own_r) {
+                    float sup = E.grp[code_group(my_tgt)].kill_supply;
+                    float nh = hp + sup;                 // Agent::add_hp: min(type.hp, hp + add)
+                    hp = G.max_hp < nh ? G.max_hp : nh;
+                }
+                continue;
+            }
+            if (bs == -1) break;
+            last = best;
+            if (ld_volatile(&E.death[R.sb + bs]) < best) continue;      // attacker dead by then
+            // attacker's group -> damage
+            int sg = 0;
+            while (sg + 1 < E.G && bs >= E.grp[sg + 1].foff) ++sg;
+            hp -= E.grp[sg].damage;
+            if (hp < 0.0f) { dn = best; break; }
+        }
+        E.hp_fin[f] = hp;
+        if (dn != E.death[f]) { st_volatile(&E.death[f], dn); changed = true; }
+    }
+    return changed;
+}
+
+// phase 5: commit attacks (attacker side and victim side) and starvation (GridWorld.cc:519-542)
+template <class Ctx>
+MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+    ArenaRef R = arena_ref(E, a);
+    GroupEnum all; enum_all(E, a, all);
+    int kills = 0, hits = 0, starved = 0;
+    for (int idx = c.tid(); idx < all.cnt; idx += c.nth()) {
+        int g, i; enum_locate(all, idx, g, i);
+        const GroupDev &G = E.grp[g];
+        const AgentSoA &s = cur_soa(E, S.curmask, g);
+        long gi = gidx(E, a, g, i);
+        long f = R.sb + G.foff + i;
+        if (s.flags[gi] & FLAG_DEAD) continue;
+        int d = E.death[f];
+        int r = E.att_rank[f];
+        if (r != RANK_NONE && d > r) {                   // my attack is executed
+            int t = E.tgt[f];
+            int dt = t >= 0 ? E.death[R.sb + lflat(E, t)] : DEATH_BEFORE;
+            if (t < 0 || dt < r) {                       // blank / already dead: penalty only
+                s.next_reward[gi] += G.attack_penalty;
+            } else if (dt == r) {                        // my hit kills
+                s.last_op[gi] = OP_KILL;
+                s.op_obj[gi] = t;
+                s.next_reward[gi] += E.grp[code_group(t)].kill_reward + G.attack_penalty;
+                ++kills; ++hits;
+            } else {
+                s.last_op[gi] = OP_ATTACK;
+                s.op_obj[gi] = t;
+                s.next_reward[gi] += 0.0f + G.attack_penalty;
+                ++hits;
+            }
+        }
+        bool evaluated = E.in_head[f] != -1 || E.tgt[f] >= 0;
+        float hp = evaluated ? E.hp_fin[f] : s.hp[gi];
+        bool dies = false;
+        if (d != DEATH_NEVER) {                          // killed in the attack phase
+            dies = true;
+        } else {                                         // Agent::starve (GridWorld.h:194-201)
+            if (G.step_recover > 0) {
+                float nh = hp + G.step_recover;
+                hp = G.max_hp < nh ? G.max_hp : nh;
+            } else {
+                hp -= -G.step_recover;
+                if (hp < 0.0f) { dies = true; ++starved; }
+            }
+        }
+        s.hp[gi] = hp;
+        if (dies) {
+            s.flags[gi] |= FLAG_DEAD;
+            s.next_reward[gi] = G.dead_penalty;          // assignment (GridWorld.h:206)
+            int x = s.x[gi], y = s.y[gi];
+            for (int bx = 0; bx < G.body_w; ++bx)
+                for (int by = 0; by < G.body_l; ++by)
+                    R.occ[(y + by) * E.W + x + bx] = OCC_EMPTY;
+            atomic_add(&E.dead_ct[g * E.A + a], 1);
+        }
+    }
+    if (kills) atomic_add64(&E.counters[CNT_KILLS], kills);
+    if (hits) atomic_add64(&E.counters[CNT_HITS], hits);
+    if (starved) atomic_add64(&E.counters[CNT_STARVED], starved);
+}
+
+// phase 6: movers compute their target footprint and queue on every target cell
+template <class Ctx>
+MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+    ArenaRef R = arena_ref(E, a);
+    GroupEnum ord; enum_order(E, S, a, ord);
+    for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
+        int k, i; enum_locate(ord, idx, k, i);
+        int g = ord.grp[k];
+        const GroupDev &G = E.grp[g];
+        const AgentSoA &s = cur_soa(E, S.curmask, g);
+        long gi = gidx(E, a, g, i);
+        int act = s.act[gi];
+        if (act < 0 || act >= G.n_move) continue;
+        if (s.flags[gi] & (FLAG_DEAD | FLAG_ABSORBED)) continue;     // GridWorld.cc:581
+        int fs = G.foff + i;
+        long f = R.sb + fs;
+        int x = s.x[gi], y = s.y[gi];
+        // insertion order of the reference: band buffers 0..nsep-1, then the boundary buffer
+        unsigned bucket = (unsigned)E.nsep;
+        if (E.large_map) {
+            int xm = x % E.bandwidth;
+            if (!(xm < 4 || xm > E.bandwidth - 4)) bucket = (unsigned)(x / E.bandwidth);
+        }
+        E.mv_key[f] = (bucket << 27) | ((unsigned)k << 23) | (unsigned)i;
+        int nx = x + G.move_dx[act], ny = y + G.move_dy[act];
+        E.mv_nx[f] = nx; E.mv_ny[f] = ny;
+        int bw = G.body_w, bh = G.body_l;
+        if (nx < 0 || ny < 0 || nx + bw >= E.W || ny + bh >= E.H) {          // Map.cc:455
+            E.mv_state[f] = MV_OOB;
+            continue;
+        }
+        bool wall = false;
+        for (int bx = 0; bx < bw; ++bx)
+            for (int by = 0; by < bh; ++by)
+                if (R.occ[(ny + by) * E.W + nx + bx] == OCC_WALL) wall = true;
+        if (wall) { E.mv_state[f] = MV_STATIC_FAIL; continue; }
+        E.mv_state[f] = MV_PENDING_FAIL;
+        int ci = 0;
+        for (int bx = 0; bx < bw; ++bx)
+            for (int by = 0; by < bh; ++by, ++ci) {
+                int node = fs * E.max_body + ci;
+                E.cl_next[R.nb + node] = atomic_exch(&R.claim[(ny + by) * E.W + nx + bx], node);
+            }
+    }
+}
+
+// who stands on cell (cx,cy) when the mover with order key `key` takes its turn?  -1 = nobody.
+// `self` (local flat id) is ignored.  Reads mover states with volatile loads.
+MG_HD int occupant_at_turn(const EngineDev &E, const ArenaRef &R, int cx, int cy, unsigned key, int self) {
+    int cell = cy * E.W + cx;
+    int o = R.occ[cell];
+    if (o >= 0) {
+        int fo = lflat(E, o);
+        if (fo != self) {
+            bool left = ld_volatile(&E.mv_state[R.sb + fo]) == MV_OK && E.mv_key[R.sb + fo] < key;
+            if (left) {
+                const GroupDev &GO = E.grp[code_group(o)];
+                int ox = E.mv_nx[R.sb + fo], oy = E.mv_ny[R.sb + fo];
+                if (cx >= ox && cx < ox + GO.body_w && cy >= oy && cy < oy + GO.body_l) left = false;
+            }
+            if (!left) return fo;
+        }
+    }
+    for (int node = R.claim[cell]; node != -1; node = E.cl_next[R.nb + node]) {
+        int fm = node / E.max_body;
+        if (fm != self && E.mv_key[R.sb + fm] < key && ld_volatile(&E.mv_state[R.sb + fm]) == MV_OK)
+            return fm;
+    }
+    return -1;
+}
+
+// phase 7 (swept until stable): a mover succeeds iff all its target cells are free at its turn
+// (Map::do_move / is_blank_area, Map.cc:313-358,454-470)
+template <class Ctx>
+MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+    ArenaRef R = arena_ref(E, a);
+    GroupEnum ord; enum_order(E, S, a, ord);
+    bool changed = false;
+    for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
+        int k, i; enum_locate(ord, idx, k, i);
+        int g = ord.grp[k];
+        const GroupDev &G = E.grp[g];
+        int fs = G.foff + i;
+        long f = R.sb + fs;
+        unsigned char st = E.mv_state[f];
+        if (st != MV_PENDING_FAIL && st != MV_OK) continue;
+        unsigned key = E.mv_key[f];
+        int nx = E.mv_nx[f], ny = E.mv_ny[f];
+        bool ok = true;
+        for (int bx = 0; bx < G.body_w && ok; ++bx)
+            for (int by = 0; by < G.body_l && ok; ++by)
+                if (occupant_at_turn(E, R, nx + bx, ny + by, key, fs) != -1) ok = false;
+        unsigned char ns = ok ? MV_OK : MV_PENDING_FAIL;
+        if (ns != st) { st_volatile(&E.mv_state[f], ns); changed = true; }
+    }
+    return changed;
+}
+
+// phase 8: losers record what they bumped into (Map::get_collide, Map.cc:486-501; GridWorld sets
+// OP_COLLIDE, Map.cc:350-353)
+template <class Ctx>
+MG_HD void phase_move_collide(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+    ArenaRef R = arena_ref(E, a);
+    GroupEnum ord; enum_order(E, S, a, ord);
+    int ok_ct = 0, blocked = 0;
+    for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
+        int k, i; enum_locate(ord, idx, k, i);
+        int g = ord.grp[k];
+        const GroupDev &G = E.grp[g];
+        int fs = G.foff + i;
+        long f = R.sb + fs;
+        unsigned char st = E.mv_state[f];
+        if (st == MV_OK) { ++ok_ct; continue; }
+        if (st == MV_NONE) continue;
+        ++blocked;
+        if (st == MV_OOB) continue;
+        unsigned key = E.mv_key[f];
+        int nx = E.mv_nx[f], ny = E.mv_ny[f];
+        int hit = -1;
+        for (int bx = 0; bx < G.body_w && hit == -1; ++bx)
+            for (int by = 0; by < G.body_l && hit == -1; ++by)
+                hit = occupant_at_turn(E, R, nx + bx, ny + by, key, fs);
+        if (hit != -1) {
+            int hg = 0;
+            while (hg + 1 < E.G && hit >= E.grp[hg + 1].foff) ++hg;
+            const AgentSoA &s = cur_soa(E, S.curmask, g);
+            long gi = gidx(E, a, g, i);
+            s.last_op[gi] = OP_COLLIDE;
+            s.op_obj[gi] = code_make(hg, hit - E.grp[hg].foff);
+        }
+    }
+    if (ok_ct) atomic_add64(&E.counters[CNT_MOVES_OK], ok_ct);
+    if (blocked) atomic_add64(&E.counters[CNT_MOVES_BLOCKED], blocked);
+}
+
+// phase 9a: winners vacate their old cells
+template <class Ctx>
+MG_HD void phase_move_clear(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+    ArenaRef R = arena_ref(E, a);
+    GroupEnum ord; enum_order(E, S, a, ord);
+    for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
+        int k, i; enum_locate(ord, idx, k, i);
+        int g = ord.grp[k];
+        const GroupDev &G = E.grp[g];
+        long f = R.sb + G.foff + i;
+        if (E.mv_state[f] != MV_OK) continue;
+        const AgentSoA &s = cur_soa(E, S.curmask, g);
+        long gi = gidx(E, a, g, i);
+        int x = s.x[gi], y = s.y[gi];
+        for (int bx = 0; bx < G.body_w; ++bx)
+            for (int by = 0; by < G.body_l; ++by)
+                R.occ[(y + by) * E.W + x + bx] = OCC_EMPTY;
+    }
+}
+
+// phase 9b: winners occupy their new cells; every queued mover unhooks its claimant nodes
+template <class Ctx>
+MG_HD void phase_move_fill(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+    ArenaRef R = arena_ref(E, a);
+    GroupEnum ord; enum_order(E, S, a, ord);
+    for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
+        int k, i; enum_locate(ord, idx, k, i);
+        int g = ord.grp[k];
+        const GroupDev &G = E.grp[g];
+        long f = R.sb + G.foff + i;
+        unsigned char st = E.mv_state[f];
+        if (st != MV_OK && st != MV_PENDING_FAIL) continue;
+        int nx = E.mv_nx[f], ny = E.mv_ny[f];
+        bool ok = st == MV_OK;
+        int code = code_make(g, i);
+        for (int bx = 0; bx < G.body_w; ++bx)
+            for (int by = 0; by < G.body_l; ++by) {
+                int cell = (ny + by) * E.W + nx + bx;
+                R.claim[cell] = -1;
+                if (ok) R.occ[cell] = code;
+            }
+        if (ok) {
+            const AgentSoA &s = cur_soa(E, S.curmask, g);
+            long gi = gidx(E, a, g, i);
+            s.x[gi] = nx; s.y[gi] = ny;
+        }
+    }
+}
+
+// phase 10: one reward rule (RewardEngine.cc:216-443 restricted to the shapes the rule compiler accepts:
+// a single 'any' subject, optionally with its op_obj bound to the object symbol)
+MG_HD bool rule_eval(const EngineDev &E, const RuleDev &Ru, unsigned curmask, int a, int sub_code, int obj_code) {
+    bool stack[MG_MAX_PROG];
+    int sp = 0;
+    for (int p = 0; p < Ru.n_prog; ++p) {
+        const RuleInstr &I = Ru.prog[p];
+        switch (I.op) {
+            case OP_AND: { bool b = stack[--sp]; bool x = stack[--sp]; stack[sp++] = x && b; break; }
+            case OP_OR:  { bool b = stack[--sp]; bool x = stack[--sp]; stack[sp++] = x || b; break; }
+            case OP_NOT: { stack[sp - 1] = !stack[sp - 1]; break; }
+            default: {
+                int ca = I.role_a ? obj_code : sub_code;
+                int ga = code_group(ca);
+                const AgentSoA &s = cur_soa(E, curmask, ga);
+                long gi = gidx(E, a, ga, code_index(ca));
+                bool v = false;
+                if (I.op == OP_KILL || I.op == OP_ATTACK || I.op == OP_COLLIDE) {
+                    int cb = I.role_b ? obj_code : sub_code;
+                    v = s.last_op[gi] == I.op && s.op_obj[gi] == cb;
+                } else if (I.op == OP_DIE) {
+                    v = (s.flags[gi] & FLAG_DEAD) != 0;
+                } else if (I.op == OP_AT) {
+                    v = s.x[gi] == I.i0 && s.y[gi] == I.i1;
+                } else if (I.op == OP_IN) {
+                    int x = s.x[gi], y = s.y[gi];
+                    v = x > I.i0 && x < I.i2 && y > I.i1 && y < I.i3;
+                }
+                stack[sp++] = v;
+            }
+        }
+    }
+    return sp > 0 && stack[sp - 1];
+}
+
+template <class Ctx>
+MG_HD void phase_reward_rule(Ctx &c, const EngineDev &E, const StepArgs &S, int a, int r) {
+    ArenaRef R = arena_ref(E, a);
+    const RuleDev &Ru = E.rules[r];
+    int g = Ru.sub_group;
+    int n = E.n[g * E.A + a];
+    const AgentSoA &s = cur_soa(E, S.curmask, g);
+    bool any = false;
+    for (int i = c.tid(); i < n; i += c.nth()) {
+        long gi = gidx(E, a, g, i);
+        int obj = -1;
+        if (Ru.has_obj) {                                 // AgentSymbol::bind_with_check (RewardEngine.cc:14-23)
+            obj = s.op_obj[gi];
+            if (obj < 0) continue;
+            if (code_group(obj) != Ru.obj_group) continue;
+            if (Ru.obj_index != -1 && code_index(obj) != Ru.obj_index) continue;
+        }
+        int sub = code_make(g, i);
+        if (!rule_eval(E, Ru, S.curmask, a, sub, obj)) continue;
+        any = true;
+        for (int q = 0; q < Ru.n_recv; ++q) {
+            const RuleRecv &rc = Ru.recv[q];
+            if (rc.role == 2) {
+                atomic_addf(&R.hdr->grp_reward[rc.group], rc.value);
+            } else {
+                int cd = rc.role ? obj : sub;
+                if (cd < 0) continue;
+                int gg = code_group(cd);
+                atomic_addf(&cur_soa(E, S.curmask, gg).next_reward[gidx(E, a, gg, code_index(cd))], rc.value);
+            }
+        }
+    }
+    if (any) atomic_or(&R.hdr->rule_trigger, 1 << r);
+}
+
+// phase 11: game-over check (GridWorld.cc:618-630) and rng commit
+template <class Ctx>
+MG_HD void phase_done(Ctx &c, const EngineDev &E, int a) {
+    if (c.tid() != 0) return;
+    ArenaRef R = arena_ref(E, a);
+    int live = 0;
+    for (int g = 0; g < E.G; ++g)
+        if (E.n[g * E.A + a] - E.dead_ct[g * E.A + a] > 0) ++live;
+    int done = live < E.G;
+    for (int r = 0; r < E.n_rules; ++r)
+        if (((R.hdr->rule_trigger >> r) & 1) && E.rules[r].is_terminal) done = 1;
+    R.hdr->done = done;
+    E.done[a] = done;
+    R.hdr->rng = R.hdr->rng_next;
+}
+
+// relaxation driver: sweep until a full sweep changes nothing.  One team barrier per sweep; the
+// rotating flag triple makes the reset of the next flag race-free.
+template <class Ctx, class Sweep>
+MG_HD void relax_until_stable(Ctx &c, ArenaHdr *hdr, Sweep sweep) {
+    for (int it = 0;; ++it) {
+        int cur = it % 3, nxt = (it + 1) % 3;
+        if (c.tid() == 0) st_volatile(&hdr->changed[nxt], 0);
+        if (sweep()) st_volatile(&hdr->changed[cur], 1);
+        c.sync();
+        if (!ld_volatile(&hdr->changed[cur])) break;
+    }
+}
+
+// the whole step for one arena (reference GridWorld::step, GridWorld.cc:456-631)
+template <class Ctx>
+MG_HD void run_step(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+    ArenaHdr *hdr = E.hdr + a;
+    phase_init(c, E, S, a);
+    c.sync();
+    int n_attack = phase_attack_scan(c, E, S, a);
+    c.sync();
+    if (n_attack > 0) {
+        phase_rng(c, E, a, n_attack);
+        c.sync();
+        phase_rank_target(c, E, S, a, n_attack);
+        c.sync();
+        relax_until_stable(c, hdr, [&]() { return phase_attack_relax(c, E, S, a); });
+    }
+    phase_attack_apply_starve(c, E, S, a);
+    c.sync();
+    phase_move_register(c, E, S, a);
+    c.sync();
+    if (c.tid() == 0) { hdr->changed[0] = hdr->changed[1] = hdr->changed[2] = 0; }
+    c.sync();
+    relax_until_stable(c, hdr, [&]() { return phase_move_relax(c, E, S, a); });
+    phase_move_collide(c, E, S, a);
+    c.sync();
+    phase_move_clear(c, E, S, a);
+    c.sync();
+    phase_move_fill(c, E, S, a);
+    c.sync();
+    for (int r = 0; r < E.n_rules; ++r) {
+        phase_reward_rule(c, E, S, a, r);
+        c.sync();
+    }
+    phase_done(c, E, a);
+    c.sync();
+}
+
+// clear_dead for one arena: stable compaction of every group into the other SoA buffer
+// (reference GridWorld::clear_dead, GridWorld.cc:633-665, Agent::init_reward GridWorld.h:168-174)
+template <class Ctx>
+MG_HD void run_cull(Ctx &c, const EngineDev &E, unsigned curmask, int a) {
+    ArenaRef R = arena_ref(E, a);
+    for (int g = 0; g < E.G; ++g) {
+        const GroupDev &G = E.grp[g];
+        const AgentSoA &src = G.soa[(curmask >> g) & 1u];
+        const AgentSoA &dst = G.soa[((curmask >> g) & 1u) ^ 1u];
+        int n = E.n[g * E.A + a];
+        c.sync();
+        auto pred = [&](int i) -> int { return (src.flags[gidx(E, a, g, i)] & FLAG_DEAD) ? 0 : 1; };
+        auto emit = [&](int i, int j) {
+            long si = gidx(E, a, g, i), di = gidx(E, a, g, j);
+            int x = src.x[si], y = src.y[si];
+            dst.x[di] = x; dst.y[di] = y;
+            dst.hp[di] = src.hp[si];
+            dst.act[di] = src.act[si];
+            dst.id[di] = src.id[si];
+            dst.last_reward[di] = src.next_reward[si];
+            dst.next_reward[di] = G.step_reward;
+            dst.op_obj[di] = -1;
+            dst.last_op[di] = OP_NULL;
+            dst.flags[di] = src.flags[si];
+            dst.dir[di] = src.dir[si];
+            if (i != j) {
+                int code = code_make(g, j);
+                for (int bx = 0; bx < G.body_w; ++bx)
+                    for (int by = 0; by < G.body_l; ++by)
+                        R.occ[(y + by) * E.W + x + bx] = code;
+            }
+        };
+        int total = c.scan(n, pred, emit);
+        c.sync();
+        if (c.tid() == 0) {
+            E.n[g * E.A + a] = total;
+            E.dead_ct[g * E.A + a] = 0;
+            R.hdr->grp_reward[g] = 0.0f;
+        }
+    }
+    c.sync();
+}
+
+}  // namespace mg

@@ -1,0 +1,132 @@
+// backend_emu.cc -- TEST INFRASTRUCTURE ONLY.
+//
+// A single-threaded host implementation of magent_b200/csrc/backend.h that runs the very same
+// phase functions (step_phases.h / obs_phases.h) the CUDA kernels run, with a team of one thread.
+// Purpose: debug the *parallel formulations* (shuffle replay, rank-ordered attack relaxation, claimant
+// list move relaxation, reward programs, compaction) against the compiled reference on development
+// containers that have no GPU.  It is built by tests/emu/build.sh into tests/_emu/libmagent_emu.so,
+// is never part of magent_b200/lib/libmagent.so, and nothing in the product path can load it.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../magent_b200/csrc/backend.h"
+#include "../../magent_b200/csrc/obs_phases.h"
+
+namespace mg {
+namespace be {
+
+struct HostCtx {
+    int tid() const { return 0; }
+    int nth() const { return 1; }
+    void sync() {}
+    template <class P, class Em> int scan(int n, P pred, Em emit) {
+        int run = 0;
+        for (int i = 0; i < n; ++i) if (pred(i)) emit(i, run++);
+        return run;
+    }
+};
+
+const char *name() { return "emu"; }
+bool init(int, std::string *) { return true; }
+int device_count() { return 1; }
+int sm_count() { return 1; }
+void *dmalloc(size_t b) { return calloc(1, b ? b : 1); }
+void dfree(void *p) { free(p); }
+void dmemset(void *p, int byte, size_t n) { memset(p, byte, n); }
+void h2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
+void d2h(void *d, const void *s, size_t n) { memcpy(d, s, n); }
+void d2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
+void *host_alloc(size_t b) { return malloc(b ? b : 1); }
+void host_free(void *p) { free(p); }
+bool is_device_ptr(const void *) { return false; }
+void sync() {}
+
+void launch_step(const EngineDev *dE, const EngineDev &, const StepArgs &S, int) {
+    HostCtx c;
+    for (int a = 0; a < dE->A; ++a) run_step(c, *dE, S, a);
+}
+void launch_cull(const EngineDev *dE, const EngineDev &, unsigned curmask, int) {
+    HostCtx c;
+    for (int a = 0; a < dE->A; ++a) run_cull(c, *dE, curmask, a);
+}
+void launch_offsets(const EngineDev *dE, const EngineDev &) {
+    const EngineDev &E = *dE;
+    for (int g = 0; g < E.G; ++g) {
+        int *off = E.off + (size_t)g * (E.A + 1);
+        off[0] = 0;
+        for (int a = 0; a < E.A; ++a) off[a + 1] = off[a] + E.n[g * E.A + a];
+    }
+}
+void launch_minimap(const EngineDev *dE, const EngineDev &, unsigned curmask, int og, float *mm_val) {
+    const EngineDev &E = *dE;
+    const GroupDev &OG = E.grp[og];
+    int cells = OG.view_w * OG.view_h;
+    for (int a = 0; a < E.A; ++a)
+        for (int j = 0; j < E.G; ++j) {
+            std::vector<int> cnt(cells, 0);
+            int n = E.n[j * E.A + a];
+            const AgentSoA &s = cur_soa(E, curmask, j);
+            for (int i = 0; i < n; ++i) {
+                int cx, cy;
+                minimap_cell(E, OG.view_w, OG.view_h, s.x[gidx(E, a, j, i)], s.y[gidx(E, a, j, i)], cx, cy);
+                cnt[cy * OG.view_w + cx]++;
+            }
+            float *out = mm_val + ((size_t)a * E.G + j) * cells;
+            for (int k = 0; k < cells; ++k) out[k] = (float)cnt[k] / (float)n;
+        }
+}
+void launch_obs(const EngineDev *dE, const EngineDev &, const ObsArgs &O, const float *mm_val, int) {
+    const EngineDev &E = *dE;
+    int g = O.group;
+    const GroupDev &G = E.grp[g];
+    int cells = G.view_w * G.view_h, C = E.n_channel;
+    const AgentSoA &s = cur_soa(E, O.curmask, g);
+    for (int a = 0; a < E.A; ++a) {
+        int n = E.n[g * E.A + a], base = E.off[(size_t)g * (E.A + 1) + a];
+        const float *mm = mm_val ? mm_val + (size_t)a * E.G * cells : nullptr;
+        for (int i = 0; i < n; ++i) {
+            long gi = gidx(E, a, g, i);
+            int cx = -1, cy = -1;
+            if (mm) minimap_cell(E, G.view_w, G.view_h, s.x[gi], s.y[gi], cx, cy);
+            float *out = O.view + (size_t)(base + i) * cells * C;
+            for (int vy = 0; vy < G.view_h; ++vy)
+                for (int vx = 0; vx < G.view_w; ++vx)
+                    obs_compose_cell(E, O.curmask, a, g, s.x[gi], s.y[gi], cx, cy, vy, vx, mm,
+                                     out + (size_t)(vy * G.view_w + vx) * C);
+            obs_feature(E, O.curmask, a, g, i, O.feature + (size_t)(base + i) * G.feature_size);
+        }
+    }
+}
+void launch_info(const EngineDev *dE, const EngineDev &, unsigned curmask, int kind, int g, void *buf, int) {
+    const EngineDev &E = *dE;
+    const AgentSoA &s = cur_soa(E, curmask, g);
+    for (int a = 0; a < E.A; ++a) {
+        int n = E.n[g * E.A + a], base = E.off[(size_t)g * (E.A + 1) + a];
+        for (int i = 0; i < n; ++i) {
+            long gi = gidx(E, a, g, i);
+            int o = base + i;
+            switch (kind) {
+                case INFO_ID: ((int *)buf)[o] = s.id[gi]; break;
+                case INFO_POS: ((int *)buf)[2 * o] = s.x[gi]; ((int *)buf)[2 * o + 1] = s.y[gi]; break;
+                case INFO_ALIVE: ((unsigned char *)buf)[o] = (s.flags[gi] & FLAG_DEAD) ? 0 : 1; break;
+                case INFO_REWARD: ((float *)buf)[o] = s.next_reward[gi] + E.hdr[a].grp_reward[g]; break;
+                case INFO_HP: ((float *)buf)[o] = s.hp[gi]; break;
+                case INFO_ACTION_SCATTER: s.act[gi] = ((const int *)buf)[o]; break;
+            }
+        }
+    }
+}
+void launch_random_actions(const EngineDev *dE, const EngineDev &, unsigned curmask, int g,
+                           unsigned long long seed, int) {
+    const EngineDev &E = *dE;
+    const AgentSoA &s = cur_soa(E, curmask, g);
+    unsigned long long x = seed | 1;
+    for (int a = 0; a < E.A; ++a)
+        for (int i = 0; i < E.n[g * E.A + a]; ++i) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            s.act[gidx(E, a, g, i)] = (int)(x % (unsigned)E.grp[g].n_action);
+        }
+}
+
+}  // namespace be
+}  // namespace mg

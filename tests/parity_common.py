@@ -1,0 +1,169 @@
+"""Shared helpers for the differential (parity) tests.
+
+A *scenario* builds an environment on a given engine library, places walls/agents and returns the
+env; `run_trace` then plays a pre-generated random action stream and records everything observable
+through the ABI at every step.  Two traces (reference vs CUDA engine, or golden vs live) are compared
+with `compare_traces`: integer state bit-exact, observations bit-exact (float32 byte equality),
+rewards within 1e-6 (BASELINE.json north_star).
+"""
+import hashlib
+import os
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(REPO, "oracle", "_ref", "libmagent.so")
+PORT_LIB = os.path.join(REPO, "oracle", "_build", "libmagent_oracle.so")
+EMU_LIB = os.path.join(REPO, "tests", "_emu", "libmagent_emu.so")
+CUDA_LIB = os.path.join(REPO, "magent_b200", "lib", "libmagent.so")
+REWARD_TOL = 1e-6
+
+
+def sha(arr):
+    return hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
+
+
+def run_trace(env, steps, seed, act_groups=None, keep_obs=False, order=None, stop_on_done=True):
+    """Play `steps` steps of uniform random actions; return a list of per-step dict records."""
+    import magent_b200  # noqa: F401  (package must be importable)
+    handles = env.get_handles()
+    act_groups = list(range(len(handles))) if act_groups is None else act_groups
+    order = act_groups if order is None else order
+    rs = np.random.RandomState(seed)
+    trace = []
+    for _ in range(steps):
+        rec = {"num": [env.get_num(h) for h in handles]}
+        obs = {}
+        for gi in act_groups:
+            if rec["num"][gi] == 0:
+                obs[gi] = (np.zeros((0,), np.float32), np.zeros((0,), np.float32))
+                continue
+            v, f = env.get_observation(handles[gi])
+            obs[gi] = (v.copy(), f.copy()) if keep_obs else (sha(v), sha(f))
+            if not keep_obs:
+                rec.setdefault("hp_chan_sum", {})[gi] = float(np.asarray(v, dtype=np.float64).sum())
+        rec["obs"] = obs
+        rec["id"] = [env.get_agent_id(h).copy() for h in handles]
+        rec["pos"] = [env.get_pos(h).copy() for h in handles]
+        acts = {}
+        for gi in act_groups:
+            n_act = env.get_action_space(handles[gi])[0]
+            acts[gi] = rs.randint(0, n_act, size=rec["num"][gi]).astype(np.int32)
+        for gi in order:
+            env.set_action(handles[gi], acts[gi])
+        rec["done"] = bool(env.step())
+        rec["reward"] = [env.get_reward(h).copy() for h in handles]
+        rec["alive"] = [env.get_alive(h).copy() for h in handles]
+        rec["pos_after"] = [env.get_pos(h).copy() for h in handles]
+        env.clear_dead()
+        trace.append(rec)
+        if rec["done"] and stop_on_done:
+            break
+    return trace
+
+
+def compare_traces(ta, tb, what="trace"):
+    assert len(ta) == len(tb), "%s: length %d vs %d" % (what, len(ta), len(tb))
+    for t, (a, b) in enumerate(zip(ta, tb)):
+        tag = "%s step %d" % (what, t)
+        assert a["num"] == b["num"], "%s num %s vs %s" % (tag, a["num"], b["num"])
+        for g in range(len(a["num"])):
+            np.testing.assert_array_equal(a["id"][g], b["id"][g], err_msg=tag + " id g%d" % g)
+            np.testing.assert_array_equal(a["pos"][g], b["pos"][g], err_msg=tag + " pos g%d" % g)
+            np.testing.assert_array_equal(a["alive"][g], b["alive"][g], err_msg=tag + " alive g%d" % g)
+            np.testing.assert_array_equal(a["pos_after"][g], b["pos_after"][g], err_msg=tag + " pos_after g%d" % g)
+            np.testing.assert_allclose(a["reward"][g], b["reward"][g], rtol=0, atol=REWARD_TOL,
+                                       err_msg=tag + " reward g%d" % g)
+        assert a["done"] == b["done"], tag + " done"
+        for g in a["obs"]:
+            va, fa = a["obs"][g]
+            vb, fb = b["obs"][g]
+            if isinstance(va, str):
+                assert fa == fb, tag + " feature hash g%d" % g
+                assert va == vb, tag + " view hash g%d" % g
+            else:
+                np.testing.assert_array_equal(fa.view(np.uint32), fb.view(np.uint32), err_msg=tag + " feature g%d" % g)
+                np.testing.assert_array_equal(va.view(np.uint32), vb.view(np.uint32), err_msg=tag + " view g%d" % g)
+
+
+# ------------------------------------------------------------------ scenarios
+def make_battle(lib, map_size=40, n=60, seed=0, **kw):
+    import magent_b200 as magent
+    env = magent.GridWorld("battle", map_size=map_size, _lib=lib, **kw)
+    env.set_seed(seed)
+    env.reset()
+    h = env.get_handles()
+    env.add_agents(h[0], method="random", n=n)
+    env.add_agents(h[1], method="random", n=n)
+    return env
+
+
+def make_battle_blocks(lib, map_size=40, **kw):
+    """the dense two-block layout of examples/train_battle.py:15-40"""
+    import math
+    import magent_b200 as magent
+    env = magent.GridWorld("battle", map_size=map_size, _lib=lib, **kw)
+    env.reset()
+    h = env.get_handles()
+    width = height = map_size
+    init_num = map_size * map_size * 0.04
+    gap = 3
+    side = int(math.sqrt(init_num)) * 2
+    pos = [[x, y, 0] for x in range(width // 2 - gap - side, width // 2 - gap, 2)
+           for y in range((height - side) // 2, (height - side) // 2 + side, 2)]
+    env.add_agents(h[0], method="custom", pos=pos)
+    pos = [[x, y, 0] for x in range(width // 2 + gap, width // 2 + gap + side, 2)
+           for y in range((height - side) // 2, (height - side) // 2 + side, 2)]
+    env.add_agents(h[1], method="custom", pos=pos)
+    return env
+
+
+def make_pursuit(lib, map_size=40, seed=0, **kw):
+    """config 1 of BASELINE.json: 40x40, 48 walls, 16 predators, 32 prey"""
+    import magent_b200 as magent
+    env = magent.GridWorld("pursuit", map_size=map_size, _lib=lib, **kw)
+    env.set_seed(seed)
+    env.reset()
+    h = env.get_handles()
+    env.add_walls(method="random", n=map_size * map_size * 0.03)
+    env.add_agents(h[0], method="random", n=map_size * map_size * 0.01)
+    env.add_agents(h[1], method="random", n=map_size * map_size * 0.02)
+    return env
+
+
+def gather_config(size):
+    """the config of examples/train_gather.py:14-43 (reference file, values only)"""
+    import magent_b200 as magent
+    gw = magent.gridworld
+    cfg = gw.Config()
+    cfg.set({"map_width": size, "map_height": size})
+    cfg.set({"minimap_mode": True})
+    agent = cfg.register_agent_type(
+        name="agent",
+        attr={'width': 1, 'length': 1, 'hp': 3, 'speed': 3,
+              'view_range': gw.CircleRange(7), 'attack_range': gw.CircleRange(1),
+              'damage': 6, 'step_recover': 0,
+              'step_reward': -0.01, 'dead_penalty': -1, 'attack_penalty': -0.1,
+              'attack_in_group': 1})
+    food = cfg.register_agent_type(
+        name='food',
+        attr={'width': 1, 'length': 1, 'hp': 25, 'speed': 0,
+              'view_range': gw.CircleRange(1), 'attack_range': gw.CircleRange(0),
+              'kill_reward': 5})
+    g_f = cfg.add_group(food)
+    g_s = cfg.add_group(agent)
+    a = gw.AgentSymbol(g_s, index='any')
+    b = gw.AgentSymbol(g_f, index='any')
+    cfg.add_reward_rule(gw.Event(a, 'attack', b), receiver=a, value=0.5)
+    return cfg
+
+
+def make_gather(lib, map_size=40, seed=0, n_agent=40, n_food=120, **kw):
+    import magent_b200 as magent
+    env = magent.GridWorld(gather_config(map_size), _lib=lib, **kw)
+    env.set_seed(seed)
+    env.reset()
+    h = env.get_handles()
+    env.add_agents(h[1], method="random", n=n_agent)
+    env.add_agents(h[0], method="random", n=n_food)
+    return env
