@@ -29,6 +29,12 @@ int magent_b200_random_actions(EnvHandle game, GroupHandle group, void *unused, 
  * moves_blocked, steps.  Returns the number written. */
 int magent_b200_get_counters(EnvHandle game, long long *out, int capacity);
 
+/* instrumentation: kernels launched by this library in this process; optional CUDA-event timing of the
+ * obs-render kernel (total milliseconds and launches since enabled; adds one event sync per launch). */
+long long magent_b200_launch_count(void);
+int magent_b200_set_profiling(int on);
+int magent_b200_get_profile(double *obs_ms_total, long long *obs_launches);
+
 #ifdef __cplusplus
 }
 #endif

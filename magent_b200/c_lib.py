@@ -65,6 +65,9 @@ EXT_SIGNATURES = {
     "magent_b200_random_actions": ([_vp, ctypes.c_int, _vp, ctypes.c_ulonglong], ctypes.c_int),
     "magent_b200_get_counters": ([_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int], ctypes.c_int),
     "magent_b200_last_error": ([], ctypes.c_char_p),
+    "magent_b200_set_profiling": ([ctypes.c_int], ctypes.c_int),
+    "magent_b200_get_profile": ([ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)], ctypes.c_int),
+    "magent_b200_launch_count": ([], ctypes.c_longlong),
 }
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -40,5 +40,10 @@ void launch_info(const EngineDev *dE, const EngineDev &hE, unsigned curmask, int
 void launch_random_actions(const EngineDev *dE, const EngineDev &hE, unsigned curmask, int group,
                            unsigned long long seed, int n_total);
 
+// instrumentation: kernel launch counter and optional CUDA-event timing of the obs-render kernel
+long long launch_count();
+void profile_enable(bool on);
+void profile_read(double *obs_ms_total, long long *obs_launches);
+
 }  // namespace be
 }  // namespace mg

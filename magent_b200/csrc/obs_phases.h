@@ -70,4 +70,20 @@ MG_HD void obs_feature(const EngineDev &E, unsigned curmask, int a, int g, int i
     }
 }
 
+// one element of the feature vector (same values as obs_feature, element-wise for coalesced stores)
+MG_HD float obs_feature_elem(const EngineDev &E, unsigned curmask, int a, int g, int i, int k) {
+    const GroupDev &G = E.grp[g];
+    const AgentSoA &s = cur_soa(E, curmask, g);
+    long gi = gidx(E, a, g, i);
+    if (k < E.embedding_size) return k < 31 ? (float)((s.id[gi] >> k) & 1) : 0.0f;
+    int kk = k - E.embedding_size;
+    if (kk < G.n_action) return kk == s.act[gi] ? 1.0f : 0.0f;
+    if (kk == G.n_action) return s.last_reward[gi];
+    if (E.minimap_mode) {
+        if (kk == G.n_action + 1) return (float)s.x[gi] / (float)E.W;
+        if (kk == G.n_action + 2) return (float)s.y[gi] / (float)E.H;
+    }
+    return 0.0f;
+}
+
 }  // namespace mg

@@ -85,3 +85,6 @@ MG_API int magent_b200_random_actions(EnvHandle game, GroupHandle group, void *,
     E(game)->random_actions(group, seed); return 0;
 }
 MG_API int magent_b200_get_counters(EnvHandle game, long long *out, int capacity) { return E(game)->get_counters(out, capacity); }
+MG_API long long magent_b200_launch_count(void) { return mg::be::launch_count(); }
+MG_API int magent_b200_set_profiling(int on) { mg::be::profile_enable(on != 0); return 0; }
+MG_API int magent_b200_get_profile(double *ms, long long *n) { mg::be::profile_read(ms, n); return 0; }

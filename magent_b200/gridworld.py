@@ -106,7 +106,10 @@ class GridWorld(Environment):
 
         L = self._lib
         game = ctypes.c_void_p()
-        L.env_new_game(ctypes.byref(game), b"GridWorld")
+        rc = L.env_new_game(ctypes.byref(game), b"GridWorld")
+        if rc != 0 or not game.value:
+            why = L.magent_b200_last_error().decode() if L.is_b200 else "env_new_game failed"
+            raise RuntimeError("cannot create the GridWorld engine: " + why)
         self.game = game
 
         # extension keys go first: they size the arena batch before anything else is configured
@@ -432,6 +435,21 @@ class GridWorld(Environment):
 
     def sync(self):
         self._lib.magent_b200_sync(self.game)
+
+    def set_profiling(self, on):
+        """bracket every obs-render kernel launch with CUDA events (adds a sync per launch)"""
+        self._lib.magent_b200_set_profiling(1 if on else 0)
+
+    def get_profile(self):
+        """(total obs-render kernel milliseconds, launches) since profiling was enabled"""
+        ms = ctypes.c_double(0.0)
+        n = ctypes.c_longlong(0)
+        self._lib.magent_b200_get_profile(ctypes.byref(ms), ctypes.byref(n))
+        return ms.value, n.value
+
+    def launch_count(self):
+        """number of kernels this library has launched in this process"""
+        return int(self._lib.magent_b200_launch_count())
 
     # ------------------------------------------------------------------ reward DSL -> ABI
     def _serialize_event_exp(self, config):

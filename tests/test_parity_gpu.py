@@ -1,0 +1,173 @@
+"""Parity of the CUDA engine against the oracle, through the C ABI, on a real GPU.
+
+Checker = the compiled reference (oracle/_ref/libmagent.so, built from /root/reference by
+oracle/Makefile and shipped to the GPU box) or, when absent, the C restatement (oracle/_build).
+Both engines are driven by the same host code (magent_b200.gridworld) with the same seeds and the same
+pre-generated action streams; integer state and observations must match bit-exactly, rewards within 1e-6.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import parity_common as pc
+
+pytestmark = pytest.mark.gpu
+
+
+def checker_lib():
+    for p in (pc.REF_LIB, pc.PORT_LIB):
+        if os.path.exists(p):
+            return p
+    pytest.skip("no oracle library available (oracle/_ref or oracle/_build)")
+
+
+def both(make, steps, seed, **kw):
+    want = pc.run_trace(make(checker_lib()), steps, seed, keep_obs=True, **kw)
+    got = pc.run_trace(make(pc.CUDA_LIB), steps, seed, keep_obs=True, **kw)
+    pc.compare_traces(want, got)
+    return want
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_battle_small(seed):
+    both(lambda lib: pc.make_battle(lib, 40, 150, seed), 60, seed)
+
+
+def test_battle_dense_blocks():
+    both(lambda lib: pc.make_battle_blocks(lib, 40), 80, 5)
+
+
+def test_battle_kills_happen():
+    """dense enough that agents die, get culled and re-indexed"""
+    want = both(lambda lib: pc.make_battle(lib, 30, 300, 3), 80, 3)
+    assert want[-1]["num"][0] < 300 and want[-1]["num"][1] < 300
+
+
+def test_battle_large_map_bands():
+    """w*h > 99*99 switches the reference to banded move buffers (GridWorld.cc:75-85,411-438)"""
+    both(lambda lib: pc.make_battle(lib, 120, 2000, 7), 25, 7)
+
+
+def test_battle_config2_200x200():
+    """BASELINE.json configs[1]: battle 200x200, 2x1000 agents"""
+    both(lambda lib: pc.make_battle(lib, 200, 1000, 0), 20, 0)
+
+
+def test_set_action_order_decides_contention():
+    """the group whose set_action is called first moves first"""
+    both(lambda lib: pc.make_battle(lib, 30, 250, 11), 30, 11, order=[1, 0])
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_pursuit_2x2_bodies(seed):
+    """BASELINE.json configs[0] geometry: 40x40, walls, 2x2 predators"""
+    both(lambda lib: pc.make_pursuit(lib, 40, seed), 100, seed)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_gather_attack_in_group(seed):
+    both(lambda lib: pc.make_gather(lib, 40, seed), 100, seed, act_groups=[1])
+
+
+def test_gather_dense_infighting():
+    """agents kill each other (hp 3, damage 6): exercises shuffle order + skip-dead-attacker"""
+    want = both(lambda lib: pc.make_gather(lib, 24, 2, n_agent=150, n_food=60), 40, 2, act_groups=[1])
+    assert want[-1]["num"][1] < 150
+
+
+def test_unculled_dead_agents_keep_their_slots():
+    """no clear_dead between steps: dead agents stay in the vectors, still get actions, are skipped"""
+    import magent_b200  # noqa: F401
+
+    def run(lib):
+        env = pc.make_battle(lib, 24, 150, 4)
+        hs = env.get_handles()
+        rs = np.random.RandomState(4)
+        out = []
+        for t in range(30):
+            obs = [tuple(x.copy() for x in env.get_observation(h)) for h in hs]
+            acts = [rs.randint(0, 21, size=env.get_num(h)).astype(np.int32) for h in hs]
+            for h, a in zip(hs, acts):
+                env.set_action(h, a)
+            done = env.step()
+            out.append((obs, [env.get_reward(h).copy() for h in hs], [env.get_alive(h).copy() for h in hs],
+                        [env.get_pos(h).copy() for h in hs], done))
+            if t % 5 == 4:
+                env.clear_dead()
+        return out
+    a, b = run(checker_lib()), run(pc.CUDA_LIB)
+    for t, (ra, rb) in enumerate(zip(a, b)):
+        for g in range(2):
+            np.testing.assert_array_equal(ra[0][g][0].view(np.uint32), rb[0][g][0].view(np.uint32), err_msg="view t%d" % t)
+            np.testing.assert_array_equal(ra[0][g][1].view(np.uint32), rb[0][g][1].view(np.uint32), err_msg="feat t%d" % t)
+            np.testing.assert_allclose(ra[1][g], rb[1][g], atol=pc.REWARD_TOL, rtol=0)
+            np.testing.assert_array_equal(ra[2][g], rb[2][g])
+            np.testing.assert_array_equal(ra[3][g], rb[3][g])
+        assert ra[4] == rb[4]
+
+
+def test_arena_batch_equals_independent_references():
+    """4 arenas behind one handle == 4 reference environments seeded seed+a"""
+    import magent_b200 as magent
+    A, n, size, steps = 4, 120, 36, 40
+    env = magent.GridWorld("battle", map_size=size, _lib=pc.CUDA_LIB, _num_arenas=A)
+    env.set_seed(20)
+    env.reset()
+    hs = env.get_handles()
+    for h in hs:
+        env.add_agents(h, method="random", n=n)
+    refs = []
+    for a in range(A):
+        r = magent.GridWorld("battle", map_size=size, _lib=checker_lib())
+        r.set_seed(20 + a)
+        r.reset()
+        for h in r.get_handles():
+            r.add_agents(h, method="random", n=n)
+        refs.append(r)
+    rs = np.random.RandomState(9)
+    for t in range(steps):
+        nums = [env.get_arena_nums(h) for h in hs]
+        for g, h in enumerate(hs):
+            v, f = env.get_observation(h)
+            off = np.concatenate([[0], np.cumsum(nums[g])])
+            for a, r in enumerate(refs):
+                rv, rf = r.get_observation(r.get_handles()[g])
+                assert rv.shape[0] == nums[g][a]
+                np.testing.assert_array_equal(v[off[a]:off[a + 1]].view(np.uint32), rv.view(np.uint32), err_msg="view t%d a%d" % (t, a))
+                np.testing.assert_array_equal(f[off[a]:off[a + 1]].view(np.uint32), rf.view(np.uint32), err_msg="feat t%d a%d" % (t, a))
+        acts = [rs.randint(0, 21, size=int(nums[g].sum())).astype(np.int32) for g in range(2)]
+        for g, h in enumerate(hs):
+            env.set_action(h, acts[g])
+            off = np.concatenate([[0], np.cumsum(nums[g])])
+            for a, r in enumerate(refs):
+                r.set_action(r.get_handles()[g], np.ascontiguousarray(acts[g][off[a]:off[a + 1]]))
+        env.step()
+        dones = [r.step() for r in refs]
+        np.testing.assert_array_equal(env.get_arena_done() != 0, np.array(dones))
+        for g, h in enumerate(hs):
+            rew, pos, alive = env.get_reward(h), env.get_pos(h), env.get_alive(h)
+            off = np.concatenate([[0], np.cumsum(nums[g])])
+            for a, r in enumerate(refs):
+                rh = r.get_handles()[g]
+                np.testing.assert_allclose(rew[off[a]:off[a + 1]], r.get_reward(rh), atol=pc.REWARD_TOL, rtol=0)
+                np.testing.assert_array_equal(pos[off[a]:off[a + 1]], r.get_pos(rh))
+                np.testing.assert_array_equal(alive[off[a]:off[a + 1]], r.get_alive(rh))
+        env.clear_dead()
+        for r in refs:
+            r.clear_dead()
+
+
+def test_huge_arena_grid_mode():
+    """> 32768 agents in one arena: the cooperative whole-grid kernels (grid.sync between phases)"""
+    both(lambda lib: pc.make_battle(lib, 320, 20000, 1), 6, 1)
+
+
+def test_device_pointer_observation_matches_host_pointer():
+    import torch
+    env = pc.make_battle(pc.CUDA_LIB, 40, 150, 0)
+    h = env.get_handles()[0]
+    v, f = env.get_observation(h)
+    tv, tf = env.get_observation_torch(h)
+    np.testing.assert_array_equal(tv.cpu().numpy().view(np.uint32), v.view(np.uint32))
+    np.testing.assert_array_equal(tf.cpu().numpy().view(np.uint32), f.view(np.uint32))
