@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the GridWorld step path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input, through the C ABI:
+    for every acting group: env_get_observation;  set_action (uniform random);  env_step;
+    env_get_reward;  gridworld_clear_dead.
+`value`   = whole-job agent-steps/s with every buffer resident in HBM (device pointers through the same
+            ABI calls, random actions generated on the device), timed with CUDA events, max over ranks.
+`e2e`     = the same loop through HOST buffers (page-locked numpy arrays): observation and reward D2H and
+            action H2D copies are inside the timed region.
+`roofline`= the observation-render kernel: algorithmic bytes per launch / mean launch duration (CUDA events
+            around every launch inside the timed region) against the measured HBM copy bandwidth.
+`cpu_baseline` / `--impl reference` = the UNMODIFIED reference C++ engine (oracle/_ref/libmagent.so, built
+            from /root/reference by oracle/Makefile) driven by the same host code on this box's host cores.
+
+Workloads (BASELINE.json configs; the default is the per-GPU share of configs[4], weak scaling):
+    battle512  battle 200x200, 2x1000 agents, 512 independent arenas per GPU          [default]
+    battle1    battle 200x200, 2x1000 agents, 1 arena                     (configs[1])
+    gather64   gather 200x200, 495 agents + 1847 food, 64 arenas          (configs[2])
+    battle1m   battle 1000x1000, 2x400k agents, 1 arena (obs-render roofline; configs[3] as placeable)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "agent-steps/sec on battle map at 1/2/4/8 B200 vs ref C++ on host cores"
+UNIT = "agent-steps/s"
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libmagent.so")
+PORT_LIB = os.path.join(ROOT, "oracle", "_build", "libmagent_oracle.so")
+
+WORKLOADS = {
+    "battle512": dict(desc="battle 200x200, 2x1000 agents random placement, 512 independent arenas per GPU "
+                           "(per-GPU share of BASELINE configs[4]), uniform random actions",
+                      game="battle", map_size=200, arenas=512, n=1000),
+    "battle1": dict(desc="battle 200x200, 2x1000 agents, 1 arena (BASELINE configs[1]), uniform random actions",
+                    game="battle", map_size=200, arenas=1, n=1000),
+    "gather64": dict(desc="gather 200x200, 495 agents + 1847 food (examples/train_gather.py layout), 64 arenas "
+                          "(BASELINE configs[2]); only the agent group observes/acts",
+                     game="gather", map_size=200, arenas=64),
+    "battle1m": dict(desc="battle 1000x1000, 2x400k agents (80% fill; BASELINE configs[3] as placeable), 1 arena",
+                     game="battle", map_size=1000, arenas=1, n=400000),
+}
+
+
+def build_env(wl, lib, arenas, seed0=0):
+    import magent_b200 as magent
+    import parity_common as pc
+    kw = {}
+    if arenas != 1:
+        kw["_num_arenas"] = arenas
+    if wl["game"] == "battle":
+        env = magent.GridWorld("battle", map_size=wl["map_size"], _lib=lib, **kw)
+        env.set_seed(seed0)
+        env.reset()
+        hs = env.get_handles()
+        for h in hs:
+            env.add_agents(h, method="random", n=wl["n"])
+        return env, list(hs)
+    if wl["game"] == "gather":
+        env = magent.GridWorld(pc.gather_config(wl["map_size"]), _lib=lib, **kw)
+        env.set_seed(seed0)
+        env.reset()
+        hs = env.get_handles()
+        gather_map(env, wl["map_size"], hs[0], hs[1])
+        return env, [hs[1]]
+    raise ValueError(wl["game"])
+
+
+def gather_map(env, map_size, food_handle, agent_handle):
+    """square rings of agents and food as in examples/train_gather.py:46-77 (legend omitted)"""
+    cx = cy = map_size // 2
+
+    def add_square(pos, side, gap):
+        side = int(side)
+        for x in range(cx - side // 2, cx + side // 2 + 1, gap):
+            pos.append([x, cy - side // 2]); pos.append([x, cy + side // 2])
+        for y in range(cy - side // 2, cy + side // 2 + 1, gap):
+            pos.append([cx - side // 2, y]); pos.append([cx + side // 2, y])
+    pos = []
+    for frac, gap in ((0.9, 3), (0.8, 4), (0.7, 6)):
+        add_square(pos, map_size * frac, gap)
+    env.add_agents(agent_handle, method="custom", pos=pos)
+    pos = []
+    for frac, gap in ((0.65, 10), (0.6, 10), (0.55, 10), (0.5, 4), (0.45, 3), (0.4, 1), (0.3, 1)):
+        add_square(pos, map_size * frac, gap)
+    for d in (2, 4, 6):
+        add_square(pos, map_size * 0.3 - d, 1)
+    env.add_agents(food_handle, method="custom", pos=pos)
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_worker(args):
+    """child process: run the reference (or the C restatement) for --cpu-steps and print agent-steps, seconds"""
+    import numpy as np
+    wl = WORKLOADS[args.workload]
+    lib = REF_LIB if os.path.exists(REF_LIB) else PORT_LIB
+    env, act = build_env(wl, lib, 1, seed0=args.cpu_seed)
+    rs = np.random.RandomState(args.cpu_seed)
+
+    def one():
+        n = 0
+        for h in act:
+            env.get_observation(h)
+        for h in act:
+            k = env.get_num(h)
+            env.set_action(h, rs.randint(0, env.get_action_space(h)[0], size=k).astype(np.int32))
+            n += k
+        env.step()
+        for h in act:
+            env.get_reward(h)
+        env.clear_dead()
+        return n
+    for _ in range(args.cpu_warmup):
+        one()
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.cpu_steps):
+        total += one()
+    dt = time.perf_counter() - t0
+    print(json.dumps({"agent_steps": total, "seconds": dt}))
+
+
+def run_cpu_baseline(workload, budget_steps=None):
+    """time the reference engine on the host cores: best of {P single-thread processes, 1 process x all
+    OpenMP threads}; every process simulates its own arena of the workload."""
+    cores = os.cpu_count() or 1
+    kind = "reference" if os.path.exists(REF_LIB) else "port"
+    if kind == "port" and not os.path.exists(PORT_LIB):
+        return None
+    wl = WORKLOADS[workload]
+    agents = 2 * wl.get("n", 500)
+    steps = budget_steps or max(3, min(400, int(3.0e6 / max(agents, 1))))
+    warm = max(1, min(20, steps // 5))
+
+    def launch(nproc, omp):
+        env = dict(os.environ, OMP_NUM_THREADS=str(omp))
+        procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--_cpu-worker", "--workload", workload,
+                                   "--cpu-steps", str(steps), "--cpu-warmup", str(warm), "--cpu-seed", str(i)],
+                                  env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 for i in range(nproc)]
+        outs = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in procs]
+        return sum(o["agent_steps"] for o in outs) / max(o["seconds"] for o in outs)
+    multi = launch(cores, 1)
+    single = launch(1, cores)
+    best, how = (multi, "%d processes x 1 thread" % cores) if multi >= single else (single, "1 process x %d OpenMP threads" % cores)
+    return {"value": best, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%s: one arena per process, %d timed steps after %d warm-up, best of {%d procs x 1 thread: %.3g, "
+                      "1 proc x %d threads: %.3g} -> %s" % (wl["desc"].split(",")[0] + " " + str(wl["map_size"]), steps, warm,
+                                                             cores, multi, cores, single, how)}
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 7:
+                    continue
+                try:
+                    sm.append(float(p[0])); mx.append(float(p[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, p[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="battle512", choices=sorted(WORKLOADS))
+    ap.add_argument("--arenas", type=int, default=None, help="override arenas per GPU")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--_cpu-worker", dest="cpu_worker", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=100)
+    ap.add_argument("--cpu-warmup", type=int, default=5)
+    ap.add_argument("--cpu-seed", type=int, default=0)
+    args = ap.parse_args()
+    if args.cpu_worker:
+        return cpu_worker(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = dict(WORKLOADS[args.workload])
+    if args.arenas:
+        wl["arenas"] = args.arenas
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = run_cpu_baseline(args.workload, budget_steps=None)
+        if cb is None:
+            print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref nor oracle/_build is built"}))
+            return
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "note": "CPU engine: rate of a bounded sample (one arena per process)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import magent_b200 as magent  # noqa: F401
+    from magent_b200.c_lib import load_library
+    lib = load_library()
+    A = wl["arenas"]
+    t_setup = time.time()
+    env, act = build_env(wl, lib.path, A, seed0=rank * A)
+    handles = env.get_handles()
+    spaces = {env._hv(h): (env.get_view_space(h), env.get_feature_space(h)) for h in handles}
+
+    # device-resident receive buffers, sized for the initial population (it only shrinks)
+    dev = torch.device("cuda", local_rank)
+    bufs = {}
+    for h in act:
+        g = env._hv(h)
+        n0 = env.get_num(h)
+        bufs[g] = (torch.empty((n0,) + spaces[g][0], dtype=torch.float32, device=dev),
+                   torch.empty((n0,) + spaces[g][1], dtype=torch.float32, device=dev),
+                   torch.empty((n0,), dtype=torch.float32, device=dev))
+
+    import ctypes
+
+    def dev_step(seed):
+        for h in act:
+            g = env._hv(h)
+            v, f, _r = bufs[g]
+            ptrs = (ctypes.c_void_p * 2)(v.data_ptr(), f.data_ptr())
+            lib.env_get_observation(env.game, g, ptrs)
+        for h in act:
+            env.set_random_actions(h, seed)
+        env.step()
+        for h in act:
+            g = env._hv(h)
+            lib.env_get_reward(env.game, g, bufs[g][2].data_ptr())
+        env.clear_dead()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        dev_step(1000 + w)
+    setup_s = time.time() - t_setup
+
+    # per-launch algorithmic bytes of the obs-render kernel at the start of the timed region
+    obs_bytes = 0
+    for h in act:
+        g = env._hv(h)
+        (vh, vw, vc), (fs,) = spaces[g]
+        obs_bytes += env.get_num(h) * 4 * (vh * vw * vc + fs) + A * wl["map_size"] ** 2 * 4
+    obs_bytes_per_launch = obs_bytes / len(act)
+
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    c0 = env.get_counters()
+    l0 = env.launch_count()
+    env.set_profiling(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for s in range(args.steps):
+        dev_step(s)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    obs_ms, obs_launches = env.get_profile()
+    env.set_profiling(False)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    c1 = env.get_counters()
+    launches = env.launch_count() - l0
+    agent_steps = c1[0] - c0[0]
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([agent_steps, launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)          # max over ranks of the device time
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)        # NCCL over NVLink: throughput counters only
+    ms_max = float(t.item())
+    total_steps, total_launches = int(cnt[0].item()), int(cnt[1].item())
+    value = total_steps / (ms_max * 1e-3)
+
+    # ---- end-to-end: host (pinned) buffers through the public API, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(3, args.steps // 4)
+        pools = {}
+        rs = np.random.RandomState(rank)
+        for h in act:
+            pools[env._hv(h)] = rs.randint(0, env.get_action_space(h)[0], size=env.get_num(h)).astype(np.int32)
+
+        def host_step():
+            h2d = d2h = 0
+            for h in act:
+                v, f = env.get_observation(h)
+                d2h += v.nbytes + f.nbytes
+            for h in act:
+                a = pools[env._hv(h)][:env.get_num(h)]
+                env.set_action(h, a)
+                h2d += a.nbytes
+            env.step()
+            d2h += 4
+            for h in act:
+                d2h += env.get_reward(h).nbytes
+            env.clear_dead()
+            return h2d, d2h
+        host_step()                                     # allocates the pinned receive buffers
+        barrier()
+        c0 = env.get_counters()
+        t0 = time.perf_counter()
+        hb = db = 0
+        for _ in range(e2e_steps):
+            a, b = host_step()
+            hb += a; db += b
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        c1 = env.get_counters()
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        cnt = torch.tensor([c1[0] - c0[0], hb, db], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        e2e = {"value": int(cnt[0].item()) / float(t.item()), "unit": UNIT, "steps": e2e_steps,
+               "h2d_bytes_per_step": int(cnt[1].item()) // e2e_steps, "d2h_bytes_per_step": int(cnt[2].item()) // e2e_steps,
+               "timing": "host wall clock around the API loop (includes PCIe copies and syncs), max over ranks",
+               "host_buffers": "page-locked numpy arrays owned by the wrapper"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = (obs_bytes_per_launch / (obs_ms / obs_launches * 1e-3)) / 1e9 if obs_launches and obs_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "obs_render_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("workload") == args.workload:
+            traffic = tj.get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "obs_render_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": obs_bytes_per_launch,
+                "mean_launch_ms": (obs_ms / obs_launches) if obs_launches else None, "launches_timed": obs_launches,
+                "kernel_share_of_step": (obs_ms / ms) if ms > 0 else None}
+
+    cpu = None
+    if args.gpus == 1 and world == 1 and not args.no_cpu:
+        cpu = run_cpu_baseline(args.workload)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "arenas_per_gpu": A, "agents_per_arena_at_start": 2 * wl.get("n", 0) or None,
+                   "buffers": "device-resident (CUDA pointers through the C ABI)", "actions": "uniform random, generated on device",
+                   "l2": "per-step observation output (%.0f MB) exceeds the 126 MB L2" % (obs_bytes / 1e6) if obs_bytes > 126e6
+                         else "per-step output %.1f MB fits L2 (latency-bound workload)" % (obs_bytes / 1e6),
+                   "parallelism": "arena-sharded x%d, no data-path collective" % world, "setup_seconds": round(setup_s, 2)},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": total_launches, "clocks": clocks,
+        "agent_steps_timed": total_steps,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
