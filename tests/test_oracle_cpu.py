@@ -136,3 +136,23 @@ def test_kat_shuffle_decides_mutual_kill(olib):
         r = env.get_reward(h[1])
         np.testing.assert_allclose(sorted(r.tolist()), [-1.0, -0.11], atol=1e-6)
     assert got == [[True, False], [False, True], [False, True], [False, True]]
+
+
+@pytest.mark.parametrize("game", ["forest", "double_attack"])
+def test_port_matches_reference_beyond_golden(game):
+    """the restatement's general rule evaluator (two free symbols in double_attack) vs the compiled reference"""
+    if not (os.path.exists(pc.REF_LIB) and os.path.exists(pc.PORT_LIB)):
+        pytest.skip("needs both oracle libraries")
+    import magent_b200 as magent
+
+    def make(lib):
+        env = magent.GridWorld(game, map_size=30, _lib=lib)
+        env.set_seed(3)
+        env.reset()
+        h = env.get_handles()
+        env.add_agents(h[0], method="random", n=120)
+        env.add_agents(h[1], method="random", n=60)
+        return env
+    a = pc.run_trace(make(pc.REF_LIB), 60, 3, keep_obs=True)
+    b = pc.run_trace(make(pc.PORT_LIB), 60, 3, keep_obs=True)
+    pc.compare_traces(a, b, game)
