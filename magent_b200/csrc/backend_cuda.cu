@@ -15,6 +15,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string>
+#include <string.h>
+#include <vector>
 
 #include "backend.h"
 #include "obs_phases.h"
@@ -35,9 +37,8 @@ namespace be {
 static int g_device = -1, g_sms = 0;
 static long long g_launches = 0;
 static bool g_profile = false;
-static cudaEvent_t g_ev0, g_ev1;
-static double g_obs_ms = 0.0;
-static long long g_obs_launches = 0;
+static std::vector<cudaEvent_t> g_events;     // pairs recorded around obs-render launches
+static size_t g_events_used = 0;
 
 const char *name() { return "cuda-sm_100a"; }
 
@@ -84,12 +85,26 @@ bool is_device_ptr(const void *p) {
 }
 void sync() { CUDA_CHECK(cudaDeviceSynchronize()); }
 long long launch_count() { return g_launches; }
-void profile_enable(bool on) {
-    if (on && !g_profile) { CUDA_CHECK(cudaEventCreate(&g_ev0)); CUDA_CHECK(cudaEventCreate(&g_ev1)); }
-    g_profile = on;
-    g_obs_ms = 0.0; g_obs_launches = 0;
+void profile_enable(bool on) { g_profile = on; g_events_used = 0; }
+static void profile_pair(cudaEvent_t *e0, cudaEvent_t *e1) {
+    if (g_events_used + 2 > g_events.size()) {
+        for (int i = 0; i < 64; ++i) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); g_events.push_back(e); }
+    }
+    *e0 = g_events[g_events_used]; *e1 = g_events[g_events_used + 1];
+    g_events_used += 2;
 }
-void profile_read(double *ms, long long *n) { *ms = g_obs_ms; *n = g_obs_launches; }
+// total device time of the obs-render launches recorded since profile_enable(true); no sync was added
+// to the timed region: the events are read here, after the fact
+void profile_read(double *ms, long long *n) {
+    double total = 0.0;
+    for (size_t i = 0; i + 1 < g_events_used; i += 2) {
+        CUDA_CHECK(cudaEventSynchronize(g_events[i + 1]));
+        float t = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&t, g_events[i], g_events[i + 1]));
+        total += t;
+    }
+    *ms = total; *n = (long long)(g_events_used / 2);
+}
 
 static void post_launch(const char *what) {
     ++g_launches;
@@ -446,94 +461,178 @@ void launch_minimap(const EngineDev *dE, const EngineDev &hE, unsigned curmask, 
 // ------------------------------------------------------------------------------------------------
 // obs_render_kernel: the observation gather (GridWorld.cc:292-401 + Map::extract_view Map.cc:129-207).
 //
-// One CTA composes a tile of OBS_TA consecutive agents of the ABI concatenation in shared memory
-// (each warp one agent at a time, each lane one view cell: n_channel floats, stride n_channel words =>
-// conflict-free for odd channel counts) and streams the tile out with 16-byte coalesced stores; the
-// tile's byte range in the output is contiguous and 16-byte aligned because OBS_TA % 4 == 0.
-// Algorithmic traffic per agent: 4*(view_h*view_w*n_channel + feature) bytes written.
+// Persistent CTAs walk tiles of OBS_TA consecutive agents of the ABI concatenation.  A tile is composed
+// in shared memory -- block-wide 16-byte zero fill, then each warp renders one agent: every lane owns
+// view cells lane, lane+32, ... and scatters only the non-zero floats (minimap channels, wall/agent/hp
+// channels; n_channel-word stride => conflict-free for odd channel counts) -- and leaves the SM as ONE
+// TMA bulk store (cp.async.bulk.global.shared::cta, SASS UBLKCP) from a double-buffered tile, so the
+// store of tile k overlaps the composition of tile k+1 and costs no LSU issue slots.  A tile's byte range
+// in the output is contiguous and 16-byte aligned because OBS_TA % 4 == 0.
+// Algorithmic traffic per agent: 4*(view_h*view_w*n_channel + feature) bytes written, plus one
+// compulsory read of the occupancy plane per arena.  No tensor cores: there is no
+// contraction on this path.
 constexpr int OBS_THREADS = 256;
+constexpr int OBS_WARPS = OBS_THREADS / 32;
 constexpr int OBS_TA = 8;
 
-struct ObsHdr { int a, x, y, cx, cy, i; };
+struct ObsGroupP { const float *hp; int cap; float max_hp; int ch; };
+struct ObsParams {
+    int A, W, H, G, C;
+    int vw, vh, cells, rec, F;
+    int ox, oy;                      // map offset of view cell (0,0) from the agent position
+    int scale_w, scale_h, minimap;
+    int cap, embedding, n_action, n_total;
+    const unsigned char *mask;
+    const int *off, *occ;
+    const int *x, *y, *id, *act;
+    const float *last_reward;
+    const float *mm;                 // [A][G][cells] normalised minimap, or nullptr
+    float *view, *feature;
+    int mm_ch[MG_MAX_GROUPS];        // observation channel of group j's minimap
+    ObsGroupP grp[MG_MAX_GROUPS];
+};
 
-__global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const EngineDev *gE, ObsArgs O, const float *mm_val, int n_total) {
-    extern __shared__ __align__(16) float tile[];
-    __shared__ EngineDev sE;
-    __shared__ ObsHdr hdr[OBS_TA];
-    load_engine(&sE, gE);
-    const EngineDev &E = sE;
-    const int g = O.group;
-    const GroupDev &G = E.grp[g];
-    const int cells = G.view_w * G.view_h, C = E.n_channel, rec = cells * C, F = G.feature_size;
-    const int *off = E.off + (size_t)g * (E.A + 1);
-    const AgentSoA &s = E.grp[g].soa[(O.curmask >> g) & 1u];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = OBS_THREADS / 32;
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-    for (int t0 = blockIdx.x * OBS_TA; t0 < n_total; t0 += gridDim.x * OBS_TA) {
-        const int cnt = min(OBS_TA, n_total - t0);
-        if (threadIdx.x < cnt) {
-            int o = t0 + threadIdx.x;
-            int a = E.A == 1 ? 0 : locate_arena(off, E.A, o);
-            int i = o - off[a];
-            long gi = (long)a * G.cap + i;
-            ObsHdr h;
-            h.a = a; h.i = i; h.x = s.x[gi]; h.y = s.y[gi];
-            h.cx = -1; h.cy = -1;
-            if (mm_val) minimap_cell(E, G.view_w, G.view_h, h.x, h.y, h.cx, h.cy);
-            hdr[threadIdx.x] = h;
+__global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_constant__ ObsParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tile_floats = OBS_TA * P.rec;                   // multiple of 8 floats => 32-byte multiple
+    int *lut = (int *)((float *)smem_raw + 2 * tile_floats);  // per view cell: packed (dy << 16 | dx), masked = far out
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (int cell = threadIdx.x; cell < P.cells; cell += OBS_THREADS) {
+        int vy = cell / P.vw, vx = cell - vy * P.vw;
+        int dx = P.mask[cell] ? P.ox + vx : -30000, dy = P.oy + vy;
+        lut[cell] = (int)(((unsigned)dy << 16) | ((unsigned)dx & 0xffffu));
+    }
+    const int n_tiles = (P.n_total + OBS_TA - 1) / OBS_TA;
+    int a_cached = 0;
+    int k = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+        float *buf = (float *)smem_raw + (k & 1) * tile_floats;
+        const int t0 = tile * OBS_TA;
+        const int cnt = min(OBS_TA, P.n_total - t0);
+        // the bulk store that last read this buffer (issued two tiles ago) must have finished reading
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+        {   // zero fill
+            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 *b4 = (float4 *)buf;
+            for (int q = threadIdx.x; q < (cnt * P.rec + 3) / 4; q += OBS_THREADS) b4[q] = z;
         }
         __syncthreads();
-        for (int ag = warp; ag < cnt; ag += nwarp) {
-            const ObsHdr h = hdr[ag];
-            const float *mm = mm_val ? mm_val + (size_t)h.a * E.G * cells : nullptr;
-            float *dst = tile + (size_t)ag * rec;
-            for (int cell = lane; cell < cells; cell += 32) {
-                int vy = cell / G.view_w, vx = cell - vy * G.view_w;
-                obs_compose_cell(E, O.curmask, h.a, g, h.x, h.y, h.cx, h.cy, vy, vx, mm, dst + cell * C);
+        for (int ag = warp; ag < cnt; ag += OBS_WARPS) {
+            const int o = t0 + ag;
+            int a = 0;
+            if (P.A > 1) {
+                a = a_cached;
+                if (!(P.off[a] <= o && o < P.off[a + 1])) a = locate_arena(P.off, P.A, o);
+                a_cached = a;
+            }
+            const int i = o - P.off[a];
+            const long gi = (long)a * P.cap + i;
+            const int ax = P.x[gi], ay = P.y[gi];
+            int self_cell = -1;
+            if (P.minimap) self_cell = (ay / P.scale_h) * P.vw + ax / P.scale_w;
+            const int *occ = P.occ + (long)a * P.W * P.H;
+            const float *mm = P.mm + (long)a * P.G * P.cells;
+            float *dst = buf + ag * P.rec;
+            for (int cell = lane; cell < P.cells; cell += 32) {
+                float *px = dst + cell * P.C;
+                if (P.minimap) {
+                    for (int j = 0; j < P.G; ++j) {
+                        float v = mm[j * P.cells + cell];
+                        if (cell == self_cell) v += 1.0f;                      // GridWorld.cc:382
+                        px[P.mm_ch[j]] = v;
+                    }
+                }
+                const int l = lut[cell];
+                const int x = ax + (int)(short)(l & 0xffff), y = ay + (l >> 16);
+                if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) {
+                    const int t = occ[y * P.W + x];
+                    if (t == OCC_WALL) px[0] = 1.0f;
+                    else if (t >= 0) {
+                        const ObsGroupP &T = P.grp[code_group(t)];
+                        px[T.ch] = 1.0f;
+                        px[T.ch + 1] = T.hp[(long)a * T.cap + code_index(t)] / T.max_hp;   // Map.cc:197
+                    }
+                }
+            }
+            // non-spatial features straight to global memory (GridWorld.cc:386-396)
+            for (int f = lane; f < P.F; f += 32) {
+                float v = 0.0f;
+                if (f < P.embedding) v = f < 31 ? (float)((P.id[gi] >> f) & 1) : 0.0f;
+                else {
+                    int kk = f - P.embedding;
+                    if (kk < P.n_action) v = kk == P.act[gi] ? 1.0f : 0.0f;
+                    else if (kk == P.n_action) v = P.last_reward[gi];
+                    else if (P.minimap && kk == P.n_action + 1) v = (float)ax / (float)P.W;
+                    else if (P.minimap && kk == P.n_action + 2) v = (float)ay / (float)P.H;
+                }
+                P.feature[(size_t)o * P.F + f] = v;
             }
         }
-        // features go straight to global memory, element-wise (coalesced)
-        for (int q = threadIdx.x; q < cnt * F; q += OBS_THREADS) {
-            int ag = q / F, k = q - ag * F;
-            O.feature[(size_t)(t0 + ag) * F + k] = obs_feature_elem(E, O.curmask, hdr[ag].a, g, hdr[ag].i, k);
-        }
+        // make the generic-proxy writes visible to the async proxy, then one thread fires the bulk store
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        // stream the tile out
-        float *gout = O.view + (size_t)t0 * rec;
-        const int nflt = cnt * rec;
-        if ((((size_t)gout) & 15) == 0) {
-            const int nv = nflt >> 2;
-            const float4 *src4 = (const float4 *)tile;
-            float4 *dst4 = (float4 *)gout;
-            for (int q = threadIdx.x; q < nv; q += OBS_THREADS) __stcs(dst4 + q, src4[q]);
-            for (int q = (nv << 2) + threadIdx.x; q < nflt; q += OBS_THREADS) __stcs(gout + q, tile[q]);
-        } else {
-            for (int q = threadIdx.x; q < nflt; q += OBS_THREADS) __stcs(gout + q, tile[q]);
+        float *gout = P.view + (size_t)t0 * P.rec;
+        const unsigned bytes = (unsigned)cnt * (unsigned)P.rec * 4u;
+        if ((bytes & 15u) == 0 && (((size_t)gout) & 15) == 0) {
+            if (threadIdx.x == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(gout), "r"(smem_u32(buf)), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {                                   // ragged last tile / unaligned caller buffer
+            for (int q = threadIdx.x; q < cnt * P.rec; q += OBS_THREADS) __stcs(gout + q, buf[q]);
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        __syncthreads();
     }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-void launch_obs(const EngineDev *dE, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total) {
-    const GroupDev &G = hE.grp[O.group];
-    const size_t smem = (size_t)OBS_TA * G.view_w * G.view_h * hE.n_channel * sizeof(float);
+void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total) {
+    const int g = O.group;
+    const GroupDev &G = hE.grp[g];
+    ObsParams P;
+    memset(&P, 0, sizeof P);
+    P.A = hE.A; P.W = hE.W; P.H = hE.H; P.G = hE.G; P.C = hE.n_channel;
+    P.vw = G.view_w; P.vh = G.view_h; P.cells = G.view_w * G.view_h; P.rec = P.cells * P.C; P.F = G.feature_size;
+    P.ox = G.view_xoff + G.view_x1; P.oy = G.view_yoff + G.view_y1;
+    P.scale_w = (hE.W + G.view_w - 1) / G.view_w; P.scale_h = (hE.H + G.view_h - 1) / G.view_h;
+    P.minimap = mm_val != nullptr;
+    P.cap = G.cap; P.embedding = hE.embedding_size; P.n_action = G.n_action; P.n_total = n_total;
+    P.mask = G.view_mask;
+    P.off = hE.off + (size_t)g * (hE.A + 1);
+    P.occ = hE.occ;
+    const AgentSoA &s = G.soa[(O.curmask >> g) & 1u];
+    P.x = s.x; P.y = s.y; P.id = s.id; P.act = s.act; P.last_reward = s.last_reward;
+    P.mm = mm_val; P.view = O.view; P.feature = O.feature;
+    const int stride = 2 + (hE.minimap_mode ? 1 : 0);
+    for (int j = 0; j < hE.G; ++j) {
+        int rel = j - g; if (rel < 0) rel += hE.G;
+        const int ch = hE.channel_base + rel * stride;                 // make_channel_trans, GridWorld.cc:897-913
+        P.mm_ch[j] = ch + 2;
+        P.grp[j].hp = hE.grp[j].soa[(O.curmask >> j) & 1u].hp;
+        P.grp[j].cap = hE.grp[j].cap; P.grp[j].max_hp = hE.grp[j].max_hp; P.grp[j].ch = ch;
+    }
+    const size_t smem = (size_t)2 * OBS_TA * P.rec * sizeof(float) + (size_t)P.cells * sizeof(int);
     static size_t configured = 0;
-    if (smem > configured) {
+    static int ctas_per_sm = 1;
+    if (smem > 227 * 1024) mg::fatal("observation record too large for the render kernel (%zu bytes of shared memory)", smem);
+    if (smem != configured) {
         CUDA_CHECK(cudaFuncSetAttribute(obs_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, obs_render_kernel, OBS_THREADS, smem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
         configured = smem;
     }
-    int tiles = (n_total + OBS_TA - 1) / OBS_TA;
-    int grid = tiles < 16 * g_sms ? tiles : 16 * g_sms;
-    if (g_profile) CUDA_CHECK(cudaEventRecord(g_ev0, 0));
-    obs_render_kernel<<<grid, OBS_THREADS, smem>>>(dE, O, mm_val, n_total);
+    const int tiles = (n_total + OBS_TA - 1) / OBS_TA;
+    const int grid = tiles < ctas_per_sm * g_sms ? tiles : ctas_per_sm * g_sms;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_profile) { profile_pair(&e0, &e1); CUDA_CHECK(cudaEventRecord(e0, 0)); }
+    obs_render_kernel<<<grid, OBS_THREADS, smem>>>(P);
     post_launch("obs_render_kernel");
-    if (g_profile) {
-        CUDA_CHECK(cudaEventRecord(g_ev1, 0));
-        CUDA_CHECK(cudaEventSynchronize(g_ev1));
-        float ms = 0;
-        CUDA_CHECK(cudaEventElapsedTime(&ms, g_ev0, g_ev1));
-        g_obs_ms += ms; ++g_obs_launches;
-    }
+    if (g_profile) CUDA_CHECK(cudaEventRecord(e1, 0));
 }
 
 }  // namespace be

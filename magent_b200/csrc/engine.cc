@@ -134,7 +134,6 @@ void Engine::register_agent_type(const char *name, int n, const char **keys, flo
     if (types_.count(str)) fatal("duplicated name of agent type in GridWorld::register_agent_type : %s", name);
     AgentTypeDef t;
     t.name = str;
-    float view_x_offset = 0, view_y_offset = 0, att_x_offset = 0, att_y_offset = 0, turn_x = 0, turn_y = 0;
     for (int i = 0; i < n; i++) {                     // AgentType.cc:52-83
         const char *k = keys[i];
         float v = values[i];
@@ -152,15 +151,11 @@ void Engine::register_agent_type(const char *name, int n, const char **keys, flo
 #undef MG_SET_INT
 #undef MG_SET_FLT
 #undef MG_SET_BOOL
-        if (strequ(k, "view_x_offset")) { view_x_offset = v; continue; }
-        if (strequ(k, "view_y_offset")) { view_y_offset = v; continue; }
-        if (strequ(k, "att_x_offset")) { att_x_offset = v; continue; }
-        if (strequ(k, "att_y_offset")) { att_y_offset = v; continue; }
-        if (strequ(k, "turn_x_offset")) { turn_x = v; continue; }
-        if (strequ(k, "turn_y_offset")) { turn_y = v; continue; }
+        // accepted but overwritten by the reference too (AgentType.cc:106-108)
+        if (strequ(k, "view_x_offset") || strequ(k, "view_y_offset") || strequ(k, "att_x_offset") ||
+            strequ(k, "att_y_offset") || strequ(k, "turn_x_offset") || strequ(k, "turn_y_offset")) continue;
         fatal("invalid agent config in AgentType::AgentType : %s", k);
     }
-    (void)view_x_offset; (void)view_y_offset; (void)att_x_offset; (void)att_y_offset; (void)turn_x; (void)turn_y;
     if (t.can_absorb) fatal("can_absorb agent types are not supported by the B200 engine yet (SURVEY.md §8f rank 1)");
     if (t.width < 1 || t.length < 1 || t.width * t.length > 16) fatal("unsupported body size %dx%d", t.width, t.length);
 
