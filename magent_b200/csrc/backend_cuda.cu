@@ -248,7 +248,8 @@ __device__ __forceinline__ void load_engine(EngineDev *sE, const EngineDev *gE) 
     __syncthreads();
 }
 
-constexpr int STEP_THREADS = 512;
+constexpr int STEP_THREADS = 1024;      // launch bound; the launch picks 256..1024 (step_block_size)
+constexpr int GRID_THREADS = 512;       // block size of the cooperative whole-grid team
 
 __global__ void __launch_bounds__(STEP_THREADS) step_kernel_cta(const EngineDev *gE, StepArgs S) {
     __shared__ EngineDev sE;
@@ -284,9 +285,17 @@ __global__ void __launch_bounds__(STEP_THREADS) cull_kernel_grid(const EngineDev
 
 static const int GRID_MODE_THRESHOLD = 32768;    // agents per arena above which the whole grid teams up
 
+// CTA-per-arena block size: the phases are latency-bound loops over the arena's agents, so with many
+// arenas we want many (small) CTAs resident per SM; with few arenas the single CTA should be wide.
+static int step_block_size(int arenas, int max_agents) {
+    if (arenas >= 2 * g_sms) return 256;
+    if (max_agents >= 768) return 1024;
+    return max_agents >= 384 ? 512 : 256;
+}
+
 static int coop_grid(const void *kernel) {
     int per_sm = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, STEP_THREADS, 0));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GRID_THREADS, 0));
     if (per_sm < 1) mg::fatal("cooperative kernel does not fit on an SM");
     int g = per_sm * g_sms;
     return g > 4096 ? 4096 : g;
@@ -297,11 +306,11 @@ void launch_step(const EngineDev *dE, const EngineDev &hE, const StepArgs &S, in
         int grid = coop_grid((const void *)step_kernel_grid);
         StepArgs s = S;
         void *args[] = {(void *)&dE, (void *)&s};
-        CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)step_kernel_grid, dim3(grid), dim3(STEP_THREADS), args, 0, 0));
+        CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)step_kernel_grid, dim3(grid), dim3(GRID_THREADS), args, 0, 0));
         post_launch("step_kernel_grid");
     } else {
         int grid = hE.A < 8 * g_sms ? hE.A : 8 * g_sms;
-        step_kernel_cta<<<grid, STEP_THREADS>>>(dE, S);
+        step_kernel_cta<<<grid, step_block_size(hE.A, max_agents)>>>(dE, S);
         post_launch("step_kernel_cta");
     }
 }
@@ -310,11 +319,11 @@ void launch_cull(const EngineDev *dE, const EngineDev &hE, unsigned curmask, int
     if (max_agents > GRID_MODE_THRESHOLD) {
         int grid = coop_grid((const void *)cull_kernel_grid);
         void *args[] = {(void *)&dE, (void *)&curmask};
-        CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)cull_kernel_grid, dim3(grid), dim3(STEP_THREADS), args, 0, 0));
+        CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)cull_kernel_grid, dim3(grid), dim3(GRID_THREADS), args, 0, 0));
         post_launch("cull_kernel_grid");
     } else {
         int grid = hE.A < 8 * g_sms ? hE.A : 8 * g_sms;
-        cull_kernel_cta<<<grid, STEP_THREADS>>>(dE, curmask);
+        cull_kernel_cta<<<grid, step_block_size(hE.A, max_agents)>>>(dE, curmask);
         post_launch("cull_kernel_cta");
     }
 }
@@ -461,13 +470,16 @@ void launch_minimap(const EngineDev *dE, const EngineDev &hE, unsigned curmask, 
 // ------------------------------------------------------------------------------------------------
 // obs_render_kernel: the observation gather (GridWorld.cc:292-401 + Map::extract_view Map.cc:129-207).
 //
-// Persistent CTAs walk tiles of OBS_TA consecutive agents of the ABI concatenation.  A tile is composed
-// in shared memory -- block-wide 16-byte zero fill, then each warp renders one agent: every lane owns
-// view cells lane, lane+32, ... and scatters only the non-zero floats (minimap channels, wall/agent/hp
-// channels; n_channel-word stride => conflict-free for odd channel counts) -- and leaves the SM as ONE
-// TMA bulk store (cp.async.bulk.global.shared::cta, SASS UBLKCP) from a double-buffered tile, so the
-// store of tile k overlaps the composition of tile k+1 and costs no LSU issue slots.  A tile's byte range
-// in the output is contiguous and 16-byte aligned because OBS_TA % 4 == 0.
+// Persistent CTAs each own a contiguous run of tiles of OBS_TA consecutive agents of the ABI concatenation.
+// A tile is composed in shared memory: (1) the tile buffer is initialised by 16-byte copies from a tile-sized
+// *template* that already holds the arena's minimap channels (rebuilt only when the CTA enters a new arena; a
+// tile that straddles two arenas falls back to zero fill + per-agent minimap scatter); (2) one warp per agent,
+// one lane per view cell: every lane first issues all its occupancy-plane loads back to back, then scatters
+// only the non-zero floats (wall / agent / hp channels, the +1 self marker; n_channel-word stride =>
+// conflict-free for odd channel counts); (3) the tile leaves the SM as ONE TMA bulk store
+// (cp.async.bulk.global.shared::cta, SASS UBLKCP) from a double-buffered tile, so the store of tile k overlaps
+// the composition of tile k+1 and costs no LSU issue slots.  A tile's byte range in the output is contiguous
+// and 16-byte aligned because OBS_TA % 4 == 0.
 // Algorithmic traffic per agent: 4*(view_h*view_w*n_channel + feature) bytes written, plus one
 // compulsory read of the occupancy plane per arena.  No tensor cores: there is no
 // contraction on this path.
@@ -494,10 +506,22 @@ struct ObsParams {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// q = n / d for 0 <= n < 2^24 and d > 0, given inv = 1.0f / d: float estimate, then exact fix-up
+__device__ __forceinline__ int small_div(int n, int d, float inv) {
+    int q = (int)((float)n * inv);
+    if (q * d > n) --q;
+    else if ((q + 1) * d <= n) ++q;
+    return q;
+}
+
+constexpr int OBS_NIT = 8;           // view cells per lane handled in one unrolled batch (8*32 = 256 cells)
+
 __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_constant__ ObsParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tile_floats = OBS_TA * P.rec;                   // multiple of 8 floats => 32-byte multiple
-    int *lut = (int *)((float *)smem_raw + 2 * tile_floats);  // per view cell: packed (dy << 16 | dx), masked = far out
+    float *tmpl = (float *)smem_raw;                          // one tile of records holding only the arena's minimap
+    float *buf_base = tmpl + tile_floats;                     // two tiles: double buffer for the bulk stores
+    int *lut = (int *)(buf_base + 2 * tile_floats);           // per view cell: packed (dy << 16 | dx); masked cells point far out
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     for (int cell = threadIdx.x; cell < P.cells; cell += OBS_THREADS) {
@@ -505,53 +529,106 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
         int dx = P.mask[cell] ? P.ox + vx : -30000, dy = P.oy + vy;
         lut[cell] = (int)(((unsigned)dy << 16) | ((unsigned)dx & 0xffffu));
     }
+    // contiguous block of tiles per CTA: consecutive tiles stay inside one arena most of the time
     const int n_tiles = (P.n_total + OBS_TA - 1) / OBS_TA;
-    int a_cached = 0;
+    const int per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int tile_lo = blockIdx.x * per_cta, tile_hi = min(n_tiles, tile_lo + per_cta);
+    const float inv_sw = 1.0f / (float)P.scale_w, inv_sh = 1.0f / (float)P.scale_h;
+    int a_cur = 0, a_lo = 0, a_hi = 0;                        // arena of the tile's first agent and its [lo, hi) range
+    int tmpl_arena = -1;
     int k = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
-        float *buf = (float *)smem_raw + (k & 1) * tile_floats;
+    for (int tile = tile_lo; tile < tile_hi; ++tile, ++k) {
+        float *buf = buf_base + (k & 1) * tile_floats;
         const int t0 = tile * OBS_TA;
         const int cnt = min(OBS_TA, P.n_total - t0);
+        if (t0 >= a_hi || t0 < a_lo) {
+            a_cur = P.A == 1 ? 0 : locate_arena(P.off, P.A, t0);
+            a_lo = P.off[a_cur]; a_hi = P.off[a_cur + 1];
+        }
+        const bool uniform = t0 + cnt <= a_hi;                // whole tile inside arena a_cur
+        const bool use_tmpl = P.minimap && uniform;
         // the bulk store that last read this buffer (issued two tiles ago) must have finished reading
         if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (use_tmpl && tmpl_arena != a_cur) {                // (block-uniform) rebuild the minimap template
+            __syncthreads();
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = threadIdx.x; q < tile_floats / 4; q += OBS_THREADS) ((float4 *)tmpl)[q] = z;
+            __syncthreads();
+            const float *mm = P.mm + (long)a_cur * P.G * P.cells;
+            const int per_slot = P.G * P.cells;
+            for (int q = threadIdx.x; q < OBS_TA * per_slot; q += OBS_THREADS) {
+                int slot = q / per_slot, r = q - slot * per_slot;
+                int j = r / P.cells, cell = r - j * P.cells;
+                tmpl[slot * P.rec + cell * P.C + P.mm_ch[j]] = mm[r];
+            }
+            tmpl_arena = a_cur;
+        }
         __syncthreads();
-        {   // zero fill
-            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 *b4 = (float4 *)buf;
-            for (int q = threadIdx.x; q < (cnt * P.rec + 3) / 4; q += OBS_THREADS) b4[q] = z;
+        if (use_tmpl) {
+            const float4 *s4 = (const float4 *)tmpl;
+            float4 *d4 = (float4 *)buf;
+            for (int q = threadIdx.x; q < tile_floats / 4; q += OBS_THREADS) d4[q] = s4[q];
+        } else {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = threadIdx.x; q < tile_floats / 4; q += OBS_THREADS) ((float4 *)buf)[q] = z;
         }
         __syncthreads();
         for (int ag = warp; ag < cnt; ag += OBS_WARPS) {
             const int o = t0 + ag;
-            int a = 0;
-            if (P.A > 1) {
-                a = a_cached;
-                if (!(P.off[a] <= o && o < P.off[a + 1])) a = locate_arena(P.off, P.A, o);
-                a_cached = a;
-            }
-            const int i = o - P.off[a];
-            const long gi = (long)a * P.cap + i;
+            int a = a_cur, lo = a_lo;
+            if (o >= a_hi) { a = locate_arena(P.off, P.A, o); lo = P.off[a]; }
+            const long gi = (long)a * P.cap + (o - lo);
             const int ax = P.x[gi], ay = P.y[gi];
-            int self_cell = -1;
-            if (P.minimap) self_cell = (ay / P.scale_h) * P.vw + ax / P.scale_w;
             const int *occ = P.occ + (long)a * P.W * P.H;
-            const float *mm = P.mm + (long)a * P.G * P.cells;
             float *dst = buf + ag * P.rec;
-            for (int cell = lane; cell < P.cells; cell += 32) {
-                float *px = dst + cell * P.C;
-                if (P.minimap) {
-                    for (int j = 0; j < P.G; ++j) {
-                        float v = mm[j * P.cells + cell];
-                        if (cell == self_cell) v += 1.0f;                      // GridWorld.cc:382
-                        px[P.mm_ch[j]] = v;
+            // issue this lane's occupancy loads back to back, then consume them
+            int tcode[OBS_NIT];
+#pragma unroll
+            for (int it = 0; it < OBS_NIT; ++it) {
+                const int cell = it * 32 + lane;
+                tcode[it] = OCC_EMPTY;
+                if (cell < P.cells) {
+                    const int l = lut[cell];
+                    const int x = ax + (int)(short)(l & 0xffff), y = ay + (l >> 16);
+                    if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) tcode[it] = __ldg(occ + y * P.W + x);
+                }
+            }
+            for (int base = OBS_NIT * 32; base < P.cells; base += 32) {        // views wider than 256 cells
+                const int cell = base + lane;
+                if (cell < P.cells) {
+                    const int l = lut[cell];
+                    const int x = ax + (int)(short)(l & 0xffff), y = ay + (l >> 16);
+                    if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) {
+                        const int t = __ldg(occ + y * P.W + x);
+                        float *px = dst + cell * P.C;
+                        if (t == OCC_WALL) px[0] = 1.0f;
+                        else if (t >= 0) {
+                            const ObsGroupP &T = P.grp[code_group(t)];
+                            px[T.ch] = 1.0f;
+                            px[T.ch + 1] = T.hp[(long)a * T.cap + code_index(t)] / T.max_hp;
+                        }
                     }
                 }
-                const int l = lut[cell];
-                const int x = ax + (int)(short)(l & 0xffff), y = ay + (l >> 16);
-                if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) {
-                    const int t = occ[y * P.W + x];
+            }
+            if (P.minimap) {
+                const int self_cell = small_div(ay, P.scale_h, inv_sh) * P.vw + small_div(ax, P.scale_w, inv_sw);
+                if (!use_tmpl) {                                   // tile straddles arenas: no template
+                    const float *mm = P.mm + (long)a * P.G * P.cells;
+                    for (int r = lane; r < P.G * P.cells; r += 32) {
+                        int j = r / P.cells, cell = r - j * P.cells;
+                        dst[cell * P.C + P.mm_ch[j]] = mm[r];
+                    }
+                    __syncwarp();
+                }
+                if (lane < P.G) dst[self_cell * P.C + P.mm_ch[lane]] += 1.0f;           // GridWorld.cc:382
+            }
+#pragma unroll
+            for (int it = 0; it < OBS_NIT; ++it) {
+                const int t = tcode[it];
+                if (t != OCC_EMPTY) {
+                    float *px = dst + (it * 32 + lane) * P.C;
                     if (t == OCC_WALL) px[0] = 1.0f;
-                    else if (t >= 0) {
+                    else {
                         const ObsGroupP &T = P.grp[code_group(t)];
                         px[T.ch] = 1.0f;
                         px[T.ch + 1] = T.hp[(long)a * T.cap + code_index(t)] / T.max_hp;   // Map.cc:197
@@ -616,7 +693,7 @@ void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const 
         P.grp[j].hp = hE.grp[j].soa[(O.curmask >> j) & 1u].hp;
         P.grp[j].cap = hE.grp[j].cap; P.grp[j].max_hp = hE.grp[j].max_hp; P.grp[j].ch = ch;
     }
-    const size_t smem = (size_t)2 * OBS_TA * P.rec * sizeof(float) + (size_t)P.cells * sizeof(int);
+    const size_t smem = (size_t)3 * OBS_TA * P.rec * sizeof(float) + (size_t)P.cells * sizeof(int);
     static size_t configured = 0;
     static int ctas_per_sm = 1;
     if (smem > 227 * 1024) mg::fatal("observation record too large for the render kernel (%zu bytes of shared memory)", smem);

@@ -81,20 +81,26 @@ struct ArenaHdr {
     float grp_reward[MG_MAX_GROUPS];
 };
 
-struct RuleInstr {           // postfix program over the bound (subject, object) pair
+// entity roles inside a rule: 0 = subject A, 1 = object inferred from A's op_obj,
+//                             2 = subject B, 3 = object inferred from B's op_obj;  4 = a whole group (receivers)
+enum { ROLE_SUB_A = 0, ROLE_OBJ_A = 1, ROLE_SUB_B = 2, ROLE_OBJ_B = 3, ROLE_GROUP = 4 };
+
+struct RuleInstr {           // postfix program over the bound entities
     unsigned char op;        // EventOp
-    unsigned char role_a;    // 0 = subject, 1 = inferred object
+    unsigned char role_a;    // entity role of the first symbol
     unsigned char role_b;
     unsigned char pad;
     int i0, i1, i2, i3;      // OP_AT: x,y ; OP_IN: x1,y1,x2,y2
 };
 
-struct RuleRecv { int role; int group; float value; };   // role 0 subject, 1 object, 2 whole group
+struct RuleRecv { int role; int group; float value; };
 
 struct RuleDev {
-    int kind;                // 0: scan one 'any' subject, optionally binding its op_obj
-    int sub_group;
-    int has_obj, obj_group, obj_index;      // obj_index -1 = any
+    int kind;                // 0: scan one 'any' subject A;  1: scan all ordered pairs (A, B) of two 'any' subjects
+    int sub_group;           // group of A
+    int has_obj, obj_group, obj_index;      // object bound from A's op_obj; obj_index -1 = any
+    int sub2_group;          // group of B (kind 1)
+    int has_obj2, obj2_group, obj2_index;   // object bound from B's op_obj
     int n_prog; RuleInstr prog[MG_MAX_PROG];
     int n_recv; RuleRecv recv[MG_MAX_RECV];
     int is_terminal;

@@ -275,12 +275,16 @@ void Engine::compile_rules() {
         for (int s : on.related)                      // second pass: the rest
             if (!added.count(s)) { input.push_back(s); infer.push_back(-1); }
 
-        if (input.size() != 1 || symbols_[input[0]].index != -1)
-            fatal("reward rule %d: only rules with a single 'any' subject symbol are supported by the "
-                  "B200 engine yet (got %d input symbols; SURVEY.md §8f rank 1)", (int)ri, (int)input.size());
+        if (input.empty() || input.size() > 2)
+            fatal("reward rule %d: rules binding %d free symbols are not supported by the B200 engine yet "
+                  "(1 or 2 'any' subjects are; SURVEY.md §8f rank 1)", (int)ri, (int)input.size());
+        for (int s : input)
+            if (symbols_[s].index != -1)
+                fatal("reward rule %d: subject symbols must be 'any' for the B200 engine yet ('all' / fixed-index "
+                      "subjects: SURVEY.md §8f rank 1)", (int)ri);
         RuleDev R;
         memset(&R, 0, sizeof R);
-        R.kind = 0;
+        R.kind = input.size() == 2 ? 1 : 0;
         R.sub_group = symbols_[input[0]].group;
         check_group(R.sub_group, "reward rule subject");
         R.has_obj = infer[0] >= 0;
@@ -289,9 +293,23 @@ void Engine::compile_rules() {
             R.obj_index = symbols_[infer[0]].index;
             if (R.obj_index == -2) fatal("reward rule %d: the object of attack/kill/collide cannot be a group", (int)ri);
         }
+        if (R.kind == 1) {
+            R.sub2_group = symbols_[input[1]].group;
+            check_group(R.sub2_group, "reward rule subject");
+            R.has_obj2 = infer[1] >= 0;
+            if (R.has_obj2) {
+                R.obj2_group = symbols_[infer[1]].group;
+                R.obj2_index = symbols_[infer[1]].index;
+                if (R.obj2_index == -2) fatal("reward rule %d: the object of attack/kill/collide cannot be a group", (int)ri);
+            }
+        }
+        // symbol -> entity role.  When both subjects infer the SAME object symbol, the binding made for B
+        // (the inner loop of the reference DFS) overwrites the one made for A (RewardEngine.cc:405-409).
         auto role_of = [&](int sym) -> int {
-            if (sym == input[0]) return 0;
-            if (R.has_obj && sym == infer[0]) return 1;
+            if (sym == input[0]) return ROLE_SUB_A;
+            if (R.kind == 1 && sym == input[1]) return ROLE_SUB_B;
+            if (R.kind == 1 && R.has_obj2 && sym == infer[1]) return ROLE_OBJ_B;
+            if (R.has_obj && sym == infer[0]) return ROLE_OBJ_A;
             fatal("reward rule %d: symbol %d is not bound by the trigger event", (int)ri, sym);
         };
         // postfix lowering of the trigger tree
@@ -321,7 +339,7 @@ void Engine::compile_rules() {
         for (size_t q = 0; q < rd.recv.size(); ++q) {
             RuleRecv rc;
             const SymbolDef &sd = symbols_[rd.recv[q]];
-            if (sd.index == -2) { rc.role = 2; rc.group = sd.group; }
+            if (sd.index == -2) { rc.role = ROLE_GROUP; rc.group = sd.group; }
             else { rc.role = role_of(rd.recv[q]); rc.group = sd.group; }
             rc.value = rd.values[q];
             R.recv[R.n_recv++] = rc;

@@ -472,8 +472,8 @@ MG_HD void phase_move_fill(Ctx &c, const EngineDev &E, const StepArgs &S, int a)
 }
 
 // phase 10: one reward rule (RewardEngine.cc:216-443 restricted to the shapes the rule compiler accepts:
-// a single 'any' subject, optionally with its op_obj bound to the object symbol)
-MG_HD bool rule_eval(const EngineDev &E, const RuleDev &Ru, unsigned curmask, int a, int sub_code, int obj_code) {
+// one or two 'any' subjects, each optionally with its op_obj bound to an object symbol)
+MG_HD bool rule_eval(const EngineDev &E, const RuleDev &Ru, unsigned curmask, int a, const int *codes) {
     bool stack[MG_MAX_PROG];
     int sp = 0;
     for (int p = 0; p < Ru.n_prog; ++p) {
@@ -483,14 +483,13 @@ MG_HD bool rule_eval(const EngineDev &E, const RuleDev &Ru, unsigned curmask, in
             case OP_OR:  { bool b = stack[--sp]; bool x = stack[--sp]; stack[sp++] = x || b; break; }
             case OP_NOT: { stack[sp - 1] = !stack[sp - 1]; break; }
             default: {
-                int ca = I.role_a ? obj_code : sub_code;
+                int ca = codes[I.role_a];
                 int ga = code_group(ca);
                 const AgentSoA &s = cur_soa(E, curmask, ga);
                 long gi = gidx(E, a, ga, code_index(ca));
                 bool v = false;
                 if (I.op == OP_KILL || I.op == OP_ATTACK || I.op == OP_COLLIDE) {
-                    int cb = I.role_b ? obj_code : sub_code;
-                    v = s.last_op[gi] == I.op && s.op_obj[gi] == cb;
+                    v = s.last_op[gi] == I.op && s.op_obj[gi] == codes[I.role_b];
                 } else if (I.op == OP_DIE) {
                     v = (s.flags[gi] & FLAG_DEAD) != 0;
                 } else if (I.op == OP_AT) {
@@ -506,36 +505,68 @@ MG_HD bool rule_eval(const EngineDev &E, const RuleDev &Ru, unsigned curmask, in
     return sp > 0 && stack[sp - 1];
 }
 
+// AgentSymbol::bind_with_check (RewardEngine.cc:14-23) for an inferred object
+MG_HD bool rule_bind(int obj, int group, int index) {
+    if (obj < 0) return false;
+    if (code_group(obj) != group) return false;
+    return index == -1 || code_index(obj) == index;
+}
+
+MG_HD void rule_pay(const EngineDev &E, const ArenaRef &R, const RuleDev &Ru, unsigned curmask, int a, const int *codes) {
+    for (int q = 0; q < Ru.n_recv; ++q) {
+        const RuleRecv &rc = Ru.recv[q];
+        if (rc.role == ROLE_GROUP) {
+            atomic_addf(&R.hdr->grp_reward[rc.group], rc.value);
+        } else {
+            int cd = codes[rc.role];
+            if (cd < 0) continue;
+            int gg = code_group(cd);
+            atomic_addf(&cur_soa(E, curmask, gg).next_reward[gidx(E, a, gg, code_index(cd))], rc.value);
+        }
+    }
+}
+
 template <class Ctx>
 MG_HD void phase_reward_rule(Ctx &c, const EngineDev &E, const StepArgs &S, int a, int r) {
     ArenaRef R = arena_ref(E, a);
     const RuleDev &Ru = E.rules[r];
-    int g = Ru.sub_group;
-    int n = E.n[g * E.A + a];
-    const AgentSoA &s = cur_soa(E, S.curmask, g);
+    const int gA = Ru.sub_group;
+    const int nA = E.n[gA * E.A + a];
+    const AgentSoA &sA = cur_soa(E, S.curmask, gA);
     bool any = false;
-    for (int i = c.tid(); i < n; i += c.nth()) {
-        long gi = gidx(E, a, g, i);
-        int obj = -1;
-        if (Ru.has_obj) {                                 // AgentSymbol::bind_with_check (RewardEngine.cc:14-23)
-            obj = s.op_obj[gi];
-            if (obj < 0) continue;
-            if (code_group(obj) != Ru.obj_group) continue;
-            if (Ru.obj_index != -1 && code_index(obj) != Ru.obj_index) continue;
-        }
-        int sub = code_make(g, i);
-        if (!rule_eval(E, Ru, S.curmask, a, sub, obj)) continue;
-        any = true;
-        for (int q = 0; q < Ru.n_recv; ++q) {
-            const RuleRecv &rc = Ru.recv[q];
-            if (rc.role == 2) {
-                atomic_addf(&R.hdr->grp_reward[rc.group], rc.value);
-            } else {
-                int cd = rc.role ? obj : sub;
-                if (cd < 0) continue;
-                int gg = code_group(cd);
-                atomic_addf(&cur_soa(E, S.curmask, gg).next_reward[gidx(E, a, gg, code_index(cd))], rc.value);
+    if (Ru.kind == 0) {
+        for (int i = c.tid(); i < nA; i += c.nth()) {
+            int codes[4] = {code_make(gA, i), -1, -1, -1};
+            if (Ru.has_obj) {
+                codes[ROLE_OBJ_A] = sA.op_obj[gidx(E, a, gA, i)];
+                if (!rule_bind(codes[ROLE_OBJ_A], Ru.obj_group, Ru.obj_index)) continue;
             }
+            if (!rule_eval(E, Ru, S.curmask, a, codes)) continue;
+            any = true;
+            rule_pay(E, R, Ru, S.curmask, a, codes);
+        }
+    } else {
+        // two 'any' subjects: every ordered pair (i, j); an agent cannot fill both roles
+        // (be_involved, RewardEngine.cc:401-403).  O(nA*nB), exact; used by cooperative rules only.
+        const int gB = Ru.sub2_group;
+        const int nB = E.n[gB * E.A + a];
+        const AgentSoA &sB = cur_soa(E, S.curmask, gB);
+        const long pairs = (long)nA * nB;
+        for (long p = c.tid(); p < pairs; p += c.nth()) {
+            int i = (int)(p / nB), j = (int)(p - (long)i * nB);
+            if (gA == gB && i == j) continue;
+            int codes[4] = {code_make(gA, i), -1, code_make(gB, j), -1};
+            if (Ru.has_obj) {
+                codes[ROLE_OBJ_A] = sA.op_obj[gidx(E, a, gA, i)];
+                if (!rule_bind(codes[ROLE_OBJ_A], Ru.obj_group, Ru.obj_index)) continue;
+            }
+            if (Ru.has_obj2) {
+                codes[ROLE_OBJ_B] = sB.op_obj[gidx(E, a, gB, j)];
+                if (!rule_bind(codes[ROLE_OBJ_B], Ru.obj2_group, Ru.obj2_index)) continue;
+            }
+            if (!rule_eval(E, Ru, S.curmask, a, codes)) continue;
+            any = true;
+            rule_pay(E, R, Ru, S.curmask, a, codes);
         }
     }
     if (any) atomic_or(&R.hdr->rule_trigger, 1 << r);

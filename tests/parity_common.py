@@ -167,3 +167,15 @@ def make_gather(lib, map_size=40, seed=0, n_agent=40, n_food=120, **kw):
     env.add_agents(h[1], method="random", n=n_agent)
     env.add_agents(h[0], method="random", n=n_food)
     return env
+
+
+def make_builtin(lib, game, map_size=30, seed=3, n0=120, n1=60, **kw):
+    """forest / double_attack: deer (group 0) and tigers (group 1), random placement"""
+    import magent_b200 as magent
+    env = magent.GridWorld(game, map_size=map_size, _lib=lib, **kw)
+    env.set_seed(seed)
+    env.reset()
+    h = env.get_handles()
+    env.add_agents(h[0], method="random", n=n0)
+    env.add_agents(h[1], method="random", n=n1)
+    return env

@@ -102,7 +102,10 @@ def test_mid_episode_add_agents_roundtrip(emu):
 
 
 def test_unsupported_rule_shapes_fail_loudly(emu):
-    code = ("import magent_b200 as m; e = m.GridWorld('double_attack', map_size=30, _lib=%r); e.reset()" % emu)
+    """an 'all' subject is not lowered yet: the engine must abort with a message, not diverge silently"""
+    code = ("import magent_b200 as m; gw = m.gridworld; c = m.builtin.config.battle.get_config(30); "
+            "c.add_reward_rule(gw.Event(gw.AgentSymbol(0, 'all'), 'die'), receiver=gw.AgentSymbol(1, 'all'), value=1); "
+            "e = m.GridWorld(c, _lib=%r); e.reset()" % emu)
     import sys
     out = subprocess.run([sys.executable, "-c", code], cwd=pc.REPO, capture_output=True, text=True)
-    assert out.returncode != 0 and "single 'any' subject" in out.stderr
+    assert out.returncode != 0 and "must be 'any'" in out.stderr

@@ -76,6 +76,18 @@ def test_gather_dense_infighting():
     assert want[-1]["num"][1] < 150
 
 
+def test_forest_kill_supply_heals():
+    """tigers eat deer: kill_supply heals the killer inside the attack timeline (Map.cc:274)"""
+    want = both(lambda lib: pc.make_builtin(lib, "forest", 30, 3), 80, 3)
+    assert want[-1]["num"][0] < 120
+
+
+def test_double_attack_two_subject_rule():
+    """`e1 & e2` with two free tiger symbols: the pair-scan rule kernel vs the reference DFS"""
+    want = both(lambda lib: pc.make_builtin(lib, "double_attack", 30, 4, n0=150, n1=120), 60, 4)
+    assert any((r["reward"][1] > 0.5).any() for r in want), "no cooperative reward ever fired: test too weak"
+
+
 def test_unculled_dead_agents_keep_their_slots():
     """no clear_dead between steps: dead agents stay in the vectors, still get actions, are skipped"""
     import magent_b200  # noqa: F401
