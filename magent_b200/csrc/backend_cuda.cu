@@ -251,9 +251,35 @@ __device__ __forceinline__ void load_engine(EngineDev *sE, const EngineDev *gE) 
 constexpr int STEP_THREADS = 1024;      // launch bound; the launch picks 256..1024 (step_block_size)
 constexpr int GRID_THREADS = 512;       // block size of the cooperative whole-grid team
 
-__global__ void __launch_bounds__(STEP_THREADS) step_kernel_cta(const EngineDev *gE, StepArgs S) {
+// bytes of per-arena step scratch (the arrays step_scratch_to_smem() re-homes)
+static size_t step_scratch_bytes(int cap_total, int max_body) {
+    return (size_t)cap_total * (14 * 4 + 4 * (size_t)max_body) + (((size_t)cap_total + 15) & ~(size_t)15);
+}
+
+// Point the scratch arrays of the CTA's private EngineDev copy at dynamic shared memory.  One CTA works on one
+// arena at a time, so the scratch needs no per-arena stride (scratch_stride = 0): every dependent load of the
+// relaxation / list walks becomes an LDS instead of an L2/HBM round trip.
+__device__ __forceinline__ void step_scratch_to_smem(EngineDev *sE, unsigned char *base) {
+    const size_t n = (size_t)sE->cap_total;
+    int *p = (int *)base;
+    sE->att_rank = p; p += n;  sE->tgt = p; p += n;       sE->in_head = p; p += n;  sE->in_next = p; p += n;
+    sE->death = p; p += n;     sE->mv_nx = p; p += n;     sE->mv_ny = p; p += n;
+    sE->mv_key = (unsigned *)p; p += n;                   sE->hp_fin = (float *)p; p += n;
+    sE->jv = p; p += n;        sE->sh_head = p; p += n;   sE->sh_next = p; p += n;  sE->sh_first = p; p += n;
+    sE->att_agent = p; p += n;
+    sE->cl_next = p; p += n * sE->max_body;
+    sE->mv_state = (unsigned char *)p;
+    sE->scratch_stride = 0;
+}
+
+__global__ void __launch_bounds__(STEP_THREADS) step_kernel_cta(const EngineDev *gE, StepArgs S, int scratch_in_smem) {
+    extern __shared__ __align__(16) unsigned char step_smem[];
     __shared__ EngineDev sE;
     load_engine(&sE, gE);
+    if (scratch_in_smem) {
+        if (threadIdx.x == 0) step_scratch_to_smem(&sE, step_smem);
+        __syncthreads();
+    }
     CtaCtx c;
     for (int a = blockIdx.x; a < sE.A; a += gridDim.x) run_step(c, sE, S, a);
 }
@@ -309,8 +335,26 @@ void launch_step(const EngineDev *dE, const EngineDev &hE, const StepArgs &S, in
         CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)step_kernel_grid, dim3(grid), dim3(GRID_THREADS), args, 0, 0));
         post_launch("step_kernel_grid");
     } else {
-        int grid = hE.A < 8 * g_sms ? hE.A : 8 * g_sms;
-        step_kernel_cta<<<grid, step_block_size(hE.A, max_agents)>>>(dE, S);
+        // scratch in shared memory whenever one arena's scratch fits: fewer, wider CTAs (latency per phase drops
+        // from HBM/L2 round trips to LDS), and the concurrently active arenas stay L2-resident
+        const size_t sbytes = step_scratch_bytes(hE.cap_total, hE.max_body);
+        const bool in_smem = sbytes <= 200 * 1024;
+        int threads = step_block_size(hE.A, max_agents);
+        size_t smem = 0;
+        if (in_smem) {
+            smem = sbytes;
+            threads = max_agents >= 768 ? 1024 : (max_agents >= 384 ? 512 : 256);
+            static size_t configured = 0;
+            if (smem > configured) {
+                CUDA_CHECK(cudaFuncSetAttribute(step_kernel_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = smem;
+            }
+        }
+        int per_sm = 1;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_cta, threads, smem));
+        if (per_sm < 1) per_sm = 1;
+        int grid = hE.A < per_sm * g_sms ? hE.A : per_sm * g_sms;
+        step_kernel_cta<<<grid, threads, smem>>>(dE, S, in_smem ? 1 : 0);
         post_launch("step_kernel_cta");
     }
 }
@@ -470,22 +514,26 @@ void launch_minimap(const EngineDev *dE, const EngineDev &hE, unsigned curmask, 
 // ------------------------------------------------------------------------------------------------
 // obs_render_kernel: the observation gather (GridWorld.cc:292-401 + Map::extract_view Map.cc:129-207).
 //
-// Persistent CTAs each own a contiguous run of tiles of OBS_TA consecutive agents of the ABI concatenation.
-// A tile is composed in shared memory: (1) the tile buffer is initialised by 16-byte copies from a tile-sized
-// *template* that already holds the arena's minimap channels (rebuilt only when the CTA enters a new arena; a
-// tile that straddles two arenas falls back to zero fill + per-agent minimap scatter); (2) one warp per agent,
-// one lane per view cell: every lane first issues all its occupancy-plane loads back to back, then scatters
-// only the non-zero floats (wall / agent / hp channels, the +1 self marker; n_channel-word stride =>
-// conflict-free for odd channel counts); (3) the tile leaves the SM as ONE TMA bulk store
-// (cp.async.bulk.global.shared::cta, SASS UBLKCP) from a double-buffered tile, so the store of tile k overlaps
-// the composition of tile k+1 and costs no LSU issue slots.  A tile's byte range in the output is contiguous
-// and 16-byte aligned because OBS_TA % 4 == 0.
-// Algorithmic traffic per agent: 4*(view_h*view_w*n_channel + feature) bytes written, plus one
-// compulsory read of the occupancy plane per arena.  No tensor cores: there is no
-// contraction on this path.
-constexpr int OBS_THREADS = 256;
-constexpr int OBS_WARPS = OBS_THREADS / 32;
-constexpr int OBS_TA = 8;
+// The kernel is a stream of 4.7 KB records (battle) whose content is ~97 % zeros + two dense minimap channels,
+// with a handful of values gathered through dependent loads (position -> occupancy plane -> hp).  It is
+// HBM-write-bound only if that load latency is hidden, so the design maximises resident warps per SM:
+//   * tile = OBS_TA (4) consecutive agents of the ABI concatenation = ONE 128-thread CTA, one warp per agent,
+//     one shared-memory tile (18.9 KB for battle) => 11 CTAs = 44 warps per SM;
+//   * the tile is initialised by a TMA bulk LOAD (cp.async.bulk ... mbarrier::complete_tx) of a per-arena
+//     *template tile* that already holds the arena's minimap channels (built once per call by
+//     obs_template_kernel, L2-resident: A x 18.9 KB) -- zero SM instructions for the 97 % of the bytes that are
+//     not agent-specific; while it is in flight every lane issues its position and occupancy-plane loads;
+//   * after the mbarrier flips, lanes scatter only the non-zero floats (wall / agent / hp channels, the +1 self
+//     marker; n_channel-word stride => conflict-free for odd channel counts);
+//   * the tile leaves the SM as ONE TMA bulk STORE (cp.async.bulk.global.shared::cta, SASS UBLKCP).  A tile's
+//     byte range in the output is contiguous and 16-byte aligned because OBS_TA % 4 == 0.
+// Tiles are dealt round-robin so that at any moment the whole grid works inside a window of a few arenas: their
+// occupancy planes, hp arrays and template tiles stay L1/L2-hot while the output streams past.
+// Algorithmic traffic per agent: 4*(view_h*view_w*n_channel + feature) bytes written, plus one compulsory read
+// of the occupancy plane per arena.  No tensor cores: there is no contraction on this path.
+constexpr int OBS_TA = 4;
+constexpr int OBS_THREADS = 32 * OBS_TA;
+constexpr int OBS_NIT = 8;           // view cells per lane handled in one unrolled batch (8*32 = 256 cells)
 
 struct ObsGroupP { const float *hp; int cap; float max_hp; int ch; };
 struct ObsParams {
@@ -499,6 +547,8 @@ struct ObsParams {
     const int *x, *y, *id, *act;
     const float *last_reward;
     const float *mm;                 // [A][G][cells] normalised minimap, or nullptr
+    const float *tmpl;               // [A][OBS_TA*rec] template tiles (minimap channels filled), or nullptr
+    const int *tile_arena;           // [n_tiles] arena of each tile's first agent
     float *view, *feature;
     int mm_ch[MG_MAX_GROUPS];        // observation channel of group j's minimap
     ObsGroupP grp[MG_MAX_GROUPS];
@@ -514,102 +564,110 @@ __device__ __forceinline__ int small_div(int n, int d, float inv) {
     return q;
 }
 
-constexpr int OBS_NIT = 8;           // view cells per lane handled in one unrolled batch (8*32 = 256 cells)
+// arena of the first agent of every tile (one thread per tile)
+__global__ void __launch_bounds__(256) obs_tiles_kernel(const int *off, int A, int n_total, int *tile_arena) {
+    const int n_tiles = (n_total + OBS_TA - 1) / OBS_TA;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x)
+        tile_arena[t] = A == 1 ? 0 : locate_arena(off, A, t * OBS_TA);
+}
+
+// template tile of arena a: OBS_TA records, zero except the minimap channels (GridWorld.cc:374-381)
+__global__ void __launch_bounds__(256) obs_template_kernel(ObsParams P, float *tmpl) {
+    const int a = blockIdx.x;
+    float *t = tmpl + (size_t)a * OBS_TA * P.rec;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = threadIdx.x; q < OBS_TA * P.rec / 4; q += blockDim.x) ((float4 *)t)[q] = z;
+    __syncthreads();
+    const float *mm = P.mm + (size_t)a * P.G * P.cells;
+    const int per_slot = P.G * P.cells;
+    for (int q = threadIdx.x; q < OBS_TA * per_slot; q += blockDim.x) {
+        int slot = q / per_slot, r = q - slot * per_slot;
+        int j = r / P.cells, cell = r - j * P.cells;
+        t[slot * P.rec + cell * P.C + P.mm_ch[j]] = mm[r];
+    }
+}
 
 __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_constant__ ObsParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int tile_floats = OBS_TA * P.rec;                   // multiple of 8 floats => 32-byte multiple
-    float *tmpl = (float *)smem_raw;                          // one tile of records holding only the arena's minimap
-    float *buf_base = tmpl + tile_floats;                     // two tiles: double buffer for the bulk stores
-    int *lut = (int *)(buf_base + 2 * tile_floats);           // per view cell: packed (dy << 16 | dx); masked cells point far out
+    float *buf = (float *)smem_raw;                           // one tile: OBS_TA records
+    int *lut = (int *)(buf + OBS_TA * P.rec);                 // per view cell: packed (dy << 16 | dx); masked cells point far out
+    __shared__ __align__(8) unsigned long long mbar;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned tile_bytes = (unsigned)OBS_TA * (unsigned)P.rec * 4u;
 
     for (int cell = threadIdx.x; cell < P.cells; cell += OBS_THREADS) {
         int vy = cell / P.vw, vx = cell - vy * P.vw;
         int dx = P.mask[cell] ? P.ox + vx : -30000, dy = P.oy + vy;
         lut[cell] = (int)(((unsigned)dy << 16) | ((unsigned)dx & 0xffffu));
     }
-    // contiguous block of tiles per CTA: consecutive tiles stay inside one arena most of the time
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     const int n_tiles = (P.n_total + OBS_TA - 1) / OBS_TA;
-    const int per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
-    const int tile_lo = blockIdx.x * per_cta, tile_hi = min(n_tiles, tile_lo + per_cta);
     const float inv_sw = 1.0f / (float)P.scale_w, inv_sh = 1.0f / (float)P.scale_h;
-    int a_cur = 0, a_lo = 0, a_hi = 0;                        // arena of the tile's first agent and its [lo, hi) range
-    int tmpl_arena = -1;
-    int k = 0;
-    for (int tile = tile_lo; tile < tile_hi; ++tile, ++k) {
-        float *buf = buf_base + (k & 1) * tile_floats;
+    unsigned phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int t0 = tile * OBS_TA;
         const int cnt = min(OBS_TA, P.n_total - t0);
-        if (t0 >= a_hi || t0 < a_lo) {
-            a_cur = P.A == 1 ? 0 : locate_arena(P.off, P.A, t0);
-            a_lo = P.off[a_cur]; a_hi = P.off[a_cur + 1];
-        }
-        const bool uniform = t0 + cnt <= a_hi;                // whole tile inside arena a_cur
-        const bool use_tmpl = P.minimap && uniform;
-        // the bulk store that last read this buffer (issued two tiles ago) must have finished reading
-        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        if (use_tmpl && tmpl_arena != a_cur) {                // (block-uniform) rebuild the minimap template
-            __syncthreads();
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = threadIdx.x; q < tile_floats / 4; q += OBS_THREADS) ((float4 *)tmpl)[q] = z;
-            __syncthreads();
-            const float *mm = P.mm + (long)a_cur * P.G * P.cells;
-            const int per_slot = P.G * P.cells;
-            for (int q = threadIdx.x; q < OBS_TA * per_slot; q += OBS_THREADS) {
-                int slot = q / per_slot, r = q - slot * per_slot;
-                int j = r / P.cells, cell = r - j * P.cells;
-                tmpl[slot * P.rec + cell * P.C + P.mm_ch[j]] = mm[r];
-            }
-            tmpl_arena = a_cur;
-        }
-        __syncthreads();
+        const int a0 = P.tile_arena[tile];
+        const int a0_hi = P.off[a0 + 1];
+        const bool use_tmpl = P.tmpl != nullptr && t0 + cnt <= a0_hi;     // whole tile inside arena a0 (block-uniform)
         if (use_tmpl) {
-            const float4 *s4 = (const float4 *)tmpl;
-            float4 *d4 = (float4 *)buf;
-            for (int q = threadIdx.x; q < tile_floats / 4; q += OBS_THREADS) d4[q] = s4[q];
+            if (threadIdx.x == 0) {
+                // the previous tile's bulk store must have finished READING the buffer before TMA overwrites it
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                             :: "r"(smem_u32(&mbar)), "r"(tile_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(buf)), "l"(P.tmpl + (size_t)a0 * OBS_TA * P.rec), "r"(tile_bytes),
+                                "r"(smem_u32(&mbar)) : "memory");
+            }
         } else {
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = threadIdx.x; q < tile_floats / 4; q += OBS_THREADS) ((float4 *)buf)[q] = z;
+            for (int q = threadIdx.x; q < OBS_TA * P.rec / 4; q += OBS_THREADS) ((float4 *)buf)[q] = z;
+            __syncthreads();
         }
-        __syncthreads();
-        for (int ag = warp; ag < cnt; ag += OBS_WARPS) {
-            const int o = t0 + ag;
-            int a = a_cur, lo = a_lo;
-            if (o >= a_hi) { a = locate_arena(P.off, P.A, o); lo = P.off[a]; }
-            const long gi = (long)a * P.cap + (o - lo);
-            const int ax = P.x[gi], ay = P.y[gi];
-            const int *occ = P.occ + (long)a * P.W * P.H;
-            float *dst = buf + ag * P.rec;
-            // issue this lane's occupancy loads back to back, then consume them
-            int tcode[OBS_NIT];
+        const bool active = warp < cnt;
+        const int o = t0 + warp;
+        int a = a0, ax = 0, ay = 0;
+        long gi = 0;
+        int tcode[OBS_NIT];
+#pragma unroll
+        for (int it = 0; it < OBS_NIT; ++it) tcode[it] = OCC_EMPTY;
+        const int *occ = nullptr;
+        if (active) {
+            int lo = P.off[a0];
+            if (o >= a0_hi) { a = locate_arena(P.off, P.A, o); lo = P.off[a]; }
+            gi = (long)a * P.cap + (o - lo);
+            ax = P.x[gi]; ay = P.y[gi];
+            occ = P.occ + (long)a * P.W * P.H;
+            // issue this lane's occupancy loads back to back (they overlap the template load)
 #pragma unroll
             for (int it = 0; it < OBS_NIT; ++it) {
                 const int cell = it * 32 + lane;
-                tcode[it] = OCC_EMPTY;
                 if (cell < P.cells) {
                     const int l = lut[cell];
                     const int x = ax + (int)(short)(l & 0xffff), y = ay + (l >> 16);
                     if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) tcode[it] = __ldg(occ + y * P.W + x);
                 }
             }
-            for (int base = OBS_NIT * 32; base < P.cells; base += 32) {        // views wider than 256 cells
-                const int cell = base + lane;
-                if (cell < P.cells) {
-                    const int l = lut[cell];
-                    const int x = ax + (int)(short)(l & 0xffff), y = ay + (l >> 16);
-                    if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) {
-                        const int t = __ldg(occ + y * P.W + x);
-                        float *px = dst + cell * P.C;
-                        if (t == OCC_WALL) px[0] = 1.0f;
-                        else if (t >= 0) {
-                            const ObsGroupP &T = P.grp[code_group(t)];
-                            px[T.ch] = 1.0f;
-                            px[T.ch + 1] = T.hp[(long)a * T.cap + code_index(t)] / T.max_hp;
-                        }
-                    }
-                }
+        }
+        if (use_tmpl) {                                           // wait for the template tile to land
+            unsigned done = 0;
+            while (!done) {
+                asm volatile("{\n\t.reg .pred p;\n\t"
+                             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                             "selp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
             }
+            phase ^= 1u;
+        }
+        if (active) {
+            float *dst = buf + warp * P.rec;
             if (P.minimap) {
                 const int self_cell = small_div(ay, P.scale_h, inv_sh) * P.vw + small_div(ax, P.scale_w, inv_sw);
                 if (!use_tmpl) {                                   // tile straddles arenas: no template
@@ -632,6 +690,23 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
                         const ObsGroupP &T = P.grp[code_group(t)];
                         px[T.ch] = 1.0f;
                         px[T.ch + 1] = T.hp[(long)a * T.cap + code_index(t)] / T.max_hp;   // Map.cc:197
+                    }
+                }
+            }
+            for (int base = OBS_NIT * 32; base < P.cells; base += 32) {        // views wider than 256 cells
+                const int cell = base + lane;
+                if (cell < P.cells) {
+                    const int l = lut[cell];
+                    const int x = ax + (int)(short)(l & 0xffff), y = ay + (l >> 16);
+                    if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) {
+                        const int t = __ldg(occ + y * P.W + x);
+                        float *px = dst + cell * P.C;
+                        if (t == OCC_WALL) px[0] = 1.0f;
+                        else if (t >= 0) {
+                            const ObsGroupP &T = P.grp[code_group(t)];
+                            px[T.ch] = 1.0f;
+                            px[T.ch + 1] = T.hp[(long)a * T.cap + code_index(t)] / T.max_hp;
+                        }
                     }
                 }
             }
@@ -662,11 +737,16 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
             }
         } else {                                   // ragged last tile / unaligned caller buffer
             for (int q = threadIdx.x; q < cnt * P.rec; q += OBS_THREADS) __stcs(gout + q, buf[q]);
-            if (threadIdx.x == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            __syncthreads();
         }
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
+
+static float *g_tmpl = nullptr;
+static size_t g_tmpl_bytes = 0;
+static int *g_tile_arena = nullptr;
+static size_t g_tile_arena_n = 0;
 
 void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total) {
     const int g = O.group;
@@ -693,17 +773,42 @@ void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const 
         P.grp[j].hp = hE.grp[j].soa[(O.curmask >> j) & 1u].hp;
         P.grp[j].cap = hE.grp[j].cap; P.grp[j].max_hp = hE.grp[j].max_hp; P.grp[j].ch = ch;
     }
-    const size_t smem = (size_t)3 * OBS_TA * P.rec * sizeof(float) + (size_t)P.cells * sizeof(int);
-    static size_t configured = 0;
-    static int ctas_per_sm = 1;
+    const size_t tile_bytes = (size_t)OBS_TA * P.rec * sizeof(float);
+    const size_t smem = tile_bytes + (size_t)P.cells * sizeof(int);
     if (smem > 227 * 1024) mg::fatal("observation record too large for the render kernel (%zu bytes of shared memory)", smem);
+    const int tiles = (n_total + OBS_TA - 1) / OBS_TA;
+    // scratch owned by the backend: tile -> arena table, per-arena template tiles
+    if ((size_t)tiles > g_tile_arena_n) {
+        if (g_tile_arena) cudaFree(g_tile_arena);
+        g_tile_arena_n = (size_t)tiles + tiles / 4 + 64;
+        CUDA_CHECK(cudaMalloc(&g_tile_arena, g_tile_arena_n * sizeof(int)));
+    }
+    P.tile_arena = g_tile_arena;
+    {
+        int gt = (tiles + 255) / 256;
+        if (gt > 4 * g_sms) gt = 4 * g_sms;
+        obs_tiles_kernel<<<gt, 256>>>(P.off, P.A, n_total, g_tile_arena);
+        post_launch("obs_tiles_kernel");
+    }
+    if (P.minimap && (tile_bytes & 15) == 0) {
+        const size_t need = (size_t)hE.A * tile_bytes;
+        if (need > g_tmpl_bytes) {
+            if (g_tmpl) cudaFree(g_tmpl);
+            g_tmpl_bytes = need + need / 8;
+            CUDA_CHECK(cudaMalloc(&g_tmpl, g_tmpl_bytes));
+        }
+        obs_template_kernel<<<hE.A, 256>>>(P, g_tmpl);
+        post_launch("obs_template_kernel");
+        P.tmpl = g_tmpl;
+    }
+    static size_t configured = (size_t)-1;
+    static int ctas_per_sm = 1;
     if (smem != configured) {
         CUDA_CHECK(cudaFuncSetAttribute(obs_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, obs_render_kernel, OBS_THREADS, smem));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         configured = smem;
     }
-    const int tiles = (n_total + OBS_TA - 1) / OBS_TA;
     const int grid = tiles < ctas_per_sm * g_sms ? tiles : ctas_per_sm * g_sms;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_profile) { profile_pair(&e0, &e1); CUDA_CHECK(cudaEventRecord(e0, 0)); }

@@ -111,6 +111,7 @@ struct EngineDev {
     int nsep, bandwidth, large_map;           // GridWorld.cc:75-85, :407
     int minimap_mode, embedding_size, n_channel, channel_base;
     int cap_total, max_body;
+    int scratch_stride;                       // per-arena stride of the step scratch: cap_total in HBM, 0 when it lives in the CTA's shared memory
     uint32_t pow2[32];                        // 16807^(2^b) mod (2^31-1)
     GroupDev grp[MG_MAX_GROUPS];
     ArenaHdr *hdr;                            // [A]

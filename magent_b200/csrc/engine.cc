@@ -576,7 +576,7 @@ void Engine::to_device() {
                 s.last_op = (unsigned char *)dalloc(n); s.flags = (unsigned char *)dalloc(n); s.dir = (unsigned char *)dalloc(n);
             }
         }
-        hE_.cap_total = foff; hE_.max_body = max_body;
+        hE_.cap_total = foff; hE_.max_body = max_body; hE_.scratch_stride = foff;
         size_t cells = (size_t)A_ * W_ * H_, sc = (size_t)A_ * foff;
         hE_.hdr = (ArenaHdr *)dalloc(sizeof(ArenaHdr) * A_);
         hE_.n = (int *)dalloc((size_t)Gn * A_ * 4); hE_.dead_ct = (int *)dalloc((size_t)Gn * A_ * 4);

@@ -51,8 +51,8 @@ MG_HD const AgentSoA &cur_soa(const EngineDev &E, unsigned curmask, int g) {
 struct ArenaRef {
     int a;
     int *occ, *claim;
-    long sb;            // base into per-agent scratch  (a * cap_total)
-    long nb;            // base into claim nodes        (a * cap_total * max_body)
+    long sb;            // base into per-agent scratch  (a * scratch_stride)
+    long nb;            // base into claim nodes        (a * scratch_stride * max_body)
     ArenaHdr *hdr;
 };
 MG_HD ArenaRef arena_ref(const EngineDev &E, int a) {
@@ -60,8 +60,8 @@ MG_HD ArenaRef arena_ref(const EngineDev &E, int a) {
     r.a = a;
     r.occ = E.occ + (long)a * E.W * E.H;
     r.claim = E.claim_head + (long)a * E.W * E.H;
-    r.sb = (long)a * E.cap_total;
-    r.nb = (long)a * E.cap_total * E.max_body;
+    r.sb = (long)a * E.scratch_stride;
+    r.nb = (long)a * E.scratch_stride * E.max_body;
     r.hdr = E.hdr + a;
     return r;
 }
