@@ -33,7 +33,9 @@ void sync();
 void launch_step(const EngineDev *dE, const EngineDev &hE, const StepArgs &S, int max_agents_per_arena);
 void launch_cull(const EngineDev *dE, const EngineDev &hE, unsigned curmask, int max_agents_per_arena);
 void launch_offsets(const EngineDev *dE, const EngineDev &hE);
-void launch_minimap(const EngineDev *dE, const EngineDev &hE, unsigned curmask, int obs_group, float *mm_val);
+// per-call preparation of get_observation: normalised minimap into mm_val ([A][G][view cells]; nullptr when
+// minimap_mode is off) plus whatever the backend wants to precompute for the render kernel
+void launch_obs_prepare(const EngineDev *dE, const EngineDev &hE, unsigned curmask, int obs_group, float *mm_val);
 void launch_obs(const EngineDev *dE, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total);
 void launch_info(const EngineDev *dE, const EngineDev &hE, unsigned curmask, int kind, int group,
                  void *buf, int n_total);

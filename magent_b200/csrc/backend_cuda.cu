@@ -460,8 +460,16 @@ void launch_random_actions(const EngineDev *dE, const EngineDev &, unsigned curm
 }
 
 // ------------------------------------------------------------------------------------------------
-// minimap: counts per (arena, group, coarse cell) then value = (float)count / (float)group size
-__global__ void __launch_bounds__(256) minimap_hist_kernel(const EngineDev *gE, unsigned curmask, int og, int chunk) {
+// obs_prepare: one pass over every agent of every group per get_observation call:
+//   * hp_norm = hp / max_hp, the f32 divide of Map.cc:197, done ONCE per agent instead of once per observer
+//     that sees it (the render kernel then only loads it);
+//   * minimap (when enabled): counts per (arena, group, coarse cell); value = (float)count / (float)group size
+static float *g_hpn[MG_MAX_GROUPS] = {nullptr};
+static size_t g_hpn_n[MG_MAX_GROUPS] = {0};
+struct HpnPtrs { float *p[MG_MAX_GROUPS]; };
+
+__global__ void __launch_bounds__(256) obs_prepare_kernel(const EngineDev *gE, unsigned curmask, int og, int chunk,
+                                                          HpnPtrs hpn, int do_minimap) {
     extern __shared__ int hist[];
     const EngineDev &E = *gE;
     const int ag = blockIdx.y;               // a * G + j
@@ -471,18 +479,24 @@ __global__ void __launch_bounds__(256) minimap_hist_kernel(const EngineDev *gE, 
     const int lo = blockIdx.x * chunk;
     if (lo >= n) return;
     const int hi = min(n, lo + chunk);
-    for (int k = threadIdx.x; k < cells; k += blockDim.x) hist[k] = 0;
-    __syncthreads();
+    if (do_minimap) {
+        for (int k = threadIdx.x; k < cells; k += blockDim.x) hist[k] = 0;
+        __syncthreads();
+    }
     const AgentSoA &s = E.grp[j].soa[(curmask >> j) & 1u];
     const int scale_h = (E.H + vh - 1) / vh, scale_w = (E.W + vw - 1) / vw;
+    const float max_hp = E.grp[j].max_hp;
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         long gi = (long)a * E.grp[j].cap + i;
-        atomicAdd(&hist[(s.y[gi] / scale_h) * vw + s.x[gi] / scale_w], 1);
+        hpn.p[j][gi] = s.hp[gi] / max_hp;
+        if (do_minimap) atomicAdd(&hist[(s.y[gi] / scale_h) * vw + s.x[gi] / scale_w], 1);
     }
-    __syncthreads();
-    int *out = E.mm_count + (size_t)ag * cells;
-    for (int k = threadIdx.x; k < cells; k += blockDim.x)
-        if (hist[k]) atomicAdd(&out[k], hist[k]);
+    if (do_minimap) {
+        __syncthreads();
+        int *out = E.mm_count + (size_t)ag * cells;
+        for (int k = threadIdx.x; k < cells; k += blockDim.x)
+            if (hist[k]) atomicAdd(&out[k], hist[k]);
+    }
 }
 
 __global__ void __launch_bounds__(256) minimap_norm_kernel(const EngineDev *gE, int og, float *mm_val, int total) {
@@ -495,20 +509,32 @@ __global__ void __launch_bounds__(256) minimap_norm_kernel(const EngineDev *gE, 
     }
 }
 
-void launch_minimap(const EngineDev *dE, const EngineDev &hE, unsigned curmask, int og, float *mm_val) {
+void launch_obs_prepare(const EngineDev *dE, const EngineDev &hE, unsigned curmask, int og, float *mm_val) {
     const int cells = hE.grp[og].view_w * hE.grp[og].view_h;
     const int total = hE.A * hE.G * cells;
-    CUDA_CHECK(cudaMemsetAsync(hE.mm_count, 0, (size_t)total * 4, 0));
+    HpnPtrs hp;
     int cap_max = 0;
-    for (int g = 0; g < hE.G; ++g) cap_max = cap_max > hE.grp[g].cap ? cap_max : hE.grp[g].cap;
+    for (int g = 0; g < hE.G; ++g) {
+        cap_max = cap_max > hE.grp[g].cap ? cap_max : hE.grp[g].cap;
+        const size_t need = (size_t)hE.A * hE.grp[g].cap;
+        if (need > g_hpn_n[g]) {
+            if (g_hpn[g]) cudaFree(g_hpn[g]);
+            CUDA_CHECK(cudaMalloc(&g_hpn[g], need * sizeof(float)));
+            g_hpn_n[g] = need;
+        }
+        hp.p[g] = g_hpn[g];
+    }
+    if (mm_val) CUDA_CHECK(cudaMemsetAsync(hE.mm_count, 0, (size_t)total * 4, 0));
     const int chunk = 4096;
     dim3 grid((cap_max + chunk - 1) / chunk, hE.A * hE.G);
-    minimap_hist_kernel<<<grid, 256, cells * sizeof(int)>>>(dE, curmask, og, chunk);
-    post_launch("minimap_hist_kernel");
-    int g2 = (total + 255) / 256;
-    if (g2 > 8 * g_sms) g2 = 8 * g_sms;
-    minimap_norm_kernel<<<g2, 256>>>(dE, og, mm_val, total);
-    post_launch("minimap_norm_kernel");
+    obs_prepare_kernel<<<grid, 256, cells * sizeof(int)>>>(dE, curmask, og, chunk, hp, mm_val ? 1 : 0);
+    post_launch("obs_prepare_kernel");
+    if (mm_val) {
+        int g2 = (total + 255) / 256;
+        if (g2 > 8 * g_sms) g2 = 8 * g_sms;
+        minimap_norm_kernel<<<g2, 256>>>(dE, og, mm_val, total);
+        post_launch("minimap_norm_kernel");
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -535,7 +561,7 @@ constexpr int OBS_TA = 4;
 constexpr int OBS_THREADS = 32 * OBS_TA;
 constexpr int OBS_NIT = 8;           // view cells per lane handled in one unrolled batch (8*32 = 256 cells)
 
-struct ObsGroupP { const float *hp; int cap; float max_hp; int ch; };
+struct ObsGroupP { const float *hpn; int cap; int ch; };      // hpn = hp / max_hp from obs_prepare_kernel
 struct ObsParams {
     int A, W, H, G, C;
     int vw, vh, cells, rec, F;
@@ -605,6 +631,15 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // this lane's view cells never change: keep their map offsets in registers
+    int ldx[OBS_NIT], ldy[OBS_NIT];
+#pragma unroll
+    for (int it = 0; it < OBS_NIT; ++it) {
+        const int cell = it * 32 + lane;
+        const int l = cell < P.cells ? lut[cell] : (int)0x00008ad0;      // dx = -30000: never in bounds
+        ldx[it] = (int)(short)(l & 0xffff); ldy[it] = l >> 16;
+    }
+    const int nit = min(OBS_NIT, (P.cells + 31) >> 5);
     const int n_tiles = (P.n_total + OBS_TA - 1) / OBS_TA;
     const float inv_sw = 1.0f / (float)P.scale_w, inv_sh = 1.0f / (float)P.scale_h;
     unsigned phase = 0;
@@ -648,10 +683,8 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
             // issue this lane's occupancy loads back to back (they overlap the template load)
 #pragma unroll
             for (int it = 0; it < OBS_NIT; ++it) {
-                const int cell = it * 32 + lane;
-                if (cell < P.cells) {
-                    const int l = lut[cell];
-                    const int x = ax + (int)(short)(l & 0xffff), y = ay + (l >> 16);
+                if (it < nit) {
+                    const int x = ax + ldx[it], y = ay + ldy[it];
                     if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) tcode[it] = __ldg(occ + y * P.W + x);
                 }
             }
@@ -689,7 +722,7 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
                     else {
                         const ObsGroupP &T = P.grp[code_group(t)];
                         px[T.ch] = 1.0f;
-                        px[T.ch + 1] = T.hp[(long)a * T.cap + code_index(t)] / T.max_hp;   // Map.cc:197
+                        px[T.ch + 1] = T.hpn[(long)a * T.cap + code_index(t)];              // hp / max_hp (Map.cc:197)
                     }
                 }
             }
@@ -705,23 +738,29 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
                         else if (t >= 0) {
                             const ObsGroupP &T = P.grp[code_group(t)];
                             px[T.ch] = 1.0f;
-                            px[T.ch + 1] = T.hp[(long)a * T.cap + code_index(t)] / T.max_hp;
+                            px[T.ch + 1] = T.hpn[(long)a * T.cap + code_index(t)];
                         }
                     }
                 }
             }
             // non-spatial features straight to global memory (GridWorld.cc:386-396)
-            for (int f = lane; f < P.F; f += 32) {
-                float v = 0.0f;
-                if (f < P.embedding) v = f < 31 ? (float)((P.id[gi] >> f) & 1) : 0.0f;
-                else {
-                    int kk = f - P.embedding;
-                    if (kk < P.n_action) v = kk == P.act[gi] ? 1.0f : 0.0f;
-                    else if (kk == P.n_action) v = P.last_reward[gi];
-                    else if (P.minimap && kk == P.n_action + 1) v = (float)ax / (float)P.W;
-                    else if (P.minimap && kk == P.n_action + 2) v = (float)ay / (float)P.H;
+            {
+                const int id = P.id[gi], act = P.act[gi];
+                const float last_reward = P.last_reward[gi];
+                float fx = 0.0f, fy = 0.0f;
+                if (P.minimap) { fx = (float)ax / (float)P.W; fy = (float)ay / (float)P.H; }
+                for (int f = lane; f < P.F; f += 32) {
+                    float v = 0.0f;
+                    if (f < P.embedding) v = f < 31 ? (float)((id >> f) & 1) : 0.0f;
+                    else {
+                        const int kk = f - P.embedding;
+                        if (kk < P.n_action) v = kk == act ? 1.0f : 0.0f;
+                        else if (kk == P.n_action) v = last_reward;
+                        else if (P.minimap && kk == P.n_action + 1) v = fx;
+                        else if (P.minimap && kk == P.n_action + 2) v = fy;
+                    }
+                    P.feature[(size_t)o * P.F + f] = v;
                 }
-                P.feature[(size_t)o * P.F + f] = v;
             }
         }
         // make the generic-proxy writes visible to the async proxy, then one thread fires the bulk store
@@ -770,8 +809,8 @@ void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const 
         int rel = j - g; if (rel < 0) rel += hE.G;
         const int ch = hE.channel_base + rel * stride;                 // make_channel_trans, GridWorld.cc:897-913
         P.mm_ch[j] = ch + 2;
-        P.grp[j].hp = hE.grp[j].soa[(O.curmask >> j) & 1u].hp;
-        P.grp[j].cap = hE.grp[j].cap; P.grp[j].max_hp = hE.grp[j].max_hp; P.grp[j].ch = ch;
+        P.grp[j].hpn = g_hpn[j];
+        P.grp[j].cap = hE.grp[j].cap; P.grp[j].ch = ch;
     }
     const size_t tile_bytes = (size_t)OBS_TA * P.rec * sizeof(float);
     const size_t smem = tile_bytes + (size_t)P.cells * sizeof(int);

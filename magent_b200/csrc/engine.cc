@@ -735,7 +735,7 @@ void Engine::get_observation(int group, float **bufs) {               // GridWor
         }
         O.feature = d_feat_stage_;
     }
-    if (minimap_mode_) be::launch_minimap(dE_, hE_, curmask_, group, d_mm_val_);
+    be::launch_obs_prepare(dE_, hE_, curmask_, group, minimap_mode_ ? d_mm_val_ : nullptr);
     be::launch_obs(dE_, hE_, O, minimap_mode_ ? d_mm_val_ : nullptr, n);
     if (!vdev) be::d2h(bufs[0], d_view_stage_, vbytes);
     if (!fdev) be::d2h(bufs[1], d_feat_stage_, fbytes);

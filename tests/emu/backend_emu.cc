@@ -57,7 +57,8 @@ void launch_offsets(const EngineDev *dE, const EngineDev &) {
         for (int a = 0; a < E.A; ++a) off[a + 1] = off[a] + E.n[g * E.A + a];
     }
 }
-void launch_minimap(const EngineDev *dE, const EngineDev &, unsigned curmask, int og, float *mm_val) {
+void launch_obs_prepare(const EngineDev *dE, const EngineDev &, unsigned curmask, int og, float *mm_val) {
+    if (!mm_val) return;
     const EngineDev &E = *dE;
     const GroupDev &OG = E.grp[og];
     int cells = OG.view_w * OG.view_h;

@@ -179,3 +179,46 @@ def make_builtin(lib, game, map_size=30, seed=3, n0=120, n1=60, **kw):
     env.add_agents(h[0], method="random", n=n0)
     env.add_agents(h[1], method="random", n=n1)
     return env
+
+
+def mixed_config(size):
+    """synthetic config that stresses what the shipped games do not: three groups, a 2x2 body next to 1x1
+    bodies, a 19x19 view (> 256 cells), starvation, kill_supply, attack_in_group, minimap + embedding, and a
+    rule set using kill / collide / in / die / not / or / and with agent, object and whole-group receivers"""
+    import magent_b200 as magent
+    gw = magent.gridworld
+    cfg = gw.Config()
+    cfg.set({"map_width": size, "map_height": size, "minimap_mode": True, "embedding_size": 5})
+    big = cfg.register_agent_type("big", dict(
+        width=2, length=2, hp=8, speed=1, damage=3, step_recover=0.05, kill_supply=1,
+        view_range=gw.CircleRange(9), attack_range=gw.CircleRange(2),
+        step_reward=-0.01, kill_reward=3, dead_penalty=-2, attack_penalty=-0.05))
+    small = cfg.register_agent_type("small", dict(
+        width=1, length=1, hp=4, speed=2, damage=1, step_recover=-0.05, kill_supply=2,
+        view_range=gw.CircleRange(4), attack_range=gw.CircleRange(1.5),
+        step_reward=0.02, kill_reward=1, dead_penalty=-1, attack_penalty=-0.02))
+    tank = cfg.register_agent_type("tank", dict(
+        width=1, length=1, hp=12, speed=1, damage=5, step_recover=0.2, attack_in_group=1,
+        view_range=gw.CircleRange(3), attack_range=gw.CircleRange(1),
+        kill_reward=4, dead_penalty=-3, attack_penalty=-0.1))
+    g0, g1, g2 = cfg.add_group(big), cfg.add_group(small), cfg.add_group(tank)
+    a, b, c = (gw.AgentSymbol(g, index='any') for g in (g0, g1, g2))
+    cfg.add_reward_rule(gw.Event(a, 'kill', b), receiver=[a, gw.AgentSymbol(g0, 'all')], value=[2, 0.25])
+    cfg.add_reward_rule(gw.Event(b, 'attack', a) | gw.Event(b, 'kill', a), receiver=[b, a], value=[0.5, -0.5])
+    cfg.add_reward_rule(gw.Event(c, 'collide', b), receiver=c, value=-0.125)
+    cfg.add_reward_rule(gw.Event(b, 'in', ((3, 3), (size // 2, size // 2))) & ~gw.Event(b, 'die'), receiver=b, value=0.0625)
+    cfg.add_reward_rule(gw.Event(c, 'attack', c2 := gw.AgentSymbol(g2, index='any')), receiver=[c, c2], value=[0.3, -0.3])
+    return cfg
+
+
+def make_mixed(lib, map_size=36, seed=6, **kw):
+    import magent_b200 as magent
+    env = magent.GridWorld(mixed_config(map_size), _lib=lib, **kw)
+    env.set_seed(seed)
+    env.reset()
+    h = env.get_handles()
+    env.add_walls(method="random", n=30)
+    env.add_agents(h[0], method="random", n=25)
+    env.add_agents(h[1], method="random", n=160)
+    env.add_agents(h[2], method="random", n=60)
+    return env

@@ -88,6 +88,12 @@ def test_double_attack_two_subject_rule():
     assert any((r["reward"][1] > 0.5).any() for r in want), "no cooperative reward ever fired: test too weak"
 
 
+def test_mixed_three_groups_big_view_rules():
+    """3 groups, 2x2 + 1x1 bodies, 19x19 view (> 256 cells), starvation, kill_supply, in-group attacks,
+    rules with kill/collide/in/die/not/or and agent / object / whole-group receivers"""
+    both(lambda lib: pc.make_mixed(lib, 36, 6), 60, 6, order=[2, 0, 1])
+
+
 def test_unculled_dead_agents_keep_their_slots():
     """no clear_dead between steps: dead agents stay in the vectors, still get actions, are skipped"""
     import magent_b200  # noqa: F401
