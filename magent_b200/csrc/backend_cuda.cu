@@ -145,6 +145,23 @@ __device__ __forceinline__ int block_excl_scan(int v, int &total) {
 }
 
 struct CtaCtx {
+    int *flag_smem;
+    MG_HD int *flags(ArenaHdr *) { return flag_smem; }
+    int cnt[MG_N_COUNTERS];
+    MG_HD void add_count(const EngineDev &, int kind, long long v) { cnt[kind] += (int)v; }
+    // one warp-reduced atomic per counter per warp, once per arena-step
+    MG_HD void flush_counts(const EngineDev &E) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int k = 0; k < MG_N_COUNTERS; ++k) {
+            int v = cnt[k];
+            cnt[k] = 0;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (v && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&E.counters[k], (unsigned long long)v);
+        }
+#endif
+    }
     MG_HD int tid() const {
 #if defined(__CUDA_ARCH__)
         return threadIdx.x;
@@ -186,6 +203,22 @@ struct CtaCtx {
 struct GridCtx {
     int *scratch;       // [2][4096]
     int parity;
+    MG_HD int *flags(ArenaHdr *hdr) { return hdr->changed; }
+    int cnt[MG_N_COUNTERS];
+    MG_HD void add_count(const EngineDev &, int kind, long long v) { cnt[kind] += (int)v; }
+    // one warp-reduced atomic per counter per warp, once per arena-step
+    MG_HD void flush_counts(const EngineDev &E) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int k = 0; k < MG_N_COUNTERS; ++k) {
+            int v = cnt[k];
+            cnt[k] = 0;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (v && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&E.counters[k], (unsigned long long)v);
+        }
+#endif
+    }
     MG_HD int tid() const {
 #if defined(__CUDA_ARCH__)
         return blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,7 +313,10 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_cta(const EngineDev 
         if (threadIdx.x == 0) step_scratch_to_smem(&sE, step_smem);
         __syncthreads();
     }
+    __shared__ int relax_flags[3];
     CtaCtx c;
+    c.flag_smem = relax_flags;
+    for (int k = 0; k < MG_N_COUNTERS; ++k) c.cnt[k] = 0;
     for (int a = blockIdx.x; a < sE.A; a += gridDim.x) run_step(c, sE, S, a);
 }
 
@@ -290,6 +326,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_grid(const EngineDev
     GridCtx c;
     c.scratch = sE.team_scratch;
     c.parity = 0;
+    for (int k = 0; k < MG_N_COUNTERS; ++k) c.cnt[k] = 0;
     for (int a = 0; a < sE.A; ++a) run_step(c, sE, S, a);
 }
 
@@ -297,6 +334,7 @@ __global__ void __launch_bounds__(STEP_THREADS) cull_kernel_cta(const EngineDev 
     __shared__ EngineDev sE;
     load_engine(&sE, gE);
     CtaCtx c;
+    c.flag_smem = nullptr;
     for (int a = blockIdx.x; a < sE.A; a += gridDim.x) run_cull(c, sE, curmask, a);
 }
 
@@ -338,7 +376,8 @@ void launch_step(const EngineDev *dE, const EngineDev &hE, const StepArgs &S, in
         // scratch in shared memory whenever one arena's scratch fits: fewer, wider CTAs (latency per phase drops
         // from HBM/L2 round trips to LDS), and the concurrently active arenas stay L2-resident
         const size_t sbytes = step_scratch_bytes(hE.cap_total, hE.max_body);
-        const bool in_smem = sbytes <= 200 * 1024;
+        static const int smem_pref = getenv("MAGENT_B200_STEP_SMEM") ? atoi(getenv("MAGENT_B200_STEP_SMEM")) : -1;
+        const bool in_smem = sbytes <= 200 * 1024 && smem_pref != 0;
         int threads = step_block_size(hE.A, max_agents);
         size_t smem = 0;
         if (in_smem) {
@@ -574,7 +613,8 @@ struct ObsParams {
     const float *last_reward;
     const float *mm;                 // [A][G][cells] normalised minimap, or nullptr
     const float *tmpl;               // [A][OBS_TA*rec] template tiles (minimap channels filled), or nullptr
-    const int *tile_arena;           // [n_tiles] arena of each tile's first agent
+    const int *tile_arena;           // [n_tiles] arena of the tile, -1 when it straddles two arenas
+    const int4 *hdr;                 // [n_total] {x, y, arena, index} per agent in ABI order
     float *view, *feature;
     int mm_ch[MG_MAX_GROUPS];        // observation channel of group j's minimap
     ObsGroupP grp[MG_MAX_GROUPS];
@@ -590,11 +630,21 @@ __device__ __forceinline__ int small_div(int n, int d, float inv) {
     return q;
 }
 
-// arena of the first agent of every tile (one thread per tile)
-__global__ void __launch_bounds__(256) obs_tiles_kernel(const int *off, int A, int n_total, int *tile_arena) {
-    const int n_tiles = (n_total + OBS_TA - 1) / OBS_TA;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x)
-        tile_arena[t] = A == 1 ? 0 : locate_arena(off, A, t * OBS_TA);
+// pre-pass: per-agent header {x, y, arena, index} in ABI order and per-tile arena (or -1 when the tile straddles
+// two arenas).  Takes the arena search and two levels of dependent loads off the render kernel's critical path.
+__global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr, int *tile_arena) {
+    const int n_tiles = (P.n_total + OBS_TA - 1) / OBS_TA;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < P.n_total; o += gridDim.x * blockDim.x) {
+        const int a = P.A == 1 ? 0 : locate_arena(P.off, P.A, o);
+        const int i = o - P.off[a];
+        const long gi = (long)a * P.cap + i;
+        hdr[o] = make_int4(P.x[gi], P.y[gi], a, i);
+        if (o % OBS_TA == 0) {
+            const int last = min(o + OBS_TA, P.n_total) - 1;
+            tile_arena[o / OBS_TA] = last < P.off[a + 1] ? a : -1;
+        }
+    }
+    (void)n_tiles;
 }
 
 // template tile of arena a: OBS_TA records, zero except the minimap channels (GridWorld.cc:374-381)
@@ -631,24 +681,24 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // this lane's view cells never change: keep their map offsets in registers
-    int ldx[OBS_NIT], ldy[OBS_NIT];
-#pragma unroll
-    for (int it = 0; it < OBS_NIT; ++it) {
-        const int cell = it * 32 + lane;
-        const int l = cell < P.cells ? lut[cell] : (int)0x00008ad0;      // dx = -30000: never in bounds
-        ldx[it] = (int)(short)(l & 0xffff); ldy[it] = l >> 16;
-    }
     const int nit = min(OBS_NIT, (P.cells + 31) >> 5);
     const int n_tiles = (P.n_total + OBS_TA - 1) / OBS_TA;
     const float inv_sw = 1.0f / (float)P.scale_w, inv_sh = 1.0f / (float)P.scale_h;
     unsigned phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // software pipeline: the header of the NEXT tile is fetched while the current one is composed
+    int tile = blockIdx.x;
+    int ta_next = -1;
+    int4 h_next = make_int4(0, 0, 0, 0);
+    if (tile < n_tiles) {
+        ta_next = P.tile_arena[tile];
+        if (tile * OBS_TA + warp < P.n_total) h_next = P.hdr[tile * OBS_TA + warp];
+    }
+    for (; tile < n_tiles; tile += gridDim.x) {
         const int t0 = tile * OBS_TA;
         const int cnt = min(OBS_TA, P.n_total - t0);
-        const int a0 = P.tile_arena[tile];
-        const int a0_hi = P.off[a0 + 1];
-        const bool use_tmpl = P.tmpl != nullptr && t0 + cnt <= a0_hi;     // whole tile inside arena a0 (block-uniform)
+        const int ta = ta_next;
+        const int4 h = h_next;
+        const bool use_tmpl = P.tmpl != nullptr && ta >= 0;          // whole tile inside arena ta (block-uniform)
         if (use_tmpl) {
             if (threadIdx.x == 0) {
                 // the previous tile's bulk store must have finished READING the buffer before TMA overwrites it
@@ -656,7 +706,7 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                              :: "r"(smem_u32(&mbar)), "r"(tile_bytes) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             :: "r"(smem_u32(buf)), "l"(P.tmpl + (size_t)a0 * OBS_TA * P.rec), "r"(tile_bytes),
+                             :: "r"(smem_u32(buf)), "l"(P.tmpl + (size_t)ta * OBS_TA * P.rec), "r"(tile_bytes),
                                 "r"(smem_u32(&mbar)) : "memory");
             }
         } else {
@@ -668,25 +718,32 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
         }
         const bool active = warp < cnt;
         const int o = t0 + warp;
-        int a = a0, ax = 0, ay = 0;
-        long gi = 0;
+        const int ax = h.x, ay = h.y, a = h.z;
+        const long gi = (long)a * P.cap + h.w;
+        const int *occ = P.occ + (long)a * P.W * P.H;
         int tcode[OBS_NIT];
 #pragma unroll
         for (int it = 0; it < OBS_NIT; ++it) tcode[it] = OCC_EMPTY;
-        const int *occ = nullptr;
+        int id = 0, act = 0;
+        float last_reward = 0.0f;
         if (active) {
-            int lo = P.off[a0];
-            if (o >= a0_hi) { a = locate_arena(P.off, P.A, o); lo = P.off[a]; }
-            gi = (long)a * P.cap + (o - lo);
-            ax = P.x[gi]; ay = P.y[gi];
-            occ = P.occ + (long)a * P.W * P.H;
             // issue this lane's occupancy loads back to back (they overlap the template load)
 #pragma unroll
             for (int it = 0; it < OBS_NIT; ++it) {
                 if (it < nit) {
-                    const int x = ax + ldx[it], y = ay + ldy[it];
+                    const int cell = it * 32 + lane;
+                    const int l = cell < P.cells ? lut[cell] : (int)0x00008ad0;
+                    const int x = ax + (int)(short)(l & 0xffff), y = ay + (l >> 16);
                     if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) tcode[it] = __ldg(occ + y * P.W + x);
                 }
+            }
+            id = P.id[gi]; act = P.act[gi]; last_reward = P.last_reward[gi];
+        }
+        {   // prefetch the next tile's header
+            const int nt = tile + gridDim.x;
+            if (nt < n_tiles) {
+                ta_next = P.tile_arena[nt];
+                if (nt * OBS_TA + warp < P.n_total) h_next = P.hdr[nt * OBS_TA + warp];
             }
         }
         if (use_tmpl) {                                           // wait for the template tile to land
@@ -745,8 +802,6 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
             }
             // non-spatial features straight to global memory (GridWorld.cc:386-396)
             {
-                const int id = P.id[gi], act = P.act[gi];
-                const float last_reward = P.last_reward[gi];
                 float fx = 0.0f, fy = 0.0f;
                 if (P.minimap) { fx = (float)ax / (float)P.W; fy = (float)ay / (float)P.H; }
                 for (int f = lane; f < P.F; f += 32) {
@@ -786,6 +841,8 @@ static float *g_tmpl = nullptr;
 static size_t g_tmpl_bytes = 0;
 static int *g_tile_arena = nullptr;
 static size_t g_tile_arena_n = 0;
+static int4 *g_obs_hdr = nullptr;
+static size_t g_obs_hdr_n = 0;
 
 void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total) {
     const int g = O.group;
@@ -822,12 +879,18 @@ void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const 
         g_tile_arena_n = (size_t)tiles + tiles / 4 + 64;
         CUDA_CHECK(cudaMalloc(&g_tile_arena, g_tile_arena_n * sizeof(int)));
     }
+    if ((size_t)n_total > g_obs_hdr_n) {
+        if (g_obs_hdr) cudaFree(g_obs_hdr);
+        g_obs_hdr_n = (size_t)n_total + n_total / 4 + 64;
+        CUDA_CHECK(cudaMalloc(&g_obs_hdr, g_obs_hdr_n * sizeof(int4)));
+    }
     P.tile_arena = g_tile_arena;
+    P.hdr = g_obs_hdr;
     {
-        int gt = (tiles + 255) / 256;
-        if (gt > 4 * g_sms) gt = 4 * g_sms;
-        obs_tiles_kernel<<<gt, 256>>>(P.off, P.A, n_total, g_tile_arena);
-        post_launch("obs_tiles_kernel");
+        int gt = (n_total + 255) / 256;
+        if (gt > 8 * g_sms) gt = 8 * g_sms;
+        obs_headers_kernel<<<gt, 256>>>(P, g_obs_hdr, g_tile_arena);
+        post_launch("obs_headers_kernel");
     }
     if (P.minimap && (tile_bytes & 15) == 0) {
         const size_t need = (size_t)hE.A * tile_bytes;

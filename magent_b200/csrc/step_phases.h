@@ -71,9 +71,8 @@ MG_HD int lflat(const EngineDev &E, int code) { return E.grp[code_group(code)].f
 // ------------------------------------------------------------------------------------------------
 // phase 0: reset per-step scratch
 template <class Ctx>
-MG_HD void phase_init(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+MG_HD void phase_init(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &all, const GroupEnum &ord) {
     ArenaRef R = arena_ref(E, a);
-    GroupEnum all; enum_all(E, a, all);
     for (int idx = c.tid(); idx < all.cnt; idx += c.nth()) {
         int g, i; enum_locate(all, idx, g, i);
         const AgentSoA &s = cur_soa(E, S.curmask, g);
@@ -92,19 +91,16 @@ MG_HD void phase_init(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
         R.hdr->n_attack = 0;
         R.hdr->rule_trigger = 0;
         R.hdr->rng_next = R.hdr->rng;
-        R.hdr->changed[0] = R.hdr->changed[1] = R.hdr->changed[2] = 0;
-        GroupEnum ord; enum_order(E, S, a, ord);
-        atomic_add64(&E.counters[CNT_AGENT_STEPS], ord.cnt);
-        if (a == 0) atomic_add64(&E.counters[CNT_STEPS], 1);
+        c.add_count(E, CNT_AGENT_STEPS, ord.cnt);
+        if (a == 0) c.add_count(E, CNT_STEPS, 1);
     }
 }
 
 // phase 1: position of every attack action in the attack buffer (reference GridWorld.cc:403-454 pushes
 // in set_action call order, then agent index order; dead-but-unculled agents are pushed too)
 template <class Ctx>
-MG_HD int phase_attack_scan(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+MG_HD int phase_attack_scan(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord) {
     ArenaRef R = arena_ref(E, a);
-    GroupEnum ord; enum_order(E, S, a, ord);
     auto pred = [&](int idx) -> int {
         int k, i; enum_locate(ord, idx, k, i);
         int g = ord.grp[k];
@@ -118,7 +114,7 @@ MG_HD int phase_attack_scan(Ctx &c, const EngineDev &E, const StepArgs &S, int a
     int total = c.scan(ord.cnt, pred, emit);
     if (c.tid() == 0) {
         R.hdr->n_attack = total;
-        atomic_add64(&E.counters[CNT_ATTACKS], total);
+        c.add_count(E, CNT_ATTACKS, total);
     }
     return total;
 }
@@ -179,9 +175,8 @@ MG_HD void phase_rank_target(Ctx &c, const EngineDev &E, const StepArgs &S, int 
 // Sequential semantics being reproduced: GridWorld.cc:475-506 + Map::do_attack (Map.cc:255-310) +
 // Agent::be_attack/add_hp (GridWorld.h:185,203-209).
 template <class Ctx>
-MG_HD bool phase_attack_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+MG_HD bool phase_attack_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &all) {
     ArenaRef R = arena_ref(E, a);
-    GroupEnum all; enum_all(E, a, all);
     bool changed = false;
     for (int idx = c.tid(); idx < all.cnt; idx += c.nth()) {
         int g, i; enum_locate(all, idx, g, i);
@@ -227,9 +222,8 @@ MG_HD bool phase_attack_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int
 
 // phase 5: commit attacks (attacker side and victim side) and starvation (GridWorld.cc:519-542)
 template <class Ctx>
-MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &all) {
     ArenaRef R = arena_ref(E, a);
-    GroupEnum all; enum_all(E, a, all);
     int kills = 0, hits = 0, starved = 0;
     for (int idx = c.tid(); idx < all.cnt; idx += c.nth()) {
         int g, i; enum_locate(all, idx, g, i);
@@ -282,16 +276,15 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
             atomic_add(&E.dead_ct[g * E.A + a], 1);
         }
     }
-    if (kills) atomic_add64(&E.counters[CNT_KILLS], kills);
-    if (hits) atomic_add64(&E.counters[CNT_HITS], hits);
-    if (starved) atomic_add64(&E.counters[CNT_STARVED], starved);
+    c.add_count(E, CNT_KILLS, kills);
+    c.add_count(E, CNT_HITS, hits);
+    c.add_count(E, CNT_STARVED, starved);
 }
 
 // phase 6: movers compute their target footprint and queue on every target cell
 template <class Ctx>
-MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord) {
     ArenaRef R = arena_ref(E, a);
-    GroupEnum ord; enum_order(E, S, a, ord);
     for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
         int k, i; enum_locate(ord, idx, k, i);
         int g = ord.grp[k];
@@ -361,9 +354,8 @@ MG_HD int occupant_at_turn(const EngineDev &E, const ArenaRef &R, int cx, int cy
 // phase 7 (swept until stable): a mover succeeds iff all its target cells are free at its turn
 // (Map::do_move / is_blank_area, Map.cc:313-358,454-470)
 template <class Ctx>
-MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord) {
     ArenaRef R = arena_ref(E, a);
-    GroupEnum ord; enum_order(E, S, a, ord);
     bool changed = false;
     for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
         int k, i; enum_locate(ord, idx, k, i);
@@ -388,9 +380,8 @@ MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a
 // phase 8: losers record what they bumped into (Map::get_collide, Map.cc:486-501; GridWorld sets
 // OP_COLLIDE, Map.cc:350-353)
 template <class Ctx>
-MG_HD void phase_move_collide(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+MG_HD void phase_move_collide(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord) {
     ArenaRef R = arena_ref(E, a);
-    GroupEnum ord; enum_order(E, S, a, ord);
     int ok_ct = 0, blocked = 0;
     for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
         int k, i; enum_locate(ord, idx, k, i);
@@ -418,15 +409,14 @@ MG_HD void phase_move_collide(Ctx &c, const EngineDev &E, const StepArgs &S, int
             s.op_obj[gi] = code_make(hg, hit - E.grp[hg].foff);
         }
     }
-    if (ok_ct) atomic_add64(&E.counters[CNT_MOVES_OK], ok_ct);
-    if (blocked) atomic_add64(&E.counters[CNT_MOVES_BLOCKED], blocked);
+    c.add_count(E, CNT_MOVES_OK, ok_ct);
+    c.add_count(E, CNT_MOVES_BLOCKED, blocked);
 }
 
 // phase 9a: winners vacate their old cells
 template <class Ctx>
-MG_HD void phase_move_clear(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+MG_HD void phase_move_clear(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord) {
     ArenaRef R = arena_ref(E, a);
-    GroupEnum ord; enum_order(E, S, a, ord);
     for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
         int k, i; enum_locate(ord, idx, k, i);
         int g = ord.grp[k];
@@ -444,9 +434,8 @@ MG_HD void phase_move_clear(Ctx &c, const EngineDev &E, const StepArgs &S, int a
 
 // phase 9b: winners occupy their new cells; every queued mover unhooks its claimant nodes
 template <class Ctx>
-MG_HD void phase_move_fill(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+MG_HD void phase_move_fill(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord) {
     ArenaRef R = arena_ref(E, a);
-    GroupEnum ord; enum_order(E, S, a, ord);
     for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
         int k, i; enum_locate(ord, idx, k, i);
         int g = ord.grp[k];
@@ -589,15 +578,18 @@ MG_HD void phase_done(Ctx &c, const EngineDev &E, int a) {
 }
 
 // relaxation driver: sweep until a full sweep changes nothing.  One team barrier per sweep; the
-// rotating flag triple makes the reset of the next flag race-free.
+// rotating flag triple makes the reset of the next flag race-free.  The flags live where the
+// team can see them cheaply: shared memory for a CTA team, the arena header in HBM for the grid team.
 template <class Ctx, class Sweep>
-MG_HD void relax_until_stable(Ctx &c, ArenaHdr *hdr, Sweep sweep) {
+MG_HD void relax_until_stable(Ctx &c, int *flags, Sweep sweep) {
+    if (c.tid() == 0) { st_volatile(&flags[0], 0); st_volatile(&flags[1], 0); st_volatile(&flags[2], 0); }
+    c.sync();
     for (int it = 0;; ++it) {
         int cur = it % 3, nxt = (it + 1) % 3;
-        if (c.tid() == 0) st_volatile(&hdr->changed[nxt], 0);
-        if (sweep()) st_volatile(&hdr->changed[cur], 1);
+        if (c.tid() == 0) st_volatile(&flags[nxt], 0);
+        if (sweep()) st_volatile(&flags[cur], 1);
         c.sync();
-        if (!ld_volatile(&hdr->changed[cur])) break;
+        if (!ld_volatile(&flags[cur])) break;
     }
 }
 
@@ -605,35 +597,36 @@ MG_HD void relax_until_stable(Ctx &c, ArenaHdr *hdr, Sweep sweep) {
 template <class Ctx>
 MG_HD void run_step(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
     ArenaHdr *hdr = E.hdr + a;
-    phase_init(c, E, S, a);
+    int *flags = c.flags(hdr);
+    GroupEnum all, ord;                       // group sizes are constant during a step: read them once
+    enum_all(E, a, all);
+    enum_order(E, S, a, ord);
+    phase_init(c, E, S, a, all, ord);
     c.sync();
-    int n_attack = phase_attack_scan(c, E, S, a);
+    int n_attack = phase_attack_scan(c, E, S, a, ord);
     c.sync();
     if (n_attack > 0) {
         phase_rng(c, E, a, n_attack);
         c.sync();
         phase_rank_target(c, E, S, a, n_attack);
-        c.sync();
-        relax_until_stable(c, hdr, [&]() { return phase_attack_relax(c, E, S, a); });
+        relax_until_stable(c, flags, [&]() { return phase_attack_relax(c, E, S, a, all); });
     }
-    phase_attack_apply_starve(c, E, S, a);
+    phase_attack_apply_starve(c, E, S, a, all);
     c.sync();
-    phase_move_register(c, E, S, a);
+    phase_move_register(c, E, S, a, ord);
+    relax_until_stable(c, flags, [&]() { return phase_move_relax(c, E, S, a, ord); });
+    phase_move_collide(c, E, S, a, ord);
     c.sync();
-    if (c.tid() == 0) { hdr->changed[0] = hdr->changed[1] = hdr->changed[2] = 0; }
+    phase_move_clear(c, E, S, a, ord);
     c.sync();
-    relax_until_stable(c, hdr, [&]() { return phase_move_relax(c, E, S, a); });
-    phase_move_collide(c, E, S, a);
-    c.sync();
-    phase_move_clear(c, E, S, a);
-    c.sync();
-    phase_move_fill(c, E, S, a);
+    phase_move_fill(c, E, S, a, ord);
     c.sync();
     for (int r = 0; r < E.n_rules; ++r) {
         phase_reward_rule(c, E, S, a, r);
         c.sync();
     }
     phase_done(c, E, a);
+    c.flush_counts(E);
     c.sync();
 }
 

@@ -19,6 +19,9 @@ struct HostCtx {
     int tid() const { return 0; }
     int nth() const { return 1; }
     void sync() {}
+    int *flags(ArenaHdr *hdr) { return hdr->changed; }
+    void add_count(const EngineDev &E, int kind, long long v) { E.counters[kind] += v; }
+    void flush_counts(const EngineDev &) {}
     template <class P, class Em> int scan(int n, P pred, Em emit) {
         int run = 0;
         for (int i = 0; i < n; ++i) if (pred(i)) emit(i, run++);
