@@ -614,7 +614,7 @@ struct ObsParams {
     const float *mm;                 // [A][G][cells] normalised minimap, or nullptr
     const float *tmpl;               // [A][OBS_TA*rec] template tiles (minimap channels filled), or nullptr
     const int *tile_arena;           // [n_tiles] arena of the tile, -1 when it straddles two arenas
-    const int4 *hdr;                 // [n_total] {x, y, arena, index} per agent in ABI order
+    const int4 *hdr;                 // [n_total][3] per-agent header in ABI order (obs_headers_kernel)
     float *view, *feature;
     int mm_ch[MG_MAX_GROUPS];        // observation channel of group j's minimap
     ObsGroupP grp[MG_MAX_GROUPS];
@@ -622,29 +622,31 @@ struct ObsParams {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// q = n / d for 0 <= n < 2^24 and d > 0, given inv = 1.0f / d: float estimate, then exact fix-up
-__device__ __forceinline__ int small_div(int n, int d, float inv) {
-    int q = (int)((float)n * inv);
-    if (q * d > n) --q;
-    else if ((q + 1) * d <= n) ++q;
-    return q;
-}
 
-// pre-pass: per-agent header {x, y, arena, index} in ABI order and per-tile arena (or -1 when the tile straddles
-// two arenas).  Takes the arena search and two levels of dependent loads off the render kernel's critical path.
+// pre-pass: per-agent header in ABI order -- everything the render kernel needs about the observer itself, so that
+// its only dependent loads are occupancy plane -> hp_norm:
+//   h0 = {x, y, arena, index}   h1 = {self minimap cell, id, last_action, bits(last_reward)}   h2 = {x/W, y/H, -, -}
+// plus, per tile, its arena (or -1 when the tile straddles two arenas).
 __global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr, int *tile_arena) {
-    const int n_tiles = (P.n_total + OBS_TA - 1) / OBS_TA;
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < P.n_total; o += gridDim.x * blockDim.x) {
         const int a = P.A == 1 ? 0 : locate_arena(P.off, P.A, o);
         const int i = o - P.off[a];
         const long gi = (long)a * P.cap + i;
-        hdr[o] = make_int4(P.x[gi], P.y[gi], a, i);
+        const int x = P.x[gi], y = P.y[gi];
+        int self_cell = -1;
+        float fx = 0.0f, fy = 0.0f;
+        if (P.minimap) {
+            self_cell = (y / P.scale_h) * P.vw + x / P.scale_w;             // GridWorld.cc:372-373
+            fx = (float)x / (float)P.W; fy = (float)y / (float)P.H;         // GridWorld.cc:394-395
+        }
+        hdr[3 * (size_t)o + 0] = make_int4(x, y, a, i);
+        hdr[3 * (size_t)o + 1] = make_int4(self_cell, P.id[gi], P.act[gi], __float_as_int(P.last_reward[gi]));
+        hdr[3 * (size_t)o + 2] = make_int4(__float_as_int(fx), __float_as_int(fy), 0, 0);
         if (o % OBS_TA == 0) {
             const int last = min(o + OBS_TA, P.n_total) - 1;
             tile_arena[o / OBS_TA] = last < P.off[a + 1] ? a : -1;
         }
     }
-    (void)n_tiles;
 }
 
 // template tile of arena a: OBS_TA records, zero except the minimap channels (GridWorld.cc:374-381)
@@ -663,41 +665,45 @@ __global__ void __launch_bounds__(256) obs_template_kernel(ObsParams P, float *t
     }
 }
 
-__global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_constant__ ObsParams P) {
+__global__ void __launch_bounds__(OBS_THREADS, 8) obs_render_kernel(const __grid_constant__ ObsParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *buf = (float *)smem_raw;                           // one tile: OBS_TA records
-    int *lut = (int *)(buf + OBS_TA * P.rec);                 // per view cell: packed (dy << 16 | dx); masked cells point far out
+    int *lut = (int *)(buf + OBS_TA * P.rec);                 // in-range view cells only: cell << 16 | (dy & 0xff) << 8 | (dx & 0xff)
     __shared__ __align__(8) unsigned long long mbar;
+    __shared__ int n_in_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned tile_bytes = (unsigned)OBS_TA * (unsigned)P.rec * 4u;
 
-    for (int cell = threadIdx.x; cell < P.cells; cell += OBS_THREADS) {
-        int vy = cell / P.vw, vx = cell - vy * P.vw;
-        int dx = P.mask[cell] ? P.ox + vx : -30000, dy = P.oy + vy;
-        lut[cell] = (int)(((unsigned)dy << 16) | ((unsigned)dx & 0xffffu));
-    }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {                                   // compact the circular view mask (CircleRange, Range.h:151-189)
+        int k = 0;
+        for (int cell = 0; cell < P.cells; ++cell)
+            if (P.mask[cell]) {
+                int vy = cell / P.vw, vx = cell - vy * P.vw;
+                lut[k++] = (cell << 16) | (((P.oy + vy) & 0xff) << 8) | ((P.ox + vx) & 0xff);
+            }
+        n_in_s = k;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int nit = min(OBS_NIT, (P.cells + 31) >> 5);
+    const int n_in = n_in_s;
+    const int nit = min(OBS_NIT, (n_in + 31) >> 5);
     const int n_tiles = (P.n_total + OBS_TA - 1) / OBS_TA;
-    const float inv_sw = 1.0f / (float)P.scale_w, inv_sh = 1.0f / (float)P.scale_h;
     unsigned phase = 0;
     // software pipeline: the header of the NEXT tile is fetched while the current one is composed
     int tile = blockIdx.x;
     int ta_next = -1;
-    int4 h_next = make_int4(0, 0, 0, 0);
+    int4 h0n = make_int4(0, 0, 0, 0), h1n = h0n, h2n = h0n;
     if (tile < n_tiles) {
         ta_next = P.tile_arena[tile];
-        if (tile * OBS_TA + warp < P.n_total) h_next = P.hdr[tile * OBS_TA + warp];
+        const int o = tile * OBS_TA + warp;
+        if (o < P.n_total) { h0n = P.hdr[3 * (size_t)o]; h1n = P.hdr[3 * (size_t)o + 1]; h2n = P.hdr[3 * (size_t)o + 2]; }
     }
     for (; tile < n_tiles; tile += gridDim.x) {
         const int t0 = tile * OBS_TA;
         const int cnt = min(OBS_TA, P.n_total - t0);
         const int ta = ta_next;
-        const int4 h = h_next;
+        const int4 h0 = h0n, h1 = h1n, h2 = h2n;
         const bool use_tmpl = P.tmpl != nullptr && ta >= 0;          // whole tile inside arena ta (block-uniform)
         if (use_tmpl) {
             if (threadIdx.x == 0) {
@@ -718,32 +724,32 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
         }
         const bool active = warp < cnt;
         const int o = t0 + warp;
-        const int ax = h.x, ay = h.y, a = h.z;
-        const long gi = (long)a * P.cap + h.w;
+        const int ax = h0.x, ay = h0.y, a = h0.z;
         const int *occ = P.occ + (long)a * P.W * P.H;
-        int tcode[OBS_NIT];
+        int tcode[OBS_NIT], tcell[OBS_NIT];
 #pragma unroll
         for (int it = 0; it < OBS_NIT; ++it) tcode[it] = OCC_EMPTY;
-        int id = 0, act = 0;
-        float last_reward = 0.0f;
         if (active) {
             // issue this lane's occupancy loads back to back (they overlap the template load)
 #pragma unroll
             for (int it = 0; it < OBS_NIT; ++it) {
                 if (it < nit) {
-                    const int cell = it * 32 + lane;
-                    const int l = cell < P.cells ? lut[cell] : (int)0x00008ad0;
-                    const int x = ax + (int)(short)(l & 0xffff), y = ay + (l >> 16);
-                    if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) tcode[it] = __ldg(occ + y * P.W + x);
+                    const int k = it * 32 + lane;
+                    if (k < n_in) {
+                        const int l = lut[k];
+                        const int x = ax + (int)(signed char)(l & 0xff), y = ay + (int)(signed char)((l >> 8) & 0xff);
+                        tcell[it] = l >> 16;
+                        if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) tcode[it] = __ldg(occ + y * P.W + x);
+                    }
                 }
             }
-            id = P.id[gi]; act = P.act[gi]; last_reward = P.last_reward[gi];
         }
         {   // prefetch the next tile's header
             const int nt = tile + gridDim.x;
             if (nt < n_tiles) {
                 ta_next = P.tile_arena[nt];
-                if (nt * OBS_TA + warp < P.n_total) h_next = P.hdr[nt * OBS_TA + warp];
+                const int on = nt * OBS_TA + warp;
+                if (on < P.n_total) { h0n = P.hdr[3 * (size_t)on]; h1n = P.hdr[3 * (size_t)on + 1]; h2n = P.hdr[3 * (size_t)on + 2]; }
             }
         }
         if (use_tmpl) {                                           // wait for the template tile to land
@@ -759,7 +765,6 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
         if (active) {
             float *dst = buf + warp * P.rec;
             if (P.minimap) {
-                const int self_cell = small_div(ay, P.scale_h, inv_sh) * P.vw + small_div(ax, P.scale_w, inv_sw);
                 if (!use_tmpl) {                                   // tile straddles arenas: no template
                     const float *mm = P.mm + (long)a * P.G * P.cells;
                     for (int r = lane; r < P.G * P.cells; r += 32) {
@@ -768,13 +773,13 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
                     }
                     __syncwarp();
                 }
-                if (lane < P.G) dst[self_cell * P.C + P.mm_ch[lane]] += 1.0f;           // GridWorld.cc:382
+                if (lane < P.G) dst[h1.x * P.C + P.mm_ch[lane]] += 1.0f;               // self marker, GridWorld.cc:382
             }
 #pragma unroll
             for (int it = 0; it < OBS_NIT; ++it) {
                 const int t = tcode[it];
                 if (t != OCC_EMPTY) {
-                    float *px = dst + (it * 32 + lane) * P.C;
+                    float *px = dst + tcell[it] * P.C;
                     if (t == OCC_WALL) px[0] = 1.0f;
                     else {
                         const ObsGroupP &T = P.grp[code_group(t)];
@@ -783,39 +788,32 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_render_kernel(const __grid_co
                     }
                 }
             }
-            for (int base = OBS_NIT * 32; base < P.cells; base += 32) {        // views wider than 256 cells
-                const int cell = base + lane;
-                if (cell < P.cells) {
-                    const int l = lut[cell];
-                    const int x = ax + (int)(short)(l & 0xffff), y = ay + (l >> 16);
-                    if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) {
-                        const int t = __ldg(occ + y * P.W + x);
-                        float *px = dst + cell * P.C;
-                        if (t == OCC_WALL) px[0] = 1.0f;
-                        else if (t >= 0) {
-                            const ObsGroupP &T = P.grp[code_group(t)];
-                            px[T.ch] = 1.0f;
-                            px[T.ch + 1] = T.hpn[(long)a * T.cap + code_index(t)];
-                        }
+            for (int k = OBS_NIT * 32 + lane; k < n_in; k += 32) {                      // views with > 256 in-range cells
+                const int l = lut[k];
+                const int x = ax + (int)(signed char)(l & 0xff), y = ay + (int)(signed char)((l >> 8) & 0xff);
+                if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) {
+                    const int t = __ldg(occ + y * P.W + x);
+                    float *px = dst + (l >> 16) * P.C;
+                    if (t == OCC_WALL) px[0] = 1.0f;
+                    else if (t >= 0) {
+                        const ObsGroupP &T = P.grp[code_group(t)];
+                        px[T.ch] = 1.0f;
+                        px[T.ch + 1] = T.hpn[(long)a * T.cap + code_index(t)];
                     }
                 }
             }
-            // non-spatial features straight to global memory (GridWorld.cc:386-396)
-            {
-                float fx = 0.0f, fy = 0.0f;
-                if (P.minimap) { fx = (float)ax / (float)P.W; fy = (float)ay / (float)P.H; }
-                for (int f = lane; f < P.F; f += 32) {
-                    float v = 0.0f;
-                    if (f < P.embedding) v = f < 31 ? (float)((id >> f) & 1) : 0.0f;
-                    else {
-                        const int kk = f - P.embedding;
-                        if (kk < P.n_action) v = kk == act ? 1.0f : 0.0f;
-                        else if (kk == P.n_action) v = last_reward;
-                        else if (P.minimap && kk == P.n_action + 1) v = fx;
-                        else if (P.minimap && kk == P.n_action + 2) v = fy;
-                    }
-                    P.feature[(size_t)o * P.F + f] = v;
+            // non-spatial features straight to global memory (GridWorld.cc:386-396); all inputs come from the header
+            for (int f = lane; f < P.F; f += 32) {
+                float v = 0.0f;
+                if (f < P.embedding) v = f < 31 ? (float)((h1.y >> f) & 1) : 0.0f;
+                else {
+                    const int kk = f - P.embedding;
+                    if (kk < P.n_action) v = kk == h1.z ? 1.0f : 0.0f;
+                    else if (kk == P.n_action) v = __int_as_float(h1.w);
+                    else if (P.minimap && kk == P.n_action + 1) v = __int_as_float(h2.x);
+                    else if (P.minimap && kk == P.n_action + 2) v = __int_as_float(h2.y);
                 }
+                P.feature[(size_t)o * P.F + f] = v;
             }
         }
         // make the generic-proxy writes visible to the async proxy, then one thread fires the bulk store
@@ -882,7 +880,7 @@ void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const 
     if ((size_t)n_total > g_obs_hdr_n) {
         if (g_obs_hdr) cudaFree(g_obs_hdr);
         g_obs_hdr_n = (size_t)n_total + n_total / 4 + 64;
-        CUDA_CHECK(cudaMalloc(&g_obs_hdr, g_obs_hdr_n * sizeof(int4)));
+        CUDA_CHECK(cudaMalloc(&g_obs_hdr, 3 * g_obs_hdr_n * sizeof(int4)));
     }
     P.tile_arena = g_tile_arena;
     P.hdr = g_obs_hdr;
