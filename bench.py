@@ -196,7 +196,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             pass
@@ -240,8 +240,8 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="battle512", choices=sorted(WORKLOADS))
     ap.add_argument("--arenas", type=int, default=None, help="override arenas per GPU")
@@ -353,7 +353,6 @@ def main():
     obs_ms, obs_launches = env.get_profile()
     env.set_profiling(False)
     barrier()
-    clocks = sampler.stop() if sampler else None
     c1 = env.get_counters()
     launches = env.launch_count() - l0
     agent_steps = c1[0] - c0[0]
@@ -412,6 +411,7 @@ def main():
                "timing": "host wall clock around the API loop (includes PCIe copies and syncs), max over ranks",
                "host_buffers": "page-locked numpy arrays owned by the wrapper"}
 
+    clocks = sampler.stop() if sampler else None      # sampled across the device-timed and the e2e timed regions
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -36,6 +36,8 @@ void launch_offsets(const EngineDev *dE, const EngineDev &hE);
 // per-call preparation of get_observation: normalised minimap into mm_val ([A][G][view cells]; nullptr when
 // minimap_mode is off) plus whatever the backend wants to precompute for the render kernel
 void launch_obs_prepare(const EngineDev *dE, const EngineDev &hE, unsigned curmask, int obs_group, float *mm_val);
+// true while the backend-side products of the last launch_obs_prepare still belong to this engine block
+bool obs_prepare_valid(const EngineDev *dE);
 void launch_obs(const EngineDev *dE, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total);
 void launch_info(const EngineDev *dE, const EngineDev &hE, unsigned curmask, int kind, int group,
                  void *buf, int n_total);

@@ -286,21 +286,24 @@ constexpr int GRID_THREADS = 512;       // block size of the cooperative whole-g
 
 // bytes of per-arena step scratch (the arrays step_scratch_to_smem() re-homes)
 static size_t step_scratch_bytes(int cap_total, int max_body) {
-    return (size_t)cap_total * (14 * 4 + 4 * (size_t)max_body) + (((size_t)cap_total + 15) & ~(size_t)15);
+    return (size_t)cap_total * (9 * 4 + 4 * (size_t)max_body) + (((size_t)cap_total + 15) & ~(size_t)15);
 }
 
 // Point the scratch arrays of the CTA's private EngineDev copy at dynamic shared memory.  One CTA works on one
 // arena at a time, so the scratch needs no per-arena stride (scratch_stride = 0): every dependent load of the
-// relaxation / list walks becomes an LDS instead of an L2/HBM round trip.
+// relaxation / list walks becomes an LDS instead of an L2/HBM round trip.  The shuffle scratch (dead after
+// phase_rank_target) shares storage with the mover scratch (first written in phase_attack_apply_starve):
+// 41 B/agent => two 2x1000-agent arenas per SM.
 __device__ __forceinline__ void step_scratch_to_smem(EngineDev *sE, unsigned char *base) {
     const size_t n = (size_t)sE->cap_total;
     int *p = (int *)base;
     sE->att_rank = p; p += n;  sE->tgt = p; p += n;       sE->in_head = p; p += n;  sE->in_next = p; p += n;
-    sE->death = p; p += n;     sE->mv_nx = p; p += n;     sE->mv_ny = p; p += n;
-    sE->mv_key = (unsigned *)p; p += n;                   sE->hp_fin = (float *)p; p += n;
-    sE->jv = p; p += n;        sE->sh_head = p; p += n;   sE->sh_next = p; p += n;  sE->sh_first = p; p += n;
-    sE->att_agent = p; p += n;
-    sE->cl_next = p; p += n * sE->max_body;
+    sE->death = p; p += n;
+    sE->mv_nx = p; sE->jv = p; p += n;
+    sE->mv_ny = p; sE->sh_head = p; p += n;
+    sE->mv_key = (unsigned *)p; sE->sh_next = p; p += n;
+    sE->hp_fin = (float *)p; sE->att_agent = p; p += n;
+    sE->cl_next = p; sE->sh_first = p; p += n * sE->max_body;
     sE->mv_state = (unsigned char *)p;
     sE->scratch_stride = 0;
 }
@@ -382,7 +385,8 @@ void launch_step(const EngineDev *dE, const EngineDev &hE, const StepArgs &S, in
         size_t smem = 0;
         if (in_smem) {
             smem = sbytes;
-            threads = max_agents >= 768 ? 1024 : (max_agents >= 384 ? 512 : 256);
+            // few arenas: one wide CTA each; many arenas: narrower CTAs so that two fit on an SM and overlap
+            threads = max_agents >= 768 ? (hE.A > g_sms ? 512 : 1024) : (max_agents >= 384 ? 512 : 256);
             static size_t configured = 0;
             if (smem > configured) {
                 CUDA_CHECK(cudaFuncSetAttribute(step_kernel_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -500,15 +504,18 @@ void launch_random_actions(const EngineDev *dE, const EngineDev &, unsigned curm
 
 // ------------------------------------------------------------------------------------------------
 // obs_prepare: one pass over every agent of every group per get_observation call:
-//   * hp_norm = hp / max_hp, the f32 divide of Map.cc:197, done ONCE per agent instead of once per observer
-//     that sees it (the render kernel then only loads it);
+//   * hp_norm plane: hpn_plane[cell] = hp / max_hp of the agent standing on the cell -- the f32 divide of Map.cc:197
+//     done ONCE per agent instead of once per observer that sees it, and stored NEXT TO the occupancy plane so the
+//     render kernel fetches cell code and hp with two independent loads (no position -> plane -> agent chain).
+//     Only living agents own cells (dead ones were cleared in the step), stale values under empty cells are never read;
 //   * minimap (when enabled): counts per (arena, group, coarse cell); value = (float)count / (float)group size
-static float *g_hpn[MG_MAX_GROUPS] = {nullptr};
-static size_t g_hpn_n[MG_MAX_GROUPS] = {0};
-struct HpnPtrs { float *p[MG_MAX_GROUPS]; };
+static float *g_hpn_plane = nullptr;
+static size_t g_hpn_plane_n = 0;
+static const EngineDev *g_prepare_owner = nullptr;
+bool obs_prepare_valid(const EngineDev *dE) { return g_prepare_owner == dE; }
 
 __global__ void __launch_bounds__(256) obs_prepare_kernel(const EngineDev *gE, unsigned curmask, int og, int chunk,
-                                                          HpnPtrs hpn, int do_minimap) {
+                                                          float *hpn_plane, int do_minimap) {
     extern __shared__ int hist[];
     const EngineDev &E = *gE;
     const int ag = blockIdx.y;               // a * G + j
@@ -522,13 +529,19 @@ __global__ void __launch_bounds__(256) obs_prepare_kernel(const EngineDev *gE, u
         for (int k = threadIdx.x; k < cells; k += blockDim.x) hist[k] = 0;
         __syncthreads();
     }
-    const AgentSoA &s = E.grp[j].soa[(curmask >> j) & 1u];
+    const GroupDev &G = E.grp[j];
+    const AgentSoA &s = G.soa[(curmask >> j) & 1u];
     const int scale_h = (E.H + vh - 1) / vh, scale_w = (E.W + vw - 1) / vw;
-    const float max_hp = E.grp[j].max_hp;
+    float *plane = hpn_plane + (size_t)a * E.W * E.H;
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        long gi = (long)a * E.grp[j].cap + i;
-        hpn.p[j][gi] = s.hp[gi] / max_hp;
-        if (do_minimap) atomicAdd(&hist[(s.y[gi] / scale_h) * vw + s.x[gi] / scale_w], 1);
+        long gi = (long)a * G.cap + i;
+        const int x = s.x[gi], y = s.y[gi];
+        if (!(s.flags[gi] & FLAG_DEAD)) {
+            const float v = s.hp[gi] / G.max_hp;
+            for (int bx = 0; bx < G.body_w; ++bx)
+                for (int by = 0; by < G.body_l; ++by) plane[(y + by) * E.W + x + bx] = v;
+        }
+        if (do_minimap) atomicAdd(&hist[(y / scale_h) * vw + x / scale_w], 1);
     }
     if (do_minimap) {
         __syncthreads();
@@ -551,22 +564,20 @@ __global__ void __launch_bounds__(256) minimap_norm_kernel(const EngineDev *gE, 
 void launch_obs_prepare(const EngineDev *dE, const EngineDev &hE, unsigned curmask, int og, float *mm_val) {
     const int cells = hE.grp[og].view_w * hE.grp[og].view_h;
     const int total = hE.A * hE.G * cells;
-    HpnPtrs hp;
     int cap_max = 0;
-    for (int g = 0; g < hE.G; ++g) {
-        cap_max = cap_max > hE.grp[g].cap ? cap_max : hE.grp[g].cap;
-        const size_t need = (size_t)hE.A * hE.grp[g].cap;
-        if (need > g_hpn_n[g]) {
-            if (g_hpn[g]) cudaFree(g_hpn[g]);
-            CUDA_CHECK(cudaMalloc(&g_hpn[g], need * sizeof(float)));
-            g_hpn_n[g] = need;
-        }
-        hp.p[g] = g_hpn[g];
+    for (int g = 0; g < hE.G; ++g) cap_max = cap_max > hE.grp[g].cap ? cap_max : hE.grp[g].cap;
+    const size_t plane_n = (size_t)hE.A * hE.W * hE.H;
+    if (plane_n > g_hpn_plane_n) {
+        if (g_hpn_plane) cudaFree(g_hpn_plane);
+        CUDA_CHECK(cudaMalloc(&g_hpn_plane, plane_n * sizeof(float)));
+        CUDA_CHECK(cudaMemsetAsync(g_hpn_plane, 0, plane_n * sizeof(float), 0));
+        g_hpn_plane_n = plane_n;
     }
     if (mm_val) CUDA_CHECK(cudaMemsetAsync(hE.mm_count, 0, (size_t)total * 4, 0));
     const int chunk = 4096;
     dim3 grid((cap_max + chunk - 1) / chunk, hE.A * hE.G);
-    obs_prepare_kernel<<<grid, 256, cells * sizeof(int)>>>(dE, curmask, og, chunk, hp, mm_val ? 1 : 0);
+    g_prepare_owner = dE;
+    obs_prepare_kernel<<<grid, 256, cells * sizeof(int)>>>(dE, curmask, og, chunk, g_hpn_plane, mm_val ? 1 : 0);
     post_launch("obs_prepare_kernel");
     if (mm_val) {
         int g2 = (total + 255) / 256;
@@ -596,11 +607,13 @@ void launch_obs_prepare(const EngineDev *dE, const EngineDev &hE, unsigned curma
 // occupancy planes, hp arrays and template tiles stay L1/L2-hot while the output streams past.
 // Algorithmic traffic per agent: 4*(view_h*view_w*n_channel + feature) bytes written, plus one compulsory read
 // of the occupancy plane per arena.  No tensor cores: there is no contraction on this path.
-constexpr int OBS_TA = 4;
+#ifndef OBS_TA_N
+#define OBS_TA_N 4
+#endif
+constexpr int OBS_TA = OBS_TA_N;      // agents per tile (multiple of 4: 16-byte aligned tile ranges)
 constexpr int OBS_THREADS = 32 * OBS_TA;
 constexpr int OBS_NIT = 8;           // view cells per lane handled in one unrolled batch (8*32 = 256 cells)
 
-struct ObsGroupP { const float *hpn; int cap; int ch; };      // hpn = hp / max_hp from obs_prepare_kernel
 struct ObsParams {
     int A, W, H, G, C;
     int vw, vh, cells, rec, F;
@@ -609,6 +622,7 @@ struct ObsParams {
     int cap, embedding, n_action, n_total;
     const unsigned char *mask;
     const int *off, *occ;
+    const float *hpn_plane;          // [A][H*W] hp / max_hp of the occupant (obs_prepare_kernel)
     const int *x, *y, *id, *act;
     const float *last_reward;
     const float *mm;                 // [A][G][cells] normalised minimap, or nullptr
@@ -617,7 +631,7 @@ struct ObsParams {
     const int4 *hdr;                 // [n_total][3] per-agent header in ABI order (obs_headers_kernel)
     float *view, *feature;
     int mm_ch[MG_MAX_GROUPS];        // observation channel of group j's minimap
-    ObsGroupP grp[MG_MAX_GROUPS];
+    int grp_ch[MG_MAX_GROUPS];       // observation channel ('has'; hp is +1) of group j
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -665,7 +679,10 @@ __global__ void __launch_bounds__(256) obs_template_kernel(ObsParams P, float *t
     }
 }
 
-__global__ void __launch_bounds__(OBS_THREADS, 8) obs_render_kernel(const __grid_constant__ ObsParams P) {
+#ifndef OBS_MIN_CTAS
+#define OBS_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(OBS_THREADS, OBS_MIN_CTAS) obs_render_kernel(const __grid_constant__ ObsParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *buf = (float *)smem_raw;                           // one tile: OBS_TA records
     int *lut = (int *)(buf + OBS_TA * P.rec);                 // in-range view cells only: cell << 16 | (dy & 0xff) << 8 | (dx & 0xff)
@@ -726,11 +743,13 @@ __global__ void __launch_bounds__(OBS_THREADS, 8) obs_render_kernel(const __grid
         const int o = t0 + warp;
         const int ax = h0.x, ay = h0.y, a = h0.z;
         const int *occ = P.occ + (long)a * P.W * P.H;
-        int tcode[OBS_NIT], tcell[OBS_NIT];
+        const float *hpnp = P.hpn_plane + (long)a * P.W * P.H;
+        int tcode[OBS_NIT];
+        float thp[OBS_NIT];
 #pragma unroll
-        for (int it = 0; it < OBS_NIT; ++it) tcode[it] = OCC_EMPTY;
+        for (int it = 0; it < OBS_NIT; ++it) { tcode[it] = OCC_EMPTY; thp[it] = 0.0f; }
         if (active) {
-            // issue this lane's occupancy loads back to back (they overlap the template load)
+            // issue this lane's plane loads (cell code + hp_norm, independent) back to back; they overlap the template load
 #pragma unroll
             for (int it = 0; it < OBS_NIT; ++it) {
                 if (it < nit) {
@@ -738,8 +757,10 @@ __global__ void __launch_bounds__(OBS_THREADS, 8) obs_render_kernel(const __grid
                     if (k < n_in) {
                         const int l = lut[k];
                         const int x = ax + (int)(signed char)(l & 0xff), y = ay + (int)(signed char)((l >> 8) & 0xff);
-                        tcell[it] = l >> 16;
-                        if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) tcode[it] = __ldg(occ + y * P.W + x);
+                        if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) {
+                            tcode[it] = __ldg(occ + y * P.W + x);
+                            thp[it] = __ldg(hpnp + y * P.W + x);
+                        }
                     }
                 }
             }
@@ -779,12 +800,12 @@ __global__ void __launch_bounds__(OBS_THREADS, 8) obs_render_kernel(const __grid
             for (int it = 0; it < OBS_NIT; ++it) {
                 const int t = tcode[it];
                 if (t != OCC_EMPTY) {
-                    float *px = dst + tcell[it] * P.C;
+                    float *px = dst + (lut[it * 32 + lane] >> 16) * P.C;
                     if (t == OCC_WALL) px[0] = 1.0f;
                     else {
-                        const ObsGroupP &T = P.grp[code_group(t)];
-                        px[T.ch] = 1.0f;
-                        px[T.ch + 1] = T.hpn[(long)a * T.cap + code_index(t)];              // hp / max_hp (Map.cc:197)
+                        const int ch = P.grp_ch[code_group(t)];
+                        px[ch] = 1.0f;
+                        px[ch + 1] = thp[it];                                           // hp / max_hp (Map.cc:197)
                     }
                 }
             }
@@ -796,9 +817,9 @@ __global__ void __launch_bounds__(OBS_THREADS, 8) obs_render_kernel(const __grid
                     float *px = dst + (l >> 16) * P.C;
                     if (t == OCC_WALL) px[0] = 1.0f;
                     else if (t >= 0) {
-                        const ObsGroupP &T = P.grp[code_group(t)];
-                        px[T.ch] = 1.0f;
-                        px[T.ch + 1] = T.hpn[(long)a * T.cap + code_index(t)];
+                        const int ch = P.grp_ch[code_group(t)];
+                        px[ch] = 1.0f;
+                        px[ch + 1] = __ldg(hpnp + y * P.W + x);
                     }
                 }
             }
@@ -856,6 +877,7 @@ void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const 
     P.mask = G.view_mask;
     P.off = hE.off + (size_t)g * (hE.A + 1);
     P.occ = hE.occ;
+    P.hpn_plane = g_hpn_plane;
     const AgentSoA &s = G.soa[(O.curmask >> g) & 1u];
     P.x = s.x; P.y = s.y; P.id = s.id; P.act = s.act; P.last_reward = s.last_reward;
     P.mm = mm_val; P.view = O.view; P.feature = O.feature;
@@ -864,8 +886,7 @@ void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const 
         int rel = j - g; if (rel < 0) rel += hE.G;
         const int ch = hE.channel_base + rel * stride;                 // make_channel_trans, GridWorld.cc:897-913
         P.mm_ch[j] = ch + 2;
-        P.grp[j].hpn = g_hpn[j];
-        P.grp[j].cap = hE.grp[j].cap; P.grp[j].ch = ch;
+        P.grp_ch[j] = ch;
     }
     const size_t tile_bytes = (size_t)OBS_TA * P.rec * sizeof(float);
     const size_t smem = tile_bytes + (size_t)P.cells * sizeof(int);

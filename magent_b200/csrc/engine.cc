@@ -659,6 +659,7 @@ void Engine::to_device() {
         be::h2d(hE_.off, h_off_.data(), h_off_.size() * 4);
     }
     be::h2d(dE_, &hE_, sizeof(EngineDev));
+    ++state_version_;
     where_ = DEVICE;
 }
 
@@ -735,7 +736,11 @@ void Engine::get_observation(int group, float **bufs) {               // GridWor
         }
         O.feature = d_feat_stage_;
     }
-    be::launch_obs_prepare(dE_, hE_, curmask_, group, minimap_mode_ ? d_mm_val_ : nullptr);
+    if (prep_version_ != state_version_ || prep_vw_ != t.view.width || prep_vh_ != t.view.height ||
+        !be::obs_prepare_valid(dE_)) {
+        be::launch_obs_prepare(dE_, hE_, curmask_, group, minimap_mode_ ? d_mm_val_ : nullptr);
+        prep_version_ = state_version_; prep_vw_ = t.view.width; prep_vh_ = t.view.height;
+    }
     be::launch_obs(dE_, hE_, O, minimap_mode_ ? d_mm_val_ : nullptr, n);
     if (!vdev) be::d2h(bufs[0], d_view_stage_, vbytes);
     if (!fdev) be::d2h(bufs[1], d_feat_stage_, fbytes);
@@ -773,6 +778,7 @@ void Engine::step(int *done) {                                        // GridWor
     S.n_order = (int)order_.size();
     for (int k = 0; k < S.n_order; ++k) S.order[k] = order_[k];
     be::launch_step(dE_, hE_, S, max_agents_per_arena());
+    ++state_version_;
     order_.clear();
     std::vector<int> d(A_);
     be::d2h(d.data(), hE_.done, (size_t)A_ * 4);
@@ -795,6 +801,7 @@ void Engine::get_reward(int group, float *buf) {                      // GridWor
 void Engine::clear_dead() {                                           // GridWorld.cc:633-665
     to_device();
     be::launch_cull(dE_, hE_, curmask_, max_agents_per_arena());
+    ++state_version_;
     curmask_ ^= (1u << G()) - 1u;
     be::launch_offsets(dE_, hE_);
     be::d2h(h_off_.data(), hE_.off, h_off_.size() * 4);

@@ -130,6 +130,9 @@ private:
     void *d_io_stage_ = nullptr; size_t io_stage_bytes_ = 0;
     int *pin_small_ = nullptr; size_t pin_small_ints_ = 0;
     unsigned long long rand_calls_ = 0;
+    // get_observation pre-pass products (hp_norm plane, minimap) stay valid until the state changes
+    unsigned long long state_version_ = 1, prep_version_ = 0;
+    int prep_vw_ = 0, prep_vh_ = 0;
 
     int G() const { return (int)group_type_.size(); }
     int group2channel(int g) const;

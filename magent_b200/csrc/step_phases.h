@@ -82,8 +82,6 @@ MG_HD void phase_init(Ctx &c, const EngineDev &E, const StepArgs &S, int a, cons
         E.tgt[f] = -1;
         E.in_head[f] = -1;
         E.death[f] = dead ? DEATH_BEFORE : DEATH_NEVER;
-        E.mv_key[f] = MVKEY_NONE;
-        E.mv_state[f] = MV_NONE;
         E.sh_head[R.sb + idx] = -1;          // shuffle scratch is indexed by buffer position < n_attack <= cnt
         E.sh_first[R.sb + idx] = DEATH_NEVER;
     }
@@ -231,6 +229,9 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
         const AgentSoA &s = cur_soa(E, S.curmask, g);
         long gi = gidx(E, a, g, i);
         long f = R.sb + G.foff + i;
+        // mover scratch is (re)initialised here, after the shuffle scratch it may share storage with is dead
+        E.mv_key[f] = MVKEY_NONE;
+        E.mv_state[f] = MV_NONE;
         if (s.flags[gi] & FLAG_DEAD) continue;
         int d = E.death[f];
         int r = E.att_rank[f];

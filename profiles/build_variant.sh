@@ -1,0 +1,16 @@
+#!/bin/bash
+# build an experimental variant of the engine library: profiles/build_variant.sh <name> [-DFLAG=V ...]
+# -> magent_b200/lib/variants/libmagent_<name>.so ; select it with MAGENT_B200_LIB=<path>
+set -e
+root="$(cd "$(dirname "$0")/.." && pwd)"
+name="$1"; shift
+out="$root/magent_b200/lib/variants"; mkdir -p "$out"
+src="$root/magent_b200/csrc"
+for f in engine.cc shim.cc backend_cuda.cu; do
+  /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -ccbin /usr/bin/g++ \
+    -Xcompiler -fPIC,-fvisibility=hidden --expt-relaxed-constexpr "$@" -x cu -c "$src/$f" -o "$out/${name}_${f%.*}.o"
+done
+/usr/local/cuda/bin/nvcc -shared -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -Xlinker -Bsymbolic \
+  -o "$out/libmagent_$name.so" "$out/${name}_engine.o" "$out/${name}_shim.o" "$out/${name}_backend_cuda.o"
+rm -f "$out/${name}_"*.o
+echo "$out/libmagent_$name.so"

@@ -60,6 +60,7 @@ void launch_offsets(const EngineDev *dE, const EngineDev &) {
         for (int a = 0; a < E.A; ++a) off[a + 1] = off[a] + E.n[g * E.A + a];
     }
 }
+bool obs_prepare_valid(const EngineDev *) { return true; }
 void launch_obs_prepare(const EngineDev *dE, const EngineDev &, unsigned curmask, int og, float *mm_val) {
     if (!mm_val) return;
     const EngineDev &E = *dE;

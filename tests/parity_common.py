@@ -222,3 +222,16 @@ def make_mixed(lib, map_size=36, seed=6, **kw):
     env.add_agents(h[1], method="random", n=160)
     env.add_agents(h[2], method="random", n=60)
     return env
+
+
+def make_battle_rect(lib, width=56, height=34, n=120, seed=2, **kw):
+    """non-square map: map_width != map_height (minimap scales, feature x/W y/H, bounds all differ per axis)"""
+    import magent_b200 as magent
+    cfg = magent.builtin.config.battle.get_config(40)
+    cfg.set({"map_width": width, "map_height": height})
+    env = magent.GridWorld(cfg, _lib=lib, **kw)
+    env.set_seed(seed)
+    env.reset()
+    for h in env.get_handles():
+        env.add_agents(h, method="random", n=n)
+    return env

@@ -94,6 +94,39 @@ def test_mixed_three_groups_big_view_rules():
     both(lambda lib: pc.make_mixed(lib, 36, 6), 60, 6, order=[2, 0, 1])
 
 
+def test_non_square_map():
+    both(lambda lib: pc.make_battle_rect(lib), 40, 2)
+
+
+def test_episodes_share_one_rng_stream():
+    """reset() keeps the engine RNG running (GridWorld.cc:29,72-118): three episodes on one env, device -> host ->
+    device round trips included"""
+    import magent_b200 as magent
+
+    def run(lib):
+        env = magent.GridWorld("battle", map_size=30, _lib=lib)
+        env.set_seed(9)
+        hs = env.get_handles()
+        rs = np.random.RandomState(9)
+        out = []
+        for ep in range(3):
+            env.reset()
+            for h in hs:
+                env.add_agents(h, method="random", n=100 + 20 * ep)
+            for t in range(12):
+                for h in hs:
+                    v, f = env.get_observation(h)
+                    out.append(pc.sha(v) + pc.sha(f))
+                for h in hs:
+                    env.set_action(h, rs.randint(0, 21, size=env.get_num(h)).astype(np.int32))
+                out.append(env.step())
+                out.append([env.get_reward(h).round(6).tolist() for h in hs])
+                out.append([env.get_pos(h).tolist() for h in hs])
+                env.clear_dead()
+        return out
+    assert run(checker_lib()) == run(pc.CUDA_LIB)
+
+
 def test_unculled_dead_agents_keep_their_slots():
     """no clear_dead between steps: dead agents stay in the vectors, still get actions, are skipped"""
     import magent_b200  # noqa: F401
