@@ -279,6 +279,7 @@ def main():
             "gpu_launches": 0}))
         return
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line
     import numpy as np
     import torch
     import torch.distributed as dist

@@ -127,6 +127,37 @@ def test_episodes_share_one_rng_stream():
     assert run(checker_lib()) == run(pc.CUDA_LIB)
 
 
+def test_empty_group_observation_and_actions():
+    """a group with no agents: its calls are no-ops, the other group still observes (its minimap channel for the
+    empty group is 0/0 = NaN in the reference; NaN payloads differ between x86 and the GPU, so NaNs compare as a class)"""
+    import magent_b200 as magent
+
+    def run(lib):
+        env = magent.GridWorld("battle", map_size=30, _lib=lib)
+        env.reset()
+        h = env.get_handles()
+        env.add_agents(h[0], method="custom", pos=[[5, 5], [8, 9], [20, 11]])
+        assert env.get_num(h[1]) == 0
+        v, f = env.get_observation(h[0])
+        v, f = v.copy(), f.copy()
+        env.set_action(h[0], np.array([3, 4, 15], dtype=np.int32))
+        env.set_action(h[1], np.zeros((0,), dtype=np.int32))
+        done = env.step()
+        r = env.get_reward(h[0]).copy()
+        assert env.get_reward(h[1]).shape == (0,) and env.get_alive(h[1]).shape == (0,)
+        env.clear_dead()
+        return v, f, done, r, env.get_pos(h[0]).copy()
+    a, b = run(checker_lib()), run(pc.CUDA_LIB)
+    assert a[2] == b[2] is True
+    np.testing.assert_array_equal(np.isnan(a[0]), np.isnan(b[0]))
+    assert np.isnan(a[0]).any()
+    ok = ~np.isnan(a[0])
+    np.testing.assert_array_equal(a[0][ok].view(np.uint32), b[0][ok].view(np.uint32))
+    np.testing.assert_array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    np.testing.assert_allclose(a[3], b[3], atol=pc.REWARD_TOL, rtol=0)
+    np.testing.assert_array_equal(a[4], b[4])
+
+
 def test_unculled_dead_agents_keep_their_slots():
     """no clear_dead between steps: dead agents stay in the vectors, still get actions, are skipped"""
     import magent_b200  # noqa: F401
