@@ -173,8 +173,11 @@ def run_cpu_baseline(workload, budget_steps=None):
         outs = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in procs]
         return sum(o["agent_steps"] for o in outs) / max(o["seconds"] for o in outs)
     tried = {}
-    for p in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
-        tried["%d procs x 1 thread" % p] = (launch(p, 1), p)
+    if wl["arenas"] > 1:      # independent arenas: the CPU can run one per process
+        for p in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
+            tried["%d procs x 1 thread" % p] = (launch(p, 1), p)
+    else:                     # a single arena cannot be split across processes: one process, 1..N OpenMP threads
+        tried["1 proc x 1 thread"] = (launch(1, 1), 1)
     omp = min(cores, 16)                      # the reference's own harness uses 8-16 OpenMP threads (scripts/test/test_fps.py:22-36)
     tried["1 proc x %d OpenMP threads" % omp] = (launch(1, omp), omp)
     how = max(tried, key=lambda k: tried[k][0])

@@ -145,6 +145,20 @@ __device__ __forceinline__ int block_excl_scan(int v, int &total) {
 }
 
 struct CtaCtx {
+    GroupEnum *enum_smem;
+    MG_HD GroupEnum *enums() { return enum_smem; }
+    MG_HD bool is_cta_leader() const {
+#if defined(__CUDA_ARCH__)
+        return threadIdx.x == 0;
+#else
+        return true;
+#endif
+    }
+    MG_HD void sync_cta() {
+#if defined(__CUDA_ARCH__)
+        __syncthreads();
+#endif
+    }
     int *flag_smem;
     MG_HD int *flags(ArenaHdr *) { return flag_smem; }
     int cnt[MG_N_COUNTERS];
@@ -201,6 +215,20 @@ struct CtaCtx {
 };
 
 struct GridCtx {
+    GroupEnum *enum_smem;
+    MG_HD GroupEnum *enums() { return enum_smem; }
+    MG_HD bool is_cta_leader() const {
+#if defined(__CUDA_ARCH__)
+        return threadIdx.x == 0;
+#else
+        return true;
+#endif
+    }
+    MG_HD void sync_cta() {
+#if defined(__CUDA_ARCH__)
+        __syncthreads();
+#endif
+    }
     int *scratch;       // [2][4096]
     int parity;
     MG_HD int *flags(ArenaHdr *hdr) { return hdr->changed; }
@@ -317,8 +345,10 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_cta(const EngineDev 
         __syncthreads();
     }
     __shared__ int relax_flags[3];
+    __shared__ GroupEnum enum_store[2];
     CtaCtx c;
     c.flag_smem = relax_flags;
+    c.enum_smem = enum_store;
     for (int k = 0; k < MG_N_COUNTERS; ++k) c.cnt[k] = 0;
     for (int a = blockIdx.x; a < sE.A; a += gridDim.x) run_step(c, sE, S, a);
 }
@@ -326,9 +356,11 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_cta(const EngineDev 
 __global__ void __launch_bounds__(STEP_THREADS) step_kernel_grid(const EngineDev *gE, StepArgs S) {
     __shared__ EngineDev sE;
     load_engine(&sE, gE);
+    __shared__ GroupEnum enum_store[2];
     GridCtx c;
     c.scratch = sE.team_scratch;
     c.parity = 0;
+    c.enum_smem = enum_store;
     for (int k = 0; k < MG_N_COUNTERS; ++k) c.cnt[k] = 0;
     for (int a = 0; a < sE.A; ++a) run_step(c, sE, S, a);
 }
@@ -338,6 +370,7 @@ __global__ void __launch_bounds__(STEP_THREADS) cull_kernel_cta(const EngineDev 
     load_engine(&sE, gE);
     CtaCtx c;
     c.flag_smem = nullptr;
+    c.enum_smem = nullptr;
     for (int a = blockIdx.x; a < sE.A; a += gridDim.x) run_cull(c, sE, curmask, a);
 }
 
@@ -347,6 +380,7 @@ __global__ void __launch_bounds__(STEP_THREADS) cull_kernel_grid(const EngineDev
     GridCtx c;
     c.scratch = sE.team_scratch;
     c.parity = 0;
+    c.enum_smem = nullptr;
     for (int a = 0; a < sE.A; ++a) run_cull(c, sE, curmask, a);
 }
 
@@ -691,16 +725,23 @@ __global__ void __launch_bounds__(OBS_THREADS, OBS_MIN_CTAS) obs_render_kernel(c
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned tile_bytes = (unsigned)OBS_TA * (unsigned)P.rec * 4u;
 
-    if (threadIdx.x == 0) {                                   // compact the circular view mask (CircleRange, Range.h:151-189)
-        int k = 0;
-        for (int cell = 0; cell < P.cells; ++cell)
-            if (P.mask[cell]) {
-                int vy = cell / P.vw, vx = cell - vy * P.vw;
-                lut[k++] = (cell << 16) | (((P.oy + vy) & 0xff) << 8) | ((P.ox + vx) & 0xff);
+    if (warp == 0) {                                          // compact the circular view mask (CircleRange, Range.h:151-189)
+        int k = 0;                                            // order-preserving: ballot prefix per 32 cells
+        for (int base = 0; base < P.cells; base += 32) {
+            const int cell = base + lane;
+            const bool in = cell < P.cells && P.mask[cell];
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const int vy = cell / P.vw, vx = cell - vy * P.vw;
+                lut[k + __popc(bal & ((1u << lane) - 1u))] = (cell << 16) | (((P.oy + vy) & 0xff) << 8) | ((P.ox + vx) & 0xff);
             }
-        n_in_s = k;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            k += __popc(bal);
+        }
+        if (lane == 0) {
+            n_in_s = k;
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
     }
     __syncthreads();
     const int n_in = n_in_s;

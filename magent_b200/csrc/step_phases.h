@@ -599,9 +599,12 @@ template <class Ctx>
 MG_HD void run_step(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
     ArenaHdr *hdr = E.hdr + a;
     int *flags = c.flags(hdr);
-    GroupEnum all, ord;                       // group sizes are constant during a step: read them once
-    enum_all(E, a, all);
-    enum_order(E, S, a, ord);
+    // group sizes are constant during a step: read them once, into storage every thread of the CTA can index
+    // cheaply (shared memory on the device: a dynamically indexed per-thread struct would live in local memory)
+    GroupEnum *en = c.enums();
+    if (c.is_cta_leader()) { enum_all(E, a, en[0]); enum_order(E, S, a, en[1]); }
+    c.sync_cta();
+    const GroupEnum &all = en[0], &ord = en[1];
     phase_init(c, E, S, a, all, ord);
     c.sync();
     int n_attack = phase_attack_scan(c, E, S, a, ord);

@@ -19,6 +19,10 @@ struct HostCtx {
     int tid() const { return 0; }
     int nth() const { return 1; }
     void sync() {}
+    void sync_cta() {}
+    bool is_cta_leader() const { return true; }
+    GroupEnum en_[2];
+    GroupEnum *enums() { return en_; }
     int *flags(ArenaHdr *hdr) { return hdr->changed; }
     void add_count(const EngineDev &E, int kind, long long v) { E.counters[kind] += v; }
     void flush_counts(const EngineDev &) {}

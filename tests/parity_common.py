@@ -235,3 +235,35 @@ def make_battle_rect(lib, width=56, height=34, n=120, seed=2, **kw):
     for h in env.get_handles():
         env.add_agents(h, method="random", n=n)
     return env
+
+
+def multi4_config(size):
+    """two armies of two unit types each: 4 groups, 13 channels, 16 rules (values of examples/train_multi.py:19-73)"""
+    import magent_b200 as magent
+    gw = magent.gridworld
+    cfg = gw.Config()
+    cfg.set({"map_width": size, "map_height": size, "minimap_mode": True, "embedding_size": 10})
+    common = dict(width=1, length=1, damage=2, step_recover=0.1, attack_in_group=True,
+                  step_reward=-0.01, kill_reward=0, dead_penalty=-0.1, attack_penalty=-1)
+    melee = cfg.register_agent_type("melee", dict(common, hp=10, speed=1, view_range=gw.CircleRange(6),
+                                                  attack_range=gw.CircleRange(1)))
+    ranged = cfg.register_agent_type("ranged", dict(common, hp=3, speed=2, view_range=gw.CircleRange(6),
+                                                    attack_range=gw.CircleRange(2)))
+    groups = [cfg.add_group(t) for t in (melee, ranged, melee, ranged)]
+    sym = [gw.AgentSymbol(g, index='any') for g in groups]
+    for verb, value in (('attack', 2), ('kill', 100)):
+        for mine, theirs in (((0, 1), (2, 3)), ((2, 3), (0, 1))):
+            for m in mine:
+                for t in theirs:
+                    cfg.add_reward_rule(gw.Event(sym[m], verb, sym[t]), receiver=sym[m], value=value)
+    return cfg
+
+
+def make_multi4(lib, map_size=40, seed=8, n=70, **kw):
+    import magent_b200 as magent
+    env = magent.GridWorld(multi4_config(map_size), _lib=lib, **kw)
+    env.set_seed(seed)
+    env.reset()
+    for h in env.get_handles():
+        env.add_agents(h, method="random", n=n)
+    return env

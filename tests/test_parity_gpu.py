@@ -94,6 +94,11 @@ def test_mixed_three_groups_big_view_rules():
     both(lambda lib: pc.make_mixed(lib, 36, 6), 60, 6, order=[2, 0, 1])
 
 
+def test_four_groups_sixteen_rules():
+    """the examples/train_multi.py game: 2 unit types x 2 armies, 13 channels, 16 attack/kill rules"""
+    both(lambda lib: pc.make_multi4(lib), 50, 8, order=[3, 1, 0, 2])
+
+
 def test_non_square_map():
     both(lambda lib: pc.make_battle_rect(lib), 40, 2)
 
