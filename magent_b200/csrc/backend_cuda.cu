@@ -566,18 +566,25 @@ __global__ void __launch_bounds__(256) obs_prepare_kernel(const EngineDev *gE, u
     const GroupDev &G = E.grp[j];
     const AgentSoA &s = G.soa[(curmask >> j) & 1u];
     const int scale_h = (E.H + vh - 1) / vh, scale_w = (E.W + vw - 1) / vw;
+    const bool skip_absorbed = E.grp[og].can_absorb != 0;     // GridWorld.cc:343-347 (the OBSERVER's type decides)
     float *plane = hpn_plane + (size_t)a * E.W * E.H;
+    int counted = 0;
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         long gi = (long)a * G.cap + i;
         const int x = s.x[gi], y = s.y[gi];
-        if (!(s.flags[gi] & FLAG_DEAD)) {
+        const unsigned char fl = s.flags[gi];
+        if (!(fl & FLAG_DEAD)) {
             const float v = s.hp[gi] / G.max_hp;
             for (int bx = 0; bx < G.body_w; ++bx)
                 for (int by = 0; by < G.body_l; ++by) plane[(y + by) * E.W + x + bx] = v;
         }
-        if (do_minimap) atomicAdd(&hist[(y / scale_h) * vw + x / scale_w], 1);
+        if (do_minimap && !(skip_absorbed && (fl & FLAG_ABSORBED))) {
+            atomicAdd(&hist[(y / scale_h) * vw + x / scale_w], 1);
+            ++counted;
+        }
     }
     if (do_minimap) {
+        if (counted) atomicAdd(&E.mm_total[ag], counted);
         __syncthreads();
         int *out = E.mm_count + (size_t)ag * cells;
         for (int k = threadIdx.x; k < cells; k += blockDim.x)
@@ -591,7 +598,8 @@ __global__ void __launch_bounds__(256) minimap_norm_kernel(const EngineDev *gE, 
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
         int ag = k / cells;
         int a = ag / E.G, j = ag - a * E.G;
-        mm_val[k] = (float)E.mm_count[k] / (float)E.n[j * E.A + a];       // GridWorld.cc:350-357
+        mm_val[k] = (float)E.mm_count[k] / (float)E.mm_total[ag];         // GridWorld.cc:350-357 (total_ct)
+        (void)a; (void)j;
     }
 }
 
@@ -607,7 +615,10 @@ void launch_obs_prepare(const EngineDev *dE, const EngineDev &hE, unsigned curma
         CUDA_CHECK(cudaMemsetAsync(g_hpn_plane, 0, plane_n * sizeof(float), 0));
         g_hpn_plane_n = plane_n;
     }
-    if (mm_val) CUDA_CHECK(cudaMemsetAsync(hE.mm_count, 0, (size_t)total * 4, 0));
+    if (mm_val) {
+        CUDA_CHECK(cudaMemsetAsync(hE.mm_count, 0, (size_t)total * 4, 0));
+        CUDA_CHECK(cudaMemsetAsync(hE.mm_total, 0, (size_t)hE.A * hE.G * 4, 0));
+    }
     const int chunk = 4096;
     dim3 grid((cap_max + chunk - 1) / chunk, hE.A * hE.G);
     g_prepare_owner = dE;

@@ -28,7 +28,7 @@ enum : unsigned { MVKEY_NONE = 0xffffffffu };
 // agent flags
 enum : unsigned char { FLAG_DEAD = 1, FLAG_ABSORBED = 2 };
 // mover states
-enum : unsigned char { MV_NONE = 0, MV_OOB = 1, MV_STATIC_FAIL = 2, MV_PENDING_FAIL = 3, MV_OK = 4 };
+enum : unsigned char { MV_NONE = 0, MV_OOB = 1, MV_STATIC_FAIL = 2, MV_PENDING_FAIL = 3, MV_OK = 4, MV_ABSORBED = 5 };
 
 // EventOp numbering of the reference (src/gridworld/grid_def.h:17-23)
 enum EventOp : unsigned char { OP_AND = 0, OP_OR, OP_NOT, OP_KILL, OP_AT, OP_IN, OP_COLLIDE, OP_ATTACK,
@@ -56,6 +56,7 @@ struct GroupDev {
     float max_hp, damage, step_recover, kill_supply;
     float step_reward, kill_reward, dead_penalty, attack_penalty;
     int attack_in_group;
+    int can_absorb;                           // AgentType::can_absorb (Map.cc:341-349)
     int view_w, view_h, view_x1, view_y1;     // view rectangle and its left-top offset from the eye
     int view_xoff, view_yoff;                 // eye offset from pos  (= width/2, length/2)
     int att_xoff, att_yoff;
@@ -111,6 +112,7 @@ struct EngineDev {
     int nsep, bandwidth, large_map;           // GridWorld.cc:75-85, :407
     int minimap_mode, embedding_size, n_channel, channel_base;
     int cap_total, max_body;
+    int any_absorb;                           // some group's type has can_absorb
     int scratch_stride;                       // per-arena stride of the step scratch: cap_total in HBM, 0 when it lives in the CTA's shared memory
     uint32_t pow2[32];                        // 16807^(2^b) mod (2^31-1)
     GroupDev grp[MG_MAX_GROUPS];
@@ -131,6 +133,7 @@ struct EngineDev {
     long long *counters;                      // [MG_N_COUNTERS]
     int *team_scratch;                        // [2 * max CTAs] partial sums of team scans
     int *mm_count;                            // [A][G][max_view_cells] minimap histogram scratch
+    int *mm_total;                            // [A][G] agents counted into the minimap
 };
 
 struct StepArgs {

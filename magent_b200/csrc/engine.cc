@@ -156,7 +156,6 @@ void Engine::register_agent_type(const char *name, int n, const char **keys, flo
             strequ(k, "att_y_offset") || strequ(k, "turn_x_offset") || strequ(k, "turn_y_offset")) continue;
         fatal("invalid agent config in AgentType::AgentType : %s", k);
     }
-    if (t.can_absorb) fatal("can_absorb agent types are not supported by the B200 engine yet (SURVEY.md §8f rank 1)");
     if (t.width < 1 || t.length < 1 || t.width * t.length > 16) fatal("unsupported body size %dx%d", t.width, t.length);
 
     int parity = t.width % 2;                         // AgentType.cc:86-105
@@ -553,6 +552,8 @@ void Engine::to_device() {
             D.step_reward = t.step_reward; D.kill_reward = t.kill_reward;
             D.dead_penalty = t.dead_penalty; D.attack_penalty = t.attack_penalty;
             D.attack_in_group = t.attack_in_group;
+            D.can_absorb = t.can_absorb;
+            if (t.can_absorb) hE_.any_absorb = 1;
             D.view_w = t.view.width; D.view_h = t.view.height; D.view_x1 = t.view.x1; D.view_y1 = t.view.y1;
             D.view_xoff = t.view_x_offset; D.view_yoff = t.view_y_offset;
             D.att_xoff = t.att_x_offset; D.att_yoff = t.att_y_offset;
@@ -595,6 +596,7 @@ void Engine::to_device() {
         be::dmemset(hE_.counters, 0, sizeof(long long) * MG_N_COUNTERS);
         hE_.team_scratch = (int *)dalloc(sizeof(int) * 2 * 4096);
         hE_.mm_count = (int *)dalloc((size_t)A_ * Gn * max_cells * 4);
+        hE_.mm_total = (int *)dalloc((size_t)A_ * Gn * 4);
         d_mm_val_ = (float *)dalloc((size_t)A_ * Gn * max_cells * 4);
         dE_ = (EngineDev *)dalloc(sizeof(EngineDev));
     }
@@ -905,6 +907,7 @@ void Engine::get_info(int group, const char *name, void *void_buffer) {        /
                 const HostGroup &hg = ar.groups[g];
                 for (int j = 0; j < hg.size(); j++) {
                     if (hg.x[j] < x1 || hg.x[j] > x2 || hg.y[j] < y1 || hg.y[j] > y2) continue;
+                    if (group_type_[g]->can_absorb && !(hg.flags[j] & FLAG_ABSORBED)) continue;     // GridWorld.cc:821
                     ib[ct * 4] = hg.id[j]; ib[ct * 4 + 1] = hg.x[j]; ib[ct * 4 + 2] = hg.y[j]; ib[ct * 4 + 3] = g; ct++;
                 }
             }

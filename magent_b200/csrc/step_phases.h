@@ -316,7 +316,8 @@ MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, in
         for (int bx = 0; bx < bw; ++bx)
             for (int by = 0; by < bh; ++by)
                 if (R.occ[(ny + by) * E.W + nx + bx] == OCC_WALL) wall = true;
-        if (wall) { E.mv_state[f] = MV_STATIC_FAIL; continue; }
+        // with absorbing types around, a wall-blocked mover may still bump into an absorber: keep it in the relaxation
+        if (wall && !E.any_absorb) { E.mv_state[f] = MV_STATIC_FAIL; continue; }
         E.mv_state[f] = MV_PENDING_FAIL;
         int ci = 0;
         for (int bx = 0; bx < bw; ++bx)
@@ -335,7 +336,9 @@ MG_HD int occupant_at_turn(const EngineDev &E, const ArenaRef &R, int cx, int cy
     if (o >= 0) {
         int fo = lflat(E, o);
         if (fo != self) {
-            bool left = ld_volatile(&E.mv_state[R.sb + fo]) == MV_OK && E.mv_key[R.sb + fo] < key;
+            const unsigned char so = ld_volatile(&E.mv_state[R.sb + fo]);
+            if (so == MV_ABSORBED && E.mv_key[R.sb + fo] < key) goto claimants;     // it died into an absorber: cell vacated
+            bool left = so == MV_OK && E.mv_key[R.sb + fo] < key;
             if (left) {
                 const GroupDev &GO = E.grp[code_group(o)];
                 int ox = E.mv_nx[R.sb + fo], oy = E.mv_ny[R.sb + fo];
@@ -344,6 +347,7 @@ MG_HD int occupant_at_turn(const EngineDev &E, const ArenaRef &R, int cx, int cy
             if (!left) return fo;
         }
     }
+claimants:
     for (int node = R.claim[cell]; node != -1; node = E.cl_next[R.nb + node]) {
         int fm = node / E.max_body;
         if (fm != self && E.mv_key[R.sb + fm] < key && ld_volatile(&E.mv_state[R.sb + fm]) == MV_OK)
@@ -365,14 +369,44 @@ MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a
         int fs = G.foff + i;
         long f = R.sb + fs;
         unsigned char st = E.mv_state[f];
-        if (st != MV_PENDING_FAIL && st != MV_OK) continue;
+        if (st != MV_PENDING_FAIL && st != MV_OK && st != MV_ABSORBED) continue;
         unsigned key = E.mv_key[f];
         int nx = E.mv_nx[f], ny = E.mv_ny[f];
         bool ok = true;
-        for (int bx = 0; bx < G.body_w && ok; ++bx)
-            for (int by = 0; by < G.body_l && ok; ++by)
-                if (occupant_at_turn(E, R, nx + bx, ny + by, key, fs) != -1) ok = false;
-        unsigned char ns = ok ? MV_OK : MV_PENDING_FAIL;
+        unsigned char ns;
+        if (!E.any_absorb) {
+            for (int bx = 0; bx < G.body_w && ok; ++bx)
+                for (int by = 0; by < G.body_l && ok; ++by)
+                    if (occupant_at_turn(E, R, nx + bx, ny + by, key, fs) != -1) ok = false;
+            ns = ok ? MV_OK : MV_PENDING_FAIL;
+        } else {
+            // Map::do_move with can_absorb types (Map.cc:334-349): the first other agent in the footprint decides
+            int hit = -1, hit_cell = -1;
+            for (int bx = 0; bx < G.body_w; ++bx)
+                for (int by = 0; by < G.body_l; ++by) {
+                    const int cell = (ny + by) * E.W + nx + bx;
+                    if (R.occ[cell] == OCC_WALL) { ok = false; continue; }
+                    const int o = occupant_at_turn(E, R, nx + bx, ny + by, key, fs);
+                    if (o != -1) { ok = false; if (hit == -1) { hit = o; hit_cell = cell; } }
+                }
+            ns = ok ? MV_OK : MV_PENDING_FAIL;
+            if (!ok && hit != -1) {
+                int hg = 0;
+                while (hg + 1 < E.G && hit >= E.grp[hg + 1].foff) ++hg;
+                const int hcode = code_make(hg, hit - E.grp[hg].foff);
+                if (E.grp[hg].can_absorb &&
+                    !(cur_soa(E, S.curmask, hg).flags[gidx(E, a, hg, code_index(hcode))] & FLAG_ABSORBED)) {
+                    // absorbed already by an earlier mover of this step?  every mover that bumps into `hit` queues on hit_cell
+                    bool taken = false;
+                    for (int node = R.claim[hit_cell]; node != -1 && !taken; node = E.cl_next[R.nb + node]) {
+                        const int fm = node / E.max_body;
+                        if (fm != fs && E.mv_key[R.sb + fm] < key && ld_volatile(&E.mv_state[R.sb + fm]) == MV_ABSORBED &&
+                            ld_volatile(&E.tgt[R.sb + fm]) == hcode) taken = true;
+                    }
+                    if (!taken) { st_volatile(&E.tgt[f], hcode); ns = MV_ABSORBED; }
+                }
+            }
+        }
         if (ns != st) { st_volatile(&E.mv_state[f], ns); changed = true; }
     }
     return changed;
@@ -395,6 +429,20 @@ MG_HD void phase_move_collide(Ctx &c, const EngineDev &E, const StepArgs &S, int
         if (st == MV_NONE) continue;
         ++blocked;
         if (st == MV_OOB) continue;
+        if (st == MV_ABSORBED) {                  // Map.cc:341-349: the absorber doubles its hp, the mover disappears
+            const int obj = E.tgt[f];
+            const int og = code_group(obj);
+            const AgentSoA &so = cur_soa(E, S.curmask, og);
+            const long oi = gidx(E, a, og, code_index(obj));
+            so.flags[oi] |= FLAG_ABSORBED;
+            so.hp[oi] = so.hp[oi] * 2;
+            const AgentSoA &s = cur_soa(E, S.curmask, g);
+            const long gi = gidx(E, a, g, i);
+            s.flags[gi] |= FLAG_DEAD;             // set_dead(true): no dead_penalty, dead_ct untouched (reference quirk)
+            s.last_op[gi] = OP_COLLIDE;
+            s.op_obj[gi] = obj;
+            continue;
+        }
         unsigned key = E.mv_key[f];
         int nx = E.mv_nx[f], ny = E.mv_ny[f];
         int hit = -1;
@@ -404,6 +452,7 @@ MG_HD void phase_move_collide(Ctx &c, const EngineDev &E, const StepArgs &S, int
         if (hit != -1) {
             int hg = 0;
             while (hg + 1 < E.G && hit >= E.grp[hg + 1].foff) ++hg;
+            if (E.grp[hg].can_absorb) continue;  // bumping into an already absorbed absorber records nothing
             const AgentSoA &s = cur_soa(E, S.curmask, g);
             long gi = gidx(E, a, g, i);
             s.last_op[gi] = OP_COLLIDE;
@@ -423,7 +472,7 @@ MG_HD void phase_move_clear(Ctx &c, const EngineDev &E, const StepArgs &S, int a
         int g = ord.grp[k];
         const GroupDev &G = E.grp[g];
         long f = R.sb + G.foff + i;
-        if (E.mv_state[f] != MV_OK) continue;
+        if (E.mv_state[f] != MV_OK && E.mv_state[f] != MV_ABSORBED) continue;
         const AgentSoA &s = cur_soa(E, S.curmask, g);
         long gi = gidx(E, a, g, i);
         int x = s.x[gi], y = s.y[gi];
@@ -443,7 +492,7 @@ MG_HD void phase_move_fill(Ctx &c, const EngineDev &E, const StepArgs &S, int a,
         const GroupDev &G = E.grp[g];
         long f = R.sb + G.foff + i;
         unsigned char st = E.mv_state[f];
-        if (st != MV_OK && st != MV_PENDING_FAIL) continue;
+        if (st != MV_OK && st != MV_PENDING_FAIL && st != MV_ABSORBED) continue;
         int nx = E.mv_nx[f], ny = E.mv_ny[f];
         bool ok = st == MV_OK;
         int code = code_make(g, i);

@@ -12,7 +12,7 @@
  * It restates the SEQUENTIAL semantics (the reference is only deterministic with OMP_NUM_THREADS=1,
  * SURVEY.md §0): each function cites the reference lines it follows.  Not restated (no shipped config on
  * the hot path uses them; the functions abort with a message): turn_mode, food_mode, goal_mode,
- * SectorRange, can_absorb, OP_ALIGN, render, DiscreteSnake.
+ * SectorRange, OP_ALIGN, render, DiscreteSnake.
  */
 #include <math.h>
 #include <stdbool.h>
@@ -68,7 +68,7 @@ typedef struct {
     int width, length;
     float speed, hp, view_radius, view_angle, attack_radius, attack_angle;
     float damage, step_recover, kill_supply;
-    int attack_in_group;
+    int attack_in_group, can_absorb;
     float step_reward, kill_reward, dead_penalty, attack_penalty;
     Range view, attack, move;
     int attack_base, n_action;
@@ -77,7 +77,7 @@ typedef struct {
 /* ---- agents live in a pool; cells and groups refer to pool slots ---- */
 typedef struct {
     int id, group, index, x, y, action, last_op, op_obj, involved;
-    bool dead;
+    bool dead, absorbed;
     float hp, next_reward, last_reward;
 } Agent;
 
@@ -190,7 +190,7 @@ API int gridworld_register_agent_type(void *game, const char *name, int n, const
         else if (!strcmp(k, "kill_reward")) t->kill_reward = v;
         else if (!strcmp(k, "dead_penalty")) t->dead_penalty = v;
         else if (!strcmp(k, "attack_penalty")) t->attack_penalty = v;
-        else if (!strcmp(k, "can_absorb")) { if ((int)(v + 0.5)) die("not restated: ", k); }
+        else if (!strcmp(k, "can_absorb")) t->can_absorb = (int)(v + 0.5) != 0;
         else if (!strcmp(k, "hear_radius") || !strcmp(k, "speak_radius") || !strcmp(k, "speak_ability") ||
                  !strcmp(k, "trace") || !strcmp(k, "eat_ability") || !strcmp(k, "food_supply") ||
                  !strcmp(k, "view_x_offset") || !strcmp(k, "view_y_offset") || !strcmp(k, "att_x_offset") ||
@@ -374,6 +374,7 @@ API int env_get_observation(void *game, int g, float **bufs) {      /* GridWorld
             size_t total = 0;
             for (int k = 0; k < e->grp[j].n; k++) {
                 const Agent *b = &e->pool[e->grp[j].slot[k]];
+                if (t->can_absorb && b->absorbed) continue;          /* :346 (the observer's type decides) */
                 mini[((b->y / scale_h) * vw + b->x / scale_w) * e->ngroup + j]++;
                 total++;
             }
@@ -569,7 +570,7 @@ API int env_step(void *game, int *done) {                           /* GridWorld
         for (int i = 0; i < e->move[b].n; i++) {
             int s = e->move[b].v[i].agent;
             Agent *a = &e->pool[s];
-            if (a->dead) continue;
+            if (a->dead || a->absorbed) continue;
             const Type *t = &e->type[e->grp[a->group].type];
             int nx = a->x + t->move.dx[e->move[b].v[i].action], ny = a->y + t->move.dy[e->move[b].v[i].action];
             if (blank_area(e, nx, ny, t->width, t->length, s)) {
@@ -578,7 +579,16 @@ API int env_step(void *game, int *done) {                           /* GridWorld
                 a->x = nx; a->y = ny;
             } else {
                 int o = first_other(e, nx, ny, t->width, t->length, s);
-                if (o >= 0) { a->last_op = OP_COLLIDE; a->op_obj = o; }
+                if (o >= 0 && e->type[e->grp[e->pool[o].group].type].can_absorb) {   /* Map.cc:341-349 */
+                    Agent *obj = &e->pool[o];
+                    if (!obj->absorbed) {
+                        obj->absorbed = true;
+                        obj->hp = obj->hp * 2;
+                        a->dead = true;                               /* no dead_penalty, dead_ct untouched */
+                        paint(e, a->x, a->y, t->width, t->length, CELL_EMPTY);
+                        a->last_op = OP_COLLIDE; a->op_obj = o;
+                    }
+                } else if (o >= 0) { a->last_op = OP_COLLIDE; a->op_obj = o; }
             }
         }
         e->move[b].n = 0;

@@ -75,13 +75,16 @@ void launch_obs_prepare(const EngineDev *dE, const EngineDev &, unsigned curmask
             std::vector<int> cnt(cells, 0);
             int n = E.n[j * E.A + a];
             const AgentSoA &s = cur_soa(E, curmask, j);
+            int total = 0;
             for (int i = 0; i < n; ++i) {
+                if (OG.can_absorb && (s.flags[gidx(E, a, j, i)] & FLAG_ABSORBED)) continue;   // GridWorld.cc:343-347
                 int cx, cy;
                 minimap_cell(E, OG.view_w, OG.view_h, s.x[gidx(E, a, j, i)], s.y[gidx(E, a, j, i)], cx, cy);
                 cnt[cy * OG.view_w + cx]++;
+                total++;
             }
             float *out = mm_val + ((size_t)a * E.G + j) * cells;
-            for (int k = 0; k < cells; ++k) out[k] = (float)cnt[k] / (float)n;
+            for (int k = 0; k < cells; ++k) out[k] = (float)cnt[k] / (float)total;
         }
 }
 void launch_obs(const EngineDev *dE, const EngineDev &, const ObsArgs &O, const float *mm_val, int) {

@@ -23,6 +23,7 @@ SCENARIOS = {
     "mixed_3groups": (lambda lib: pc.make_mixed(lib, 36, 6), 60, 6, {"order": [2, 0, 1]}),
     "battle_rect": (lambda lib: pc.make_battle_rect(lib), 40, 2, {}),
     "multi4": (lambda lib: pc.make_multi4(lib), 50, 8, {"order": [3, 1, 0, 2]}),
+    "arrange_absorb": (lambda lib: pc.make_arrange(lib), 60, 12, {"act_groups": [1], "stop_on_done": False}),
     "gather_infight": (lambda lib: pc.make_gather(lib, 24, 2, n_agent=150, n_food=60), 40, 2, {"act_groups": [1]}),
 }
 FULL_OBS_STEPS = (0, 7)      # steps whose observation tensors are stored in full (others: sha256)

@@ -267,3 +267,32 @@ def make_multi4(lib, map_size=40, seed=8, n=70, **kw):
     for h in env.get_handles():
         env.add_agents(h, method="random", n=n)
     return env
+
+
+def arrange_config(size):
+    """absorbing goals (values of examples/train_arrange.py:180-212): a mover that bumps into a free goal dies
+    into it (Map.cc:341-349), the goal doubles its hp and ignores later visitors"""
+    import magent_b200 as magent
+    gw = magent.gridworld
+    cfg = gw.Config()
+    cfg.set({"map_width": size, "map_height": size, "minimap_mode": True, "embedding_size": 12})
+    goal = cfg.register_agent_type("goal", {'width': 1, 'length': 1, 'can_absorb': True})
+    agent = cfg.register_agent_type("agent", {'width': 1, 'length': 1, 'hp': 10, 'speed': 2,
+                                              'view_range': gw.CircleRange(6), 'step_recover': -10.0 / 400,
+                                              'step_reward': 0})
+    g_goal, g_agent = cfg.add_group(goal), cfg.add_group(agent)
+    g, a = gw.AgentSymbol(g_goal, 'any'), gw.AgentSymbol(g_agent, 'any')
+    cfg.add_reward_rule(gw.Event(a, 'collide', g), receiver=a, value=10)
+    return cfg
+
+
+def make_arrange(lib, map_size=30, seed=12, n_goal=70, n_agent=160, **kw):
+    import magent_b200 as magent
+    env = magent.GridWorld(arrange_config(map_size), _lib=lib, **kw)
+    env.set_seed(seed)
+    env.reset()
+    h = env.get_handles()
+    env.add_walls(method="random", n=25)
+    env.add_agents(h[0], method="random", n=n_goal)
+    env.add_agents(h[1], method="random", n=n_agent)
+    return env

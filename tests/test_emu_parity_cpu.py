@@ -109,3 +109,14 @@ def test_unsupported_rule_shapes_fail_loudly(emu):
     import sys
     out = subprocess.run([sys.executable, "-c", code], cwd=pc.REPO, capture_output=True, text=True)
     assert out.returncode != 0 and "must be 'any'" in out.stderr
+
+
+@pytest.mark.parametrize("seed", [13, 14, 15])
+def test_absorb_contention_matches_reference(emu, seed):
+    """dense absorbers: several movers reach the same goal in one step; only the first in move order is absorbed"""
+    if not os.path.exists(pc.REF_LIB):
+        pytest.skip("needs the compiled reference")
+    kw = dict(act_groups=[1], keep_obs=True, stop_on_done=False)
+    a = pc.run_trace(pc.make_arrange(pc.REF_LIB, 20, seed, n_goal=40, n_agent=200), 40, seed, **kw)
+    b = pc.run_trace(pc.make_arrange(emu, 20, seed, n_goal=40, n_agent=200), 40, seed, **kw)
+    pc.compare_traces(a, b, "absorb")

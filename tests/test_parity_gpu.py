@@ -99,6 +99,13 @@ def test_four_groups_sixteen_rules():
     both(lambda lib: pc.make_multi4(lib), 50, 8, order=[3, 1, 0, 2])
 
 
+@pytest.mark.parametrize("seed", [12, 13])
+def test_absorbing_goals(seed):
+    """can_absorb types (train_arrange): the first mover (in move order) that bumps into a free goal dies into it"""
+    want = both(lambda lib: pc.make_arrange(lib, 30, seed), 60, seed, act_groups=[1], stop_on_done=False)
+    assert want[-1]["num"][1] < 160
+
+
 def test_non_square_map():
     both(lambda lib: pc.make_battle_rect(lib), 40, 2)
 
