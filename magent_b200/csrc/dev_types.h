@@ -28,7 +28,7 @@ enum : unsigned { MVKEY_NONE = 0xffffffffu };
 // agent flags
 enum : unsigned char { FLAG_DEAD = 1, FLAG_ABSORBED = 2 };
 // mover states
-enum : unsigned char { MV_NONE = 0, MV_OOB = 1, MV_STATIC_FAIL = 2, MV_PENDING_FAIL = 3, MV_OK = 4, MV_ABSORBED = 5 };
+enum : unsigned char { MV_NONE = 0, MV_OOB = 1, MV_STATIC_FAIL = 2, MV_PENDING_FAIL = 3, MV_OK = 4, MV_ABSORBED = 5, MV_SKIPPED = 6 };
 
 // EventOp numbering of the reference (src/gridworld/grid_def.h:17-23)
 enum EventOp : unsigned char { OP_AND = 0, OP_OR, OP_NOT, OP_KILL, OP_AT, OP_IN, OP_COLLIDE, OP_ATTACK,
@@ -70,6 +70,7 @@ struct GroupDev {
     int cap;                                  // per-arena capacity of the SoA arrays
     int foff;                                 // flat scratch offset of this group inside an arena
     AgentSoA soa[2];                          // ping-pong; bit g of `curmask` selects the live one
+    int *ev_rank;                             // [A][cap] execution rank of the agent's attack this step, -1 if none (render only)
 };
 
 struct ArenaHdr {
@@ -138,6 +139,7 @@ struct EngineDev {
 
 struct StepArgs {
     unsigned curmask;
+    int record_events;                        // fill GroupDev::ev_rank (attack events for env_render)
     int n_order;
     int order[MG_MAX_GROUPS];                 // groups that received set_action, in call order
 };

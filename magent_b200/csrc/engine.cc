@@ -7,7 +7,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <fstream>
 #include <set>
+#include <sstream>
 
 #include "backend.h"
 
@@ -110,7 +112,7 @@ void Engine::set_config(const char *key, void *p_value) {     // GridWorld.cc:12
     } else if (strequ(key, "minimap_mode")) minimap_mode_ = bvalue;
     else if (strequ(key, "goal_mode")) goal_mode_ = bvalue;
     else if (strequ(key, "embedding_size")) embedding_size_ = ivalue;
-    else if (strequ(key, "render_dir")) { /* replay dump is out of scope; accepted and ignored */ }
+    else if (strequ(key, "render_dir")) render_dir_ = (const char *)p_value;      // RenderGenerator::set_render("save_dir")
     else if (strequ(key, "seed")) {
         if (where_ == DEVICE) to_host(false);
         for (int a = 0; a < A_; ++a)
@@ -367,6 +369,7 @@ void Engine::reset() {                                // GridWorld.cc:72-118, Ma
         for (int a = 0; a < A_; ++a) arenas_[a].rng = hdr[a].rng;
         where_ = HOST;
     }
+    file_ct_++; frame_ct_ = 0;                        // RenderGenerator::next_file (GridWorld.cc:97)
     large_map_ = (long)W_ * H_ > 99 * 99;
     nsep_ = large_map_ ? ((long)W_ * H_ > 1000 * 1000 ? 16 : 8) : 1;
     for (auto &ar : arenas_) {
@@ -576,6 +579,7 @@ void Engine::to_device() {
                 s.op_obj = (int *)dalloc(n * 4);
                 s.last_op = (unsigned char *)dalloc(n); s.flags = (unsigned char *)dalloc(n); s.dir = (unsigned char *)dalloc(n);
             }
+            D.ev_rank = (int *)dalloc(n * 4);
         }
         hE_.cap_total = foff; hE_.max_body = max_body; hE_.scratch_stride = foff;
         size_t cells = (size_t)A_ * W_ * H_, sc = (size_t)A_ * foff;
@@ -777,6 +781,7 @@ void Engine::step(int *done) {                                        // GridWor
     StepArgs S;
     memset(&S, 0, sizeof S);
     S.curmask = curmask_;
+    S.record_events = first_render_ ? 0 : 1;           // GridWorld.cc:484: only once rendering has started
     S.n_order = (int)order_.size();
     for (int k = 0; k < S.n_order; ++k) S.order[k] = order_[k];
     be::launch_step(dE_, hE_, S, max_agents_per_arena());
@@ -787,6 +792,7 @@ void Engine::step(int *done) {                                        // GridWor
     int all = 1;
     for (int a = 0; a < A_; ++a) { arenas_[a].done = d[a]; all &= d[a] != 0; }
     *done = all;
+    if (!first_render_) collect_attack_events();
 }
 
 void Engine::get_reward(int group, float *buf) {                      // GridWorld.cc:694-704
@@ -813,7 +819,118 @@ void Engine::set_goal(int, const char *, const int *) {
     fatal("goal_mode is deprecated in the reference and not supported by the B200 engine");
 }
 
-void Engine::render() { /* replay dump (RenderGenerator) is out of scope: SURVEY.md §8f rank 3 */ }
+// ---------------------------------------------------------------------------------------------
+// replay dump for the reference viewer (RenderGenerator.cc:63-185).  Cold path: works on a host snapshot of the
+// selected arena (arena 0 by default); byte-identical files for identical runs.
+void Engine::collect_attack_events() {                // the list GridWorld::step hands to the RenderGenerator (:471-509)
+    const int a = sel_arena_ >= 0 ? sel_arena_ : 0;
+    struct Ev { int rank, id, x, y; };
+    std::vector<Ev> evs;
+    for (int g = 0; g < G(); ++g) {
+        const int n = count(g, a);
+        if (n == 0) continue;
+        const AgentTypeDef &t = *group_type_[g];
+        const AgentSoA &s = hE_.grp[g].soa[(curmask_ >> g) & 1u];
+        const size_t base = (size_t)a * cap_[g];
+        std::vector<int> rank(n), x(n), y(n), act(n), id(n);
+        be::d2h(rank.data(), hE_.grp[g].ev_rank + base, (size_t)n * 4);
+        be::d2h(x.data(), s.x + base, (size_t)n * 4); be::d2h(y.data(), s.y + base, (size_t)n * 4);
+        be::d2h(act.data(), s.act + base, (size_t)n * 4); be::d2h(id.data(), s.id + base, (size_t)n * 4);
+        for (int i = 0; i < n; ++i) {
+            if (rank[i] < 0) continue;
+            const int k = act[i] - t.attack_base;
+            evs.push_back({rank[i], id[i], x[i] + t.att_x_offset + t.attack.dx[k], y[i] + t.att_y_offset + t.attack.dy[k]});
+        }
+    }
+    std::sort(evs.begin(), evs.end(), [](const Ev &p, const Ev &q) { return p.rank < q.rank; });
+    attack_events_.clear();
+    for (const Ev &e : evs) attack_events_.push_back({e.id, e.x, e.y});
+}
+
+void Engine::render_next_file() { file_ct_++; frame_ct_ = 0; }
+
+namespace {
+template <typename T> void print_json(std::ofstream &os, const char *key, T value, bool last = false) {
+    os << "\"" << key << "\": " << value;
+    if (last) os << std::endl; else os << "," << std::endl;
+}
+std::string rgba_string(int r, int g, int b, float alpha) {
+    std::stringstream ss;
+    ss << "\"rgba(" << r << "," << g << "," << b << "," << alpha << ")\"";
+    return ss.str();
+}
+}  // namespace
+
+void Engine::render() {                               // GridWorld.cc:939-949
+    static const int colors[][3] = {{192, 64, 64}, {64, 64, 192}, {64, 192, 64}, {64, 64, 64}};
+    if (render_dir_ == "___debug___") return;         // terminal dump of the reference's debug mode: not provided
+    if (first_render_) {
+        first_render_ = false;
+        std::ofstream f(render_dir_ + "/" + "config.json");           // RenderGenerator::gen_config
+        f << "{" << std::endl;
+        print_json(f, "width", W_);
+        print_json(f, "height", H_);
+        print_json(f, "static-file", "\"static.map\"");
+        print_json(f, "obstacle-style", rgba_string(127, 127, 127, 1));
+        print_json(f, "dynamic-file-directory", "\".\"");
+        print_json(f, "attack-style", rgba_string(63, 63, 63, 0.8));
+        print_json(f, "minimap-width", 300);
+        print_json(f, "minimap-height", 250);
+        f << "\"group\" : [" << std::endl;
+        for (int i = 0; i < G(); i++) {
+            const AgentTypeDef &t = *group_type_[i];
+            const int *c = colors[i % 4];
+            f << "{" << std::endl;
+            print_json(f, "height", t.length);
+            print_json(f, "width", t.width);
+            print_json(f, "style", rgba_string(c[0], c[1], c[2], 1));
+            print_json(f, "anchor", "[0, 0]");
+            print_json(f, "max-speed", (int)t.speed);
+            print_json(f, "speed-style", rgba_string(c[0], c[1], c[2], 0.01));
+            print_json(f, "vision-radius", t.view_radius);
+            print_json(f, "vision-angle", t.view_angle);
+            print_json(f, "vision-style", rgba_string(c[0], c[1], c[2], 0.2));
+            print_json(f, "attack-radius", t.attack_radius);
+            print_json(f, "attack-angle", t.attack_angle);
+            print_json(f, "attack-style", rgba_string(c[0], c[1], c[2], 0.1));
+            print_json(f, "broadcast-radius", 1, true);
+            f << (i == G() - 1 ? "}" : "},") << std::endl;
+        }
+        f << "]" << std::endl << "}" << std::endl;
+    }
+    if (render_dir_.empty()) return;                  // RenderGenerator::render_a_frame
+    if (was_reset_ && where_ == DEVICE) to_host(true);
+    const HostArena &ar = arenas_[sel_arena_ >= 0 ? sel_arena_ : 0];
+    std::ofstream fout(render_dir_ + "/" + "video_" + std::to_string(file_ct_) + ".txt",
+                       frame_ct_ == 0 ? std::ios::out : std::ios::app);
+    if (frame_ct_ == 0) {
+        std::vector<int> walls;
+        for (int i = 0; i < W_ * H_; i++) if (ar.occ[i] == OCC_WALL) walls.push_back(i);
+        fout << "W" << " " << walls.size() << std::endl;
+        for (int w : walls) fout << w % W_ << " " << w / W_ << std::endl;
+    }
+    int num_agents = 0;
+    for (int g = 0; g < G(); g++) {
+        const HostGroup &hg = ar.groups[g];
+        num_agents += hg.size();
+        if (group_type_[g]->can_absorb)
+            for (int j = 0; j < hg.size(); j++) if (!(hg.flags[j] & FLAG_ABSORBED)) num_agents--;
+    }
+    fout << "F" << " " << num_agents << " " << (int)attack_events_.size() << " " << 0 << std::endl;
+    for (int g = 0; g < G(); g++) {
+        const HostGroup &hg = ar.groups[g];
+        const AgentTypeDef &t = *group_type_[g];
+        for (int j = 0; j < hg.size(); j++) {
+            if (t.can_absorb && !(hg.flags[j] & FLAG_ABSORBED)) continue;
+            int hp = std::max(0, int(100 * hg.hp[j] / t.hp));
+            hp = std::min(hp, 100);
+            static const int dir2angle[] = {0, 90, 180, 270};
+            fout << hg.id[j] << " " << hp << " " << dir2angle[hg.dir[j] & 3] << " " << hg.x[j] << " " << hg.y[j] << " " << g << std::endl;
+        }
+    }
+    for (const AttackEvent &e : attack_events_) fout << 0 << " " << e.id << " " << e.x << " " << e.y << std::endl;
+    if (frame_ct_++ > frame_per_file_) { frame_ct_ = 0; file_ct_++; }
+}
 
 void Engine::sync() { if (device_ready_) be::sync(); }
 
@@ -902,6 +1019,7 @@ void Engine::get_info(int group, const char *name, void *void_buffer) {        /
             fb[0] = sx / hg.size(); fb[1] = sy / hg.size();
             for (int i = 0; i < na; i++) fb[2 + i] = (float)(1.0 * ctr[i] / hg.size());
         } else if (strequ(name, "render_window_info")) {
+            first_render_ = false;                     // GridWorld.cc:798
             int x1 = ib[0], y1 = ib[1], x2 = ib[2], y2 = ib[3], ct = 1;
             for (int g = 0; g < G(); g++) {
                 const HostGroup &hg = ar.groups[g];
@@ -911,7 +1029,11 @@ void Engine::get_info(int group, const char *name, void *void_buffer) {        /
                     ib[ct * 4] = hg.id[j]; ib[ct * 4 + 1] = hg.x[j]; ib[ct * 4 + 2] = hg.y[j]; ib[ct * 4 + 3] = g; ct++;
                 }
             }
-            ib[0] = ct - 1; ib[1] = 0;                 // attack events are not recorded (render is out of scope)
+            ib[0] = ct - 1; ib[1] = (int)attack_events_.size();
+        } else if (strequ(name, "attack_event")) {
+            for (size_t i = 0; i < attack_events_.size(); i++) {
+                ib[i * 3] = attack_events_[i].id; ib[i * 3 + 1] = attack_events_[i].x; ib[i * 3 + 2] = attack_events_[i].y;
+            }
         }
     } else {
         fatal("unsupported info name in GridWorld::get_info : %s", name);

@@ -87,6 +87,8 @@ public:
     void set_goal(int group, const char *method, const int *buf);
     void render();
 
+    void render_next_file();
+
     // ---- extensions
     void select_arena(int a) { sel_arena_ = a; }
     void random_actions(int group, unsigned long long seed);
@@ -112,6 +114,14 @@ private:
     int nsep_ = 1;
     bool large_map_ = false;
     int sel_arena_ = -1;
+
+    // replay dump (reference RenderGenerator, src/gridworld/RenderGenerator.cc)
+    std::string render_dir_;
+    int file_ct_ = 0, frame_ct_ = 0, frame_per_file_ = 10000;
+    bool first_render_ = true;
+    struct AttackEvent { int id, x, y; };
+    std::vector<AttackEvent> attack_events_;
+    void collect_attack_events();
 
     // host image
     std::vector<HostArena> arenas_;

@@ -39,7 +39,7 @@ MG_API int env_step(EnvHandle game, int *done) { E(game)->step(done); return 0; 
 MG_API int env_get_reward(EnvHandle game, GroupHandle group, float *buffer) { E(game)->get_reward(group, buffer); return 0; }
 MG_API int env_get_info(EnvHandle game, GroupHandle group, const char *name, void *buffer) { E(game)->get_info(group, name, buffer); return 0; }
 MG_API int env_render(EnvHandle game) { E(game)->render(); return 0; }
-MG_API int env_render_next_file(EnvHandle) { return 0; }
+MG_API int env_render_next_file(EnvHandle game) { E(game)->render_next_file(); return 0; }
 
 MG_API int gridworld_register_agent_type(EnvHandle game, const char *name, int n, const char **keys, float *values) {
     E(game)->register_agent_type(name, n, keys, values); return 0;

@@ -232,9 +232,11 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
         // mover scratch is (re)initialised here, after the shuffle scratch it may share storage with is dead
         E.mv_key[f] = MVKEY_NONE;
         E.mv_state[f] = MV_NONE;
+        if (S.record_events) G.ev_rank[gi] = -1;
         if (s.flags[gi] & FLAG_DEAD) continue;
         int d = E.death[f];
         int r = E.att_rank[f];
+        if (S.record_events && r != RANK_NONE && d > r) G.ev_rank[gi] = r;     // RenderAttackEvent, GridWorld.cc:484-485
         if (r != RANK_NONE && d > r) {                   // my attack is executed
             int t = E.tgt[f];
             int dt = t >= 0 ? E.death[R.sb + lflat(E, t)] : DEATH_BEFORE;
@@ -369,12 +371,30 @@ MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a
         int fs = G.foff + i;
         long f = R.sb + fs;
         unsigned char st = E.mv_state[f];
-        if (st != MV_PENDING_FAIL && st != MV_OK && st != MV_ABSORBED) continue;
+        if (st != MV_PENDING_FAIL && st != MV_OK && st != MV_ABSORBED && st != MV_SKIPPED) continue;
         unsigned key = E.mv_key[f];
         int nx = E.mv_nx[f], ny = E.mv_ny[f];
         bool ok = true;
         unsigned char ns;
-        if (!E.any_absorb) {
+        bool skipped = false;
+        if (G.can_absorb) {
+            // an absorber that swallowed somebody earlier in this move phase is `absorbed` by the time its own turn
+            // comes and is skipped (GridWorld.cc:581): whoever bumped into it queued on one of its current cells
+            const AgentSoA &sm = cur_soa(E, S.curmask, g);
+            const long gm = gidx(E, a, g, i);
+            const int mycode = code_make(g, i);
+            const int x0 = sm.x[gm], y0 = sm.y[gm];
+            for (int bx = 0; bx < G.body_w && !skipped; ++bx)
+                for (int by = 0; by < G.body_l && !skipped; ++by)
+                    for (int node = R.claim[(y0 + by) * E.W + x0 + bx]; node != -1; node = E.cl_next[R.nb + node]) {
+                        const int fm = node / E.max_body;
+                        if (fm != fs && E.mv_key[R.sb + fm] < key && ld_volatile(&E.mv_state[R.sb + fm]) == MV_ABSORBED &&
+                            ld_volatile(&E.tgt[R.sb + fm]) == mycode) { skipped = true; break; }
+                    }
+        }
+        if (skipped) {
+            ns = MV_SKIPPED;
+        } else if (!E.any_absorb) {
             for (int bx = 0; bx < G.body_w && ok; ++bx)
                 for (int by = 0; by < G.body_l && ok; ++by)
                     if (occupant_at_turn(E, R, nx + bx, ny + by, key, fs) != -1) ok = false;
@@ -426,7 +446,7 @@ MG_HD void phase_move_collide(Ctx &c, const EngineDev &E, const StepArgs &S, int
         long f = R.sb + fs;
         unsigned char st = E.mv_state[f];
         if (st == MV_OK) { ++ok_ct; continue; }
-        if (st == MV_NONE) continue;
+        if (st == MV_NONE || st == MV_SKIPPED) continue;
         ++blocked;
         if (st == MV_OOB) continue;
         if (st == MV_ABSORBED) {                  // Map.cc:341-349: the absorber doubles its hp, the mover disappears
@@ -492,7 +512,7 @@ MG_HD void phase_move_fill(Ctx &c, const EngineDev &E, const StepArgs &S, int a,
         const GroupDev &G = E.grp[g];
         long f = R.sb + G.foff + i;
         unsigned char st = E.mv_state[f];
-        if (st != MV_OK && st != MV_PENDING_FAIL && st != MV_ABSORBED) continue;
+        if (st != MV_OK && st != MV_PENDING_FAIL && st != MV_ABSORBED && st != MV_SKIPPED) continue;
         int nx = E.mv_nx[f], ny = E.mv_ny[f];
         bool ok = st == MV_OK;
         int code = code_make(g, i);

@@ -120,3 +120,37 @@ def test_absorb_contention_matches_reference(emu, seed):
     a = pc.run_trace(pc.make_arrange(pc.REF_LIB, 20, seed, n_goal=40, n_agent=200), 40, seed, **kw)
     b = pc.run_trace(pc.make_arrange(emu, 20, seed, n_goal=40, n_agent=200), 40, seed, **kw)
     pc.compare_traces(a, b, "absorb")
+
+
+def _render_episode(lib, tmpdir, scenario):
+    os.makedirs(tmpdir, exist_ok=True)
+    env = scenario(lib)
+    env.set_render_dir(tmpdir)
+    hs = env.get_handles()
+    rs = np.random.RandomState(3)
+    for t in range(12):
+        for h in hs:
+            env.set_action(h, rs.randint(0, env.get_action_space(h)[0], size=env.get_num(h)).astype(np.int32))
+        env.step()
+        env.render()
+        env.clear_dead()
+    info = env._get_render_info((0, 20), (0, 20))
+    files = {}
+    for name in sorted(os.listdir(tmpdir)):
+        files[name] = open(os.path.join(tmpdir, name), "rb").read()
+    return files, sorted((k, tuple(v)) for k, v in info[0].items()), info[1].tolist()
+
+
+@pytest.mark.parametrize("which", ["battle", "arrange"])
+def test_render_dump_is_byte_identical(emu, tmp_path, which):
+    """env_render: config.json + video_N.txt frames incl. attack events (RenderGenerator.cc:63-185)"""
+    if not os.path.exists(pc.REF_LIB):
+        pytest.skip("needs the compiled reference")
+    scen = (lambda lib: pc.make_battle(lib, 30, 200, 3)) if which == "battle" else (lambda lib: pc.make_arrange(lib, 30, 12))
+    a = _render_episode(pc.REF_LIB, str(tmp_path / "ref"), scen)
+    b = _render_episode(emu, str(tmp_path / "emu"), scen)
+    assert sorted(a[0]) == sorted(b[0]) and "config.json" in a[0]
+    for name in a[0]:
+        assert a[0][name] == b[0][name], name
+    assert any(line.startswith(b"0 ") for line in a[0]["video_1.txt"].splitlines()) or which != "battle"
+    assert a[1] == b[1] and a[2] == b[2]

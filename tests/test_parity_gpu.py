@@ -106,6 +106,23 @@ def test_absorbing_goals(seed):
     assert want[-1]["num"][1] < 160
 
 
+def test_absorbing_goals_that_move_themselves():
+    """goals receive actions too: a goal bumping into a goal is absorbed by it, and an absorber that swallowed somebody
+    earlier in the move phase skips its own move (GridWorld.cc:581 evaluated at its turn)"""
+    both(lambda lib: pc.make_arrange(lib, 24, 14, n_goal=60, n_agent=150), 40, 14, stop_on_done=False)
+
+
+def test_render_dump_matches_reference(tmp_path):
+    """env_render through the CUDA engine: config.json + video_N.txt byte-identical, attack events included"""
+    from test_emu_parity_cpu import _render_episode
+    if not os.path.exists(pc.REF_LIB):
+        pytest.skip("the replay dump is only provided by the compiled reference (oracle/_ref)")
+    scen = lambda lib: pc.make_battle(lib, 30, 200, 3)
+    a = _render_episode(pc.REF_LIB, str(tmp_path / "ref"), scen)
+    b = _render_episode(pc.CUDA_LIB, str(tmp_path / "gpu"), scen)
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
+
+
 def test_non_square_map():
     both(lambda lib: pc.make_battle_rect(lib), 40, 2)
 
