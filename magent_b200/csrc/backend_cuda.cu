@@ -657,7 +657,13 @@ void launch_obs_prepare(const EngineDev *dE, const EngineDev &hE, unsigned curma
 #endif
 constexpr int OBS_TA = OBS_TA_N;      // agents per tile (multiple of 4: 16-byte aligned tile ranges)
 constexpr int OBS_THREADS = 32 * OBS_TA;
-constexpr int OBS_NIT = 8;           // view cells per lane handled in one unrolled batch (8*32 = 256 cells)
+#ifndef OBS_NIT_N
+#define OBS_NIT_N 8
+#endif
+#ifndef OBS_PREFETCH
+#define OBS_PREFETCH 1
+#endif
+constexpr int OBS_NIT = OBS_NIT_N;   // view cells per lane handled in one unrolled batch (8*32 = 256 in-range cells)
 
 struct ObsParams {
     int A, W, H, G, C;
@@ -771,8 +777,14 @@ __global__ void __launch_bounds__(OBS_THREADS, OBS_MIN_CTAS) obs_render_kernel(c
     for (; tile < n_tiles; tile += gridDim.x) {
         const int t0 = tile * OBS_TA;
         const int cnt = min(OBS_TA, P.n_total - t0);
+#if OBS_PREFETCH
         const int ta = ta_next;
         const int4 h0 = h0n, h1 = h1n, h2 = h2n;
+#else
+        const int ta = P.tile_arena[tile];
+        int4 h0 = make_int4(0, 0, 0, 0), h1 = h0, h2 = h0;
+        if (t0 + warp < P.n_total) { h0 = P.hdr[3 * (size_t)(t0 + warp)]; h1 = P.hdr[3 * (size_t)(t0 + warp) + 1]; h2 = P.hdr[3 * (size_t)(t0 + warp) + 2]; }
+#endif
         const bool use_tmpl = P.tmpl != nullptr && ta >= 0;          // whole tile inside arena ta (block-uniform)
         if (use_tmpl) {
             if (threadIdx.x == 0) {
@@ -817,6 +829,7 @@ __global__ void __launch_bounds__(OBS_THREADS, OBS_MIN_CTAS) obs_render_kernel(c
                 }
             }
         }
+#if OBS_PREFETCH
         {   // prefetch the next tile's header
             const int nt = tile + gridDim.x;
             if (nt < n_tiles) {
@@ -825,6 +838,7 @@ __global__ void __launch_bounds__(OBS_THREADS, OBS_MIN_CTAS) obs_render_kernel(c
                 if (on < P.n_total) { h0n = P.hdr[3 * (size_t)on]; h1n = P.hdr[3 * (size_t)on + 1]; h2n = P.hdr[3 * (size_t)on + 2]; }
             }
         }
+#endif
         if (use_tmpl) {                                           // wait for the template tile to land
             unsigned done = 0;
             while (!done) {

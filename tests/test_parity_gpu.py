@@ -123,6 +123,32 @@ def test_render_dump_matches_reference(tmp_path):
     assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
 
 
+def test_two_engines_interleaved_in_one_process():
+    """two CUDA environments of different games stepping alternately: per-engine state must not leak through the
+    backend's shared scratch (hp_norm plane, template tiles, header table)"""
+    ea, eb = pc.make_battle(pc.CUDA_LIB, 40, 150, 0), pc.make_pursuit(pc.CUDA_LIB, 40, 0)
+    ra, rb = pc.make_battle(checker_lib(), 40, 150, 0), pc.make_pursuit(checker_lib(), 40, 0)
+    rs = np.random.RandomState(0)
+    for t in range(15):
+        for env, ref in ((ea, ra), (eb, rb)):
+            hs, hr = env.get_handles(), ref.get_handles()
+            for h, k in zip(hs, hr):
+                v, f = env.get_observation(h)
+                rv, rf = ref.get_observation(k)
+                np.testing.assert_array_equal(v.view(np.uint32), rv.view(np.uint32), err_msg="view t%d" % t)
+                np.testing.assert_array_equal(f.view(np.uint32), rf.view(np.uint32), err_msg="feat t%d" % t)
+        for env, ref in ((ea, ra), (eb, rb)):
+            for h, k in zip(env.get_handles(), ref.get_handles()):
+                a = rs.randint(0, env.get_action_space(h)[0], size=env.get_num(h)).astype(np.int32)
+                env.set_action(h, a)
+                ref.set_action(k, a)
+            assert env.step() == ref.step()
+            for h, k in zip(env.get_handles(), ref.get_handles()):
+                np.testing.assert_array_equal(env.get_pos(h), ref.get_pos(k))
+            env.clear_dead()
+            ref.clear_dead()
+
+
 def test_non_square_map():
     both(lambda lib: pc.make_battle_rect(lib), 40, 2)
 
