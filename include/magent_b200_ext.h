@@ -25,6 +25,11 @@ int magent_b200_select_arena(EnvHandle game, int arena);
 /* set_action with uniform random actions generated on the device (throughput runs; not part of parity).
  * `unused` must be NULL. */
 int magent_b200_random_actions(EnvHandle game, GroupHandle group, void *unused, unsigned long long seed);
+/* compact observation hand-off: same call, layout and pointer rules as env_get_observation
+ * (reference src/runtime_api.h:35), but every element is an IEEE binary16 = the float32 value rounded to
+ * nearest-even.  buffer[0] = view [n][view_h][view_w][n_channel], buffer[1] = feature [n][feature_size];
+ * host or CUDA device pointers.  Halves the HBM / PCIe bytes per observation. */
+int magent_b200_get_observation_f16(EnvHandle game, GroupHandle group, void **buffer);
 /* int64 event counters since construction: agent_steps, attacks, hits, kills, starved, moves_ok,
  * moves_blocked, steps.  Returns the number written. */
 int magent_b200_get_counters(EnvHandle game, long long *out, int capacity);

@@ -12,6 +12,7 @@
 //   info_kernel       id/pos/alive/reward gathers and the action scatter.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string>
@@ -597,9 +598,10 @@ __global__ void __launch_bounds__(256) minimap_norm_kernel(const EngineDev *gE, 
     const int cells = E.grp[og].view_w * E.grp[og].view_h;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
         int ag = k / cells;
-        int a = ag / E.G, j = ag - a * E.G;
-        mm_val[k] = (float)E.mm_count[k] / (float)E.mm_total[ag];         // GridWorld.cc:350-357 (total_ct)
-        (void)a; (void)j;
+        // GridWorld.cc:350-357 (total_ct).  An empty (or fully absorbed) group is 0/0 in the reference: x86 divss
+        // yields the default quiet NaN 0xFFC00000 whereas the GPU would give 0x7FFFFFFF, so emit the x86 payload.
+        const int tot = E.mm_total[ag];
+        mm_val[k] = tot ? (float)E.mm_count[k] / (float)tot : __int_as_float((int)0xFFC00000u);
     }
 }
 
@@ -655,15 +657,37 @@ void launch_obs_prepare(const EngineDev *dE, const EngineDev &hE, unsigned curma
 #ifndef OBS_TA_N
 #define OBS_TA_N 4
 #endif
-constexpr int OBS_TA = OBS_TA_N;      // agents per tile (multiple of 4: 16-byte aligned tile ranges)
-constexpr int OBS_THREADS = 32 * OBS_TA;
 #ifndef OBS_NIT_N
 #define OBS_NIT_N 8
 #endif
 #ifndef OBS_PREFETCH
 #define OBS_PREFETCH 1
 #endif
+#ifndef OBS_ABLATE
+#define OBS_ABLATE 0                 // profiling experiments only (profiles/README.md): 1 no plane gather, 2 no template
+#endif                               // load, 4 no feature rows, 8 no bulk store -- results are WRONG with any bit set
 constexpr int OBS_NIT = OBS_NIT_N;   // view cells per lane handled in one unrolled batch (8*32 = 256 in-range cells)
+
+// output element type of the observation: float = the reference ABI (env_get_observation); __half = the compact
+// hand-off format of magent_b200_get_observation_f16 (each value is the f32 value rounded to nearest-even).
+// TA = agents per tile = warps per CTA; TA * sizeof(T) % 16 == 0 keeps every tile's byte range 16-byte aligned.
+template <typename T> struct ObsOut;
+template <> struct ObsOut<float> {
+    static constexpr int TA = OBS_TA_N;
+    static __device__ __forceinline__ float cv(float v) { return v; }
+};
+template <> struct ObsOut<__half> {
+    static constexpr int TA = 2 * OBS_TA_N;
+    static __device__ __forceinline__ __half cv(float v) {
+        if (v != v) {                    // keep sign and top payload bits like a software f32->f16 cast does (numpy astype)
+            const unsigned u = __float_as_uint(v);
+            unsigned short r = (unsigned short)(0x7c00u + ((u & 0x7fffffu) >> 13));
+            if (r == 0x7c00u) ++r;
+            return __ushort_as_half((unsigned short)(r | ((u >> 16) & 0x8000u)));
+        }
+        return __float2half_rn(v);
+    }
+};
 
 struct ObsParams {
     int A, W, H, G, C;
@@ -677,10 +701,11 @@ struct ObsParams {
     const int *x, *y, *id, *act;
     const float *last_reward;
     const float *mm;                 // [A][G][cells] normalised minimap, or nullptr
-    const float *tmpl;               // [A][OBS_TA*rec] template tiles (minimap channels filled), or nullptr
+    const void *tmpl;                // [A][TA*rec] template tiles (minimap channels filled), or nullptr
+    int ta;                          // agents per tile of the launched instantiation
     const int *tile_arena;           // [n_tiles] arena of the tile, -1 when it straddles two arenas
     const int4 *hdr;                 // [n_total][3] per-agent header in ABI order (obs_headers_kernel)
-    float *view, *feature;
+    void *view, *feature;            // element type = the kernel's template argument
     int mm_ch[MG_MAX_GROUPS];        // observation channel of group j's minimap
     int grp_ch[MG_MAX_GROUPS];       // observation channel ('has'; hp is +1) of group j
 };
@@ -707,40 +732,46 @@ __global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr
         hdr[3 * (size_t)o + 0] = make_int4(x, y, a, i);
         hdr[3 * (size_t)o + 1] = make_int4(self_cell, P.id[gi], P.act[gi], __float_as_int(P.last_reward[gi]));
         hdr[3 * (size_t)o + 2] = make_int4(__float_as_int(fx), __float_as_int(fy), 0, 0);
-        if (o % OBS_TA == 0) {
-            const int last = min(o + OBS_TA, P.n_total) - 1;
-            tile_arena[o / OBS_TA] = last < P.off[a + 1] ? a : -1;
+        if (o % P.ta == 0) {
+            const int last = min(o + P.ta, P.n_total) - 1;
+            tile_arena[o / P.ta] = last < P.off[a + 1] ? a : -1;
         }
     }
 }
 
-// template tile of arena a: OBS_TA records, zero except the minimap channels (GridWorld.cc:374-381)
-__global__ void __launch_bounds__(256) obs_template_kernel(ObsParams P, float *tmpl) {
+// template tile of arena a: TA records, zero except the minimap channels (GridWorld.cc:374-381)
+template <typename T>
+__global__ void __launch_bounds__(256) obs_template_kernel(ObsParams P, T *tmpl) {
+    constexpr int TA = ObsOut<T>::TA;
     const int a = blockIdx.x;
-    float *t = tmpl + (size_t)a * OBS_TA * P.rec;
+    T *t = tmpl + (size_t)a * TA * P.rec;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = threadIdx.x; q < OBS_TA * P.rec / 4; q += blockDim.x) ((float4 *)t)[q] = z;
+    for (int q = threadIdx.x; q < (int)(TA * P.rec * sizeof(T) / 16); q += blockDim.x) ((float4 *)t)[q] = z;
     __syncthreads();
     const float *mm = P.mm + (size_t)a * P.G * P.cells;
     const int per_slot = P.G * P.cells;
-    for (int q = threadIdx.x; q < OBS_TA * per_slot; q += blockDim.x) {
+    for (int q = threadIdx.x; q < TA * per_slot; q += blockDim.x) {
         int slot = q / per_slot, r = q - slot * per_slot;
         int j = r / P.cells, cell = r - j * P.cells;
-        t[slot * P.rec + cell * P.C + P.mm_ch[j]] = mm[r];
+        t[slot * P.rec + cell * P.C + P.mm_ch[j]] = ObsOut<T>::cv(mm[r]);
     }
 }
 
 #ifndef OBS_MIN_CTAS
 #define OBS_MIN_CTAS 8
 #endif
-__global__ void __launch_bounds__(OBS_THREADS, OBS_MIN_CTAS) obs_render_kernel(const __grid_constant__ ObsParams P) {
+template <typename T>
+__global__ void __launch_bounds__(32 * ObsOut<T>::TA, OBS_MIN_CTAS * OBS_TA_N / ObsOut<T>::TA)
+obs_render_kernel(const __grid_constant__ ObsParams P) {
+    constexpr int OBS_TA = ObsOut<T>::TA;
+    constexpr int OBS_THREADS = 32 * OBS_TA;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *buf = (float *)smem_raw;                           // one tile: OBS_TA records
+    T *buf = (T *)smem_raw;                                   // one tile: OBS_TA records
     int *lut = (int *)(buf + OBS_TA * P.rec);                 // in-range view cells only: cell << 16 | (dy & 0xff) << 8 | (dx & 0xff)
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ int n_in_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned tile_bytes = (unsigned)OBS_TA * (unsigned)P.rec * 4u;
+    const unsigned tile_bytes = (unsigned)OBS_TA * (unsigned)P.rec * (unsigned)sizeof(T);
 
     if (warp == 0) {                                          // compact the circular view mask (CircleRange, Range.h:151-189)
         int k = 0;                                            // order-preserving: ballot prefix per 32 cells
@@ -787,20 +818,23 @@ __global__ void __launch_bounds__(OBS_THREADS, OBS_MIN_CTAS) obs_render_kernel(c
 #endif
         const bool use_tmpl = P.tmpl != nullptr && ta >= 0;          // whole tile inside arena ta (block-uniform)
         if (use_tmpl) {
-            if (threadIdx.x == 0) {
+            if ((OBS_ABLATE & 2) && tile != (int)blockIdx.x) {
+                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+            } else if (threadIdx.x == 0) {
                 // the previous tile's bulk store must have finished READING the buffer before TMA overwrites it
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                              :: "r"(smem_u32(&mbar)), "r"(tile_bytes) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             :: "r"(smem_u32(buf)), "l"(P.tmpl + (size_t)ta * OBS_TA * P.rec), "r"(tile_bytes),
+                             :: "r"(smem_u32(buf)), "l"((const T *)P.tmpl + (size_t)ta * OBS_TA * P.rec), "r"(tile_bytes),
                                 "r"(smem_u32(&mbar)) : "memory");
             }
         } else {
             if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncthreads();
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = threadIdx.x; q < OBS_TA * P.rec / 4; q += OBS_THREADS) ((float4 *)buf)[q] = z;
+            for (int q = threadIdx.x; q < (int)(tile_bytes / 16u); q += OBS_THREADS) ((float4 *)buf)[q] = z;
             __syncthreads();
         }
         const bool active = warp < cnt;
@@ -812,7 +846,7 @@ __global__ void __launch_bounds__(OBS_THREADS, OBS_MIN_CTAS) obs_render_kernel(c
         float thp[OBS_NIT];
 #pragma unroll
         for (int it = 0; it < OBS_NIT; ++it) { tcode[it] = OCC_EMPTY; thp[it] = 0.0f; }
-        if (active) {
+        if (active && !(OBS_ABLATE & 1)) {
             // issue this lane's plane loads (cell code + hp_norm, independent) back to back; they overlap the template load
 #pragma unroll
             for (int it = 0; it < OBS_NIT; ++it) {
@@ -839,7 +873,7 @@ __global__ void __launch_bounds__(OBS_THREADS, OBS_MIN_CTAS) obs_render_kernel(c
             }
         }
 #endif
-        if (use_tmpl) {                                           // wait for the template tile to land
+        if (use_tmpl && ((OBS_ABLATE & 2) == 0 || tile == (int)blockIdx.x)) {   // wait for the template tile to land
             unsigned done = 0;
             while (!done) {
                 asm volatile("{\n\t.reg .pred p;\n\t"
@@ -850,28 +884,38 @@ __global__ void __launch_bounds__(OBS_THREADS, OBS_MIN_CTAS) obs_render_kernel(c
             phase ^= 1u;
         }
         if (active) {
-            float *dst = buf + warp * P.rec;
+            T *dst = buf + warp * P.rec;
             if (P.minimap) {
                 if (!use_tmpl) {                                   // tile straddles arenas: no template
                     const float *mm = P.mm + (long)a * P.G * P.cells;
                     for (int r = lane; r < P.G * P.cells; r += 32) {
                         int j = r / P.cells, cell = r - j * P.cells;
-                        dst[cell * P.C + P.mm_ch[j]] = mm[r];
+                        dst[cell * P.C + P.mm_ch[j]] = ObsOut<T>::cv(mm[r]);
                     }
                     __syncwarp();
                 }
-                if (lane < P.G) dst[h1.x * P.C + P.mm_ch[lane]] += 1.0f;               // self marker, GridWorld.cc:382
+                if (lane < P.G) {                                                       // self marker, GridWorld.cc:382
+                    T *pm = dst + h1.x * P.C + P.mm_ch[lane];
+                    // NaN + 1 keeps the x86 payload in the reference; FADD would canonicalise it
+                    if constexpr (sizeof(T) == 4) {
+                        const float v = *pm;
+                        if (v == v) *pm = v + 1.0f;
+                    } else {                                // round once: f16(f32 minimap value + 1)
+                        const float v = __ldg(P.mm + ((long)a * P.G + lane) * P.cells + h1.x);
+                        *pm = ObsOut<T>::cv(v == v ? v + 1.0f : v);
+                    }
+                }
             }
 #pragma unroll
             for (int it = 0; it < OBS_NIT; ++it) {
                 const int t = tcode[it];
                 if (t != OCC_EMPTY) {
-                    float *px = dst + (lut[it * 32 + lane] >> 16) * P.C;
-                    if (t == OCC_WALL) px[0] = 1.0f;
+                    T *px = dst + (lut[it * 32 + lane] >> 16) * P.C;
+                    if (t == OCC_WALL) px[0] = ObsOut<T>::cv(1.0f);
                     else {
                         const int ch = P.grp_ch[code_group(t)];
-                        px[ch] = 1.0f;
-                        px[ch + 1] = thp[it];                                           // hp / max_hp (Map.cc:197)
+                        px[ch] = ObsOut<T>::cv(1.0f);
+                        px[ch + 1] = ObsOut<T>::cv(thp[it]);                            // hp / max_hp (Map.cc:197)
                     }
                 }
             }
@@ -880,16 +924,17 @@ __global__ void __launch_bounds__(OBS_THREADS, OBS_MIN_CTAS) obs_render_kernel(c
                 const int x = ax + (int)(signed char)(l & 0xff), y = ay + (int)(signed char)((l >> 8) & 0xff);
                 if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) {
                     const int t = __ldg(occ + y * P.W + x);
-                    float *px = dst + (l >> 16) * P.C;
-                    if (t == OCC_WALL) px[0] = 1.0f;
+                    T *px = dst + (l >> 16) * P.C;
+                    if (t == OCC_WALL) px[0] = ObsOut<T>::cv(1.0f);
                     else if (t >= 0) {
                         const int ch = P.grp_ch[code_group(t)];
-                        px[ch] = 1.0f;
-                        px[ch + 1] = __ldg(hpnp + y * P.W + x);
+                        px[ch] = ObsOut<T>::cv(1.0f);
+                        px[ch + 1] = ObsOut<T>::cv(__ldg(hpnp + y * P.W + x));
                     }
                 }
             }
             // non-spatial features straight to global memory (GridWorld.cc:386-396); all inputs come from the header
+            if (!(OBS_ABLATE & 4))
             for (int f = lane; f < P.F; f += 32) {
                 float v = 0.0f;
                 if (f < P.embedding) v = f < 31 ? (float)((h1.y >> f) & 1) : 0.0f;
@@ -900,34 +945,89 @@ __global__ void __launch_bounds__(OBS_THREADS, OBS_MIN_CTAS) obs_render_kernel(c
                     else if (P.minimap && kk == P.n_action + 1) v = __int_as_float(h2.x);
                     else if (P.minimap && kk == P.n_action + 2) v = __int_as_float(h2.y);
                 }
-                P.feature[(size_t)o * P.F + f] = v;
+                ((T *)P.feature)[(size_t)o * P.F + f] = ObsOut<T>::cv(v);
             }
         }
         // make the generic-proxy writes visible to the async proxy, then one thread fires the bulk store
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        float *gout = P.view + (size_t)t0 * P.rec;
-        const unsigned bytes = (unsigned)cnt * (unsigned)P.rec * 4u;
+        T *gout = (T *)P.view + (size_t)t0 * P.rec;
+        const unsigned bytes = (unsigned)cnt * (unsigned)P.rec * (unsigned)sizeof(T);
         if ((bytes & 15u) == 0 && (((size_t)gout) & 15) == 0) {
-            if (threadIdx.x == 0) {
+            if (threadIdx.x == 0 && !(OBS_ABLATE & 8)) {
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(gout), "r"(smem_u32(buf)), "r"(bytes) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         } else {                                   // ragged last tile / unaligned caller buffer
-            for (int q = threadIdx.x; q < cnt * P.rec; q += OBS_THREADS) __stcs(gout + q, buf[q]);
+            for (int q = threadIdx.x; q < cnt * P.rec; q += OBS_THREADS) gout[q] = buf[q];
             __syncthreads();
         }
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-static float *g_tmpl = nullptr;
+static void *g_tmpl = nullptr;
 static size_t g_tmpl_bytes = 0;
 static int *g_tile_arena = nullptr;
 static size_t g_tile_arena_n = 0;
 static int4 *g_obs_hdr = nullptr;
 static size_t g_obs_hdr_n = 0;
+
+template <typename T>
+static void launch_obs_typed(const EngineDev &hE, ObsParams &P, int n_total) {
+    constexpr int TA = ObsOut<T>::TA;
+    constexpr int THREADS = 32 * TA;
+    P.ta = TA;
+    const size_t tile_bytes = (size_t)TA * P.rec * sizeof(T);            // multiple of 16 by construction of TA
+    const size_t smem = tile_bytes + (size_t)P.cells * sizeof(int);
+    if (smem > 227 * 1024) mg::fatal("observation record too large for the render kernel (%zu bytes of shared memory)", smem);
+    const int tiles = (n_total + TA - 1) / TA;
+    // scratch owned by the backend: tile -> arena table, per-agent headers, per-arena template tiles
+    if ((size_t)tiles > g_tile_arena_n) {
+        if (g_tile_arena) cudaFree(g_tile_arena);
+        g_tile_arena_n = (size_t)tiles + tiles / 4 + 64;
+        CUDA_CHECK(cudaMalloc(&g_tile_arena, g_tile_arena_n * sizeof(int)));
+    }
+    if ((size_t)n_total > g_obs_hdr_n) {
+        if (g_obs_hdr) cudaFree(g_obs_hdr);
+        g_obs_hdr_n = (size_t)n_total + n_total / 4 + 64;
+        CUDA_CHECK(cudaMalloc(&g_obs_hdr, 3 * g_obs_hdr_n * sizeof(int4)));
+    }
+    P.tile_arena = g_tile_arena;
+    P.hdr = g_obs_hdr;
+    {
+        int gt = (n_total + 255) / 256;
+        if (gt > 8 * g_sms) gt = 8 * g_sms;
+        obs_headers_kernel<<<gt, 256>>>(P, g_obs_hdr, g_tile_arena);
+        post_launch("obs_headers_kernel");
+    }
+    if (P.minimap) {
+        const size_t need = (size_t)hE.A * tile_bytes;
+        if (need > g_tmpl_bytes) {
+            if (g_tmpl) cudaFree(g_tmpl);
+            g_tmpl_bytes = need + need / 8;
+            CUDA_CHECK(cudaMalloc(&g_tmpl, g_tmpl_bytes));
+        }
+        obs_template_kernel<T><<<hE.A, 256>>>(P, (T *)g_tmpl);
+        post_launch("obs_template_kernel");
+        P.tmpl = g_tmpl;
+    }
+    static size_t configured = (size_t)-1;
+    static int ctas_per_sm = 1;
+    if (smem != configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(obs_render_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, obs_render_kernel<T>, THREADS, smem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        configured = smem;
+    }
+    const int grid = tiles < ctas_per_sm * g_sms ? tiles : ctas_per_sm * g_sms;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_profile) { profile_pair(&e0, &e1); CUDA_CHECK(cudaEventRecord(e0, 0)); }
+    obs_render_kernel<T><<<grid, THREADS, smem>>>(P);
+    post_launch("obs_render_kernel");
+    if (g_profile) CUDA_CHECK(cudaEventRecord(e1, 0));
+}
 
 void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total) {
     const int g = O.group;
@@ -954,54 +1054,8 @@ void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const 
         P.mm_ch[j] = ch + 2;
         P.grp_ch[j] = ch;
     }
-    const size_t tile_bytes = (size_t)OBS_TA * P.rec * sizeof(float);
-    const size_t smem = tile_bytes + (size_t)P.cells * sizeof(int);
-    if (smem > 227 * 1024) mg::fatal("observation record too large for the render kernel (%zu bytes of shared memory)", smem);
-    const int tiles = (n_total + OBS_TA - 1) / OBS_TA;
-    // scratch owned by the backend: tile -> arena table, per-arena template tiles
-    if ((size_t)tiles > g_tile_arena_n) {
-        if (g_tile_arena) cudaFree(g_tile_arena);
-        g_tile_arena_n = (size_t)tiles + tiles / 4 + 64;
-        CUDA_CHECK(cudaMalloc(&g_tile_arena, g_tile_arena_n * sizeof(int)));
-    }
-    if ((size_t)n_total > g_obs_hdr_n) {
-        if (g_obs_hdr) cudaFree(g_obs_hdr);
-        g_obs_hdr_n = (size_t)n_total + n_total / 4 + 64;
-        CUDA_CHECK(cudaMalloc(&g_obs_hdr, 3 * g_obs_hdr_n * sizeof(int4)));
-    }
-    P.tile_arena = g_tile_arena;
-    P.hdr = g_obs_hdr;
-    {
-        int gt = (n_total + 255) / 256;
-        if (gt > 8 * g_sms) gt = 8 * g_sms;
-        obs_headers_kernel<<<gt, 256>>>(P, g_obs_hdr, g_tile_arena);
-        post_launch("obs_headers_kernel");
-    }
-    if (P.minimap && (tile_bytes & 15) == 0) {
-        const size_t need = (size_t)hE.A * tile_bytes;
-        if (need > g_tmpl_bytes) {
-            if (g_tmpl) cudaFree(g_tmpl);
-            g_tmpl_bytes = need + need / 8;
-            CUDA_CHECK(cudaMalloc(&g_tmpl, g_tmpl_bytes));
-        }
-        obs_template_kernel<<<hE.A, 256>>>(P, g_tmpl);
-        post_launch("obs_template_kernel");
-        P.tmpl = g_tmpl;
-    }
-    static size_t configured = (size_t)-1;
-    static int ctas_per_sm = 1;
-    if (smem != configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(obs_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, obs_render_kernel, OBS_THREADS, smem));
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-        configured = smem;
-    }
-    const int grid = tiles < ctas_per_sm * g_sms ? tiles : ctas_per_sm * g_sms;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (g_profile) { profile_pair(&e0, &e1); CUDA_CHECK(cudaEventRecord(e0, 0)); }
-    obs_render_kernel<<<grid, OBS_THREADS, smem>>>(P);
-    post_launch("obs_render_kernel");
-    if (g_profile) CUDA_CHECK(cudaEventRecord(e1, 0));
+    if (O.half) launch_obs_typed<__half>(hE, P, n_total);
+    else launch_obs_typed<float>(hE, P, n_total);
 }
 
 }  // namespace be

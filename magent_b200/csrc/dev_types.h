@@ -147,8 +147,9 @@ struct StepArgs {
 struct ObsArgs {
     unsigned curmask;
     int group;
-    float *view;                              // [sum_a n][view_h][view_w][n_channel]
-    float *feature;                           // [sum_a n][feature_size]
+    void *view;                               // [sum_a n][view_h][view_w][n_channel]
+    void *feature;                            // [sum_a n][feature_size]
+    int half;                                 // 0: float32 (reference ABI), 1: IEEE half (compact hand-off)
 };
 
 enum InfoKind { INFO_ID = 0, INFO_POS, INFO_ALIVE, INFO_REWARD, INFO_ACTION_SCATTER, INFO_HP };

@@ -713,23 +713,24 @@ void Engine::to_host(bool keep_device_authoritative) {
 
 // ---------------------------------------------------------------------------------------------
 // the step loop
-void Engine::get_observation(int group, float **bufs) {               // GridWorld.cc:292-401
+void Engine::get_observation(int group, void **bufs, int half) {      // GridWorld.cc:292-401
     check_group(group, "GridWorld::get_observation");
     to_device();
     const int n = total(group);
     if (n == 0) return;
     const AgentTypeDef &t = *group_type_[group];
-    const size_t vbytes = (size_t)n * t.view.height * t.view.width * n_channel() * 4;
-    const size_t fbytes = (size_t)n * feature_size(group) * 4;
+    const size_t esz = half ? 2 : 4;
+    const size_t vbytes = (size_t)n * t.view.height * t.view.width * n_channel() * esz;
+    const size_t fbytes = (size_t)n * feature_size(group) * esz;
     const bool vdev = be::is_device_ptr(bufs[0]), fdev = be::is_device_ptr(bufs[1]);
     ObsArgs O;
-    O.curmask = curmask_; O.group = group;
+    O.curmask = curmask_; O.group = group; O.half = half ? 1 : 0;
     if (vdev) O.view = bufs[0];
     else {
         if (vbytes > view_stage_bytes_) {
             if (d_view_stage_) be::dfree(d_view_stage_);
             view_stage_bytes_ = vbytes + vbytes / 8 + 256;
-            d_view_stage_ = (float *)be::dmalloc(view_stage_bytes_);
+            d_view_stage_ = be::dmalloc(view_stage_bytes_);
         }
         O.view = d_view_stage_;
     }
@@ -738,7 +739,7 @@ void Engine::get_observation(int group, float **bufs) {               // GridWor
         if (fbytes > feat_stage_bytes_) {
             if (d_feat_stage_) be::dfree(d_feat_stage_);
             feat_stage_bytes_ = fbytes + fbytes / 8 + 256;
-            d_feat_stage_ = (float *)be::dmalloc(feat_stage_bytes_);
+            d_feat_stage_ = be::dmalloc(feat_stage_bytes_);
         }
         O.feature = d_feat_stage_;
     }

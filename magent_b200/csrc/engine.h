@@ -78,7 +78,7 @@ public:
 
     void reset();
     void add_agents(int group, int n, const char *method, const int *pos_x, const int *pos_y, const int *dir);
-    void get_observation(int group, float **bufs);
+    void get_observation(int group, void **bufs, int half = 0);     // half: compact f16 hand-off (extension)
     void set_action(int group, const int *actions);
     void step(int *done);
     void get_reward(int group, float *buf);
@@ -135,7 +135,8 @@ private:
     std::vector<int> cap_;              // per group capacity on the device
     unsigned curmask_ = 0;
     std::vector<int> order_;            // groups with set_action this step, in call order
-    float *d_view_stage_ = nullptr, *d_feat_stage_ = nullptr, *d_mm_val_ = nullptr;
+    void *d_view_stage_ = nullptr, *d_feat_stage_ = nullptr;
+    float *d_mm_val_ = nullptr;
     size_t view_stage_bytes_ = 0, feat_stage_bytes_ = 0;
     void *d_io_stage_ = nullptr; size_t io_stage_bytes_ = 0;
     int *pin_small_ = nullptr; size_t pin_small_ints_ = 0;

@@ -33,7 +33,7 @@ MG_API int env_new_game(EnvHandle *game, const char *name) {
 MG_API int env_delete_game(EnvHandle game) { delete E(game); return 0; }
 MG_API int env_config_game(EnvHandle game, const char *name, void *p_value) { E(game)->set_config(name, p_value); return 0; }
 MG_API int env_reset(EnvHandle game) { E(game)->reset(); return 0; }
-MG_API int env_get_observation(EnvHandle game, GroupHandle group, float **buffer) { E(game)->get_observation(group, buffer); return 0; }
+MG_API int env_get_observation(EnvHandle game, GroupHandle group, float **buffer) { E(game)->get_observation(group, (void **)buffer, 0); return 0; }
 MG_API int env_set_action(EnvHandle game, GroupHandle group, const int *actions) { E(game)->set_action(group, actions); return 0; }
 MG_API int env_step(EnvHandle game, int *done) { E(game)->step(done); return 0; }
 MG_API int env_get_reward(EnvHandle game, GroupHandle group, float *buffer) { E(game)->get_reward(group, buffer); return 0; }
@@ -83,6 +83,10 @@ MG_API int magent_b200_sync(EnvHandle game) { E(game)->sync(); return 0; }
 MG_API int magent_b200_select_arena(EnvHandle game, int arena) { E(game)->select_arena(arena); return 0; }
 MG_API int magent_b200_random_actions(EnvHandle game, GroupHandle group, void *, unsigned long long seed) {
     E(game)->random_actions(group, seed); return 0;
+}
+MG_API int magent_b200_get_observation_f16(EnvHandle game, GroupHandle group, void **buffer) {
+    E(game)->get_observation(group, buffer, 1);
+    return 0;
 }
 MG_API int magent_b200_get_counters(EnvHandle game, long long *out, int capacity) { return E(game)->get_counters(out, capacity); }
 MG_API long long magent_b200_launch_count(void) { return mg::be::launch_count(); }

@@ -423,7 +423,12 @@ MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a
                         if (fm != fs && E.mv_key[R.sb + fm] < key && ld_volatile(&E.mv_state[R.sb + fm]) == MV_ABSORBED &&
                             ld_volatile(&E.tgt[R.sb + fm]) == hcode) taken = true;
                     }
-                    if (!taken) { st_volatile(&E.tgt[f], hcode); ns = MV_ABSORBED; }
+                    if (!taken) {
+                        // the absorber's identity is part of this mover's state: later movers compare against it
+                        if (st == MV_ABSORBED && ld_volatile(&E.tgt[f]) != hcode) changed = true;
+                        st_volatile(&E.tgt[f], hcode);
+                        ns = MV_ABSORBED;
+                    }
                 }
             }
         }

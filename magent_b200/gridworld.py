@@ -229,7 +229,7 @@ class GridWorld(Environment):
 
     # ------------------------------------------------------------------ run
     def _init_obs_buf(self):
-        self.obs_bufs = [{}, {}]
+        self.obs_bufs = [{}, {}, {}, {}]       # view, feature (reference); f16 view, f16 feature (extension)
         self._blocks = {}
 
     def _get_obs_buf(self, group, key, shape, dtype):
@@ -408,19 +408,40 @@ class GridWorld(Environment):
         """route subsequent setup calls (add_agents/add_walls/set_seed) to one arena; -1 = all"""
         self._lib.magent_b200_select_arena(self.game, int(arena))
 
-    def get_observation_torch(self, handle, out=None):
+    def get_observation_torch(self, handle, out=None, dtype=None):
         """observation written straight into CUDA tensors through the same ABI call
-        (device pointers are detected by the engine; no PCIe traffic)."""
+        (device pointers are detected by the engine; no PCIe traffic).
+
+        dtype: torch.float32 (default, the reference layout) or torch.float16 (compact hand-off: every element
+        is the float32 value rounded to nearest-even; half the bytes)."""
         import torch
         g = self._hv(handle)
         n = self.get_num(handle)
         if out is None:
-            view = torch.empty((n,) + self.view_space[g], dtype=torch.float32, device="cuda")
-            feat = torch.empty((n,) + self.feature_space[g], dtype=torch.float32, device="cuda")
+            dtype = torch.float32 if dtype is None else dtype
+            view = torch.empty((n,) + self.view_space[g], dtype=dtype, device="cuda")
+            feat = torch.empty((n,) + self.feature_space[g], dtype=dtype, device="cuda")
         else:
             view, feat = out
+            dtype = view.dtype
+            assert feat.dtype == dtype and view.is_contiguous() and feat.is_contiguous()
         bufs = (ctypes.c_void_p * 2)(view.data_ptr(), feat.data_ptr())
-        self._lib.env_get_observation(self.game, g, bufs)
+        if dtype == torch.float16:
+            self._lib.magent_b200_get_observation_f16(self.game, g, bufs)
+        elif dtype == torch.float32:
+            self._lib.env_get_observation(self.game, g, bufs)
+        else:
+            raise ValueError("observation dtype must be torch.float32 or torch.float16")
+        return view, feat
+
+    def get_observation_f16(self, handle):
+        """(views, features) as float16 numpy arrays (compact hand-off; see get_observation for the layout)"""
+        g = self._hv(handle)
+        n = self.get_num(handle)
+        view = self._get_obs_buf(g, 2, (n,) + self.view_space[g], np.float16)
+        feat = self._get_obs_buf(g, 3, (n,) + self.feature_space[g], np.float16)
+        bufs = (ctypes.c_void_p * 2)(view.ctypes.data, feat.ctypes.data)
+        self._lib.magent_b200_get_observation_f16(self.game, g, bufs)
         return view, feat
 
     def set_random_actions(self, handle, seed):

@@ -87,12 +87,40 @@ void launch_obs_prepare(const EngineDev *dE, const EngineDev &, unsigned curmask
             for (int k = 0; k < cells; ++k) out[k] = (float)cnt[k] / (float)total;
         }
 }
+// software float32 -> binary16, round to nearest even (the emulation's own statement of the f16 hand-off format)
+static uint16_t f32_to_f16(float f) {
+    uint32_t u; memcpy(&u, &f, 4);
+    const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+    const uint32_t ex = (u >> 23) & 0xffu, man = u & 0x7fffffu;
+    if (ex == 0xffu) {
+        if (!man) return sign | 0x7c00u;
+        uint16_t r = (uint16_t)(0x7c00u + (man >> 13));
+        if (r == 0x7c00u) ++r;
+        return sign | r;
+    }
+    const int e = (int)ex - 127 + 15;
+    if (e >= 31) return sign | 0x7c00u;
+    if (e <= 0) {
+        if (e < -10) return sign;
+        const uint32_t m = man | 0x800000u;
+        const int shift = 14 - e;
+        uint32_t r = m >> shift;
+        const uint32_t rem = m & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+        if (rem > halfway || (rem == halfway && (r & 1u))) ++r;
+        return sign | (uint16_t)r;
+    }
+    uint32_t r = ((uint32_t)e << 10) | (man >> 13);
+    const uint32_t rem = man & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (r & 1u))) ++r;
+    return sign | (uint16_t)r;
+}
 void launch_obs(const EngineDev *dE, const EngineDev &, const ObsArgs &O, const float *mm_val, int) {
     const EngineDev &E = *dE;
     int g = O.group;
     const GroupDev &G = E.grp[g];
     int cells = G.view_w * G.view_h, C = E.n_channel;
     const AgentSoA &s = cur_soa(E, O.curmask, g);
+    std::vector<float> rec((size_t)cells * C), feat((size_t)G.feature_size);
     for (int a = 0; a < E.A; ++a) {
         int n = E.n[g * E.A + a], base = E.off[(size_t)g * (E.A + 1) + a];
         const float *mm = mm_val ? mm_val + (size_t)a * E.G * cells : nullptr;
@@ -100,12 +128,19 @@ void launch_obs(const EngineDev *dE, const EngineDev &, const ObsArgs &O, const 
             long gi = gidx(E, a, g, i);
             int cx = -1, cy = -1;
             if (mm) minimap_cell(E, G.view_w, G.view_h, s.x[gi], s.y[gi], cx, cy);
-            float *out = O.view + (size_t)(base + i) * cells * C;
+            float *out = O.half ? rec.data() : (float *)O.view + (size_t)(base + i) * cells * C;
             for (int vy = 0; vy < G.view_h; ++vy)
                 for (int vx = 0; vx < G.view_w; ++vx)
                     obs_compose_cell(E, O.curmask, a, g, s.x[gi], s.y[gi], cx, cy, vy, vx, mm,
                                      out + (size_t)(vy * G.view_w + vx) * C);
-            obs_feature(E, O.curmask, a, g, i, O.feature + (size_t)(base + i) * G.feature_size);
+            float *fo = O.half ? feat.data() : (float *)O.feature + (size_t)(base + i) * G.feature_size;
+            obs_feature(E, O.curmask, a, g, i, fo);
+            if (O.half) {
+                uint16_t *hv = (uint16_t *)O.view + (size_t)(base + i) * cells * C;
+                for (int q = 0; q < cells * C; ++q) hv[q] = f32_to_f16(rec[q]);
+                uint16_t *hf = (uint16_t *)O.feature + (size_t)(base + i) * G.feature_size;
+                for (int q = 0; q < G.feature_size; ++q) hf[q] = f32_to_f16(feat[q]);
+            }
         }
     }
 }

@@ -154,3 +154,41 @@ def test_render_dump_is_byte_identical(emu, tmp_path, which):
         assert a[0][name] == b[0][name], name
     assert any(line.startswith(b"0 ") for line in a[0]["video_1.txt"].splitlines()) or which != "battle"
     assert a[1] == b[1] and a[2] == b[2]
+
+
+def _f16_trace(lib, mk, steps, seed):
+    """per step: ((view, feature) float32, (view, feature) float16) of every group, random actions in between"""
+    env = mk(lib)
+    handles = env.get_handles()
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(steps):
+        rec = []
+        for h in handles:
+            if env.get_num(h) == 0:
+                continue
+            v32, f32 = [x.copy() for x in env.get_observation(h)]
+            v16, f16 = [x.copy() for x in env.get_observation_f16(h)]
+            rec.append((v32, f32, v16, f16))
+        out.append(rec)
+        for h in handles:
+            env.set_action(h, rs.randint(0, env.get_action_space(h)[0], size=env.get_num(h)).astype(np.int32))
+        env.step()
+        env.clear_dead()
+    return out
+
+
+@pytest.mark.parametrize("which", ["battle", "pursuit", "arrange"])
+def test_f16_observation_is_the_rounded_f32_observation(emu, which):
+    """magent_b200_get_observation_f16 (include/magent_b200_ext.h): every element equals the float32 observation
+    of the same state rounded to nearest-even (numpy astype), NaN payloads included; interleaving the two calls
+    does not disturb the state."""
+    mk = {"battle": lambda lib: pc.make_battle(lib, 40, 60, seed=3),
+          "pursuit": lambda lib: pc.make_pursuit(lib),
+          "arrange": lambda lib: pc.make_arrange(lib, 24, 14, n_goal=60, n_agent=150)}[which]
+    for rec in _f16_trace(emu, mk, 12 if which != "arrange" else 40, 5):
+        for v32, f32, v16, f16 in rec:
+            assert v16.dtype == np.float16 and v16.shape == v32.shape and f16.shape == f32.shape
+            with np.errstate(all="ignore"):
+                np.testing.assert_array_equal(v16.view(np.uint16), v32.astype(np.float16).view(np.uint16))
+                np.testing.assert_array_equal(f16.view(np.uint16), f32.astype(np.float16).view(np.uint16))

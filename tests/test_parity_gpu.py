@@ -184,7 +184,7 @@ def test_episodes_share_one_rng_stream():
 
 def test_empty_group_observation_and_actions():
     """a group with no agents: its calls are no-ops, the other group still observes (its minimap channel for the
-    empty group is 0/0 = NaN in the reference; NaN payloads differ between x86 and the GPU, so NaNs compare as a class)"""
+    empty group is 0/0 = NaN in the reference; the engine emits the x86 default-NaN payload, so even that is bit-exact)"""
     import magent_b200 as magent
 
     def run(lib):
@@ -204,10 +204,8 @@ def test_empty_group_observation_and_actions():
         return v, f, done, r, env.get_pos(h[0]).copy()
     a, b = run(checker_lib()), run(pc.CUDA_LIB)
     assert a[2] == b[2] is True
-    np.testing.assert_array_equal(np.isnan(a[0]), np.isnan(b[0]))
     assert np.isnan(a[0]).any()
-    ok = ~np.isnan(a[0])
-    np.testing.assert_array_equal(a[0][ok].view(np.uint32), b[0][ok].view(np.uint32))
+    np.testing.assert_array_equal(a[0].view(np.uint32), b[0].view(np.uint32))
     np.testing.assert_array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
     np.testing.assert_allclose(a[3], b[3], atol=pc.REWARD_TOL, rtol=0)
     np.testing.assert_array_equal(a[4], b[4])
@@ -308,3 +306,66 @@ def test_device_pointer_observation_matches_host_pointer():
     tv, tf = env.get_observation_torch(h)
     np.testing.assert_array_equal(tv.cpu().numpy().view(np.uint32), v.view(np.uint32))
     np.testing.assert_array_equal(tf.cpu().numpy().view(np.uint32), f.view(np.uint32))
+
+
+@pytest.mark.parametrize("which", ["battle", "pursuit", "arrange", "batch"])
+def test_f16_observation_is_the_rounded_reference_observation(which):
+    """compact hand-off (magent_b200_get_observation_f16): every element == the REFERENCE float32 observation of
+    the same state rounded to nearest-even, bit for bit (NaN payloads included); tiles of 8 agents, ragged tails
+    and arena-straddling tiles are covered by the 3-arena batch with odd group sizes"""
+    import magent_b200 as magent
+    if which == "batch":
+        A, size = 3, 30
+        env = magent.GridWorld("battle", map_size=size, _lib=pc.CUDA_LIB, _num_arenas=A)
+        env.set_seed(7)
+        env.reset()
+        for k, h in enumerate(env.get_handles()):
+            env.add_agents(h, method="random", n=37 + 6 * k)
+        refs = []
+        for a in range(A):
+            r = magent.GridWorld("battle", map_size=size, _lib=checker_lib())
+            r.set_seed(7 + a)
+            r.reset()
+            for k, h in enumerate(r.get_handles()):
+                r.add_agents(h, method="random", n=37 + 6 * k)
+            refs.append(r)
+        for g, h in enumerate(env.get_handles()):
+            v16, f16 = env.get_observation_f16(h)
+            rv = np.concatenate([r.get_observation(r.get_handles()[g])[0] for r in refs])
+            rf = np.concatenate([r.get_observation(r.get_handles()[g])[1] for r in refs])
+            np.testing.assert_array_equal(v16.view(np.uint16), rv.astype(np.float16).view(np.uint16))
+            np.testing.assert_array_equal(f16.view(np.uint16), rf.astype(np.float16).view(np.uint16))
+        return
+    mk = {"battle": lambda lib: pc.make_battle(lib, 40, 61, seed=3),
+          "pursuit": lambda lib: pc.make_pursuit(lib),
+          "arrange": lambda lib: pc.make_arrange(lib, 24, 14, n_goal=60, n_agent=150)}[which]
+    ref, env = mk(checker_lib()), mk(pc.CUDA_LIB)
+    rs = np.random.RandomState(14)
+    saw_nan = False
+    for _ in range(40 if which == "arrange" else 10):
+        for hr, he in zip(ref.get_handles(), env.get_handles()):
+            if ref.get_num(hr) == 0:
+                continue
+            rv, rf = ref.get_observation(hr)
+            v16, f16 = env.get_observation_f16(he)
+            saw_nan |= bool(np.isnan(rv).any())
+            with np.errstate(all="ignore"):
+                np.testing.assert_array_equal(v16.view(np.uint16), rv.astype(np.float16).view(np.uint16))
+                np.testing.assert_array_equal(f16.view(np.uint16), rf.astype(np.float16).view(np.uint16))
+        for hr, he in zip(ref.get_handles(), env.get_handles()):
+            act = rs.randint(0, ref.get_action_space(hr)[0], size=ref.get_num(hr)).astype(np.int32)
+            ref.set_action(hr, act)
+            env.set_action(he, act)
+        ref.step(), env.step()
+        ref.clear_dead(), env.clear_dead()
+
+
+def test_f16_device_pointer_observation():
+    import torch
+    env = pc.make_battle(pc.CUDA_LIB, 40, 150, 0)
+    h = env.get_handles()[1]
+    v, f = env.get_observation(h)
+    tv, tf = env.get_observation_torch(h, dtype=torch.float16)
+    assert tv.dtype == torch.float16 and tuple(tv.shape) == v.shape
+    np.testing.assert_array_equal(tv.cpu().numpy().view(np.uint16), v.astype(np.float16).view(np.uint16))
+    np.testing.assert_array_equal(tf.cpu().numpy().view(np.uint16), f.astype(np.float16).view(np.uint16))
