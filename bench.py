@@ -248,6 +248,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="battle512", choices=sorted(WORKLOADS))
     ap.add_argument("--arenas", type=int, default=None, help="override arenas per GPU")
+    ap.add_argument("--obs-dtype", default="f32", choices=["f32", "f16"],
+                    help="f32 = the reference ABI (headline); f16 = the compact hand-off extension (reported separately)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--_cpu-worker", dest="cpu_worker", action="store_true")
@@ -300,12 +302,15 @@ def main():
 
     # device-resident receive buffers, sized for the initial population (it only shrinks)
     dev = torch.device("cuda", local_rank)
+    half = args.obs_dtype == "f16"
+    obs_torch_dtype, obs_esz = (torch.float16, 2) if half else (torch.float32, 4)
+    obs_call = lib.magent_b200_get_observation_f16 if half else lib.env_get_observation
     bufs = {}
     for h in act:
         g = env._hv(h)
         n0 = env.get_num(h)
-        bufs[g] = (torch.empty((n0,) + spaces[g][0], dtype=torch.float32, device=dev),
-                   torch.empty((n0,) + spaces[g][1], dtype=torch.float32, device=dev),
+        bufs[g] = (torch.empty((n0,) + spaces[g][0], dtype=obs_torch_dtype, device=dev),
+                   torch.empty((n0,) + spaces[g][1], dtype=obs_torch_dtype, device=dev),
                    torch.empty((n0,), dtype=torch.float32, device=dev))
 
     import ctypes
@@ -315,7 +320,7 @@ def main():
             g = env._hv(h)
             v, f, _r = bufs[g]
             ptrs = (ctypes.c_void_p * 2)(v.data_ptr(), f.data_ptr())
-            lib.env_get_observation(env.game, g, ptrs)
+            obs_call(env.game, g, ptrs)
         for h in act:
             env.set_random_actions(h, seed)
         env.step()
@@ -339,7 +344,7 @@ def main():
     for h in act:
         g = env._hv(h)
         (vh, vw, vc), (fs,) = spaces[g]
-        obs_bytes += env.get_num(h) * 4 * (vh * vw * vc + fs) + A * wl["map_size"] ** 2 * 4
+        obs_bytes += env.get_num(h) * obs_esz * (vh * vw * vc + fs) + A * wl["map_size"] ** 2 * 4
     obs_bytes_per_launch = obs_bytes / len(act)
 
     barrier()
@@ -382,7 +387,7 @@ def main():
         def host_step():
             h2d = d2h = 0
             for h in act:
-                v, f = env.get_observation(h)
+                v, f = env.get_observation_f16(h) if half else env.get_observation(h)
                 d2h += v.nbytes + f.nbytes
             for h in act:
                 a = pools[env._hv(h)][:env.get_num(h)]
@@ -431,7 +436,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "obs_render_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if tj.get("workload") == args.workload:
+        if tj.get("workload") == args.workload and not half:
             traffic = tj.get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": "obs_render_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
@@ -446,8 +451,11 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "f32" if not half else "f32 state, f16 observation hand-off (extension, not the reference ABI)",
+        "data": "synthetic",
         "config": {"workload": wl["desc"], "arenas_per_gpu": A, "agents_per_arena_at_start": 2 * wl.get("n", 0) or None,
+                   "observation": "float16 via magent_b200_get_observation_f16 (extension)" if half
+                                  else "float32 via env_get_observation (reference ABI)",
                    "buffers": "device-resident (CUDA pointers through the C ABI)", "actions": "uniform random, generated on device",
                    "l2": "per-step observation output (%.0f MB) exceeds the 126 MB L2" % (obs_bytes / 1e6) if obs_bytes > 126e6
                          else "per-step output %.1f MB fits L2 (latency-bound workload)" % (obs_bytes / 1e6),
