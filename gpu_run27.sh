@@ -1,0 +1,18 @@
+#!/bin/bash
+cd /root/repo
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -q -m gpu 2>&1 | tail -8
+for rep in 1 2; do
+for v in base abl1 abl2 abl3 abl8; do
+  lib=$PWD/magent_b200/lib/variants/libmagent_$v.so; [ $v = base ] && lib=$PWD/magent_b200/lib/libmagent.so
+  MAGENT_B200_LIB=$lib timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu --no-e2e > gpurun_out/var_${v}.json 2> gpurun_out/var_${v}.err
+  python -c "
+import json; j=json.load(open('gpurun_out/var_${v}.json')); print('VAR $v rep$rep value %.3e ms/step %.3f obs_ms %.3f frac %.3f'%(j['value'], j['ms_per_step'], j['roofline']['mean_launch_ms'], j['roofline']['frac']))" || tail -3 gpurun_out/var_${v}.err
+done
+done
+for w in gather64 battle1m battle1; do
+  timeout 600 python bench.py --workload $w --steps 20 --warmup 5 --no-cpu --no-e2e > gpurun_out/v12_$w.json 2> gpurun_out/v12_$w.err
+  python -c "
+import json; j=json.load(open('gpurun_out/v12_$w.json')); print('WL $w value %.3e ms/step %.3f obs_ms %.3f frac %.3f'%(j['value'], j['ms_per_step'], j['roofline']['mean_launch_ms'], j['roofline']['frac']))" || tail -3 gpurun_out/v12_$w.err
+done
+python bench.py --obs-dtype f16 --steps 20 --warmup 5 --no-cpu > gpurun_out/v12_f16.json 2> gpurun_out/v12_f16.err; cat gpurun_out/v12_f16.json

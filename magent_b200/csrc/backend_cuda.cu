@@ -544,13 +544,16 @@ void launch_random_actions(const EngineDev *dE, const EngineDev &, unsigned curm
 //     render kernel fetches cell code and hp with two independent loads (no position -> plane -> agent chain).
 //     Only living agents own cells (dead ones were cleared in the step), stale values under empty cells are never read;
 //   * minimap (when enabled): counts per (arena, group, coarse cell); value = (float)count / (float)group size
-static float *g_hpn_plane = nullptr;
-static size_t g_hpn_plane_n = 0;
+static float *g_mm_pad = nullptr;             // [A][g_mm_stride] normalised minimap of the last prepare
+static size_t g_mm_pad_n = 0;
+static int g_mm_stride = 0;
 static const EngineDev *g_prepare_owner = nullptr;
 bool obs_prepare_valid(const EngineDev *dE) { return g_prepare_owner == dE; }
 
-__global__ void __launch_bounds__(256) obs_prepare_kernel(const EngineDev *gE, unsigned curmask, int og, int chunk,
-                                                          float *hpn_plane, int do_minimap) {
+// per observation state: (1) the hp_norm plane (hp / max_hp of the occupant, Map.cc:197) at every living agent's
+// body cells -- stale values elsewhere are never read because the kind plane says "empty" there; (2) the minimap
+// histogram of every (arena, group) in the observer's coarse grid.
+__global__ void __launch_bounds__(256) obs_prepare_kernel(const EngineDev *gE, unsigned curmask, int og, int chunk, int do_minimap) {
     extern __shared__ int hist[];
     const EngineDev &E = *gE;
     const int ag = blockIdx.y;               // a * G + j
@@ -568,7 +571,7 @@ __global__ void __launch_bounds__(256) obs_prepare_kernel(const EngineDev *gE, u
     const AgentSoA &s = G.soa[(curmask >> j) & 1u];
     const int scale_h = (E.H + vh - 1) / vh, scale_w = (E.W + vw - 1) / vw;
     const bool skip_absorbed = E.grp[og].can_absorb != 0;     // GridWorld.cc:343-347 (the OBSERVER's type decides)
-    float *plane = hpn_plane + (size_t)a * E.W * E.H;
+    float *plane = E.hpn + a * E.kplane;
     int counted = 0;
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         long gi = (long)a * G.cap + i;
@@ -576,8 +579,10 @@ __global__ void __launch_bounds__(256) obs_prepare_kernel(const EngineDev *gE, u
         const unsigned char fl = s.flags[gi];
         if (!(fl & FLAG_DEAD)) {
             const float v = s.hp[gi] / G.max_hp;
-            for (int bx = 0; bx < G.body_w; ++bx)
-                for (int by = 0; by < G.body_l; ++by) plane[(y + by) * E.W + x + bx] = v;
+            int bw, bh;
+            body_dims(G, agent_dir(E, s, gi), bw, bh);
+            for (int bx = 0; bx < bw; ++bx)
+                for (int by = 0; by < bh; ++by) plane[(long)(y + by + E.kpad) * E.kw + x + bx + E.kpad] = v;
         }
         if (do_minimap && !(skip_absorbed && (fl & FLAG_ABSORBED))) {
             atomicAdd(&hist[(y / scale_h) * vw + x / scale_w], 1);
@@ -593,7 +598,9 @@ __global__ void __launch_bounds__(256) obs_prepare_kernel(const EngineDev *gE, u
     }
 }
 
-__global__ void __launch_bounds__(256) minimap_norm_kernel(const EngineDev *gE, int og, float *mm_val, int total) {
+// normalised minimap, one padded row per arena: mm[a * stride + j * cells + cell]  (stride % 4 == 0 so that a row is a
+// legal TMA bulk-copy source)
+__global__ void __launch_bounds__(256) minimap_norm_kernel(const EngineDev *gE, int og, float *mm_val, int total, int stride) {
     const EngineDev &E = *gE;
     const int cells = E.grp[og].view_w * E.grp[og].view_h;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
@@ -601,7 +608,8 @@ __global__ void __launch_bounds__(256) minimap_norm_kernel(const EngineDev *gE, 
         // GridWorld.cc:350-357 (total_ct).  An empty (or fully absorbed) group is 0/0 in the reference: x86 divss
         // yields the default quiet NaN 0xFFC00000 whereas the GPU would give 0x7FFFFFFF, so emit the x86 payload.
         const int tot = E.mm_total[ag];
-        mm_val[k] = tot ? (float)E.mm_count[k] / (float)tot : __int_as_float((int)0xFFC00000u);
+        const int a = ag / E.G;
+        mm_val[(size_t)a * stride + (k - a * E.G * cells)] = tot ? (float)E.mm_count[k] / (float)tot : __int_as_float((int)0xFFC00000u);
     }
 }
 
@@ -610,26 +618,27 @@ void launch_obs_prepare(const EngineDev *dE, const EngineDev &hE, unsigned curma
     const int total = hE.A * hE.G * cells;
     int cap_max = 0;
     for (int g = 0; g < hE.G; ++g) cap_max = cap_max > hE.grp[g].cap ? cap_max : hE.grp[g].cap;
-    const size_t plane_n = (size_t)hE.A * hE.W * hE.H;
-    if (plane_n > g_hpn_plane_n) {
-        if (g_hpn_plane) cudaFree(g_hpn_plane);
-        CUDA_CHECK(cudaMalloc(&g_hpn_plane, plane_n * sizeof(float)));
-        CUDA_CHECK(cudaMemsetAsync(g_hpn_plane, 0, plane_n * sizeof(float), 0));
-        g_hpn_plane_n = plane_n;
-    }
+    g_prepare_owner = dE;
     if (mm_val) {
         CUDA_CHECK(cudaMemsetAsync(hE.mm_count, 0, (size_t)total * 4, 0));
         CUDA_CHECK(cudaMemsetAsync(hE.mm_total, 0, (size_t)hE.A * hE.G * 4, 0));
     }
     const int chunk = 4096;
     dim3 grid((cap_max + chunk - 1) / chunk, hE.A * hE.G);
-    g_prepare_owner = dE;
-    obs_prepare_kernel<<<grid, 256, cells * sizeof(int)>>>(dE, curmask, og, chunk, g_hpn_plane, mm_val ? 1 : 0);
+    obs_prepare_kernel<<<grid, 256, cells * sizeof(int)>>>(dE, curmask, og, chunk, mm_val ? 1 : 0);
     post_launch("obs_prepare_kernel");
     if (mm_val) {
+        g_mm_stride = (hE.G * cells + 3) & ~3;
+        const size_t need = (size_t)hE.A * g_mm_stride;
+        if (need > g_mm_pad_n) {
+            if (g_mm_pad) cudaFree(g_mm_pad);
+            CUDA_CHECK(cudaMalloc(&g_mm_pad, need * sizeof(float)));
+            CUDA_CHECK(cudaMemsetAsync(g_mm_pad, 0, need * sizeof(float), 0));
+            g_mm_pad_n = need;
+        }
         int g2 = (total + 255) / 256;
         if (g2 > 8 * g_sms) g2 = 8 * g_sms;
-        minimap_norm_kernel<<<g2, 256>>>(dE, og, mm_val, total);
+        minimap_norm_kernel<<<g2, 256>>>(dE, og, g_mm_pad, total, g_mm_stride);
         post_launch("minimap_norm_kernel");
     }
 }
@@ -637,36 +646,29 @@ void launch_obs_prepare(const EngineDev *dE, const EngineDev &hE, unsigned curma
 // ------------------------------------------------------------------------------------------------
 // obs_render_kernel: the observation gather (GridWorld.cc:292-401 + Map::extract_view Map.cc:129-207).
 //
-// The kernel is a stream of 4.7 KB records (battle) whose content is ~97 % zeros + two dense minimap channels,
-// with a handful of values gathered through dependent loads (position -> occupancy plane -> hp).  It is
-// HBM-write-bound only if that load latency is hidden, so the design maximises resident warps per SM:
-//   * tile = OBS_TA (4) consecutive agents of the ABI concatenation = ONE 128-thread CTA, one warp per agent,
-//     one shared-memory tile (18.9 KB for battle) => 11 CTAs = 44 warps per SM;
-//   * the tile is initialised by a TMA bulk LOAD (cp.async.bulk ... mbarrier::complete_tx) of a per-arena
-//     *template tile* that already holds the arena's minimap channels (built once per call by
-//     obs_template_kernel, L2-resident: A x 18.9 KB) -- zero SM instructions for the 97 % of the bytes that are
-//     not agent-specific; while it is in flight every lane issues its position and occupancy-plane loads;
-//   * after the mbarrier flips, lanes scatter only the non-zero floats (wall / agent / hp channels, the +1 self
-//     marker; n_channel-word stride => conflict-free for odd channel counts);
+// The kernel is a stream of 4.7 KB records (battle) whose content is ~97 % zeros + the dense minimap channels +
+// a handful of values gathered from the map.  Two ceilings matter on B200 (profiles/README.md): the TMA
+// bulk-store stream itself (6.3 TB/s measured for this tile size) and the L2 slice throughput (~12 TB/s summed
+// over reads and writes) -- so every byte the kernel READS through L2 competes with the bytes it writes:
+//   * tile = TA (4) consecutive agents of the ABI concatenation = ONE 128-thread CTA, one warp per agent, one
+//     shared-memory tile (18.9 KB for battle), 8 CTAs = 32 warps per SM, tiles dealt round-robin so the whole
+//     grid works inside a window of a few arenas (their planes / minimaps stay L1/L2-hot);
+//   * the map is gathered from a ONE-BYTE kind plane (0 empty / 1 wall / 2+group; a view row is one 32-byte
+//     sector) and only occupied cells (~5 %) take a second, dependent load from the hp_norm plane;
+//   * the tile is composed entirely on the SM: each warp zero-fills its own record, copies the arena's
+//     normalised minimap (G x cells floats, L1-resident) into the minimap channels, adds the self marker and
+//     scatters the non-zero map values (n_channel-word stride => conflict-free for odd channel counts) --
+//     no template tile is read through L2;
 //   * the tile leaves the SM as ONE TMA bulk STORE (cp.async.bulk.global.shared::cta, SASS UBLKCP).  A tile's
-//     byte range in the output is contiguous and 16-byte aligned because OBS_TA % 4 == 0.
-// Tiles are dealt round-robin so that at any moment the whole grid works inside a window of a few arenas: their
-// occupancy planes, hp arrays and template tiles stay L1/L2-hot while the output streams past.
-// Algorithmic traffic per agent: 4*(view_h*view_w*n_channel + feature) bytes written, plus one compulsory read
-// of the occupancy plane per arena.  No tensor cores: there is no contraction on this path.
+//     byte range in the output is contiguous and 16-byte aligned because TA * sizeof(T) % 16 == 0.
+// Algorithmic traffic per agent: sizeof(T)*(view_h*view_w*n_channel + feature) bytes written, plus one compulsory
+// read of the occupancy plane per arena.  No tensor cores: there is no contraction here.
 #ifndef OBS_TA_N
 #define OBS_TA_N 4
 #endif
-#ifndef OBS_NIT_N
-#define OBS_NIT_N 8
-#endif
-#ifndef OBS_PREFETCH
-#define OBS_PREFETCH 1
-#endif
 #ifndef OBS_ABLATE
-#define OBS_ABLATE 0                 // profiling experiments only (profiles/README.md): 1 no plane gather, 2 no template
-#endif                               // load, 4 no feature rows, 8 no bulk store -- results are WRONG with any bit set
-constexpr int OBS_NIT = OBS_NIT_N;   // view cells per lane handled in one unrolled batch (8*32 = 256 in-range cells)
+#define OBS_ABLATE 0                 // profiling experiments only (profiles/README.md): 1 no plane gather, 2 no tile
+#endif                               // init (zero + minimap), 4 no feature rows, 8 no bulk store -- results are WRONG
 
 // output element type of the observation: float = the reference ABI (env_get_observation); __half = the compact
 // hand-off format of magent_b200_get_observation_f16 (each value is the f32 value rounded to nearest-even).
@@ -696,15 +698,18 @@ struct ObsParams {
     int scale_w, scale_h, minimap;
     int cap, embedding, n_action, n_total;
     const unsigned char *mask;
-    const int *off, *occ;
-    const float *hpn_plane;          // [A][H*W] hp / max_hp of the occupant (obs_prepare_kernel)
+    const int *off;
+    const unsigned char *kind_plane; // [A][kplane] padded: 0 empty / 1 wall / 2+group (EngineDev::kind)
+    const float *hpn_plane;          // [A][kplane] padded: hp / max_hp of the occupant (EngineDev::hpn)
+    int kpad, kw;
+    long kplane;
+    int turn, body_w, body_l;        // turn_mode: 4 view LUTs (one per heading), the heading rides in the header
+    const unsigned char *dir;
     const int *x, *y, *id, *act;
     const float *last_reward;
-    const float *mm;                 // [A][G][cells] normalised minimap, or nullptr
-    const void *tmpl;                // [A][TA*rec] template tiles (minimap channels filled), or nullptr
-    int ta;                          // agents per tile of the launched instantiation
-    const int *tile_arena;           // [n_tiles] arena of the tile, -1 when it straddles two arenas
-    const int4 *hdr;                 // [n_total][3] per-agent header in ABI order (obs_headers_kernel)
+    const float *mm;                 // [A][mm_stride] normalised minimap rows (G x cells floats each), or nullptr
+    int mm_stride;
+    const int4 *hdr;                 // [n_total] per-agent header in ABI order (obs_headers_kernel)
     void *view, *feature;            // element type = the kernel's template argument
     int mm_ch[MG_MAX_GROUPS];        // observation channel of group j's minimap
     int grp_ch[MG_MAX_GROUPS];       // observation channel ('has'; hp is +1) of group j
@@ -712,68 +717,77 @@ struct ObsParams {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-
-// pre-pass: per-agent header in ABI order -- everything the render kernel needs about the observer itself, so that
-// its only dependent loads are occupancy plane -> hp_norm:
-//   h0 = {x, y, arena, index}   h1 = {self minimap cell, id, last_action, bits(last_reward)}   h2 = {x/W, y/H, -, -}
-// plus, per tile, its arena (or -1 when the tile straddles two arenas).
-__global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr, int *tile_arena) {
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < P.n_total; o += gridDim.x * blockDim.x) {
-        const int a = P.A == 1 ? 0 : locate_arena(P.off, P.A, o);
-        const int i = o - P.off[a];
-        const long gi = (long)a * P.cap + i;
-        const int x = P.x[gi], y = P.y[gi];
-        int self_cell = -1;
-        float fx = 0.0f, fy = 0.0f;
-        if (P.minimap) {
-            self_cell = (y / P.scale_h) * P.vw + x / P.scale_w;             // GridWorld.cc:372-373
-            fx = (float)x / (float)P.W; fy = (float)y / (float)P.H;         // GridWorld.cc:394-395
-        }
-        hdr[3 * (size_t)o + 0] = make_int4(x, y, a, i);
-        hdr[3 * (size_t)o + 1] = make_int4(self_cell, P.id[gi], P.act[gi], __float_as_int(P.last_reward[gi]));
-        hdr[3 * (size_t)o + 2] = make_int4(__float_as_int(fx), __float_as_int(fy), 0, 0);
-        if (o % P.ta == 0) {
-            const int last = min(o + P.ta, P.n_total) - 1;
-            tile_arena[o / P.ta] = last < P.off[a + 1] ? a : -1;
-        }
-    }
-}
-
-// template tile of arena a: TA records, zero except the minimap channels (GridWorld.cc:374-381)
+// pre-pass, one warp per 32 observers in ABI order:
+//   * header h = {x, y, arena, self minimap cell | heading << 16}: everything the render kernel needs about the observer itself, so
+//     that its only dependent loads are kind plane -> hp_norm plane;
+//   * the complete non-spatial feature row (GridWorld.cc:386-396): id bits LSB first, one-hot last action, last
+//     reward, and x/W, y/H with the minimap.  A fresh agent's last_action == n_action ("dangerous", GridWorld.h:140)
+//     lands on the reward slot and is overwritten by it -- here the reward simply wins.  Rows are written by the
+//     whole warp (lane = feature index) so the stores coalesce.
 template <typename T>
-__global__ void __launch_bounds__(256) obs_template_kernel(ObsParams P, T *tmpl) {
-    constexpr int TA = ObsOut<T>::TA;
-    const int a = blockIdx.x;
-    T *t = tmpl + (size_t)a * TA * P.rec;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = threadIdx.x; q < (int)(TA * P.rec * sizeof(T) / 16); q += blockDim.x) ((float4 *)t)[q] = z;
-    __syncthreads();
-    const float *mm = P.mm + (size_t)a * P.G * P.cells;
-    const int per_slot = P.G * P.cells;
-    for (int q = threadIdx.x; q < TA * per_slot; q += blockDim.x) {
-        int slot = q / per_slot, r = q - slot * per_slot;
-        int j = r / P.cells, cell = r - j * P.cells;
-        t[slot * P.rec + cell * P.C + P.mm_ch[j]] = ObsOut<T>::cv(mm[r]);
+__global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr) {
+    __shared__ int s_id[8][32], s_act[8][32], s_x[8][32], s_y[8][32];
+    __shared__ float s_rew[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n_warps = gridDim.x * (blockDim.x >> 5);
+    for (int base = (blockIdx.x * (blockDim.x >> 5) + w) * 32; base < P.n_total; base += n_warps * 32) {
+        const int o = base + lane;
+        __syncwarp();
+        if (o < P.n_total) {
+            const int a = P.A == 1 ? 0 : locate_arena(P.off, P.A, o);
+            const long gi = (long)a * P.cap + (o - P.off[a]);
+            const int x = P.x[gi], y = P.y[gi];
+            s_x[w][lane] = x; s_y[w][lane] = y; s_id[w][lane] = P.id[gi]; s_act[w][lane] = P.act[gi]; s_rew[w][lane] = P.last_reward[gi];
+            const int self_cell = P.minimap ? (y / P.scale_h) * P.vw + x / P.scale_w : -1;  // GridWorld.cc:372-373
+            const int heading = P.turn ? (int)P.dir[gi] : 0;
+            hdr[o] = make_int4(x, y, a, (self_cell & 0xffff) | (heading << 16));
+        }
+        __syncwarp();
+        // the 32 rows are one contiguous block of 32 * F elements: lane-strided, fully coalesced
+        const int total = min(32, P.n_total - base) * P.F;
+        T *rows = (T *)P.feature + (size_t)base * P.F;
+        int k = lane / P.F, f = lane - k * P.F;
+        const int dk = 32 / P.F, df = 32 - dk * P.F;
+        for (int t = lane; t < total; t += 32) {
+            float v = 0.0f;
+            if (f < P.embedding) v = f < 31 ? (float)((s_id[w][k] >> f) & 1) : 0.0f;
+            else {
+                const int kk = f - P.embedding;
+                if (kk < P.n_action) v = kk == s_act[w][k] ? 1.0f : 0.0f;
+                else if (kk == P.n_action) v = s_rew[w][k];
+                else if (P.minimap && kk == P.n_action + 1) v = (float)s_x[w][k] / (float)P.W;     // GridWorld.cc:394-395
+                else if (P.minimap && kk == P.n_action + 2) v = (float)s_y[w][k] / (float)P.H;
+            }
+            rows[t] = ObsOut<T>::cv(v);
+            k += dk; f += df;
+            if (f >= P.F) { f -= P.F; ++k; }
+        }
     }
 }
 
 #ifndef OBS_MIN_CTAS
 #define OBS_MIN_CTAS 8
 #endif
-template <typename T>
+// NIT = view cells per lane held in registers (NIT * 32 >= in-range cells of the view whenever that is <= 256;
+// larger views take the unpipelined tail loop).
+template <typename T, int NIT>
 __global__ void __launch_bounds__(32 * ObsOut<T>::TA, OBS_MIN_CTAS * OBS_TA_N / ObsOut<T>::TA)
 obs_render_kernel(const __grid_constant__ ObsParams P) {
     constexpr int OBS_TA = ObsOut<T>::TA;
     constexpr int OBS_THREADS = 32 * OBS_TA;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *buf = (T *)smem_raw;                                   // one tile: OBS_TA records
-    int *lut = (int *)(buf + OBS_TA * P.rec);                 // in-range view cells only: cell << 16 | (dy & 0xff) << 8 | (dx & 0xff)
+    // in-range view cells only: lut[k] = {word offset of the cell inside a record, offset of the map cell in the
+    // padded planes relative to the observer's own cell}
+    int2 *lut = (int2 *)(buf + OBS_TA * P.rec);
+    float *mmbuf = (float *)(lut + (P.turn ? 4 : 1) * ((P.cells + 1) & ~1));     // the minimap row of the tile's first arena (TMA-staged)
     __shared__ __align__(8) unsigned long long mbar;
-    __shared__ int n_in_s;
+    __shared__ int n_in_s, tile_a0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned tile_bytes = (unsigned)OBS_TA * (unsigned)P.rec * (unsigned)sizeof(T);
+    const unsigned mm_bytes = (unsigned)P.mm_stride * 4u;
 
-    if (warp == 0) {                                          // compact the circular view mask (CircleRange, Range.h:151-189)
+    const int lut_stride = (P.cells + 1) & ~1;
+    if (warp == 0) {                                          // compact the view mask (Range.h:104-189)
         int k = 0;                                            // order-preserving: ballot prefix per 32 cells
         for (int base = 0; base < P.cells; base += 32) {
             const int cell = base + lane;
@@ -781,7 +795,25 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
             const unsigned bal = __ballot_sync(0xffffffffu, in);
             if (in) {
                 const int vy = cell / P.vw, vx = cell - vy * P.vw;
-                lut[k + __popc(bal & ((1u << lane) - 1u))] = (cell << 16) | (((P.oy + vy) & 0xff) << 8) | ((P.ox + vx) & 0xff);
+                const int q = k + __popc(bal & ((1u << lane) - 1u));
+                if (!P.turn) lut[q] = make_int2(cell * P.C, (P.oy + vy) * P.kw + P.ox + vx);
+                else {
+                    // the window is laid out in the observer's frame: one LUT per heading (Map.cc:140-146, 515-560)
+                    for (int d = 0; d < 4; ++d) {
+                        const bool upright = d == DIR_NORTH || d == DIR_SOUTH;
+                        int rx = 0, ry = 0, dx, dy;                     // save_to_real
+                        if (d == DIR_SOUTH) { rx = P.body_w - 1; ry = P.body_l - 1; }
+                        else if (d == DIR_WEST) ry = P.body_w - 1;
+                        else if (d == DIR_EAST) rx = P.body_l - 1;
+                        (void)upright;
+                        const int ex = P.ox + vx, ey = P.oy + vy;       // rela_to_abs
+                        if (d == DIR_NORTH) { dx = ex; dy = ey; }
+                        else if (d == DIR_SOUTH) { dx = -ex; dy = -ey; }
+                        else if (d == DIR_WEST) { dx = ey; dy = -ex; }
+                        else { dx = -ey; dy = ex; }
+                        lut[d * lut_stride + q] = make_int2(cell * P.C, (ry + dy) * P.kw + rx + dx);
+                    }
+                }
             }
             k += __popc(bal);
         }
@@ -792,162 +824,170 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
         }
     }
     __syncthreads();
-    const int n_in = n_in_s;
-    const int nit = min(OBS_NIT, (n_in + 31) >> 5);
-    const int n_tiles = (P.n_total + OBS_TA - 1) / OBS_TA;
     unsigned phase = 0;
-    // software pipeline: the header of the NEXT tile is fetched while the current one is composed
+    const int n_in = n_in_s;
+    const int n_tiles = (P.n_total + OBS_TA - 1) / OBS_TA;
+    constexpr bool WARP_FILL = sizeof(T) == 4;                // f16 records may share a word with their neighbour
+    // this lane's slice of the view LUT never changes: small views keep it in registers, large ones re-read smem
+    constexpr bool LUT_REGS = NIT <= 4;
+    int2 lreg[LUT_REGS ? NIT : 1];
+    if (LUT_REGS) {
+#pragma unroll
+        for (int it = 0; it < (LUT_REGS ? NIT : 1); ++it) lreg[it] = it * 32 + lane < n_in ? lut[it * 32 + lane] : make_int2(-1, 0);
+    }
+    // hd = heading of the observer (always 0 without turn_mode)
+    auto lutv = [&](int it, int hd) -> int2 {
+        if (P.turn) return it * 32 + lane < n_in ? lut[hd * lut_stride + it * 32 + lane] : make_int2(-1, 0);
+        return LUT_REGS ? lreg[LUT_REGS ? it : 0] : (it * 32 + lane < n_in ? lut[it * 32 + lane] : make_int2(-1, 0));
+    };
+    // position of an observer's own cell in the padded planes (header word h = {x, y, arena, self cell})
+    auto plane_base = [&](const int4 &h) -> long { return h.z * P.kplane + (long)(h.y + P.kpad) * P.kw + h.x + P.kpad; };
+
+    // issue the kind-plane loads of one observer; the pad makes every view cell addressable
+    auto load_kinds = [&](const int4 &h, bool on, int (&kd)[NIT]) {
+        const unsigned char *kp = P.kind_plane + plane_base(h);
+        const int hd = (h.w >> 16) & 3;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int2 l = lutv(it, hd);
+            kd[it] = (on && l.x >= 0 && !(OBS_ABLATE & 1)) ? __ldg(kp + l.y) : 0;
+        }
+    };
+
+    // software pipeline over this CTA's tiles i, i + grid, ...: while tile i is composed, the kind loads of tile
+    // i+1 and the header loads of tile i+2 are in flight
+    const int4 zero4 = make_int4(0, 0, 0, 0);
     int tile = blockIdx.x;
-    int ta_next = -1;
-    int4 h0n = make_int4(0, 0, 0, 0), h1n = h0n, h2n = h0n;
-    if (tile < n_tiles) {
-        ta_next = P.tile_arena[tile];
-        const int o = tile * OBS_TA + warp;
-        if (o < P.n_total) { h0n = P.hdr[3 * (size_t)o]; h1n = P.hdr[3 * (size_t)o + 1]; h2n = P.hdr[3 * (size_t)o + 2]; }
+    int4 hA = zero4;                      // tile i   : {x, y, arena, self cell}
+    int4 hA1 = zero4;                     // tile i+1
+    int kind[NIT];
+    {
+        const int o0 = tile * OBS_TA + warp, o1 = (tile + (int)gridDim.x) * OBS_TA + warp;
+        if (tile < n_tiles && o0 < P.n_total) hA = P.hdr[o0];
+        if (o1 < P.n_total) hA1 = P.hdr[o1];
+        load_kinds(hA, tile < n_tiles && o0 < P.n_total, kind);
     }
     for (; tile < n_tiles; tile += gridDim.x) {
         const int t0 = tile * OBS_TA;
         const int cnt = min(OBS_TA, P.n_total - t0);
-#if OBS_PREFETCH
-        const int ta = ta_next;
-        const int4 h0 = h0n, h1 = h1n, h2 = h2n;
-#else
-        const int ta = P.tile_arena[tile];
-        int4 h0 = make_int4(0, 0, 0, 0), h1 = h0, h2 = h0;
-        if (t0 + warp < P.n_total) { h0 = P.hdr[3 * (size_t)(t0 + warp)]; h1 = P.hdr[3 * (size_t)(t0 + warp) + 1]; h2 = P.hdr[3 * (size_t)(t0 + warp) + 2]; }
-#endif
-        const bool use_tmpl = P.tmpl != nullptr && ta >= 0;          // whole tile inside arena ta (block-uniform)
-        if (use_tmpl) {
-            if ((OBS_ABLATE & 2) && tile != (int)blockIdx.x) {
-                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncthreads();
-            } else if (threadIdx.x == 0) {
-                // the previous tile's bulk store must have finished READING the buffer before TMA overwrites it
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                             :: "r"(smem_u32(&mbar)), "r"(tile_bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             :: "r"(smem_u32(buf)), "l"((const T *)P.tmpl + (size_t)ta * OBS_TA * P.rec), "r"(tile_bytes),
-                                "r"(smem_u32(&mbar)) : "memory");
-            }
-        } else {
-            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncthreads();
+        const bool active = warp < cnt;
+        const int a = hA.z;
+        if (P.minimap && threadIdx.x == 0 && !(OBS_ABLATE & 2)) {
+            // stage the minimap row of the tile's first arena (thread 0 belongs to the first agent's warp).  mmbuf is
+            // free: every warp finished reading it before the __syncthreads that preceded the previous store.
+            tile_a0 = a;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(mm_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(mmbuf)), "l"(P.mm + (size_t)a * P.mm_stride), "r"(mm_bytes), "r"(smem_u32(&mbar)) : "memory");
+        }
+        // occupied cells only: the occupant's hp / max_hp (the kinds were loaded one tile ago)
+        const float *hpnp = P.hpn_plane + plane_base(hA);
+        const int hd = (hA.w >> 16) & 3;
+        float thp[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            thp[it] = 0.0f;
+            if (kind[it] >= 2) thp[it] = __ldg(hpnp + lutv(it, hd).y);
+        }
+        // next tile's kinds, next-next tile's header
+        int kind1[NIT];
+        const int o1 = (tile + (int)gridDim.x) * OBS_TA + warp;
+        load_kinds(hA1, o1 < P.n_total, kind1);
+        int4 hA2 = zero4;
+        {
+            const long o2 = ((long)tile + 2l * gridDim.x) * OBS_TA + warp;
+            if (o2 < P.n_total) hA2 = P.hdr[o2];
+        }
+        // the previous tile's bulk store must have finished READING the buffer before it is rewritten
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
+        if (!WARP_FILL && !(OBS_ABLATE & 2)) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = threadIdx.x; q < (int)(tile_bytes / 16u); q += OBS_THREADS) ((float4 *)buf)[q] = z;
+            for (int q = threadIdx.x; q < (int)((unsigned)OBS_TA * (unsigned)P.rec * (unsigned)sizeof(T) / 16u); q += OBS_THREADS) ((float4 *)buf)[q] = z;
             __syncthreads();
         }
-        const bool active = warp < cnt;
-        const int o = t0 + warp;
-        const int ax = h0.x, ay = h0.y, a = h0.z;
-        const int *occ = P.occ + (long)a * P.W * P.H;
-        const float *hpnp = P.hpn_plane + (long)a * P.W * P.H;
-        int tcode[OBS_NIT];
-        float thp[OBS_NIT];
-#pragma unroll
-        for (int it = 0; it < OBS_NIT; ++it) { tcode[it] = OCC_EMPTY; thp[it] = 0.0f; }
-        if (active && !(OBS_ABLATE & 1)) {
-            // issue this lane's plane loads (cell code + hp_norm, independent) back to back; they overlap the template load
-#pragma unroll
-            for (int it = 0; it < OBS_NIT; ++it) {
-                if (it < nit) {
-                    const int k = it * 32 + lane;
-                    if (k < n_in) {
-                        const int l = lut[k];
-                        const int x = ax + (int)(signed char)(l & 0xff), y = ay + (int)(signed char)((l >> 8) & 0xff);
-                        if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) {
-                            tcode[it] = __ldg(occ + y * P.W + x);
-                            thp[it] = __ldg(hpnp + y * P.W + x);
+        if (active) {
+            T *dst = buf + warp * P.rec;
+            if (!(OBS_ABLATE & 2)) {
+                if (WARP_FILL) {                                   // zero this warp's own record: scalar head / tail, 16-byte body
+                    float *w = (float *)dst;
+                    const int n = P.rec;
+                    const int head = min(n, (int)((4u - ((unsigned)(warp * P.rec) & 3u)) & 3u));
+                    const int body = (n - head) >> 2;
+                    if (lane < head) w[lane] = 0.0f;
+                    float4 *w4 = (float4 *)(w + head);
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                    for (int q = lane; q < body; q += 32) w4[q] = z;
+                    const int tail0 = head + (body << 2);
+                    if (tail0 + lane < n) w[tail0 + lane] = 0.0f;
+                    __syncwarp();
+                }
+                if (P.minimap) {                                   // GridWorld.cc:374-383: every group's minimap, unmasked
+                    unsigned done = 0;                             // the staged row has landed?
+                    while (!done) {
+                        asm volatile("{\n\t.reg .pred p;\n\t"
+                                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                     "selp.u32 %0, 1, 0, p;\n\t}"
+                                     : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+                    }
+                    const int self = (int)(short)(hA.w & 0xffff);
+                    const int step = 32 * P.C;
+                    if (a == tile_a0) {                            // the staged row (shared memory)
+                        for (int j = 0; j < P.G; ++j) {
+                            const float *row = mmbuf + j * P.cells;
+                            T *d = dst + P.mm_ch[j] + lane * P.C;
+#pragma unroll 2
+                            for (int cell = lane; cell < P.cells; cell += 32, d += step) *d = ObsOut<T>::cv(row[cell]);
+                        }
+                        __syncwarp();
+                        if (lane < P.G) {
+                            // self marker: +1 at the observer's coarse cell; NaN + 1 keeps the x86 payload in the reference
+                            const float v = mmbuf[lane * P.cells + self];
+                            if (v == v) dst[self * P.C + P.mm_ch[lane]] = ObsOut<T>::cv(v + 1.0f);
+                        }
+                    } else {                                       // the tile straddles arenas: this record reads its own row from L2
+                        const float *rows = P.mm + (size_t)a * P.mm_stride;
+                        for (int j = 0; j < P.G; ++j) {
+                            const float *row = rows + j * P.cells;
+                            T *d = dst + P.mm_ch[j] + lane * P.C;
+                            for (int cell = lane; cell < P.cells; cell += 32, d += step) *d = ObsOut<T>::cv(__ldg(row + cell));
+                        }
+                        __syncwarp();
+                        if (lane < P.G) {
+                            const float v = __ldg(rows + lane * P.cells + self);
+                            if (v == v) dst[self * P.C + P.mm_ch[lane]] = ObsOut<T>::cv(v + 1.0f);
                         }
                     }
                 }
             }
-        }
-#if OBS_PREFETCH
-        {   // prefetch the next tile's header
-            const int nt = tile + gridDim.x;
-            if (nt < n_tiles) {
-                ta_next = P.tile_arena[nt];
-                const int on = nt * OBS_TA + warp;
-                if (on < P.n_total) { h0n = P.hdr[3 * (size_t)on]; h1n = P.hdr[3 * (size_t)on + 1]; h2n = P.hdr[3 * (size_t)on + 2]; }
-            }
-        }
-#endif
-        if (use_tmpl && ((OBS_ABLATE & 2) == 0 || tile == (int)blockIdx.x)) {   // wait for the template tile to land
-            unsigned done = 0;
-            while (!done) {
-                asm volatile("{\n\t.reg .pred p;\n\t"
-                             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                             "selp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
-            }
-            phase ^= 1u;
-        }
-        if (active) {
-            T *dst = buf + warp * P.rec;
-            if (P.minimap) {
-                if (!use_tmpl) {                                   // tile straddles arenas: no template
-                    const float *mm = P.mm + (long)a * P.G * P.cells;
-                    for (int r = lane; r < P.G * P.cells; r += 32) {
-                        int j = r / P.cells, cell = r - j * P.cells;
-                        dst[cell * P.C + P.mm_ch[j]] = ObsOut<T>::cv(mm[r]);
-                    }
-                    __syncwarp();
-                }
-                if (lane < P.G) {                                                       // self marker, GridWorld.cc:382
-                    T *pm = dst + h1.x * P.C + P.mm_ch[lane];
-                    // NaN + 1 keeps the x86 payload in the reference; FADD would canonicalise it
-                    if constexpr (sizeof(T) == 4) {
-                        const float v = *pm;
-                        if (v == v) *pm = v + 1.0f;
-                    } else {                                // round once: f16(f32 minimap value + 1)
-                        const float v = __ldg(P.mm + ((long)a * P.G + lane) * P.cells + h1.x);
-                        *pm = ObsOut<T>::cv(v == v ? v + 1.0f : v);
-                    }
-                }
-            }
 #pragma unroll
-            for (int it = 0; it < OBS_NIT; ++it) {
-                const int t = tcode[it];
-                if (t != OCC_EMPTY) {
-                    T *px = dst + (lut[it * 32 + lane] >> 16) * P.C;
-                    if (t == OCC_WALL) px[0] = ObsOut<T>::cv(1.0f);
+            for (int it = 0; it < NIT; ++it) {
+                const int t = kind[it];
+                if (t != 0) {
+                    T *px = dst + lutv(it, hd).x;
+                    if (t == 1) px[0] = ObsOut<T>::cv(1.0f);
                     else {
-                        const int ch = P.grp_ch[code_group(t)];
+                        const int ch = P.grp_ch[t - 2];
                         px[ch] = ObsOut<T>::cv(1.0f);
                         px[ch + 1] = ObsOut<T>::cv(thp[it]);                            // hp / max_hp (Map.cc:197)
                     }
                 }
             }
-            for (int k = OBS_NIT * 32 + lane; k < n_in; k += 32) {                      // views with > 256 in-range cells
-                const int l = lut[k];
-                const int x = ax + (int)(signed char)(l & 0xff), y = ay + (int)(signed char)((l >> 8) & 0xff);
-                if ((unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H) {
-                    const int t = __ldg(occ + y * P.W + x);
-                    T *px = dst + (l >> 16) * P.C;
-                    if (t == OCC_WALL) px[0] = ObsOut<T>::cv(1.0f);
-                    else if (t >= 0) {
-                        const int ch = P.grp_ch[code_group(t)];
-                        px[ch] = ObsOut<T>::cv(1.0f);
-                        px[ch + 1] = ObsOut<T>::cv(__ldg(hpnp + y * P.W + x));
-                    }
+            const unsigned char *kindp = P.kind_plane + plane_base(hA);
+            for (int k = NIT * 32 + lane; k < n_in; k += 32) {                          // views with > NIT * 32 in-range cells
+                const int2 l = lut[hd * lut_stride + k];
+                const int t = __ldg(kindp + l.y);
+                T *px = dst + l.x;
+                if (t == 1) px[0] = ObsOut<T>::cv(1.0f);
+                else if (t >= 2) {
+                    const int ch = P.grp_ch[t - 2];
+                    px[ch] = ObsOut<T>::cv(1.0f);
+                    px[ch + 1] = ObsOut<T>::cv(__ldg(hpnp + l.y));
                 }
-            }
-            // non-spatial features straight to global memory (GridWorld.cc:386-396); all inputs come from the header
-            if (!(OBS_ABLATE & 4))
-            for (int f = lane; f < P.F; f += 32) {
-                float v = 0.0f;
-                if (f < P.embedding) v = f < 31 ? (float)((h1.y >> f) & 1) : 0.0f;
-                else {
-                    const int kk = f - P.embedding;
-                    if (kk < P.n_action) v = kk == h1.z ? 1.0f : 0.0f;
-                    else if (kk == P.n_action) v = __int_as_float(h1.w);
-                    else if (P.minimap && kk == P.n_action + 1) v = __int_as_float(h2.x);
-                    else if (P.minimap && kk == P.n_action + 2) v = __int_as_float(h2.y);
-                }
-                ((T *)P.feature)[(size_t)o * P.F + f] = ObsOut<T>::cv(v);
             }
         }
+        if (P.minimap && !(OBS_ABLATE & 2)) phase ^= 1u;
         // make the generic-proxy writes visible to the async proxy, then one thread fires the bulk store
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
@@ -963,68 +1003,49 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
             for (int q = threadIdx.x; q < cnt * P.rec; q += OBS_THREADS) gout[q] = buf[q];
             __syncthreads();
         }
+        // rotate the pipeline
+        hA = hA1; hA1 = hA2;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) kind[it] = kind1[it];
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-static void *g_tmpl = nullptr;
-static size_t g_tmpl_bytes = 0;
-static int *g_tile_arena = nullptr;
-static size_t g_tile_arena_n = 0;
 static int4 *g_obs_hdr = nullptr;
 static size_t g_obs_hdr_n = 0;
 
-template <typename T>
+template <typename T, int NIT>
 static void launch_obs_typed(const EngineDev &hE, ObsParams &P, int n_total) {
     constexpr int TA = ObsOut<T>::TA;
     constexpr int THREADS = 32 * TA;
-    P.ta = TA;
     const size_t tile_bytes = (size_t)TA * P.rec * sizeof(T);            // multiple of 16 by construction of TA
-    const size_t smem = tile_bytes + (size_t)P.cells * sizeof(int);
+    const size_t smem = tile_bytes + (size_t)(P.turn ? 4 : 1) * ((P.cells + 1) & ~1) * sizeof(int2) + (size_t)P.mm_stride * sizeof(float);
     if (smem > 227 * 1024) mg::fatal("observation record too large for the render kernel (%zu bytes of shared memory)", smem);
     const int tiles = (n_total + TA - 1) / TA;
-    // scratch owned by the backend: tile -> arena table, per-agent headers, per-arena template tiles
-    if ((size_t)tiles > g_tile_arena_n) {
-        if (g_tile_arena) cudaFree(g_tile_arena);
-        g_tile_arena_n = (size_t)tiles + tiles / 4 + 64;
-        CUDA_CHECK(cudaMalloc(&g_tile_arena, g_tile_arena_n * sizeof(int)));
-    }
-    if ((size_t)n_total > g_obs_hdr_n) {
+    if ((size_t)n_total > g_obs_hdr_n) {                                 // scratch owned by the backend: per-agent headers
         if (g_obs_hdr) cudaFree(g_obs_hdr);
         g_obs_hdr_n = (size_t)n_total + n_total / 4 + 64;
-        CUDA_CHECK(cudaMalloc(&g_obs_hdr, 3 * g_obs_hdr_n * sizeof(int4)));
+        CUDA_CHECK(cudaMalloc(&g_obs_hdr, g_obs_hdr_n * sizeof(int4)));
     }
-    P.tile_arena = g_tile_arena;
     P.hdr = g_obs_hdr;
     {
-        int gt = (n_total + 255) / 256;
-        if (gt > 8 * g_sms) gt = 8 * g_sms;
-        obs_headers_kernel<<<gt, 256>>>(P, g_obs_hdr, g_tile_arena);
+        int gt = (n_total + 255) / 256;                                  // one warp per 32 observers
+        if (gt > 16 * g_sms) gt = 16 * g_sms;
+        obs_headers_kernel<T><<<gt, 256>>>(P, g_obs_hdr);
         post_launch("obs_headers_kernel");
-    }
-    if (P.minimap) {
-        const size_t need = (size_t)hE.A * tile_bytes;
-        if (need > g_tmpl_bytes) {
-            if (g_tmpl) cudaFree(g_tmpl);
-            g_tmpl_bytes = need + need / 8;
-            CUDA_CHECK(cudaMalloc(&g_tmpl, g_tmpl_bytes));
-        }
-        obs_template_kernel<T><<<hE.A, 256>>>(P, (T *)g_tmpl);
-        post_launch("obs_template_kernel");
-        P.tmpl = g_tmpl;
     }
     static size_t configured = (size_t)-1;
     static int ctas_per_sm = 1;
     if (smem != configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(obs_render_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, obs_render_kernel<T>, THREADS, smem));
+        CUDA_CHECK(cudaFuncSetAttribute(obs_render_kernel<T, NIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, obs_render_kernel<T, NIT>, THREADS, smem));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         configured = smem;
     }
     const int grid = tiles < ctas_per_sm * g_sms ? tiles : ctas_per_sm * g_sms;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_profile) { profile_pair(&e0, &e1); CUDA_CHECK(cudaEventRecord(e0, 0)); }
-    obs_render_kernel<T><<<grid, THREADS, smem>>>(P);
+    obs_render_kernel<T, NIT><<<grid, THREADS, smem>>>(P);
     post_launch("obs_render_kernel");
     if (g_profile) CUDA_CHECK(cudaEventRecord(e1, 0));
 }
@@ -1042,11 +1063,12 @@ void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const 
     P.cap = G.cap; P.embedding = hE.embedding_size; P.n_action = G.n_action; P.n_total = n_total;
     P.mask = G.view_mask;
     P.off = hE.off + (size_t)g * (hE.A + 1);
-    P.occ = hE.occ;
-    P.hpn_plane = g_hpn_plane;
+    P.kind_plane = hE.kind; P.hpn_plane = hE.hpn; P.kpad = hE.kpad; P.kw = hE.kw; P.kplane = hE.kplane;
     const AgentSoA &s = G.soa[(O.curmask >> g) & 1u];
-    P.x = s.x; P.y = s.y; P.id = s.id; P.act = s.act; P.last_reward = s.last_reward;
-    P.mm = mm_val; P.view = O.view; P.feature = O.feature;
+    P.x = s.x; P.y = s.y; P.id = s.id; P.act = s.act; P.last_reward = s.last_reward; P.dir = s.dir;
+    P.turn = hE.turn_mode; P.body_w = G.body_w; P.body_l = G.body_l;
+    P.mm = mm_val ? g_mm_pad : nullptr; P.mm_stride = mm_val ? g_mm_stride : 0;
+    P.view = O.view; P.feature = O.feature;
     const int stride = 2 + (hE.minimap_mode ? 1 : 0);
     for (int j = 0; j < hE.G; ++j) {
         int rel = j - g; if (rel < 0) rel += hE.G;
@@ -1054,8 +1076,9 @@ void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const 
         P.mm_ch[j] = ch + 2;
         P.grp_ch[j] = ch;
     }
-    if (O.half) launch_obs_typed<__half>(hE, P, n_total);
-    else launch_obs_typed<float>(hE, P, n_total);
+    const bool small_view = G.view_count <= 4 * 32;             // in-range view cells held in registers: 4 or 8 per lane
+    if (O.half) { if (small_view) launch_obs_typed<__half, 4>(hE, P, n_total); else launch_obs_typed<__half, 8>(hE, P, n_total); }
+    else { if (small_view) launch_obs_typed<float, 4>(hE, P, n_total); else launch_obs_typed<float, 8>(hE, P, n_total); }
 }
 
 }  // namespace be

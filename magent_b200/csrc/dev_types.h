@@ -38,6 +38,8 @@ MG_HD int code_make(int g, int i) { return (g << 24) | i; }
 MG_HD int code_group(int c) { return c >> 24; }
 MG_HD int code_index(int c) { return c & 0xffffff; }
 
+enum { DIR_EAST = 0, DIR_SOUTH = 1, DIR_WEST = 2, DIR_NORTH = 3 };     // reference Direction (grid_def.h:15)
+
 struct AgentSoA {           // arena-major [A][cap]
     int *x, *y;             // top-left cell of the body (reference Agent::pos)
     float *hp;
@@ -58,6 +60,7 @@ struct GroupDev {
     int attack_in_group;
     int can_absorb;                           // AgentType::can_absorb (Map.cc:341-349)
     int view_w, view_h, view_x1, view_y1;     // view rectangle and its left-top offset from the eye
+    int view_count;                           // in-range cells of the view mask
     int view_xoff, view_yoff;                 // eye offset from pos  (= width/2, length/2)
     int att_xoff, att_yoff;
     int n_move, attack_base, n_action, n_attack;
@@ -112,6 +115,7 @@ struct EngineDev {
     int A, W, H, G;
     int nsep, bandwidth, large_map;           // GridWorld.cc:75-85, :407
     int minimap_mode, embedding_size, n_channel, channel_base;
+    int turn_mode;                            // agents carry a direction; [moves][turn L, R][attacks] (AgentType.cc:113-117)
     int cap_total, max_body;
     int any_absorb;                           // some group's type has can_absorb
     int scratch_stride;                       // per-arena stride of the step scratch: cap_total in HBM, 0 when it lives in the CTA's shared memory
@@ -122,6 +126,12 @@ struct EngineDev {
     int *off;                                 // [G][A+1] prefix of n over arenas (ABI concatenation)
     int *done;                                // [A] done flag of the last step
     int *occ, *claim_head;                    // [A][H*W]
+    // observation planes, padded by kpad cells on every side so that a view window never needs a bounds check:
+    // cell (x, y) of arena a lives at a * kplane + (y + kpad) * kw + x + kpad
+    unsigned char *kind;                      // [A][kplane] 0 empty / 1 wall / 2 + group; kept in step with occ
+    float *hpn;                               // [A][kplane] hp / max_hp of the occupant, rebuilt per observation state
+    int kpad, kw;
+    long kplane;
     // per-agent step scratch [A][cap_total]
     int *att_rank, *tgt, *in_head, *in_next, *death, *mv_nx, *mv_ny;
     unsigned *mv_key;

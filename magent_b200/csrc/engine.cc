@@ -1,5 +1,6 @@
 // engine.cc -- host side of the B200 grid-world engine.  See engine.h.
 #include "engine.h"
+#include "step_phases.h"
 
 #include <math.h>
 #include <stdarg.h>
@@ -64,6 +65,34 @@ RangeTab make_circle_range(float radius, float inner_radius, int parity) {
     return r;
 }
 
+// Sector of `angle` degrees opening towards -y (NORTH), stored as a height x width rectangle above the anchor
+// (reference src/gridworld/Range.h:104-144; used when view_angle / attack_angle < 180)
+RangeTab make_sector_range(float angle, float radius, int parity) {
+    static const double kPi = 3.1415926536;           // the reference's constant, not M_PI (Range.h:16)
+    const double eps = 0.00001;
+    RangeTab r;
+    r.height = (int)(radius + 0.5);
+    r.width = (int)(2 * radius * sin(angle / 2 * (kPi / 180)) + 0.5);
+    if (r.width % 2 != parity) r.width--;             // "fit to parity"
+    if (r.width < 0) r.width = 0;
+    r.mask.assign((size_t)r.width * r.height, 0);
+    const double lim = tan(angle / 2 * kPi / 180) + eps;
+    for (int i = 0; i < r.height; i++)
+        for (int j = 0; j < r.width; j++) {
+            const double dis_x = fabs(j - (r.width - 1) / 2.0), dis_y = fabs((double)(r.height - i));
+            const double dis = sqrt(dis_x * dis_x + dis_y * dis_y);
+            if (dis < radius + 0.2 + eps && dis_x / dis_y < lim) {
+                r.mask[(size_t)i * r.width + j] = 1;
+                r.dx.push_back(j - r.width / 2);
+                r.dy.push_back(i - r.height);
+                r.count++;
+            }
+        }
+    r.x1 = -(r.width / 2); r.y1 = -r.height;
+    r.x2 = (r.width - 1) / 2; r.y2 = -1;
+    return r;
+}
+
 void HostGroup::clear() { resize(0); dead_ct = 0; grp_reward = 0.0f; }
 void HostGroup::resize(int n) {
     x.resize(n); y.resize(n); id.resize(n); act.resize(n); op_obj.resize(n);
@@ -108,7 +137,6 @@ void Engine::set_config(const char *key, void *p_value) {     // GridWorld.cc:12
         if (bvalue) fatal("food_mode is not supported by the B200 engine yet (SURVEY.md §8f rank 4)");
     } else if (strequ(key, "turn_mode")) {
         turn_mode_ = bvalue;
-        if (bvalue) fatal("turn_mode is not supported by the B200 engine yet (SURVEY.md §8f rank 4)");
     } else if (strequ(key, "minimap_mode")) minimap_mode_ = bvalue;
     else if (strequ(key, "goal_mode")) goal_mode_ = bvalue;
     else if (strequ(key, "embedding_size")) embedding_size_ = ivalue;
@@ -164,20 +192,23 @@ void Engine::register_agent_type(const char *name, int n, const char **keys, flo
     if (t.view_angle >= 180) {
         if (fabs(t.view_angle - 360) > 1e-5) fatal("only supports ranges with angle = 360, when angle > 180.");
         t.view = make_circle_range(t.view_radius, 0, parity);
-    } else fatal("SectorRange views are not supported by the B200 engine yet (SURVEY.md §8f rank 4)");
+    } else {
+        t.view = make_sector_range(t.view_angle, t.view_radius, parity);
+        if (t.view.width < 1 || t.view.height < 1) fatal("empty view range (view_radius %g, view_angle %g)", t.view_radius, t.view_angle);
+    }
     if (t.attack_angle >= 180) {
         if (fabs(t.attack_angle - 360) > 1e-5) fatal("only supports ranges with angle = 360, when angle > 180.");
         t.attack = make_circle_range(t.attack_radius, t.width / 2.0f, parity);
-    } else if (t.attack_radius == 0 && t.attack_angle == 0) {
-        // the reference default (attack_angle = 0) builds an empty SectorRange(0, 0): no attack actions
-        t.attack = RangeTab();
-    } else fatal("SectorRange attacks are not supported by the B200 engine yet (SURVEY.md §8f rank 4)");
+    } else {
+        // the reference default (attack_angle = 0, radius 0) builds an empty SectorRange: no attack actions
+        t.attack = make_sector_range(t.attack_angle, t.attack_radius, parity);
+    }
     t.move = make_circle_range(t.speed, 0, 1);
     t.view_x_offset = t.width / 2; t.view_y_offset = t.length / 2;       // AgentType.cc:106-108
     t.att_x_offset = t.width / 2;  t.att_y_offset = t.length / 2;
     t.move_base = 0;
     t.turn_base = t.move.count;
-    t.attack_base = t.turn_base;                      // turn_mode off
+    t.attack_base = t.turn_base + (turn_mode_ ? 2 : 0);        // AgentType.cc:113-117: [moves][turn L, R][attacks]
     t.n_action = t.attack_base + t.attack.count;
     types_.insert(std::make_pair(str, t));
 }
@@ -415,9 +446,11 @@ int Engine::host_add_wall(HostArena &ar, int x, int y) {                        
     return 0;
 }
 
-int Engine::host_add_agent(HostArena &ar, int g, int x, int y) {                      // Map.cc:75-97 + Agent ctor
+int Engine::host_add_agent(HostArena &ar, int g, int x, int y, int dir) {             // Map.cc:75-97 + Agent ctor
     const AgentTypeDef &t = *group_type_[g];
-    if (!host_is_blank(ar, x, y, t.width, t.length)) return 1;
+    const bool upright = dir == DIR_NORTH || dir == DIR_SOUTH;                        // get_size_for_dir, Map.cc:597-607
+    const int bw = upright ? t.width : t.length, bh = upright ? t.length : t.width;
+    if (!host_is_blank(ar, x, y, bw, bh)) return 1;
     HostGroup &hg = ar.groups[g];
     int i = hg.size();
     if (i >= (1 << 23)) fatal("too many agents in one group of one arena (max %d)", 1 << 23);
@@ -427,10 +460,10 @@ int Engine::host_add_agent(HostArena &ar, int g, int x, int y) {                
     hg.op_obj[i] = -1;
     hg.hp[i] = t.hp;
     hg.next_reward[i] = t.step_reward; hg.last_reward[i] = 0.0f;
-    hg.last_op[i] = OP_NULL; hg.flags[i] = 0; hg.dir[i] = 3;
+    hg.last_op[i] = OP_NULL; hg.flags[i] = 0; hg.dir[i] = (unsigned char)dir;
     int code = code_make(g, i);
-    for (int bx = 0; bx < t.width; bx++)
-        for (int by = 0; by < t.length; by++)
+    for (int bx = 0; bx < bw; bx++)
+        for (int by = 0; by < bh; by++)
             ar.occ[(size_t)(y + by) * W_ + x + bx] = code;
     return 0;
 }
@@ -458,16 +491,28 @@ void Engine::add_agents(int group, int n, const char *method,
         } else {
             const AgentTypeDef &t = *group_type_[group];
             if (is_random) {
-                for (int i = 0; i < n; i++) { int x, y; host_random_blank(ar, t.width, t.length, x, y); host_add_agent(ar, group, x, y); }
+                for (int i = 0; i < n; i++) {
+                    // GridWorld.cc:228-243: with turn_mode the direction is drawn first, then the position of the
+                    // (possibly rotated) footprint
+                    const int dir = turn_mode_ ? (int)(rng_next(ar.rng) % 4u) : DIR_NORTH;
+                    const bool upright = dir == DIR_NORTH || dir == DIR_SOUTH;
+                    int x, y;
+                    host_random_blank(ar, upright ? t.width : t.length, upright ? t.length : t.width, x, y);
+                    host_add_agent(ar, group, x, y, dir);
+                }
             } else if (is_custom) {
                 for (int i = 0; i < n; i++) {
                     if (pos_dir && pos_dir[i] >= 4) fatal("invalid direction in GridWorld::add_agent");
-                    host_add_agent(ar, group, pos_x[i], pos_y[i]);
+                    host_add_agent(ar, group, pos_x[i], pos_y[i], turn_mode_ && pos_dir ? pos_dir[i] : DIR_NORTH);
                 }
             } else {
                 int x0 = pos_x[0], y0 = pos_x[1], x1 = x0 + pos_x[2], y1 = y0 + pos_x[3];
-                for (int x = x0; x < x1; x += t.width)
-                    for (int y = y0; y < y1; y += t.length) host_add_agent(ar, group, x, y);
+                const int dir = turn_mode_ ? pos_x[4] : DIR_NORTH;                    // GridWorld.cc:264-287
+                if (dir < 0 || dir >= 4) fatal("invalid direction in GridWorld::add_agent");
+                const bool upright = dir == DIR_NORTH || dir == DIR_SOUTH;
+                const int mw = upright ? t.width : t.length, mh = upright ? t.length : t.width;
+                for (int x = x0; x < x1; x += mw)
+                    for (int y = y0; y < y1; y += mh) host_add_agent(ar, group, x, y, dir);
             }
         }
     }
@@ -558,6 +603,7 @@ void Engine::to_device() {
             D.can_absorb = t.can_absorb;
             if (t.can_absorb) hE_.any_absorb = 1;
             D.view_w = t.view.width; D.view_h = t.view.height; D.view_x1 = t.view.x1; D.view_y1 = t.view.y1;
+            D.view_count = t.view.count;
             D.view_xoff = t.view_x_offset; D.view_yoff = t.view_y_offset;
             D.att_xoff = t.att_x_offset; D.att_yoff = t.att_y_offset;
             D.n_move = t.move.count; D.attack_base = t.attack_base; D.n_action = t.n_action; D.n_attack = t.attack.count;
@@ -588,6 +634,19 @@ void Engine::to_device() {
         hE_.off = (int *)dalloc((size_t)Gn * (A_ + 1) * 4);
         hE_.done = (int *)dalloc((size_t)A_ * 4);
         hE_.occ = (int *)dalloc(cells * 4); hE_.claim_head = (int *)dalloc(cells * 4);
+        {   // padded observation planes (dev_types.h): the pad covers the widest view window of any group
+            int pad = 0;
+            for (int g = 0; g < Gn; ++g) {
+                const AgentTypeDef &t = *group_type_[g];
+                const int ox = t.view_x_offset + t.view.x1, oy = t.view_y_offset + t.view.y1;
+                const int ext[4] = {-ox, ox + t.view.width - 1, -oy, oy + t.view.height - 1};
+                for (int e : ext) pad = std::max(pad, e + (turn_mode_ ? std::max(t.width, t.length) : 0));   // any heading
+            }
+            hE_.kpad = pad; hE_.kw = W_ + 2 * pad; hE_.kplane = (long)hE_.kw * (H_ + 2 * pad);
+            hE_.kind = (unsigned char *)dalloc((size_t)A_ * hE_.kplane + 16);
+            hE_.hpn = (float *)dalloc(((size_t)A_ * hE_.kplane + 4) * 4);
+            be::dmemset(hE_.hpn, 0, ((size_t)A_ * hE_.kplane + 4) * 4);
+        }
         hE_.att_rank = (int *)dalloc(sc * 4); hE_.tgt = (int *)dalloc(sc * 4);
         hE_.in_head = (int *)dalloc(sc * 4); hE_.in_next = (int *)dalloc(sc * 4);
         hE_.death = (int *)dalloc(sc * 4); hE_.mv_nx = (int *)dalloc(sc * 4); hE_.mv_ny = (int *)dalloc(sc * 4);
@@ -606,7 +665,7 @@ void Engine::to_device() {
     }
     // constants that may change between episodes without a re-allocation
     hE_.nsep = nsep_; hE_.large_map = large_map_; hE_.bandwidth = (W_ + nsep_ - 1) / nsep_;
-    hE_.minimap_mode = minimap_mode_; hE_.embedding_size = embedding_size_;
+    hE_.minimap_mode = minimap_mode_; hE_.embedding_size = embedding_size_; hE_.turn_mode = turn_mode_ ? 1 : 0;
     hE_.n_channel = n_channel(); hE_.channel_base = group2channel(0);
     {
         uint32_t p = MINSTD_A;
@@ -644,6 +703,20 @@ void Engine::to_device() {
     }
     for (int a = 0; a < A_; ++a)
         be::h2d(hE_.occ + (size_t)a * W_ * H_, arenas_[a].occ.data(), (size_t)W_ * H_ * 4);
+    {   // the kind plane mirrors the occupancy image; from here on the step kernels keep it current
+        std::vector<unsigned char> kp((size_t)hE_.kplane);
+        for (int a = 0; a < A_; ++a) {
+            std::fill(kp.begin(), kp.end(), (unsigned char)0);
+            const std::vector<int> &occ = arenas_[a].occ;
+            for (int y = 0; y < H_; ++y)
+                for (int x = 0; x < W_; ++x) {
+                    const int o = occ[(size_t)y * W_ + x];
+                    kp[(size_t)(y + hE_.kpad) * hE_.kw + x + hE_.kpad] =
+                        o == OCC_WALL ? 1 : o >= 0 ? (unsigned char)(2 + code_group(o)) : 0;
+                }
+            be::h2d(hE_.kind + (size_t)a * hE_.kplane, kp.data(), kp.size());
+        }
+    }
     be::dmemset(hE_.claim_head, 0xff, (size_t)A_ * W_ * H_ * 4);
     {
         std::vector<ArenaHdr> hdr(A_);
@@ -816,8 +889,19 @@ void Engine::clear_dead() {                                           // GridWor
     be::d2h(h_off_.data(), hE_.off, h_off_.size() * 4);
 }
 
-void Engine::set_goal(int, const char *, const int *) {
-    fatal("goal_mode is deprecated in the reference and not supported by the B200 engine");
+void Engine::set_goal(int group, const char *method, const int *) {                  // GridWorld.cc:667-679 (deprecated)
+    // Each agent of the group draws a goal position from the engine RNG.  Nothing in the reference ever reads
+    // Agent::goal (the two goal_mode feature slots are never written), so the observable effect is exactly the
+    // two draws per agent the RNG stream advances by.
+    check_group(group, "GridWorld::set_goal");
+    if (!strequ(method, "random")) fatal("invalid goal type in GridWorld::set_goal");
+    if (!was_reset_) fatal("set_goal before reset");
+    if (where_ == DEVICE) to_host(false);
+    for (int a = 0; a < A_; ++a) {
+        if (sel_arena_ >= 0 && sel_arena_ != a) continue;
+        HostArena &ar = arenas_[a];
+        for (int i = 0, n = ar.groups[group].size(); i < n; ++i) { rng_next(ar.rng); rng_next(ar.rng); }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -837,10 +921,16 @@ void Engine::collect_attack_events() {                // the list GridWorld::ste
         be::d2h(rank.data(), hE_.grp[g].ev_rank + base, (size_t)n * 4);
         be::d2h(x.data(), s.x + base, (size_t)n * 4); be::d2h(y.data(), s.y + base, (size_t)n * 4);
         be::d2h(act.data(), s.act + base, (size_t)n * 4); be::d2h(id.data(), s.id + base, (size_t)n * 4);
+        std::vector<unsigned char> dir(n, (unsigned char)DIR_NORTH);
+        if (turn_mode_) be::d2h(dir.data(), s.dir + base, (size_t)n);
         for (int i = 0; i < n; ++i) {
             if (rank[i] < 0) continue;
             const int k = act[i] - t.attack_base;
-            evs.push_back({rank[i], id[i], x[i] + t.att_x_offset + t.attack.dx[k], y[i] + t.att_y_offset + t.attack.dy[k]});
+            // Map::get_attack_obj (Map.cc:209-221): an attacker neither moves nor turns in the step it attacks
+            int rx, ry, dx, dy;
+            dir_real(hE_.grp[g], dir[i], rx, ry);
+            dir_rot(dir[i], t.att_x_offset + t.attack.dx[k], t.att_y_offset + t.attack.dy[k], dx, dy);
+            evs.push_back({rank[i], id[i], x[i] + rx + dx, y[i] + ry + dy});
         }
     }
     std::sort(evs.begin(), evs.end(), [](const Ev &p, const Ev &q) { return p.rank < q.rank; });

@@ -23,6 +23,7 @@ struct RangeTab {
     std::vector<int> dx, dy;            // num2delta
 };
 RangeTab make_circle_range(float radius, float inner_radius, int parity);
+RangeTab make_sector_range(float angle, float radius, int parity);
 
 // reference src/gridworld/AgentType.h:17-48
 struct AgentTypeDef {
@@ -165,7 +166,7 @@ private:
 
     // host-side placement (reference Map.cc:49-115, GridWorld.cc:180-290)
     bool host_is_blank(const HostArena &ar, int x, int y, int w, int h) const;
-    int host_add_agent(HostArena &ar, int g, int x, int y);
+    int host_add_agent(HostArena &ar, int g, int x, int y, int dir);
     int host_add_wall(HostArena &ar, int x, int y);
     void host_random_blank(HostArena &ar, int w, int h, int &x, int &y);
 };

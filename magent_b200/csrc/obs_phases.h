@@ -2,7 +2,7 @@
 // the test-only host emulation.
 //
 // Reference being restated: GridWorld::get_observation (src/gridworld/GridWorld.cc:292-401) and
-// Map::extract_view (src/gridworld/Map.cc:129-207) for dir == NORTH.
+// Map::extract_view (src/gridworld/Map.cc:129-207).
 #pragma once
 #include "step_phases.h"
 
@@ -26,7 +26,7 @@ MG_HD int obs_channel(const EngineDev &E, int me, int other) {
 // Compose the n_channel floats of view cell (vy, vx) of one observer.
 //   mm   : normalised minimap of the observer's arena, [G][vh*vw], or nullptr when minimap is off
 //   out  : n_channel floats, fully written
-MG_HD void obs_compose_cell(const EngineDev &E, unsigned curmask, int a, int g, int ax, int ay,
+MG_HD void obs_compose_cell(const EngineDev &E, unsigned curmask, int a, int g, int ax, int ay, int dir,
                             int self_cx, int self_cy, int vy, int vx, const float *mm, float *out) {
     const GroupDev &G = E.grp[g];
     const int C = E.n_channel;
@@ -43,6 +43,12 @@ MG_HD void obs_compose_cell(const EngineDev &E, unsigned curmask, int a, int g, 
     if (!G.view_mask[cell]) return;
     int x = ax + G.view_xoff + G.view_x1 + vx;
     int y = ay + G.view_yoff + G.view_y1 + vy;
+    if (E.turn_mode) {                   // the window is laid out in the observer's frame (Map.cc:140-146)
+        int ox, oy, dx, dy;
+        dir_real(G, dir, ox, oy);
+        dir_rot(dir, G.view_xoff + G.view_x1 + vx, G.view_yoff + G.view_y1 + vy, dx, dy);
+        x = ax + ox + dx; y = ay + oy + dy;
+    }
     if (x < 0 || x >= E.W || y < 0 || y >= E.H) return;
     int t = (E.occ + (long)a * E.W * E.H)[y * E.W + x];
     if (t == OCC_EMPTY) return;

@@ -55,6 +55,35 @@ struct ArenaRef {
     long nb;            // base into claim nodes        (a * scratch_stride * max_body)
     ArenaHdr *hdr;
 };
+// the one-byte kind plane of the observation (dev_types.h) follows every occupancy write
+MG_HD void kind_set(const EngineDev &E, int a, int x, int y, unsigned char k) {
+    E.kind[a * E.kplane + (long)(y + E.kpad) * E.kw + x + E.kpad] = k;
+}
+// ---- directions (turn_mode; reference Map.cc:515-607).  Without turn_mode every agent faces NORTH, for which
+// relative = absolute and the body is width x length.
+MG_HD int agent_dir(const EngineDev &E, const AgentSoA &s, long gi) { return E.turn_mode ? (int)s.dir[gi] : (int)DIR_NORTH; }
+// get_size_for_dir: footprint of a body facing `dir`
+MG_HD void body_dims(const GroupDev &G, int dir, int &w, int &h) {
+    if (dir == DIR_NORTH || dir == DIR_SOUTH) { w = G.body_w; h = G.body_l; } else { w = G.body_l; h = G.body_w; }
+}
+// rela_to_abs: displacement (rx, ry) in the agent's frame -> map displacement
+MG_HD void dir_rot(int dir, int rx, int ry, int &dx, int &dy) {
+    switch (dir) {
+        case DIR_NORTH: dx = rx; dy = ry; break;
+        case DIR_SOUTH: dx = -rx; dy = -ry; break;
+        case DIR_WEST: dx = ry; dy = -rx; break;
+        default: dx = -ry; dy = rx; break;          // EAST
+    }
+}
+// save_to_real: offset of the "real" (head) corner from the stored top-left corner
+MG_HD void dir_real(const GroupDev &G, int dir, int &ox, int &oy) {
+    switch (dir) {
+        case DIR_NORTH: ox = 0; oy = 0; break;
+        case DIR_SOUTH: ox = G.body_w - 1; oy = G.body_l - 1; break;
+        case DIR_WEST: ox = 0; oy = G.body_w - 1; break;
+        default: ox = G.body_l - 1; oy = 0; break;  // EAST
+    }
+}
 MG_HD ArenaRef arena_ref(const EngineDev &E, int a) {
     ArenaRef r;
     r.a = a;
@@ -156,10 +185,17 @@ MG_HD void phase_rank_target(Ctx &c, const EngineDev &E, const StepArgs &S, int 
         int fs = G.foff + i;
         E.att_rank[R.sb + fs] = pos;
         if (s.flags[gi] & FLAG_DEAD) continue;          // skipped at execution (GridWorld.cc:479)
-        // Map::get_attack_obj (Map.cc:209-252), dir == NORTH
+        // Map::get_attack_obj (Map.cc:209-252)
         int k = s.act[gi] - G.attack_base;
         int tx = s.x[gi] + G.att_xoff + G.att_dx[k];
         int ty = s.y[gi] + G.att_yoff + G.att_dy[k];
+        if (E.turn_mode) {
+            const int dir = s.dir[gi];
+            int rx, ry, dx, dy;
+            dir_real(G, dir, rx, ry);
+            dir_rot(dir, G.att_xoff + G.att_dx[k], G.att_yoff + G.att_dy[k], dx, dy);
+            tx = s.x[gi] + rx + dx; ty = s.y[gi] + ry + dy;
+        }
         if (tx < 0 || tx >= E.W || ty < 0 || ty >= E.H) continue;
         int t = R.occ[ty * E.W + tx];
         if (t < 0) continue;
@@ -272,10 +308,13 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
         if (dies) {
             s.flags[gi] |= FLAG_DEAD;
             s.next_reward[gi] = G.dead_penalty;          // assignment (GridWorld.h:206)
-            int x = s.x[gi], y = s.y[gi];
-            for (int bx = 0; bx < G.body_w; ++bx)
-                for (int by = 0; by < G.body_l; ++by)
+            int x = s.x[gi], y = s.y[gi], bw, bh;
+            body_dims(G, agent_dir(E, s, gi), bw, bh);
+            for (int bx = 0; bx < bw; ++bx)
+                for (int by = 0; by < bh; ++by) {
                     R.occ[(y + by) * E.W + x + bx] = OCC_EMPTY;
+                    kind_set(E, a, x + bx, y + by, 0);
+                }
             atomic_add(&E.dead_ct[g * E.A + a], 1);
         }
     }
@@ -284,9 +323,19 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
     c.add_count(E, CNT_STARVED, starved);
 }
 
-// phase 6: movers compute their target footprint and queue on every target cell
+// footprint a mover wants to occupy: its current footprint for a move, the rotated one for a turn
+MG_HD void mover_dims(const EngineDev &E, const GroupDev &G, const AgentSoA &s, long gi, bool turn, int &w, int &h) {
+    body_dims(G, agent_dir(E, s, gi), w, h);
+    if (turn) { int t = w; w = h; h = t; }           // every turn is by 90 degrees (wise = 2 * act - 1 is odd)
+}
+// direction after a turn action (reference GridWorld.cc:556 passes act - move_base, so wise = 2 * act - 1 is neither
+// -1 nor 1: Map::do_turn takes its "else" formula and new_dir = (dir + wise + 4) % 4, Map.cc:367)
+MG_HD int turned_dir(int dir, int act) { return (dir + 2 * act - 1 + 4) % 4; }
+
+// phase 6: movers (turn == false) or turners (turn == true, turn_mode only) compute their target footprint and
+// queue on every target cell.  Turn: Map::do_turn, Map.cc:361-406; move: Map::do_move, Map.cc:313-358.
 template <class Ctx>
-MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord) {
+MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord, bool turn) {
     ArenaRef R = arena_ref(E, a);
     for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
         int k, i; enum_locate(ord, idx, k, i);
@@ -295,8 +344,8 @@ MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, in
         const AgentSoA &s = cur_soa(E, S.curmask, g);
         long gi = gidx(E, a, g, i);
         int act = s.act[gi];
-        if (act < 0 || act >= G.n_move) continue;
-        if (s.flags[gi] & (FLAG_DEAD | FLAG_ABSORBED)) continue;     // GridWorld.cc:581
+        if (turn ? (act < G.n_move || act >= G.attack_base) : (act < 0 || act >= G.n_move)) continue;
+        if (s.flags[gi] & (turn ? FLAG_DEAD : (FLAG_DEAD | FLAG_ABSORBED))) continue;     // GridWorld.cc:553,581
         int fs = G.foff + i;
         long f = R.sb + fs;
         int x = s.x[gi], y = s.y[gi];
@@ -307,9 +356,23 @@ MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, in
             if (!(xm < 4 || xm > E.bandwidth - 4)) bucket = (unsigned)(x / E.bandwidth);
         }
         E.mv_key[f] = (bucket << 27) | ((unsigned)k << 23) | (unsigned)i;
-        int nx = x + G.move_dx[act], ny = y + G.move_dy[act];
+        int nx, ny;
+        if (turn) {
+            // the body pivots about its "real" corner (turn offsets are 0, AgentType.cc:108): the stored top-left
+            // corner follows from real_to_save with the new direction
+            const int dir = s.dir[gi], nd = turned_dir(dir, act);
+            int rx, ry, qx, qy;
+            dir_real(G, dir, rx, ry);
+            dir_real(G, nd, qx, qy);
+            nx = x + rx - qx; ny = y + ry - qy;
+        } else {
+            int dx = G.move_dx[act], dy = G.move_dy[act];
+            if (E.turn_mode) dir_rot(s.dir[gi], G.move_dx[act], G.move_dy[act], dx, dy);     // GridWorld.cc:587-598
+            nx = x + dx; ny = y + dy;
+        }
         E.mv_nx[f] = nx; E.mv_ny[f] = ny;
-        int bw = G.body_w, bh = G.body_l;
+        int bw, bh;
+        mover_dims(E, G, s, gi, turn, bw, bh);
         if (nx < 0 || ny < 0 || nx + bw >= E.W || ny + bh >= E.H) {          // Map.cc:455
             E.mv_state[f] = MV_OOB;
             continue;
@@ -319,7 +382,7 @@ MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, in
             for (int by = 0; by < bh; ++by)
                 if (R.occ[(ny + by) * E.W + nx + bx] == OCC_WALL) wall = true;
         // with absorbing types around, a wall-blocked mover may still bump into an absorber: keep it in the relaxation
-        if (wall && !E.any_absorb) { E.mv_state[f] = MV_STATIC_FAIL; continue; }
+        if (wall && (turn || !E.any_absorb)) { E.mv_state[f] = MV_STATIC_FAIL; continue; }
         E.mv_state[f] = MV_PENDING_FAIL;
         int ci = 0;
         for (int bx = 0; bx < bw; ++bx)
@@ -332,7 +395,7 @@ MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, in
 
 // who stands on cell (cx,cy) when the mover with order key `key` takes its turn?  -1 = nobody.
 // `self` (local flat id) is ignored.  Reads mover states with volatile loads.
-MG_HD int occupant_at_turn(const EngineDev &E, const ArenaRef &R, int cx, int cy, unsigned key, int self) {
+MG_HD int occupant_at_turn(const EngineDev &E, const ArenaRef &R, unsigned curmask, int cx, int cy, unsigned key, int self, bool turn) {
     int cell = cy * E.W + cx;
     int o = R.occ[cell];
     if (o >= 0) {
@@ -343,8 +406,9 @@ MG_HD int occupant_at_turn(const EngineDev &E, const ArenaRef &R, int cx, int cy
             bool left = so == MV_OK && E.mv_key[R.sb + fo] < key;
             if (left) {
                 const GroupDev &GO = E.grp[code_group(o)];
-                int ox = E.mv_nx[R.sb + fo], oy = E.mv_ny[R.sb + fo];
-                if (cx >= ox && cx < ox + GO.body_w && cy >= oy && cy < oy + GO.body_l) left = false;
+                int ox = E.mv_nx[R.sb + fo], oy = E.mv_ny[R.sb + fo], ow, oh;
+                mover_dims(E, GO, cur_soa(E, curmask, code_group(o)), gidx(E, R.a, code_group(o), code_index(o)), turn, ow, oh);
+                if (cx >= ox && cx < ox + ow && cy >= oy && cy < oy + oh) left = false;
             }
             if (!left) return fo;
         }
@@ -361,7 +425,7 @@ claimants:
 // phase 7 (swept until stable): a mover succeeds iff all its target cells are free at its turn
 // (Map::do_move / is_blank_area, Map.cc:313-358,454-470)
 template <class Ctx>
-MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord) {
+MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord, bool turn) {
     ArenaRef R = arena_ref(E, a);
     bool changed = false;
     for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
@@ -374,18 +438,20 @@ MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a
         if (st != MV_PENDING_FAIL && st != MV_OK && st != MV_ABSORBED && st != MV_SKIPPED) continue;
         unsigned key = E.mv_key[f];
         int nx = E.mv_nx[f], ny = E.mv_ny[f];
+        int bw, bh;                                   // footprint being claimed
+        mover_dims(E, G, cur_soa(E, S.curmask, g), gidx(E, a, g, i), turn, bw, bh);
         bool ok = true;
         unsigned char ns;
         bool skipped = false;
-        if (G.can_absorb) {
+        if (G.can_absorb && !turn) {
             // an absorber that swallowed somebody earlier in this move phase is `absorbed` by the time its own turn
             // comes and is skipped (GridWorld.cc:581): whoever bumped into it queued on one of its current cells
             const AgentSoA &sm = cur_soa(E, S.curmask, g);
             const long gm = gidx(E, a, g, i);
             const int mycode = code_make(g, i);
             const int x0 = sm.x[gm], y0 = sm.y[gm];
-            for (int bx = 0; bx < G.body_w && !skipped; ++bx)
-                for (int by = 0; by < G.body_l && !skipped; ++by)
+            for (int bx = 0; bx < bw && !skipped; ++bx)
+                for (int by = 0; by < bh && !skipped; ++by)
                     for (int node = R.claim[(y0 + by) * E.W + x0 + bx]; node != -1; node = E.cl_next[R.nb + node]) {
                         const int fm = node / E.max_body;
                         if (fm != fs && E.mv_key[R.sb + fm] < key && ld_volatile(&E.mv_state[R.sb + fm]) == MV_ABSORBED &&
@@ -394,19 +460,19 @@ MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a
         }
         if (skipped) {
             ns = MV_SKIPPED;
-        } else if (!E.any_absorb) {
-            for (int bx = 0; bx < G.body_w && ok; ++bx)
-                for (int by = 0; by < G.body_l && ok; ++by)
-                    if (occupant_at_turn(E, R, nx + bx, ny + by, key, fs) != -1) ok = false;
+        } else if (!E.any_absorb || turn) {
+            for (int bx = 0; bx < bw && ok; ++bx)
+                for (int by = 0; by < bh && ok; ++by)
+                    if (occupant_at_turn(E, R, S.curmask, nx + bx, ny + by, key, fs, turn) != -1) ok = false;
             ns = ok ? MV_OK : MV_PENDING_FAIL;
         } else {
             // Map::do_move with can_absorb types (Map.cc:334-349): the first other agent in the footprint decides
             int hit = -1, hit_cell = -1;
-            for (int bx = 0; bx < G.body_w; ++bx)
-                for (int by = 0; by < G.body_l; ++by) {
+            for (int bx = 0; bx < bw; ++bx)
+                for (int by = 0; by < bh; ++by) {
                     const int cell = (ny + by) * E.W + nx + bx;
                     if (R.occ[cell] == OCC_WALL) { ok = false; continue; }
-                    const int o = occupant_at_turn(E, R, nx + bx, ny + by, key, fs);
+                    const int o = occupant_at_turn(E, R, S.curmask, nx + bx, ny + by, key, fs, false);
                     if (o != -1) { ok = false; if (hit == -1) { hit = o; hit_cell = cell; } }
                 }
             ns = ok ? MV_OK : MV_PENDING_FAIL;
@@ -470,10 +536,12 @@ MG_HD void phase_move_collide(Ctx &c, const EngineDev &E, const StepArgs &S, int
         }
         unsigned key = E.mv_key[f];
         int nx = E.mv_nx[f], ny = E.mv_ny[f];
+        int bw, bh;
+        mover_dims(E, G, cur_soa(E, S.curmask, g), gidx(E, a, g, i), false, bw, bh);
         int hit = -1;
-        for (int bx = 0; bx < G.body_w && hit == -1; ++bx)
-            for (int by = 0; by < G.body_l && hit == -1; ++by)
-                hit = occupant_at_turn(E, R, nx + bx, ny + by, key, fs);
+        for (int bx = 0; bx < bw && hit == -1; ++bx)
+            for (int by = 0; by < bh && hit == -1; ++by)
+                hit = occupant_at_turn(E, R, S.curmask, nx + bx, ny + by, key, fs, false);
         if (hit != -1) {
             int hg = 0;
             while (hg + 1 < E.G && hit >= E.grp[hg + 1].foff) ++hg;
@@ -500,16 +568,19 @@ MG_HD void phase_move_clear(Ctx &c, const EngineDev &E, const StepArgs &S, int a
         if (E.mv_state[f] != MV_OK && E.mv_state[f] != MV_ABSORBED) continue;
         const AgentSoA &s = cur_soa(E, S.curmask, g);
         long gi = gidx(E, a, g, i);
-        int x = s.x[gi], y = s.y[gi];
-        for (int bx = 0; bx < G.body_w; ++bx)
-            for (int by = 0; by < G.body_l; ++by)
+        int x = s.x[gi], y = s.y[gi], bw, bh;
+        body_dims(G, agent_dir(E, s, gi), bw, bh);
+        for (int bx = 0; bx < bw; ++bx)
+            for (int by = 0; by < bh; ++by) {
                 R.occ[(y + by) * E.W + x + bx] = OCC_EMPTY;
+                kind_set(E, a, x + bx, y + by, 0);
+            }
     }
 }
 
 // phase 9b: winners occupy their new cells; every queued mover unhooks its claimant nodes
 template <class Ctx>
-MG_HD void phase_move_fill(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord) {
+MG_HD void phase_move_fill(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord, bool turn) {
     ArenaRef R = arena_ref(E, a);
     for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
         int k, i; enum_locate(ord, idx, k, i);
@@ -521,17 +592,21 @@ MG_HD void phase_move_fill(Ctx &c, const EngineDev &E, const StepArgs &S, int a,
         int nx = E.mv_nx[f], ny = E.mv_ny[f];
         bool ok = st == MV_OK;
         int code = code_make(g, i);
-        for (int bx = 0; bx < G.body_w; ++bx)
-            for (int by = 0; by < G.body_l; ++by) {
+        const AgentSoA &s = cur_soa(E, S.curmask, g);
+        long gi = gidx(E, a, g, i);
+        int bw, bh;
+        mover_dims(E, G, s, gi, turn, bw, bh);
+        for (int bx = 0; bx < bw; ++bx)
+            for (int by = 0; by < bh; ++by) {
                 int cell = (ny + by) * E.W + nx + bx;
                 R.claim[cell] = -1;
-                if (ok) R.occ[cell] = code;
+                if (ok) { R.occ[cell] = code; kind_set(E, a, nx + bx, ny + by, (unsigned char)(2 + g)); }
             }
         if (ok) {
-            const AgentSoA &s = cur_soa(E, S.curmask, g);
-            long gi = gidx(E, a, g, i);
             s.x[gi] = nx; s.y[gi] = ny;
+            if (turn) s.dir[gi] = (unsigned char)turned_dir(s.dir[gi], s.act[gi]);
         }
+        if (turn) { E.mv_state[f] = MV_NONE; E.mv_key[f] = MVKEY_NONE; }     // the move phase starts from a clean slate
     }
 }
 
@@ -691,13 +766,21 @@ MG_HD void run_step(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
     }
     phase_attack_apply_starve(c, E, S, a, all);
     c.sync();
-    phase_move_register(c, E, S, a, ord);
-    relax_until_stable(c, flags, [&]() { return phase_move_relax(c, E, S, a, ord); });
+    if (E.turn_mode) {                                   // GridWorld.cc:544-571: all turns, then all moves
+        phase_move_register(c, E, S, a, ord, true);
+        relax_until_stable(c, flags, [&]() { return phase_move_relax(c, E, S, a, ord, true); });
+        phase_move_clear(c, E, S, a, ord);
+        c.sync();
+        phase_move_fill(c, E, S, a, ord, true);
+        c.sync();
+    }
+    phase_move_register(c, E, S, a, ord, false);
+    relax_until_stable(c, flags, [&]() { return phase_move_relax(c, E, S, a, ord, false); });
     phase_move_collide(c, E, S, a, ord);
     c.sync();
     phase_move_clear(c, E, S, a, ord);
     c.sync();
-    phase_move_fill(c, E, S, a, ord);
+    phase_move_fill(c, E, S, a, ord, false);
     c.sync();
     for (int r = 0; r < E.n_rules; ++r) {
         phase_reward_rule(c, E, S, a, r);
@@ -734,9 +817,10 @@ MG_HD void run_cull(Ctx &c, const EngineDev &E, unsigned curmask, int a) {
             dst.flags[di] = src.flags[si];
             dst.dir[di] = src.dir[si];
             if (i != j) {
-                int code = code_make(g, j);
-                for (int bx = 0; bx < G.body_w; ++bx)
-                    for (int by = 0; by < G.body_l; ++by)
+                int code = code_make(g, j), bw, bh;
+                body_dims(G, agent_dir(E, src, si), bw, bh);
+                for (int bx = 0; bx < bw; ++bx)
+                    for (int by = 0; by < bh; ++by)
                         R.occ[(y + by) * E.W + x + bx] = code;
             }
         };

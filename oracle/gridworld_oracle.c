@@ -11,8 +11,8 @@
  *
  * It restates the SEQUENTIAL semantics (the reference is only deterministic with OMP_NUM_THREADS=1,
  * SURVEY.md §0): each function cites the reference lines it follows.  Not restated (no shipped config on
- * the hot path uses them; the functions abort with a message): turn_mode, food_mode, goal_mode,
- * SectorRange, OP_ALIGN, render, DiscreteSnake.
+ * the hot path uses them; the functions abort with a message): food_mode, OP_ALIGN, render,
+ * DiscreteSnake.
  */
 #include <math.h>
 #include <stdbool.h>
@@ -62,6 +62,34 @@ static Range circle_range(float radius, float inner, int parity) {
     return r;
 }
 
+/* Range.h:104-144 (SectorRange): a sector of `angle` degrees opening to the north, in a rectangle above the anchor */
+static Range sector_range(float angle, float radius, int parity) {
+    static const double PI_REF = 3.1415926536;    /* Range.h:16 */
+    const double eps = 0.00001;
+    Range r;
+    r.height = (int)(radius + 0.5);
+    r.width = (int)(2 * radius * sin(angle / 2 * (PI_REF / 180)) + 0.5);
+    if (r.width % 2 != parity) r.width--;
+    if (r.width < 0) r.width = 0;
+    size_t n = (size_t)r.width * r.height;
+    r.in = calloc(n + 1, 1);
+    r.dx = calloc(n + 1, sizeof(int));
+    r.dy = calloc(n + 1, sizeof(int));
+    r.count = 0;
+    for (int i = 0; i < r.height; i++)
+        for (int j = 0; j < r.width; j++) {
+            double ax = fabs(j - (r.width - 1) / 2.0), ay = fabs((double)(r.height - i));
+            double d = sqrt(ax * ax + ay * ay);
+            if (d < radius + 0.2 + eps && ax / ay < tan(angle / 2 * PI_REF / 180) + eps) {
+                r.in[i * r.width + j] = 1;
+                r.dx[r.count] = j - r.width / 2; r.dy[r.count] = i - r.height; r.count++;
+            }
+        }
+    r.x1 = -r.width / 2; r.y1 = -r.height;
+    r.x2 = (r.width - 1) / 2; r.y2 = -1;
+    return r;
+}
+
 /* ---- agent types: AgentType.cc:30-123 ---- */
 typedef struct {
     char name[64];
@@ -71,18 +99,19 @@ typedef struct {
     int attack_in_group, can_absorb;
     float step_reward, kill_reward, dead_penalty, attack_penalty;
     Range view, attack, move;
-    int attack_base, n_action;
+    int turn_base, attack_base, n_action;
 } Type;
 
 /* ---- agents live in a pool; cells and groups refer to pool slots ---- */
 typedef struct {
-    int id, group, index, x, y, action, last_op, op_obj, involved;
+    int id, group, index, x, y, dir, action, last_op, op_obj, involved;   /* dir: EAST 0, SOUTH 1, WEST 2, NORTH 3 (grid_def.h:15) */
     bool dead, absorbed;
     float hp, next_reward, last_reward;
 } Agent;
 
 typedef struct { int type, n, cap, dead_ct; int *slot; float reward; } Group;
 typedef struct { int agent, action; } Act;
+enum { EAST = 0, SOUTH = 1, WEST = 2, NORTH = 3 };
 typedef struct { Act *v; int n, cap; } ActBuf;
 
 typedef struct { int group, index, entity; } Symbol;               /* RewardEngine.h:17-32 */
@@ -90,14 +119,14 @@ typedef struct { int op, nraw, raw[8]; int related[16], nrel; int isub[16], iobj
 typedef struct { int on, nrecv, recv[8]; float val[8]; bool terminal, trigger; int nin, in[16], inf[16]; } Rule;
 
 typedef struct {
-    int w, h, minimap_mode, goal_mode, embedding, reset_done, rules_ready;
+    int w, h, minimap_mode, goal_mode, turn_mode, embedding, reset_done, rules_ready;
     uint32_t rng;                                                   /* minstd_rand0 state */
     int ntype; Type type[MAXT];
     int ngroup; Group grp[MAXG];
     Agent *pool; int npool, cappool;
     int *cell;
     int id_counter, nsep, large;
-    ActBuf attack, move[17];
+    ActBuf attack, move[17], turn[17];
     Symbol sym[32]; int nsym;
     Node node[32]; int nnode;
     Rule rule[16]; int nrule;
@@ -116,7 +145,7 @@ static int feature_size(const Env *e, int g) {                                  
     return e->embedding + e->type[e->grp[g].type].n_action + 1 + (e->goal_mode ? 2 : 0) + (e->minimap_mode ? 2 : 0);
 }
 
-/* ---- map helpers: Map.cc:454-513 (dir is always NORTH: turn_mode not restated) ---- */
+/* ---- map helpers: Map.cc:454-513 ---- */
 static bool blank_area(const Env *e, int x, int y, int w, int h, int self) {
     if (x < 0 || y < 0 || x + w >= e->w || y + h >= e->h) return false;
     for (int i = 0; i < w; i++)
@@ -156,12 +185,13 @@ API int env_config_game(void *game, const char *key, void *p) {    /* GridWorld.
     else if (!strcmp(key, "map_height")) e->h = iv;
     else if (!strcmp(key, "minimap_mode")) e->minimap_mode = bv;
     else if (!strcmp(key, "goal_mode")) e->goal_mode = bv;
+    else if (!strcmp(key, "turn_mode")) e->turn_mode = bv;
     else if (!strcmp(key, "embedding_size")) e->embedding = iv;
     else if (!strcmp(key, "render_dir")) {}
     else if (!strcmp(key, "seed")) {
         uint32_t s = (uint32_t)(((unsigned long long)(long long)iv) % 2147483647ull);
         e->rng = s ? s : 1;
-    } else if (!strcmp(key, "food_mode") || !strcmp(key, "turn_mode")) { if (bv) die("not restated: ", key); }
+    } else if (!strcmp(key, "food_mode")) { if (bv) die("not restated: ", key); }
     else die("invalid argument in set_config : ", key);
     return 0;
 }
@@ -198,12 +228,13 @@ API int gridworld_register_agent_type(void *game, const char *name, int n, const
         else die("invalid agent config : ", k);
     }
     int parity = t->width % 2;                                      /* AgentType.cc:86-118 */
-    if (t->view_angle < 180) die("SectorRange not restated", NULL);
-    t->view = circle_range(t->view_radius, 0, parity);
+    if (t->view_angle < 180) t->view = sector_range(t->view_angle, t->view_radius, parity);
+    else t->view = circle_range(t->view_radius, 0, parity);
     if (t->attack_angle >= 180) t->attack = circle_range(t->attack_radius, t->width / 2.0f, parity);
-    else { memset(&t->attack, 0, sizeof(Range)); if (t->attack_radius != 0 || t->attack_angle != 0) die("SectorRange not restated", NULL); }
+    else t->attack = sector_range(t->attack_angle, t->attack_radius, parity);
     t->move = circle_range(t->speed, 0, 1);
-    t->attack_base = t->move.count;
+    t->turn_base = t->move.count;                                   /* AgentType.cc:110-118: [moves][turn L, R][attacks] */
+    t->attack_base = t->turn_base + (e->turn_mode ? 2 : 0);
     t->n_action = t->attack_base + t->attack.count;
     return 0;
 }
@@ -298,7 +329,7 @@ API int env_reset(void *game) {                                     /* GridWorld
     e->npool = 0;
     for (int g = 0; g < e->ngroup; g++) { e->grp[g].n = 0; e->grp[g].dead_ct = 0; }
     e->attack.n = 0;
-    for (int b = 0; b <= 16; b++) e->move[b].n = 0;
+    for (int b = 0; b <= 16; b++) e->move[b].n = e->turn[b].n = 0;
     if (!e->rules_ready) { plan_rules(e); e->rules_ready = 1; }
     e->reset_done = 1;
     return 0;
@@ -317,21 +348,52 @@ static void add_wall(Env *e, int x, int y) {                         /* Map.cc:1
     if (e->cell[y * e->w + x] >= 0) return;
     e->cell[y * e->w + x] = CELL_WALL;
 }
-static void add_agent(Env *e, int g, int x, int y) {                 /* Map.cc:75-97 + Agent ctor GridWorld.h:133-144 */
+/* ---- headings (turn_mode): Map.cc:515-607 ---- */
+static void size_for_dir(const Type *t, int dir, int *w, int *h) {   /* get_size_for_dir */
+    if (dir == NORTH || dir == SOUTH) { *w = t->width; *h = t->length; } else { *w = t->length; *h = t->width; }
+}
+static void rela_to_abs(int cx, int cy, int dir, int rx, int ry, int *ax, int *ay) {
+    switch (dir) {
+        case NORTH: *ax = cx + rx; *ay = cy + ry; break;
+        case SOUTH: *ax = cx - rx; *ay = cy - ry; break;
+        case WEST: *ax = cx + ry; *ay = cy - rx; break;
+        default: *ax = cx - ry; *ay = cy + rx; break;               /* EAST */
+    }
+}
+static void save_to_real(const Type *t, const Agent *a, int *rx, int *ry) {
+    switch (a->dir) {
+        case NORTH: *rx = a->x; *ry = a->y; break;
+        case SOUTH: *rx = a->x + t->width - 1; *ry = a->y + t->length - 1; break;
+        case WEST: *rx = a->x; *ry = a->y + t->width - 1; break;
+        default: *rx = a->x + t->length - 1; *ry = a->y; break;     /* EAST */
+    }
+}
+static void real_to_save(const Type *t, int rx, int ry, int dir, int *sx, int *sy) {
+    switch (dir) {
+        case NORTH: *sx = rx; *sy = ry; break;
+        case SOUTH: *sx = rx - t->width + 1; *sy = ry - t->length + 1; break;
+        case WEST: *sx = rx; *sy = ry - t->width + 1; break;
+        default: *sx = rx - t->length + 1; *sy = ry; break;         /* EAST */
+    }
+}
+
+static void add_agent(Env *e, int g, int x, int y, int dir) {        /* Map.cc:75-97 + Agent ctor GridWorld.h:133-144 */
     Group *G = &e->grp[g];
     const Type *t = &e->type[G->type];
-    if (!blank_area(e, x, y, t->width, t->length, -1)) return;       /* occupied: silently ignored, no id used */
+    int bw, bh;
+    size_for_dir(t, dir, &bw, &bh);
+    if (!blank_area(e, x, y, bw, bh, -1)) return;                    /* occupied: silently ignored, no id used */
     if (e->npool == e->cappool) { e->cappool = e->cappool ? 2 * e->cappool : 1024; e->pool = realloc(e->pool, sizeof(Agent) * e->cappool); }
     int s = e->npool++;
     Agent *a = &e->pool[s];
     memset(a, 0, sizeof *a);
-    a->id = e->id_counter++; a->group = g; a->x = x; a->y = y;
+    a->id = e->id_counter++; a->group = g; a->x = x; a->y = y; a->dir = dir;
     a->hp = t->hp; a->action = t->n_action; a->last_op = OP_NULL; a->op_obj = -1;
     a->last_reward = 0; a->next_reward = t->step_reward;
     if (G->n == G->cap) { G->cap = G->cap ? 2 * G->cap : 256; G->slot = realloc(G->slot, sizeof(int) * G->cap); }
     a->index = G->n;
     G->slot[G->n++] = s;
-    paint(e, x, y, t->width, t->length, s);
+    paint(e, x, y, bw, bh, s);
 }
 
 API int gridworld_add_agents(void *game, int group, int n, const char *method,
@@ -346,9 +408,22 @@ API int gridworld_add_agents(void *game, int group, int n, const char *method,
         return 0;
     }
     const Type *t = &e->type[e->grp[group].type];
-    if (rnd) for (int i = 0; i < n; i++) { int x, y; random_blank(e, t->width, t->length, &x, &y); add_agent(e, group, x, y); }
-    else if (cus) for (int i = 0; i < n; i++) { if (pdir && pdir[i] >= 4) die("invalid direction", NULL); add_agent(e, group, px[i], py[i]); }
-    else for (int x = px[0]; x < px[0] + px[2]; x += t->width) for (int y = px[1]; y < px[1] + px[3]; y += t->length) add_agent(e, group, x, y);
+    if (rnd) for (int i = 0; i < n; i++) {                           /* :228-243: heading first, then the rotated footprint */
+        int dir = e->turn_mode ? (int)(rng_draw(e) % 4u) : NORTH, bw, bh, x, y;
+        size_for_dir(t, dir, &bw, &bh);
+        random_blank(e, bw, bh, &x, &y);
+        add_agent(e, group, x, y, dir);
+    }
+    else if (cus) for (int i = 0; i < n; i++) {
+        if (pdir && pdir[i] >= 4) die("invalid direction", NULL);
+        add_agent(e, group, px[i], py[i], e->turn_mode && pdir ? pdir[i] : NORTH);
+    }
+    else {                                                           /* :264-287 */
+        int dir = e->turn_mode ? px[4] : NORTH, bw, bh;
+        if (dir < 0 || dir >= 4) die("invalid direction", NULL);
+        size_for_dir(t, dir, &bw, &bh);
+        for (int x = px[0]; x < px[0] + px[2]; x += bw) for (int y = px[1]; y < px[1] + px[3]; y += bh) add_agent(e, group, x, y, dir);
+    }
     return 0;
 }
 
@@ -384,11 +459,13 @@ API int env_get_observation(void *game, int g, float **bufs) {      /* GridWorld
     for (int i = 0; i < G->n; i++) {
         const Agent *a = &e->pool[G->slot[i]];
         float *out = view + (size_t)i * vh * vw * C;
-        int eye_x = a->x + t->width / 2, eye_y = a->y + t->length / 2;
-        int x_lo = eye_x + t->view.x1, y_lo = eye_y + t->view.y1;
+        int real_x, real_y, eye_x, eye_y;                           /* Map.cc:138-146: the window lives in the agent's frame */
+        save_to_real(t, a, &real_x, &real_y);
+        rela_to_abs(real_x, real_y, a->dir, t->width / 2, t->length / 2, &eye_x, &eye_y);
         for (int vy = 0; vy < vh; vy++)
             for (int vx = 0; vx < vw; vx++) {
-                int x = x_lo + vx, y = y_lo + vy;
+                int x, y;
+                rela_to_abs(eye_x, eye_y, a->dir, t->view.x1 + vx, t->view.y1 + vy, &x, &y);
                 if (x < 0 || x >= e->w || y < 0 || y >= e->h) continue;          /* window clipped to the map */
                 int c = e->cell[y * e->w + x];
                 if (c == CELL_EMPTY || !t->view.in[vy * vw + vx]) continue;
@@ -432,7 +509,7 @@ API int env_set_action(void *game, int g, const int *actions) {     /* GridWorld
         if (act < t->attack_base) {
             int b = 16;                                              /* boundary buffer */
             if (e->large) { int xm = e->pool[s].x % bw; if (!(xm < 4 || xm > bw - 4)) b = e->pool[s].x / bw; }
-            push(&e->move[b], s, act);
+            push(act < t->turn_base ? &e->move[b] : &e->turn[b], s, act);     /* the turn action keeps its raw number (:430-433) */
         } else push(&e->attack, s, act - t->attack_base);
     }
     return 0;
@@ -442,7 +519,9 @@ static void kill_agent(Env *e, Agent *v) {                          /* Agent::be
     const Type *tv = &e->type[e->grp[v->group].type];
     v->dead = true;
     v->next_reward = tv->dead_penalty;
-    paint(e, v->x, v->y, tv->width, tv->length, CELL_EMPTY);
+    int bw, bh;
+    size_for_dir(tv, v->dir, &bw, &bh);
+    paint(e, v->x, v->y, bw, bh, CELL_EMPTY);
     e->grp[v->group].dead_ct++;
 }
 
@@ -538,7 +617,9 @@ API int env_step(void *game, int *done) {                           /* GridWorld
         if (a->dead) continue;
         const Type *t = &e->type[e->grp[a->group].type];
         int k = e->attack.v[i].action;
-        int tx = a->x + t->width / 2 + t->attack.dx[k], ty = a->y + t->length / 2 + t->attack.dy[k];
+        int rx, ry, tx, ty;
+        save_to_real(t, a, &rx, &ry);
+        rela_to_abs(rx, ry, a->dir, t->width / 2 + t->attack.dx[k], t->length / 2 + t->attack.dy[k], &tx, &ty);
         int c = (tx >= 0 && tx < e->w && ty >= 0 && ty < e->h) ? e->cell[ty * e->w + tx] : CELL_EMPTY;
         if (c < 0 || (!t->attack_in_group && e->pool[c].group == a->group)) { a->next_reward += t->attack_penalty; continue; }
         Agent *v = &e->pool[c];
@@ -564,6 +645,29 @@ API int env_step(void *game, int *done) {                           /* GridWorld
             else { a->hp -= -t->step_recover; if (a->hp < 0.0) kill_agent(e, a); }
         }
     }
+    /* turn: :544-571, Map::do_turn Map.cc:361-406.  The caller passes the raw action number, so wise = 2 * act - 1 is
+       never -1: the "else" rotation formula always applies and new_dir = (dir + wise + 4) % 4.  With turn offsets 0
+       the pivot is the agent's real corner, which therefore stays put. */
+    for (int bi = 0; bi <= 16 && e->turn_mode; bi++) {
+        for (int i = 0; i < e->turn[bi].n; i++) {
+            int s = e->turn[bi].v[i].agent;
+            Agent *a = &e->pool[s];
+            if (a->dead) continue;
+            const Type *t = &e->type[e->grp[a->group].type];
+            int wise = e->turn[bi].v[i].action * 2 - 1;
+            int new_dir = (a->dir + wise + 4) % 4, bw, bh, rx, ry, sx, sy;
+            size_for_dir(t, a->dir, &bw, &bh);
+            save_to_real(t, a, &rx, &ry);
+            real_to_save(t, rx, ry, new_dir, &sx, &sy);
+            if (blank_area(e, sx, sy, bh, bw, s)) {
+                paint(e, a->x, a->y, bw, bh, CELL_EMPTY);
+                a->dir = new_dir;
+                paint(e, sx, sy, bh, bw, s);
+                a->x = sx; a->y = sy;
+            }
+        }
+        e->turn[bi].n = 0;
+    }
     /* move: :573-613, Map::do_move Map.cc:313-358; band buffers in order, then the boundary buffer */
     for (int bi = 0; bi <= 16; bi++) {
         int b = bi < 16 ? bi : 16;
@@ -572,20 +676,22 @@ API int env_step(void *game, int *done) {                           /* GridWorld
             Agent *a = &e->pool[s];
             if (a->dead || a->absorbed) continue;
             const Type *t = &e->type[e->grp[a->group].type];
-            int nx = a->x + t->move.dx[e->move[b].v[i].action], ny = a->y + t->move.dy[e->move[b].v[i].action];
-            if (blank_area(e, nx, ny, t->width, t->length, s)) {
-                paint(e, a->x, a->y, t->width, t->length, CELL_EMPTY);
-                paint(e, nx, ny, t->width, t->length, s);
+            int nx, ny, bw, bh;
+            rela_to_abs(a->x, a->y, a->dir, t->move.dx[e->move[b].v[i].action], t->move.dy[e->move[b].v[i].action], &nx, &ny);   /* :587-598 */
+            size_for_dir(t, a->dir, &bw, &bh);
+            if (blank_area(e, nx, ny, bw, bh, s)) {
+                paint(e, a->x, a->y, bw, bh, CELL_EMPTY);
+                paint(e, nx, ny, bw, bh, s);
                 a->x = nx; a->y = ny;
             } else {
-                int o = first_other(e, nx, ny, t->width, t->length, s);
+                int o = first_other(e, nx, ny, bw, bh, s);
                 if (o >= 0 && e->type[e->grp[e->pool[o].group].type].can_absorb) {   /* Map.cc:341-349 */
                     Agent *obj = &e->pool[o];
                     if (!obj->absorbed) {
                         obj->absorbed = true;
                         obj->hp = obj->hp * 2;
                         a->dead = true;                               /* no dead_penalty, dead_ct untouched */
-                        paint(e, a->x, a->y, t->width, t->length, CELL_EMPTY);
+                        paint(e, a->x, a->y, bw, bh, CELL_EMPTY);
                         a->last_op = OP_COLLIDE; a->op_obj = o;
                     }
                 } else if (o >= 0) { a->last_op = OP_COLLIDE; a->op_obj = o; }
@@ -649,6 +755,13 @@ API int env_get_info(void *game, int g, const char *name, void *buf) {          
 
 API int env_render(void *game) { (void)game; return 0; }
 API int env_render_next_file(void *game) { (void)game; return 0; }
-API int gridworld_set_goal(void *game, int g, const char *m, const int *b) { (void)game; (void)g; (void)m; (void)b; die("goal not restated", NULL); return 0; }
+API int gridworld_set_goal(void *game, int g, const char *m, const int *b) {     /* GridWorld.cc:667-679 (deprecated) */
+    Env *e = game;
+    (void)b;
+    if (strcmp(m, "random")) die("invalid goal type in GridWorld::set_goal", NULL);
+    /* two draws per agent; Agent::goal itself is never read anywhere in the reference */
+    for (int i = 0; i < e->grp[g].n; i++) { rng_draw(e); rng_draw(e); }
+    return 0;
+}
 API int discrete_snake_clear_dead(void *game) { (void)game; die("DiscreteSnake not restated", NULL); return 0; }
 API int discrete_snake_add_object(void *game, int a, int b, const char *c, const int *d) { (void)game; (void)a; (void)b; (void)c; (void)d; die("DiscreteSnake not restated", NULL); return 0; }

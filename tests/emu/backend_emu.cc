@@ -131,7 +131,7 @@ void launch_obs(const EngineDev *dE, const EngineDev &, const ObsArgs &O, const 
             float *out = O.half ? rec.data() : (float *)O.view + (size_t)(base + i) * cells * C;
             for (int vy = 0; vy < G.view_h; ++vy)
                 for (int vx = 0; vx < G.view_w; ++vx)
-                    obs_compose_cell(E, O.curmask, a, g, s.x[gi], s.y[gi], cx, cy, vy, vx, mm,
+                    obs_compose_cell(E, O.curmask, a, g, s.x[gi], s.y[gi], s.dir[gi], cx, cy, vy, vx, mm,
                                      out + (size_t)(vy * G.view_w + vx) * C);
             float *fo = O.half ? feat.data() : (float *)O.feature + (size_t)(base + i) * G.feature_size;
             obs_feature(E, O.curmask, a, g, i, fo);

@@ -224,6 +224,84 @@ def make_mixed(lib, map_size=36, seed=6, **kw):
     return env
 
 
+def sector_config(size):
+    """SectorRange views and attacks (angle < 180; reference Range.h:104-144, AgentType.cc:86-105): a 120-degree
+    view cone + 90-degree attack cone on 1x1 bodies against 2x2 bodies with a 60-degree view / 150-degree attack"""
+    import magent_b200 as magent
+    gw = magent.gridworld
+    cfg = gw.Config()
+    cfg.set({"map_width": size, "map_height": size, "minimap_mode": True, "embedding_size": 6})
+    scout = cfg.register_agent_type("scout", dict(
+        width=1, length=1, hp=6, speed=2, damage=2, step_recover=0.1, kill_supply=1,
+        view_range=gw.SectorRange(7, 120), attack_range=gw.SectorRange(2, 90),
+        step_reward=-0.005, kill_reward=2, dead_penalty=-1, attack_penalty=-0.05))
+    brute = cfg.register_agent_type("brute", dict(
+        width=2, length=2, hp=9, speed=1, damage=3, step_recover=0.05,
+        view_range=gw.SectorRange(5, 60), attack_range=gw.SectorRange(3, 150),
+        step_reward=0.0, kill_reward=1, dead_penalty=-0.5, attack_penalty=-0.1))
+    g0, g1 = cfg.add_group(scout), cfg.add_group(brute)
+    a, b = gw.AgentSymbol(g0, index='any'), gw.AgentSymbol(g1, index='any')
+    cfg.add_reward_rule(gw.Event(a, 'attack', b), receiver=a, value=0.2)
+    cfg.add_reward_rule(gw.Event(b, 'attack', a), receiver=[b, a], value=[0.3, -0.1])
+    return cfg
+
+
+def make_sector(lib, map_size=34, seed=4, **kw):
+    import magent_b200 as magent
+    env = magent.GridWorld(sector_config(map_size), _lib=lib, **kw)
+    env.set_seed(seed)
+    env.reset()
+    h = env.get_handles()
+    env.add_walls(method="random", n=20)
+    env.add_agents(h[0], method="random", n=140)
+    env.add_agents(h[1], method="random", n=40)
+    return env
+
+
+def turn_config(size):
+    """turn_mode (deprecated in the reference, no shipped config): agents carry a direction, the action space is
+    [moves][turn left, turn right][attacks], views / attacks / moves are relative to the heading, long bodies
+    (2x1, 1x3, 2x2) pivot about their head and can be blocked (Map::do_turn, Map.cc:361-406)"""
+    import magent_b200 as magent
+    gw = magent.gridworld
+    cfg = gw.Config()
+    cfg.set({"map_width": size, "map_height": size, "turn_mode": True, "minimap_mode": True, "embedding_size": 8})
+    lancer = cfg.register_agent_type("lancer", dict(
+        width=1, length=3, hp=7, speed=2, damage=2, step_recover=0.1, kill_supply=1,
+        view_range=gw.SectorRange(6, 100), attack_range=gw.SectorRange(3, 60),
+        step_reward=-0.005, kill_reward=2, dead_penalty=-1, attack_penalty=-0.05))
+    cart = cfg.register_agent_type("cart", dict(
+        width=2, length=1, hp=9, speed=1, damage=3, step_recover=0.05,
+        view_range=gw.CircleRange(4), attack_range=gw.CircleRange(1.5),
+        step_reward=0.0, kill_reward=1, dead_penalty=-0.5, attack_penalty=-0.1))
+    foot = cfg.register_agent_type("foot", dict(
+        width=1, length=1, hp=5, speed=1, damage=1, step_recover=0.1,
+        view_range=gw.CircleRange(5), attack_range=gw.SectorRange(2, 120),
+        step_reward=0.01, kill_reward=0.5, dead_penalty=-0.2, attack_penalty=-0.02))
+    g0, g1, g2 = cfg.add_group(lancer), cfg.add_group(cart), cfg.add_group(foot)
+    a, b, c = (gw.AgentSymbol(g, index='any') for g in (g0, g1, g2))
+    cfg.add_reward_rule(gw.Event(a, 'attack', b), receiver=a, value=0.2)
+    cfg.add_reward_rule(gw.Event(b, 'attack', c), receiver=[b, c], value=[0.3, -0.1])
+    cfg.add_reward_rule(gw.Event(c, 'collide', a), receiver=c, value=-0.05)
+    return cfg
+
+
+def make_turn(lib, map_size=36, seed=8, **kw):
+    import magent_b200 as magent
+    env = magent.GridWorld(turn_config(map_size), _lib=lib, **kw)
+    env.set_seed(seed)
+    env.reset()
+    h = env.get_handles()
+    env.add_walls(method="random", n=25)
+    env.add_agents(h[0], method="random", n=60)
+    env.add_agents(h[1], method="random", n=60)
+    env.add_agents(h[2], method="random", n=80)
+    # explicit headings as well: custom takes (x, y, dir), fill takes dir
+    env.add_agents(h[2], method="custom", pos=[[3, 3, 0], [5, 3, 1], [7, 3, 2], [9, 3, 3]])
+    env.add_agents(h[1], method="fill", pos=(12, 2), size=(4, 4), dir=0)
+    return env
+
+
 def make_battle_rect(lib, width=56, height=34, n=120, seed=2, **kw):
     """non-square map: map_width != map_height (minimap scales, feature x/W y/H, bounds all differ per axis)"""
     import magent_b200 as magent

@@ -192,3 +192,41 @@ def test_f16_observation_is_the_rounded_f32_observation(emu, which):
             with np.errstate(all="ignore"):
                 np.testing.assert_array_equal(v16.view(np.uint16), v32.astype(np.float16).view(np.uint16))
                 np.testing.assert_array_equal(f16.view(np.uint16), f32.astype(np.float16).view(np.uint16))
+
+
+def _goal_trace(lib):
+    """goal_mode (deprecated in the reference, GridWorld.cc:137,667-679,929): two extra, never-written feature
+    slots; set_goal('random') only advances the engine RNG by two draws per agent"""
+    import magent_b200 as magent
+    cfg = magent.builtin.config.battle.get_config(30)
+    cfg.set({"goal_mode": True})
+    env = magent.GridWorld(cfg, _lib=lib)
+    env.set_seed(5)
+    env.reset()
+    h = env.get_handles()
+    env.add_agents(h[0], method="random", n=40)
+    env.set_goal(h[0], "random")
+    env.add_agents(h[1], method="random", n=40)      # placement after the goal draws: the RNG stream must agree
+    out = [env.get_feature_space(h[0]), env.get_pos(h[1]).copy()]
+    rs = np.random.RandomState(1)
+    for _ in range(5):
+        for g in h:
+            v, f = env.get_observation(g)
+            out += [v.copy(), f.copy()]
+        for g in h:
+            env.set_action(g, rs.randint(0, 21, size=env.get_num(g)).astype(np.int32))
+        env.step()
+        env.set_goal(h[1], "random")                 # mid-episode: moves the attack shuffle of the next step
+        out.append(env.get_reward(h[0]).copy())
+        env.clear_dead()
+    return out
+
+
+def test_goal_mode_feature_slots_and_rng_draws(emu):
+    want, got = _goal_trace(pc.REF_LIB if os.path.exists(pc.REF_LIB) else pc.PORT_LIB), _goal_trace(emu)
+    assert want[0] == got[0] == (34 + 2,)
+    for a, b in zip(want[1:], got[1:]):
+        if a.dtype == np.float32 and a.ndim == 1:
+            np.testing.assert_allclose(a, b, atol=pc.REWARD_TOL, rtol=0)
+        else:
+            np.testing.assert_array_equal(a, b)

@@ -106,6 +106,17 @@ def test_absorbing_goals(seed):
     assert want[-1]["num"][1] < 160
 
 
+def test_sector_view_and_attack_ranges():
+    """SectorRange (angle < 180) views and attacks, 1x1 and 2x2 bodies (Range.h:104-144)"""
+    both(lambda lib: pc.make_sector(lib), 50, 9, order=[1, 0])
+
+
+@pytest.mark.parametrize("seed,order", [(3, [1, 2, 0]), (5, [2, 0, 1])])
+def test_turn_mode_headings_long_bodies(seed, order):
+    """turn_mode: headings, [moves][turn L,R][attacks], rotated views / attacks / moves, pivoting 1x3 and 2x1 bodies"""
+    both(lambda lib: pc.make_turn(lib, 30, seed), 80, seed, order=order, stop_on_done=False)
+
+
 def test_absorbing_goals_that_move_themselves():
     """goals receive actions too: a goal bumping into a goal is absorbed by it, and an absorber that swallowed somebody
     earlier in the move phase skips its own move (GridWorld.cc:581 evaluated at its turn)"""
