@@ -15,5 +15,5 @@ for w in gather64 battle1m; do
   python -c "
 import json; j=json.load(open('gpurun_out/v12_$w.json')); print('WL $w value %.3e ms/step %.3f obs_ms %.3f frac %.3f'%(j['value'], j['ms_per_step'], j['roofline']['mean_launch_ms'], j['roofline']['frac']))" || tail -3 gpurun_out/v12_$w.err
 done
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_v12g.csv python bench.py --steps 3 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_launch_v12g.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:obs_render -s 2 -c 1 -f -o gpurun_out/obs_render_v12g python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_v12g.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_v12h.csv python bench.py --steps 3 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_launch_v12h.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:obs_render -s 2 -c 1 -f -o gpurun_out/obs_render_v12h python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_v12h.log 2>&1

@@ -726,8 +726,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 //     whole warp (lane = feature index) so the stores coalesce.
 template <typename T>
 __global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr) {
-    __shared__ int s_id[8][32], s_act[8][32], s_x[8][32], s_y[8][32];
-    __shared__ float s_rew[8][32];
+    __shared__ int s_id[8][32], s_act[8][32];
+    __shared__ float s_rew[8][32], s_fx[8][32], s_fy[8][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n_warps = gridDim.x * (blockDim.x >> 5);
     for (int base = (blockIdx.x * (blockDim.x >> 5) + w) * 32; base < P.n_total; base += n_warps * 32) {
@@ -737,7 +737,8 @@ __global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr
             const int a = P.A == 1 ? 0 : locate_arena(P.off, P.A, o);
             const long gi = (long)a * P.cap + (o - P.off[a]);
             const int x = P.x[gi], y = P.y[gi];
-            s_x[w][lane] = x; s_y[w][lane] = y; s_id[w][lane] = P.id[gi]; s_act[w][lane] = P.act[gi]; s_rew[w][lane] = P.last_reward[gi];
+            s_id[w][lane] = P.id[gi]; s_act[w][lane] = P.act[gi]; s_rew[w][lane] = P.last_reward[gi];
+            s_fx[w][lane] = (float)x / (float)P.W; s_fy[w][lane] = (float)y / (float)P.H;                  // GridWorld.cc:394-395
             const int self_cell = P.minimap ? (y / P.scale_h) * P.vw + x / P.scale_w : -1;  // GridWorld.cc:372-373
             const int heading = P.turn ? (int)P.dir[gi] : 0;
             hdr[o] = make_int4(x, y, a, (self_cell & 0xffff) | (heading << 16));
@@ -755,8 +756,8 @@ __global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr
                 const int kk = f - P.embedding;
                 if (kk < P.n_action) v = kk == s_act[w][k] ? 1.0f : 0.0f;
                 else if (kk == P.n_action) v = s_rew[w][k];
-                else if (P.minimap && kk == P.n_action + 1) v = (float)s_x[w][k] / (float)P.W;     // GridWorld.cc:394-395
-                else if (P.minimap && kk == P.n_action + 2) v = (float)s_y[w][k] / (float)P.H;
+                else if (P.minimap && kk == P.n_action + 1) v = s_fx[w][k];
+                else if (P.minimap && kk == P.n_action + 2) v = s_fy[w][k];
             }
             rows[t] = ObsOut<T>::cv(v);
             k += dk; f += df;
@@ -770,7 +771,7 @@ __global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr
 #endif
 // NIT = view cells per lane held in registers (NIT * 32 >= in-range cells of the view whenever that is <= 256;
 // larger views take the unpipelined tail loop).
-template <typename T, int NIT>
+template <typename T, int NIT, bool TURN>
 __global__ void __launch_bounds__(32 * ObsOut<T>::TA, OBS_MIN_CTAS * OBS_TA_N / ObsOut<T>::TA)
 obs_render_kernel(const __grid_constant__ ObsParams P) {
     constexpr int OBS_TA = ObsOut<T>::TA;
@@ -780,7 +781,7 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
     // in-range view cells only: lut[k] = {word offset of the cell inside a record, offset of the map cell in the
     // padded planes relative to the observer's own cell}
     int2 *lut = (int2 *)(buf + OBS_TA * P.rec);
-    float *mmbuf = (float *)(lut + (P.turn ? 4 : 1) * ((P.cells + 1) & ~1));     // the minimap row of the tile's first arena (TMA-staged)
+    float *mmbuf = (float *)(lut + (TURN ? 4 : 1) * ((P.cells + 1) & ~1));     // the minimap row of the tile's first arena (TMA-staged)
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ int n_in_s, tile_a0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -796,7 +797,7 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
             if (in) {
                 const int vy = cell / P.vw, vx = cell - vy * P.vw;
                 const int q = k + __popc(bal & ((1u << lane) - 1u));
-                if (!P.turn) lut[q] = make_int2(cell * P.C, (P.oy + vy) * P.kw + P.ox + vx);
+                if (!TURN) lut[q] = make_int2(cell * P.C, (P.oy + vy) * P.kw + P.ox + vx);
                 else {
                     // the window is laid out in the observer's frame: one LUT per heading (Map.cc:140-146, 515-560)
                     for (int d = 0; d < 4; ++d) {
@@ -829,7 +830,7 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
     const int n_tiles = (P.n_total + OBS_TA - 1) / OBS_TA;
     constexpr bool WARP_FILL = sizeof(T) == 4;                // f16 records may share a word with their neighbour
     // this lane's slice of the view LUT never changes: small views keep it in registers, large ones re-read smem
-    constexpr bool LUT_REGS = NIT <= 4;
+    constexpr bool LUT_REGS = NIT <= 4 && !TURN;
     int2 lreg[LUT_REGS ? NIT : 1];
     if (LUT_REGS) {
 #pragma unroll
@@ -837,7 +838,7 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
     }
     // hd = heading of the observer (always 0 without turn_mode)
     auto lutv = [&](int it, int hd) -> int2 {
-        if (P.turn) return it * 32 + lane < n_in ? lut[hd * lut_stride + it * 32 + lane] : make_int2(-1, 0);
+        if (TURN) return it * 32 + lane < n_in ? lut[hd * lut_stride + it * 32 + lane] : make_int2(-1, 0);
         return LUT_REGS ? lreg[LUT_REGS ? it : 0] : (it * 32 + lane < n_in ? lut[it * 32 + lane] : make_int2(-1, 0));
     };
     // position of an observer's own cell in the padded planes (header word h = {x, y, arena, self cell})
@@ -846,7 +847,7 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
     // issue the kind-plane loads of one observer; the pad makes every view cell addressable
     auto load_kinds = [&](const int4 &h, bool on, int (&kd)[NIT]) {
         const unsigned char *kp = P.kind_plane + plane_base(h);
-        const int hd = (h.w >> 16) & 3;
+        const int hd = TURN ? (h.w >> 16) & 3 : 0;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             const int2 l = lutv(it, hd);
@@ -882,12 +883,12 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
         }
         // occupied cells only: the occupant's hp / max_hp (the kinds were loaded one tile ago)
         const float *hpnp = P.hpn_plane + plane_base(hA);
-        const int hd = (hA.w >> 16) & 3;
+        const int hd = TURN ? (hA.w >> 16) & 3 : 0;
         float thp[NIT];
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             thp[it] = 0.0f;
-            if (kind[it] >= 2) thp[it] = __ldg(hpnp + lutv(it, hd).y);
+            if (kind[it] >= KIND_GROUP0 && kind[it] != KIND_FOOD) thp[it] = __ldg(hpnp + lutv(it, hd).y);
         }
         // next tile's kinds, next-next tile's header
         int kind1[NIT];
@@ -917,8 +918,9 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
                     if (lane < head) w[lane] = 0.0f;
                     float4 *w4 = (float4 *)(w + head);
                     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-                    for (int q = lane; q < body; q += 32) w4[q] = z;
+                    int q = lane;
+                    for (; q + 96 < body; q += 128) { w4[q] = z; w4[q + 32] = z; w4[q + 64] = z; w4[q + 96] = z; }
+                    for (; q < body; q += 32) w4[q] = z;
                     const int tail0 = head + (body << 2);
                     if (tail0 + lane < n) w[tail0 + lane] = 0.0f;
                     __syncwarp();
@@ -934,11 +936,18 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
                     const int self = (int)(short)(hA.w & 0xffff);
                     const int step = 32 * P.C;
                     if (a == tile_a0) {                            // the staged row (shared memory)
+                        const int nfull = P.cells >> 5, rest = P.cells & 31;
                         for (int j = 0; j < P.G; ++j) {
-                            const float *row = mmbuf + j * P.cells;
-                            T *d = dst + P.mm_ch[j] + lane * P.C;
-#pragma unroll 2
-                            for (int cell = lane; cell < P.cells; cell += 32, d += step) *d = ObsOut<T>::cv(row[cell]);
+                            const float *rp = mmbuf + j * P.cells + lane;
+                            T *dp = dst + P.mm_ch[j] + lane * P.C;
+                            int it = 0;
+                            for (; it + 4 <= nfull; it += 4, rp += 128, dp += 4 * step) {
+                                const float v0 = rp[0], v1 = rp[32], v2 = rp[64], v3 = rp[96];
+                                dp[0] = ObsOut<T>::cv(v0); dp[step] = ObsOut<T>::cv(v1);
+                                dp[2 * step] = ObsOut<T>::cv(v2); dp[3 * step] = ObsOut<T>::cv(v3);
+                            }
+                            for (; it < nfull; ++it, rp += 32, dp += step) *dp = ObsOut<T>::cv(*rp);
+                            if (lane < rest) *dp = ObsOut<T>::cv(*rp);
                         }
                         __syncwarp();
                         if (lane < P.G) {
@@ -966,7 +975,8 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
                 const int t = kind[it];
                 if (t != 0) {
                     T *px = dst + lutv(it, hd).x;
-                    if (t == 1) px[0] = ObsOut<T>::cv(1.0f);
+                    if (t == KIND_WALL) px[0] = ObsOut<T>::cv(1.0f);
+                    else if (t == KIND_FOOD) px[1] = ObsOut<T>::cv(1.0f);                   // food channel (food_mode)
                     else {
                         const int ch = P.grp_ch[t - 2];
                         px[ch] = ObsOut<T>::cv(1.0f);
@@ -976,10 +986,11 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
             }
             const unsigned char *kindp = P.kind_plane + plane_base(hA);
             for (int k = NIT * 32 + lane; k < n_in; k += 32) {                          // views with > NIT * 32 in-range cells
-                const int2 l = lut[hd * lut_stride + k];
+                const int2 l = lut[(TURN ? hd * lut_stride : 0) + k];
                 const int t = __ldg(kindp + l.y);
                 T *px = dst + l.x;
-                if (t == 1) px[0] = ObsOut<T>::cv(1.0f);
+                if (t == KIND_WALL) px[0] = ObsOut<T>::cv(1.0f);
+                else if (t == KIND_FOOD) px[1] = ObsOut<T>::cv(1.0f);
                 else if (t >= 2) {
                     const int ch = P.grp_ch[t - 2];
                     px[ch] = ObsOut<T>::cv(1.0f);
@@ -1014,7 +1025,7 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
 static int4 *g_obs_hdr = nullptr;
 static size_t g_obs_hdr_n = 0;
 
-template <typename T, int NIT>
+template <typename T, int NIT, bool TURN>
 static void launch_obs_typed(const EngineDev &hE, ObsParams &P, int n_total) {
     constexpr int TA = ObsOut<T>::TA;
     constexpr int THREADS = 32 * TA;
@@ -1037,15 +1048,15 @@ static void launch_obs_typed(const EngineDev &hE, ObsParams &P, int n_total) {
     static size_t configured = (size_t)-1;
     static int ctas_per_sm = 1;
     if (smem != configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(obs_render_kernel<T, NIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, obs_render_kernel<T, NIT>, THREADS, smem));
+        CUDA_CHECK(cudaFuncSetAttribute(obs_render_kernel<T, NIT, TURN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, obs_render_kernel<T, NIT, TURN>, THREADS, smem));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         configured = smem;
     }
     const int grid = tiles < ctas_per_sm * g_sms ? tiles : ctas_per_sm * g_sms;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_profile) { profile_pair(&e0, &e1); CUDA_CHECK(cudaEventRecord(e0, 0)); }
-    obs_render_kernel<T, NIT><<<grid, THREADS, smem>>>(P);
+    obs_render_kernel<T, NIT, TURN><<<grid, THREADS, smem>>>(P);
     post_launch("obs_render_kernel");
     if (g_profile) CUDA_CHECK(cudaEventRecord(e1, 0));
 }
@@ -1077,8 +1088,13 @@ void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const 
         P.grp_ch[j] = ch;
     }
     const bool small_view = G.view_count <= 4 * 32;             // in-range view cells held in registers: 4 or 8 per lane
-    if (O.half) { if (small_view) launch_obs_typed<__half, 4>(hE, P, n_total); else launch_obs_typed<__half, 8>(hE, P, n_total); }
-    else { if (small_view) launch_obs_typed<float, 4>(hE, P, n_total); else launch_obs_typed<float, 8>(hE, P, n_total); }
+    if (hE.turn_mode) {                                         // headings: per-heading LUTs in shared memory (NIT = 8 code path)
+        if (O.half) launch_obs_typed<__half, 8, true>(hE, P, n_total); else launch_obs_typed<float, 8, true>(hE, P, n_total);
+    } else if (O.half) {
+        if (small_view) launch_obs_typed<__half, 4, false>(hE, P, n_total); else launch_obs_typed<__half, 8, false>(hE, P, n_total);
+    } else {
+        if (small_view) launch_obs_typed<float, 4, false>(hE, P, n_total); else launch_obs_typed<float, 8, false>(hE, P, n_total);
+    }
 }
 
 }  // namespace be

@@ -21,7 +21,9 @@ enum { MG_N_COUNTERS = 8 };
 enum Counter { CNT_AGENT_STEPS = 0, CNT_ATTACKS, CNT_HITS, CNT_KILLS, CNT_STARVED,
                CNT_MOVES_OK, CNT_MOVES_BLOCKED, CNT_STEPS };
 
-enum : int { OCC_EMPTY = -1, OCC_WALL = -2 };
+enum : int { OCC_EMPTY = -1, OCC_WALL = -2, OCC_FOOD = -3 };   // OCC_FOOD: food_mode only (amount in EngineDev::food)
+enum : int { TGT_NONE = -1, TGT_FOOD = -3 };                  // EngineDev::tgt of an attacker: none / an agent code (>= 0) / a food cell
+enum : int { KIND_EMPTY = 0, KIND_WALL = 1, KIND_GROUP0 = 2, KIND_FOOD = 255 };   // EngineDev::kind
 enum : int { RANK_NONE = -1, DEATH_NEVER = 0x7fffffff, DEATH_BEFORE = -1 };
 enum : unsigned { MVKEY_NONE = 0xffffffffu };
 
@@ -56,6 +58,7 @@ struct GroupDev {
     // ---- type constants (reference AgentType, src/gridworld/AgentType.h:17-48)
     int body_w, body_l;
     float max_hp, damage, step_recover, kill_supply;
+    float eat_ability, food_supply;           // food_mode (Map.cc:276-303)
     float step_reward, kill_reward, dead_penalty, attack_penalty;
     int attack_in_group;
     int can_absorb;                           // AgentType::can_absorb (Map.cc:341-349)
@@ -115,6 +118,8 @@ struct EngineDev {
     int A, W, H, G;
     int nsep, bandwidth, large_map;           // GridWorld.cc:75-85, :407
     int minimap_mode, embedding_size, n_channel, channel_base;
+    int food_mode;                            // kills leave food on the attacked cell (Map.cc:276-283)
+    float *food;                              // [A][H*W] amount of food on OCC_FOOD cells (food_mode only)
     int turn_mode;                            // agents carry a direction; [moves][turn L, R][attacks] (AgentType.cc:113-117)
     int cap_total, max_body;
     int any_absorb;                           // some group's type has can_absorb

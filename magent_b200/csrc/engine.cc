@@ -134,7 +134,6 @@ void Engine::set_config(const char *key, void *p_value) {     // GridWorld.cc:12
     else if (strequ(key, "map_height")) H_ = ivalue;
     else if (strequ(key, "food_mode")) {
         food_mode_ = bvalue;
-        if (bvalue) fatal("food_mode is not supported by the B200 engine yet (SURVEY.md §8f rank 4)");
     } else if (strequ(key, "turn_mode")) {
         turn_mode_ = bvalue;
     } else if (strequ(key, "minimap_mode")) minimap_mode_ = bvalue;
@@ -407,6 +406,7 @@ void Engine::reset() {                                // GridWorld.cc:72-118, Ma
         ar.id_counter = 0;
         ar.done = 0;
         ar.occ.assign((size_t)W_ * H_, OCC_EMPTY);
+        ar.food.assign(food_mode_ ? (size_t)W_ * H_ : 0, 0.0f);
         for (int i = 0; i < W_; i++) { ar.occ[i] = OCC_WALL; ar.occ[(size_t)(H_ - 1) * W_ + i] = OCC_WALL; }
         for (int i = 0; i < H_; i++) { ar.occ[(size_t)i * W_] = OCC_WALL; ar.occ[(size_t)i * W_ + W_ - 1] = OCC_WALL; }
         ar.groups.resize(G());
@@ -441,7 +441,7 @@ void Engine::host_random_blank(HostArena &ar, int w, int h, int &x, int &y) {   
 int Engine::host_add_wall(HostArena &ar, int x, int y) {                              // Map.cc:108-115
     if (x < 0 || y < 0 || x >= W_ || y >= H_) return 1;
     int &c = ar.occ[(size_t)y * W_ + x];
-    if (c >= 0) return 1;
+    if (c >= 0 || c == OCC_FOOD) return 1;            // a BLANK slot with an occupier is refused (Map.cc:108-112)
     c = OCC_WALL;
     return 0;
 }
@@ -597,6 +597,7 @@ void Engine::to_device() {
             GroupDev &D = hE_.grp[g];
             D.body_w = t.width; D.body_l = t.length;
             D.max_hp = t.hp; D.damage = t.damage; D.step_recover = t.step_recover; D.kill_supply = t.kill_supply;
+            D.eat_ability = t.eat_ability; D.food_supply = t.food_supply;
             D.step_reward = t.step_reward; D.kill_reward = t.kill_reward;
             D.dead_penalty = t.dead_penalty; D.attack_penalty = t.attack_penalty;
             D.attack_in_group = t.attack_in_group;
@@ -634,6 +635,7 @@ void Engine::to_device() {
         hE_.off = (int *)dalloc((size_t)Gn * (A_ + 1) * 4);
         hE_.done = (int *)dalloc((size_t)A_ * 4);
         hE_.occ = (int *)dalloc(cells * 4); hE_.claim_head = (int *)dalloc(cells * 4);
+        hE_.food = food_mode_ ? (float *)dalloc(cells * 4) : nullptr;
         {   // padded observation planes (dev_types.h): the pad covers the widest view window of any group
             int pad = 0;
             for (int g = 0; g < Gn; ++g) {
@@ -666,6 +668,7 @@ void Engine::to_device() {
     // constants that may change between episodes without a re-allocation
     hE_.nsep = nsep_; hE_.large_map = large_map_; hE_.bandwidth = (W_ + nsep_ - 1) / nsep_;
     hE_.minimap_mode = minimap_mode_; hE_.embedding_size = embedding_size_; hE_.turn_mode = turn_mode_ ? 1 : 0;
+    hE_.food_mode = food_mode_ ? 1 : 0;
     hE_.n_channel = n_channel(); hE_.channel_base = group2channel(0);
     {
         uint32_t p = MINSTD_A;
@@ -703,6 +706,11 @@ void Engine::to_device() {
     }
     for (int a = 0; a < A_; ++a)
         be::h2d(hE_.occ + (size_t)a * W_ * H_, arenas_[a].occ.data(), (size_t)W_ * H_ * 4);
+    if (food_mode_)
+        for (int a = 0; a < A_; ++a) {
+            arenas_[a].food.resize((size_t)W_ * H_, 0.0f);
+            be::h2d(hE_.food + (size_t)a * W_ * H_, arenas_[a].food.data(), (size_t)W_ * H_ * 4);
+        }
     {   // the kind plane mirrors the occupancy image; from here on the step kernels keep it current
         std::vector<unsigned char> kp((size_t)hE_.kplane);
         for (int a = 0; a < A_; ++a) {
@@ -712,7 +720,7 @@ void Engine::to_device() {
                 for (int x = 0; x < W_; ++x) {
                     const int o = occ[(size_t)y * W_ + x];
                     kp[(size_t)(y + hE_.kpad) * hE_.kw + x + hE_.kpad] =
-                        o == OCC_WALL ? 1 : o >= 0 ? (unsigned char)(2 + code_group(o)) : 0;
+                        o == OCC_WALL ? KIND_WALL : o == OCC_FOOD ? KIND_FOOD : o >= 0 ? (unsigned char)(KIND_GROUP0 + code_group(o)) : KIND_EMPTY;
                 }
             be::h2d(hE_.kind + (size_t)a * hE_.kplane, kp.data(), kp.size());
         }
@@ -778,6 +786,10 @@ void Engine::to_host(bool keep_device_authoritative) {
     for (int a = 0; a < A_; ++a) {
         arenas_[a].occ.resize((size_t)W_ * H_);
         be::d2h(arenas_[a].occ.data(), hE_.occ + (size_t)a * W_ * H_, (size_t)W_ * H_ * 4);
+        if (food_mode_) {
+            arenas_[a].food.resize((size_t)W_ * H_);
+            be::d2h(arenas_[a].food.data(), hE_.food + (size_t)a * W_ * H_, (size_t)W_ * H_ * 4);
+        }
         arenas_[a].rng = hdr[a].rng;
         arenas_[a].done = hdr[a].done;
     }

@@ -54,6 +54,7 @@ struct HostGroup {                      // one group of one arena, in vector ord
 
 struct HostArena {
     std::vector<int> occ;
+    std::vector<float> food;            // food_mode: amount per OCC_FOOD cell
     std::vector<HostGroup> groups;
     uint32_t rng = 1;
     int id_counter = 0;

@@ -53,6 +53,7 @@ MG_HD void obs_compose_cell(const EngineDev &E, unsigned curmask, int a, int g, 
     int t = (E.occ + (long)a * E.W * E.H)[y * E.W + x];
     if (t == OCC_EMPTY) return;
     if (t == OCC_WALL) { out[0] = 1.0f; return; }
+    if (t == OCC_FOOD) { out[1] = 1.0f; return; }                     // food channel, no hp (Map.cc:191-199)
     int tg = code_group(t);
     int ch = obs_channel(E, g, tg);
     out[ch] = 1.0f;

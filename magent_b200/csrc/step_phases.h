@@ -161,6 +161,91 @@ MG_HD void phase_rng(Ctx &c, const EngineDev &E, int a, int n_attack) {
     }
 }
 
+// cell an attack action aims at (Map::get_attack_obj, Map.cc:209-221); may lie off the board
+MG_HD void attack_cell(const EngineDev &E, const GroupDev &G, const AgentSoA &s, long gi, int &tx, int &ty) {
+    const int k = s.act[gi] - G.attack_base;
+    tx = s.x[gi] + G.att_xoff + G.att_dx[k];
+    ty = s.y[gi] + G.att_yoff + G.att_dy[k];
+    if (E.turn_mode) {
+        const int dir = s.dir[gi];
+        int rx, ry, dx, dy;
+        dir_real(G, dir, rx, ry);
+        dir_rot(dir, G.att_xoff + G.att_dx[k], G.att_yoff + G.att_dy[k], dx, dy);
+        tx = s.x[gi] + rx + dx; ty = s.y[gi] + ry + dy;
+    }
+}
+MG_HD int flat_group(const EngineDev &E, int flat) {
+    int g = 0;
+    while (g + 1 < E.G && flat >= E.grp[g + 1].foff) ++g;
+    return g;
+}
+// target cell of the attacker with local flat id `flat`, as a linear cell index
+MG_HD int attack_cell_of(const EngineDev &E, unsigned curmask, int a, int flat) {
+    const int g = flat_group(E, flat);
+    int tx, ty;
+    attack_cell(E, E.grp[g], cur_soa(E, curmask, g), gidx(E, a, g, flat - E.grp[g].foff), tx, ty);
+    return ty * E.W + tx;
+}
+// an attack on an agent of one's own group is refused unless the type has attack_in_group (Map.cc:236-240)
+MG_HD bool friendly_fire_refused(const EngineDev &E, int att_group, int victim_group) {
+    return att_group == victim_group && !E.grp[att_group].attack_in_group;
+}
+
+// ---- food_mode (Map.cc:245,276-303).  A kill leaves victim.food_supply units of food on the ATTACKED cell; every later
+// attack on that cell -- this step or any later one, by any group -- eats min(eat_ability, food) and the food is gone
+// once less than 0.1 is left.  Eating only depends on which eaters are still alive at their rank, so a cell's food
+// level is a rank-ordered timeline like a victim's hp.
+//   list: chain of attacker flat ids through in_next (a victim's in-list, or the cell list hung off the claim plane)
+//   only eaters with start_rank < rank < upto that aim at `cell` and execute (death > rank) take their bite
+// Returns the food left for an event at rank `upto`; gone = nothing (left) there.
+MG_HD float food_timeline(const EngineDev &E, const ArenaRef &R, unsigned curmask, int cell, int list, float food0,
+                          int start_rank, int upto, bool &gone) {
+    float food = food0;
+    gone = false;
+    int last = start_rank;
+    for (;;) {
+        int best = upto, be = -1;
+        for (int e = list; e != -1; e = E.in_next[R.sb + e]) {
+            const int r = E.att_rank[R.sb + e];
+            if (r > last && r < best) { best = r; be = e; }
+        }
+        if (be == -1) break;
+        last = best;
+        if (ld_volatile(&E.death[R.sb + be]) <= best) continue;             // dead before (or at) its turn: no bite
+        if (attack_cell_of(E, curmask, R.a, be) != cell) continue;
+        const float bite = E.grp[flat_group(E, be)].eat_ability;
+        const float add = bite < food ? bite : food;                        // Map.cc:295-297
+        food -= add;
+        if ((double)food < 0.1) { gone = true; return 0.0f; }               // Map.cc:298-302
+    }
+    return food;
+}
+// food an attacker finds on its target cell when its turn (rank own_r) comes; found = false when the cell is blank or
+// holds a living agent by then.  list_out / food0_out / start_out describe the cell's timeline for the commit phase.
+MG_HD float food_found(const EngineDev &E, const ArenaRef &R, unsigned curmask, int my_tgt, int my_cell, int own_r, bool &found) {
+    found = false;
+    if (my_tgt == TGT_FOOD) {
+        bool gone;
+        const float f = food_timeline(E, R, curmask, my_cell, R.claim[my_cell], E.food[(long)R.a * E.W * E.H + my_cell], -1, own_r, gone);
+        found = !gone;
+        return f;
+    }
+    // the target agent died earlier this step: food lies here iff the killing blow landed on this very cell
+    const int vflat = lflat(E, my_tgt);
+    const int dv = ld_volatile(&E.death[R.sb + vflat]);
+    if (dv >= own_r || dv < 0) return 0.0f;
+    const int vg = code_group(my_tgt);
+    for (int k = E.in_head[R.sb + vflat]; k != -1; k = E.in_next[R.sb + k]) {
+        if (E.att_rank[R.sb + k] != dv) continue;
+        if (attack_cell_of(E, curmask, R.a, k) != my_cell) return 0.0f;
+        bool gone;
+        const float f = food_timeline(E, R, curmask, my_cell, E.in_head[R.sb + vflat], E.grp[vg].food_supply, dv, own_r, gone);
+        found = !gone;
+        return f;
+    }
+    return 0.0f;
+}
+
 // phase 3: final buffer position (= execution rank) of each attack, and its target
 template <class Ctx>
 MG_HD void phase_rank_target(Ctx &c, const EngineDev &E, const StepArgs &S, int a, int n_attack) {
@@ -186,20 +271,19 @@ MG_HD void phase_rank_target(Ctx &c, const EngineDev &E, const StepArgs &S, int 
         E.att_rank[R.sb + fs] = pos;
         if (s.flags[gi] & FLAG_DEAD) continue;          // skipped at execution (GridWorld.cc:479)
         // Map::get_attack_obj (Map.cc:209-252)
-        int k = s.act[gi] - G.attack_base;
-        int tx = s.x[gi] + G.att_xoff + G.att_dx[k];
-        int ty = s.y[gi] + G.att_yoff + G.att_dy[k];
-        if (E.turn_mode) {
-            const int dir = s.dir[gi];
-            int rx, ry, dx, dy;
-            dir_real(G, dir, rx, ry);
-            dir_rot(dir, G.att_xoff + G.att_dx[k], G.att_yoff + G.att_dy[k], dx, dy);
-            tx = s.x[gi] + rx + dx; ty = s.y[gi] + ry + dy;
-        }
+        int tx, ty;
+        attack_cell(E, G, s, gi, tx, ty);
         if (tx < 0 || tx >= E.W || ty < 0 || ty >= E.H) continue;
         int t = R.occ[ty * E.W + tx];
+        if (E.food_mode && t == OCC_FOOD) {             // eaters of one cell queue on the (idle) claim plane
+            E.tgt[R.sb + fs] = TGT_FOOD;
+            E.in_next[R.sb + fs] = atomic_exch(&R.claim[ty * E.W + tx], fs);
+            continue;
+        }
         if (t < 0) continue;
-        if (!G.attack_in_group && code_group(t) == g) continue;
+        // a refused in-group attack is a blank -- unless the cell holds food by the time its turn comes (food_mode),
+        // so it still joins the occupant's list, as a non-damaging member
+        if (friendly_fire_refused(E, g, code_group(t)) && !E.food_mode) continue;
         E.tgt[R.sb + fs] = t;
         E.in_next[R.sb + fs] = atomic_exch(&E.in_head[R.sb + lflat(E, t)], fs);
     }
@@ -218,11 +302,11 @@ MG_HD bool phase_attack_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int
         long f = R.sb + ft;
         int head = E.in_head[f];
         int my_tgt = E.tgt[f];
-        if (head == -1 && my_tgt < 0) continue;
+        if (head == -1 && my_tgt == TGT_NONE) continue;
         const GroupDev &G = E.grp[g];
         float hp = cur_soa(E, S.curmask, g).hp[gidx(E, a, g, i)];
-        int own_r = my_tgt >= 0 ? E.att_rank[f] : DEATH_NEVER;
-        bool own_done = my_tgt < 0;
+        int own_r = my_tgt != TGT_NONE ? E.att_rank[f] : DEATH_NEVER;
+        bool own_done = my_tgt == TGT_NONE;
         int last = -1, dn = DEATH_NEVER;
         for (;;) {
             int best = DEATH_NEVER, bs = -1;
@@ -232,10 +316,18 @@ MG_HD bool phase_attack_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int
             }
             if (!own_done && own_r < best) {            // my own attack comes first: kill => supply
                 own_done = true;
-                if (ld_volatile(&E.death[R.sb + lflat(E, my_tgt)]) == own_r) {
+                if (my_tgt >= 0 && ld_volatile(&E.death[R.sb + lflat(E, my_tgt)]) == own_r) {
                     float sup = E.grp[code_group(my_tgt)].kill_supply;
                     float nh = hp + sup;                 // Agent::add_hp: min(type.hp, hp + add)
                     hp = G.max_hp < nh ? G.max_hp : nh;
+                } else if (E.food_mode) {                // food on my target cell by now?  eat (Map.cc:292-297)
+                    bool found;
+                    const float food = food_found(E, R, S.curmask, my_tgt, attack_cell_of(E, S.curmask, a, ft), own_r, found);
+                    if (found) {
+                        const float add = G.eat_ability < food ? G.eat_ability : food;
+                        const float nh = hp + add;
+                        hp = G.max_hp < nh ? G.max_hp : nh;
+                    }
                 }
                 continue;
             }
@@ -243,8 +335,8 @@ MG_HD bool phase_attack_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int
             last = best;
             if (ld_volatile(&E.death[R.sb + bs]) < best) continue;      // attacker dead by then
             // attacker's group -> damage
-            int sg = 0;
-            while (sg + 1 < E.G && bs >= E.grp[sg + 1].foff) ++sg;
+            const int sg = flat_group(E, bs);
+            if (E.food_mode && friendly_fire_refused(E, sg, g)) continue;   // listed only as a potential eater
             hp -= E.grp[sg].damage;
             if (hp < 0.0f) { dn = best; break; }
         }
@@ -276,7 +368,8 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
         if (r != RANK_NONE && d > r) {                   // my attack is executed
             int t = E.tgt[f];
             int dt = t >= 0 ? E.death[R.sb + lflat(E, t)] : DEATH_BEFORE;
-            if (t < 0 || dt < r) {                       // blank / already dead: penalty only
+            if (t >= 0 && E.food_mode && friendly_fire_refused(E, g, code_group(t))) dt = DEATH_BEFORE;
+            if (t < 0 || dt < r) {                       // blank / already dead / food (eating earns nothing): penalty only
                 s.next_reward[gi] += G.attack_penalty;
             } else if (dt == r) {                        // my hit kills
                 s.last_op[gi] = OP_KILL;
@@ -290,7 +383,7 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
                 ++hits;
             }
         }
-        bool evaluated = E.in_head[f] != -1 || E.tgt[f] >= 0;
+        bool evaluated = E.in_head[f] != -1 || E.tgt[f] != TGT_NONE;
         float hp = evaluated ? E.hp_fin[f] : s.hp[gi];
         bool dies = false;
         if (d != DEATH_NEVER) {                          // killed in the attack phase
@@ -321,6 +414,42 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
     c.add_count(E, CNT_KILLS, kills);
     c.add_count(E, CNT_HITS, hits);
     c.add_count(E, CNT_STARVED, starved);
+}
+
+// phase 5b/5c (food_mode only): what is left on every cell whose food was created or bitten this step.  Every
+// participant of a cell's timeline computes the same final amount (5b, into hp_fin) and writes it (5c): the
+// writes agree, so no owner has to be elected.  5c runs after the victims' bodies were cleared in phase 5.
+template <class Ctx>
+MG_HD void phase_food_commit(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &all, bool write) {
+    ArenaRef R = arena_ref(E, a);
+    float *foodp = E.food + (long)a * E.W * E.H;
+    for (int idx = c.tid(); idx < all.cnt; idx += c.nth()) {
+        int g, i; enum_locate(all, idx, g, i);
+        const int ft = E.grp[g].foff + i;
+        const long f = R.sb + ft;
+        const int t = E.tgt[f], r = E.att_rank[f];
+        if (t == TGT_FOOD && write) R.claim[attack_cell_of(E, S.curmask, a, ft)] = -1;    // unhook the eaters' queue, executed or not
+        if (t == TGT_NONE || r == RANK_NONE || E.death[f] <= r) continue;          // my attack was not executed
+        int list, start;
+        float food0;
+        if (t == TGT_FOOD) { start = -1; }
+        else if (!friendly_fire_refused(E, g, code_group(t)) && E.death[R.sb + lflat(E, t)] == r) { start = r; }   // my kill
+        else continue;
+        const int cell = attack_cell_of(E, S.curmask, a, ft);
+        if (!write) {
+            if (t == TGT_FOOD) { list = R.claim[cell]; food0 = foodp[cell]; }
+            else { list = E.in_head[R.sb + lflat(E, t)]; food0 = E.grp[code_group(t)].food_supply; }
+            bool gone;
+            const float left = food_timeline(E, R, S.curmask, cell, list, food0, start, DEATH_NEVER, gone);
+            E.hp_fin[f] = gone ? -1.0f : left;
+        } else {
+            const float left = E.hp_fin[f];
+            const bool gone = left < 0.0f;
+            foodp[cell] = gone ? 0.0f : left;
+            R.occ[cell] = gone ? OCC_EMPTY : OCC_FOOD;
+            kind_set(E, a, cell % E.W, cell / E.W, gone ? (unsigned char)KIND_EMPTY : (unsigned char)KIND_FOOD);
+        }
+    }
 }
 
 // footprint a mover wants to occupy: its current footprint for a move, the rotated one for a turn
@@ -380,7 +509,7 @@ MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, in
         bool wall = false;
         for (int bx = 0; bx < bw; ++bx)
             for (int by = 0; by < bh; ++by)
-                if (R.occ[(ny + by) * E.W + nx + bx] == OCC_WALL) wall = true;
+                if (R.occ[(ny + by) * E.W + nx + bx] <= OCC_WALL) wall = true;       // walls and food (is_blank_area, Map.cc:461-465)
         // with absorbing types around, a wall-blocked mover may still bump into an absorber: keep it in the relaxation
         if (wall && (turn || !E.any_absorb)) { E.mv_state[f] = MV_STATIC_FAIL; continue; }
         E.mv_state[f] = MV_PENDING_FAIL;
@@ -471,7 +600,7 @@ MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a
             for (int bx = 0; bx < bw; ++bx)
                 for (int by = 0; by < bh; ++by) {
                     const int cell = (ny + by) * E.W + nx + bx;
-                    if (R.occ[cell] == OCC_WALL) { ok = false; continue; }
+                    if (R.occ[cell] <= OCC_WALL) { ok = false; continue; }
                     const int o = occupant_at_turn(E, R, S.curmask, nx + bx, ny + by, key, fs, false);
                     if (o != -1) { ok = false; if (hit == -1) { hit = o; hit_cell = cell; } }
                 }
@@ -766,6 +895,12 @@ MG_HD void run_step(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
     }
     phase_attack_apply_starve(c, E, S, a, all);
     c.sync();
+    if (E.food_mode && n_attack > 0) {
+        phase_food_commit(c, E, S, a, all, false);
+        c.sync();
+        phase_food_commit(c, E, S, a, all, true);
+        c.sync();
+    }
     if (E.turn_mode) {                                   // GridWorld.cc:544-571: all turns, then all moves
         phase_move_register(c, E, S, a, ord, true);
         relax_until_stable(c, flags, [&]() { return phase_move_relax(c, E, S, a, ord, true); });

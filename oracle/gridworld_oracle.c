@@ -11,8 +11,7 @@
  *
  * It restates the SEQUENTIAL semantics (the reference is only deterministic with OMP_NUM_THREADS=1,
  * SURVEY.md §0): each function cites the reference lines it follows.  Not restated (no shipped config on
- * the hot path uses them; the functions abort with a message): food_mode, OP_ALIGN, render,
- * DiscreteSnake.
+ * the hot path uses them; the functions abort with a message): OP_ALIGN, render, DiscreteSnake.
  */
 #include <math.h>
 #include <stdbool.h>
@@ -26,7 +25,7 @@
 #define MAXT 16
 
 enum { OP_AND, OP_OR, OP_NOT, OP_KILL, OP_AT, OP_IN, OP_COLLIDE, OP_ATTACK, OP_DIE, OP_IN_A_LINE, OP_ALIGN, OP_NULL };
-enum { CELL_EMPTY = -1, CELL_WALL = -2 };
+enum { CELL_EMPTY = -1, CELL_WALL = -2, CELL_FOOD = -3 };     /* food: what a killed agent leaves behind in food_mode (Map.cc:276-283) */
 
 static void die(const char *msg, const char *arg) {
     fprintf(stderr, "[gridworld_oracle FATAL] %s%s\n", msg, arg ? arg : "");
@@ -95,7 +94,7 @@ typedef struct {
     char name[64];
     int width, length;
     float speed, hp, view_radius, view_angle, attack_radius, attack_angle;
-    float damage, step_recover, kill_supply;
+    float damage, step_recover, kill_supply, eat_ability, food_supply;
     int attack_in_group, can_absorb;
     float step_reward, kill_reward, dead_penalty, attack_penalty;
     Range view, attack, move;
@@ -119,12 +118,13 @@ typedef struct { int op, nraw, raw[8]; int related[16], nrel; int isub[16], iobj
 typedef struct { int on, nrecv, recv[8]; float val[8]; bool terminal, trigger; int nin, in[16], inf[16]; } Rule;
 
 typedef struct {
-    int w, h, minimap_mode, goal_mode, turn_mode, embedding, reset_done, rules_ready;
+    int w, h, minimap_mode, goal_mode, turn_mode, food_mode, embedding, reset_done, rules_ready;
     uint32_t rng;                                                   /* minstd_rand0 state */
     int ntype; Type type[MAXT];
     int ngroup; Group grp[MAXG];
     Agent *pool; int npool, cappool;
     int *cell;
+    float *food;                                                    /* amount per CELL_FOOD cell */
     int id_counter, nsep, large;
     ActBuf attack, move[17], turn[17];
     Symbol sym[32]; int nsym;
@@ -140,7 +140,7 @@ static void push(ActBuf *b, int agent, int action) {
     if (b->n == b->cap) { b->cap = b->cap ? 2 * b->cap : 256; b->v = realloc(b->v, sizeof(Act) * b->cap); }
     b->v[b->n].agent = agent; b->v[b->n].action = action; b->n++;
 }
-static int g2c(const Env *e, int g) { return 1 + g * (2 + (e->minimap_mode ? 1 : 0)); }      /* GridWorld.cc:915-924 */
+static int g2c(const Env *e, int g) { return 1 + (e->food_mode ? 1 : 0) + g * (2 + (e->minimap_mode ? 1 : 0)); }      /* GridWorld.cc:915-924 */
 static int feature_size(const Env *e, int g) {                                                /* :926-934 */
     return e->embedding + e->type[e->grp[g].type].n_action + 1 + (e->goal_mode ? 2 : 0) + (e->minimap_mode ? 2 : 0);
 }
@@ -151,7 +151,7 @@ static bool blank_area(const Env *e, int x, int y, int w, int h, int self) {
     for (int i = 0; i < w; i++)
         for (int j = 0; j < h; j++) {
             int c = e->cell[(y + j) * e->w + x + i];
-            if (c == CELL_WALL || (c >= 0 && c != self)) return false;
+            if (c == CELL_WALL || c == CELL_FOOD || (c >= 0 && c != self)) return false;   /* food is an occupier too */
         }
     return true;
 }
@@ -191,7 +191,7 @@ API int env_config_game(void *game, const char *key, void *p) {    /* GridWorld.
     else if (!strcmp(key, "seed")) {
         uint32_t s = (uint32_t)(((unsigned long long)(long long)iv) % 2147483647ull);
         e->rng = s ? s : 1;
-    } else if (!strcmp(key, "food_mode")) { if (bv) die("not restated: ", key); }
+    } else if (!strcmp(key, "food_mode")) e->food_mode = bv;
     else die("invalid argument in set_config : ", key);
     return 0;
 }
@@ -215,6 +215,8 @@ API int gridworld_register_agent_type(void *game, const char *name, int n, const
         else if (!strcmp(k, "damage")) t->damage = v;
         else if (!strcmp(k, "step_recover")) t->step_recover = v;
         else if (!strcmp(k, "kill_supply")) t->kill_supply = v;
+        else if (!strcmp(k, "eat_ability")) t->eat_ability = v;
+        else if (!strcmp(k, "food_supply")) t->food_supply = v;
         else if (!strcmp(k, "attack_in_group")) t->attack_in_group = (int)(v + 0.5) != 0;
         else if (!strcmp(k, "step_reward")) t->step_reward = v;
         else if (!strcmp(k, "kill_reward")) t->kill_reward = v;
@@ -222,7 +224,7 @@ API int gridworld_register_agent_type(void *game, const char *name, int n, const
         else if (!strcmp(k, "attack_penalty")) t->attack_penalty = v;
         else if (!strcmp(k, "can_absorb")) t->can_absorb = (int)(v + 0.5) != 0;
         else if (!strcmp(k, "hear_radius") || !strcmp(k, "speak_radius") || !strcmp(k, "speak_ability") ||
-                 !strcmp(k, "trace") || !strcmp(k, "eat_ability") || !strcmp(k, "food_supply") ||
+                 !strcmp(k, "trace") ||
                  !strcmp(k, "view_x_offset") || !strcmp(k, "view_y_offset") || !strcmp(k, "att_x_offset") ||
                  !strcmp(k, "att_y_offset") || !strcmp(k, "turn_x_offset") || !strcmp(k, "turn_y_offset")) {}
         else die("invalid agent config : ", k);
@@ -324,6 +326,8 @@ API int env_reset(void *game) {                                     /* GridWorld
     free(e->cell);
     e->cell = malloc(sizeof(int) * e->w * e->h);
     for (int i = 0; i < e->w * e->h; i++) e->cell[i] = CELL_EMPTY;
+    free(e->food);
+    e->food = calloc((size_t)e->w * e->h, sizeof(float));
     for (int i = 0; i < e->w; i++) { e->cell[i] = CELL_WALL; e->cell[(e->h - 1) * e->w + i] = CELL_WALL; }
     for (int i = 0; i < e->h; i++) { e->cell[i * e->w] = CELL_WALL; e->cell[i * e->w + e->w - 1] = CELL_WALL; }
     e->npool = 0;
@@ -345,7 +349,7 @@ static void random_blank(Env *e, int w, int h, int *px, int *py) {  /* Map.cc:49
 }
 static void add_wall(Env *e, int x, int y) {                         /* Map.cc:108-115 */
     if (x < 0 || y < 0 || x >= e->w || y >= e->h) return;
-    if (e->cell[y * e->w + x] >= 0) return;
+    if (e->cell[y * e->w + x] >= 0 || e->cell[y * e->w + x] == CELL_FOOD) return;   /* BLANK slot with an occupier: refused */
     e->cell[y * e->w + x] = CELL_WALL;
 }
 /* ---- headings (turn_mode): Map.cc:515-607 ---- */
@@ -471,6 +475,7 @@ API int env_get_observation(void *game, int g, float **bufs) {      /* GridWorld
                 if (c == CELL_EMPTY || !t->view.in[vy * vw + vx]) continue;
                 float *px = out + (size_t)(vy * vw + vx) * C;
                 if (c == CELL_WALL) { px[0] = 1; continue; }
+                if (c == CELL_FOOD) { px[1] = 1; continue; }        /* food channel, no hp (Map.cc:191-199) */
                 const Agent *b = &e->pool[c];
                 int ch = chan(e, g, b->group);
                 px[ch] = 1;
@@ -621,6 +626,15 @@ API int env_step(void *game, int *done) {                           /* GridWorld
         save_to_real(t, a, &rx, &ry);
         rela_to_abs(rx, ry, a->dir, t->width / 2 + t->attack.dx[k], t->length / 2 + t->attack.dy[k], &tx, &ty);
         int c = (tx >= 0 && tx < e->w && ty >= 0 && ty < e->h) ? e->cell[ty * e->w + tx] : CELL_EMPTY;
+        if (c == CELL_FOOD) {                                        /* Map.cc:292-303: eat; any group may (get_attack_obj :245) */
+            float *food = &e->food[ty * e->w + tx];
+            float add = t->eat_ability < *food ? t->eat_ability : *food;
+            float nh = a->hp + add; a->hp = nh < t->hp ? nh : t->hp;
+            *food -= add;
+            if (*food < 0.1) { e->cell[ty * e->w + tx] = CELL_EMPTY; *food = 0; }
+            a->next_reward += 0.0f + t->attack_penalty;
+            continue;
+        }
         if (c < 0 || (!t->attack_in_group && e->pool[c].group == a->group)) { a->next_reward += t->attack_penalty; continue; }
         Agent *v = &e->pool[c];
         const Type *tv = &e->type[e->grp[v->group].type];
@@ -630,6 +644,7 @@ API int env_step(void *game, int *done) {                           /* GridWorld
             kill_agent(e, v);
             a->last_op = OP_KILL; a->op_obj = c;
             float nh = a->hp + tv->kill_supply; a->hp = nh < t->hp ? nh : t->hp;     /* std::min(type.hp, hp+add) */
+            if (e->food_mode) { e->cell[ty * e->w + tx] = CELL_FOOD; e->food[ty * e->w + tx] = tv->food_supply; }   /* the attacked cell only */
             reward = tv->kill_reward;
         } else { a->last_op = OP_ATTACK; a->op_obj = c; }
         a->next_reward += reward + t->attack_penalty;

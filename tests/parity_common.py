@@ -302,6 +302,47 @@ def make_turn(lib, map_size=36, seed=8, **kw):
     return env
 
 
+def food_config(size):
+    """food_mode (deprecated in the reference, no shipped config): a killed agent leaves food_supply units of food on
+    the ATTACKED cell; food blocks movement and placement, shows up in its own channel, and is eaten by whoever
+    attacks that cell (eat_ability per bite, any group, gone below 0.1) -- Map.cc:245,276-303"""
+    import magent_b200 as magent
+    gw = magent.gridworld
+    cfg = gw.Config()
+    cfg.set({"map_width": size, "map_height": size, "food_mode": True, "minimap_mode": True, "embedding_size": 6})
+    wolf = cfg.register_agent_type("wolf", dict(
+        width=2, length=2, hp=6, speed=1, damage=3, step_recover=-0.15, kill_supply=0.5, eat_ability=1.5, food_supply=2.0,
+        view_range=gw.CircleRange(5), attack_range=gw.CircleRange(2),
+        step_reward=-0.01, kill_reward=2, dead_penalty=-1, attack_penalty=-0.03))
+    deer = cfg.register_agent_type("deer", dict(
+        width=1, length=1, hp=2.5, speed=2, damage=1, step_recover=0.05, eat_ability=0.4, food_supply=3.3,
+        view_range=gw.CircleRange(4), attack_range=gw.CircleRange(1.5),
+        step_reward=0.01, kill_reward=1, dead_penalty=-0.5, attack_penalty=-0.01))
+    crow = cfg.register_agent_type("crow", dict(
+        width=1, length=1, hp=1.5, speed=3, damage=0.6, step_recover=-0.02, eat_ability=0.75, food_supply=0.25, attack_in_group=1,
+        view_range=gw.CircleRange(3), attack_range=gw.CircleRange(1),
+        kill_reward=0.5, dead_penalty=-0.1, attack_penalty=-0.02))
+    g0, g1, g2 = cfg.add_group(wolf), cfg.add_group(deer), cfg.add_group(crow)
+    a, b, c = (gw.AgentSymbol(g, index='any') for g in (g0, g1, g2))
+    cfg.add_reward_rule(gw.Event(a, 'kill', b), receiver=a, value=1)
+    cfg.add_reward_rule(gw.Event(b, 'attack', a), receiver=[b, a], value=[0.2, -0.2])
+    cfg.add_reward_rule(gw.Event(c, 'attack', b), receiver=c, value=0.1)
+    return cfg
+
+
+def make_food(lib, map_size=30, seed=6, **kw):
+    import magent_b200 as magent
+    env = magent.GridWorld(food_config(map_size), _lib=lib, **kw)
+    env.set_seed(seed)
+    env.reset()
+    h = env.get_handles()
+    env.add_walls(method="random", n=20)
+    env.add_agents(h[0], method="random", n=30)
+    env.add_agents(h[1], method="random", n=220)
+    env.add_agents(h[2], method="random", n=120)
+    return env
+
+
 def make_battle_rect(lib, width=56, height=34, n=120, seed=2, **kw):
     """non-square map: map_width != map_height (minimap scales, feature x/W y/H, bounds all differ per axis)"""
     import magent_b200 as magent

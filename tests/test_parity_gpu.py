@@ -117,6 +117,12 @@ def test_turn_mode_headings_long_bodies(seed, order):
     both(lambda lib: pc.make_turn(lib, 30, seed), 80, seed, order=order, stop_on_done=False)
 
 
+@pytest.mark.parametrize("seed,order", [(3, [1, 2, 0]), (5, [2, 0, 1]), (9, [0, 1, 2])])
+def test_food_mode_kills_leave_food_that_is_eaten(seed, order):
+    """food_mode: food on the attacked cell of a kill, eaten by later attackers (any group), blocks moves, own channel"""
+    both(lambda lib: pc.make_food(lib, 30, seed), 80, seed, order=order, stop_on_done=False)
+
+
 def test_absorbing_goals_that_move_themselves():
     """goals receive actions too: a goal bumping into a goal is absorbed by it, and an absorber that swallowed somebody
     earlier in the move phase skips its own move (GridWorld.cc:581 evaluated at its turn)"""
