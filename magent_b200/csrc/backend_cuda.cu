@@ -703,6 +703,7 @@ struct ObsParams {
     const float *hpn_plane;          // [A][kplane] padded: hp / max_hp of the occupant (EngineDev::hpn)
     int kpad, kw;
     long kplane;
+    int chunk;                       // consecutive tiles per CTA visit (<= OBS_CHUNK)
     int turn, body_w, body_l;        // turn_mode: 4 view LUTs (one per heading), the heading rides in the header
     const unsigned char *dir;
     const int *x, *y, *id, *act;
@@ -769,8 +770,18 @@ __global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr
 #ifndef OBS_MIN_CTAS
 #define OBS_MIN_CTAS 8
 #endif
+#ifndef OBS_CHUNK
+#define OBS_CHUNK 4                  // consecutive tiles a CTA renders before it jumps ahead by grid * OBS_CHUNK tiles
+#endif
 // NIT = view cells per lane held in registers (NIT * 32 >= in-range cells of the view whenever that is <= 256;
 // larger views take the unpipelined tail loop).
+//
+// The tile buffer is PERSISTENT: consecutive tiles of a CTA belong to the same arena (blocked tile assignment), so
+// the zeros and the arena's minimap channels already in the buffer are still right for the next tile.  After the
+// bulk store has read the buffer, each warp only UNDOES the few cells it marked for the previous observer (kinds
+// remembered in one packed register) and restores the self-marker cell, then marks the new observer's cells.  A
+// warp rebuilds its record (zero fill + minimap rows from L2) only when its observer's arena changes -- once or
+// twice per launch.
 template <typename T, int NIT, bool TURN>
 __global__ void __launch_bounds__(32 * ObsOut<T>::TA, OBS_MIN_CTAS * OBS_TA_N / ObsOut<T>::TA)
 obs_render_kernel(const __grid_constant__ ObsParams P) {
@@ -781,11 +792,8 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
     // in-range view cells only: lut[k] = {word offset of the cell inside a record, offset of the map cell in the
     // padded planes relative to the observer's own cell}
     int2 *lut = (int2 *)(buf + OBS_TA * P.rec);
-    float *mmbuf = (float *)(lut + (TURN ? 4 : 1) * ((P.cells + 1) & ~1));     // the minimap row of the tile's first arena (TMA-staged)
-    __shared__ __align__(8) unsigned long long mbar;
-    __shared__ int n_in_s, tile_a0;
+    __shared__ int n_in_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned mm_bytes = (unsigned)P.mm_stride * 4u;
 
     const int lut_stride = (P.cells + 1) & ~1;
     if (warp == 0) {                                          // compact the view mask (Range.h:104-189)
@@ -801,12 +809,10 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
                 else {
                     // the window is laid out in the observer's frame: one LUT per heading (Map.cc:140-146, 515-560)
                     for (int d = 0; d < 4; ++d) {
-                        const bool upright = d == DIR_NORTH || d == DIR_SOUTH;
                         int rx = 0, ry = 0, dx, dy;                     // save_to_real
                         if (d == DIR_SOUTH) { rx = P.body_w - 1; ry = P.body_l - 1; }
                         else if (d == DIR_WEST) ry = P.body_w - 1;
                         else if (d == DIR_EAST) rx = P.body_l - 1;
-                        (void)upright;
                         const int ex = P.ox + vx, ey = P.oy + vy;       // rela_to_abs
                         if (d == DIR_NORTH) { dx = ex; dy = ey; }
                         else if (d == DIR_SOUTH) { dx = -ex; dy = -ey; }
@@ -818,17 +824,11 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
             }
             k += __popc(bal);
         }
-        if (lane == 0) {
-            n_in_s = k;
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
+        if (lane == 0) n_in_s = k;
     }
     __syncthreads();
-    unsigned phase = 0;
     const int n_in = n_in_s;
     const int n_tiles = (P.n_total + OBS_TA - 1) / OBS_TA;
-    constexpr bool WARP_FILL = sizeof(T) == 4;                // f16 records may share a word with their neighbour
     // this lane's slice of the view LUT never changes: small views keep it in registers, large ones re-read smem
     constexpr bool LUT_REGS = NIT <= 4 && !TURN;
     int2 lreg[LUT_REGS ? NIT : 1];
@@ -841,7 +841,7 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
         if (TURN) return it * 32 + lane < n_in ? lut[hd * lut_stride + it * 32 + lane] : make_int2(-1, 0);
         return LUT_REGS ? lreg[LUT_REGS ? it : 0] : (it * 32 + lane < n_in ? lut[it * 32 + lane] : make_int2(-1, 0));
     };
-    // position of an observer's own cell in the padded planes (header word h = {x, y, arena, self cell})
+    // position of an observer's own cell in the padded planes (header word h = {x, y, arena, self cell | heading << 16})
     auto plane_base = [&](const int4 &h) -> long { return h.z * P.kplane + (long)(h.y + P.kpad) * P.kw + h.x + P.kpad; };
 
     // issue the kind-plane loads of one observer; the pad makes every view cell addressable
@@ -854,33 +854,51 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
             kd[it] = (on && l.x >= 0 && !(OBS_ABLATE & 1)) ? __ldg(kp + l.y) : 0;
         }
     };
+    // write (on = true) or erase what an occupied view cell shows: wall / food flag, or a group's {1, hp / max_hp}
+    auto mark = [&](T *px, int t, float hp, bool on) {
+        const T one = ObsOut<T>::cv(on ? 1.0f : 0.0f);
+        if (t == KIND_WALL) px[0] = one;
+        else if (t == KIND_FOOD) px[1] = one;                              // food channel (food_mode)
+        else {
+            const int ch = P.grp_ch[t - KIND_GROUP0];
+            px[ch] = one;
+            px[ch + 1] = ObsOut<T>::cv(on ? hp : 0.0f);                    // hp / max_hp (Map.cc:197)
+        }
+    };
 
-    // software pipeline over this CTA's tiles i, i + grid, ...: while tile i is composed, the kind loads of tile
-    // i+1 and the header loads of tile i+2 are in flight
+    // tile assignment: chunks of OBS_CHUNK consecutive tiles, dealt round-robin over the CTAs.  Inside a chunk the
+    // arena (almost) never changes, so the persistent tile needs no rebuild; across the grid all CTAs write inside one
+    // window of grid * OBS_CHUNK tiles (~90 MB), which keeps the output stream inside the TLB reach (blocked
+    // assignment -- one 4 MB region per CTA -- measured 20 % slower) and the planes of ~20 arenas L2-hot.
+    // Software pipeline: while tile i is composed, the kind loads of tile i+1 and the header load of tile i+2 fly.
+    const int chunk = P.chunk;                 // 1 when there are too few tiles to keep every CTA busy with longer chunks
+    auto next_tile = [&](int t) -> int { return ((t + 1) % chunk) ? t + 1 : t + 1 + ((int)gridDim.x - 1) * chunk; };
+    int tile = blockIdx.x * chunk;
+    const int tile_end = n_tiles;
     const int4 zero4 = make_int4(0, 0, 0, 0);
-    int tile = blockIdx.x;
-    int4 hA = zero4;                      // tile i   : {x, y, arena, self cell}
-    int4 hA1 = zero4;                     // tile i+1
+    int4 hA = zero4, hA1 = zero4;             // headers of tile i and i+1
     int kind[NIT];
+    // what this warp's record currently shows: the arena whose minimap rows it holds (-1: garbage), the previous
+    // observer's heading, marked kinds (packed bytes; > 4 * 32 cells per lane never happens with NIT <= 8) and
+    // self-marker cell with its unmarked minimap value per group lane
+    int rec_arena = -1, prev_hd = 0, prev_self = -1;
+    unsigned prev_kinds[(NIT + 3) / 4];
+#pragma unroll
+    for (int q = 0; q < (NIT + 3) / 4; ++q) prev_kinds[q] = 0u;
+    float self_orig = 0.0f;
+    bool prev_tail = false;                    // the previous observer had cells beyond NIT * 32 marked (large views)
     {
-        const int o0 = tile * OBS_TA + warp, o1 = (tile + (int)gridDim.x) * OBS_TA + warp;
-        if (tile < n_tiles && o0 < P.n_total) hA = P.hdr[o0];
+        const int o0 = tile * OBS_TA + warp, o1 = next_tile(tile) * OBS_TA + warp;
+        const bool on0 = tile < tile_end && o0 < P.n_total;
+        if (on0) hA = P.hdr[o0];
         if (o1 < P.n_total) hA1 = P.hdr[o1];
-        load_kinds(hA, tile < n_tiles && o0 < P.n_total, kind);
+        load_kinds(hA, on0, kind);
     }
-    for (; tile < n_tiles; tile += gridDim.x) {
+    for (; tile < tile_end; tile = next_tile(tile)) {
         const int t0 = tile * OBS_TA;
         const int cnt = min(OBS_TA, P.n_total - t0);
         const bool active = warp < cnt;
         const int a = hA.z;
-        if (P.minimap && threadIdx.x == 0 && !(OBS_ABLATE & 2)) {
-            // stage the minimap row of the tile's first arena (thread 0 belongs to the first agent's warp).  mmbuf is
-            // free: every warp finished reading it before the __syncthreads that preceded the previous store.
-            tile_a0 = a;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(mm_bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(smem_u32(mmbuf)), "l"(P.mm + (size_t)a * P.mm_stride), "r"(mm_bytes), "r"(smem_u32(&mbar)) : "memory");
-        }
         // occupied cells only: the occupant's hp / max_hp (the kinds were loaded one tile ago)
         const float *hpnp = P.hpn_plane + plane_base(hA);
         const int hd = TURN ? (hA.w >> 16) & 3 : 0;
@@ -892,25 +910,24 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
         }
         // next tile's kinds, next-next tile's header
         int kind1[NIT];
-        const int o1 = (tile + (int)gridDim.x) * OBS_TA + warp;
+        const int t1 = next_tile(tile);
+        const long o1 = (long)t1 * OBS_TA + warp;
         load_kinds(hA1, o1 < P.n_total, kind1);
         int4 hA2 = zero4;
         {
-            const long o2 = ((long)tile + 2l * gridDim.x) * OBS_TA + warp;
+            const long o2 = (long)next_tile(t1) * OBS_TA + warp;
             if (o2 < P.n_total) hA2 = P.hdr[o2];
         }
-        // the previous tile's bulk store must have finished READING the buffer before it is rewritten
+        // the previous tile's bulk store must have finished READING the buffer before it is touched
         if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncthreads();
-        if (!WARP_FILL && !(OBS_ABLATE & 2)) {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = threadIdx.x; q < (int)((unsigned)OBS_TA * (unsigned)P.rec * (unsigned)sizeof(T) / 16u); q += OBS_THREADS) ((float4 *)buf)[q] = z;
-            __syncthreads();
-        }
-        if (active) {
+        if (active && !(OBS_ABLATE & 2)) {
             T *dst = buf + warp * P.rec;
-            if (!(OBS_ABLATE & 2)) {
-                if (WARP_FILL) {                                   // zero this warp's own record: scalar head / tail, 16-byte body
+            const int self = (int)(short)(hA.w & 0xffff);
+            if (a != rec_arena) {
+                // (re)build the record: zeros + the arena's minimap rows (GridWorld.cc:374-383), element stores because
+                // f16 records share 32-bit words with their neighbours
+                if (sizeof(T) == 4) {                              // 16-byte body, scalar head / tail
                     float *w = (float *)dst;
                     const int n = P.rec;
                     const int head = min(n, (int)((4u - ((unsigned)(warp * P.rec) & 3u)) & 3u));
@@ -918,87 +935,67 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
                     if (lane < head) w[lane] = 0.0f;
                     float4 *w4 = (float4 *)(w + head);
                     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    int q = lane;
-                    for (; q + 96 < body; q += 128) { w4[q] = z; w4[q + 32] = z; w4[q + 64] = z; w4[q + 96] = z; }
-                    for (; q < body; q += 32) w4[q] = z;
+                    for (int q = lane; q < body; q += 32) w4[q] = z;
                     const int tail0 = head + (body << 2);
                     if (tail0 + lane < n) w[tail0 + lane] = 0.0f;
-                    __syncwarp();
+                } else {
+                    for (int q = lane; q < P.rec; q += 32) dst[q] = ObsOut<T>::cv(0.0f);
                 }
-                if (P.minimap) {                                   // GridWorld.cc:374-383: every group's minimap, unmasked
-                    unsigned done = 0;                             // the staged row has landed?
-                    while (!done) {
-                        asm volatile("{\n\t.reg .pred p;\n\t"
-                                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                                     "selp.u32 %0, 1, 0, p;\n\t}"
-                                     : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+                __syncwarp();
+                if (P.minimap) {
+                    const float *rows = P.mm + (size_t)a * P.mm_stride;
+                    for (int j = 0; j < P.G; ++j) {
+                        T *d = dst + P.mm_ch[j];
+                        for (int cell = lane; cell < P.cells; cell += 32) d[cell * P.C] = ObsOut<T>::cv(__ldg(rows + j * P.cells + cell));
                     }
-                    const int self = (int)(short)(hA.w & 0xffff);
-                    const int step = 32 * P.C;
-                    if (a == tile_a0) {                            // the staged row (shared memory)
-                        const int nfull = P.cells >> 5, rest = P.cells & 31;
-                        for (int j = 0; j < P.G; ++j) {
-                            const float *rp = mmbuf + j * P.cells + lane;
-                            T *dp = dst + P.mm_ch[j] + lane * P.C;
-                            int it = 0;
-                            for (; it + 4 <= nfull; it += 4, rp += 128, dp += 4 * step) {
-                                const float v0 = rp[0], v1 = rp[32], v2 = rp[64], v3 = rp[96];
-                                dp[0] = ObsOut<T>::cv(v0); dp[step] = ObsOut<T>::cv(v1);
-                                dp[2 * step] = ObsOut<T>::cv(v2); dp[3 * step] = ObsOut<T>::cv(v3);
-                            }
-                            for (; it < nfull; ++it, rp += 32, dp += step) *dp = ObsOut<T>::cv(*rp);
-                            if (lane < rest) *dp = ObsOut<T>::cv(*rp);
-                        }
-                        __syncwarp();
-                        if (lane < P.G) {
-                            // self marker: +1 at the observer's coarse cell; NaN + 1 keeps the x86 payload in the reference
-                            const float v = mmbuf[lane * P.cells + self];
-                            if (v == v) dst[self * P.C + P.mm_ch[lane]] = ObsOut<T>::cv(v + 1.0f);
-                        }
-                    } else {                                       // the tile straddles arenas: this record reads its own row from L2
-                        const float *rows = P.mm + (size_t)a * P.mm_stride;
-                        for (int j = 0; j < P.G; ++j) {
-                            const float *row = rows + j * P.cells;
-                            T *d = dst + P.mm_ch[j] + lane * P.C;
-                            for (int cell = lane; cell < P.cells; cell += 32, d += step) *d = ObsOut<T>::cv(__ldg(row + cell));
-                        }
-                        __syncwarp();
-                        if (lane < P.G) {
-                            const float v = __ldg(rows + lane * P.cells + self);
-                            if (v == v) dst[self * P.C + P.mm_ch[lane]] = ObsOut<T>::cv(v + 1.0f);
+                }
+                rec_arena = a;
+                __syncwarp();
+            } else {
+                // undo the previous observer: its marked cells and its self marker
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const int t = (prev_kinds[it >> 2] >> ((it & 3) * 8)) & 0xff;
+                    if (t != 0) mark(dst + lutv(it, prev_hd).x, t, 0.0f, false);
+                }
+                if (prev_tail) {                                                   // large views: recompute which tail cells were marked
+                    for (int k = NIT * 32 + lane; k < n_in; k += 32) {
+                        T *px = dst + lut[(TURN ? prev_hd * lut_stride : 0) + k].x;
+                        for (int ch = 0; ch < P.C; ++ch) {
+                            bool mm_ch = false;
+                            for (int j = 0; j < P.G; ++j) mm_ch |= P.minimap && ch == P.mm_ch[j];
+                            if (!mm_ch) px[ch] = ObsOut<T>::cv(0.0f);
                         }
                     }
                 }
+                if (P.minimap && lane < P.G && prev_self >= 0) dst[prev_self * P.C + P.mm_ch[lane]] = ObsOut<T>::cv(self_orig);
+                __syncwarp();
             }
+            // the new observer: self marker (+1 at its coarse cell; NaN + 1 keeps the x86 payload in the reference)
+            if (P.minimap && lane < P.G) {
+                const float v = __ldg(P.mm + (size_t)a * P.mm_stride + lane * P.cells + self);
+                self_orig = v;
+                if (v == v) dst[self * P.C + P.mm_ch[lane]] = ObsOut<T>::cv(v + 1.0f);
+            }
+            prev_self = self;
+            prev_hd = hd;
+#pragma unroll
+            for (int q = 0; q < (NIT + 3) / 4; ++q) prev_kinds[q] = 0u;
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
                 const int t = kind[it];
-                if (t != 0) {
-                    T *px = dst + lutv(it, hd).x;
-                    if (t == KIND_WALL) px[0] = ObsOut<T>::cv(1.0f);
-                    else if (t == KIND_FOOD) px[1] = ObsOut<T>::cv(1.0f);                   // food channel (food_mode)
-                    else {
-                        const int ch = P.grp_ch[t - 2];
-                        px[ch] = ObsOut<T>::cv(1.0f);
-                        px[ch + 1] = ObsOut<T>::cv(thp[it]);                            // hp / max_hp (Map.cc:197)
-                    }
-                }
+                prev_kinds[it >> 2] |= (unsigned)t << ((it & 3) * 8);
+                if (t != 0) mark(dst + lutv(it, hd).x, t, thp[it], true);
             }
+            prev_tail = false;
             const unsigned char *kindp = P.kind_plane + plane_base(hA);
             for (int k = NIT * 32 + lane; k < n_in; k += 32) {                          // views with > NIT * 32 in-range cells
                 const int2 l = lut[(TURN ? hd * lut_stride : 0) + k];
                 const int t = __ldg(kindp + l.y);
-                T *px = dst + l.x;
-                if (t == KIND_WALL) px[0] = ObsOut<T>::cv(1.0f);
-                else if (t == KIND_FOOD) px[1] = ObsOut<T>::cv(1.0f);
-                else if (t >= 2) {
-                    const int ch = P.grp_ch[t - 2];
-                    px[ch] = ObsOut<T>::cv(1.0f);
-                    px[ch + 1] = ObsOut<T>::cv(__ldg(hpnp + l.y));
-                }
+                if (t != 0) { mark(dst + l.x, t, t >= KIND_GROUP0 && t != KIND_FOOD ? __ldg(hpnp + l.y) : 0.0f, true); }
+                prev_tail = true;
             }
         }
-        if (P.minimap && !(OBS_ABLATE & 2)) phase ^= 1u;
         // make the generic-proxy writes visible to the async proxy, then one thread fires the bulk store
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
@@ -1030,7 +1027,7 @@ static void launch_obs_typed(const EngineDev &hE, ObsParams &P, int n_total) {
     constexpr int TA = ObsOut<T>::TA;
     constexpr int THREADS = 32 * TA;
     const size_t tile_bytes = (size_t)TA * P.rec * sizeof(T);            // multiple of 16 by construction of TA
-    const size_t smem = tile_bytes + (size_t)(P.turn ? 4 : 1) * ((P.cells + 1) & ~1) * sizeof(int2) + (size_t)P.mm_stride * sizeof(float);
+    const size_t smem = tile_bytes + (size_t)(P.turn ? 4 : 1) * ((P.cells + 1) & ~1) * sizeof(int2);
     if (smem > 227 * 1024) mg::fatal("observation record too large for the render kernel (%zu bytes of shared memory)", smem);
     const int tiles = (n_total + TA - 1) / TA;
     if ((size_t)n_total > g_obs_hdr_n) {                                 // scratch owned by the backend: per-agent headers
@@ -1054,6 +1051,9 @@ static void launch_obs_typed(const EngineDev &hE, ObsParams &P, int n_total) {
         configured = smem;
     }
     const int grid = tiles < ctas_per_sm * g_sms ? tiles : ctas_per_sm * g_sms;
+    P.chunk = tiles / (ctas_per_sm * g_sms);                            // keep every CTA busy before lengthening chunks
+    if (P.chunk < 1) P.chunk = 1;
+    if (P.chunk > OBS_CHUNK) P.chunk = OBS_CHUNK;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_profile) { profile_pair(&e0, &e1); CUDA_CHECK(cudaEventRecord(e0, 0)); }
     obs_render_kernel<T, NIT, TURN><<<grid, THREADS, smem>>>(P);
