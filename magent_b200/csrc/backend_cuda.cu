@@ -750,16 +750,15 @@ __global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr
         T *rows = (T *)P.feature + (size_t)base * P.F;
         int k = lane / P.F, f = lane - k * P.F;
         const int dk = 32 / P.F, df = 32 - dk * P.F;
+        const int fx_slot = P.minimap ? P.embedding + P.n_action + 1 : -1;
         for (int t = lane; t < total; t += 32) {
-            float v = 0.0f;
-            if (f < P.embedding) v = f < 31 ? (float)((s_id[w][k] >> f) & 1) : 0.0f;
-            else {
-                const int kk = f - P.embedding;
-                if (kk < P.n_action) v = kk == s_act[w][k] ? 1.0f : 0.0f;
-                else if (kk == P.n_action) v = s_rew[w][k];
-                else if (P.minimap && kk == P.n_action + 1) v = s_fx[w][k];
-                else if (P.minimap && kk == P.n_action + 2) v = s_fy[w][k];
-            }
+            // branch-free: lanes of one iteration sit in different segments of the row
+            const int kk = f - P.embedding;
+            float v = (f < P.embedding && f < 31 && ((s_id[w][k] >> (f & 31)) & 1)) ? 1.0f : 0.0f;
+            v = (kk >= 0 && kk < P.n_action && kk == s_act[w][k]) ? 1.0f : v;
+            v = kk == P.n_action ? s_rew[w][k] : v;
+            v = f == fx_slot ? s_fx[w][k] : v;
+            v = (fx_slot >= 0 && f == fx_slot + 1) ? s_fy[w][k] : v;
             rows[t] = ObsOut<T>::cv(v);
             k += dk; f += df;
             if (f >= P.F) { f -= P.F; ++k; }
@@ -908,6 +907,10 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
             thp[it] = 0.0f;
             if (kind[it] >= KIND_GROUP0 && kind[it] != KIND_FOOD) thp[it] = __ldg(hpnp + lutv(it, hd).y);
         }
+        // ... and the unmarked minimap value of the observer's own coarse cell (one lane per group)
+        const int self = (int)(short)(hA.w & 0xffff);
+        float selfv = 0.0f;
+        if (P.minimap && lane < P.G && self >= 0) selfv = __ldg(P.mm + (size_t)a * P.mm_stride + lane * P.cells + self);
         // next tile's kinds, next-next tile's header
         int kind1[NIT];
         const int t1 = next_tile(tile);
@@ -923,7 +926,6 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
         __syncthreads();
         if (active && !(OBS_ABLATE & 2)) {
             T *dst = buf + warp * P.rec;
-            const int self = (int)(short)(hA.w & 0xffff);
             if (a != rec_arena) {
                 // (re)build the record: zeros + the arena's minimap rows (GridWorld.cc:374-383), element stores because
                 // f16 records share 32-bit words with their neighbours
@@ -972,10 +974,9 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
                 __syncwarp();
             }
             // the new observer: self marker (+1 at its coarse cell; NaN + 1 keeps the x86 payload in the reference)
-            if (P.minimap && lane < P.G) {
-                const float v = __ldg(P.mm + (size_t)a * P.mm_stride + lane * P.cells + self);
-                self_orig = v;
-                if (v == v) dst[self * P.C + P.mm_ch[lane]] = ObsOut<T>::cv(v + 1.0f);
+            if (P.minimap && lane < P.G && self >= 0) {
+                self_orig = selfv;
+                if (selfv == selfv) dst[self * P.C + P.mm_ch[lane]] = ObsOut<T>::cv(selfv + 1.0f);
             }
             prev_self = self;
             prev_hd = hd;

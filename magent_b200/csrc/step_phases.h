@@ -55,6 +55,8 @@ struct ArenaRef {
     long nb;            // base into claim nodes        (a * scratch_stride * max_body)
     ArenaHdr *hdr;
 };
+// claimant node -> the mover that owns it (nodes are numbered mover * max_body + body cell; 1x1 bodies skip the divide)
+MG_HD int node_owner(const EngineDev &E, int node) { return E.max_body == 1 ? node : node / E.max_body; }
 // the one-byte kind plane of the observation (dev_types.h) follows every occupancy write
 MG_HD void kind_set(const EngineDev &E, int a, int x, int y, unsigned char k) {
     E.kind[a * E.kplane + (long)(y + E.kpad) * E.kw + x + E.kpad] = k;
@@ -544,7 +546,7 @@ MG_HD int occupant_at_turn(const EngineDev &E, const ArenaRef &R, unsigned curma
     }
 claimants:
     for (int node = R.claim[cell]; node != -1; node = E.cl_next[R.nb + node]) {
-        int fm = node / E.max_body;
+        int fm = node_owner(E, node);
         if (fm != self && E.mv_key[R.sb + fm] < key && ld_volatile(&E.mv_state[R.sb + fm]) == MV_OK)
             return fm;
     }
@@ -582,7 +584,7 @@ MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a
             for (int bx = 0; bx < bw && !skipped; ++bx)
                 for (int by = 0; by < bh && !skipped; ++by)
                     for (int node = R.claim[(y0 + by) * E.W + x0 + bx]; node != -1; node = E.cl_next[R.nb + node]) {
-                        const int fm = node / E.max_body;
+                        const int fm = node_owner(E, node);
                         if (fm != fs && E.mv_key[R.sb + fm] < key && ld_volatile(&E.mv_state[R.sb + fm]) == MV_ABSORBED &&
                             ld_volatile(&E.tgt[R.sb + fm]) == mycode) { skipped = true; break; }
                     }
@@ -614,7 +616,7 @@ MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a
                     // absorbed already by an earlier mover of this step?  every mover that bumps into `hit` queues on hit_cell
                     bool taken = false;
                     for (int node = R.claim[hit_cell]; node != -1 && !taken; node = E.cl_next[R.nb + node]) {
-                        const int fm = node / E.max_body;
+                        const int fm = node_owner(E, node);
                         if (fm != fs && E.mv_key[R.sb + fm] < key && ld_volatile(&E.mv_state[R.sb + fm]) == MV_ABSORBED &&
                             ld_volatile(&E.tgt[R.sb + fm]) == hcode) taken = true;
                     }
