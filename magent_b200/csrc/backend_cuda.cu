@@ -907,10 +907,6 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
             thp[it] = 0.0f;
             if (kind[it] >= KIND_GROUP0 && kind[it] != KIND_FOOD) thp[it] = __ldg(hpnp + lutv(it, hd).y);
         }
-        // ... and the unmarked minimap value of the observer's own coarse cell (one lane per group)
-        const int self = (int)(short)(hA.w & 0xffff);
-        float selfv = 0.0f;
-        if (P.minimap && lane < P.G && self >= 0) selfv = __ldg(P.mm + (size_t)a * P.mm_stride + lane * P.cells + self);
         // next tile's kinds, next-next tile's header
         int kind1[NIT];
         const int t1 = next_tile(tile);
@@ -926,6 +922,7 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
         __syncthreads();
         if (active && !(OBS_ABLATE & 2)) {
             T *dst = buf + warp * P.rec;
+            const int self = (int)(short)(hA.w & 0xffff);
             if (a != rec_arena) {
                 // (re)build the record: zeros + the arena's minimap rows (GridWorld.cc:374-383), element stores because
                 // f16 records share 32-bit words with their neighbours
@@ -974,9 +971,10 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
                 __syncwarp();
             }
             // the new observer: self marker (+1 at its coarse cell; NaN + 1 keeps the x86 payload in the reference)
-            if (P.minimap && lane < P.G && self >= 0) {
-                self_orig = selfv;
-                if (selfv == selfv) dst[self * P.C + P.mm_ch[lane]] = ObsOut<T>::cv(selfv + 1.0f);
+            if (P.minimap && lane < P.G) {
+                const float v = __ldg(P.mm + (size_t)a * P.mm_stride + lane * P.cells + self);
+                self_orig = v;
+                if (v == v) dst[self * P.C + P.mm_ch[lane]] = ObsOut<T>::cv(v + 1.0f);
             }
             prev_self = self;
             prev_hd = hd;
