@@ -340,12 +340,14 @@ def main():
     setup_s = time.time() - t_setup
 
     # per-launch algorithmic bytes of the obs-render kernel at the start of the timed region
-    obs_bytes = 0
+    obs_bytes = 0          # everything get_observation writes per step (views + feature rows)
+    render_bytes = 0       # what obs_render_kernel itself moves: the views it writes + one pass over the 1-byte kind plane
     for h in act:
         g = env._hv(h)
         (vh, vw, vc), (fs,) = spaces[g]
-        obs_bytes += env.get_num(h) * obs_esz * (vh * vw * vc + fs) + A * wl["map_size"] ** 2 * 4
-    obs_bytes_per_launch = obs_bytes / len(act)
+        obs_bytes += env.get_num(h) * obs_esz * (vh * vw * vc + fs)
+        render_bytes += env.get_num(h) * obs_esz * (vh * vw * vc) + A * wl["map_size"] ** 2 * 1
+    obs_bytes_per_launch = render_bytes / len(act)
 
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -441,6 +443,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": "obs_render_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": obs_bytes_per_launch,
+                "algorithmic_bytes": "views written by this kernel (sizeof(elem) * H_v * W_v * C per observer) + one read of the "
+                                     "1-byte kind plane per arena; the feature rows (F elements per observer) are written by "
+                                     "obs_headers_kernel and not counted here",
                 "mean_launch_ms": (obs_ms / obs_launches) if obs_launches else None, "launches_timed": obs_launches,
                 "kernel_share_of_step": (obs_ms / ms) if ms > 0 else None}
 
