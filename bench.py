@@ -285,6 +285,11 @@ def main():
         return
 
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line
+    # ... and make sure of it: libraries (NCCL prints its version banner with printf) get stderr as their fd 1; the JSON
+    # line goes to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -468,7 +473,8 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": total_launches, "clocks": clocks,
         "agent_steps_timed": total_steps,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -335,7 +335,9 @@ MG_HD bool phase_attack_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int
             }
             if (bs == -1) break;
             last = best;
-            if (ld_volatile(&E.death[R.sb + bs]) < best) continue;      // attacker dead by then
+            // attacker dead by then?  (a long body with attack_in_group can aim at one of its own cells: if the walk got
+            // this far the agent is alive at its own rank)
+            if (bs != ft && ld_volatile(&E.death[R.sb + bs]) < best) continue;
             // attacker's group -> damage
             const int sg = flat_group(E, bs);
             if (E.food_mode && friendly_fire_refused(E, sg, g)) continue;   // listed only as a potential eater
@@ -366,8 +368,13 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
         if (s.flags[gi] & FLAG_DEAD) continue;
         int d = E.death[f];
         int r = E.att_rank[f];
-        if (S.record_events && r != RANK_NONE && d > r) G.ev_rank[gi] = r;     // RenderAttackEvent, GridWorld.cc:484-485
-        if (r != RANK_NONE && d > r) {                   // my attack is executed
+        // my attack is executed iff I am alive when its rank comes; d == r can only mean that it is my own blow that
+        // kills me (an in-group attack aimed at one of my own cells)
+        const bool executed = r != RANK_NONE && (d > r || (d == r && E.tgt[f] == code_make(g, i)));
+        const bool self_kill = executed && d == r;
+        if (S.record_events && executed) G.ev_rank[gi] = r;                    // RenderAttackEvent, GridWorld.cc:484-485
+        float late_reward = 0.0f;                        // a self-kill is rewarded AFTER the death assignment (Map.cc:265-283)
+        if (executed) {
             int t = E.tgt[f];
             int dt = t >= 0 ? E.death[R.sb + lflat(E, t)] : DEATH_BEFORE;
             if (t >= 0 && E.food_mode && friendly_fire_refused(E, g, code_group(t))) dt = DEATH_BEFORE;
@@ -376,7 +383,8 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
             } else if (dt == r) {                        // my hit kills
                 s.last_op[gi] = OP_KILL;
                 s.op_obj[gi] = t;
-                s.next_reward[gi] += E.grp[code_group(t)].kill_reward + G.attack_penalty;
+                if (self_kill) late_reward = E.grp[code_group(t)].kill_reward + G.attack_penalty;
+                else s.next_reward[gi] += E.grp[code_group(t)].kill_reward + G.attack_penalty;
                 ++kills; ++hits;
             } else {
                 s.last_op[gi] = OP_ATTACK;
@@ -403,6 +411,7 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
         if (dies) {
             s.flags[gi] |= FLAG_DEAD;
             s.next_reward[gi] = G.dead_penalty;          // assignment (GridWorld.h:206)
+            if (self_kill) s.next_reward[gi] += late_reward;
             int x = s.x[gi], y = s.y[gi], bw, bh;
             body_dims(G, agent_dir(E, s, gi), bw, bh);
             for (int bx = 0; bx < bw; ++bx)
@@ -431,7 +440,7 @@ MG_HD void phase_food_commit(Ctx &c, const EngineDev &E, const StepArgs &S, int 
         const long f = R.sb + ft;
         const int t = E.tgt[f], r = E.att_rank[f];
         if (t == TGT_FOOD && write) R.claim[attack_cell_of(E, S.curmask, a, ft)] = -1;    // unhook the eaters' queue, executed or not
-        if (t == TGT_NONE || r == RANK_NONE || E.death[f] <= r) continue;          // my attack was not executed
+        if (t == TGT_NONE || r == RANK_NONE || E.death[f] < r || (E.death[f] == r && t != code_make(g, i))) continue;   // not executed
         int list, start;
         float food0;
         if (t == TGT_FOOD) { start = -1; }

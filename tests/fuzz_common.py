@@ -1,0 +1,98 @@
+"""Randomised differential testing: random (valid) game configs, random placements and action streams, played on two
+engine libraries through the same host code and compared step by step (tests/parity_common.compare_traces).
+
+The generator only emits configurations the reference accepts (it aborts the process on invalid ones): modest
+densities, ranges that exist, rules of the shapes both engines lower.  Everything derives from one integer seed.
+"""
+import numpy as np
+
+import parity_common as pc
+
+
+def random_config(seed):
+    import magent_b200 as magent
+    gw = magent.gridworld
+    rs = np.random.RandomState(seed)
+    size_w, size_h = int(rs.randint(14, 40)), int(rs.randint(14, 40))
+    turn = bool(rs.rand() < 0.3)
+    food = bool(rs.rand() < 0.3)
+    minimap = bool(rs.rand() < 0.6)
+    cfg = gw.Config()
+    cfg.set({"map_width": size_w, "map_height": size_h, "minimap_mode": minimap, "turn_mode": turn, "food_mode": food,
+             "embedding_size": int(rs.randint(0, 12)), "goal_mode": bool(rs.rand() < 0.15)})
+    n_groups = int(rs.randint(2, 5))
+    groups, bodies = [], []
+    for g in range(n_groups):
+        width, length = [(1, 1), (1, 1), (2, 2), (1, 2), (2, 1), (1, 3)][int(rs.randint(0, 6))]
+        if not turn and rs.rand() < 0.5:
+            width = length = max(1, min(width, length))
+        def rng_range(lo, hi, body):
+            r = float(rs.choice(np.arange(lo, hi, 0.5)))
+            if rs.rand() < 0.35:
+                return gw.SectorRange(max(r, 2.0), float(rs.choice([60, 90, 120, 150])))
+            return gw.CircleRange(r)
+        attrs = dict(
+            width=width, length=length, hp=float(rs.choice([1.5, 3, 6, 10])), speed=float(rs.choice([0, 1, 1.5, 2, 3])),
+            damage=float(rs.choice([0.5, 1, 2, 3.5])), step_recover=float(rs.choice([-0.3, -0.05, 0, 0.1, 0.5])),
+            kill_supply=float(rs.choice([0, 0.5, 2])), eat_ability=float(rs.choice([0, 0.3, 1.2])),
+            food_supply=float(rs.choice([0.05, 0.5, 2.5])), attack_in_group=int(rs.rand() < 0.3),
+            view_range=rng_range(1.0, 6.5, width), attack_range=rng_range(0.5, 3.0, width),
+            step_reward=float(rs.choice([-0.01, 0, 0.02])), kill_reward=float(rs.choice([0, 1, 5])),
+            dead_penalty=float(rs.choice([-1, -0.1, 0])), attack_penalty=float(rs.choice([-0.1, -0.01, 0])))
+        t = cfg.register_agent_type("t%d" % g, attrs)
+        groups.append(cfg.add_group(t))
+        bodies.append((width, length))
+    syms = [gw.AgentSymbol(g, index='any') for g in groups]
+    for _ in range(int(rs.randint(0, 5))):
+        i, j = rs.choice(n_groups, 2, replace=False)
+        a, b = syms[i], syms[j]
+        kind = int(rs.randint(0, 6))
+        if kind == 0:
+            cfg.add_reward_rule(gw.Event(a, 'attack', b), receiver=a, value=float(rs.choice([0.1, 0.2, 1])))
+        elif kind == 1:
+            cfg.add_reward_rule(gw.Event(a, 'kill', b), receiver=[a, b], value=[float(rs.choice([1, 2])), -0.5])
+        elif kind == 2:
+            cfg.add_reward_rule(gw.Event(a, 'collide', b), receiver=a, value=-0.05)
+        elif kind == 3:
+            cfg.add_reward_rule(gw.Event(a, 'attack', b) | gw.Event(a, 'kill', b), receiver=[a, gw.AgentSymbol(groups[i], 'all')],
+                                value=[0.3, 0.01])
+        elif kind == 4:
+            x0, y0 = int(rs.randint(1, size_w // 2)), int(rs.randint(1, size_h // 2))
+            cfg.add_reward_rule(gw.Event(a, 'in', ((x0, y0), (x0 + size_w // 3, y0 + size_h // 3))) & ~gw.Event(a, 'die'),
+                                receiver=a, value=0.03)
+        else:
+            cfg.add_reward_rule(gw.Event(a, 'die'), receiver=gw.AgentSymbol(groups[j], 'all'), value=0.25, terminal=bool(rs.rand() < 0.1))
+    return cfg, dict(w=size_w, h=size_h, n_groups=n_groups, bodies=bodies, turn=turn)
+
+
+def make_env(lib, seed, **kw):
+    import magent_b200 as magent
+    cfg, info = random_config(seed)
+    env = magent.GridWorld(cfg, _lib=lib, **kw)
+    rs = np.random.RandomState(seed + 7919)
+    env.set_seed(int(rs.randint(0, 10000)))
+    env.reset()
+    free = (info["w"] - 2) * (info["h"] - 2)
+    env.add_walls(method="random", n=int(rs.randint(0, max(1, free // 25))))
+    handles = env.get_handles()
+    for g, h in enumerate(handles):
+        bw, bl = info["bodies"][g]
+        share = free * float(rs.choice([0.02, 0.06, 0.12])) / (bw * bl) / info["n_groups"] * 2
+        n = max(1, int(share))
+        env.add_agents(h, method="random", n=n)
+        if rs.rand() < 0.3:                                   # explicit placements, some of them blocked or off the map
+            pos = [[int(rs.randint(1, info["w"] - 1)), int(rs.randint(1, info["h"] - 1)), int(rs.randint(0, 4))] for _ in range(6)]
+            env.add_agents(h, method="custom", pos=pos)
+    return env
+
+
+def play(seed, lib_a, lib_b, steps=25, **kw):
+    rs = np.random.RandomState(seed)
+    n_groups = len(make_env(lib_a, seed).get_handles())
+    order = [int(g) for g in rs.permutation(n_groups)]
+    acting = sorted(int(g) for g in rs.choice(n_groups, size=int(rs.randint(1, n_groups + 1)), replace=False))
+    order = [g for g in order if g in acting]
+    a = pc.run_trace(make_env(lib_a, seed), steps, seed, keep_obs=True, act_groups=acting, order=order, stop_on_done=False)
+    b = pc.run_trace(make_env(lib_b, seed, **kw), steps, seed, keep_obs=True, act_groups=acting, order=order, stop_on_done=False)
+    pc.compare_traces(a, b, what="fuzz seed %d" % seed)
+    return a
