@@ -828,10 +828,12 @@ void Engine::get_observation(int group, void **bufs, int half) {      // GridWor
         }
         O.feature = d_feat_stage_;
     }
+    // the pre-pass products depend on the state, on the observer's view size (minimap grid) and on whether the
+    // observer's type skips absorbed agents in the minimap (GridWorld.cc:343-347)
     if (prep_version_ != state_version_ || prep_vw_ != t.view.width || prep_vh_ != t.view.height ||
-        !be::obs_prepare_valid(dE_)) {
+        prep_skip_absorbed_ != t.can_absorb || !be::obs_prepare_valid(dE_)) {
         be::launch_obs_prepare(dE_, hE_, curmask_, group, minimap_mode_ ? d_mm_val_ : nullptr);
-        prep_version_ = state_version_; prep_vw_ = t.view.width; prep_vh_ = t.view.height;
+        prep_version_ = state_version_; prep_vw_ = t.view.width; prep_vh_ = t.view.height; prep_skip_absorbed_ = t.can_absorb;
     }
     be::launch_obs(dE_, hE_, O, minimap_mode_ ? d_mm_val_ : nullptr, n);
     if (!vdev) be::d2h(bufs[0], d_view_stage_, vbytes);

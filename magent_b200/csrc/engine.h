@@ -146,6 +146,7 @@ private:
     // get_observation pre-pass products (hp_norm plane, minimap) stay valid until the state changes
     unsigned long long state_version_ = 1, prep_version_ = 0;
     int prep_vw_ = 0, prep_vh_ = 0;
+    bool prep_skip_absorbed_ = false;
 
     int G() const { return (int)group_type_.size(); }
     int group2channel(int g) const;

@@ -728,6 +728,7 @@ MG_HD void phase_move_fill(Ctx &c, const EngineDev &E, const StepArgs &S, int a,
         const GroupDev &G = E.grp[g];
         long f = R.sb + G.foff + i;
         unsigned char st = E.mv_state[f];
+        if (turn && st != MV_NONE) { E.mv_state[f] = MV_NONE; E.mv_key[f] = MVKEY_NONE; }   // the move phase starts from a clean slate
         if (st != MV_OK && st != MV_PENDING_FAIL && st != MV_ABSORBED && st != MV_SKIPPED) continue;
         int nx = E.mv_nx[f], ny = E.mv_ny[f];
         bool ok = st == MV_OK;
@@ -746,7 +747,6 @@ MG_HD void phase_move_fill(Ctx &c, const EngineDev &E, const StepArgs &S, int a,
             s.x[gi] = nx; s.y[gi] = ny;
             if (turn) s.dir[gi] = (unsigned char)turned_dir(s.dir[gi], s.act[gi]);
         }
-        if (turn) { E.mv_state[f] = MV_NONE; E.mv_key[f] = MVKEY_NONE; }     // the move phase starts from a clean slate
     }
 }
 

@@ -31,6 +31,9 @@ def random_config(seed):
             if rs.rand() < 0.35:
                 return gw.SectorRange(max(r, 2.0), float(rs.choice([60, 90, 120, 150])))
             return gw.CircleRange(r)
+        absorber = (seed % 3 == 2) and g == 0 and not food                       # train_arrange-style goals (Map.cc:341-349)
+        if absorber:
+            width = length = 1
         attrs = dict(
             width=width, length=length, hp=float(rs.choice([1.5, 3, 6, 10])), speed=float(rs.choice([0, 1, 1.5, 2, 3])),
             damage=float(rs.choice([0.5, 1, 2, 3.5])), step_recover=float(rs.choice([-0.3, -0.05, 0, 0.1, 0.5])),
@@ -39,6 +42,8 @@ def random_config(seed):
             view_range=rng_range(1.0, 6.5, width), attack_range=rng_range(0.5, 3.0, width),
             step_reward=float(rs.choice([-0.01, 0, 0.02])), kill_reward=float(rs.choice([0, 1, 5])),
             dead_penalty=float(rs.choice([-1, -0.1, 0])), attack_penalty=float(rs.choice([-0.1, -0.01, 0])))
+        if absorber:
+            attrs.update(can_absorb=1, damage=0.0, step_recover=0.0, attack_range=gw.CircleRange(0))
         t = cfg.register_agent_type("t%d" % g, attrs)
         groups.append(cfg.add_group(t))
         bodies.append((width, length))
@@ -46,7 +51,7 @@ def random_config(seed):
     for _ in range(int(rs.randint(0, 5))):
         i, j = rs.choice(n_groups, 2, replace=False)
         a, b = syms[i], syms[j]
-        kind = int(rs.randint(0, 6))
+        kind = int(rs.randint(0, 7 if seed % 3 == 1 else 6))
         if kind == 0:
             cfg.add_reward_rule(gw.Event(a, 'attack', b), receiver=a, value=float(rs.choice([0.1, 0.2, 1])))
         elif kind == 1:
@@ -60,6 +65,13 @@ def random_config(seed):
             x0, y0 = int(rs.randint(1, size_w // 2)), int(rs.randint(1, size_h // 2))
             cfg.add_reward_rule(gw.Event(a, 'in', ((x0, y0), (x0 + size_w // 3, y0 + size_h // 3))) & ~gw.Event(a, 'die'),
                                 receiver=a, value=0.03)
+        elif kind == 6:                                                           # two free subjects, one shared object (double_attack)
+            k = int(rs.choice([x for x in range(n_groups) if x != i]))
+            c = syms[k]
+            a2 = gw.AgentSymbol(groups[i], index='any') if rs.rand() < 0.5 else b
+            if a2 is b and k == j:
+                a2 = gw.AgentSymbol(groups[i], index='any')
+            cfg.add_reward_rule(gw.Event(a, 'attack', c) & gw.Event(a2, 'attack', c), receiver=[a, a2], value=[0.5, 0.5])
         else:
             cfg.add_reward_rule(gw.Event(a, 'die'), receiver=gw.AgentSymbol(groups[j], 'all'), value=0.25, terminal=bool(rs.rand() < 0.1))
     return cfg, dict(w=size_w, h=size_h, n_groups=n_groups, bodies=bodies, turn=turn)
@@ -77,7 +89,7 @@ def make_env(lib, seed, **kw):
     handles = env.get_handles()
     for g, h in enumerate(handles):
         bw, bl = info["bodies"][g]
-        share = free * float(rs.choice([0.02, 0.06, 0.12])) / (bw * bl) / info["n_groups"] * 2
+        share = free * float(rs.choice([0.02, 0.06, 0.12] if seed % 3 != 1 else [0.1, 0.2, 0.3])) / (bw * bl) / info["n_groups"] * 2
         n = max(1, int(share))
         env.add_agents(h, method="random", n=n)
         if rs.rand() < 0.3:                                   # explicit placements, some of them blocked or off the map

@@ -1,0 +1,25 @@
+"""Randomised differential tests on CPU: the test-only host emulation of the engine (same phase functions as the CUDA
+kernels) and the plain-C oracle port against the compiled reference, on random configurations (tests/fuzz_common.py:
+2-4 groups, 1x1 .. 2x2 / 1x3 bodies, circle and sector ranges, turn_mode / food_mode / goal_mode / minimap on or off,
+random rule sets, walls, random and explicit placements, random call order and acting subset)."""
+import os
+
+import pytest
+
+import fuzz_common as fz
+import parity_common as pc
+from test_emu_parity_cpu import emu  # noqa: F401  (fixture: builds tests/_emu on demand)
+
+HAVE_REF = os.path.exists(pc.REF_LIB)
+CHECKER = pc.REF_LIB if HAVE_REF else pc.PORT_LIB
+
+
+@pytest.mark.parametrize("seed", list(range(0, 24)))
+def test_emulated_engine_matches_checker_on_random_games(emu, seed):
+    fz.play(seed, CHECKER, emu, steps=20)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs oracle/_ref (the compiled reference)")
+@pytest.mark.parametrize("seed", list(range(100, 116)))
+def test_oracle_port_matches_reference_on_random_games(seed):
+    fz.play(seed, pc.REF_LIB, pc.PORT_LIB, steps=20)

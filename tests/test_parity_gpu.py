@@ -386,3 +386,12 @@ def test_f16_device_pointer_observation():
     assert tv.dtype == torch.float16 and tuple(tv.shape) == v.shape
     np.testing.assert_array_equal(tv.cpu().numpy().view(np.uint16), v.astype(np.float16).view(np.uint16))
     np.testing.assert_array_equal(tf.cpu().numpy().view(np.uint16), f.astype(np.float16).view(np.uint16))
+
+
+@pytest.mark.parametrize("seed", list(range(0, 36)))
+def test_random_games_match_checker(seed):
+    """randomised differential test (tests/fuzz_common.py): random configs (2-4 groups, long bodies, sector ranges,
+    turn / food / goal / minimap modes, absorbers, random rule sets incl. two-subject rules), random placements, call
+    order and acting subsets -- CUDA engine vs the checker, step by step, bit-exact observations"""
+    import fuzz_common as fz
+    fz.play(seed, checker_lib(), pc.CUDA_LIB, steps=20)
