@@ -108,3 +108,49 @@ def play(seed, lib_a, lib_b, steps=25, **kw):
     b = pc.run_trace(make_env(lib_b, seed, **kw), steps, seed, keep_obs=True, act_groups=acting, order=order, stop_on_done=False)
     pc.compare_traces(a, b, what="fuzz seed %d" % seed)
     return a
+
+
+def trace_irregular(env, steps, seed, acting, order):
+    """like parity_common.run_trace, but the caller misbehaves the way real scripts do: clear_dead is skipped on some
+    steps (dead agents keep their slots and still receive actions), agents are added in the middle of the episode,
+    observations are not fetched every step"""
+    handles = env.get_handles()
+    rs = np.random.RandomState(seed ^ 0x5bd1)
+    trace = []
+    for t in range(steps):
+        rec = {"num": [env.get_num(h) for h in handles]}
+        obs = {}
+        if rs.rand() < 0.7:
+            for gi in acting:
+                if rec["num"][gi] == 0:
+                    continue
+                v, f = env.get_observation(handles[gi])
+                obs[gi] = (v.copy(), f.copy())
+        rec["obs"] = obs
+        rec["id"] = [env.get_agent_id(h).copy() for h in handles]
+        rec["pos"] = [env.get_pos(h).copy() for h in handles]
+        acts = {gi: rs.randint(0, env.get_action_space(handles[gi])[0], size=rec["num"][gi]).astype(np.int32) for gi in acting}
+        for gi in order:
+            env.set_action(handles[gi], acts[gi])
+        rec["done"] = bool(env.step())
+        rec["reward"] = [env.get_reward(h).copy() for h in handles]
+        rec["alive"] = [env.get_alive(h).copy() for h in handles]
+        rec["pos_after"] = [env.get_pos(h).copy() for h in handles]
+        if rs.rand() < 0.65:
+            env.clear_dead()
+        if rs.rand() < 0.15:
+            env.add_agents(handles[int(rs.randint(0, len(handles)))], method="random", n=int(rs.randint(1, 4)))
+        trace.append(rec)
+    return trace
+
+
+def play_irregular(seed, lib_a, lib_b, steps=25, **kw):
+    rs = np.random.RandomState(seed)
+    n_groups = len(make_env(lib_a, seed).get_handles())
+    order = [int(g) for g in rs.permutation(n_groups)]
+    acting = sorted(int(g) for g in rs.choice(n_groups, size=int(rs.randint(1, n_groups + 1)), replace=False))
+    order = [g for g in order if g in acting]
+    a = trace_irregular(make_env(lib_a, seed), steps, seed, acting, order)
+    b = trace_irregular(make_env(lib_b, seed, **kw), steps, seed, acting, order)
+    pc.compare_traces(a, b, what="irregular fuzz seed %d" % seed)
+    return a

@@ -23,3 +23,10 @@ def test_emulated_engine_matches_checker_on_random_games(emu, seed):
 @pytest.mark.parametrize("seed", list(range(100, 116)))
 def test_oracle_port_matches_reference_on_random_games(seed):
     fz.play(seed, pc.REF_LIB, pc.PORT_LIB, steps=20)
+
+
+@pytest.mark.parametrize("seed", list(range(200, 212)))
+def test_emulated_engine_matches_checker_with_an_irregular_caller(emu, seed):
+    """skipped clear_dead (dead agents keep slots and still get actions), agents added mid-episode, observations
+    not fetched every step"""
+    fz.play_irregular(seed, CHECKER, emu, steps=20)

@@ -395,3 +395,11 @@ def test_random_games_match_checker(seed):
     order and acting subsets -- CUDA engine vs the checker, step by step, bit-exact observations"""
     import fuzz_common as fz
     fz.play(seed, checker_lib(), pc.CUDA_LIB, steps=20)
+
+
+@pytest.mark.parametrize("seed", list(range(300, 312)))
+def test_random_games_with_an_irregular_caller(seed):
+    """fuzz_common.play_irregular: skipped clear_dead, agents added mid-episode (host <-> device round trips of the
+    whole state incl. kind / food planes), observations not fetched every step"""
+    import fuzz_common as fz
+    fz.play_irregular(seed, checker_lib(), pc.CUDA_LIB, steps=20)
