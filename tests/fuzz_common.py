@@ -154,3 +154,60 @@ def play_irregular(seed, lib_a, lib_b, steps=25, **kw):
     b = trace_irregular(make_env(lib_b, seed, **kw), steps, seed, acting, order)
     pc.compare_traces(a, b, what="irregular fuzz seed %d" % seed)
     return a
+
+
+def play_batch(seed, checker_lib, engine_lib, n_arenas=3, steps=15):
+    """`_num_arenas` batch of the engine vs n_arenas independent checker environments (arena a is seeded seed0 + a;
+    every setup call goes to all arenas).  Groups are presented as the concatenation over arenas."""
+    import magent_b200 as magent
+    cfg, info = random_config(seed)
+    rs = np.random.RandomState(seed + 7919)
+    seed0 = int(rs.randint(0, 10000))
+    batch = magent.GridWorld(cfg, _lib=engine_lib, _num_arenas=n_arenas)
+    singles = [magent.GridWorld(random_config(seed)[0], _lib=checker_lib) for _ in range(n_arenas)]
+    batch.set_seed(seed0)
+    batch.reset()
+    for a, env in enumerate(singles):
+        env.set_seed(seed0 + a)
+        env.reset()
+    free = (info["w"] - 2) * (info["h"] - 2)
+    n_walls = int(rs.randint(0, max(1, free // 25)))
+    for env in [batch] + singles:
+        env.add_walls(method="random", n=n_walls)
+    handles = batch.get_handles()
+    for g, h in enumerate(handles):
+        bw, bl = info["bodies"][g]
+        n = max(1, int(free * float(rs.choice([0.02, 0.06, 0.12])) / (bw * bl) / info["n_groups"] * 2))
+        for env in [batch] + singles:
+            env.add_agents(env.get_handles()[g], method="random", n=n)
+    G = len(handles)
+    for t in range(steps):
+        nums = [[env.get_num(env.get_handles()[g]) for g in range(G)] for env in singles]
+        for g in range(G):
+            tot = sum(n[g] for n in nums)
+            assert batch.get_num(handles[g]) == tot, "step %d group %d num" % (t, g)
+            if tot == 0:
+                continue
+            v, f = batch.get_observation(handles[g])
+            parts = [env.get_observation(env.get_handles()[g]) for env in singles if env.get_num(env.get_handles()[g])]
+            np.testing.assert_array_equal(v.view(np.uint32), np.concatenate([p[0] for p in parts]).view(np.uint32), err_msg="batch seed %d step %d view g%d" % (seed, t, g))
+            np.testing.assert_array_equal(f.view(np.uint32), np.concatenate([p[1] for p in parts]).view(np.uint32), err_msg="batch seed %d step %d feat g%d" % (seed, t, g))
+        for g in range(G):
+            n_act = batch.get_action_space(handles[g])[0]
+            acts = [rs.randint(0, n_act, size=n[g]).astype(np.int32) for n in nums]
+            batch.set_action(handles[g], np.concatenate(acts) if acts else np.zeros((0,), np.int32))
+            for env, a in zip(singles, acts):
+                env.set_action(env.get_handles()[g], a)
+        batch.step()
+        for env in singles:
+            env.step()
+        for g in range(G):
+            want_r = np.concatenate([env.get_reward(env.get_handles()[g]) for env in singles])
+            want_p = np.concatenate([env.get_pos(env.get_handles()[g]).reshape(-1, 2) for env in singles])
+            want_a = np.concatenate([env.get_alive(env.get_handles()[g]) for env in singles])
+            np.testing.assert_allclose(batch.get_reward(handles[g]), want_r, atol=pc.REWARD_TOL, rtol=0, err_msg="batch seed %d step %d reward g%d" % (seed, t, g))
+            np.testing.assert_array_equal(batch.get_pos(handles[g]).reshape(-1, 2), want_p, err_msg="batch seed %d step %d pos g%d" % (seed, t, g))
+            np.testing.assert_array_equal(batch.get_alive(handles[g]), want_a, err_msg="batch seed %d step %d alive g%d" % (seed, t, g))
+        batch.clear_dead()
+        for env in singles:
+            env.clear_dead()

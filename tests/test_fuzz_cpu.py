@@ -30,3 +30,8 @@ def test_emulated_engine_matches_checker_with_an_irregular_caller(emu, seed):
     """skipped clear_dead (dead agents keep slots and still get actions), agents added mid-episode, observations
     not fetched every step"""
     fz.play_irregular(seed, CHECKER, emu, steps=20)
+
+
+@pytest.mark.parametrize("seed", list(range(400, 410)))
+def test_emulated_arena_batch_matches_independent_checkers(emu, seed):
+    fz.play_batch(seed, CHECKER, emu, n_arenas=1 + seed % 4, steps=10)

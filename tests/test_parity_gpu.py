@@ -403,3 +403,11 @@ def test_random_games_with_an_irregular_caller(seed):
     whole state incl. kind / food planes), observations not fetched every step"""
     import fuzz_common as fz
     fz.play_irregular(seed, checker_lib(), pc.CUDA_LIB, steps=20)
+
+
+@pytest.mark.parametrize("seed", list(range(500, 516)))
+def test_random_arena_batches_match_independent_checkers(seed):
+    """`_num_arenas` batches of random games vs independent checker environments (tiles straddling arenas, ragged
+    tails, empty groups in some arenas)"""
+    import fuzz_common as fz
+    fz.play_batch(seed, checker_lib(), pc.CUDA_LIB, n_arenas=2 + seed % 5, steps=12)
