@@ -723,45 +723,51 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 //     that its only dependent loads are kind plane -> hp_norm plane;
 //   * the complete non-spatial feature row (GridWorld.cc:386-396): id bits LSB first, one-hot last action, last
 //     reward, and x/W, y/H with the minimap.  A fresh agent's last_action == n_action ("dangerous", GridWorld.h:140)
-//     lands on the reward slot and is overwritten by it -- here the reward simply wins.  Rows are written by the
-//     whole warp (lane = feature index) so the stores coalesce.
+//     lands on the reward slot and is overwritten by it -- here the reward simply wins.  The rows of 32 observers are
+//     zeroed with coalesced 16-byte stores, then each lane writes its observer's handful of non-zeros.
 template <typename T>
 __global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr) {
-    __shared__ int s_id[8][32], s_act[8][32];
-    __shared__ float s_rew[8][32], s_fx[8][32], s_fy[8][32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int n_warps = gridDim.x * (blockDim.x >> 5);
-    for (int base = (blockIdx.x * (blockDim.x >> 5) + w) * 32; base < P.n_total; base += n_warps * 32) {
+    for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < P.n_total; base += n_warps * 32) {
         const int o = base + lane;
-        __syncwarp();
+        const int cnt = min(32, P.n_total - base);
+        // the 32 feature rows of this warp are one contiguous block of cnt * F elements: zero it with 16-byte stores (the
+        // block starts 16-byte aligned because base % 32 == 0), then every lane drops its own observer's few non-zeros
+        T *rows = (T *)P.feature + (size_t)base * P.F;
+        const int total = cnt * P.F, vec = (int)(16 / sizeof(T));
+        if ((((size_t)rows) & 15) == 0) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = lane; q < total / vec; q += 32) ((float4 *)rows)[q] = z;
+            for (int q = (total / vec) * vec + lane; q < total; q += 32) rows[q] = ObsOut<T>::cv(0.0f);
+        } else {
+            for (int q = lane; q < total; q += 32) rows[q] = ObsOut<T>::cv(0.0f);
+        }
+        __syncwarp();                                          // orders the zero fill before the value stores below
         if (o < P.n_total) {
             const int a = P.A == 1 ? 0 : locate_arena(P.off, P.A, o);
             const long gi = (long)a * P.cap + (o - P.off[a]);
             const int x = P.x[gi], y = P.y[gi];
-            s_id[w][lane] = P.id[gi]; s_act[w][lane] = P.act[gi]; s_rew[w][lane] = P.last_reward[gi];
-            s_fx[w][lane] = (float)x / (float)P.W; s_fy[w][lane] = (float)y / (float)P.H;                  // GridWorld.cc:394-395
             const int self_cell = P.minimap ? (y / P.scale_h) * P.vw + x / P.scale_w : -1;  // GridWorld.cc:372-373
             const int heading = P.turn ? (int)P.dir[gi] : 0;
             hdr[o] = make_int4(x, y, a, (self_cell & 0xffff) | (heading << 16));
-        }
-        __syncwarp();
-        // the 32 rows are one contiguous block of 32 * F elements: lane-strided, fully coalesced
-        const int total = min(32, P.n_total - base) * P.F;
-        T *rows = (T *)P.feature + (size_t)base * P.F;
-        int k = lane / P.F, f = lane - k * P.F;
-        const int dk = 32 / P.F, df = 32 - dk * P.F;
-        const int fx_slot = P.minimap ? P.embedding + P.n_action + 1 : -1;
-        for (int t = lane; t < total; t += 32) {
-            // branch-free: lanes of one iteration sit in different segments of the row
-            const int kk = f - P.embedding;
-            float v = (f < P.embedding && f < 31 && ((s_id[w][k] >> (f & 31)) & 1)) ? 1.0f : 0.0f;
-            v = (kk >= 0 && kk < P.n_action && kk == s_act[w][k]) ? 1.0f : v;
-            v = kk == P.n_action ? s_rew[w][k] : v;
-            v = f == fx_slot ? s_fx[w][k] : v;
-            v = (fx_slot >= 0 && f == fx_slot + 1) ? s_fy[w][k] : v;
-            rows[t] = ObsOut<T>::cv(v);
-            k += dk; f += df;
-            if (f >= P.F) { f -= P.F; ++k; }
+            T *f = rows + (size_t)lane * P.F;
+            unsigned id = (unsigned)P.id[gi];
+            const int nbits = min(P.embedding, 31);
+            id &= nbits >= 32 ? 0xffffffffu : ((1u << nbits) - 1u);
+            while (id) {                                       // embedding: the set bits of the id, LSB first (GridWorld.h:155-164)
+                const int bit = __ffs(id) - 1;
+                f[bit] = ObsOut<T>::cv(1.0f);
+                id &= id - 1;
+            }
+            T *g = f + P.embedding;
+            const int act = P.act[gi];
+            if (act >= 0 && act < P.n_action) g[act] = ObsOut<T>::cv(1.0f);
+            g[P.n_action] = ObsOut<T>::cv(P.last_reward[gi]);   // also overwrites the "dangerous" fresh-agent one-hot slot
+            if (P.minimap) {
+                g[P.n_action + 1] = ObsOut<T>::cv((float)x / (float)P.W);                   // GridWorld.cc:394-395
+                g[P.n_action + 2] = ObsOut<T>::cv((float)y / (float)P.H);
+            }
         }
     }
 }
@@ -1052,7 +1058,8 @@ static void launch_obs_typed(const EngineDev &hE, ObsParams &P, int n_total) {
     const int grid = tiles < ctas_per_sm * g_sms ? tiles : ctas_per_sm * g_sms;
     P.chunk = tiles / (ctas_per_sm * g_sms);                            // keep every CTA busy before lengthening chunks
     if (P.chunk < 1) P.chunk = 1;
-    if (P.chunk > OBS_CHUNK) P.chunk = OBS_CHUNK;
+    const int max_chunk = sizeof(T) == 2 ? 2 * OBS_CHUNK : OBS_CHUNK;   // f16 tiles are rebuilt for 8 observers at once: longer chunks pay (measured)
+    if (P.chunk > max_chunk) P.chunk = max_chunk;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_profile) { profile_pair(&e0, &e1); CUDA_CHECK(cudaEventRecord(e0, 0)); }
     obs_render_kernel<T, NIT, TURN><<<grid, THREADS, smem>>>(P);

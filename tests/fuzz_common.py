@@ -140,6 +140,8 @@ def trace_irregular(env, steps, seed, acting, order):
             env.clear_dead()
         if rs.rand() < 0.15:
             env.add_agents(handles[int(rs.randint(0, len(handles)))], method="random", n=int(rs.randint(1, 4)))
+        if env.config.config_dict.get("goal_mode") and rs.rand() < 0.3:      # deprecated API: two RNG draws per agent
+            env.set_goal(handles[int(rs.randint(0, len(handles)))], "random")
         trace.append(rec)
     return trace
 

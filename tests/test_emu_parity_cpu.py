@@ -141,12 +141,13 @@ def _render_episode(lib, tmpdir, scenario):
     return files, sorted((k, tuple(v)) for k, v in info[0].items()), info[1].tolist()
 
 
-@pytest.mark.parametrize("which", ["battle", "arrange"])
+@pytest.mark.parametrize("which", ["battle", "arrange", "turn", "food"])
 def test_render_dump_is_byte_identical(emu, tmp_path, which):
     """env_render: config.json + video_N.txt frames incl. attack events (RenderGenerator.cc:63-185)"""
     if not os.path.exists(pc.REF_LIB):
         pytest.skip("needs the compiled reference")
-    scen = (lambda lib: pc.make_battle(lib, 30, 200, 3)) if which == "battle" else (lambda lib: pc.make_arrange(lib, 30, 12))
+    scen = {"battle": lambda lib: pc.make_battle(lib, 30, 200, 3), "arrange": lambda lib: pc.make_arrange(lib, 30, 12),
+            "turn": lambda lib: pc.make_turn(lib, 30, 5), "food": lambda lib: pc.make_food(lib, 30, 3)}[which]
     a = _render_episode(pc.REF_LIB, str(tmp_path / "ref"), scen)
     b = _render_episode(emu, str(tmp_path / "emu"), scen)
     assert sorted(a[0]) == sorted(b[0]) and "config.json" in a[0]
