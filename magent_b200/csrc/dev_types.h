@@ -16,7 +16,7 @@
 
 namespace mg {
 
-enum { MG_MAX_GROUPS = 8, MG_MAX_RULES = 16, MG_MAX_PROG = 16, MG_MAX_RECV = 4 };
+enum { MG_MAX_GROUPS = 8, MG_MAX_RULES = 16, MG_MAX_PROG = 16, MG_MAX_RECV = 4, MG_MAX_IN = 4, MG_MAX_ALLQ = 16 };
 enum { MG_N_COUNTERS = 8 };
 enum Counter { CNT_AGENT_STEPS = 0, CNT_ATTACKS, CNT_HITS, CNT_KILLS, CNT_STARVED,
                CNT_MOVES_OK, CNT_MOVES_BLOCKED, CNT_STEPS };
@@ -87,28 +87,42 @@ struct ArenaHdr {
     int changed[3];          // rotating "something changed" flags of the relaxation loops
     int rule_trigger;        // bitmask of rules triggered this step
     float grp_reward[MG_MAX_GROUPS];
+    // Agent::index of the reference is written by clear_dead only (GridWorld.cc:655) and is 0 from the
+    // constructor (GridWorld.h:136): agents at positions >= n_cull[g] (added since the last clear_dead) have index 0
+    int n_cull[MG_MAX_GROUPS];
+    // group-quantified ('all' subject) event nodes, reduced once per step (phase_rule_allq): number of agents
+    // violating the predicate, and min / max of the varying coordinate for in_a_line
+    int allq_viol[MG_MAX_ALLQ], allq_min[MG_MAX_ALLQ], allq_max[MG_MAX_ALLQ];
 };
 
-// entity roles inside a rule: 0 = subject A, 1 = object inferred from A's op_obj,
-//                             2 = subject B, 3 = object inferred from B's op_obj;  4 = a whole group (receivers)
-enum { ROLE_SUB_A = 0, ROLE_OBJ_A = 1, ROLE_SUB_B = 2, ROLE_OBJ_B = 3, ROLE_GROUP = 4 };
+// Entity roles inside a rule.  The reference binds the rule's input symbols depth-first in order
+// (RewardEngine.cc:373-443); input k writes its subject symbol (role 2k) and then the symbol inferred from the
+// subject's op_obj (role 2k+1).  A symbol's entity at the leaf is the LAST write to it, resolved at compile time.
+enum { ROLE_GROUP = 254, ROLE_ALL = 255 };      // a whole group as receiver / an 'all' subject of an event node
+enum { IN_ANY = 0, IN_ALL = 1, IN_FIXED = 2 };  // AgentSymbol::index -1 / -2 / >= 0
 
 struct RuleInstr {           // postfix program over the bound entities
     unsigned char op;        // EventOp
-    unsigned char role_a;    // entity role of the first symbol
+    unsigned char role_a;    // entity role of the first symbol (ROLE_ALL: quantified over `all_group`)
     unsigned char role_b;
-    unsigned char pad;
+    unsigned char allq;      // ROLE_ALL: slot of the per-step reduction in ArenaHdr::allq_*
     int i0, i1, i2, i3;      // OP_AT: x,y ; OP_IN: x1,y1,x2,y2
+    int all_group;
 };
 
 struct RuleRecv { int role; int group; float value; };
 
+struct RuleInput {           // one level of the reference's DFS (input_symbols[k], infer_obj[k])
+    int kind;                // IN_ANY: loop over the group; IN_ALL: binds nothing itself; IN_FIXED: agent `index`
+    int group, index;
+    int has_obj, obj_group, obj_index;      // symbol bound from the subject's op_obj; obj_index -1 = any
+};
+
 struct RuleDev {
-    int kind;                // 0: scan one 'any' subject A;  1: scan all ordered pairs (A, B) of two 'any' subjects
-    int sub_group;           // group of A
-    int has_obj, obj_group, obj_index;      // object bound from A's op_obj; obj_index -1 = any
-    int sub2_group;          // group of B (kind 1)
-    int has_obj2, obj2_group, obj2_index;   // object bound from B's op_obj
+    int n_in; RuleInput in[MG_MAX_IN];
+    int n_any; int any_in[MG_MAX_IN];       // the IN_ANY levels, outermost first
+    int dead;                               // can never fire (fixed-index subject without an inferred object,
+                                            // RewardEngine.cc:426-441 has no else branch)
     int n_prog; RuleInstr prog[MG_MAX_PROG];
     int n_recv; RuleRecv recv[MG_MAX_RECV];
     int is_terminal;
@@ -146,6 +160,7 @@ struct EngineDev {
     int *jv, *sh_head, *sh_next, *sh_first, *att_agent;
     int *cl_next;                             // [A][cap_total*max_body] claimant list links
     int n_rules; RuleDev rules[MG_MAX_RULES];
+    int n_allq;                               // group-quantified event nodes over all rules (ArenaHdr::allq_*)
     long long *counters;                      // [MG_N_COUNTERS]
     int *team_scratch;                        // [2 * max CTAs] partial sums of team scans
     int *mm_count;                            // [A][G][max_view_cells] minimap histogram scratch

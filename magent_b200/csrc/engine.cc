@@ -93,7 +93,7 @@ RangeTab make_sector_range(float angle, float radius, int parity) {
     return r;
 }
 
-void HostGroup::clear() { resize(0); dead_ct = 0; grp_reward = 0.0f; }
+void HostGroup::clear() { resize(0); dead_ct = 0; n_cull = 0; grp_reward = 0.0f; }
 void HostGroup::resize(int n) {
     x.resize(n); y.resize(n); id.resize(n); act.resize(n); op_obj.resize(n);
     hp.resize(n); next_reward.resize(n); last_reward.resize(n);
@@ -248,7 +248,7 @@ void Engine::add_reward_rule(int on, int *receivers, float *values, int n_receiv
 // ---------------------------------------------------------------------------------------------
 // Reward-rule compiler.  Re-derives the reference's binding plan (related symbols, inference map,
 // input_symbols / infer_obj; RewardEngine.cc:71-189) and lowers the shapes the device evaluator
-// handles: ONE 'any' subject symbol, optionally with its op_obj bound to a second symbol.
+// into a flat binding plan (RuleDev): 'any' levels become loops, 'all' / fixed-index levels bind once.
 namespace {
 struct NodeInfo { std::set<int> related; std::map<int, int> infer; };
 
@@ -285,6 +285,7 @@ void collect(const std::vector<NodeDef> &nodes, int no, std::vector<NodeInfo> &i
 
 void Engine::compile_rules() {
     compiled_rules_.clear();
+    n_allq_ = 0;
     if (rules_.size() > MG_MAX_RULES) fatal("too many reward rules (max %d)", (int)MG_MAX_RULES);
     std::vector<NodeInfo> info(nodes_.size());
     std::vector<char> seen(nodes_.size(), 0);
@@ -306,46 +307,54 @@ void Engine::compile_rules() {
         for (int s : on.related)                      // second pass: the rest
             if (!added.count(s)) { input.push_back(s); infer.push_back(-1); }
 
-        if (input.empty() || input.size() > 2)
-            fatal("reward rule %d: rules binding %d free symbols are not supported by the B200 engine yet "
-                  "(1 or 2 'any' subjects are; SURVEY.md §8f rank 1)", (int)ri, (int)input.size());
-        for (int s : input)
-            if (symbols_[s].index != -1)
-                fatal("reward rule %d: subject symbols must be 'any' for the B200 engine yet ('all' / fixed-index "
-                      "subjects: SURVEY.md §8f rank 1)", (int)ri);
+        if (input.empty()) fatal("reward rule %d: the trigger event binds no agent symbol", (int)ri);
+        if (input.size() > MG_MAX_IN)
+            fatal("reward rule %d: %d input symbols (max %d)", (int)ri, (int)input.size(), (int)MG_MAX_IN);
         RuleDev R;
         memset(&R, 0, sizeof R);
-        R.kind = input.size() == 2 ? 1 : 0;
-        R.sub_group = symbols_[input[0]].group;
-        check_group(R.sub_group, "reward rule subject");
-        R.has_obj = infer[0] >= 0;
-        if (R.has_obj) {
-            R.obj_group = symbols_[infer[0]].group;
-            R.obj_index = symbols_[infer[0]].index;
-            if (R.obj_index == -2) fatal("reward rule %d: the object of attack/kill/collide cannot be a group", (int)ri);
-        }
-        if (R.kind == 1) {
-            R.sub2_group = symbols_[input[1]].group;
-            check_group(R.sub2_group, "reward rule subject");
-            R.has_obj2 = infer[1] >= 0;
-            if (R.has_obj2) {
-                R.obj2_group = symbols_[infer[1]].group;
-                R.obj2_index = symbols_[infer[1]].index;
-                if (R.obj2_index == -2) fatal("reward rule %d: the object of attack/kill/collide cannot be a group", (int)ri);
+        R.n_in = (int)input.size();
+        // writes[sym] = role of the LAST binding of the symbol along the reference's depth-first order: level k
+        // sets its subject (any / fixed index; an 'all' symbol has no entity) and then the symbol inferred from
+        // the subject's op_obj (RewardEngine.cc:396-441).  Two levels inferring the same object symbol, or a level
+        // inferring an earlier level's subject, overwrite -- the leaf sees the last one.
+        std::map<int, int> writes;
+        for (int k = 0; k < R.n_in; ++k) {
+            const SymbolDef &sd = symbols_[input[k]];
+            RuleInput &in = R.in[k];
+            check_group(sd.group, "reward rule subject");
+            in.group = sd.group; in.index = sd.index;
+            in.kind = sd.index == -1 ? IN_ANY : sd.index == -2 ? IN_ALL : IN_FIXED;
+            if (sd.index < -2) fatal("reward rule %d: invalid agent symbol index %d", (int)ri, sd.index);
+            if (in.kind == IN_ANY) R.any_in[R.n_any++] = k;
+            if (in.kind != IN_ALL) writes[input[k]] = 2 * k;
+            in.has_obj = infer[k] >= 0;
+            if (in.has_obj) {
+                const SymbolDef &od = symbols_[infer[k]];
+                check_group(od.group, "reward rule object");
+                if (od.index == -2) fatal("reward rule %d: the object of attack/kill/collide cannot be a group", (int)ri);
+                in.obj_group = od.group; in.obj_index = od.index;
+                writes[infer[k]] = 2 * k + 1;
+            } else if (in.kind == IN_FIXED) {
+                R.dead = 1;                            // calc_rule never recurses past it (RewardEngine.cc:426-441)
             }
         }
-        // symbol -> entity role.  When both subjects infer the SAME object symbol, the binding made for B
-        // (the inner loop of the reference DFS) overwrites the one made for A (RewardEngine.cc:405-409).
         auto role_of = [&](int sym) -> int {
-            if (sym == input[0]) return ROLE_SUB_A;
-            if (R.kind == 1 && sym == input[1]) return ROLE_SUB_B;
-            if (R.kind == 1 && R.has_obj2 && sym == infer[1]) return ROLE_OBJ_B;
-            if (R.has_obj && sym == infer[0]) return ROLE_OBJ_A;
-            fatal("reward rule %d: symbol %d is not bound by the trigger event", (int)ri, sym);
+            auto it = writes.find(sym);
+            if (it == writes.end()) fatal("reward rule %d: symbol %d is not bound by the trigger event", (int)ri, sym);
+            return it->second;
         };
         // postfix lowering of the trigger tree
         struct Lower {
-            const std::vector<NodeDef> &nodes; RuleDev &R; decltype(role_of) &role;
+            const std::vector<NodeDef> &nodes; const std::vector<SymbolDef> &syms; RuleDev &R;
+            decltype(role_of) &role; int &n_allq; int ri;
+            void subject(RuleInstr &I, int sym) {
+                if (syms[sym].index == -2) {           // quantified over the group (calc_event_node's is_all() branches)
+                    if (n_allq >= MG_MAX_ALLQ) fatal("too many group-quantified ('all') events in the reward rules");
+                    I.role_a = ROLE_ALL; I.all_group = syms[sym].group; I.allq = (unsigned char)n_allq++;
+                } else {
+                    I.role_a = (unsigned char)role(sym);
+                }
+            }
             void go(int no) {
                 const NodeDef &n = nodes[no];
                 RuleInstr I; memset(&I, 0, sizeof I);
@@ -354,24 +363,33 @@ void Engine::compile_rules() {
                     case OP_AND: case OP_OR: go(n.raw[0]); go(n.raw[1]); break;
                     case OP_NOT: go(n.raw[0]); break;
                     case OP_KILL: case OP_COLLIDE: case OP_ATTACK:
-                        I.role_a = (unsigned char)role(n.raw[0]); I.role_b = (unsigned char)role(n.raw[1]); break;
-                    case OP_AT: I.role_a = (unsigned char)role(n.raw[0]); I.i0 = n.raw[1]; I.i1 = n.raw[2]; break;
-                    case OP_IN: I.role_a = (unsigned char)role(n.raw[0]);
+                        if (syms[n.raw[1]].index == -2)
+                            fatal("reward rule %d: the object of attack/kill/collide cannot be a group", ri);
+                        subject(I, n.raw[0]); I.role_b = (unsigned char)role(n.raw[1]); break;
+                    case OP_AT: subject(I, n.raw[0]); I.i0 = n.raw[1]; I.i1 = n.raw[2]; break;
+                    case OP_IN: subject(I, n.raw[0]);
                         I.i0 = n.raw[1]; I.i1 = n.raw[2]; I.i2 = n.raw[3]; I.i3 = n.raw[4]; break;
-                    case OP_DIE: I.role_a = (unsigned char)role(n.raw[0]); break;
-                    default: fatal("event op %d is not supported by the B200 engine yet", n.op);
+                    case OP_DIE: subject(I, n.raw[0]); break;
+                    case OP_IN_A_LINE:                 // the reference asserts is_all() (RewardEngine.cc:263)
+                        if (syms[n.raw[0]].index != -2) fatal("reward rule %d: 'in_a_line' needs an 'all' subject", ri);
+                        subject(I, n.raw[0]); break;
+                    case OP_ALIGN:
+                        fatal("reward rule %d: 'align' reads GridWorld::counter_x/counter_y, which the reference never "
+                              "allocates (GridWorld.cc:31, RewardEngine.cc:241-260: null dereference); not supported", ri);
+                    default: fatal("invalid op of EventNode (%d)", n.op);
                 }
                 if (R.n_prog >= MG_MAX_PROG) fatal("reward rule trigger too large");
                 R.prog[R.n_prog++] = I;
             }
-        } lower{nodes_, R, role_of};
+        } lower{nodes_, symbols_, R, role_of, n_allq_, (int)ri};
         lower.go(rd.on);
         if (rd.recv.size() > MG_MAX_RECV) fatal("too many receivers in a reward rule");
         for (size_t q = 0; q < rd.recv.size(); ++q) {
             RuleRecv rc;
             const SymbolDef &sd = symbols_[rd.recv[q]];
+            check_group(sd.group, "reward rule receiver");
             if (sd.index == -2) { rc.role = ROLE_GROUP; rc.group = sd.group; }
-            else { rc.role = role_of(rd.recv[q]); rc.group = sd.group; }
+            else { rc.role = R.dead ? 0 : role_of(rd.recv[q]); rc.group = sd.group; }
             rc.value = rd.values[q];
             R.recv[R.n_recv++] = rc;
         }
@@ -676,6 +694,7 @@ void Engine::to_device() {
     }
     hE_.n_rules = (int)compiled_rules_.size();
     for (int r = 0; r < hE_.n_rules; ++r) hE_.rules[r] = compiled_rules_[r];
+    hE_.n_allq = n_allq_;
     for (int g = 0; g < Gn; ++g) hE_.grp[g].feature_size = feature_size(g);
     curmask_ = 0;
 
@@ -735,6 +754,7 @@ void Engine::to_device() {
             hdr[a].done = done[a] = arenas_[a].done;
             for (int g = 0; g < Gn; ++g) {
                 hdr[a].grp_reward[g] = arenas_[a].groups[g].grp_reward;
+                hdr[a].n_cull[g] = arenas_[a].groups[g].n_cull;
                 n[(size_t)g * A_ + a] = arenas_[a].groups[g].size();
                 dc[(size_t)g * A_ + a] = arenas_[a].groups[g].dead_ct;
             }
@@ -781,6 +801,7 @@ void Engine::to_host(bool keep_device_authoritative) {
         for (int a = 0; a < A_; ++a) {
             arenas_[a].groups[g].dead_ct = dc[(size_t)g * A_ + a];
             arenas_[a].groups[g].grp_reward = hdr[a].grp_reward[g];
+            arenas_[a].groups[g].n_cull = hdr[a].n_cull[g];
         }
     }
     for (int a = 0; a < A_; ++a) {

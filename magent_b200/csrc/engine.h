@@ -46,6 +46,7 @@ struct HostGroup {                      // one group of one arena, in vector ord
     std::vector<float> hp, next_reward, last_reward;
     std::vector<unsigned char> last_op, flags, dir;
     int dead_ct = 0;
+    int n_cull = 0;                     // size after the last clear_dead (reference Agent::index is refreshed only there)
     float grp_reward = 0.0f;
     int size() const { return (int)x.size(); }
     void clear();
@@ -111,6 +112,7 @@ private:
     std::vector<NodeDef> nodes_;
     std::vector<RuleDef> rules_;
     std::vector<RuleDev> compiled_rules_;
+    int n_allq_ = 0;
     bool rules_compiled_ = false;
     bool was_reset_ = false;
     int nsep_ = 1;

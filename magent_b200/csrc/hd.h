@@ -33,6 +33,13 @@ MG_HD int atomic_min(int *p, int v) {
     int o = *p; if (v < o) *p = v; return o;
 #endif
 }
+MG_HD int atomic_max(int *p, int v) {
+#if defined(__CUDA_ARCH__)
+    return atomicMax(p, v);
+#else
+    int o = *p; if (v > o) *p = v; return o;
+#endif
+}
 MG_HD int atomic_add(int *p, int v) {
 #if defined(__CUDA_ARCH__)
     return atomicAdd(p, v);

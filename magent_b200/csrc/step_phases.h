@@ -119,6 +119,7 @@ MG_HD void phase_init(Ctx &c, const EngineDev &E, const StepArgs &S, int a, cons
     if (c.tid() == 0) {
         R.hdr->n_attack = 0;
         R.hdr->rule_trigger = 0;
+        for (int q = 0; q < E.n_allq; ++q) { R.hdr->allq_viol[q] = 0; R.hdr->allq_min[q] = 0x7fffffff; R.hdr->allq_max[q] = -0x7fffffff - 1; }
         R.hdr->rng_next = R.hdr->rng;
         c.add_count(E, CNT_AGENT_STEPS, ord.cnt);
         if (a == 0) c.add_count(E, CNT_STEPS, 1);
@@ -750,9 +751,58 @@ MG_HD void phase_move_fill(Ctx &c, const EngineDev &E, const StepArgs &S, int a,
     }
 }
 
-// phase 10: one reward rule (RewardEngine.cc:216-443 restricted to the shapes the rule compiler accepts:
-// one or two 'any' subjects, each optionally with its op_obj bound to an object symbol)
-MG_HD bool rule_eval(const EngineDev &E, const RuleDev &Ru, unsigned curmask, int a, const int *codes) {
+// ------------------------------------------------------------------------------------------------
+// phase 10: reward rules (reference GridWorld::calc_reward / calc_rule / calc_event_node,
+// GridWorld.cc:681-692, RewardEngine.cc:216-443)
+//
+// Group-quantified event nodes ('all' subject, RewardEngine.cc:223-233,294-343): "every agent of the group,
+// dead-but-unculled ones included, satisfies the predicate".  Reduced once per step and arena into
+// ArenaHdr::allq_*; the binary ops (attack/kill/collide) compare every agent with agent 0 of the group, so
+// the leaf only has to compare agent 0's op_obj with the bound object.
+template <class Ctx>
+MG_HD void phase_rule_allq(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
+    ArenaRef R = arena_ref(E, a);
+    for (int r = 0; r < E.n_rules; ++r) {
+        const RuleDev &Ru = E.rules[r];
+        for (int p = 0; p < Ru.n_prog; ++p) {
+            const RuleInstr &I = Ru.prog[p];
+            if (I.role_a != ROLE_ALL) continue;
+            const int g = I.all_group, n = E.n[g * E.A + a];
+            const AgentSoA &s = cur_soa(E, S.curmask, g);
+            const long b0 = gidx(E, a, g, 0);
+            int viol = 0, mn = 0x7fffffff, mx = -0x7fffffff - 1;
+            int obj0 = -1, vertical = 0, base = 0;
+            if (n > 0 && (I.op == OP_KILL || I.op == OP_ATTACK || I.op == OP_COLLIDE)) obj0 = s.op_obj[b0];
+            if (I.op == OP_IN_A_LINE && n >= 2) {              // RewardEngine.cc:262-292
+                int dx = s.x[b0] - s.x[b0 + 1], dy = s.y[b0] - s.y[b0 + 1];
+                if (dx == 0 && dy != 0) { vertical = 1; base = s.x[b0]; }
+                else if (dx != 0 && dy == 0) { vertical = 0; base = s.y[b0]; }
+                else viol = 1;
+            }
+            for (int i = c.tid(); i < n; i += c.nth()) {
+                const long gi = b0 + i;
+                switch (I.op) {
+                    case OP_KILL: case OP_ATTACK: case OP_COLLIDE:
+                        viol |= !(s.last_op[gi] == I.op && s.op_obj[gi] == obj0); break;
+                    case OP_DIE: viol |= !(s.flags[gi] & FLAG_DEAD); break;
+                    case OP_AT: viol |= !(s.x[gi] == I.i0 && s.y[gi] == I.i1); break;
+                    case OP_IN: { int x = s.x[gi], y = s.y[gi];
+                        viol |= !(x > I.i0 && x < I.i2 && y > I.i1 && y < I.i3); break; }
+                    case OP_IN_A_LINE: {
+                        int fix = vertical ? s.x[gi] : s.y[gi], var = vertical ? s.y[gi] : s.x[gi];
+                        viol |= fix != base;
+                        mn = var < mn ? var : mn; mx = var > mx ? var : mx; break; }
+                    default: break;
+                }
+            }
+            if (viol) atomic_or(&R.hdr->allq_viol[I.allq], 1);
+            if (I.op == OP_IN_A_LINE && mn <= mx) { atomic_min(&R.hdr->allq_min[I.allq], mn); atomic_max(&R.hdr->allq_max[I.allq], mx); }
+        }
+    }
+}
+
+// calc_event_node on the bound entities (postfix program; no short-circuit needed: nodes have no side effects)
+MG_HD bool rule_eval(const EngineDev &E, const ArenaRef &R, const RuleDev &Ru, unsigned curmask, int a, const int *codes) {
     bool stack[MG_MAX_PROG];
     int sp = 0;
     for (int p = 0; p < Ru.n_prog; ++p) {
@@ -762,20 +812,31 @@ MG_HD bool rule_eval(const EngineDev &E, const RuleDev &Ru, unsigned curmask, in
             case OP_OR:  { bool b = stack[--sp]; bool x = stack[--sp]; stack[sp++] = x || b; break; }
             case OP_NOT: { stack[sp - 1] = !stack[sp - 1]; break; }
             default: {
-                int ca = codes[I.role_a];
-                int ga = code_group(ca);
-                const AgentSoA &s = cur_soa(E, curmask, ga);
-                long gi = gidx(E, a, ga, code_index(ca));
                 bool v = false;
-                if (I.op == OP_KILL || I.op == OP_ATTACK || I.op == OP_COLLIDE) {
-                    v = s.last_op[gi] == I.op && s.op_obj[gi] == codes[I.role_b];
-                } else if (I.op == OP_DIE) {
-                    v = (s.flags[gi] & FLAG_DEAD) != 0;
-                } else if (I.op == OP_AT) {
-                    v = s.x[gi] == I.i0 && s.y[gi] == I.i1;
-                } else if (I.op == OP_IN) {
-                    int x = s.x[gi], y = s.y[gi];
-                    v = x > I.i0 && x < I.i2 && y > I.i1 && y < I.i3;
+                if (I.role_a == ROLE_ALL) {
+                    const int g = I.all_group, n = E.n[g * E.A + a];
+                    const bool clean = R.hdr->allq_viol[I.allq] == 0;
+                    if (I.op == OP_KILL || I.op == OP_ATTACK || I.op == OP_COLLIDE)
+                        v = n == 0 || (clean && cur_soa(E, curmask, g).op_obj[gidx(E, a, g, 0)] == codes[I.role_b]);
+                    else if (I.op == OP_IN_A_LINE)
+                        v = n < 2 || (clean && R.hdr->allq_max[I.allq] - R.hdr->allq_min[I.allq] + 1 == n);
+                    else
+                        v = clean;
+                } else {
+                    int ca = codes[I.role_a];
+                    int ga = code_group(ca);
+                    const AgentSoA &s = cur_soa(E, curmask, ga);
+                    long gi = gidx(E, a, ga, code_index(ca));
+                    if (I.op == OP_KILL || I.op == OP_ATTACK || I.op == OP_COLLIDE) {
+                        v = s.last_op[gi] == I.op && s.op_obj[gi] == codes[I.role_b];
+                    } else if (I.op == OP_DIE) {
+                        v = (s.flags[gi] & FLAG_DEAD) != 0;
+                    } else if (I.op == OP_AT) {
+                        v = s.x[gi] == I.i0 && s.y[gi] == I.i1;
+                    } else if (I.op == OP_IN) {
+                        int x = s.x[gi], y = s.y[gi];
+                        v = x > I.i0 && x < I.i2 && y > I.i1 && y < I.i3;
+                    }
                 }
                 stack[sp++] = v;
             }
@@ -785,10 +846,15 @@ MG_HD bool rule_eval(const EngineDev &E, const RuleDev &Ru, unsigned curmask, in
 }
 
 // AgentSymbol::bind_with_check (RewardEngine.cc:14-23) for an inferred object
-MG_HD bool rule_bind(int obj, int group, int index) {
+// Agent::get_index() as the reference keeps it: the position after the last clear_dead, 0 for agents added since
+MG_HD int stale_index(const ArenaRef &R, int code) {
+    int i = code_index(code);
+    return i < R.hdr->n_cull[code_group(code)] ? i : 0;
+}
+MG_HD bool rule_bind(const ArenaRef &R, int obj, int group, int index) {
     if (obj < 0) return false;
     if (code_group(obj) != group) return false;
-    return index == -1 || code_index(obj) == index;
+    return index == -1 || stale_index(R, obj) == index;
 }
 
 MG_HD void rule_pay(const EngineDev &E, const ArenaRef &R, const RuleDev &Ru, unsigned curmask, int a, const int *codes) {
@@ -805,48 +871,65 @@ MG_HD void rule_pay(const EngineDev &E, const ArenaRef &R, const RuleDev &Ru, un
     }
 }
 
+// One rule: the reference's depth-first binding (calc_rule, RewardEngine.cc:373-443) flattened.  The 'all' and
+// fixed-index levels bind the same entities whatever the enclosing loops hold, so they are resolved first (a
+// failed bind there kills the rule for this step); the 'any' levels span a mixed-radix index space that the team
+// strides over -- one level for the shipped games, two for double_attack, O(n^k) in general exactly like the
+// reference.  An agent cannot fill two 'any' levels at once (be_involved, RewardEngine.cc:401-403).
 template <class Ctx>
 MG_HD void phase_reward_rule(Ctx &c, const EngineDev &E, const StepArgs &S, int a, int r) {
     ArenaRef R = arena_ref(E, a);
     const RuleDev &Ru = E.rules[r];
-    const int gA = Ru.sub_group;
-    const int nA = E.n[gA * E.A + a];
-    const AgentSoA &sA = cur_soa(E, S.curmask, gA);
+    if (Ru.dead) return;
+    int codes[2 * MG_MAX_IN];
+    for (int k = 0; k < 2 * MG_MAX_IN; ++k) codes[k] = -1;
+    for (int k = 0; k < Ru.n_in; ++k) {
+        const RuleInput &in = Ru.in[k];
+        if (in.kind == IN_ANY) continue;
+        const int n = E.n[in.group * E.A + a];
+        int who = 0;
+        if (in.kind == IN_FIXED) {
+            if (in.index >= n) return;
+            who = in.index;
+            codes[2 * k] = code_make(in.group, who);
+        }
+        if (in.has_obj) {
+            if (n == 0) return;                       // 'all': the first agent of the group infers (:414-421)
+            int obj = cur_soa(E, S.curmask, in.group).op_obj[gidx(E, a, in.group, who)];
+            if (!rule_bind(R, obj, in.obj_group, in.obj_index)) return;
+            codes[2 * k + 1] = obj;
+        }
+    }
+    long long combos = 1;
+    int radix[MG_MAX_IN];
+    for (int q = 0; q < Ru.n_any; ++q) {
+        radix[q] = E.n[Ru.in[Ru.any_in[q]].group * E.A + a];
+        combos *= radix[q];
+    }
     bool any = false;
-    if (Ru.kind == 0) {
-        for (int i = c.tid(); i < nA; i += c.nth()) {
-            int codes[4] = {code_make(gA, i), -1, -1, -1};
-            if (Ru.has_obj) {
-                codes[ROLE_OBJ_A] = sA.op_obj[gidx(E, a, gA, i)];
-                if (!rule_bind(codes[ROLE_OBJ_A], Ru.obj_group, Ru.obj_index)) continue;
+    for (long long p = c.tid(); p < combos; p += c.nth()) {
+        long long rest = p;
+        bool ok = true;
+        for (int q = Ru.n_any - 1; q >= 0; --q) {
+            const int k = Ru.any_in[q];
+            const RuleInput &in = Ru.in[k];
+            const int i = (int)(rest % radix[q]);
+            rest /= radix[q];
+            codes[2 * k] = code_make(in.group, i);
+            if (in.has_obj) {
+                int obj = cur_soa(E, S.curmask, in.group).op_obj[gidx(E, a, in.group, i)];
+                if (!rule_bind(R, obj, in.obj_group, in.obj_index)) { ok = false; break; }
+                codes[2 * k + 1] = obj;
             }
-            if (!rule_eval(E, Ru, S.curmask, a, codes)) continue;
-            any = true;
-            rule_pay(E, R, Ru, S.curmask, a, codes);
         }
-    } else {
-        // two 'any' subjects: every ordered pair (i, j); an agent cannot fill both roles
-        // (be_involved, RewardEngine.cc:401-403).  O(nA*nB), exact; used by cooperative rules only.
-        const int gB = Ru.sub2_group;
-        const int nB = E.n[gB * E.A + a];
-        const AgentSoA &sB = cur_soa(E, S.curmask, gB);
-        const long pairs = (long)nA * nB;
-        for (long p = c.tid(); p < pairs; p += c.nth()) {
-            int i = (int)(p / nB), j = (int)(p - (long)i * nB);
-            if (gA == gB && i == j) continue;
-            int codes[4] = {code_make(gA, i), -1, code_make(gB, j), -1};
-            if (Ru.has_obj) {
-                codes[ROLE_OBJ_A] = sA.op_obj[gidx(E, a, gA, i)];
-                if (!rule_bind(codes[ROLE_OBJ_A], Ru.obj_group, Ru.obj_index)) continue;
-            }
-            if (Ru.has_obj2) {
-                codes[ROLE_OBJ_B] = sB.op_obj[gidx(E, a, gB, j)];
-                if (!rule_bind(codes[ROLE_OBJ_B], Ru.obj2_group, Ru.obj2_index)) continue;
-            }
-            if (!rule_eval(E, Ru, S.curmask, a, codes)) continue;
-            any = true;
-            rule_pay(E, R, Ru, S.curmask, a, codes);
-        }
+        if (!ok) continue;
+        for (int q = 1; q < Ru.n_any && ok; ++q)
+            for (int q2 = 0; q2 < q; ++q2)
+                if (codes[2 * Ru.any_in[q]] == codes[2 * Ru.any_in[q2]]) ok = false;
+        if (!ok) continue;
+        if (!rule_eval(E, R, Ru, S.curmask, a, codes)) continue;
+        any = true;
+        rule_pay(E, R, Ru, S.curmask, a, codes);
     }
     if (any) atomic_or(&R.hdr->rule_trigger, 1 << r);
 }
@@ -928,6 +1011,10 @@ MG_HD void run_step(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
     c.sync();
     phase_move_fill(c, E, S, a, ord, false);
     c.sync();
+    if (E.n_allq > 0) {
+        phase_rule_allq(c, E, S, a);
+        c.sync();
+    }
     for (int r = 0; r < E.n_rules; ++r) {
         phase_reward_rule(c, E, S, a, r);
         c.sync();
@@ -976,6 +1063,7 @@ MG_HD void run_cull(Ctx &c, const EngineDev &E, unsigned curmask, int a) {
             E.n[g * E.A + a] = total;
             E.dead_ct[g * E.A + a] = 0;
             R.hdr->grp_reward[g] = 0.0f;
+            R.hdr->n_cull[g] = total;
         }
     }
     c.sync();

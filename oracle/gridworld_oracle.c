@@ -395,7 +395,7 @@ static void add_agent(Env *e, int g, int x, int y, int dir) {        /* Map.cc:7
     a->hp = t->hp; a->action = t->n_action; a->last_op = OP_NULL; a->op_obj = -1;
     a->last_reward = 0; a->next_reward = t->step_reward;
     if (G->n == G->cap) { G->cap = G->cap ? 2 * G->cap : 256; G->slot = realloc(G->slot, sizeof(int) * G->cap); }
-    a->index = G->n;
+    a->index = 0;                          /* GridWorld.h:136: index(0); only clear_dead refreshes it (GridWorld.cc:655) */
     G->slot[G->n++] = s;
     paint(e, x, y, bw, bh, s);
 }
@@ -560,6 +560,29 @@ static bool eval_node(Env *e, int no) {
             }
             return true;
         }
+        case OP_IN_A_LINE: {                                           /* RewardEngine.cc:262-292 */
+            Symbol *s = &e->sym[n->raw[0]];
+            if (s->index != -2) die("in_a_line needs an 'all' subject (the reference asserts)", NULL);
+            Group *G = &e->grp[s->group];
+            if (G->n < 2) return true;
+            Agent *a0 = &e->pool[G->slot[0]], *a1 = &e->pool[G->slot[1]];
+            int dx = a0->x - a1->x, dy = a0->y - a1->y;
+            bool vertical;
+            if (dx == 0 && dy != 0) vertical = true;
+            else if (dx != 0 && dy == 0) vertical = false;
+            else return false;
+            int base = vertical ? a0->x : a0->y, mn = vertical ? a0->y : a0->x, mx = mn;
+            for (int i = 1; i < G->n; i++) {
+                Agent *a = &e->pool[G->slot[i]];
+                int var = vertical ? a->y : a->x, fix = vertical ? a->x : a->y;
+                if (var < mn) mn = var;
+                if (var > mx) mx = var;
+                if (fix != base) return false;
+            }
+            return mx - mn + 1 == G->n;
+        }
+        /* OP_ALIGN reads counter_x / counter_y, which the reference never allocates (GridWorld.cc:31): a null
+           dereference there, refused here */
         default: die("event op not restated", NULL);
     }
     return false;

@@ -74,7 +74,60 @@ def random_config(seed):
             cfg.add_reward_rule(gw.Event(a, 'attack', c) & gw.Event(a2, 'attack', c), receiver=[a, a2], value=[0.5, 0.5])
         else:
             cfg.add_reward_rule(gw.Event(a, 'die'), receiver=gw.AgentSymbol(groups[j], 'all'), value=0.25, terminal=bool(rs.rand() < 0.1))
+    if seed >= 1000:
+        general_rules(gw, cfg, rs, groups, syms, size_w, size_h)
     return cfg, dict(w=size_w, h=size_h, n_groups=n_groups, bodies=bodies, turn=turn)
+
+
+def general_rules(gw, cfg, rs, groups, syms, size_w, size_h):
+    """seeds >= 1000 add rules of the general shapes of the reference's binder (RewardEngine.cc:373-443): 'all' and
+    fixed-index subjects, three free symbols, chains that re-bind a subject, group-quantified events"""
+    n_groups = len(groups)
+
+    def rect():
+        if rs.rand() < 0.5:
+            return ((0, 0), (size_w, size_h))                                     # everyone is inside
+        x0, y0 = int(rs.randint(0, size_w // 2)), int(rs.randint(0, size_h // 2))
+        return ((x0, y0), (x0 + int(rs.randint(3, size_w)), y0 + int(rs.randint(3, size_h))))
+
+    for _ in range(int(rs.randint(1, 4))):
+        i, j = (int(v) for v in rs.choice(n_groups, 2, replace=False))
+        a, b = syms[i], syms[j]
+        all_i, all_j = gw.AgentSymbol(groups[i], 'all'), gw.AgentSymbol(groups[j], 'all')
+        fix_i = gw.AgentSymbol(groups[i], int(rs.randint(0, 6)))
+        kind = int(rs.randint(0, 11))
+        if kind == 0:
+            cfg.add_reward_rule(gw.Event(all_i, 'in', rect()), receiver=all_i, value=0.07)
+        elif kind == 1:
+            cfg.add_reward_rule(gw.Event(all_i, 'die'), receiver=all_j, value=1.5, terminal=bool(rs.rand() < 0.5))
+        elif kind == 2:
+            cfg.add_reward_rule(gw.Event(fix_i, 'attack', b), receiver=[fix_i, b], value=[0.4, -0.2])
+        elif kind == 3:                                                           # fixed subject, nothing inferred: never fires
+            cfg.add_reward_rule(gw.Event(fix_i, 'in', rect()), receiver=fix_i, value=9.0)
+        elif kind == 4:
+            cfg.add_reward_rule(gw.Event(all_i, 'attack', b) | gw.Event(all_i, 'kill', b), receiver=[b, all_i], value=[-0.6, 0.2])
+        elif kind == 5:                                                           # three free symbols
+            k = int(rs.choice([x for x in range(n_groups) if x != i]))
+            a2 = gw.AgentSymbol(groups[i], 'any')
+            a3 = gw.AgentSymbol(groups[int(rs.randint(0, n_groups))], 'any')
+            cfg.add_reward_rule(gw.Event(a, 'attack', syms[k]) & gw.Event(a2, 'attack', syms[k]) & gw.Event(a3, 'in', rect()),
+                                receiver=[a, a2, a3], value=[0.5, 0.25, 0.125])
+        elif kind == 6:
+            cfg.add_reward_rule(gw.Event(all_i, 'in_a_line'), receiver=all_i, value=0.3)
+        elif kind == 7:                                                           # chain: the later level re-binds an earlier subject
+            if rs.rand() < 0.5:
+                cfg.add_reward_rule(gw.Event(a, 'attack', b) & gw.Event(b, 'attack', a), receiver=[a, b], value=[0.2, 0.1])
+            else:
+                c = gw.AgentSymbol(groups[j], 'any')
+                ev = gw.Event(c, 'attack', a) & gw.Event(a, 'attack', b) if rs.rand() < 0.5 else gw.Event(a, 'attack', b) & gw.Event(c, 'attack', a)
+                cfg.add_reward_rule(ev, receiver=[a, b, c], value=[0.2, 0.1, 0.05])
+        elif kind == 8:
+            cfg.add_reward_rule(gw.Event(a, 'attack', gw.AgentSymbol(groups[j], int(rs.randint(0, 4)))), receiver=a, value=0.35)
+        elif kind == 9:
+            cfg.add_reward_rule(gw.Event(a, 'attack', b) & ~gw.Event(all_j, 'in', rect()), receiver=[a, all_j], value=[0.15, -0.01])
+        else:                                                                     # 'all' level and fixed level next to a free one
+            cfg.add_reward_rule((gw.Event(all_i, 'collide', b) | gw.Event(fix_i, 'attack', b)) & ~gw.Event(a, 'die'),
+                                receiver=[a, b], value=[0.02, 0.04])
 
 
 def make_env(lib, seed, **kw):

@@ -28,6 +28,7 @@ SCENARIOS = {
     "sector_ranges": (lambda lib: pc.make_sector(lib), 50, 9, {"order": [1, 0]}),
     "turn_mode": (lambda lib: pc.make_turn(lib, 30, 5), 60, 5, {"order": [2, 0, 1], "stop_on_done": False}),
     "food_mode": (lambda lib: pc.make_food(lib, 30, 3), 70, 3, {"order": [1, 2, 0], "stop_on_done": False}),
+    "general_rules": (lambda lib: pc.make_general_rules(lib), 70, 21, {"stop_on_done": False}),
     "gather_infight": (lambda lib: pc.make_gather(lib, 24, 2, n_agent=150, n_food=60), 40, 2, {"act_groups": [1]}),
 }
 FULL_OBS_STEPS = (0, 7)      # steps whose observation tensors are stored in full (others: sha256)

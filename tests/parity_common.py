@@ -415,3 +415,55 @@ def make_arrange(lib, map_size=30, seed=12, n_goal=70, n_agent=160, **kw):
     env.add_agents(h[0], method="random", n=n_goal)
     env.add_agents(h[1], method="random", n=n_agent)
     return env
+
+
+def general_rules_config(size=16):
+    """rule shapes beyond the shipped games (RewardEngine.cc:373-443): 'all' subjects of attack / in_a_line / die /
+    at, a fixed-index subject, a fixed-index object (Agent::index is refreshed by clear_dead only), three free symbols"""
+    import magent_b200 as magent
+    gw = magent.gridworld
+    cfg = gw.Config()
+    cfg.set({"map_width": size, "map_height": size, "minimap_mode": True, "embedding_size": 6})
+    statue = cfg.register_agent_type("statue", dict(width=1, length=1, hp=4, speed=0, damage=0.5, step_recover=0.0,
+                                                    view_range=gw.CircleRange(3), attack_range=gw.CircleRange(1),
+                                                    step_reward=0, kill_reward=0, dead_penalty=-1, attack_penalty=0))
+    target = cfg.register_agent_type("target", dict(width=1, length=1, hp=1000, speed=0, damage=0, step_recover=0.0,
+                                                    view_range=gw.CircleRange(2), attack_range=gw.CircleRange(0),
+                                                    step_reward=0, kill_reward=0, dead_penalty=0, attack_penalty=0))
+    queue = cfg.register_agent_type("queue", dict(width=1, length=1, hp=2, speed=0, damage=0, step_recover=0.0,
+                                                  view_range=gw.CircleRange(2), attack_range=gw.CircleRange(0),
+                                                  step_reward=0, kill_reward=0, dead_penalty=-2, attack_penalty=0))
+    rover = cfg.register_agent_type("rover", dict(width=1, length=1, hp=6, speed=2, damage=1, step_recover=0.05,
+                                                  view_range=gw.CircleRange(4), attack_range=gw.CircleRange(1.5),
+                                                  step_reward=-0.005, kill_reward=1, dead_penalty=-0.5, attack_penalty=-0.01))
+    S, T, Q, R = (cfg.add_group(t) for t in (statue, target, queue, rover))
+    t_any, q_any, r_any = (gw.AgentSymbol(g, 'any') for g in (T, Q, R))
+    r2, r3 = gw.AgentSymbol(R, 'any'), gw.AgentSymbol(R, 'any')
+    all_s, all_t, all_q, all_r = (gw.AgentSymbol(g, 'all') for g in (S, T, Q, R))
+    cfg.add_reward_rule(gw.Event(all_s, 'attack', t_any), receiver=[t_any, all_s], value=[-0.25, 0.5])
+    cfg.add_reward_rule(gw.Event(all_q, 'in_a_line'), receiver=all_q, value=0.3)
+    r_fix = gw.AgentSymbol(R, 2)
+    cfg.add_reward_rule(gw.Event(r_fix, 'attack', q_any), receiver=[r_fix, q_any], value=[0.7, -0.1])
+    cfg.add_reward_rule(gw.Event(r_any, 'kill', gw.AgentSymbol(Q, 1)), receiver=r_any, value=5.0)
+    cfg.add_reward_rule(gw.Event(r_any, 'attack', gw.AgentSymbol(Q, 0)), receiver=r_any, value=0.11)
+    cfg.add_reward_rule(gw.Event(all_t, 'at', (6, 5)), receiver=all_t, value=0.01)
+    cfg.add_reward_rule(gw.Event(r_any, 'attack', q_any) & gw.Event(r2, 'attack', q_any) & gw.Event(r3, 'in', ((0, 0), (size, size // 2))),
+                        receiver=[r_any, r2, r3], value=[0.2, 0.1, 0.05])
+    cfg.add_reward_rule(gw.Event(gw.AgentSymbol(S, 0), 'in', ((0, 0), (size, size))), receiver=all_s, value=99.0)   # never fires
+    cfg.add_reward_rule(gw.Event(all_q, 'die'), receiver=all_r, value=10.0, terminal=True)
+    return cfg
+
+
+def make_general_rules(lib, seed=21, size=16, n_rover=40, **kw):
+    """two statues flank one immobile target (both must hit it in the same step for the 'all' attack rule), a vertical
+    queue that rovers attack until the line breaks, rovers added before AND after the first clear_dead"""
+    import magent_b200 as magent
+    env = magent.GridWorld(general_rules_config(size), _lib=lib, **kw)
+    env.set_seed(seed)
+    env.reset()
+    S, T, Q, R = env.get_handles()
+    env.add_agents(S, method="custom", pos=[[5, 5, 0], [7, 5, 0]])
+    env.add_agents(T, method="custom", pos=[[6, 5, 0]])
+    env.add_agents(Q, method="custom", pos=[[12, 8 + i, 0] for i in range(4)])
+    env.add_agents(R, method="random", n=n_rover)
+    return env

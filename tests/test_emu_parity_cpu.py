@@ -102,13 +102,15 @@ def test_mid_episode_add_agents_roundtrip(emu):
 
 
 def test_unsupported_rule_shapes_fail_loudly(emu):
-    """an 'all' subject is not lowered yet: the engine must abort with a message, not diverge silently"""
-    code = ("import magent_b200 as m; gw = m.gridworld; c = m.builtin.config.battle.get_config(30); "
-            "c.add_reward_rule(gw.Event(gw.AgentSymbol(0, 'all'), 'die'), receiver=gw.AgentSymbol(1, 'all'), value=1); "
-            "e = m.GridWorld(c, _lib=%r); e.reset()" % emu)
+    """'align' reads counters the reference never allocates (a null dereference there): the engine must abort with a
+    message naming the rule, not diverge silently; same for a receiver the trigger does not bind"""
     import sys
-    out = subprocess.run([sys.executable, "-c", code], cwd=pc.REPO, capture_output=True, text=True)
-    assert out.returncode != 0 and "must be 'any'" in out.stderr
+    for rule, msg in (("gw.Event(gw.AgentSymbol(0, 'any'), 'align'), receiver=gw.AgentSymbol(1, 'all')", "'align'"),
+                      ("gw.Event(gw.AgentSymbol(0, 'any'), 'die'), receiver=gw.AgentSymbol(1, 'any')", "not bound")):
+        code = ("import magent_b200 as m; gw = m.gridworld; c = m.builtin.config.battle.get_config(30); "
+                "c.add_reward_rule(%s, value=1); e = m.GridWorld(c, _lib=%r); e.reset()" % (rule, emu))
+        out = subprocess.run([sys.executable, "-c", code], cwd=pc.REPO, capture_output=True, text=True)
+        assert out.returncode != 0 and msg in out.stderr, out.stderr
 
 
 @pytest.mark.parametrize("seed", [13, 14, 15])

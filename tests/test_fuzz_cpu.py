@@ -14,18 +14,18 @@ HAVE_REF = os.path.exists(pc.REF_LIB)
 CHECKER = pc.REF_LIB if HAVE_REF else pc.PORT_LIB
 
 
-@pytest.mark.parametrize("seed", list(range(0, 24)))
+@pytest.mark.parametrize("seed", list(range(0, 24)) + list(range(1000, 1016)))
 def test_emulated_engine_matches_checker_on_random_games(emu, seed):
     fz.play(seed, CHECKER, emu, steps=20)
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="needs oracle/_ref (the compiled reference)")
-@pytest.mark.parametrize("seed", list(range(100, 116)))
+@pytest.mark.parametrize("seed", list(range(100, 116)) + list(range(1100, 1110)))
 def test_oracle_port_matches_reference_on_random_games(seed):
     fz.play(seed, pc.REF_LIB, pc.PORT_LIB, steps=20)
 
 
-@pytest.mark.parametrize("seed", list(range(200, 212)))
+@pytest.mark.parametrize("seed", list(range(200, 212)) + list(range(1200, 1206)))
 def test_emulated_engine_matches_checker_with_an_irregular_caller(emu, seed):
     """skipped clear_dead (dead agents keep slots and still get actions), agents added mid-episode, observations
     not fetched every step"""

@@ -99,6 +99,13 @@ def test_four_groups_sixteen_rules():
     both(lambda lib: pc.make_multi4(lib), 50, 8, order=[3, 1, 0, 2])
 
 
+def test_general_rule_shapes():
+    """'all' subjects (attack / in_a_line / die / at), fixed-index subjects and objects (Agent::index is refreshed by
+    clear_dead only), three free symbols, a rule that can never fire, a terminal group rule (RewardEngine.cc:216-443)"""
+    want = both(lambda lib: pc.make_general_rules(lib), 70, 21, stop_on_done=False)
+    assert any(r["done"] for r in want) and want[-1]["num"][2] == 0
+
+
 @pytest.mark.parametrize("seed", [12, 13])
 def test_absorbing_goals(seed):
     """can_absorb types (train_arrange): the first mover (in move order) that bumps into a free goal dies into it"""
@@ -388,7 +395,7 @@ def test_f16_device_pointer_observation():
     np.testing.assert_array_equal(tf.cpu().numpy().view(np.uint16), f.astype(np.float16).view(np.uint16))
 
 
-@pytest.mark.parametrize("seed", list(range(0, 36)))
+@pytest.mark.parametrize("seed", list(range(0, 36)) + list(range(1000, 1024)))
 def test_random_games_match_checker(seed):
     """randomised differential test (tests/fuzz_common.py): random configs (2-4 groups, long bodies, sector ranges,
     turn / food / goal / minimap modes, absorbers, random rule sets incl. two-subject rules), random placements, call
@@ -397,7 +404,7 @@ def test_random_games_match_checker(seed):
     fz.play(seed, checker_lib(), pc.CUDA_LIB, steps=20)
 
 
-@pytest.mark.parametrize("seed", list(range(300, 312)))
+@pytest.mark.parametrize("seed", list(range(300, 312)) + list(range(1300, 1308)))
 def test_random_games_with_an_irregular_caller(seed):
     """fuzz_common.play_irregular: skipped clear_dead, agents added mid-episode (host <-> device round trips of the
     whole state incl. kind / food planes), observations not fetched every step"""
