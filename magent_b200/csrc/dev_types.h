@@ -16,7 +16,7 @@
 
 namespace mg {
 
-enum { MG_MAX_GROUPS = 8, MG_MAX_RULES = 16, MG_MAX_PROG = 16, MG_MAX_RECV = 4, MG_MAX_IN = 4, MG_MAX_ALLQ = 16 };
+enum { MG_MAX_GROUPS = 8, MG_MAX_RULES = 64, MG_MAX_PROG = 16, MG_MAX_RECV = 4, MG_MAX_IN = 4, MG_MAX_ALLQ = 16 };
 enum { MG_N_COUNTERS = 8 };
 enum Counter { CNT_AGENT_STEPS = 0, CNT_ATTACKS, CNT_HITS, CNT_KILLS, CNT_STARVED,
                CNT_MOVES_OK, CNT_MOVES_BLOCKED, CNT_STEPS };
@@ -85,7 +85,7 @@ struct ArenaHdr {
     int done;
     int n_attack;
     int changed[3];          // rotating "something changed" flags of the relaxation loops
-    int rule_trigger;        // bitmask of rules triggered this step
+    unsigned char rule_trig[MG_MAX_RULES];   // rule r triggered this step (RewardRule::trigger)
     float grp_reward[MG_MAX_GROUPS];
     // Agent::index of the reference is written by clear_dead only (GridWorld.cc:655) and is 0 from the
     // constructor (GridWorld.h:136): agents at positions >= n_cull[g] (added since the last clear_dead) have index 0
@@ -159,7 +159,7 @@ struct EngineDev {
     // shuffle scratch [A][cap_total]
     int *jv, *sh_head, *sh_next, *sh_first, *att_agent;
     int *cl_next;                             // [A][cap_total*max_body] claimant list links
-    int n_rules; RuleDev rules[MG_MAX_RULES];
+    int n_rules; const RuleDev *rules;        // [n_rules] in HBM (read through L2; not part of the per-CTA smem copy)
     int n_allq;                               // group-quantified event nodes over all rules (ArenaHdr::allq_*)
     long long *counters;                      // [MG_N_COUNTERS]
     int *team_scratch;                        // [2 * max CTAs] partial sums of team scans

@@ -681,6 +681,7 @@ void Engine::to_device() {
         hE_.mm_count = (int *)dalloc((size_t)A_ * Gn * max_cells * 4);
         hE_.mm_total = (int *)dalloc((size_t)A_ * Gn * 4);
         d_mm_val_ = (float *)dalloc((size_t)A_ * Gn * max_cells * 4);
+        hE_.rules = (const RuleDev *)dalloc(sizeof(RuleDev) * (compiled_rules_.size() + 1));
         dE_ = (EngineDev *)dalloc(sizeof(EngineDev));
     }
     // constants that may change between episodes without a re-allocation
@@ -693,7 +694,7 @@ void Engine::to_device() {
         for (int b = 0; b < 32; ++b) { hE_.pow2[b] = p; p = mulmod31(p, p); }
     }
     hE_.n_rules = (int)compiled_rules_.size();
-    for (int r = 0; r < hE_.n_rules; ++r) hE_.rules[r] = compiled_rules_[r];
+    if (hE_.n_rules) be::h2d((void *)hE_.rules, compiled_rules_.data(), sizeof(RuleDev) * compiled_rules_.size());
     hE_.n_allq = n_allq_;
     for (int g = 0; g < Gn; ++g) hE_.grp[g].feature_size = feature_size(g);
     curmask_ = 0;

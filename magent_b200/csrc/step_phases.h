@@ -118,7 +118,7 @@ MG_HD void phase_init(Ctx &c, const EngineDev &E, const StepArgs &S, int a, cons
     }
     if (c.tid() == 0) {
         R.hdr->n_attack = 0;
-        R.hdr->rule_trigger = 0;
+        for (int r = 0; r < E.n_rules; ++r) R.hdr->rule_trig[r] = 0;
         for (int q = 0; q < E.n_allq; ++q) { R.hdr->allq_viol[q] = 0; R.hdr->allq_min[q] = 0x7fffffff; R.hdr->allq_max[q] = -0x7fffffff - 1; }
         R.hdr->rng_next = R.hdr->rng;
         c.add_count(E, CNT_AGENT_STEPS, ord.cnt);
@@ -931,7 +931,7 @@ MG_HD void phase_reward_rule(Ctx &c, const EngineDev &E, const StepArgs &S, int 
         any = true;
         rule_pay(E, R, Ru, S.curmask, a, codes);
     }
-    if (any) atomic_or(&R.hdr->rule_trigger, 1 << r);
+    if (any) R.hdr->rule_trig[r] = 1;             // every writer stores the same byte
 }
 
 // phase 11: game-over check (GridWorld.cc:618-630) and rng commit
@@ -944,7 +944,7 @@ MG_HD void phase_done(Ctx &c, const EngineDev &E, int a) {
         if (E.n[g * E.A + a] - E.dead_ct[g * E.A + a] > 0) ++live;
     int done = live < E.G;
     for (int r = 0; r < E.n_rules; ++r)
-        if (((R.hdr->rule_trigger >> r) & 1) && E.rules[r].is_terminal) done = 1;
+        if (R.hdr->rule_trig[r] && E.rules[r].is_terminal) done = 1;
     R.hdr->done = done;
     E.done[a] = done;
     R.hdr->rng = R.hdr->rng_next;

@@ -467,3 +467,21 @@ def make_general_rules(lib, seed=21, size=16, n_rover=40, **kw):
     env.add_agents(Q, method="custom", pos=[[12, 8 + i, 0] for i in range(4)])
     env.add_agents(R, method="random", n=n_rover)
     return env
+
+
+def make_many_rules(lib, size=30, n=120, seed=5, n_rules=40, **kw):
+    """battle with 40 reward rules (the reference has no limit; the device keeps the rule table in HBM)"""
+    import magent_b200 as magent
+    gw = magent.gridworld
+    cfg = magent.builtin.config.battle.get_config(size)
+    a, b = gw.AgentSymbol(0, 'any'), gw.AgentSymbol(1, 'any')
+    for k in range(n_rules):
+        s, o = (a, b) if k % 2 == 0 else (b, a)
+        ev = gw.Event(s, 'attack', o) if k % 3 else gw.Event(s, 'in', ((k % 7, k % 5), (size - k % 4, size - k % 6)))
+        cfg.add_reward_rule(ev, receiver=s, value=0.001 * (k + 1))
+    env = magent.GridWorld(cfg, _lib=lib, **kw)
+    env.set_seed(seed)
+    env.reset()
+    for h in env.get_handles():
+        env.add_agents(h, method="random", n=n)
+    return env

@@ -101,6 +101,14 @@ def test_mid_episode_add_agents_roundtrip(emu):
     assert run(ref) == run(emu)
 
 
+def test_forty_rules(emu):
+    if not os.path.exists(pc.REF_LIB):
+        pytest.skip("needs the compiled reference")
+    want = pc.run_trace(pc.make_many_rules(pc.REF_LIB), 25, 5, keep_obs=True)
+    got = pc.run_trace(pc.make_many_rules(emu), 25, 5, keep_obs=True)
+    pc.compare_traces(want, got, "many rules")
+
+
 def test_unsupported_rule_shapes_fail_loudly(emu):
     """'align' reads counters the reference never allocates (a null dereference there): the engine must abort with a
     message naming the rule, not diverge silently; same for a receiver the trigger does not bind"""

@@ -106,6 +106,10 @@ def test_general_rule_shapes():
     assert any(r["done"] for r in want) and want[-1]["num"][2] == 0
 
 
+def test_forty_rules():
+    both(lambda lib: pc.make_many_rules(lib), 25, 5)
+
+
 @pytest.mark.parametrize("seed", [12, 13])
 def test_absorbing_goals(seed):
     """can_absorb types (train_arrange): the first mover (in move order) that bumps into a free goal dies into it"""
