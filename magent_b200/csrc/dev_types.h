@@ -84,6 +84,7 @@ struct ArenaHdr {
     uint32_t rng_next;
     int done;
     int n_attack;
+    int any_dead;            // some agent of this arena carries FLAG_DEAD (set where it dies, cleared by the cull)
     int changed[3];          // rotating "something changed" flags of the relaxation loops
     unsigned char rule_trig[MG_MAX_RULES];   // rule r triggered this step (RewardRule::trigger)
     float grp_reward[MG_MAX_GROUPS];

@@ -768,6 +768,7 @@ void Engine::to_device() {
     }
     be::h2d(dE_, &hE_, sizeof(EngineDev));
     ++state_version_;
+    may_have_dead_ = true;                            // conservative: the first clear_dead after an upload re-reads the counts
     where_ = DEVICE;
 }
 
@@ -900,7 +901,7 @@ void Engine::step(int *done) {                                        // GridWor
     std::vector<int> d(A_);
     be::d2h(d.data(), hE_.done, (size_t)A_ * 4);
     int all = 1;
-    for (int a = 0; a < A_; ++a) { arenas_[a].done = d[a]; all &= d[a] != 0; }
+    for (int a = 0; a < A_; ++a) { arenas_[a].done = d[a] & 1; all &= arenas_[a].done; may_have_dead_ |= (d[a] & 2) != 0; }
     *done = all;
     if (!first_render_) collect_attack_events();
 }
@@ -921,6 +922,8 @@ void Engine::clear_dead() {                                           // GridWor
     be::launch_cull(dE_, hE_, curmask_, max_agents_per_arena());
     ++state_version_;
     curmask_ ^= (1u << G()) - 1u;
+    if (!may_have_dead_) return;                      // nobody died since the last cull: counts and offsets stand
+    may_have_dead_ = false;
     be::launch_offsets(dE_, hE_);
     be::d2h(h_off_.data(), hE_.off, h_off_.size() * 4);
 }

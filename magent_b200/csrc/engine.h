@@ -113,6 +113,7 @@ private:
     std::vector<RuleDef> rules_;
     std::vector<RuleDev> compiled_rules_;
     int n_allq_ = 0;
+    bool may_have_dead_ = true;         // some arena reported dead agents since the last clear_dead (bit 1 of EngineDev::done)
     bool rules_compiled_ = false;
     bool was_reset_ = false;
     int nsep_ = 1;

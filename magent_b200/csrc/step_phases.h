@@ -411,6 +411,7 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
         s.hp[gi] = hp;
         if (dies) {
             s.flags[gi] |= FLAG_DEAD;
+            R.hdr->any_dead = 1;
             s.next_reward[gi] = G.dead_penalty;          // assignment (GridWorld.h:206)
             if (self_kill) s.next_reward[gi] += late_reward;
             int x = s.x[gi], y = s.y[gi], bw, bh;
@@ -671,6 +672,7 @@ MG_HD void phase_move_collide(Ctx &c, const EngineDev &E, const StepArgs &S, int
             const AgentSoA &s = cur_soa(E, S.curmask, g);
             const long gi = gidx(E, a, g, i);
             s.flags[gi] |= FLAG_DEAD;             // set_dead(true): no dead_penalty, dead_ct untouched (reference quirk)
+            R.hdr->any_dead = 1;
             s.last_op[gi] = OP_COLLIDE;
             s.op_obj[gi] = obj;
             continue;
@@ -946,7 +948,9 @@ MG_HD void phase_done(Ctx &c, const EngineDev &E, int a) {
     for (int r = 0; r < E.n_rules; ++r)
         if (R.hdr->rule_trig[r] && E.rules[r].is_terminal) done = 1;
     R.hdr->done = done;
-    E.done[a] = done;
+    // bit 1 tells the host whether this arena holds dead agents: when no arena does, clear_dead cannot change a
+    // count and the host skips re-reading the offsets (one blocking copy less per step)
+    E.done[a] = done | (R.hdr->any_dead ? 2 : 0);
     R.hdr->rng = R.hdr->rng_next;
 }
 
@@ -1064,6 +1068,7 @@ MG_HD void run_cull(Ctx &c, const EngineDev &E, unsigned curmask, int a) {
             E.dead_ct[g * E.A + a] = 0;
             R.hdr->grp_reward[g] = 0.0f;
             R.hdr->n_cull[g] = total;
+            R.hdr->any_dead = 0;
         }
     }
     c.sync();
