@@ -20,6 +20,9 @@
 #include <vector>
 
 #include "backend.h"
+#if defined(MG_PHASE_TIMING)
+namespace mg { __device__ long long mg_phase_clock[8 * 16]; }
+#endif
 #include "obs_phases.h"
 
 namespace cg = cooperative_groups;
@@ -42,6 +45,12 @@ static std::vector<cudaEvent_t> g_events;     // pairs recorded around obs-rende
 static size_t g_events_used = 0;
 
 const char *name() { return "cuda-sm_100a"; }
+
+#if defined(MG_PHASE_TIMING)
+extern "C" __attribute__((visibility("default"))) void magent_b200_debug_phase_clocks(long long *out) {
+    CUDA_CHECK(cudaMemcpyFromSymbol(out, mg::mg_phase_clock, sizeof(long long) * 8 * 16));
+}
+#endif
 
 int device_count() {
     int n = 0;

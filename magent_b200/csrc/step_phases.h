@@ -958,7 +958,7 @@ MG_HD void phase_done(Ctx &c, const EngineDev &E, int a) {
 // rotating flag triple makes the reset of the next flag race-free.  The flags live where the
 // team can see them cheaply: shared memory for a CTA team, the arena header in HBM for the grid team.
 template <class Ctx, class Sweep>
-MG_HD void relax_until_stable(Ctx &c, int *flags, Sweep sweep) {
+MG_HD int relax_until_stable(Ctx &c, int *flags, Sweep sweep) {
     if (c.tid() == 0) { st_volatile(&flags[0], 0); st_volatile(&flags[1], 0); st_volatile(&flags[2], 0); }
     c.sync();
     for (int it = 0;; ++it) {
@@ -966,9 +966,19 @@ MG_HD void relax_until_stable(Ctx &c, int *flags, Sweep sweep) {
         if (c.tid() == 0) st_volatile(&flags[nxt], 0);
         if (sweep()) st_volatile(&flags[cur], 1);
         c.sync();
-        if (!ld_volatile(&flags[cur])) break;
+        if (!ld_volatile(&flags[cur])) return it + 1;
     }
 }
+
+// MG_PHASE_TIMING (profiling variants only, profiles/build_variant.sh -DMG_PHASE_TIMING): thread 0 of the team
+// stamps the SM clock after every phase of the first arenas into a device array the profiling script reads back
+#if defined(MG_PHASE_TIMING) && defined(__CUDA_ARCH__)
+#define MG_MARK(k) do { if (c.tid() == 0 && a < 8) mg_phase_clock[a * 16 + (k)] = clock64(); } while (0)
+#define MG_MARKV(k, v) do { if (c.tid() == 0 && a < 8) mg_phase_clock[a * 16 + (k)] = (v); } while (0)
+#else
+#define MG_MARK(k) do { } while (0)
+#define MG_MARKV(k, v) do { (void)(v); } while (0)
+#endif
 
 // the whole step for one arena (reference GridWorld::step, GridWorld.cc:456-631)
 template <class Ctx>
@@ -981,18 +991,26 @@ MG_HD void run_step(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
     if (c.is_cta_leader()) { enum_all(E, a, en[0]); enum_order(E, S, a, en[1]); }
     c.sync_cta();
     const GroupEnum &all = en[0], &ord = en[1];
+    MG_MARK(0);
     phase_init(c, E, S, a, all, ord);
     c.sync();
+    MG_MARK(1);
     int n_attack = phase_attack_scan(c, E, S, a, ord);
     c.sync();
+    MG_MARK(2);
     if (n_attack > 0) {
         phase_rng(c, E, a, n_attack);
         c.sync();
+        MG_MARK(3);
         phase_rank_target(c, E, S, a, n_attack);
-        relax_until_stable(c, flags, [&]() { return phase_attack_relax(c, E, S, a, all); });
+        MG_MARK(4);
+        int sweeps = relax_until_stable(c, flags, [&]() { return phase_attack_relax(c, E, S, a, all); });
+        MG_MARKV(14, sweeps);
     }
+    MG_MARK(5);
     phase_attack_apply_starve(c, E, S, a, all);
     c.sync();
+    MG_MARK(6);
     if (E.food_mode && n_attack > 0) {
         phase_food_commit(c, E, S, a, all, false);
         c.sync();
@@ -1008,13 +1026,19 @@ MG_HD void run_step(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
         c.sync();
     }
     phase_move_register(c, E, S, a, ord, false);
-    relax_until_stable(c, flags, [&]() { return phase_move_relax(c, E, S, a, ord, false); });
+    MG_MARK(7);
+    int mv_sweeps = relax_until_stable(c, flags, [&]() { return phase_move_relax(c, E, S, a, ord, false); });
+    MG_MARKV(15, mv_sweeps);
+    MG_MARK(8);
     phase_move_collide(c, E, S, a, ord);
     c.sync();
+    MG_MARK(9);
     phase_move_clear(c, E, S, a, ord);
     c.sync();
+    MG_MARK(10);
     phase_move_fill(c, E, S, a, ord, false);
     c.sync();
+    MG_MARK(11);
     if (E.n_allq > 0) {
         phase_rule_allq(c, E, S, a);
         c.sync();
@@ -1023,9 +1047,11 @@ MG_HD void run_step(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
         phase_reward_rule(c, E, S, a, r);
         c.sync();
     }
+    MG_MARK(12);
     phase_done(c, E, a);
     c.flush_counts(E);
     c.sync();
+    MG_MARK(13);
 }
 
 // clear_dead for one arena: stable compaction of every group into the other SoA buffer
