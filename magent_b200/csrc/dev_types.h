@@ -100,7 +100,8 @@ struct ArenaHdr {
 // (RewardEngine.cc:373-443); input k writes its subject symbol (role 2k) and then the symbol inferred from the
 // subject's op_obj (role 2k+1).  A symbol's entity at the leaf is the LAST write to it, resolved at compile time.
 enum { ROLE_GROUP = 254, ROLE_ALL = 255 };      // a whole group as receiver / an 'all' subject of an event node
-enum { IN_ANY = 0, IN_ALL = 1, IN_FIXED = 2 };  // AgentSymbol::index -1 / -2 / >= 0
+enum { IN_ANY = 0, IN_ALL = 1, IN_FIXED = 2 };
+enum { RULE_GENERAL = 0, RULE_ONE_ANY = 1, RULE_DEAD = 2 };   // EngineDev::rule_shape  // AgentSymbol::index -1 / -2 / >= 0
 
 struct RuleInstr {           // postfix program over the bound entities
     unsigned char op;        // EventOp
@@ -161,6 +162,8 @@ struct EngineDev {
     int *jv, *sh_head, *sh_next, *sh_first, *att_agent;
     int *cl_next;                             // [A][cap_total*max_body] claimant list links
     int n_rules; const RuleDev *rules;        // [n_rules] in HBM (read through L2; not part of the per-CTA smem copy)
+    unsigned char rule_shape[MG_MAX_RULES];   // RULE_*: what phase_reward_rule needs before touching the table
+    unsigned char rule_terminal[MG_MAX_RULES];
     int n_allq;                               // group-quantified event nodes over all rules (ArenaHdr::allq_*)
     long long *counters;                      // [MG_N_COUNTERS]
     int *team_scratch;                        // [2 * max CTAs] partial sums of team scans

@@ -696,6 +696,11 @@ void Engine::to_device() {
     hE_.n_rules = (int)compiled_rules_.size();
     if (hE_.n_rules) be::h2d((void *)hE_.rules, compiled_rules_.data(), sizeof(RuleDev) * compiled_rules_.size());
     hE_.n_allq = n_allq_;
+    for (int r = 0; r < hE_.n_rules; ++r) {
+        const RuleDev &R = compiled_rules_[r];
+        hE_.rule_shape[r] = R.dead ? RULE_DEAD : (R.n_in == 1 && R.n_any == 1) ? RULE_ONE_ANY : RULE_GENERAL;
+        hE_.rule_terminal[r] = R.is_terminal ? 1 : 0;
+    }
     for (int g = 0; g < Gn; ++g) hE_.grp[g].feature_size = feature_size(g);
     curmask_ = 0;
 

@@ -69,6 +69,26 @@ MG_HD void atomic_add64(long long *p, long long v) {
 #endif
 }
 
+// Per-thread "this item needs no further sweeps" marks of a relaxation (phase_move_relax).  Device: one register,
+// the first 32 items of the thread (a 512-thread team visits ~4 movers per thread).  Host emulation (one thread
+// visits every mover): unbounded, so the CPU test-suite exercises the same skipping logic on every mover.
+#if defined(__CUDACC__)
+struct SettledMask {
+    unsigned bits = 0;
+    MG_HD bool get(int j) const { return j < 32 && ((bits >> j) & 1u); }
+    MG_HD void set(int j) { if (j < 32) bits |= 1u << j; }
+};
+#else
+}  // namespace mg
+#include <vector>
+namespace mg {
+struct SettledMask {
+    std::vector<bool> v;
+    bool get(int j) const { return j < (int)v.size() && v[j]; }
+    void set(int j) { if (j >= (int)v.size()) v.resize(j + 1, false); v[j] = true; }
+};
+#endif
+
 // loads that must observe in-place updates made by other threads during a relaxation sweep
 MG_HD int ld_volatile(const int *p) { return *(const volatile int *)p; }
 MG_HD unsigned char ld_volatile(const unsigned char *p) { return *(const volatile unsigned char *)p; }

@@ -537,13 +537,17 @@ MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, in
 
 // who stands on cell (cx,cy) when the mover with order key `key` takes its turn?  -1 = nobody.
 // `self` (local flat id) is ignored.  Reads mover states with volatile loads.
-MG_HD int occupant_at_turn(const EngineDev &E, const ArenaRef &R, unsigned curmask, int cx, int cy, unsigned key, int self, bool turn) {
+// `stable` is cleared when the answer rests on the state of a mover that a later sweep may still change (an
+// earlier-keyed mover that has not been refused for good): answers that stay stable need no re-evaluation.
+MG_HD int occupant_at_turn(const EngineDev &E, const ArenaRef &R, unsigned curmask, int cx, int cy, unsigned key, int self, bool turn,
+                           bool &stable) {
     int cell = cy * E.W + cx;
     int o = R.occ[cell];
     if (o >= 0) {
         int fo = lflat(E, o);
         if (fo != self) {
             const unsigned char so = ld_volatile(&E.mv_state[R.sb + fo]);
+            if (so >= MV_PENDING_FAIL && E.mv_key[R.sb + fo] < key) stable = false;   // PENDING_FAIL / OK / ABSORBED / SKIPPED may flip
             if (so == MV_ABSORBED && E.mv_key[R.sb + fo] < key) goto claimants;     // it died into an absorber: cell vacated
             bool left = so == MV_OK && E.mv_key[R.sb + fo] < key;
             if (left) {
@@ -558,8 +562,10 @@ MG_HD int occupant_at_turn(const EngineDev &E, const ArenaRef &R, unsigned curma
 claimants:
     for (int node = R.claim[cell]; node != -1; node = E.cl_next[R.nb + node]) {
         int fm = node_owner(E, node);
-        if (fm != self && E.mv_key[R.sb + fm] < key && ld_volatile(&E.mv_state[R.sb + fm]) == MV_OK)
-            return fm;
+        if (fm != self && E.mv_key[R.sb + fm] < key) {
+            stable = false;
+            if (ld_volatile(&E.mv_state[R.sb + fm]) == MV_OK) return fm;
+        }
     }
     return -1;
 }
@@ -567,10 +573,17 @@ claimants:
 // phase 7 (swept until stable): a mover succeeds iff all its target cells are free at its turn
 // (Map::do_move / is_blank_area, Map.cc:313-358,454-470)
 template <class Ctx>
-MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord, bool turn) {
+MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord, bool turn,
+                            SettledMask &settled) {
     ArenaRef R = arena_ref(E, a);
     bool changed = false;
+    // `settled` is private to the thread and lives across the sweeps of one relaxation: bit j = the thread's j-th
+    // mover got an answer that no later sweep can change (occupant_at_turn's `stable`), so it is not looked at again.
+    // A thread visits the same movers in the same order in every sweep.
+    int j = -1;
     for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
+        ++j;
+        if (settled.get(j)) continue;
         int k, i; enum_locate(ord, idx, k, i);
         int g = ord.grp[k];
         const GroupDev &G = E.grp[g];
@@ -603,10 +616,12 @@ MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a
         if (skipped) {
             ns = MV_SKIPPED;
         } else if (!E.any_absorb || turn) {
+            bool stable = true;
             for (int bx = 0; bx < bw && ok; ++bx)
                 for (int by = 0; by < bh && ok; ++by)
-                    if (occupant_at_turn(E, R, S.curmask, nx + bx, ny + by, key, fs, turn) != -1) ok = false;
+                    if (occupant_at_turn(E, R, S.curmask, nx + bx, ny + by, key, fs, turn, stable) != -1) ok = false;
             ns = ok ? MV_OK : MV_PENDING_FAIL;
+            if (stable) settled.set(j);
         } else {
             // Map::do_move with can_absorb types (Map.cc:334-349): the first other agent in the footprint decides
             int hit = -1, hit_cell = -1;
@@ -614,7 +629,8 @@ MG_HD bool phase_move_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int a
                 for (int by = 0; by < bh; ++by) {
                     const int cell = (ny + by) * E.W + nx + bx;
                     if (R.occ[cell] <= OCC_WALL) { ok = false; continue; }
-                    const int o = occupant_at_turn(E, R, S.curmask, nx + bx, ny + by, key, fs, false);
+                    bool unused = true;
+                    const int o = occupant_at_turn(E, R, S.curmask, nx + bx, ny + by, key, fs, false, unused);
                     if (o != -1) { ok = false; if (hit == -1) { hit = o; hit_cell = cell; } }
                 }
             ns = ok ? MV_OK : MV_PENDING_FAIL;
@@ -682,9 +698,10 @@ MG_HD void phase_move_collide(Ctx &c, const EngineDev &E, const StepArgs &S, int
         int bw, bh;
         mover_dims(E, G, cur_soa(E, S.curmask, g), gidx(E, a, g, i), false, bw, bh);
         int hit = -1;
+        bool unused = true;
         for (int bx = 0; bx < bw && hit == -1; ++bx)
             for (int by = 0; by < bh && hit == -1; ++by)
-                hit = occupant_at_turn(E, R, S.curmask, nx + bx, ny + by, key, fs, false);
+                hit = occupant_at_turn(E, R, S.curmask, nx + bx, ny + by, key, fs, false, unused);
         if (hit != -1) {
             int hg = 0;
             while (hg + 1 < E.G && hit >= E.grp[hg + 1].foff) ++hg;
@@ -882,8 +899,31 @@ template <class Ctx>
 MG_HD void phase_reward_rule(Ctx &c, const EngineDev &E, const StepArgs &S, int a, int r) {
     ArenaRef R = arena_ref(E, a);
     const RuleDev &Ru = E.rules[r];
-    if (Ru.dead) return;
+    const int shape = E.rule_shape[r];                  // per-CTA copy: the rule table itself lives in HBM
+    if (shape == RULE_DEAD) return;
     int codes[2 * MG_MAX_IN];
+    bool any = false;
+    if (shape == RULE_ONE_ANY) {
+        // one free subject, optionally binding its op_obj: every shipped game's rules.  One thread per subject.
+        const RuleInput in = Ru.in[0];
+        const int n = E.n[in.group * E.A + a];
+        const AgentSoA &s = cur_soa(E, S.curmask, in.group);
+        const long b0 = gidx(E, a, in.group, 0);
+        for (int i = c.tid(); i < n; i += c.nth()) {
+            codes[1] = -1;
+            if (in.has_obj) {
+                const int obj = s.op_obj[b0 + i];
+                if (!rule_bind(R, obj, in.obj_group, in.obj_index)) continue;
+                codes[1] = obj;
+            }
+            codes[0] = code_make(in.group, i);
+            if (!rule_eval(E, R, Ru, S.curmask, a, codes)) continue;
+            any = true;
+            rule_pay(E, R, Ru, S.curmask, a, codes);
+        }
+        if (any) R.hdr->rule_trig[r] = 1;
+        return;
+    }
     for (int k = 0; k < 2 * MG_MAX_IN; ++k) codes[k] = -1;
     for (int k = 0; k < Ru.n_in; ++k) {
         const RuleInput &in = Ru.in[k];
@@ -908,7 +948,6 @@ MG_HD void phase_reward_rule(Ctx &c, const EngineDev &E, const StepArgs &S, int 
         radix[q] = E.n[Ru.in[Ru.any_in[q]].group * E.A + a];
         combos *= radix[q];
     }
-    bool any = false;
     for (long long p = c.tid(); p < combos; p += c.nth()) {
         long long rest = p;
         bool ok = true;
@@ -946,7 +985,7 @@ MG_HD void phase_done(Ctx &c, const EngineDev &E, int a) {
         if (E.n[g * E.A + a] - E.dead_ct[g * E.A + a] > 0) ++live;
     int done = live < E.G;
     for (int r = 0; r < E.n_rules; ++r)
-        if (R.hdr->rule_trig[r] && E.rules[r].is_terminal) done = 1;
+        if (E.rule_terminal[r] && R.hdr->rule_trig[r]) done = 1;
     R.hdr->done = done;
     // bit 1 tells the host whether this arena holds dead agents: when no arena does, clear_dead cannot change a
     // count and the host skips re-reading the offsets (one blocking copy less per step)
@@ -1019,7 +1058,8 @@ MG_HD void run_step(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
     }
     if (E.turn_mode) {                                   // GridWorld.cc:544-571: all turns, then all moves
         phase_move_register(c, E, S, a, ord, true);
-        relax_until_stable(c, flags, [&]() { return phase_move_relax(c, E, S, a, ord, true); });
+        SettledMask turn_settled;
+        relax_until_stable(c, flags, [&]() { return phase_move_relax(c, E, S, a, ord, true, turn_settled); });
         phase_move_clear(c, E, S, a, ord);
         c.sync();
         phase_move_fill(c, E, S, a, ord, true);
@@ -1027,7 +1067,8 @@ MG_HD void run_step(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
     }
     phase_move_register(c, E, S, a, ord, false);
     MG_MARK(7);
-    int mv_sweeps = relax_until_stable(c, flags, [&]() { return phase_move_relax(c, E, S, a, ord, false); });
+    SettledMask mv_settled;
+    int mv_sweeps = relax_until_stable(c, flags, [&]() { return phase_move_relax(c, E, S, a, ord, false, mv_settled); });
     MG_MARKV(15, mv_sweeps);
     MG_MARK(8);
     phase_move_collide(c, E, S, a, ord);
