@@ -101,7 +101,8 @@ struct ArenaHdr {
 // subject's op_obj (role 2k+1).  A symbol's entity at the leaf is the LAST write to it, resolved at compile time.
 enum { ROLE_GROUP = 254, ROLE_ALL = 255 };      // a whole group as receiver / an 'all' subject of an event node
 enum { IN_ANY = 0, IN_ALL = 1, IN_FIXED = 2 };
-enum { RULE_GENERAL = 0, RULE_ONE_ANY = 1, RULE_DEAD = 2 };   // EngineDev::rule_shape  // AgentSymbol::index -1 / -2 / >= 0
+enum { RULE_GENERAL = 0, RULE_ONE_ANY = 1, RULE_DEAD = 2 };
+enum { MG_HOT_RULES = 16, MG_HOT_PROG = 4, MG_HOT_RECV = 2 };   // rules whose program also fits the per-CTA copy   // EngineDev::rule_shape  // AgentSymbol::index -1 / -2 / >= 0
 
 struct RuleInstr {           // postfix program over the bound entities
     unsigned char op;        // EventOp
@@ -128,6 +129,24 @@ struct RuleDev {
     int n_prog; RuleInstr prog[MG_MAX_PROG];
     int n_recv; RuleRecv recv[MG_MAX_RECV];
     int is_terminal;
+};
+
+// the part of a rule every thread reads every step, kept in the per-CTA copy of EngineDev (shared memory)
+struct RuleHot {
+    unsigned char shape;     // RULE_*
+    unsigned char terminal;
+    unsigned char group;     // RULE_ONE_ANY: the subject's group ...
+    unsigned char has_obj;   // ... and the symbol bound from its op_obj
+    int obj_group, obj_index;
+    int simple_op;           // RULE_ONE_ANY whose trigger is the single node op(subject, inferred object): the verdict is
+                             // last_op == simple_op (op_obj equals the bound object by construction); 0 = evaluate the program
+};
+// trigger program and receivers of the first MG_HOT_RULES rules when they are small enough (every shipped game's are):
+// a candidate that passes the bind evaluates and pays from shared memory instead of walking the HBM table
+struct RuleSmall {
+    int n_prog, n_recv;      // n_prog < 0: does not fit, use EngineDev::rules[r]
+    RuleInstr prog[MG_HOT_PROG];
+    RuleRecv recv[MG_HOT_RECV];
 };
 
 struct EngineDev {
@@ -162,8 +181,8 @@ struct EngineDev {
     int *jv, *sh_head, *sh_next, *sh_first, *att_agent;
     int *cl_next;                             // [A][cap_total*max_body] claimant list links
     int n_rules; const RuleDev *rules;        // [n_rules] in HBM (read through L2; not part of the per-CTA smem copy)
-    unsigned char rule_shape[MG_MAX_RULES];   // RULE_*: what phase_reward_rule needs before touching the table
-    unsigned char rule_terminal[MG_MAX_RULES];
+    RuleSmall rule_small[MG_HOT_RULES];
+    RuleHot rule_hot[MG_MAX_RULES];           // what phase_reward_rule / phase_done need without touching the table
     int n_allq;                               // group-quantified event nodes over all rules (ArenaHdr::allq_*)
     long long *counters;                      // [MG_N_COUNTERS]
     int *team_scratch;                        // [2 * max CTAs] partial sums of team scans

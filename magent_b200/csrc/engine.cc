@@ -698,8 +698,25 @@ void Engine::to_device() {
     hE_.n_allq = n_allq_;
     for (int r = 0; r < hE_.n_rules; ++r) {
         const RuleDev &R = compiled_rules_[r];
-        hE_.rule_shape[r] = R.dead ? RULE_DEAD : (R.n_in == 1 && R.n_any == 1) ? RULE_ONE_ANY : RULE_GENERAL;
-        hE_.rule_terminal[r] = R.is_terminal ? 1 : 0;
+        RuleHot &H = hE_.rule_hot[r];
+        H.shape = R.dead ? RULE_DEAD : (R.n_in == 1 && R.n_any == 1) ? RULE_ONE_ANY : RULE_GENERAL;
+        H.terminal = R.is_terminal ? 1 : 0;
+        H.group = (unsigned char)R.in[0].group; H.has_obj = (unsigned char)R.in[0].has_obj;
+        H.obj_group = R.in[0].obj_group; H.obj_index = R.in[0].obj_index;
+        H.simple_op = 0;
+        if (H.shape == RULE_ONE_ANY && R.in[0].has_obj && R.n_prog == 1 && R.prog[0].role_a == 0 && R.prog[0].role_b == 1 &&
+            (R.prog[0].op == OP_KILL || R.prog[0].op == OP_ATTACK || R.prog[0].op == OP_COLLIDE))
+            H.simple_op = R.prog[0].op;
+        if (r < MG_HOT_RULES) {
+            RuleSmall &Sm = hE_.rule_small[r];
+            memset(&Sm, 0, sizeof Sm);
+            Sm.n_prog = -1;
+            if (R.n_prog <= MG_HOT_PROG && R.n_recv <= MG_HOT_RECV) {
+                Sm.n_prog = R.n_prog; Sm.n_recv = R.n_recv;
+                for (int q = 0; q < R.n_prog; ++q) Sm.prog[q] = R.prog[q];
+                for (int q = 0; q < R.n_recv; ++q) Sm.recv[q] = R.recv[q];
+            }
+        }
     }
     for (int g = 0; g < Gn; ++g) hE_.grp[g].feature_size = feature_size(g);
     curmask_ = 0;

@@ -89,6 +89,15 @@ struct SettledMask {
 };
 #endif
 
+// small read-only tables (range offsets): through the non-coherent L1 path on the device
+MG_HD int ld_ro(const int *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
 // loads that must observe in-place updates made by other threads during a relaxation sweep
 MG_HD int ld_volatile(const int *p) { return *(const volatile int *)p; }
 MG_HD unsigned char ld_volatile(const unsigned char *p) { return *(const volatile unsigned char *)p; }

@@ -165,17 +165,20 @@ MG_HD void phase_rng(Ctx &c, const EngineDev &E, int a, int n_attack) {
 }
 
 // cell an attack action aims at (Map::get_attack_obj, Map.cc:209-221); may lie off the board
-MG_HD void attack_cell(const EngineDev &E, const GroupDev &G, const AgentSoA &s, long gi, int &tx, int &ty) {
-    const int k = s.act[gi] - G.attack_base;
-    tx = s.x[gi] + G.att_xoff + G.att_dx[k];
-    ty = s.y[gi] + G.att_yoff + G.att_dy[k];
+MG_HD void attack_cell_from(const EngineDev &E, const GroupDev &G, int act, int x, int y, int dir, int &tx, int &ty) {
+    const int k = act - G.attack_base;
+    const int adx = ld_ro(G.att_dx + k), ady = ld_ro(G.att_dy + k);
+    tx = x + G.att_xoff + adx;
+    ty = y + G.att_yoff + ady;
     if (E.turn_mode) {
-        const int dir = s.dir[gi];
         int rx, ry, dx, dy;
         dir_real(G, dir, rx, ry);
-        dir_rot(dir, G.att_xoff + G.att_dx[k], G.att_yoff + G.att_dy[k], dx, dy);
-        tx = s.x[gi] + rx + dx; ty = s.y[gi] + ry + dy;
+        dir_rot(dir, G.att_xoff + adx, G.att_yoff + ady, dx, dy);
+        tx = x + rx + dx; ty = y + ry + dy;
     }
+}
+MG_HD void attack_cell(const EngineDev &E, const GroupDev &G, const AgentSoA &s, long gi, int &tx, int &ty) {
+    attack_cell_from(E, G, s.act[gi], s.x[gi], s.y[gi], E.turn_mode ? (int)s.dir[gi] : (int)DIR_NORTH, tx, ty);
 }
 MG_HD int flat_group(const EngineDev &E, int flat) {
     int g = 0;
@@ -256,6 +259,15 @@ MG_HD void phase_rank_target(Ctx &c, const EngineDev &E, const StepArgs &S, int 
     for (int e = c.tid(); e < n_attack; e += c.nth()) {
         // element e is swapped to position v=j_e at step e; afterwards it moves whenever a later step
         // picks its current position: first to ne = next step with the same j, then along sh_first.
+        // the attacker's own fields are requested first: their global round trip overlaps the shuffle walk below
+        const int code = E.att_agent[R.sb + e];
+        const int g = code_group(code), i = code_index(code);
+        const GroupDev &G = E.grp[g];
+        const AgentSoA &s = cur_soa(E, S.curmask, g);
+        const long gi = gidx(E, a, g, i);
+        const unsigned char fl = s.flags[gi];
+        const int act = s.act[gi], ax = s.x[gi], ay = s.y[gi];
+        const int adir = E.turn_mode ? (int)s.dir[gi] : (int)DIR_NORTH;
         int v = E.jv[R.sb + e];
         int ne = DEATH_NEVER;
         for (int q = E.sh_head[R.sb + v]; q != -1; q = E.sh_next[R.sb + q])
@@ -265,17 +277,12 @@ MG_HD void phase_rank_target(Ctx &c, const EngineDev &E, const StepArgs &S, int 
             pos = ne;
             for (int nx = E.sh_first[R.sb + pos]; nx != DEATH_NEVER; nx = E.sh_first[R.sb + pos]) pos = nx;
         }
-        int code = E.att_agent[R.sb + e];
-        int g = code_group(code), i = code_index(code);
-        const GroupDev &G = E.grp[g];
-        const AgentSoA &s = cur_soa(E, S.curmask, g);
-        long gi = gidx(E, a, g, i);
         int fs = G.foff + i;
         E.att_rank[R.sb + fs] = pos;
-        if (s.flags[gi] & FLAG_DEAD) continue;          // skipped at execution (GridWorld.cc:479)
+        if (fl & FLAG_DEAD) continue;                   // skipped at execution (GridWorld.cc:479)
         // Map::get_attack_obj (Map.cc:209-252)
         int tx, ty;
-        attack_cell(E, G, s, gi, tx, ty);
+        attack_cell_from(E, G, act, ax, ay, adir, tx, ty);
         if (tx < 0 || tx >= E.W || ty < 0 || ty >= E.H) continue;
         int t = R.occ[ty * E.W + tx];
         if (E.food_mode && t == OCC_FOOD) {             // eaters of one cell queue on the (idle) claim plane
@@ -366,7 +373,11 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
         E.mv_key[f] = MVKEY_NONE;
         E.mv_state[f] = MV_NONE;
         if (S.record_events) G.ev_rank[gi] = -1;
-        if (s.flags[gi] & FLAG_DEAD) continue;
+        // requested together, before the first test needs one: one global round trip instead of three
+        const unsigned char fl = s.flags[gi];
+        const float hp0 = s.hp[gi];
+        float nr = s.next_reward[gi];                    // only this thread writes this agent's reward in this phase
+        if (fl & FLAG_DEAD) continue;
         int d = E.death[f];
         int r = E.att_rank[f];
         // my attack is executed iff I am alive when its rank comes; d == r can only mean that it is my own blow that
@@ -380,22 +391,22 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
             int dt = t >= 0 ? E.death[R.sb + lflat(E, t)] : DEATH_BEFORE;
             if (t >= 0 && E.food_mode && friendly_fire_refused(E, g, code_group(t))) dt = DEATH_BEFORE;
             if (t < 0 || dt < r) {                       // blank / already dead / food (eating earns nothing): penalty only
-                s.next_reward[gi] += G.attack_penalty;
+                nr += G.attack_penalty;
             } else if (dt == r) {                        // my hit kills
                 s.last_op[gi] = OP_KILL;
                 s.op_obj[gi] = t;
                 if (self_kill) late_reward = E.grp[code_group(t)].kill_reward + G.attack_penalty;
-                else s.next_reward[gi] += E.grp[code_group(t)].kill_reward + G.attack_penalty;
+                else nr += E.grp[code_group(t)].kill_reward + G.attack_penalty;
                 ++kills; ++hits;
             } else {
                 s.last_op[gi] = OP_ATTACK;
                 s.op_obj[gi] = t;
-                s.next_reward[gi] += 0.0f + G.attack_penalty;
+                nr += 0.0f + G.attack_penalty;
                 ++hits;
             }
         }
         bool evaluated = E.in_head[f] != -1 || E.tgt[f] != TGT_NONE;
-        float hp = evaluated ? E.hp_fin[f] : s.hp[gi];
+        float hp = evaluated ? E.hp_fin[f] : hp0;
         bool dies = false;
         if (d != DEATH_NEVER) {                          // killed in the attack phase
             dies = true;
@@ -410,10 +421,10 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
         }
         s.hp[gi] = hp;
         if (dies) {
-            s.flags[gi] |= FLAG_DEAD;
+            s.flags[gi] = fl | FLAG_DEAD;
             R.hdr->any_dead = 1;
-            s.next_reward[gi] = G.dead_penalty;          // assignment (GridWorld.h:206)
-            if (self_kill) s.next_reward[gi] += late_reward;
+            nr = G.dead_penalty;                         // assignment (GridWorld.h:206)
+            if (self_kill) nr += late_reward;
             int x = s.x[gi], y = s.y[gi], bw, bh;
             body_dims(G, agent_dir(E, s, gi), bw, bh);
             for (int bx = 0; bx < bw; ++bx)
@@ -423,6 +434,7 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
                 }
             atomic_add(&E.dead_ct[g * E.A + a], 1);
         }
+        if (executed || dies) s.next_reward[gi] = nr;
     }
     c.add_count(E, CNT_KILLS, kills);
     c.add_count(E, CNT_HITS, hits);
@@ -485,12 +497,15 @@ MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, in
         const GroupDev &G = E.grp[g];
         const AgentSoA &s = cur_soa(E, S.curmask, g);
         long gi = gidx(E, a, g, i);
-        int act = s.act[gi];
+        // the agent's fields are requested together, before the first test needs one of them: one global round trip
+        // instead of three (the tests would otherwise serialise the loads)
+        const int act = s.act[gi];
+        const unsigned char fl = s.flags[gi];
+        const int x = s.x[gi], y = s.y[gi];
         if (turn ? (act < G.n_move || act >= G.attack_base) : (act < 0 || act >= G.n_move)) continue;
-        if (s.flags[gi] & (turn ? FLAG_DEAD : (FLAG_DEAD | FLAG_ABSORBED))) continue;     // GridWorld.cc:553,581
+        if (fl & (turn ? FLAG_DEAD : (FLAG_DEAD | FLAG_ABSORBED))) continue;     // GridWorld.cc:553,581
         int fs = G.foff + i;
         long f = R.sb + fs;
-        int x = s.x[gi], y = s.y[gi];
         // insertion order of the reference: band buffers 0..nsep-1, then the boundary buffer
         unsigned bucket = (unsigned)E.nsep;
         if (E.large_map) {
@@ -508,8 +523,8 @@ MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, in
             dir_real(G, nd, qx, qy);
             nx = x + rx - qx; ny = y + ry - qy;
         } else {
-            int dx = G.move_dx[act], dy = G.move_dy[act];
-            if (E.turn_mode) dir_rot(s.dir[gi], G.move_dx[act], G.move_dy[act], dx, dy);     // GridWorld.cc:587-598
+            int dx = ld_ro(G.move_dx + act), dy = ld_ro(G.move_dy + act);
+            if (E.turn_mode) { const int rx = dx, ry = dy; dir_rot(s.dir[gi], rx, ry, dx, dy); }     // GridWorld.cc:587-598
             nx = x + dx; ny = y + dy;
         }
         E.mv_nx[f] = nx; E.mv_ny[f] = ny;
@@ -543,6 +558,7 @@ MG_HD int occupant_at_turn(const EngineDev &E, const ArenaRef &R, unsigned curma
                            bool &stable) {
     int cell = cy * E.W + cx;
     int o = R.occ[cell];
+    const int head = R.claim[cell];                   // issued with the occupancy load: one round trip, not two
     if (o >= 0) {
         int fo = lflat(E, o);
         if (fo != self) {
@@ -560,7 +576,7 @@ MG_HD int occupant_at_turn(const EngineDev &E, const ArenaRef &R, unsigned curma
         }
     }
 claimants:
-    for (int node = R.claim[cell]; node != -1; node = E.cl_next[R.nb + node]) {
+    for (int node = head; node != -1; node = E.cl_next[R.nb + node]) {
         int fm = node_owner(E, node);
         if (fm != self && E.mv_key[R.sb + fm] < key) {
             stable = false;
@@ -821,11 +837,11 @@ MG_HD void phase_rule_allq(Ctx &c, const EngineDev &E, const StepArgs &S, int a)
 }
 
 // calc_event_node on the bound entities (postfix program; no short-circuit needed: nodes have no side effects)
-MG_HD bool rule_eval(const EngineDev &E, const ArenaRef &R, const RuleDev &Ru, unsigned curmask, int a, const int *codes) {
+MG_HD bool rule_eval(const EngineDev &E, const ArenaRef &R, const RuleInstr *prog, int n_prog, unsigned curmask, int a, const int *codes) {
     bool stack[MG_MAX_PROG];
     int sp = 0;
-    for (int p = 0; p < Ru.n_prog; ++p) {
-        const RuleInstr &I = Ru.prog[p];
+    for (int p = 0; p < n_prog; ++p) {
+        const RuleInstr &I = prog[p];
         switch (I.op) {
             case OP_AND: { bool b = stack[--sp]; bool x = stack[--sp]; stack[sp++] = x && b; break; }
             case OP_OR:  { bool b = stack[--sp]; bool x = stack[--sp]; stack[sp++] = x || b; break; }
@@ -876,9 +892,9 @@ MG_HD bool rule_bind(const ArenaRef &R, int obj, int group, int index) {
     return index == -1 || stale_index(R, obj) == index;
 }
 
-MG_HD void rule_pay(const EngineDev &E, const ArenaRef &R, const RuleDev &Ru, unsigned curmask, int a, const int *codes) {
-    for (int q = 0; q < Ru.n_recv; ++q) {
-        const RuleRecv &rc = Ru.recv[q];
+MG_HD void rule_pay(const EngineDev &E, const ArenaRef &R, const RuleRecv *recv, int n_recv, unsigned curmask, int a, const int *codes) {
+    for (int q = 0; q < n_recv; ++q) {
+        const RuleRecv &rc = recv[q];
         if (rc.role == ROLE_GROUP) {
             atomic_addf(&R.hdr->grp_reward[rc.group], rc.value);
         } else {
@@ -896,30 +912,36 @@ MG_HD void rule_pay(const EngineDev &E, const ArenaRef &R, const RuleDev &Ru, un
 // strides over -- one level for the shipped games, two for double_attack, O(n^k) in general exactly like the
 // reference.  An agent cannot fill two 'any' levels at once (be_involved, RewardEngine.cc:401-403).
 template <class Ctx>
-MG_HD void phase_reward_rule(Ctx &c, const EngineDev &E, const StepArgs &S, int a, int r) {
+MG_HD void phase_reward_rule(Ctx &c, const EngineDev &E, const StepArgs &S, int a, int r, const GroupEnum &all) {
     ArenaRef R = arena_ref(E, a);
-    const RuleDev &Ru = E.rules[r];
-    const int shape = E.rule_shape[r];                  // per-CTA copy: the rule table itself lives in HBM
-    if (shape == RULE_DEAD) return;
+    const RuleDev &Ru = E.rules[r];                     // in HBM: only touched by candidates that pass the bind
+    const RuleHot H = E.rule_hot[r];
+    if (H.shape == RULE_DEAD) return;
     int codes[2 * MG_MAX_IN];
     bool any = false;
-    if (shape == RULE_ONE_ANY) {
-        // one free subject, optionally binding its op_obj: every shipped game's rules.  One thread per subject.
-        const RuleInput in = Ru.in[0];
-        const int n = E.n[in.group * E.A + a];
-        const AgentSoA &s = cur_soa(E, S.curmask, in.group);
-        const long b0 = gidx(E, a, in.group, 0);
+    const bool small = r < MG_HOT_RULES && E.rule_small[r].n_prog >= 0;
+    const RuleInstr *prog = small ? E.rule_small[r].prog : Ru.prog;
+    const RuleRecv *recv = small ? E.rule_small[r].recv : Ru.recv;
+    const int n_prog = small ? E.rule_small[r].n_prog : Ru.n_prog, n_recv = small ? E.rule_small[r].n_recv : Ru.n_recv;
+    if (H.shape == RULE_ONE_ANY) {
+        // one free subject, optionally binding its op_obj: every shipped game's rules.  One thread per subject; the
+        // only global round trip before the verdict is the subject's op_obj.
+        const int n = all.pre[H.group + 1] - all.pre[H.group];
+        const AgentSoA &s = cur_soa(E, S.curmask, H.group);
+        const long b0 = gidx(E, a, H.group, 0);
         for (int i = c.tid(); i < n; i += c.nth()) {
             codes[1] = -1;
-            if (in.has_obj) {
+            if (H.has_obj) {
                 const int obj = s.op_obj[b0 + i];
-                if (!rule_bind(R, obj, in.obj_group, in.obj_index)) continue;
+                const int lop = H.simple_op ? (int)s.last_op[b0 + i] : 0;    // requested together with op_obj
+                if (!rule_bind(R, obj, H.obj_group, H.obj_index)) continue;
+                if (H.simple_op && lop != H.simple_op) continue;
                 codes[1] = obj;
             }
-            codes[0] = code_make(in.group, i);
-            if (!rule_eval(E, R, Ru, S.curmask, a, codes)) continue;
+            codes[0] = code_make(H.group, i);
+            if (!H.simple_op && !rule_eval(E, R, prog, n_prog, S.curmask, a, codes)) continue;
             any = true;
-            rule_pay(E, R, Ru, S.curmask, a, codes);
+            rule_pay(E, R, recv, n_recv, S.curmask, a, codes);
         }
         if (any) R.hdr->rule_trig[r] = 1;
         return;
@@ -968,9 +990,9 @@ MG_HD void phase_reward_rule(Ctx &c, const EngineDev &E, const StepArgs &S, int 
             for (int q2 = 0; q2 < q; ++q2)
                 if (codes[2 * Ru.any_in[q]] == codes[2 * Ru.any_in[q2]]) ok = false;
         if (!ok) continue;
-        if (!rule_eval(E, R, Ru, S.curmask, a, codes)) continue;
+        if (!rule_eval(E, R, prog, n_prog, S.curmask, a, codes)) continue;
         any = true;
-        rule_pay(E, R, Ru, S.curmask, a, codes);
+        rule_pay(E, R, recv, n_recv, S.curmask, a, codes);
     }
     if (any) R.hdr->rule_trig[r] = 1;             // every writer stores the same byte
 }
@@ -985,7 +1007,7 @@ MG_HD void phase_done(Ctx &c, const EngineDev &E, int a) {
         if (E.n[g * E.A + a] - E.dead_ct[g * E.A + a] > 0) ++live;
     int done = live < E.G;
     for (int r = 0; r < E.n_rules; ++r)
-        if (E.rule_terminal[r] && R.hdr->rule_trig[r]) done = 1;
+        if (E.rule_hot[r].terminal && R.hdr->rule_trig[r]) done = 1;
     R.hdr->done = done;
     // bit 1 tells the host whether this arena holds dead agents: when no arena does, clear_dead cannot change a
     // count and the host skips re-reading the offsets (one blocking copy less per step)
@@ -1085,7 +1107,7 @@ MG_HD void run_step(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
         c.sync();
     }
     for (int r = 0; r < E.n_rules; ++r) {
-        phase_reward_rule(c, E, S, a, r);
+        phase_reward_rule(c, E, S, a, r, all);
         c.sync();
     }
     MG_MARK(12);
