@@ -21,7 +21,7 @@
 
 #include "backend.h"
 #if defined(MG_PHASE_TIMING)
-namespace mg { __device__ long long mg_phase_clock[8 * 16]; }
+namespace mg { __device__ long long mg_phase_clock[8 * 32]; }
 #endif
 #include "obs_phases.h"
 
@@ -48,7 +48,7 @@ const char *name() { return "cuda-sm_100a"; }
 
 #if defined(MG_PHASE_TIMING)
 extern "C" __attribute__((visibility("default"))) void magent_b200_debug_phase_clocks(long long *out) {
-    CUDA_CHECK(cudaMemcpyFromSymbol(out, mg::mg_phase_clock, sizeof(long long) * 8 * 16));
+    CUDA_CHECK(cudaMemcpyFromSymbol(out, mg::mg_phase_clock, sizeof(long long) * 8 * 32));
 }
 #endif
 

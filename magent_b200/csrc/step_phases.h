@@ -488,65 +488,117 @@ MG_HD int turned_dir(int dir, int act) { return (dir + 2 * act - 1 + 4) % 4; }
 
 // phase 6: movers (turn == false) or turners (turn == true, turn_mode only) compute their target footprint and
 // queue on every target cell.  Turn: Map::do_turn, Map.cc:361-406; move: Map::do_move, Map.cc:313-358.
+// A thread owns ~4 movers.  One at a time each costs three dependent global round trips (own fields -> occupancy of
+// the target -> claim exchange); the batch below issues each kind of request for all of the thread's movers
+// before it consumes the first answer.  Everything indexed by `u` is unrolled into registers.
 template <class Ctx>
 MG_HD void phase_move_register(Ctx &c, const EngineDev &E, const StepArgs &S, int a, const GroupEnum &ord, bool turn) {
     ArenaRef R = arena_ref(E, a);
-    for (int idx = c.tid(); idx < ord.cnt; idx += c.nth()) {
-        int k, i; enum_locate(ord, idx, k, i);
-        int g = ord.grp[k];
-        const GroupDev &G = E.grp[g];
-        const AgentSoA &s = cur_soa(E, S.curmask, g);
-        long gi = gidx(E, a, g, i);
-        // the agent's fields are requested together, before the first test needs one of them: one global round trip
-        // instead of three (the tests would otherwise serialise the loads)
-        const int act = s.act[gi];
-        const unsigned char fl = s.flags[gi];
-        const int x = s.x[gi], y = s.y[gi];
-        if (turn ? (act < G.n_move || act >= G.attack_base) : (act < 0 || act >= G.n_move)) continue;
-        if (fl & (turn ? FLAG_DEAD : (FLAG_DEAD | FLAG_ABSORBED))) continue;     // GridWorld.cc:553,581
-        int fs = G.foff + i;
-        long f = R.sb + fs;
-        // insertion order of the reference: band buffers 0..nsep-1, then the boundary buffer
-        unsigned bucket = (unsigned)E.nsep;
-        if (E.large_map) {
-            int xm = x % E.bandwidth;
-            if (!(xm < 4 || xm > E.bandwidth - 4)) bucket = (unsigned)(x / E.bandwidth);
-        }
-        E.mv_key[f] = (bucket << 27) | ((unsigned)k << 23) | (unsigned)i;
-        int nx, ny;
-        if (turn) {
-            // the body pivots about its "real" corner (turn offsets are 0, AgentType.cc:108): the stored top-left
-            // corner follows from real_to_save with the new direction
-            const int dir = s.dir[gi], nd = turned_dir(dir, act);
-            int rx, ry, qx, qy;
-            dir_real(G, dir, rx, ry);
-            dir_real(G, nd, qx, qy);
-            nx = x + rx - qx; ny = y + ry - qy;
-        } else {
-            int dx = ld_ro(G.move_dx + act), dy = ld_ro(G.move_dy + act);
-            if (E.turn_mode) { const int rx = dx, ry = dy; dir_rot(s.dir[gi], rx, ry, dx, dy); }     // GridWorld.cc:587-598
-            nx = x + dx; ny = y + dy;
-        }
-        E.mv_nx[f] = nx; E.mv_ny[f] = ny;
-        int bw, bh;
-        mover_dims(E, G, s, gi, turn, bw, bh);
-        if (nx < 0 || ny < 0 || nx + bw >= E.W || ny + bh >= E.H) {          // Map.cc:455
-            E.mv_state[f] = MV_OOB;
-            continue;
-        }
-        bool wall = false;
-        for (int bx = 0; bx < bw; ++bx)
-            for (int by = 0; by < bh; ++by)
-                if (R.occ[(ny + by) * E.W + nx + bx] <= OCC_WALL) wall = true;       // walls and food (is_blank_area, Map.cc:461-465)
-        // with absorbing types around, a wall-blocked mover may still bump into an absorber: keep it in the relaxation
-        if (wall && (turn || !E.any_absorb)) { E.mv_state[f] = MV_STATIC_FAIL; continue; }
-        E.mv_state[f] = MV_PENDING_FAIL;
-        int ci = 0;
-        for (int bx = 0; bx < bw; ++bx)
-            for (int by = 0; by < bh; ++by, ++ci) {
-                int node = fs * E.max_body + ci;
-                E.cl_next[R.nb + node] = atomic_exch(&R.claim[(ny + by) * E.W + nx + bx], node);
+    constexpr int U = 4;
+    for (int base = c.tid(); base < ord.cnt; base += U * c.nth()) {
+        int act[U], x[U], y[U], fl[U], dir[U];
+        // request 1: the agents' own fields
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int u = 0; u < U; ++u) {
+            const int idx = base + u * c.nth();
+            act[u] = -1; x[u] = y[u] = fl[u] = 0; dir[u] = DIR_NORTH;
+            if (idx < ord.cnt) {
+                int k, i; enum_locate(ord, idx, k, i);
+                const int g = ord.grp[k];
+                const AgentSoA &s = cur_soa(E, S.curmask, g);
+                const long gi = gidx(E, a, g, i);
+                act[u] = s.act[gi]; fl[u] = s.flags[gi]; x[u] = s.x[gi]; y[u] = s.y[gi];
+                if (E.turn_mode) dir[u] = s.dir[gi];
             }
+        }
+        int cell[U], node[U];                           // single-cell footprints wait here for requests 2 and 3
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int u = 0; u < U; ++u) {
+            cell[u] = -1; node[u] = 0;
+            const int idx = base + u * c.nth();
+            if (idx >= ord.cnt) continue;
+            int k, i; enum_locate(ord, idx, k, i);
+            const int g = ord.grp[k];
+            const GroupDev &G = E.grp[g];
+            const int av = act[u];
+            if (turn ? (av < G.n_move || av >= G.attack_base) : (av < 0 || av >= G.n_move)) continue;
+            if (fl[u] & (turn ? FLAG_DEAD : (FLAG_DEAD | FLAG_ABSORBED))) continue;     // GridWorld.cc:553,581
+            const int fs = G.foff + i;
+            const long f = R.sb + fs;
+            // insertion order of the reference: band buffers 0..nsep-1, then the boundary buffer
+            unsigned bucket = (unsigned)E.nsep;
+            if (E.large_map) {
+                int xm = x[u] % E.bandwidth;
+                if (!(xm < 4 || xm > E.bandwidth - 4)) bucket = (unsigned)(x[u] / E.bandwidth);
+            }
+            E.mv_key[f] = (bucket << 27) | ((unsigned)k << 23) | (unsigned)i;
+            int nx, ny;
+            if (turn) {
+                // the body pivots about its "real" corner (turn offsets are 0, AgentType.cc:108): the stored top-left
+                // corner follows from real_to_save with the new direction
+                const int nd = turned_dir(dir[u], av);
+                int rx, ry, qx, qy;
+                dir_real(G, dir[u], rx, ry);
+                dir_real(G, nd, qx, qy);
+                nx = x[u] + rx - qx; ny = y[u] + ry - qy;
+            } else {
+                int dx = ld_ro(G.move_dx + av), dy = ld_ro(G.move_dy + av);
+                if (E.turn_mode) { const int rx = dx, ry = dy; dir_rot(dir[u], rx, ry, dx, dy); }     // GridWorld.cc:587-598
+                nx = x[u] + dx; ny = y[u] + dy;
+            }
+            E.mv_nx[f] = nx; E.mv_ny[f] = ny;
+            int bw, bh;
+            body_dims(G, dir[u], bw, bh);
+            if (turn) { int t = bw; bw = bh; bh = t; }   // every turn is by 90 degrees
+            if (nx < 0 || ny < 0 || nx + bw >= E.W || ny + bh >= E.H) {          // Map.cc:455
+                E.mv_state[f] = MV_OOB;
+                continue;
+            }
+            if (bw == 1 && bh == 1) { cell[u] = ny * E.W + nx; node[u] = fs * E.max_body; continue; }
+            // larger bodies: walls / food under the footprint (is_blank_area, Map.cc:461-465), then queue on every cell
+            bool wall = false;
+            for (int bx = 0; bx < bw; ++bx)
+                for (int by = 0; by < bh; ++by)
+                    if (R.occ[(ny + by) * E.W + nx + bx] <= OCC_WALL) wall = true;
+            // with absorbing types around, a wall-blocked mover may still bump into an absorber: keep it in the relaxation
+            if (wall && (turn || !E.any_absorb)) { E.mv_state[f] = MV_STATIC_FAIL; continue; }
+            E.mv_state[f] = MV_PENDING_FAIL;
+            int ci = 0;
+            for (int bx = 0; bx < bw; ++bx)
+                for (int by = 0; by < bh; ++by, ++ci) {
+                    int nd = fs * E.max_body + ci;
+                    E.cl_next[R.nb + nd] = atomic_exch(&R.claim[(ny + by) * E.W + nx + bx], nd);
+                }
+        }
+        // request 2: occupancy of the single target cells
+        int occv[U];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int u = 0; u < U; ++u) occv[u] = cell[u] >= 0 ? R.occ[cell[u]] : 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int u = 0; u < U; ++u) {
+            if (cell[u] < 0) continue;
+            const long f = R.sb + node[u] / E.max_body;
+            if (occv[u] <= OCC_WALL && (turn || !E.any_absorb)) { E.mv_state[f] = MV_STATIC_FAIL; cell[u] = -1; }
+            else E.mv_state[f] = MV_PENDING_FAIL;
+        }
+        // request 3: the claim exchanges
+        int prev[U];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int u = 0; u < U; ++u) prev[u] = cell[u] >= 0 ? atomic_exch(&R.claim[cell[u]], node[u]) : -1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int u = 0; u < U; ++u) if (cell[u] >= 0) E.cl_next[R.nb + node[u]] = prev[u];
     }
 }
 
@@ -1015,11 +1067,21 @@ MG_HD void phase_done(Ctx &c, const EngineDev &E, int a) {
     R.hdr->rng = R.hdr->rng_next;
 }
 
+// MG_PHASE_TIMING (profiling variants only, profiles/build_variant.sh -DMG_PHASE_TIMING): thread 0 of the team
+// stamps the SM clock after every phase of the first arenas into a device array the profiling script reads back
+#if defined(MG_PHASE_TIMING) && defined(__CUDA_ARCH__)
+#define MG_MARK(k) do { if (c.tid() == 0 && a < 8) mg_phase_clock[a * 32 + (k)] = clock64(); } while (0)
+#define MG_MARKV(k, v) do { if (c.tid() == 0 && a < 8) mg_phase_clock[a * 32 + (k)] = (v); } while (0)
+#else
+#define MG_MARK(k) do { } while (0)
+#define MG_MARKV(k, v) do { (void)(v); } while (0)
+#endif
+
 // relaxation driver: sweep until a full sweep changes nothing.  One team barrier per sweep; the
 // rotating flag triple makes the reset of the next flag race-free.  The flags live where the
 // team can see them cheaply: shared memory for a CTA team, the arena header in HBM for the grid team.
 template <class Ctx, class Sweep>
-MG_HD int relax_until_stable(Ctx &c, int *flags, Sweep sweep) {
+MG_HD int relax_until_stable(Ctx &c, int *flags, Sweep sweep, int a = 0, int mark = -1) {
     if (c.tid() == 0) { st_volatile(&flags[0], 0); st_volatile(&flags[1], 0); st_volatile(&flags[2], 0); }
     c.sync();
     for (int it = 0;; ++it) {
@@ -1027,19 +1089,10 @@ MG_HD int relax_until_stable(Ctx &c, int *flags, Sweep sweep) {
         if (c.tid() == 0) st_volatile(&flags[nxt], 0);
         if (sweep()) st_volatile(&flags[cur], 1);
         c.sync();
+        if (it == 0 && mark >= 0) { MG_MARK(mark); }
         if (!ld_volatile(&flags[cur])) return it + 1;
     }
 }
-
-// MG_PHASE_TIMING (profiling variants only, profiles/build_variant.sh -DMG_PHASE_TIMING): thread 0 of the team
-// stamps the SM clock after every phase of the first arenas into a device array the profiling script reads back
-#if defined(MG_PHASE_TIMING) && defined(__CUDA_ARCH__)
-#define MG_MARK(k) do { if (c.tid() == 0 && a < 8) mg_phase_clock[a * 16 + (k)] = clock64(); } while (0)
-#define MG_MARKV(k, v) do { if (c.tid() == 0 && a < 8) mg_phase_clock[a * 16 + (k)] = (v); } while (0)
-#else
-#define MG_MARK(k) do { } while (0)
-#define MG_MARKV(k, v) do { (void)(v); } while (0)
-#endif
 
 // the whole step for one arena (reference GridWorld::step, GridWorld.cc:456-631)
 template <class Ctx>
@@ -1090,7 +1143,7 @@ MG_HD void run_step(Ctx &c, const EngineDev &E, const StepArgs &S, int a) {
     phase_move_register(c, E, S, a, ord, false);
     MG_MARK(7);
     SettledMask mv_settled;
-    int mv_sweeps = relax_until_stable(c, flags, [&]() { return phase_move_relax(c, E, S, a, ord, false, mv_settled); });
+    int mv_sweeps = relax_until_stable(c, flags, [&]() { return phase_move_relax(c, E, S, a, ord, false, mv_settled); }, a, 16);
     MG_MARKV(15, mv_sweeps);
     MG_MARK(8);
     phase_move_collide(c, E, S, a, ord);

@@ -26,14 +26,14 @@ def main():
     env, act = bench.build_env(wl, lib.path, wl["arenas"])
     raw = ctypes.CDLL(lib.path)
     mhz = 1965.0          # SM max clock (MEASURED_PEAKS.json); a lightly loaded SM runs at it
-    rows, sweeps = [], []
+    rows, sweeps, first = [], [], []
     for s in range(12):
         for h in act:
             env.set_random_actions(h, s)
         env.step()
-        buf = (ctypes.c_longlong * 128)()
+        buf = (ctypes.c_longlong * 256)()
         raw.magent_b200_debug_phase_clocks(buf)
-        t = np.array(buf[:], dtype=np.int64).reshape(8, 16)
+        t = np.array(buf[:], dtype=np.int64).reshape(8, 32)
         env.clear_dead()
         if s < 2:
             continue
@@ -43,12 +43,14 @@ def main():
             d[d < 0] = np.nan                      # phases skipped this step keep an old stamp
             rows.append(d)
             sweeps.append(t[a, 14:16])
+            first.append(float(t[a, 16] - t[a, 7]))
     rows = np.array(rows)
     med = np.nanmedian(rows, axis=0)
     print("workload %s: per-arena phase durations (median over %d samples), us at %.0f MHz" % (wl_name, len(rows), mhz))
     for nm, cyc in zip(NAMES[1:], med):
         print("  %-14s %8.0f cycles  %6.2f us" % (nm, cyc, cyc / mhz))
     print("  %-14s %8.0f cycles  %6.2f us" % ("TOTAL", np.nansum(med), np.nansum(med) / mhz))
+    print("  %-14s %8.0f cycles  %6.2f us   (first sweep of move_relax incl. its barrier)" % ("relax sweep 1", np.median(first), np.median(first) / mhz))
     sw = np.array(sweeps)
     print("  relaxation sweeps: attack median %d max %d, move median %d max %d" % (np.median(sw[:, 0]), sw[:, 0].max(), np.median(sw[:, 1]), sw[:, 1].max()))
 
