@@ -1,0 +1,114 @@
+"""Parity at BASELINE.json's full sizes (configs[1..4] as bench.py runs them), on a real GPU, through the C ABI.
+
+The sequential reference cannot replay 512 arenas (or 64) in test time, so these tests check
+  * SAMPLED arenas exactly against independent checker environments seeded seed+arena, and
+  * the WHOLE batch through size-independent properties (tests/fullsize_common.py): unique in-board cells,
+    ordered ids, bounded moves, and every observation record against a plain PyTorch restatement of
+    get_observation that is itself pinned to the compiled reference on the CPU (tests/test_fullsize_cpu.py).
+The single 1000x1000 arena (2x400k agents) is small enough for the reference: it is compared record by record.
+Observations are taken through device pointers (`get_observation_torch`), the path bench.py's `value` times.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import fullsize_common as fs
+import parity_common as pc
+
+pytestmark = pytest.mark.gpu
+
+ENGINE = os.environ.get("MAGENT_FULLSIZE_ENGINE", pc.CUDA_LIB)      # (tests/_emu library for a dry run on the CPU)
+ON_GPU = ENGINE == pc.CUDA_LIB
+
+
+def checker_lib():
+    for p in (pc.REF_LIB, pc.PORT_LIB):
+        if os.path.exists(p):
+            return p
+    pytest.skip("no oracle library available (oracle/_ref or oracle/_build)")
+
+
+def batched_battle(arenas, size, n, seed):
+    import magent_b200 as magent
+    kw = {"_num_arenas": arenas} if arenas != 1 else {}
+    env = magent.GridWorld("battle", map_size=size, _lib=ENGINE, **kw)
+    env.set_seed(seed)
+    env.reset()
+    for h in env.get_handles():
+        env.add_agents(h, method="random", n=n)
+    return env
+
+
+def test_battle_512_arenas_of_2x1000():
+    """BASELINE configs[4] per-GPU share (= bench.py's default workload): 1.024 M agents per step"""
+    A, size, n, seed = 512, 200, 1000, 100
+    env = batched_battle(A, size, n, seed)
+    samples = {a: pc.make_battle(checker_lib(), size, n, seed + a) for a in (0, 255, 511)}
+    fs.play_battle_and_check(env, size, size, 3, 17, samples=samples, use_torch_obs=ON_GPU)
+
+
+def test_battle_one_arena_of_2x400k():
+    """BASELINE configs[3] as placeable (2x400k on 1000x1000; the whole-grid cooperative kernels): every record
+    of every step against the reference"""
+    size, n, seed = 1000, 400000, 3
+    env = batched_battle(1, size, n, seed)
+    ref = pc.make_battle(checker_lib(), size, n, seed)
+    fs.play_battle_and_check(env, size, size, 2, 23, samples={0: ref}, use_torch_obs=ON_GPU)
+
+
+def test_gather_64_arenas():
+    """BASELINE configs[2]: gather 200x200 (495 agents + 1847 food per arena), 64 arenas, only the agent group
+    observes and acts; arenas 0, 31 and 63 against independent checkers"""
+    import bench
+    import magent_b200 as magent
+    A, size, seed = 64, 200, 40
+    wl = bench.WORKLOADS["gather64"]
+    env, act = bench.build_env(wl, ENGINE, A, seed0=seed)
+    hs = env.get_handles()
+    gi = [list(hs).index(h) for h in act]
+    refs = {}
+    for a in (0, 31, 63):
+        r, _ = bench.build_env(wl, checker_lib(), 1, seed0=seed + a)
+        refs[a] = r
+    rs = np.random.RandomState(7)
+    for t in range(6):
+        nums = [env.get_arena_nums(h).astype(np.int64) for h in hs]
+        off = [np.concatenate([[0], np.cumsum(k)]) for k in nums]
+        assert all(int(k.sum()) == env.get_num(h) for k, h in zip(nums, hs))
+        for g in gi:
+            if ON_GPU:
+                v, f = env.get_observation_torch(hs[g])
+                v, f = v.cpu().numpy(), f.cpu().numpy()
+            else:
+                v, f = env.get_observation(hs[g])
+            for a, r in refs.items():
+                rv, rf = r.get_observation(r.get_handles()[g])
+                sl = slice(int(off[g][a]), int(off[g][a + 1]))
+                np.testing.assert_array_equal(v[sl].view(np.uint32), rv.view(np.uint32), err_msg="view t%d arena %d" % (t, a))
+                np.testing.assert_array_equal(f[sl].view(np.uint32), rf.view(np.uint32), err_msg="feature t%d arena %d" % (t, a))
+        acts = {g: rs.randint(0, env.get_action_space(hs[g])[0], size=int(nums[g].sum())).astype(np.int32) for g in gi}
+        for g in gi:
+            env.set_action(hs[g], acts[g])
+            for a, r in refs.items():
+                r.set_action(r.get_handles()[g], np.ascontiguousarray(acts[g][off[g][a]:off[g][a + 1]]))
+        env.step()
+        done = env.get_arena_done() != 0
+        for a, r in refs.items():
+            assert bool(done[a]) == bool(r.step())
+        for g, h in enumerate(hs):
+            rew, pos, alive, ids = env.get_reward(h), env.get_pos(h), env.get_alive(h), env.get_agent_id(h)
+            for a, r in refs.items():
+                rh = r.get_handles()[g]
+                sl = slice(int(off[g][a]), int(off[g][a + 1]))
+                np.testing.assert_allclose(rew[sl], r.get_reward(rh), atol=pc.REWARD_TOL, rtol=0)
+                np.testing.assert_array_equal(pos[sl], r.get_pos(rh))
+                np.testing.assert_array_equal(alive[sl], r.get_alive(rh))
+                np.testing.assert_array_equal(ids[sl], r.get_agent_id(rh))
+        # every arena starts from the same layout and differs only by its seed and its actions: arenas must
+        # not leak into each other -- the food group of an arena only ever shrinks
+        env.clear_dead()
+        for r in refs.values():
+            r.clear_dead()
+        after = env.get_arena_nums(hs[0]).astype(np.int64)
+        assert (after <= nums[0]).all()
