@@ -20,6 +20,7 @@ Workloads (BASELINE.json configs; the default is the per-GPU share of configs[4]
     battle1    battle 200x200, 2x1000 agents, 1 arena                     (configs[1])
     gather64   gather 200x200, 495 agents + 1847 food, 64 arenas          (configs[2])
     battle1m   battle 1000x1000, 2x400k agents, 1 arena (obs-render roofline; configs[3] as placeable)
+    battle1m_sparse  battle 4472x4472, 2x500k agents, 1 arena (configs[3] in the reference's own 1 M geometry)
 """
 import argparse
 import json
@@ -49,6 +50,9 @@ WORKLOADS = {
                      game="gather", map_size=200, arenas=64),
     "battle1m": dict(desc="battle 1000x1000, 2x400k agents (80% fill; BASELINE configs[3] as placeable), 1 arena",
                      game="battle", map_size=1000, arenas=1, n=400000),
+    "battle1m_sparse": dict(desc="battle 4472x4472, 2x500k agents (the reference's own 1 M geometry, "
+                                 "scripts/test/test_1m.py:66-74: map = sqrt(20 N)), 1 arena",
+                            game="battle", map_size=4472, arenas=1, n=500000),
 }
 
 

@@ -8,12 +8,25 @@ import numpy as np
 
 import parity_common as pc
 
+LARGE_MAP_SEED = 100000      # seeds from here on draw maps in large_map_mode (8 bands)
+HUGE_MAP_SEED = 200000       # ... and from here on strips of more than 1000 x 1000 cells (16 bands)
+
 
 def random_config(seed):
     import magent_b200 as magent
     gw = magent.gridworld
     rs = np.random.RandomState(seed)
     size_w, size_h = int(rs.randint(14, 40)), int(rs.randint(14, 40))
+    if seed >= LARGE_MAP_SEED:
+        # more than 99 x 99 cells: the reference's large_map_mode (GridWorld.cc:74-85, 403-438) -- movers and
+        # turners are queued per vertical band (8 bands; 16 above 1000 x 1000 cells), band edges go to the
+        # boundary buffer that runs last.  Strips keep the agent count (and the test time) small.
+        if seed >= HUGE_MAP_SEED:
+            size_w = int(rs.randint(4004, 5200))
+            size_h = 1000 * 1000 // size_w + int(rs.randint(2, 12))
+        else:
+            size_w = int(rs.randint(100, 330))
+            size_h = max(int(rs.randint(30, 100)), 99 * 99 // size_w + 1)
     turn = bool(rs.rand() < 0.3)
     food = bool(rs.rand() < 0.3)
     minimap = bool(rs.rand() < 0.6)
@@ -51,7 +64,7 @@ def random_config(seed):
     for _ in range(int(rs.randint(0, 5))):
         i, j = rs.choice(n_groups, 2, replace=False)
         a, b = syms[i], syms[j]
-        kind = int(rs.randint(0, 7 if seed % 3 == 1 else 6))
+        kind = int(rs.randint(0, 7 if seed % 3 == 1 and seed < LARGE_MAP_SEED else 6))   # pair rules are O(n^2): small maps only
         if kind == 0:
             cfg.add_reward_rule(gw.Event(a, 'attack', b), receiver=a, value=float(rs.choice([0.1, 0.2, 1])))
         elif kind == 1:
@@ -74,7 +87,7 @@ def random_config(seed):
             cfg.add_reward_rule(gw.Event(a, 'attack', c) & gw.Event(a2, 'attack', c), receiver=[a, a2], value=[0.5, 0.5])
         else:
             cfg.add_reward_rule(gw.Event(a, 'die'), receiver=gw.AgentSymbol(groups[j], 'all'), value=0.25, terminal=bool(rs.rand() < 0.1))
-    if seed >= 1000:
+    if 1000 <= seed < LARGE_MAP_SEED:
         general_rules(gw, cfg, rs, groups, syms, size_w, size_h)
     return cfg, dict(w=size_w, h=size_h, n_groups=n_groups, bodies=bodies, turn=turn)
 
@@ -143,6 +156,8 @@ def make_env(lib, seed, **kw):
     for g, h in enumerate(handles):
         bw, bl = info["bodies"][g]
         share = free * float(rs.choice([0.02, 0.06, 0.12] if seed % 3 != 1 else [0.1, 0.2, 0.3])) / (bw * bl) / info["n_groups"] * 2
+        if seed >= LARGE_MAP_SEED:
+            share *= 0.03 if seed >= HUGE_MAP_SEED else 0.4
         n = max(1, int(share))
         env.add_agents(h, method="random", n=n)
         if rs.rand() < 0.3:                                   # explicit placements, some of them blocked or off the map

@@ -35,3 +35,26 @@ def test_emulated_engine_matches_checker_with_an_irregular_caller(emu, seed):
 @pytest.mark.parametrize("seed", list(range(400, 410)))
 def test_emulated_arena_batch_matches_independent_checkers(emu, seed):
     fz.play_batch(seed, CHECKER, emu, n_arenas=1 + seed % 4, steps=10)
+
+
+# maps in the reference's large_map_mode (more than 99 x 99 cells: movers / turners queued per vertical band, 8 bands;
+# 16 bands above 1000 x 1000 cells -- GridWorld.cc:74-85, 403-438), tests/fuzz_common.py LARGE_MAP_SEED / HUGE_MAP_SEED
+@pytest.mark.parametrize("seed", list(range(100000, 100008)) + [200000, 200001])
+def test_emulated_engine_matches_checker_on_banded_maps(emu, seed):
+    fz.play(seed, CHECKER, emu, steps=15)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs oracle/_ref (the compiled reference)")
+@pytest.mark.parametrize("seed", list(range(100600, 100604)) + [200002])
+def test_oracle_port_matches_reference_on_banded_maps(seed):
+    fz.play(seed, pc.REF_LIB, pc.PORT_LIB, steps=15)
+
+
+@pytest.mark.parametrize("seed", [101000, 101001, 101002, 201000])
+def test_emulated_engine_on_banded_maps_with_an_irregular_caller(emu, seed):
+    fz.play_irregular(seed, CHECKER, emu, steps=15)
+
+
+@pytest.mark.parametrize("seed", [102000, 102001])
+def test_emulated_arena_batch_on_banded_maps(emu, seed):
+    fz.play_batch(seed, CHECKER, emu, n_arenas=2 + seed % 2, steps=8)

@@ -112,3 +112,23 @@ def test_gather_64_arenas():
             r.clear_dead()
         after = env.get_arena_nums(hs[0]).astype(np.int64)
         assert (after <= nums[0]).all()
+
+
+# ---- randomised differential games on maps in the reference's large_map_mode (8 / 16 move bands), CUDA engine vs
+# the checker (tests/fuzz_common.py; the same seeds run against the host emulation in tests/test_fuzz_cpu.py)
+@pytest.mark.parametrize("seed", list(range(100000, 100012)) + [200000, 200001, 200002])
+def test_random_games_on_banded_maps(seed):
+    import fuzz_common as fz
+    fz.play(seed, checker_lib(), ENGINE, steps=20)
+
+
+@pytest.mark.parametrize("seed", [101000, 101001, 101002, 101003, 201000])
+def test_random_games_on_banded_maps_with_an_irregular_caller(seed):
+    import fuzz_common as fz
+    fz.play_irregular(seed, checker_lib(), ENGINE, steps=20)
+
+
+@pytest.mark.parametrize("seed", [102000, 102001, 102002])
+def test_random_arena_batches_on_banded_maps(seed):
+    import fuzz_common as fz
+    fz.play_batch(seed, checker_lib(), ENGINE, n_arenas=2 + seed % 3, steps=10)
