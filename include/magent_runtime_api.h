@@ -53,7 +53,8 @@ int env_get_reward(EnvHandle game, GroupHandle group, float *buffer);  /* GridWo
  * extension names: arena_num (int[num_arenas]), arena_done (int[num_arenas]), hp (float[n], test aid)     */
 int env_get_info(EnvHandle game, GroupHandle group, const char *name, void *buffer);
 
-/* ---- render (reference: src/runtime_api.h:35-36); replay dump is out of scope: accepted, no-op ------- */
+/* ---- render (reference: src/runtime_api.h:35-36): replay dump of arena 0, byte-identical to the files the
+ * reference's RenderGenerator writes (src/gridworld/RenderGenerator.cc:107-185); cold path, host snapshot ---- */
 int env_render(EnvHandle game);
 int env_render_next_file(EnvHandle game);
 
