@@ -132,3 +132,14 @@ def test_random_games_on_banded_maps_with_an_irregular_caller(seed):
 def test_random_arena_batches_on_banded_maps(seed):
     import fuzz_common as fz
     fz.play_batch(seed, checker_lib(), ENGINE, n_arenas=2 + seed % 3, steps=10)
+
+
+def test_plain_c_caller_prints_the_same_trace_as_on_the_checker():
+    """tests/c/battle_caller.c: the same binary, host buffers, reference ABI only --
+    once on the checker library and once on the CUDA library"""
+    import c_caller_common as cc
+    want = cc.run(checker_lib(), steps=60, size=40, n=250)
+    got = cc.run(ENGINE, steps=60, size=40, n=250)
+    assert want.returncode == 0, want.stderr
+    assert got.returncode == 0, got.stderr
+    assert got.stdout == want.stdout
