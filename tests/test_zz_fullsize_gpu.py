@@ -143,3 +143,13 @@ def test_plain_c_caller_prints_the_same_trace_as_on_the_checker():
     assert want.returncode == 0, want.stderr
     assert got.returncode == 0, got.stderr
     assert got.stdout == want.stdout
+
+
+def test_two_huge_arenas_behind_one_handle():
+    """arena batch x whole-grid kernels: 2 arenas of 2x20000 agents (more than 32768 per arena, so every arena is
+    stepped by the cooperative grid one after the other); both arenas exactly against independent checkers and the
+    whole batch against the PyTorch restatement"""
+    A, size, n, seed = 2, 320, 20000, 60
+    env = batched_battle(A, size, n, seed)
+    samples = {a: pc.make_battle(checker_lib(), size, n, seed + a) for a in range(A)}
+    fs.play_battle_and_check(env, size, size, 4, 29, samples=samples, use_torch_obs=ON_GPU)
