@@ -153,3 +153,11 @@ def test_two_huge_arenas_behind_one_handle():
     env = batched_battle(A, size, n, seed)
     samples = {a: pc.make_battle(checker_lib(), size, n, seed + a) for a in range(A)}
     fs.play_battle_and_check(env, size, size, 4, 29, samples=samples, use_torch_obs=ON_GPU)
+
+
+def test_arena_whose_step_scratch_does_not_fit_shared_memory():
+    """2x4000 agents on 120x120: one CTA per arena, but 8000 agents x 41 B of step scratch exceed the 200 KB the
+    launch keeps in shared memory, so the scratch arrays stay in HBM (backend_cuda.cu launch_step)"""
+    want = pc.run_trace(pc.make_battle(checker_lib(), 120, 4000, 2), 8, 3, keep_obs=True)
+    got = pc.run_trace(pc.make_battle(ENGINE, 120, 4000, 2), 8, 3, keep_obs=True)
+    pc.compare_traces(want, got)
