@@ -18,6 +18,7 @@ A "step" is one pass of the hot path over one batch of synthetic input, through 
 Workloads (BASELINE.json configs; the default is the per-GPU share of configs[4], weak scaling):
     battle512  battle 200x200, 2x1000 agents, 512 independent arenas per GPU          [default]
     battle1    battle 200x200, 2x1000 agents, 1 arena                     (configs[1])
+    battle512_blocks  the dense two-block layout of examples/train_battle.py (2x1600), 512 arenas per GPU
     gather64   gather 200x200, 495 agents + 1847 food, 64 arenas          (configs[2])
     battle1m   battle 1000x1000, 2x400k agents, 1 arena (obs-render roofline; configs[3] as placeable)
     battle1m_sparse  battle 4472x4472, 2x500k agents, 1 arena (configs[3] in the reference's own 1 M geometry)
@@ -43,6 +44,9 @@ WORKLOADS = {
     "battle512": dict(desc="battle 200x200, 2x1000 agents random placement, 512 independent arenas per GPU "
                            "(per-GPU share of BASELINE configs[4]), uniform random actions",
                       game="battle", map_size=200, arenas=512, n=1000),
+    "battle512_blocks": dict(desc="battle 200x200, 2x1600 agents in the two facing blocks of examples/train_battle.py:15-40 "
+                                  "(dense fighting; SURVEY 8d 'dense variant'), 512 independent arenas per GPU",
+                             game="battle_blocks", map_size=200, arenas=512),
     "battle1": dict(desc="battle 200x200, 2x1000 agents, 1 arena (BASELINE configs[1]), uniform random actions",
                     game="battle", map_size=200, arenas=1, n=1000),
     "gather64": dict(desc="gather 200x200, 495 agents + 1847 food (examples/train_gather.py layout), 64 arenas "
@@ -69,6 +73,18 @@ def build_env(wl, lib, arenas, seed0=0):
         hs = env.get_handles()
         for h in hs:
             env.add_agents(h, method="random", n=wl["n"])
+        return env, list(hs)
+    if wl["game"] == "battle_blocks":
+        import math
+        size = wl["map_size"]
+        env = magent.GridWorld("battle", map_size=size, _lib=lib, **kw)
+        env.set_seed(seed0)
+        env.reset()
+        hs = env.get_handles()
+        gap, side = 3, int(math.sqrt(size * size * 0.04)) * 2
+        ys = range((size - side) // 2, (size - side) // 2 + side, 2)
+        env.add_agents(hs[0], method="custom", pos=[[x, y, 0] for x in range(size // 2 - gap - side, size // 2 - gap, 2) for y in ys])
+        env.add_agents(hs[1], method="custom", pos=[[x, y, 0] for x in range(size // 2 + gap, size // 2 + gap + side, 2) for y in ys])
         return env, list(hs)
     if wl["game"] == "gather":
         env = magent.GridWorld(pc.gather_config(wl["map_size"]), _lib=lib, **kw)
@@ -175,18 +191,20 @@ def run_cpu_baseline(workload, budget_steps=None):
                                   env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
                  for i in range(nproc)]
         outs = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in procs]
-        return sum(o["agent_steps"] for o in outs) / max(o["seconds"] for o in outs)
+        slowest = max(o["seconds"] for o in outs)
+        return sum(o["agent_steps"] for o in outs) / slowest, 1e3 * slowest / steps
     tried = {}
     if wl["arenas"] > 1:      # independent arenas: the CPU can run one per process
         for p in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
-            tried["%d procs x 1 thread" % p] = (launch(p, 1), p)
+            tried["%d procs x 1 thread" % p] = launch(p, 1) + (p,)
     else:                     # a single arena cannot be split across processes: one process, 1..N OpenMP threads
-        tried["1 proc x 1 thread"] = (launch(1, 1), 1)
+        tried["1 proc x 1 thread"] = launch(1, 1) + (1,)
     omp = min(cores, 16)                      # the reference's own harness uses 8-16 OpenMP threads (scripts/test/test_fps.py:22-36)
-    tried["1 proc x %d OpenMP threads" % omp] = (launch(1, omp), omp)
+    tried["1 proc x %d OpenMP threads" % omp] = launch(1, omp) + (omp,)
     how = max(tried, key=lambda k: tried[k][0])
-    best, used = tried[how]
+    best, ms_per_sample_step, used = tried[how]
     return {"value": best, "unit": UNIT, "cores": used, "kind": kind, "cores_usable": cores,
+            "ms_per_sample_step": ms_per_sample_step,
             "sample": "%s: one arena per process, %d timed steps after %d warm-up; tried %s -> best: %s"
                       % (wl["desc"].split(",")[0], steps, warm,
                          ", ".join("%s: %.3g" % (k, v[0]) for k, v in tried.items()), how)}
@@ -280,9 +298,10 @@ def main():
             return
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_sample_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "note": "CPU engine: rate of a bounded sample (one arena per process)"},
+            "config": {"workload": wl["desc"], "note": "CPU engine: rate of a bounded sample (one arena per process); ms_per_step = wall time of one "
+                                                    "loop iteration of that sample (all its processes in parallel)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
