@@ -13,8 +13,7 @@ in test time, so the full-size tests combine
         rebuilds EVERY agent's view and feature row from the engine's own positions / ids / last actions / last
         rewards and is compared bit for bit.  The hp an observer sees on a cell is taken from the occupant's own
         centre cell (`hp / max_hp` is the same float whoever looks at it), the in-range mask of the view is
-        learned from the data (the union of all marked cells) and checked for the 8-fold symmetry and, for
-        radius 6, the 113 cells of the reference's CircleRange(6) (Range.h:149-190).
+        CircleRange's `dx^2 + dy^2 <= R^2` (Range.h:149-190; 113 cells for radius 6).
 
 The restatement itself is pinned on the CPU against the compiled reference (tests/test_fullsize_cpu.py).
 """
@@ -153,13 +152,14 @@ def check_battle_observation(views, feats, pos, ids, nums, last_action, last_rew
                              expect_mask_cells=113):
     """views / feats: per-group float32 tensors as the engine returned them (any device).  Everything else numpy."""
     dev = views[0].device
-    mask = learned_mask(views)
-    assert mask is not None
-    m = mask
-    assert torch.equal(m, m.t()) and torch.equal(m, m.flip(0)) and torch.equal(m, m.flip(1)), "view mask not symmetric"
-    if expect_mask_cells is not None:
-        assert int(m.sum()) == expect_mask_cells, "view mask has %d cells" % int(m.sum())
     R = views[0].shape[1] // 2
+    # CircleRange(R) (Range.h:149-190): cells whose distance from the centre is < R + 1e-8, i.e. dx^2 + dy^2 <= R^2
+    d = torch.arange(-R, R + 1, device=dev)
+    mask = (d.view(-1, 1) ** 2 + d.view(1, -1) ** 2) <= R * R
+    if expect_mask_cells is not None:
+        assert int(mask.sum()) == expect_mask_cells
+    seen = learned_mask(views)
+    assert seen is not None and bool((seen & ~mask).sum() == 0), "something is marked outside the view range"
     centre = [v[:, R, R, 2].contiguous() for v in views]
     for g, c in enumerate(centre):
         assert bool(((c > 0) & (c <= 1)).all()), "group %d: a live observer's own hp/max_hp is outside (0, 1]" % g
@@ -249,3 +249,61 @@ def play_battle_and_check(env, width, height, steps, seed, samples=None, use_tor
         last_reward = [rew[g][keep[g]].astype(np.float32) for g in range(G)]
         nums = new_nums
     return t + 1
+
+
+def soak_battle_and_check(env, width, height, steps, seed, obs_every=8, use_torch_obs=False, speed=2,
+                          expect_mask_cells=113):
+    """Many steps of the throughput loop (uniform actions drawn on the device, `set_random_actions`) on a batched
+    battle environment with the whole-batch checks only: state invariants after every step, the PyTorch restatement
+    of every observation record every `obs_every` steps.  The actions are not known to the host, so the one-hot of
+    the last action is read from the feature row itself and only required to BE a one-hot (or empty before the first
+    action); everything else is rebuilt and compared bit for bit."""
+    hs = env.get_handles()
+    G = len(hs)
+    A = getattr(env, "num_arenas", 1)
+    n_action = env.get_action_space(hs[0])[0]
+    emb = env.get_feature_space(hs[0])[0] - n_action - 3
+    arena_nums = lambda: [env.get_arena_nums(h).astype(np.int64) if A > 1 else np.array([env.get_num(h)], dtype=np.int64)
+                          for h in hs]
+    nums = arena_nums()
+    last_reward = [np.zeros(int(n.sum()), dtype=np.float32) for n in nums]
+    prev = None
+    deaths = 0
+    for t in range(steps):
+        pos = [env.get_pos(h).copy() for h in hs]
+        ids = [env.get_agent_id(h).copy() for h in hs]
+        check_state(pos, ids, nums, width, height, prev=prev, speed=speed)
+        if t % obs_every == 0 or t == steps - 1:
+            if use_torch_obs:
+                obs = [env.get_observation_torch(h) for h in hs]
+                views, feats = [o[0] for o in obs], [o[1] for o in obs]
+            else:
+                obs = [env.get_observation(h) for h in hs]
+                views = [torch.from_numpy(o[0].copy()).to(device()) for o in obs]
+                feats = [torch.from_numpy(o[1].copy()).to(device()) for o in obs]
+            last_action = []
+            for g in range(G):
+                hot = feats[g][:, emb:emb + n_action]
+                assert bool(((hot == 0) | (hot == 1)).all()), "last-action slots hold something else than 0 / 1"
+                cnt = hot.sum(dim=1)
+                assert bool((cnt == (0 if t == 0 else 1)).all()), "last-action slots are not a one-hot"
+                la = hot.argmax(dim=1) if t > 0 else torch.full((hot.shape[0],), n_action, device=hot.device)
+                last_action.append(la.cpu().numpy().astype(np.int64))
+            check_battle_observation(views, feats, pos, ids, nums, last_action, last_reward, width, height,
+                                     expect_mask_cells=expect_mask_cells)
+        for h in hs:
+            env.set_random_actions(h, seed * 1000 + t)
+        env.step()
+        rew = [env.get_reward(h) for h in hs]
+        alive = [env.get_alive(h).astype(bool) for h in hs]
+        env.clear_dead()
+        prev = (ids, pos, nums)
+        new_nums = arena_nums()
+        for g in range(G):
+            ar = np.repeat(np.arange(len(nums[g])), nums[g])
+            np.testing.assert_array_equal(np.bincount(ar[alive[g]], minlength=len(nums[g])), new_nums[g],
+                                          err_msg="clear_dead kept a different number of agents than were alive")
+            deaths += int((~alive[g]).sum())
+        last_reward = [rew[g][alive[g]].astype(np.float32) for g in range(G)]
+        nums = new_nums
+    return deaths

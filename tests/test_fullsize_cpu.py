@@ -80,3 +80,18 @@ def test_batched_driver_on_the_host_emulation():
         env.add_agents(h, method="random", n=n)
     samples = {a: pc.make_battle(checker_lib(), size, n, 11 + a) for a in (0, 2)}
     fs.play_battle_and_check(env, size, size, 20, 5, samples=samples)
+
+
+def test_soak_driver_on_the_host_emulation():
+    """device-drawn actions, whole-batch checks only (the loop tests/test_zz_fullsize_gpu.py runs at full size)"""
+    if not os.path.exists(pc.EMU_LIB):
+        pytest.skip("tests/_emu not built")
+    import magent_b200 as magent
+    A, size, n = 3, 30, 200
+    env = magent.GridWorld("battle", map_size=size, _lib=pc.EMU_LIB, _num_arenas=A)
+    env.set_seed(4)
+    env.reset()
+    for h in env.get_handles():
+        env.add_agents(h, method="random", n=n)
+    deaths = fs.soak_battle_and_check(env, size, size, 40, 9, obs_every=5)
+    assert deaths > 0

@@ -161,3 +161,19 @@ def test_arena_whose_step_scratch_does_not_fit_shared_memory():
     want = pc.run_trace(pc.make_battle(checker_lib(), 120, 4000, 2), 8, 3, keep_obs=True)
     got = pc.run_trace(pc.make_battle(ENGINE, 120, 4000, 2), 8, 3, keep_obs=True)
     pc.compare_traces(want, got)
+
+
+SOAK_ARENAS = int(os.environ.get("MAGENT_FULLSIZE_SOAK_ARENAS", "512"))   # (smaller for a dry run on the CPU)
+
+
+@pytest.mark.parametrize("workload", ["battle512", "battle512_blocks"])
+def test_soak_of_the_throughput_loop(workload):
+    """40 steps of bench.py's own loop (actions drawn on the device) at its own size -- 512 arenas of 2x1000 randomly
+    placed agents, and of 2x1600 agents packed in two facing blocks (every move contended) -- with the whole-batch
+    checks: one agent per cell, ordered ids, bounded moves and exact survivor counts after every step, every
+    observation record against the PyTorch restatement every 10 steps"""
+    import bench
+    wl = bench.WORKLOADS[workload]
+    env, _ = bench.build_env(wl, ENGINE, SOAK_ARENAS, seed0=77)
+    size = wl["map_size"]
+    fs.soak_battle_and_check(env, size, size, 40, 13, obs_every=10, use_torch_obs=ON_GPU)
