@@ -485,3 +485,56 @@ def make_many_rules(lib, size=30, n=120, seed=5, n_rules=40, **kw):
     for h in env.get_handles():
         env.add_agents(h, method="random", n=n)
     return env
+
+
+# ------------------------------------------------------------------ the cold info getters (GridWorld.cc:717-894)
+def info_snapshot(env, with_mean=True):
+    """everything env_get_info serves besides num/id/pos/alive: spaces, view2attack + attack_base, groups_info,
+    walls_info, global_minimap (two shapes, every group as the viewer's channel 0), mean_info"""
+    import ctypes
+    out = {}
+    hs = env.get_handles()
+    out["groups_info"] = env._get_groups_info().copy()
+    out["walls_info"] = env._get_walls_info().copy()
+    for h in hs:
+        g = env._hv(h)
+        out["spaces", g] = (env.get_view_space(h), env.get_feature_space(h), env.get_action_space(h))
+        base, v2a = env.get_view2attack(h)
+        out["view2attack", g] = (base, v2a.copy())
+        for shape in ((5, 7), (10, 10)):
+            buf = np.empty(shape + (len(hs),), dtype=np.float32)
+            buf[0, 0, 0], buf[0, 0, 1] = shape
+            env._lib.env_get_info(env.game, g, b"global_minimap", buf.ctypes.data)
+            out["global_minimap", g, shape] = buf
+        if with_mean and env.get_num(h) > 0:
+            out["mean_info", g] = env.get_mean_info(h).copy()
+    return out
+
+
+def compare_info_snapshots(a, b, what=""):
+    assert a.keys() == b.keys(), what
+    for k in a:
+        if k[0] == "spaces":
+            assert a[k] == b[k], "%s %s" % (what, k)
+        elif k[0] == "view2attack":
+            assert a[k][0] == b[k][0], "%s attack_base %s" % (what, k)
+            np.testing.assert_array_equal(a[k][1], b[k][1], err_msg="%s %s" % (what, k))
+        elif k[0] in ("global_minimap", "mean_info"):
+            np.testing.assert_array_equal(a[k].view(np.uint32), b[k].view(np.uint32), err_msg="%s %s" % (what, k))
+        else:
+            np.testing.assert_array_equal(a[k], b[k], err_msg="%s %s" % (what, k))
+
+
+def play_and_compare_info(make, lib_a, lib_b, steps=6, seed=3):
+    ea, eb = make(lib_a), make(lib_b)
+    compare_info_snapshots(info_snapshot(ea, with_mean=False), info_snapshot(eb, with_mean=False), "before the first step")
+    rs = np.random.RandomState(seed)
+    for t in range(steps):
+        for h in ea.get_handles():
+            act = rs.randint(0, ea.get_action_space(h)[0], size=ea.get_num(h)).astype(np.int32)
+            ea.set_action(h, act)
+            eb.set_action(h, act)
+        ea.step(); eb.step()
+        compare_info_snapshots(info_snapshot(ea), info_snapshot(eb), "after step %d" % t)
+        ea.clear_dead(); eb.clear_dead()
+        compare_info_snapshots(info_snapshot(ea), info_snapshot(eb), "after clear_dead %d" % t)

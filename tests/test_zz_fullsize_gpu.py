@@ -177,3 +177,14 @@ def test_soak_of_the_throughput_loop(workload):
     env, _ = bench.build_env(wl, ENGINE, SOAK_ARENAS, seed0=77)
     size = wl["map_size"]
     fs.soak_battle_and_check(env, size, size, 40, 13, obs_every=10, use_torch_obs=ON_GPU)
+
+
+@pytest.mark.parametrize("which", ["battle", "pursuit", "mixed", "arrange"])
+def test_cold_info_getters_match_the_reference(which):
+    """view2attack / attack_base / groups_info / walls_info / global_minimap / mean_info (GridWorld.cc:717-894),
+    served from a host snapshot of the device state"""
+    if not os.path.exists(pc.REF_LIB):
+        pytest.skip("needs oracle/_ref (the C restatement does not serve the cold getters)")
+    make = {"battle": lambda lib: pc.make_battle(lib, 30, 120, 1), "pursuit": lambda lib: pc.make_pursuit(lib, 40, 2),
+            "mixed": lambda lib: pc.make_mixed(lib), "arrange": lambda lib: pc.make_arrange(lib)}[which]
+    pc.play_and_compare_info(make, pc.REF_LIB, ENGINE)
