@@ -163,6 +163,16 @@ def make_env(lib, seed, **kw):
         if rs.rand() < 0.3:                                   # explicit placements, some of them blocked or off the map
             pos = [[int(rs.randint(1, info["w"] - 1)), int(rs.randint(1, info["h"] - 1)), int(rs.randint(0, 4))] for _ in range(6)]
             env.add_agents(h, method="custom", pos=pos)
+    if seed % 5 == 4:                                         # rectangle fills (GridWorld.cc:180-290 "fill"): walls and agents,
+        rf = np.random.RandomState(seed + 104729)             # partly on occupied cells and across the border
+        for _ in range(int(rf.randint(1, 3))):
+            x, y = int(rf.randint(0, info["w"] - 2)), int(rf.randint(0, info["h"] - 2))
+            env.add_walls(method="fill", pos=(x, y), size=(int(rf.randint(1, 5)), int(rf.randint(1, 4))))
+        for _ in range(int(rf.randint(1, 4))):
+            h = handles[int(rf.randint(0, len(handles)))]
+            x, y = int(rf.randint(1, info["w"] - 3)), int(rf.randint(1, info["h"] - 3))
+            env.add_agents(h, method="fill", pos=(x, y), size=(int(rf.randint(1, 7)), int(rf.randint(1, 6))),
+                           dir=int(rf.randint(0, 4)))
     return env
 
 
