@@ -538,3 +538,71 @@ def play_and_compare_info(make, lib_a, lib_b, steps=6, seed=3):
         compare_info_snapshots(info_snapshot(ea), info_snapshot(eb), "after step %d" % t)
         ea.clear_dead(); eb.clear_dead()
         compare_info_snapshots(info_snapshot(ea), info_snapshot(eb), "after clear_dead %d" % t)
+
+
+# ------------------------------------------------------------------ extensions: select_arena, event counters
+def play_selected_arenas(engine_lib, checker_lib, steps=12):
+    """3 battle arenas behind one handle, set up DIFFERENTLY per arena through magent_b200_select_arena (own seed,
+    own walls, own extra agents), against 3 independent checker environments set up the same way; also checks the
+    per-arena cold getters and the device event counters (agent_steps, kills + starved = deaths, steps)."""
+    import magent_b200 as magent
+    A, size = 3, 28
+    seeds = [5, 40, 7]
+    extra = {0: [[3, 3, 0], [4, 3, 0], [5, 3, 0]], 2: [[20, 20, 0]]}
+    walls = {1: [[10, y, 0] for y in range(5, 15)], 2: [[x, 9, 0] for x in range(12, 18)]}
+    batch = magent.GridWorld("battle", map_size=size, _lib=engine_lib, _num_arenas=A)
+    singles = [magent.GridWorld("battle", map_size=size, _lib=checker_lib) for _ in range(A)]
+    batch.reset()
+    for a, env in enumerate(singles):
+        env.set_seed(seeds[a]); env.reset()
+        batch.select_arena(a); batch.set_seed(seeds[a])
+        if a in walls:
+            env.add_walls(method="custom", pos=walls[a]); batch.add_walls(method="custom", pos=walls[a])
+    batch.select_arena(-1)
+    for g in range(2):
+        for env in singles:
+            env.add_agents(env.get_handles()[g], method="random", n=90)
+        batch.add_agents(batch.get_handles()[g], method="random", n=90)
+    for a, pos in extra.items():
+        batch.select_arena(a)
+        batch.add_agents(batch.get_handles()[1], method="custom", pos=pos)
+        singles[a].add_agents(singles[a].get_handles()[1], method="custom", pos=pos)
+        np.testing.assert_array_equal(batch._get_walls_info(), singles[a]._get_walls_info())
+    batch.select_arena(-1)
+    hs = batch.get_handles()
+    c0 = batch.get_counters()
+    rs = np.random.RandomState(2)
+    agent_steps = deaths = 0
+    for t in range(steps):
+        nums = [batch.get_arena_nums(h) for h in hs]
+        for g, h in enumerate(hs):
+            assert list(nums[g]) == [s.get_num(s.get_handles()[g]) for s in singles]
+            v, f = batch.get_observation(h)
+            off = np.concatenate([[0], np.cumsum(nums[g])])
+            for a, s in enumerate(singles):
+                rv, rf = s.get_observation(s.get_handles()[g])
+                np.testing.assert_array_equal(v[off[a]:off[a + 1]].view(np.uint32), rv.view(np.uint32))
+                np.testing.assert_array_equal(f[off[a]:off[a + 1]].view(np.uint32), rf.view(np.uint32))
+            act = rs.randint(0, 21, size=int(nums[g].sum())).astype(np.int32)
+            batch.set_action(h, act)
+            agent_steps += act.size
+            for a, s in enumerate(singles):
+                s.set_action(s.get_handles()[g], np.ascontiguousarray(act[off[a]:off[a + 1]]))
+        batch.step()
+        for s in singles:
+            s.step()
+        for g, h in enumerate(hs):
+            alive = batch.get_alive(h)
+            deaths += int((~alive.astype(bool)).sum())
+            np.testing.assert_array_equal(alive, np.concatenate([s.get_alive(s.get_handles()[g]) for s in singles]))
+            np.testing.assert_array_equal(batch.get_pos(h), np.concatenate([s.get_pos(s.get_handles()[g]) for s in singles]))
+        batch.clear_dead()
+        for s in singles:
+            s.clear_dead()
+    c1 = batch.get_counters()
+    d = [b - a for a, b in zip(c0, c1)]
+    assert d[0] == agent_steps, "agent_steps counter %d, host count %d" % (d[0], agent_steps)
+    assert d[3] + d[4] == deaths, "kills %d + starved %d != deaths %d" % (d[3], d[4], deaths)
+    assert d[7] == steps, "steps counter %d" % d[7]          # counted once per env_step (step_phases.h: arena 0)
+    assert d[5] + d[6] > 0 and d[1] >= d[2] >= d[3]
+    return d

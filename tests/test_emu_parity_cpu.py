@@ -250,3 +250,10 @@ def test_cold_info_getters_match_the_reference(emu, which):
     make = {"battle": lambda lib: pc.make_battle(lib, 30, 120, 1), "pursuit": lambda lib: pc.make_pursuit(lib, 40, 2),
             "mixed": lambda lib: pc.make_mixed(lib), "arrange": lambda lib: pc.make_arrange(lib)}[which]
     pc.play_and_compare_info(make, pc.REF_LIB, emu)
+
+
+def test_select_arena_and_event_counters(emu):
+    """per-arena setup through magent_b200_select_arena; counters of the batch against host-side counts"""
+    checker = pc.REF_LIB if os.path.exists(pc.REF_LIB) else pc.PORT_LIB
+    d = pc.play_selected_arenas(emu, checker)
+    assert d[3] + d[4] > 0, "the scenario is supposed to see deaths"

@@ -188,3 +188,9 @@ def test_cold_info_getters_match_the_reference(which):
     make = {"battle": lambda lib: pc.make_battle(lib, 30, 120, 1), "pursuit": lambda lib: pc.make_pursuit(lib, 40, 2),
             "mixed": lambda lib: pc.make_mixed(lib), "arrange": lambda lib: pc.make_arrange(lib)}[which]
     pc.play_and_compare_info(make, pc.REF_LIB, ENGINE)
+
+
+def test_select_arena_and_event_counters():
+    """per-arena setup through magent_b200_select_arena (own seed, walls, extra agents per arena) against independent
+    checkers; the device event counters against host-side counts"""
+    pc.play_selected_arenas(ENGINE, checker_lib())
