@@ -541,7 +541,7 @@ def play_and_compare_info(make, lib_a, lib_b, steps=6, seed=3):
 
 
 # ------------------------------------------------------------------ extensions: select_arena, event counters
-def play_selected_arenas(engine_lib, checker_lib, steps=12):
+def play_selected_arenas(engine_lib, checker_lib, steps=40, n=160):
     """3 battle arenas behind one handle, set up DIFFERENTLY per arena through magent_b200_select_arena (own seed,
     own walls, own extra agents), against 3 independent checker environments set up the same way; also checks the
     per-arena cold getters and the device event counters (agent_steps, kills + starved = deaths, steps)."""
@@ -561,8 +561,8 @@ def play_selected_arenas(engine_lib, checker_lib, steps=12):
     batch.select_arena(-1)
     for g in range(2):
         for env in singles:
-            env.add_agents(env.get_handles()[g], method="random", n=90)
-        batch.add_agents(batch.get_handles()[g], method="random", n=90)
+            env.add_agents(env.get_handles()[g], method="random", n=n)
+        batch.add_agents(batch.get_handles()[g], method="random", n=n)
     for a, pos in extra.items():
         batch.select_arena(a)
         batch.add_agents(batch.get_handles()[1], method="custom", pos=pos)
