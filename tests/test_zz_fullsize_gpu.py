@@ -16,7 +16,7 @@ import pytest
 import fullsize_common as fs
 import parity_common as pc
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]      # (pytest-timeout: a stuck test fails instead of hanging the suite)
 
 ENGINE = os.environ.get("MAGENT_FULLSIZE_ENGINE", pc.CUDA_LIB)      # (tests/_emu library for a dry run on the CPU)
 ON_GPU = ENGINE == pc.CUDA_LIB
