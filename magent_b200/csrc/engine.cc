@@ -93,7 +93,9 @@ RangeTab make_sector_range(float angle, float radius, int parity) {
     return r;
 }
 
-void HostGroup::clear() { resize(0); dead_ct = 0; n_cull = 0; grp_reward = 0.0f; }
+// Group::clear (GridWorld.h:277-280) empties the agent list and dead_ct but leaves the group's next_reward alone: a
+// group reward that was not collected by clear_dead survives a reset (found by the chaotic-caller fuzz).
+void HostGroup::clear() { resize(0); dead_ct = 0; n_cull = 0; }
 void HostGroup::resize(int n) {
     x.resize(n); y.resize(n); id.resize(n); act.resize(n); op_obj.resize(n);
     hp.resize(n); next_reward.resize(n); last_reward.resize(n);
@@ -414,7 +416,10 @@ void Engine::reset() {                                // GridWorld.cc:72-118, Ma
     if (where_ == DEVICE) {                           // keep the RNG streams: they persist across reset
         std::vector<ArenaHdr> hdr(A_);
         be::d2h(hdr.data(), hE_.hdr, sizeof(ArenaHdr) * A_);
-        for (int a = 0; a < A_; ++a) arenas_[a].rng = hdr[a].rng;
+        for (int a = 0; a < A_; ++a) {
+            arenas_[a].rng = hdr[a].rng;
+            for (int g = 0; g < (int)arenas_[a].groups.size(); ++g) arenas_[a].groups[g].grp_reward = hdr[a].grp_reward[g];
+        }
         where_ = HOST;
     }
     file_ct_++; frame_ct_ = 0;                        // RenderGenerator::next_file (GridWorld.cc:97)

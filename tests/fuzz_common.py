@@ -291,3 +291,77 @@ def play_batch(seed, checker_lib, engine_lib, n_arenas=3, steps=15):
         batch.clear_dead()
         for env in singles:
             env.clear_dead()
+
+
+def trace_chaotic(env, steps, seed, acting, order):
+    """A caller that reads at every point of the loop: observations and rewards are fetched (from random groups, also
+    non-acting ones) before set_action, between set_action calls, after step, after clear_dead and twice in a row;
+    the acting subset changes from step to step; the episode is reset and repopulated once in the middle.  Every
+    value read is recorded in call order, so two engines must agree on all of them (state-version caches of the
+    observation pre-passes and host-side count caches are what this is after)."""
+    handles = env.get_handles()
+    rs = np.random.RandomState(seed ^ 0x2c1b3)
+    log = []
+    free = (env.config.config_dict["map_width"] - 2) * (env.config.config_dict["map_height"] - 2)
+
+    def peek(tag):
+        r = rs.rand()
+        if r < 0.45:
+            gi = int(rs.randint(0, len(handles)))
+            if env.get_num(handles[gi]) > 0:
+                v, f = env.get_observation(handles[gi])
+                log.append((tag + " obs g%d" % gi, v.copy(), f.copy()))
+                if rs.rand() < 0.2:
+                    v, f = env.get_observation(handles[gi])
+                    log.append((tag + " obs again g%d" % gi, v.copy(), f.copy()))
+        elif r < 0.65:
+            gi = int(rs.randint(0, len(handles)))
+            log.append((tag + " reward g%d" % gi, env.get_reward(handles[gi]).copy()))
+        elif r < 0.8:
+            gi = int(rs.randint(0, len(handles)))
+            log.append((tag + " state g%d" % gi, env.get_pos(handles[gi]).copy(), env.get_agent_id(handles[gi]).copy(),
+                        env.get_alive(handles[gi]).copy().astype(np.uint8)))
+
+    for t in range(steps):
+        if t == steps // 2:                                  # a new episode in the same process: the RNG stream goes on
+            env.reset()
+            for gi, h in enumerate(handles):
+                env.add_agents(h, method="random", n=int(rs.randint(1, 2 + free // (40 * len(handles)))))
+            log.append(("reset", np.array([env.get_num(h) for h in handles])))
+        peek("t%d top" % t)
+        now = [g for g in order if rs.rand() < 0.8]
+        for gi in now:
+            n = env.get_num(handles[gi])
+            env.set_action(handles[gi], rs.randint(0, env.get_action_space(handles[gi])[0], size=n).astype(np.int32))
+            peek("t%d after set_action g%d" % (t, gi))
+        done = env.step()
+        log.append(("t%d done" % t, np.array([int(done)] + [env.get_num(h) for h in handles])))
+        peek("t%d after step" % t)
+        peek("t%d after step (2)" % t)
+        if rs.rand() < 0.8:
+            env.clear_dead()
+            peek("t%d after clear_dead" % t)
+        for gi, h in enumerate(handles):
+            log.append(("t%d end g%d" % (t, gi), env.get_pos(h).copy(), env.get_agent_id(h).copy()))
+    return log
+
+
+def play_chaotic(seed, lib_a, lib_b, steps=24, **kw):
+    rs = np.random.RandomState(seed)
+    n_groups = len(make_env(lib_a, seed).get_handles())
+    order = [int(g) for g in rs.permutation(n_groups)]
+    a = trace_chaotic(make_env(lib_a, seed), steps, seed, None, order)
+    b = trace_chaotic(make_env(lib_b, seed, **kw), steps, seed, None, order)
+    assert len(a) == len(b), "chaotic fuzz seed %d: %d vs %d records" % (seed, len(a), len(b))
+    for ra, rb in zip(a, b):
+        assert ra[0] == rb[0], "chaotic fuzz seed %d: %s vs %s" % (seed, ra[0], rb[0])
+        for xa, xb in zip(ra[1:], rb[1:]):
+            what = "chaotic fuzz seed %d: %s" % (seed, ra[0])
+            assert xa.shape == xb.shape, what + " shape %s vs %s" % (xa.shape, xb.shape)
+            if xa.dtype == np.float32 and " reward" in ra[0]:
+                np.testing.assert_allclose(xa, xb, rtol=0, atol=pc.REWARD_TOL, err_msg=what)
+            elif xa.dtype == np.float32:
+                np.testing.assert_array_equal(xa.view(np.uint32), xb.view(np.uint32), err_msg=what)
+            else:
+                np.testing.assert_array_equal(xa, xb, err_msg=what)
+    return a

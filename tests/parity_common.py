@@ -606,3 +606,36 @@ def play_selected_arenas(engine_lib, checker_lib, steps=40, n=160):
     assert d[7] == steps, "steps counter %d" % d[7]          # counted once per env_step (step_phases.h: arena 0)
     assert d[5] + d[6] > 0 and d[1] >= d[2] >= d[3]
     return d
+
+
+def group_reward_across_reset(lib):
+    """two agents of group 0 next to one of group 1; every attack of group 0 pays 1.0 to the whole group 0
+    (receiver index 'all' = group reward).  Returns [rewards after the step, rewards of the fresh episode before and
+    after its first clear_dead]."""
+    import magent_b200 as magent
+    gw = magent.gridworld
+    cfg = gw.Config()
+    cfg.set({"map_width": 12, "map_height": 12})
+    t = cfg.register_agent_type("t", dict(width=1, length=1, hp=10, speed=1, view_range=gw.CircleRange(3),
+                                          attack_range=gw.CircleRange(1), damage=1, step_recover=0, step_reward=0.25))
+    g0, g1 = cfg.add_group(t), cfg.add_group(t)
+    a, b = gw.AgentSymbol(g0, index='any'), gw.AgentSymbol(g1, index='any')
+    cfg.add_reward_rule(gw.Event(a, 'attack', b), receiver=gw.AgentSymbol(g0, index='all'), value=1.0)
+    env = magent.GridWorld(cfg, _lib=lib)
+    env.reset()
+    h0, h1 = env.get_handles()
+    env.add_agents(h0, method="custom", pos=[[5, 5], [8, 8]])
+    env.add_agents(h1, method="custom", pos=[[6, 5]])
+    base, v2a = env.get_view2attack(h0)
+    hit = base + int(v2a[v2a.shape[0] // 2, v2a.shape[1] // 2 + 1])          # attack the cell to the east
+    env.set_action(h0, np.array([hit, 0], dtype=np.int32))
+    env.set_action(h1, np.array([0], dtype=np.int32))
+    env.step()
+    out = [env.get_reward(h0).copy()]
+    env.reset()                                                               # no clear_dead before the new episode
+    env.add_agents(h0, method="custom", pos=[[2, 2], [3, 3], [4, 4]])
+    env.add_agents(h1, method="custom", pos=[[9, 9]])
+    out.append(env.get_reward(h0).copy())
+    env.clear_dead()
+    out.append(env.get_reward(h0).copy())
+    return out

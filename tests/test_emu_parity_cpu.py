@@ -257,3 +257,15 @@ def test_select_arena_and_event_counters(emu):
     checker = pc.REF_LIB if os.path.exists(pc.REF_LIB) else pc.PORT_LIB
     d = pc.play_selected_arenas(emu, checker)
     assert d[3] + d[4] > 0, "the scenario is supposed to see deaths"
+
+
+def test_uncollected_group_reward_survives_reset(emu):
+    """Group::clear (GridWorld.h:277-280) keeps the group's next_reward: a group reward earned in the last step of an
+    episode that ends without clear_dead is still added to every get_reward of the next episode until clear_dead"""
+    checker = pc.REF_LIB if os.path.exists(pc.REF_LIB) else pc.PORT_LIB
+    outs = []
+    for lib in (checker, emu):
+        outs.append(pc.group_reward_across_reset(lib))
+    assert outs[0][0].max() > 0.5, "the scenario is supposed to earn a group reward"
+    for a, b in zip(*outs):
+        np.testing.assert_allclose(a, b, rtol=0, atol=pc.REWARD_TOL)

@@ -58,3 +58,16 @@ def test_emulated_engine_on_banded_maps_with_an_irregular_caller(emu, seed):
 @pytest.mark.parametrize("seed", [102000, 102001])
 def test_emulated_arena_batch_on_banded_maps(emu, seed):
     fz.play_batch(seed, CHECKER, emu, n_arenas=2 + seed % 2, steps=8)
+
+
+# a caller that reads at every point of the loop, changes the acting subset every step and resets in mid-run
+# (fuzz_common.trace_chaotic); found: a group reward that clear_dead has not collected survives reset()
+@pytest.mark.parametrize("seed", list(range(40000, 40016)) + [40029, 110000, 110001])
+def test_emulated_engine_matches_checker_with_a_chaotic_caller(emu, seed):
+    fz.play_chaotic(seed, CHECKER, emu)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs oracle/_ref (the compiled reference)")
+@pytest.mark.parametrize("seed", list(range(43000, 43008)))
+def test_oracle_port_matches_reference_with_a_chaotic_caller(seed):
+    fz.play_chaotic(seed, pc.REF_LIB, pc.PORT_LIB)

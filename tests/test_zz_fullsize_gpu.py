@@ -194,3 +194,17 @@ def test_select_arena_and_event_counters():
     """per-arena setup through magent_b200_select_arena (own seed, walls, extra agents per arena) against independent
     checkers; the device event counters against host-side counts"""
     pc.play_selected_arenas(ENGINE, checker_lib())
+
+
+@pytest.mark.parametrize("seed", list(range(40000, 40024)) + [40029, 110000, 110001, 110002])
+def test_random_games_with_a_chaotic_caller(seed):
+    """reads at every point of the loop, acting subset changes every step, reset in mid-run (fuzz_common.trace_chaotic)"""
+    import fuzz_common as fz
+    fz.play_chaotic(seed, checker_lib(), ENGINE)
+
+
+def test_uncollected_group_reward_survives_reset():
+    want = pc.group_reward_across_reset(checker_lib())
+    got = pc.group_reward_across_reset(ENGINE)
+    for a, b in zip(want, got):
+        np.testing.assert_allclose(a, b, rtol=0, atol=pc.REWARD_TOL)
