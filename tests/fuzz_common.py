@@ -334,6 +334,14 @@ def trace_chaotic(env, steps, seed, acting, order):
             n = env.get_num(handles[gi])
             env.set_action(handles[gi], rs.randint(0, env.get_action_space(handles[gi])[0], size=n).astype(np.int32))
             peek("t%d after set_action g%d" % (t, gi))
+            if rs.rand() < 0.06:                             # setup calls between set_action and step: the newcomers have
+                gj = int(rs.randint(0, len(handles)))        # no action this step, walls may block queued moves
+                env.add_agents(handles[gj], method="random", n=int(rs.randint(1, 3)))
+                log.append(("t%d late add g%d" % (t, gj), np.array([env.get_num(h) for h in handles])))
+            if rs.rand() < 0.04:
+                env.add_walls(method="random", n=int(rs.randint(1, 4)))
+            if rs.rand() < 0.03:
+                env.set_seed(int(rs.randint(0, 1000)))
         done = env.step()
         log.append(("t%d done" % t, np.array([int(done)] + [env.get_num(h) for h in handles])))
         peek("t%d after step" % t)
