@@ -314,6 +314,12 @@ def trace_chaotic(env, steps, seed, acting, order):
                 if rs.rand() < 0.2:
                     v, f = env.get_observation(handles[gi])
                     log.append((tag + " obs again g%d" % gi, v.copy(), f.copy()))
+                if rs.rand() < 0.25:                         # the compact hand-off on the same state: the engine's f16 call
+                    if getattr(env._lib, "is_b200", False):  # against the checker's float32 observation rounded to f16
+                        v, f = env.get_observation_f16(handles[gi])
+                        log.append((tag + " obs f16 g%d" % gi, v.copy(), f.copy()))
+                    else:
+                        log.append((tag + " obs f16 g%d" % gi, v.astype(np.float16), f.astype(np.float16)))
         elif r < 0.65:
             gi = int(rs.randint(0, len(handles)))
             log.append((tag + " reward g%d" % gi, env.get_reward(handles[gi]).copy()))
@@ -370,6 +376,8 @@ def play_chaotic(seed, lib_a, lib_b, steps=24, **kw):
                 np.testing.assert_allclose(xa, xb, rtol=0, atol=pc.REWARD_TOL, err_msg=what)
             elif xa.dtype == np.float32:
                 np.testing.assert_array_equal(xa.view(np.uint32), xb.view(np.uint32), err_msg=what)
+            elif xa.dtype == np.float16:
+                np.testing.assert_array_equal(xa.view(np.uint16), xb.view(np.uint16), err_msg=what)
             else:
                 np.testing.assert_array_equal(xa, xb, err_msg=what)
     return a
