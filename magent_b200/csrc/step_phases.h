@@ -350,7 +350,14 @@ MG_HD bool phase_attack_relax(Ctx &c, const EngineDev &E, const StepArgs &S, int
             const int sg = flat_group(E, bs);
             if (E.food_mode && friendly_fire_refused(E, sg, g)) continue;   // listed only as a potential eater
             hp -= E.grp[sg].damage;
-            if (hp < 0.0f) { dn = best; break; }
+            if (hp < 0.0f) {
+                dn = best;
+                if (bs == ft) {                          // my own blow killed me: do_attack still feeds the (dead) killer the
+                    const float nh = hp + G.kill_supply; // victim's kill_supply (Map.cc:268-273) -- visible only as the hp of
+                    hp = G.max_hp < nh ? G.max_hp : nh;  // an un-culled corpse in the replay dump
+                }
+                break;
+            }
         }
         E.hp_fin[f] = hp;
         if (dn != E.death[f]) { st_volatile(&E.death[f], dn); changed = true; }

@@ -293,7 +293,7 @@ def play_batch(seed, checker_lib, engine_lib, n_arenas=3, steps=15):
             env.clear_dead()
 
 
-def trace_chaotic(env, steps, seed, acting, order):
+def trace_chaotic(env, steps, seed, acting, order, render_dir=None):
     """A caller that reads at every point of the loop: observations and rewards are fetched (from random groups, also
     non-acting ones) before set_action, between set_action calls, after step, after clear_dead and twice in a row;
     the acting subset changes from step to step; the episode is reset and repopulated once in the middle.  Every
@@ -304,8 +304,25 @@ def trace_chaotic(env, steps, seed, acting, order):
     log = []
     free = (env.config.config_dict["map_width"] - 2) * (env.config.config_dict["map_height"] - 2)
 
+    if render_dir is not None:
+        env.set_render_dir(render_dir)
+    W, H = env.config.config_dict["map_width"], env.config.config_dict["map_height"]
+
     def peek(tag):
         r = rs.rand()
+        if render_dir is not None and r > 0.8:               # the cold path: replay frames, window queries, density maps
+            q = rs.rand()
+            if q < 0.4:
+                if all(env.get_num(h) > 0 for h in handles):   # RenderGenerator.cc:151 reads agents[0] of every group
+                    env.render()
+            elif q < 0.7:
+                x0, y0 = int(rs.randint(0, W - 3)), int(rs.randint(0, H - 3))
+                info, events = env._get_render_info((x0, x0 + int(rs.randint(2, W))), (y0, y0 + int(rs.randint(2, H))))
+                rows = np.array(sorted([k] + list(v) for k, v in info.items()), dtype=np.int64).reshape(-1, 4)
+                log.append((tag + " window", rows, np.asarray(events, dtype=np.int64).reshape(-1, 3)))
+            else:
+                log.append((tag + " global_minimap", env.get_global_minimap(int(rs.randint(2, 9)), int(rs.randint(2, 9))).copy()))
+            return
         if r < 0.45:
             gi = int(rs.randint(0, len(handles)))
             if env.get_num(handles[gi]) > 0:
@@ -357,6 +374,10 @@ def trace_chaotic(env, steps, seed, acting, order):
             peek("t%d after clear_dead" % t)
         for gi, h in enumerate(handles):
             log.append(("t%d end g%d" % (t, gi), env.get_pos(h).copy(), env.get_agent_id(h).copy()))
+    if render_dir is not None:
+        import os
+        for name in sorted(os.listdir(render_dir)):
+            log.append(("file " + name, np.frombuffer(open(os.path.join(render_dir, name), "rb").read(), dtype=np.uint8)))
     return log
 
 
@@ -364,8 +385,15 @@ def play_chaotic(seed, lib_a, lib_b, steps=24, **kw):
     rs = np.random.RandomState(seed)
     n_groups = len(make_env(lib_a, seed).get_handles())
     order = [int(g) for g in rs.permutation(n_groups)]
-    a = trace_chaotic(make_env(lib_a, seed), steps, seed, None, order)
-    b = trace_chaotic(make_env(lib_b, seed, **kw), steps, seed, None, order)
+    import tempfile
+    can_render = all(l != pc.PORT_LIB for l in (lib_a, lib_b))           # the C restatement has no replay dump
+    da, db = (tempfile.mkdtemp(), tempfile.mkdtemp()) if can_render else (None, None)
+    a = trace_chaotic(make_env(lib_a, seed), steps, seed, None, order, render_dir=da)
+    b = trace_chaotic(make_env(lib_b, seed, **kw), steps, seed, None, order, render_dir=db)
+    for d in (da, db):
+        if d is not None:
+            import shutil
+            shutil.rmtree(d, ignore_errors=True)
     assert len(a) == len(b), "chaotic fuzz seed %d: %d vs %d records" % (seed, len(a), len(b))
     for ra, rb in zip(a, b):
         assert ra[0] == rb[0], "chaotic fuzz seed %d: %s vs %s" % (seed, ra[0], rb[0])

@@ -61,8 +61,9 @@ def test_emulated_arena_batch_on_banded_maps(emu, seed):
 
 
 # a caller that reads at every point of the loop, changes the acting subset every step and resets in mid-run
-# (fuzz_common.trace_chaotic); found: a group reward that clear_dead has not collected survives reset()
-@pytest.mark.parametrize("seed", list(range(40000, 40016)) + [40029, 110000, 110001])
+# (fuzz_common.trace_chaotic), replay frames / window queries / density maps included; found: a group reward that
+# clear_dead has not collected survives reset(); a long body that kills itself is still fed its own kill_supply (corpse hp)
+@pytest.mark.parametrize("seed", list(range(40000, 40016)) + [40029, 47002, 47012, 47086, 110000, 110001, 113018])
 def test_emulated_engine_matches_checker_with_a_chaotic_caller(emu, seed):
     fz.play_chaotic(seed, CHECKER, emu)
 

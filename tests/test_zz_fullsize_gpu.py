@@ -196,7 +196,7 @@ def test_select_arena_and_event_counters():
     pc.play_selected_arenas(ENGINE, checker_lib())
 
 
-@pytest.mark.parametrize("seed", list(range(40000, 40024)) + [40029, 110000, 110001, 110002])
+@pytest.mark.parametrize("seed", list(range(40000, 40024)) + [40029, 47002, 47012, 47086, 47170, 110000, 110001, 110002, 113018])
 def test_random_games_with_a_chaotic_caller(seed):
     """reads at every point of the loop, acting subset changes every step, reset in mid-run (fuzz_common.trace_chaotic)"""
     import fuzz_common as fz
