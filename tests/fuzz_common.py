@@ -303,6 +303,13 @@ def trace_chaotic(env, steps, seed, acting, order, render_dir=None):
     rs = np.random.RandomState(seed ^ 0x2c1b3)
     log = []
     free = (env.config.config_dict["map_width"] - 2) * (env.config.config_dict["map_height"] - 2)
+    attack_bias = float(rs.choice([0.0, 0.5, 0.85]))
+    attack_base = []                                         # (not get_view2attack: it writes the attack cells into a
+    for h in handles:                                        #  view-sized buffer, out of bounds when the attack range is
+        import ctypes                                        #  the wider one -- in the reference as well)
+        base = ctypes.c_int(0)
+        env._lib.env_get_info(env.game, env._hv(h), b"attack_base", ctypes.cast(ctypes.byref(base), ctypes.c_void_p))
+        attack_base.append(base.value)
 
     if render_dir is not None:
         env.set_render_dir(render_dir)
@@ -355,7 +362,12 @@ def trace_chaotic(env, steps, seed, acting, order, render_dir=None):
         now = [g for g in order if rs.rand() < 0.8]
         for gi in now:
             n = env.get_num(handles[gi])
-            env.set_action(handles[gi], rs.randint(0, env.get_action_space(handles[gi])[0], size=n).astype(np.int32))
+            n_act = env.get_action_space(handles[gi])[0]
+            act = rs.randint(0, n_act, size=n).astype(np.int32)
+            if attack_bias > 0 and attack_base[gi] < n_act:   # bloodier episodes: kill chains, mutual and self kills
+                hit = rs.rand(n) < attack_bias
+                act[hit] = rs.randint(attack_base[gi], n_act, size=int(hit.sum()))
+            env.set_action(handles[gi], act)
             peek("t%d after set_action g%d" % (t, gi))
             if rs.rand() < 0.06:                             # setup calls between set_action and step: the newcomers have
                 gj = int(rs.randint(0, len(handles)))        # no action this step, walls may block queued moves
