@@ -639,3 +639,44 @@ def group_reward_across_reset(lib):
     env.clear_dead()
     out.append(env.get_reward(h0).copy())
     return out
+
+
+def self_kill_frames(lib, render_dir, action=None):
+    """a 1x2 body whose type may attack its own group aims at one of its own cells and kills itself; Map::do_attack
+    then feeds the (dead) killer its victim's kill_supply (Map.cc:265-273), which the replay dump shows as the hp of
+    the un-culled corpse.  With action=None: returns the first attack action that makes the lone agent die."""
+    import magent_b200 as magent
+    gw = magent.gridworld
+
+    def make():
+        cfg = gw.Config()
+        cfg.set({"map_width": 10, "map_height": 10})
+        t = cfg.register_agent_type("t", dict(width=1, length=2, hp=1.0, speed=0, view_range=gw.CircleRange(2),
+                                              attack_range=gw.CircleRange(1.5), damage=2.0, step_recover=0.0,
+                                              kill_supply=1.5, attack_in_group=1, kill_reward=3.0, dead_penalty=-0.5))
+        cfg.add_group(t)
+        env = magent.GridWorld(cfg, _lib=lib)
+        env.reset()
+        env.add_agents(env.get_handles()[0], method="custom", pos=[[4, 4], [7, 2]])
+        return env
+    if action is None:
+        n_act = make().get_action_space(make().get_handles()[0])[0]
+        for a in range(n_act):
+            env = make()
+            h = env.get_handles()[0]
+            env.set_action(h, np.array([a, 0], dtype=np.int32))
+            env.step()
+            if not env.get_alive(h)[0]:
+                return a
+        raise AssertionError("no attack action makes the agent kill itself")
+    os.makedirs(render_dir, exist_ok=True)
+    env = make()
+    env.set_render_dir(render_dir)
+    h = env.get_handles()[0]
+    env.set_action(h, np.array([action, 0], dtype=np.int32))
+    env.step()
+    rew = env.get_reward(h).copy()
+    env.render()                                            # before clear_dead: the corpse is still listed
+    env.clear_dead()
+    env.render()
+    return rew, {n: open(os.path.join(render_dir, n), "rb").read() for n in sorted(os.listdir(render_dir))}

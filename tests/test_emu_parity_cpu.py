@@ -269,3 +269,16 @@ def test_uncollected_group_reward_survives_reset(emu):
     assert outs[0][0].max() > 0.5, "the scenario is supposed to earn a group reward"
     for a, b in zip(*outs):
         np.testing.assert_allclose(a, b, rtol=0, atol=pc.REWARD_TOL)
+
+
+def test_self_kill_feeds_the_corpse(emu, tmp_path):
+    """found by the chaotic fuzz: hp of an un-culled corpse in the replay dump after a self-aimed in-group attack"""
+    if not os.path.exists(pc.REF_LIB):
+        pytest.skip("needs the compiled reference (replay dump)")
+    act = pc.self_kill_frames(pc.REF_LIB, None)
+    want = pc.self_kill_frames(pc.REF_LIB, str(tmp_path / "ref"), act)
+    got = pc.self_kill_frames(emu, str(tmp_path / "emu"), act)
+    np.testing.assert_allclose(want[0], got[0], rtol=0, atol=pc.REWARD_TOL)
+    assert want[1] == got[1]
+    frame = want[1]["video_1.txt"].decode().splitlines()
+    assert any(l.split()[:2] == ["0", "50"] for l in frame), frame       # corpse: hp = -1 + 1.5 = 0.5 of 1.0 -> "50"
