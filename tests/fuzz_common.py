@@ -421,3 +421,99 @@ def play_chaotic(seed, lib_a, lib_b, steps=24, **kw):
             else:
                 np.testing.assert_array_equal(xa, xb, err_msg=what)
     return a
+
+
+def play_batch_chaotic(seed, checker_lib, engine_lib, n_arenas=3, steps=16):
+    """The chaotic caller on an arena batch: `_num_arenas` arenas behind one engine handle against n_arenas independent
+    checker environments (arena a seeded seed0 + a).  Reads happen at every point of the loop and are compared on the
+    spot; the acting subset changes every step; clear_dead is skipped now and then; agents are added late to ALL arenas
+    (random placement, each arena from its own RNG stream) or, through magent_b200_select_arena, to ONE arena at explicit
+    positions; one reset in mid-run."""
+    import magent_b200 as magent
+    cfg, info = random_config(seed)
+    rs = np.random.RandomState(seed + 15485863)
+    seed0 = int(rs.randint(0, 10000))
+    batch = magent.GridWorld(cfg, _lib=engine_lib, _num_arenas=n_arenas)
+    singles = [magent.GridWorld(random_config(seed)[0], _lib=checker_lib) for _ in range(n_arenas)]
+    both = [batch] + singles
+    G = len(batch.get_handles())
+    free = (info["w"] - 2) * (info["h"] - 2)
+    what = "batch-chaotic seed %d" % seed
+
+    def H(env, g):
+        return env.get_handles()[g]
+
+    def populate(scale):
+        for g in range(G):
+            bw, bl = info["bodies"][g]
+            n = max(1, int(free * scale * float(rs.choice([0.03, 0.08])) / (bw * bl) / G * 2))
+            for env in both:
+                env.add_agents(H(env, g), method="random", n=n)
+
+    batch.set_seed(seed0)
+    batch.reset()
+    for a, env in enumerate(singles):
+        env.set_seed(seed0 + a)
+        env.reset()
+    n_walls = int(rs.randint(0, max(1, free // 30)))
+    for env in both:
+        env.add_walls(method="random", n=n_walls)
+    populate(1.0)
+
+    def cat(parts, shape_tail=None):
+        parts = [p for p in parts if p.shape[0]]
+        return np.concatenate(parts) if parts else None
+
+    def peek(tag):
+        r, g = rs.rand(), int(rs.randint(0, G))
+        nums = [env.get_num(H(env, g)) for env in singles]
+        assert batch.get_num(H(batch, g)) == sum(nums), "%s %s num g%d" % (what, tag, g)
+        np.testing.assert_array_equal(batch.get_arena_nums(H(batch, g)), nums, err_msg="%s %s arena_num" % (what, tag))
+        if sum(nums) == 0:
+            return
+        if r < 0.45:
+            v, f = batch.get_observation(H(batch, g))
+            parts = [env.get_observation(H(env, g)) for env, n in zip(singles, nums) if n]
+            np.testing.assert_array_equal(v.view(np.uint32), np.concatenate([p[0] for p in parts]).view(np.uint32), err_msg="%s %s view g%d" % (what, tag, g))
+            np.testing.assert_array_equal(f.view(np.uint32), np.concatenate([p[1] for p in parts]).view(np.uint32), err_msg="%s %s feature g%d" % (what, tag, g))
+        elif r < 0.7:
+            np.testing.assert_allclose(batch.get_reward(H(batch, g)), np.concatenate([env.get_reward(H(env, g)) for env in singles]),
+                                       rtol=0, atol=pc.REWARD_TOL, err_msg="%s %s reward g%d" % (what, tag, g))
+        else:
+            np.testing.assert_array_equal(batch.get_pos(H(batch, g)).reshape(-1, 2), np.concatenate([env.get_pos(H(env, g)).reshape(-1, 2) for env in singles]), err_msg="%s %s pos g%d" % (what, tag, g))
+            np.testing.assert_array_equal(batch.get_agent_id(H(batch, g)), np.concatenate([env.get_agent_id(H(env, g)) for env in singles]), err_msg="%s %s id g%d" % (what, tag, g))
+            np.testing.assert_array_equal(batch.get_alive(H(batch, g)), np.concatenate([env.get_alive(H(env, g)) for env in singles]), err_msg="%s %s alive g%d" % (what, tag, g))
+
+    for t in range(steps):
+        if t == steps // 2:
+            for env in both:
+                env.reset()
+            populate(0.5)
+        peek("t%d top" % t)
+        for g in [int(x) for x in rs.permutation(G) if rs.rand() < 0.8]:
+            n_act = batch.get_action_space(H(batch, g))[0]
+            acts = [rs.randint(0, n_act, size=env.get_num(H(env, g))).astype(np.int32) for env in singles]
+            batch.set_action(H(batch, g), np.concatenate(acts))
+            for env, a in zip(singles, acts):
+                env.set_action(H(env, g), a)
+            peek("t%d after set_action g%d" % (t, g))
+            if rs.rand() < 0.08:
+                gj, k = int(rs.randint(0, G)), int(rs.randint(1, 3))
+                for env in both:
+                    env.add_agents(H(env, gj), method="random", n=k)
+            if rs.rand() < 0.08:                              # one arena only, explicit positions (some of them taken)
+                a, gj = int(rs.randint(0, n_arenas)), int(rs.randint(0, G))
+                pos = [[int(rs.randint(1, info["w"] - 1)), int(rs.randint(1, info["h"] - 1)), int(rs.randint(0, 4))] for _ in range(3)]
+                batch.select_arena(a)
+                batch.add_agents(H(batch, gj), method="custom", pos=pos)
+                batch.select_arena(-1)
+                singles[a].add_agents(H(singles[a], gj), method="custom", pos=pos)
+        batch.step()
+        dones = [env.step() for env in singles]
+        np.testing.assert_array_equal(batch.get_arena_done() != 0, np.array(dones), err_msg="%s t%d done" % (what, t))
+        peek("t%d after step" % t)
+        peek("t%d after step (2)" % t)
+        if rs.rand() < 0.8:
+            for env in both:
+                env.clear_dead()
+            peek("t%d after clear_dead" % t)

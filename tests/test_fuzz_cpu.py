@@ -72,3 +72,9 @@ def test_emulated_engine_matches_checker_with_a_chaotic_caller(emu, seed):
 @pytest.mark.parametrize("seed", list(range(43000, 43008)))
 def test_oracle_port_matches_reference_with_a_chaotic_caller(seed):
     fz.play_chaotic(seed, pc.REF_LIB, pc.PORT_LIB)
+
+
+@pytest.mark.parametrize("seed", list(range(60000, 60010)) + [115000, 115001])
+def test_emulated_arena_batch_with_a_chaotic_caller(emu, seed):
+    """reads at every point of the loop, late adds to all arenas and (select_arena) to one, mid-run reset"""
+    fz.play_batch_chaotic(seed, CHECKER, emu, n_arenas=1 + seed % 4)

@@ -219,3 +219,9 @@ def test_self_kill_feeds_the_corpse(tmp_path):
     got = pc.self_kill_frames(ENGINE, str(tmp_path / "b200"), act)
     np.testing.assert_allclose(want[0], got[0], rtol=0, atol=pc.REWARD_TOL)
     assert want[1] == got[1]
+
+
+@pytest.mark.parametrize("seed", list(range(60000, 60014)) + [115000, 115001])
+def test_random_arena_batches_with_a_chaotic_caller(seed):
+    import fuzz_common as fz
+    fz.play_batch_chaotic(seed, checker_lib(), ENGINE, n_arenas=1 + seed % 4)
