@@ -78,3 +78,14 @@ def test_oracle_port_matches_reference_with_a_chaotic_caller(seed):
 def test_emulated_arena_batch_with_a_chaotic_caller(emu, seed):
     """reads at every point of the loop, late adds to all arenas and (select_arena) to one, mid-run reset"""
     fz.play_batch_chaotic(seed, CHECKER, emu, n_arenas=1 + seed % 4)
+
+
+# 5-8 groups (up to 25 observation channels; fuzz_common.MANY_GROUPS_SEED)
+@pytest.mark.parametrize("seed", list(range(70000, 70008)))
+def test_emulated_engine_matches_checker_with_many_groups(emu, seed):
+    fz.play(seed, CHECKER, emu, steps=15)
+
+
+@pytest.mark.parametrize("seed", [72000, 72001, 72002, 72003])
+def test_emulated_engine_with_many_groups_and_a_chaotic_caller(emu, seed):
+    fz.play_chaotic(seed, CHECKER, emu)

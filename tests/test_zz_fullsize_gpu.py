@@ -225,3 +225,19 @@ def test_self_kill_feeds_the_corpse(tmp_path):
 def test_random_arena_batches_with_a_chaotic_caller(seed):
     import fuzz_common as fz
     fz.play_batch_chaotic(seed, checker_lib(), ENGINE, n_arenas=1 + seed % 4)
+
+
+# 5-8 groups: up to 25 observation channels per view cell (fuzz_common.MANY_GROUPS_SEED)
+@pytest.mark.parametrize("seed", list(range(70000, 70016)))
+def test_random_games_with_many_groups(seed):
+    import fuzz_common as fz
+    fz.play(seed, checker_lib(), ENGINE, steps=20)
+
+
+@pytest.mark.parametrize("seed", list(range(72000, 72008)) + [73000, 73001])
+def test_random_games_with_many_groups_and_a_chaotic_caller(seed):
+    import fuzz_common as fz
+    if seed >= 73000:
+        fz.play_batch_chaotic(seed, checker_lib(), ENGINE, n_arenas=1 + seed % 4)
+    else:
+        fz.play_chaotic(seed, checker_lib(), ENGINE)
