@@ -374,6 +374,9 @@ def trace_chaotic(env, steps, seed, acting, order, render_dir=None):
                 gj = int(rs.randint(0, len(handles)))        # no action this step, walls may block queued moves
                 env.add_agents(handles[gj], method="random", n=int(rs.randint(1, 3)))
                 log.append(("t%d late add g%d" % (t, gj), np.array([env.get_num(h) for h in handles])))
+                peek("t%d after late add" % t)
+            if env.config.config_dict.get("goal_mode") and rs.rand() < 0.2:    # deprecated API: two RNG draws per agent
+                env.set_goal(handles[int(rs.randint(0, len(handles)))], "random")
             if rs.rand() < 0.04:
                 env.add_walls(method="random", n=int(rs.randint(1, 4)))
             if rs.rand() < 0.03:
