@@ -241,3 +241,52 @@ def test_random_games_with_many_groups_and_a_chaotic_caller(seed):
         fz.play_batch_chaotic(seed, checker_lib(), ENGINE, n_arenas=1 + seed % 4)
     else:
         fz.play_chaotic(seed, checker_lib(), ENGINE)
+
+
+def test_every_step_loop_buffer_as_a_device_pointer():
+    """include/magent_runtime_api.h: observation, action, reward and id / pos / alive buffers may be CUDA device pointers
+    (read / written in place).  One engine is driven through device tensors only, the checker through host arrays."""
+    import ctypes
+    import torch
+    dev = torch.device("cuda") if ON_GPU else torch.device("cpu")           # (CPU tensors in the dry run: host pointers)
+    env = pc.make_battle(ENGINE, 40, 180, 4)
+    ref = pc.make_battle(checker_lib(), 40, 180, 4)
+    L = env._lib
+    rs = np.random.RandomState(6)
+    for t in range(25):
+        for g, h in enumerate(env.get_handles()):
+            rh = ref.get_handles()[g]
+            n = env.get_num(h)
+            assert n == ref.get_num(rh)
+            if n == 0:
+                continue
+            v, f = env.get_observation_torch(h) if ON_GPU else [torch.from_numpy(x.copy()) for x in env.get_observation(h)]
+            rv, rf = ref.get_observation(rh)
+            np.testing.assert_array_equal(v.cpu().numpy().view(np.uint32), rv.view(np.uint32))
+            np.testing.assert_array_equal(f.cpu().numpy().view(np.uint32), rf.view(np.uint32))
+            act = rs.randint(0, 21, size=n).astype(np.int32)
+            d_act = torch.from_numpy(act).to(dev)
+            L.env_set_action(env.game, env._hv(h), ctypes.c_void_p(d_act.data_ptr()))
+            ref.set_action(rh, act)
+        if ON_GPU:
+            torch.cuda.synchronize()
+        env.step()
+        ref.step()
+        for g, h in enumerate(env.get_handles()):
+            rh = ref.get_handles()[g]
+            n = env.get_num(h)
+            d_rew = torch.full((n,), -7.0, dtype=torch.float32, device=dev)
+            d_pos = torch.full((n, 2), -7, dtype=torch.int32, device=dev)
+            d_id = torch.full((n,), -7, dtype=torch.int32, device=dev)
+            d_alive = torch.full((n,), 7, dtype=torch.uint8, device=dev)
+            L.env_get_reward(env.game, env._hv(h), ctypes.c_void_p(d_rew.data_ptr()))
+            L.env_get_info(env.game, env._hv(h), b"pos", ctypes.c_void_p(d_pos.data_ptr()))
+            L.env_get_info(env.game, env._hv(h), b"id", ctypes.c_void_p(d_id.data_ptr()))
+            L.env_get_info(env.game, env._hv(h), b"alive", ctypes.c_void_p(d_alive.data_ptr()))
+            env.sync()
+            np.testing.assert_allclose(d_rew.cpu().numpy(), ref.get_reward(rh), rtol=0, atol=pc.REWARD_TOL)
+            np.testing.assert_array_equal(d_pos.cpu().numpy(), ref.get_pos(rh))
+            np.testing.assert_array_equal(d_id.cpu().numpy(), ref.get_agent_id(rh))
+            np.testing.assert_array_equal(d_alive.cpu().numpy().astype(bool), ref.get_alive(rh).astype(bool))
+        env.clear_dead()
+        ref.clear_dead()
