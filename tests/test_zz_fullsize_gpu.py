@@ -290,3 +290,22 @@ def test_every_step_loop_buffer_as_a_device_pointer():
             np.testing.assert_array_equal(d_alive.cpu().numpy().astype(bool), ref.get_alive(rh).astype(bool))
         env.clear_dead()
         ref.clear_dead()
+
+
+def test_observation_into_one_host_and_one_device_buffer():
+    """env_get_observation with bufs[0] on the device and bufs[1] on the host, and the other way round"""
+    import ctypes
+    import torch
+    dev = torch.device("cuda") if ON_GPU else torch.device("cpu")
+    env = pc.make_battle(ENGINE, 36, 140, 9)
+    h = env.get_handles()[1]
+    want_v, want_f = [x.copy() for x in env.get_observation(h)]
+    n = env.get_num(h)
+    for view_on_device in (True, False):
+        v = torch.full((n,) + env.get_view_space(h), -3.0, dtype=torch.float32, device=dev if view_on_device else "cpu")
+        f = torch.full((n,) + env.get_feature_space(h), -3.0, dtype=torch.float32, device="cpu" if view_on_device else dev)
+        bufs = (ctypes.c_void_p * 2)(v.data_ptr(), f.data_ptr())
+        env._lib.env_get_observation(env.game, env._hv(h), bufs)
+        env.sync()
+        np.testing.assert_array_equal(v.cpu().numpy().view(np.uint32), want_v.view(np.uint32))
+        np.testing.assert_array_equal(f.cpu().numpy().view(np.uint32), want_f.view(np.uint32))
