@@ -154,8 +154,11 @@ def make_env(lib, seed, **kw):
     free = (info["w"] - 2) * (info["h"] - 2)
     env.add_walls(method="random", n=int(rs.randint(0, max(1, free // 25))))
     handles = env.get_handles()
+    never = int(rs.randint(0, len(handles))) if seed % 7 == 6 else -1     # a group that stays empty for the whole episode
     for g, h in enumerate(handles):
         bw, bl = info["bodies"][g]
+        if g == never:
+            continue
         share = free * float(rs.choice([0.02, 0.06, 0.12] if seed % 3 != 1 else [0.1, 0.2, 0.3])) / (bw * bl) / info["n_groups"] * 2
         if seed >= LARGE_MAP_SEED:
             share *= 0.03 if seed >= HUGE_MAP_SEED else 0.4
