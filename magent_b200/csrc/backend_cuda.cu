@@ -437,6 +437,9 @@ void launch_step(const EngineDev *dE, const EngineDev &hE, const StepArgs &S, in
                 configured = smem;
             }
         }
+        // measurement knob (profiles/scripts): MAGENT_B200_STEP_THREADS=256..1024 overrides the block size choice above
+        static const int threads_pref = getenv("MAGENT_B200_STEP_THREADS") ? atoi(getenv("MAGENT_B200_STEP_THREADS")) : 0;
+        if (threads_pref >= 32 && threads_pref <= STEP_THREADS) threads = threads_pref & ~31;
         int per_sm = 1;
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_cta, threads, smem));
         if (per_sm < 1) per_sm = 1;
