@@ -297,7 +297,7 @@ def play_batch(seed, checker_lib, engine_lib, n_arenas=3, steps=15):
             env.clear_dead()
 
 
-def trace_chaotic(env, steps, seed, acting, order, render_dir=None):
+def trace_chaotic_gen(env, steps, seed, acting, order, render_dir=None):
     """A caller that reads at every point of the loop: observations and rewards are fetched (from random groups, also
     non-acting ones) before set_action, between set_action calls, after step, after clear_dead and twice in a row;
     the acting subset changes from step to step; the episode is reset and repopulated once in the middle.  Every
@@ -363,6 +363,7 @@ def trace_chaotic(env, steps, seed, acting, order, render_dir=None):
                 env.add_agents(h, method="random", n=int(rs.randint(1, 2 + free // (40 * len(handles)))))
             log.append(("reset", np.array([env.get_num(h) for h in handles])))
         peek("t%d top" % t)
+        yield
         now = [g for g in order if rs.rand() < 0.8]
         for gi in now:
             n = env.get_num(handles[gi])
@@ -373,6 +374,7 @@ def trace_chaotic(env, steps, seed, acting, order, render_dir=None):
                 act[hit] = rs.randint(attack_base[gi], n_act, size=int(hit.sum()))
             env.set_action(handles[gi], act)
             peek("t%d after set_action g%d" % (t, gi))
+            yield
             if rs.rand() < 0.06:                             # setup calls between set_action and step: the newcomers have
                 gj = int(rs.randint(0, len(handles)))        # no action this step, walls may block queued moves
                 env.add_agents(handles[gj], method="random", n=int(rs.randint(1, 3)))
@@ -388,6 +390,7 @@ def trace_chaotic(env, steps, seed, acting, order, render_dir=None):
         log.append(("t%d done" % t, np.array([int(done)] + [env.get_num(h) for h in handles])))
         peek("t%d after step" % t)
         peek("t%d after step (2)" % t)
+        yield
         if rs.rand() < 0.8:
             env.clear_dead()
             peek("t%d after clear_dead" % t)
@@ -398,6 +401,16 @@ def trace_chaotic(env, steps, seed, acting, order, render_dir=None):
         for name in sorted(os.listdir(render_dir)):
             log.append(("file " + name, np.frombuffer(open(os.path.join(render_dir, name), "rb").read(), dtype=np.uint8)))
     return log
+
+
+def trace_chaotic(env, steps, seed, acting, order, render_dir=None):
+    """trace_chaotic_gen run to its end (the generator yields between API calls so that two engines can be interleaved)"""
+    g = trace_chaotic_gen(env, steps, seed, acting, order, render_dir=render_dir)
+    try:
+        while True:
+            next(g)
+    except StopIteration as e:
+        return e.value
 
 
 def play_chaotic(seed, lib_a, lib_b, steps=24, **kw):
@@ -526,3 +539,47 @@ def play_batch_chaotic(seed, checker_lib, engine_lib, n_arenas=3, steps=16):
             for env in both:
                 env.clear_dead()
             peek("t%d after clear_dead" % t)
+
+
+def compare_chaotic_logs(a, b, what):
+    assert len(a) == len(b), "%s: %d vs %d records" % (what, len(a), len(b))
+    for ra, rb in zip(a, b):
+        assert ra[0] == rb[0], "%s: %s vs %s" % (what, ra[0], rb[0])
+        for xa, xb in zip(ra[1:], rb[1:]):
+            w = "%s: %s" % (what, ra[0])
+            assert xa.shape == xb.shape, w + " shape %s vs %s" % (xa.shape, xb.shape)
+            if xa.dtype == np.float32 and " reward" in ra[0]:
+                np.testing.assert_allclose(xa, xb, rtol=0, atol=pc.REWARD_TOL, err_msg=w)
+            elif xa.dtype == np.float32:
+                np.testing.assert_array_equal(xa.view(np.uint32), xb.view(np.uint32), err_msg=w)
+            elif xa.dtype == np.float16:
+                np.testing.assert_array_equal(xa.view(np.uint16), xb.view(np.uint16), err_msg=w)
+            else:
+                np.testing.assert_array_equal(xa, xb, err_msg=w)
+
+
+def play_interleaved_engines(seed, checker_lib, engine_lib, n_engines=3, steps=16):
+    """n_engines DIFFERENT random games alive in one process on the engine library, their chaotic callers advanced in
+    random interleaving (a switch between any two API calls), each compared with the same game played alone on the
+    checker: anything process-global in the backend (scratch buffers, cached launch configurations, the observation
+    pre-pass products) must not leak between engines."""
+    rs = np.random.RandomState(seed + 32452843)
+    seeds = [seed * 10 + k for k in range(n_engines)]
+    orders = []
+    for sd in seeds:
+        r = np.random.RandomState(sd)
+        n_groups = len(make_env(checker_lib, sd).get_handles())
+        orders.append([int(g) for g in r.permutation(n_groups)])
+    want = [trace_chaotic(make_env(checker_lib, sd), steps, sd, None, o) for sd, o in zip(seeds, orders)]
+    gens = [trace_chaotic_gen(make_env(engine_lib, sd), steps, sd, None, o) for sd, o in zip(seeds, orders)]
+    got = [None] * n_engines
+    live = list(range(n_engines))
+    while live:
+        k = live[int(rs.randint(0, len(live)))]
+        try:
+            next(gens[k])
+        except StopIteration as e:
+            got[k] = e.value
+            live.remove(k)
+    for k in range(n_engines):
+        compare_chaotic_logs(want[k], got[k], "interleaved engines seed %d game %d" % (seed, k))

@@ -89,3 +89,8 @@ def test_emulated_engine_matches_checker_with_many_groups(emu, seed):
 @pytest.mark.parametrize("seed", [72000, 72001, 72002, 72003])
 def test_emulated_engine_with_many_groups_and_a_chaotic_caller(emu, seed):
     fz.play_chaotic(seed, CHECKER, emu)
+
+
+@pytest.mark.parametrize("seed", list(range(9000, 9006)))
+def test_three_emulated_engines_interleaved_with_chaotic_callers(emu, seed):
+    fz.play_interleaved_engines(seed, CHECKER, emu)

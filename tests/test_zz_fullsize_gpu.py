@@ -309,3 +309,12 @@ def test_observation_into_one_host_and_one_device_buffer():
         env.sync()
         np.testing.assert_array_equal(v.cpu().numpy().view(np.uint32), want_v.view(np.uint32))
         np.testing.assert_array_equal(f.cpu().numpy().view(np.uint32), want_f.view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", list(range(9000, 9012)))
+def test_three_engines_interleaved_with_chaotic_callers(seed):
+    """three different random games alive in one process, their callers switched between any two API calls: the
+    backend's process-global scratch (per-agent headers, padded minimap rows, cached launch configurations, staging
+    buffers) must not leak from one engine into another"""
+    import fuzz_common as fz
+    fz.play_interleaved_engines(seed, checker_lib(), ENGINE)
