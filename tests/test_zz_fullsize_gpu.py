@@ -40,80 +40,6 @@ def batched_battle(arenas, size, n, seed):
     return env
 
 
-def test_battle_512_arenas_of_2x1000():
-    """BASELINE configs[4] per-GPU share (= bench.py's default workload): 1.024 M agents per step"""
-    A, size, n, seed = 512, 200, 1000, 100
-    env = batched_battle(A, size, n, seed)
-    samples = {a: pc.make_battle(checker_lib(), size, n, seed + a) for a in (0, 255, 511)}
-    fs.play_battle_and_check(env, size, size, 3, 17, samples=samples, use_torch_obs=ON_GPU)
-
-
-def test_battle_one_arena_of_2x400k():
-    """BASELINE configs[3] as placeable (2x400k on 1000x1000; the whole-grid cooperative kernels): every record
-    of every step against the reference"""
-    size, n, seed = 1000, 400000, 3
-    env = batched_battle(1, size, n, seed)
-    ref = pc.make_battle(checker_lib(), size, n, seed)
-    fs.play_battle_and_check(env, size, size, 2, 23, samples={0: ref}, use_torch_obs=ON_GPU)
-
-
-def test_gather_64_arenas():
-    """BASELINE configs[2]: gather 200x200 (495 agents + 1847 food per arena), 64 arenas, only the agent group
-    observes and acts; arenas 0, 31 and 63 against independent checkers"""
-    import bench
-    import magent_b200 as magent
-    A, size, seed = 64, 200, 40
-    wl = bench.WORKLOADS["gather64"]
-    env, act = bench.build_env(wl, ENGINE, A, seed0=seed)
-    hs = env.get_handles()
-    gi = [list(hs).index(h) for h in act]
-    refs = {}
-    for a in (0, 31, 63):
-        r, _ = bench.build_env(wl, checker_lib(), 1, seed0=seed + a)
-        refs[a] = r
-    rs = np.random.RandomState(7)
-    for t in range(6):
-        nums = [env.get_arena_nums(h).astype(np.int64) for h in hs]
-        off = [np.concatenate([[0], np.cumsum(k)]) for k in nums]
-        assert all(int(k.sum()) == env.get_num(h) for k, h in zip(nums, hs))
-        for g in gi:
-            if ON_GPU:
-                v, f = env.get_observation_torch(hs[g])
-                v, f = v.cpu().numpy(), f.cpu().numpy()
-            else:
-                v, f = env.get_observation(hs[g])
-            for a, r in refs.items():
-                rv, rf = r.get_observation(r.get_handles()[g])
-                sl = slice(int(off[g][a]), int(off[g][a + 1]))
-                np.testing.assert_array_equal(v[sl].view(np.uint32), rv.view(np.uint32), err_msg="view t%d arena %d" % (t, a))
-                np.testing.assert_array_equal(f[sl].view(np.uint32), rf.view(np.uint32), err_msg="feature t%d arena %d" % (t, a))
-        acts = {g: rs.randint(0, env.get_action_space(hs[g])[0], size=int(nums[g].sum())).astype(np.int32) for g in gi}
-        for g in gi:
-            env.set_action(hs[g], acts[g])
-            for a, r in refs.items():
-                r.set_action(r.get_handles()[g], np.ascontiguousarray(acts[g][off[g][a]:off[g][a + 1]]))
-        env.step()
-        done = env.get_arena_done() != 0
-        for a, r in refs.items():
-            assert bool(done[a]) == bool(r.step())
-        for g, h in enumerate(hs):
-            rew, pos, alive, ids = env.get_reward(h), env.get_pos(h), env.get_alive(h), env.get_agent_id(h)
-            for a, r in refs.items():
-                rh = r.get_handles()[g]
-                sl = slice(int(off[g][a]), int(off[g][a + 1]))
-                np.testing.assert_allclose(rew[sl], r.get_reward(rh), atol=pc.REWARD_TOL, rtol=0)
-                np.testing.assert_array_equal(pos[sl], r.get_pos(rh))
-                np.testing.assert_array_equal(alive[sl], r.get_alive(rh))
-                np.testing.assert_array_equal(ids[sl], r.get_agent_id(rh))
-        # every arena starts from the same layout and differs only by its seed and its actions: arenas must
-        # not leak into each other -- the food group of an arena only ever shrinks
-        env.clear_dead()
-        for r in refs.values():
-            r.clear_dead()
-        after = env.get_arena_nums(hs[0]).astype(np.int64)
-        assert (after <= nums[0]).all()
-
-
 # ---- randomised differential games on maps in the reference's large_map_mode (8 / 16 move bands), CUDA engine vs
 # the checker (tests/fuzz_common.py; the same seeds run against the host emulation in tests/test_fuzz_cpu.py)
 @pytest.mark.parametrize("seed", list(range(100000, 100012)) + [200000, 200001, 200002])
@@ -145,38 +71,12 @@ def test_plain_c_caller_prints_the_same_trace_as_on_the_checker():
     assert got.stdout == want.stdout
 
 
-def test_two_huge_arenas_behind_one_handle():
-    """arena batch x whole-grid kernels: 2 arenas of 2x20000 agents (more than 32768 per arena, so every arena is
-    stepped by the cooperative grid one after the other); both arenas exactly against independent checkers and the
-    whole batch against the PyTorch restatement"""
-    A, size, n, seed = 2, 320, 20000, 60
-    env = batched_battle(A, size, n, seed)
-    samples = {a: pc.make_battle(checker_lib(), size, n, seed + a) for a in range(A)}
-    fs.play_battle_and_check(env, size, size, 4, 29, samples=samples, use_torch_obs=ON_GPU)
-
-
 def test_arena_whose_step_scratch_does_not_fit_shared_memory():
     """2x4000 agents on 120x120: one CTA per arena, but 8000 agents x 41 B of step scratch exceed the 200 KB the
     launch keeps in shared memory, so the scratch arrays stay in HBM (backend_cuda.cu launch_step)"""
     want = pc.run_trace(pc.make_battle(checker_lib(), 120, 4000, 2), 8, 3, keep_obs=True)
     got = pc.run_trace(pc.make_battle(ENGINE, 120, 4000, 2), 8, 3, keep_obs=True)
     pc.compare_traces(want, got)
-
-
-SOAK_ARENAS = int(os.environ.get("MAGENT_FULLSIZE_SOAK_ARENAS", "512"))   # (smaller for a dry run on the CPU)
-
-
-@pytest.mark.parametrize("workload", ["battle512", "battle512_blocks"])
-def test_soak_of_the_throughput_loop(workload):
-    """40 steps of bench.py's own loop (actions drawn on the device) at its own size -- 512 arenas of 2x1000 randomly
-    placed agents, and of 2x1600 agents packed in two facing blocks (every move contended) -- with the whole-batch
-    checks: one agent per cell, ordered ids, bounded moves and exact survivor counts after every step, every
-    observation record against the PyTorch restatement every 10 steps"""
-    import bench
-    wl = bench.WORKLOADS[workload]
-    env, _ = bench.build_env(wl, ENGINE, SOAK_ARENAS, seed0=77)
-    size = wl["map_size"]
-    fs.soak_battle_and_check(env, size, size, 40, 13, obs_every=10, use_torch_obs=ON_GPU)
 
 
 @pytest.mark.parametrize("which", ["battle", "pursuit", "mixed", "arrange"])
@@ -318,3 +218,105 @@ def test_three_engines_interleaved_with_chaotic_callers(seed):
     buffers) must not leak from one engine into another"""
     import fuzz_common as fz
     fz.play_interleaved_engines(seed, checker_lib(), ENGINE)
+
+
+# ---- bench.py's workloads at their full sizes
+def test_battle_512_arenas_of_2x1000():
+    """BASELINE configs[4] per-GPU share (= bench.py's default workload): 1.024 M agents per step"""
+    A, size, n, seed = 512, 200, 1000, 100
+    env = batched_battle(A, size, n, seed)
+    samples = {a: pc.make_battle(checker_lib(), size, n, seed + a) for a in (0, 255, 511)}
+    fs.play_battle_and_check(env, size, size, 3, 17, samples=samples, use_torch_obs=ON_GPU)
+
+
+def test_gather_64_arenas():
+    """BASELINE configs[2]: gather 200x200 (495 agents + 1847 food per arena), 64 arenas, only the agent group
+    observes and acts; arenas 0, 31 and 63 against independent checkers"""
+    import bench
+    import magent_b200 as magent
+    A, size, seed = 64, 200, 40
+    wl = bench.WORKLOADS["gather64"]
+    env, act = bench.build_env(wl, ENGINE, A, seed0=seed)
+    hs = env.get_handles()
+    gi = [list(hs).index(h) for h in act]
+    refs = {}
+    for a in (0, 31, 63):
+        r, _ = bench.build_env(wl, checker_lib(), 1, seed0=seed + a)
+        refs[a] = r
+    rs = np.random.RandomState(7)
+    for t in range(6):
+        nums = [env.get_arena_nums(h).astype(np.int64) for h in hs]
+        off = [np.concatenate([[0], np.cumsum(k)]) for k in nums]
+        assert all(int(k.sum()) == env.get_num(h) for k, h in zip(nums, hs))
+        for g in gi:
+            if ON_GPU:
+                v, f = env.get_observation_torch(hs[g])
+                v, f = v.cpu().numpy(), f.cpu().numpy()
+            else:
+                v, f = env.get_observation(hs[g])
+            for a, r in refs.items():
+                rv, rf = r.get_observation(r.get_handles()[g])
+                sl = slice(int(off[g][a]), int(off[g][a + 1]))
+                np.testing.assert_array_equal(v[sl].view(np.uint32), rv.view(np.uint32), err_msg="view t%d arena %d" % (t, a))
+                np.testing.assert_array_equal(f[sl].view(np.uint32), rf.view(np.uint32), err_msg="feature t%d arena %d" % (t, a))
+        acts = {g: rs.randint(0, env.get_action_space(hs[g])[0], size=int(nums[g].sum())).astype(np.int32) for g in gi}
+        for g in gi:
+            env.set_action(hs[g], acts[g])
+            for a, r in refs.items():
+                r.set_action(r.get_handles()[g], np.ascontiguousarray(acts[g][off[g][a]:off[g][a + 1]]))
+        env.step()
+        done = env.get_arena_done() != 0
+        for a, r in refs.items():
+            assert bool(done[a]) == bool(r.step())
+        for g, h in enumerate(hs):
+            rew, pos, alive, ids = env.get_reward(h), env.get_pos(h), env.get_alive(h), env.get_agent_id(h)
+            for a, r in refs.items():
+                rh = r.get_handles()[g]
+                sl = slice(int(off[g][a]), int(off[g][a + 1]))
+                np.testing.assert_allclose(rew[sl], r.get_reward(rh), atol=pc.REWARD_TOL, rtol=0)
+                np.testing.assert_array_equal(pos[sl], r.get_pos(rh))
+                np.testing.assert_array_equal(alive[sl], r.get_alive(rh))
+                np.testing.assert_array_equal(ids[sl], r.get_agent_id(rh))
+        # every arena starts from the same layout and differs only by its seed and its actions: arenas must
+        # not leak into each other -- the food group of an arena only ever shrinks
+        env.clear_dead()
+        for r in refs.values():
+            r.clear_dead()
+        after = env.get_arena_nums(hs[0]).astype(np.int64)
+        assert (after <= nums[0]).all()
+
+
+# ---- the heaviest tests run last (a problem in one of them must not hide the rest under -x)
+def test_battle_one_arena_of_2x400k():
+    """BASELINE configs[3] as placeable (2x400k on 1000x1000; the whole-grid cooperative kernels): every record
+    of every step against the reference"""
+    size, n, seed = 1000, 400000, 3
+    env = batched_battle(1, size, n, seed)
+    ref = pc.make_battle(checker_lib(), size, n, seed)
+    fs.play_battle_and_check(env, size, size, 2, 23, samples={0: ref}, use_torch_obs=ON_GPU)
+
+
+def test_two_huge_arenas_behind_one_handle():
+    """arena batch x whole-grid kernels: 2 arenas of 2x20000 agents (more than 32768 per arena, so every arena is
+    stepped by the cooperative grid one after the other); both arenas exactly against independent checkers and the
+    whole batch against the PyTorch restatement"""
+    A, size, n, seed = 2, 320, 20000, 60
+    env = batched_battle(A, size, n, seed)
+    samples = {a: pc.make_battle(checker_lib(), size, n, seed + a) for a in range(A)}
+    fs.play_battle_and_check(env, size, size, 4, 29, samples=samples, use_torch_obs=ON_GPU)
+
+
+SOAK_ARENAS = int(os.environ.get("MAGENT_FULLSIZE_SOAK_ARENAS", "512"))   # (smaller for a dry run on the CPU)
+
+
+@pytest.mark.parametrize("workload", ["battle512", "battle512_blocks"])
+def test_soak_of_the_throughput_loop(workload):
+    """40 steps of bench.py's own loop (actions drawn on the device) at its own size -- 512 arenas of 2x1000 randomly
+    placed agents, and of 2x1600 agents packed in two facing blocks (every move contended) -- with the whole-batch
+    checks: one agent per cell, ordered ids, bounded moves and exact survivor counts after every step, every
+    observation record against the PyTorch restatement every 10 steps"""
+    import bench
+    wl = bench.WORKLOADS[workload]
+    env, _ = bench.build_env(wl, ENGINE, SOAK_ARENAS, seed0=77)
+    size = wl["map_size"]
+    fs.soak_battle_and_check(env, size, size, 40, 13, obs_every=10, use_torch_obs=ON_GPU)
