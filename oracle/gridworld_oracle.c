@@ -11,7 +11,8 @@
  *
  * It restates the SEQUENTIAL semantics (the reference is only deterministic with OMP_NUM_THREADS=1,
  * SURVEY.md §0): each function cites the reference lines it follows.  Not restated (no shipped config on
- * the hot path uses them; the functions abort with a message): OP_ALIGN, render, DiscreteSnake.
+ * the hot path uses them; the functions abort with a message): OP_ALIGN, the replay dump (env_render is a no-op,
+ * render_window_info / attack_event are not served), DiscreteSnake.
  */
 #include <math.h>
 #include <stdbool.h>
@@ -787,6 +788,42 @@ API int env_get_info(void *game, int g, const char *name, void *buf) {          
         const Type *t = &e->type[e->grp[g].type];
         for (int i = 0; i < t->view.width * t->view.height; i++) ib[i] = -1;
         for (int i = 0; i < t->attack.count; i++) ib[(t->attack.dy[i] - t->view.y1) * t->view.width + t->attack.dx[i] - t->view.x1] = i;
+    } else if (!strcmp(name, "groups_info")) {                      /* GridWorld.cc:872-887 (4 colours: callers with <= 4 groups) */
+        static const int colors[4][3] = {{192, 64, 64}, {64, 64, 192}, {64, 192, 64}, {64, 64, 64}};
+        for (int i = 0; i < e->ngroup; i++) {
+            ib[i * 5] = e->type[e->grp[i].type].width; ib[i * 5 + 1] = e->type[e->grp[i].type].length;
+            for (int c = 0; c < 3; c++) ib[i * 5 + 2 + c] = colors[i % 4][c];
+        }
+    } else if (!strcmp(name, "walls_info")) {                       /* GridWorld.cc:785-795, Map::get_wall Map.cc:609-615 */
+        int ct = 0;
+        for (int i = 0; i < e->w * e->h; i++)
+            if (e->cell[i] == CELL_WALL) { ct++; ib[ct * 2] = i % e->w; ib[ct * 2 + 1] = i / e->w; }
+        ib[0] = ct;
+    } else if (!strcmp(name, "global_minimap")) {                   /* GridWorld.cc:738-762: dead-but-unculled agents count too */
+        float *fb = buf;
+        int vh = (int)lroundf(fb[0]), vw = (int)lroundf(fb[1]), ng = e->ngroup;
+        for (int i = 0; i < vh * vw * ng; i++) fb[i] = 0.0f;
+        int sh = (e->h + vh - 1) / vh, sw = (e->w + vw - 1) / vw;
+        for (int i = 0; i < ng; i++) {
+            int ch = ((i - g) % ng + ng) % ng;
+            for (int j = 0; j < e->grp[i].n; j++) {
+                const Agent *a = &e->pool[e->grp[i].slot[j]];
+                fb[((a->y / sh) * vw + a->x / sw) * ng + ch] += 1.0f;
+            }
+            for (int j = 0; j < vh * vw; j++) fb[j * ng + ch] /= (float)e->grp[i].n;
+        }
+    } else if (!strcmp(name, "mean_info")) {                        /* GridWorld.cc:763-784 (every agent must hold a valid action) */
+        float *fb = buf;
+        int n = e->grp[g].n, na = e->type[e->grp[g].type].n_action;
+        float sx = 0, sy = 0;
+        int ctr[256] = {0};
+        for (int i = 0; i < n; i++) {
+            const Agent *a = &e->pool[e->grp[g].slot[i]];
+            sx += a->x; sy += a->y;
+            if (a->action >= 0 && a->action < na && a->action < 256) ctr[a->action]++;
+        }
+        fb[0] = sx / n; fb[1] = sy / n;
+        for (int i = 0; i < na && i < 256; i++) fb[2 + i] = (float)(1.0 * ctr[i] / n);
     } else die("info name not restated : ", name);
     return 0;
 }

@@ -156,3 +156,12 @@ def test_port_matches_reference_beyond_golden(game):
     a = pc.run_trace(make(pc.REF_LIB), 60, 3, keep_obs=True)
     b = pc.run_trace(make(pc.PORT_LIB), 60, 3, keep_obs=True)
     pc.compare_traces(a, b, game)
+
+
+@pytest.mark.skipif(not os.path.exists(pc.REF_LIB), reason="needs oracle/_ref")
+@pytest.mark.parametrize("which", ["battle", "pursuit", "mixed", "arrange"])
+def test_port_serves_the_cold_info_getters_like_the_reference(which):
+    """view2attack / attack_base / groups_info / walls_info / global_minimap / mean_info (GridWorld.cc:717-894)"""
+    make = {"battle": lambda lib: pc.make_battle(lib, 30, 120, 1), "pursuit": lambda lib: pc.make_pursuit(lib, 40, 2),
+            "mixed": lambda lib: pc.make_mixed(lib), "arrange": lambda lib: pc.make_arrange(lib)}[which]
+    pc.play_and_compare_info(make, pc.REF_LIB, pc.PORT_LIB)

@@ -83,11 +83,9 @@ def test_arena_whose_step_scratch_does_not_fit_shared_memory():
 def test_cold_info_getters_match_the_reference(which):
     """view2attack / attack_base / groups_info / walls_info / global_minimap / mean_info (GridWorld.cc:717-894),
     served from a host snapshot of the device state"""
-    if not os.path.exists(pc.REF_LIB):
-        pytest.skip("needs oracle/_ref (the C restatement does not serve the cold getters)")
     make = {"battle": lambda lib: pc.make_battle(lib, 30, 120, 1), "pursuit": lambda lib: pc.make_pursuit(lib, 40, 2),
             "mixed": lambda lib: pc.make_mixed(lib), "arrange": lambda lib: pc.make_arrange(lib)}[which]
-    pc.play_and_compare_info(make, pc.REF_LIB, ENGINE)
+    pc.play_and_compare_info(make, checker_lib(), ENGINE)
 
 
 def test_select_arena_and_event_counters():
