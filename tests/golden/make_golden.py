@@ -27,3 +27,8 @@ if __name__ == "__main__":
         np.savez_compressed(path, **a)
         print("%-16s %3d steps  final num %s  %6.1f KB" % (name, int(a["n_steps"]),
               a["s%d_num" % (int(a["n_steps"]) - 1)].tolist(), os.path.getsize(path) / 1024))
+    import tempfile
+    a, b = gc.record_edge_cases(pc.REF_LIB, tempfile.mkdtemp()), gc.record_edge_cases(pc.REF_LIB, tempfile.mkdtemp())
+    assert sorted(a) == sorted(b) and all(np.array_equal(a[k], b[k]) for k in a), "edge cases: reference not deterministic"
+    np.savez_compressed(gc.EDGE_FILE, **a)
+    print("edge_cases       %s" % sorted(a))

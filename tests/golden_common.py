@@ -83,3 +83,33 @@ def compare_to_golden(name, trace):
 
 def check_against_golden(name, lib):
     compare_to_golden(name, record(name, lib))
+
+
+# ------------------------------------------------------------------ edge cases found by the chaotic-caller fuzz
+EDGE_FILE = os.path.join(GOLDEN_DIR, "edge_cases.npz")
+
+
+def record_edge_cases(lib, tmpdir):
+    """group reward across reset (parity_common.group_reward_across_reset) and the self-kill replay frames
+    (parity_common.self_kill_frames) as a flat dict of arrays"""
+    out = {}
+    for i, r in enumerate(pc.group_reward_across_reset(lib)):
+        out["group_reward_%d" % i] = r
+    act = pc.self_kill_frames(lib, None)
+    rew, files = pc.self_kill_frames(lib, tmpdir, act)
+    out["self_kill_action"] = np.array([act])
+    out["self_kill_reward"] = rew
+    for name, data in files.items():
+        out["self_kill_file_" + name] = np.frombuffer(data, dtype=np.uint8)
+    return out
+
+
+def check_edge_cases(lib, tmpdir, with_render=True):
+    want = np.load(EDGE_FILE)
+    for i, r in enumerate(pc.group_reward_across_reset(lib)):
+        np.testing.assert_allclose(r, want["group_reward_%d" % i], rtol=0, atol=pc.REWARD_TOL)
+    if with_render:
+        rew, files = pc.self_kill_frames(lib, tmpdir, int(want["self_kill_action"][0]))
+        np.testing.assert_allclose(rew, want["self_kill_reward"], rtol=0, atol=pc.REWARD_TOL)
+        for name, data in files.items():
+            assert data == want["self_kill_file_" + name].tobytes(), "replay file %s differs from the golden" % name

@@ -281,3 +281,8 @@ def test_self_kill_feeds_the_corpse(emu, tmp_path):
     assert want[1] == got[1]
     frame = want[1]["video_1.txt"].decode().splitlines()
     assert any(l.split()[:2] == ["0", "50"] for l in frame), frame       # corpse: hp = -1 + 1.5 = 0.5 of 1.0 -> "50"
+
+
+def test_golden_edge_cases(emu, tmp_path):
+    """tests/golden/edge_cases.npz: group reward across reset, replay frames after a self-kill"""
+    gc.check_edge_cases(emu, str(tmp_path / "frames"))

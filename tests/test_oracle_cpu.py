@@ -165,3 +165,8 @@ def test_port_serves_the_cold_info_getters_like_the_reference(which):
     make = {"battle": lambda lib: pc.make_battle(lib, 30, 120, 1), "pursuit": lambda lib: pc.make_pursuit(lib, 40, 2),
             "mixed": lambda lib: pc.make_mixed(lib), "arrange": lambda lib: pc.make_arrange(lib)}[which]
     pc.play_and_compare_info(make, pc.REF_LIB, pc.PORT_LIB)
+
+
+def test_port_reproduces_the_golden_edge_cases():
+    """tests/golden/edge_cases.npz (recorded from the compiled reference): a group reward that survives reset()"""
+    gc.check_edge_cases(pc.PORT_LIB, None, with_render=False)

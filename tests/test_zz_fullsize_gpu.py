@@ -218,6 +218,13 @@ def test_three_engines_interleaved_with_chaotic_callers(seed):
     fz.play_interleaved_engines(seed, checker_lib(), ENGINE)
 
 
+def test_golden_edge_cases(tmp_path):
+    """tests/golden/edge_cases.npz (recorded from the compiled reference): group reward across reset, replay frames
+    after a self-kill -- needs no checker library"""
+    import golden_common as gc
+    gc.check_edge_cases(ENGINE, str(tmp_path / "frames"))
+
+
 # ---- bench.py's workloads at their full sizes
 def test_battle_512_arenas_of_2x1000():
     """BASELINE configs[4] per-GPU share (= bench.py's default workload): 1.024 M agents per step"""
