@@ -11,8 +11,7 @@
  *
  * It restates the SEQUENTIAL semantics (the reference is only deterministic with OMP_NUM_THREADS=1,
  * SURVEY.md §0): each function cites the reference lines it follows.  Not restated (no shipped config on
- * the hot path uses them; the functions abort with a message): OP_ALIGN, the replay dump (env_render is a no-op,
- * render_window_info / attack_event are not served), DiscreteSnake.
+ * the hot path uses them; the functions abort with a message): OP_ALIGN, DiscreteSnake.
  */
 #include <math.h>
 #include <stdbool.h>
@@ -131,6 +130,10 @@ typedef struct {
     Symbol sym[32]; int nsym;
     Node node[32]; int nnode;
     Rule rule[16]; int nrule;
+    /* replay dump: RenderGenerator.h, GridWorld.cc:18,97,484-509,797-842,939-948 */
+    char render_dir[1024];
+    int first_render_done, file_ct, frame_ct;                       /* first_render starts true (GridWorld.cc:18) */
+    int *ev; int nev, capev;                                        /* attack events of the last step: id, x, y */
 } Env;
 
 static uint32_t rng_draw(Env *e) {                                  /* x <- 16807 x mod (2^31-1) */
@@ -188,7 +191,7 @@ API int env_config_game(void *game, const char *key, void *p) {    /* GridWorld.
     else if (!strcmp(key, "goal_mode")) e->goal_mode = bv;
     else if (!strcmp(key, "turn_mode")) e->turn_mode = bv;
     else if (!strcmp(key, "embedding_size")) e->embedding = iv;
-    else if (!strcmp(key, "render_dir")) {}
+    else if (!strcmp(key, "render_dir")) { strncpy(e->render_dir, (const char *)p, sizeof e->render_dir - 1); }
     else if (!strcmp(key, "seed")) {
         uint32_t s = (uint32_t)(((unsigned long long)(long long)iv) % 2147483647ull);
         e->rng = s ? s : 1;
@@ -322,6 +325,7 @@ static void plan_rules(Env *e) {
 API int env_reset(void *game) {                                     /* GridWorld.cc:72-118, Map.cc:23-47 */
     Env *e = game;
     e->id_counter = 0;
+    e->file_ct++; e->frame_ct = 0;                                  /* RenderGenerator::next_file (GridWorld.cc:97) */
     e->large = e->w * e->h > 99 * 99;
     e->nsep = e->large ? (e->w * e->h > 1000 * 1000 ? 16 : 8) : 1;
     free(e->cell);
@@ -641,6 +645,8 @@ API int env_step(void *game, int *done) {                           /* GridWorld
         Act t = e->attack.v[i]; e->attack.v[i] = e->attack.v[j]; e->attack.v[j] = t;
     }
     /* attack: :475-506, Map::get_attack_obj Map.cc:209-252, Map::do_attack :255-310 */
+    const int record = e->first_render_done;                        /* `if (!first_render)`, :484,508: else the old events stay */
+    if (record) e->nev = 0;
     for (int i = 0; i < e->attack.n; i++) {
         Agent *a = &e->pool[e->attack.v[i].agent];
         if (a->dead) continue;
@@ -649,6 +655,10 @@ API int env_step(void *game, int *done) {                           /* GridWorld
         int rx, ry, tx, ty;
         save_to_real(t, a, &rx, &ry);
         rela_to_abs(rx, ry, a->dir, t->width / 2 + t->attack.dx[k], t->length / 2 + t->attack.dy[k], &tx, &ty);
+        if (record) {                                               /* RenderAttackEvent{id, obj_x, obj_y}, on or off the board */
+            if (e->nev == e->capev) { e->capev = e->capev ? 2 * e->capev : 256; e->ev = realloc(e->ev, sizeof(int) * 3 * e->capev); }
+            e->ev[3 * e->nev] = a->id; e->ev[3 * e->nev + 1] = tx; e->ev[3 * e->nev + 2] = ty; e->nev++;
+        }
         int c = (tx >= 0 && tx < e->w && ty >= 0 && ty < e->h) ? e->cell[ty * e->w + tx] : CELL_EMPTY;
         if (c == CELL_FOOD) {                                        /* Map.cc:292-303: eat; any group may (get_attack_obj :245) */
             float *food = &e->food[ty * e->w + tx];
@@ -788,6 +798,21 @@ API int env_get_info(void *game, int g, const char *name, void *buf) {          
         const Type *t = &e->type[e->grp[g].type];
         for (int i = 0; i < t->view.width * t->view.height; i++) ib[i] = -1;
         for (int i = 0; i < t->attack.count; i++) ib[(t->attack.dy[i] - t->view.y1) * t->view.width + t->attack.dx[i] - t->view.x1] = i;
+    } else if (!strcmp(name, "render_window_info")) {               /* GridWorld.cc:797-834 */
+        e->first_render_done = 1;
+        int x1 = ib[0], y1 = ib[1], x2 = ib[2], y2 = ib[3], ct = 1;
+        for (int i = 0; i < e->ngroup; i++) {
+            const Type *t = &e->type[e->grp[i].type];
+            for (int j = 0; j < e->grp[i].n; j++) {
+                const Agent *a = &e->pool[e->grp[i].slot[j]];
+                if (a->x < x1 || a->x > x2 || a->y < y1 || a->y > y2) continue;
+                if (t->can_absorb && !a->absorbed) continue;
+                ib[ct * 4] = a->id; ib[ct * 4 + 1] = a->x; ib[ct * 4 + 2] = a->y; ib[ct * 4 + 3] = i; ct++;
+            }
+        }
+        ib[0] = ct - 1; ib[1] = e->nev;
+    } else if (!strcmp(name, "attack_event")) {                     /* GridWorld.cc:835-842 */
+        for (int i = 0; i < 3 * e->nev; i++) ib[i] = e->ev[i];
     } else if (!strcmp(name, "groups_info")) {                      /* GridWorld.cc:872-887 (4 colours: callers with <= 4 groups) */
         static const int colors[4][3] = {{192, 64, 64}, {64, 64, 192}, {64, 192, 64}, {64, 64, 64}};
         for (int i = 0; i < e->ngroup; i++) {
@@ -828,8 +853,78 @@ API int env_get_info(void *game, int g, const char *name, void *buf) {          
     return 0;
 }
 
-API int env_render(void *game) { (void)game; return 0; }
-API int env_render_next_file(void *game) { (void)game; return 0; }
+/* ---- replay dump: GridWorld::render (GridWorld.cc:939-948), RenderGenerator::gen_config / render_a_frame
+ * (RenderGenerator.cc:56-185).  ostream << float prints like "%g". ---- */
+static void rgba(FILE *f, const char *key, const int *c, const char *alpha, int last) {
+    fprintf(f, "\"%s\": \"rgba(%d,%d,%d,%s)\"%s\n", key, c[0], c[1], c[2], alpha, last ? "" : ",");
+}
+static void gen_config(Env *e) {
+    static const int colors[4][3] = {{192, 64, 64}, {64, 64, 192}, {64, 192, 64}, {64, 64, 64}};
+    static const int grey[3] = {127, 127, 127}, dark[3] = {63, 63, 63};
+    char path[1200];
+    snprintf(path, sizeof path, "%s/config.json", e->render_dir);
+    FILE *f = fopen(path, "w");
+    if (!f) return;
+    fprintf(f, "{\n\"width\": %d,\n\"height\": %d,\n\"static-file\": \"static.map\",\n", e->w, e->h);
+    rgba(f, "obstacle-style", grey, "1", 0);
+    fprintf(f, "\"dynamic-file-directory\": \".\",\n");
+    rgba(f, "attack-style", dark, "0.8", 0);
+    fprintf(f, "\"minimap-width\": 300,\n\"minimap-height\": 250,\n\"group\" : [\n");
+    for (int i = 0; i < e->ngroup; i++) {
+        const Type *t = &e->type[e->grp[i].type];
+        const int *c = colors[i % 4];                               /* (the reference reads past its 4 rows for i >= 4) */
+        fprintf(f, "{\n\"height\": %d,\n\"width\": %d,\n", t->length, t->width);
+        rgba(f, "style", c, "1", 0);
+        fprintf(f, "\"anchor\": [0, 0],\n\"max-speed\": %d,\n", (int)t->speed);
+        rgba(f, "speed-style", c, "0.01", 0);
+        fprintf(f, "\"vision-radius\": %g,\n\"vision-angle\": %g,\n", t->view_radius, t->view_angle);
+        rgba(f, "vision-style", c, "0.2", 0);
+        fprintf(f, "\"attack-radius\": %g,\n\"attack-angle\": %g,\n", t->attack_radius, t->attack_angle);
+        rgba(f, "attack-style", c, "0.1", 0);
+        fprintf(f, "\"broadcast-radius\": 1\n%s\n", i == e->ngroup - 1 ? "}" : "},");
+    }
+    fprintf(f, "]\n}\n");
+    fclose(f);
+}
+
+API int env_render(void *game) {
+    Env *e = game;
+    if (!e->first_render_done) { e->first_render_done = 1; if (e->render_dir[0]) gen_config(e); }
+    if (!e->render_dir[0]) return 0;                                /* RenderGenerator.cc:109-111 */
+    char path[1200];
+    snprintf(path, sizeof path, "%s/video_%d.txt", e->render_dir, e->file_ct);
+    FILE *f = fopen(path, e->frame_ct == 0 ? "w" : "a");
+    if (!f) return 0;
+    if (e->frame_ct == 0) {
+        int nw = 0;
+        for (int i = 0; i < e->w * e->h; i++) nw += e->cell[i] == CELL_WALL;
+        fprintf(f, "W %d\n", nw);
+        for (int i = 0; i < e->w * e->h; i++) if (e->cell[i] == CELL_WALL) fprintf(f, "%d %d\n", i % e->w, i / e->w);
+    }
+    int n_agents = 0;
+    for (int g = 0; g < e->ngroup; g++) {
+        n_agents += e->grp[g].n;
+        if (e->type[e->grp[g].type].can_absorb)
+            for (int j = 0; j < e->grp[g].n; j++) if (!e->pool[e->grp[g].slot[j]].absorbed) n_agents--;
+    }
+    fprintf(f, "F %d %d 0\n", n_agents, e->nev);
+    static const int dir2angle[4] = {0, 90, 180, 270};
+    for (int g = 0; g < e->ngroup; g++) {
+        const Type *t = &e->type[e->grp[g].type];
+        for (int j = 0; j < e->grp[g].n; j++) {
+            const Agent *a = &e->pool[e->grp[g].slot[j]];
+            if (t->can_absorb && !a->absorbed) continue;
+            int hp = (int)(100 * a->hp / t->hp);
+            hp = hp < 0 ? 0 : (hp > 100 ? 100 : hp);
+            fprintf(f, "%d %d %d %d %d %d\n", a->id, hp, dir2angle[a->dir], a->x, a->y, g);
+        }
+    }
+    for (int i = 0; i < e->nev; i++) fprintf(f, "0 %d %d %d\n", e->ev[3 * i], e->ev[3 * i + 1], e->ev[3 * i + 2]);
+    fclose(f);
+    if (e->frame_ct++ > 10000) { e->frame_ct = 0; e->file_ct++; }  /* frame_per_file = 10000 (RenderGenerator.cc:19,181-184) */
+    return 0;
+}
+API int env_render_next_file(void *game) { Env *e = game; e->file_ct++; e->frame_ct = 0; return 0; }
 API int gridworld_set_goal(void *game, int g, const char *m, const int *b) {     /* GridWorld.cc:667-679 (deprecated) */
     Env *e = game;
     (void)b;

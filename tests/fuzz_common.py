@@ -418,9 +418,9 @@ def play_chaotic(seed, lib_a, lib_b, steps=24, **kw):
     n_groups = len(make_env(lib_a, seed).get_handles())
     order = [int(g) for g in rs.permutation(n_groups)]
     import tempfile
-    # the C restatement has no replay dump; with more than 4 groups the reference indexes its 4-row colour table out of
-    # bounds (RenderGenerator.cc gen_config: uninitialised stack in config.json)
-    can_render = all(l != pc.PORT_LIB for l in (lib_a, lib_b)) and n_groups <= 4
+    # with more than 4 groups the reference indexes its 4-row colour table out of bounds (RenderGenerator.cc gen_config:
+    # uninitialised stack in config.json)
+    can_render = n_groups <= 4
     da, db = (tempfile.mkdtemp(), tempfile.mkdtemp()) if can_render else (None, None)
     a = trace_chaotic(make_env(lib_a, seed), steps, seed, None, order, render_dir=da)
     b = trace_chaotic(make_env(lib_b, seed, **kw), steps, seed, None, order, render_dir=db)

@@ -168,5 +168,23 @@ def test_port_serves_the_cold_info_getters_like_the_reference(which):
 
 
 def test_port_reproduces_the_golden_edge_cases():
-    """tests/golden/edge_cases.npz (recorded from the compiled reference): a group reward that survives reset()"""
-    gc.check_edge_cases(pc.PORT_LIB, None, with_render=False)
+    """tests/golden/edge_cases.npz (recorded from the compiled reference): a group reward that survives reset(), the
+    replay frames after a self-kill"""
+    import tempfile
+    gc.check_edge_cases(pc.PORT_LIB, tempfile.mkdtemp())
+
+
+@pytest.mark.skipif(not os.path.exists(pc.REF_LIB), reason="needs oracle/_ref")
+@pytest.mark.parametrize("which", ["battle", "arrange", "turn", "food"])
+def test_port_writes_the_replay_dump_of_the_reference(tmp_path, which):
+    """env_render: config.json + video_N.txt frames incl. attack events, render_window_info / attack_event
+    (RenderGenerator.cc:56-185, GridWorld.cc:797-842)"""
+    from test_emu_parity_cpu import _render_episode
+    scen = {"battle": lambda lib: pc.make_battle(lib, 30, 200, 3), "arrange": lambda lib: pc.make_arrange(lib, 30, 12),
+            "turn": lambda lib: pc.make_turn(lib, 30, 5), "food": lambda lib: pc.make_food(lib, 30, 3)}[which]
+    want = _render_episode(pc.REF_LIB, str(tmp_path / "ref"), scen)
+    got = _render_episode(pc.PORT_LIB, str(tmp_path / "port"), scen)
+    assert want[0].keys() == got[0].keys()
+    for name in want[0]:
+        assert want[0][name] == got[0][name], name
+    assert want[1] == got[1] and want[2] == got[2]
