@@ -154,11 +154,9 @@ def _render_episode(lib, tmpdir, scenario):
 @pytest.mark.parametrize("which", ["battle", "arrange", "turn", "food"])
 def test_render_dump_is_byte_identical(emu, tmp_path, which):
     """env_render: config.json + video_N.txt frames incl. attack events (RenderGenerator.cc:63-185)"""
-    if not os.path.exists(pc.REF_LIB):
-        pytest.skip("needs the compiled reference")
     scen = {"battle": lambda lib: pc.make_battle(lib, 30, 200, 3), "arrange": lambda lib: pc.make_arrange(lib, 30, 12),
             "turn": lambda lib: pc.make_turn(lib, 30, 5), "food": lambda lib: pc.make_food(lib, 30, 3)}[which]
-    a = _render_episode(pc.REF_LIB, str(tmp_path / "ref"), scen)
+    a = _render_episode(pc.REF_LIB if os.path.exists(pc.REF_LIB) else pc.PORT_LIB, str(tmp_path / "ref"), scen)
     b = _render_episode(emu, str(tmp_path / "emu"), scen)
     assert sorted(a[0]) == sorted(b[0]) and "config.json" in a[0]
     for name in a[0]:
@@ -272,10 +270,9 @@ def test_uncollected_group_reward_survives_reset(emu):
 
 def test_self_kill_feeds_the_corpse(emu, tmp_path):
     """found by the chaotic fuzz: hp of an un-culled corpse in the replay dump after a self-aimed in-group attack"""
-    if not os.path.exists(pc.REF_LIB):
-        pytest.skip("needs the compiled reference (replay dump)")
-    act = pc.self_kill_frames(pc.REF_LIB, None)
-    want = pc.self_kill_frames(pc.REF_LIB, str(tmp_path / "ref"), act)
+    checker = pc.REF_LIB if os.path.exists(pc.REF_LIB) else pc.PORT_LIB
+    act = pc.self_kill_frames(checker, None)
+    want = pc.self_kill_frames(checker, str(tmp_path / "ref"), act)
     got = pc.self_kill_frames(emu, str(tmp_path / "emu"), act)
     np.testing.assert_allclose(want[0], got[0], rtol=0, atol=pc.REWARD_TOL)
     assert want[1] == got[1]

@@ -143,10 +143,8 @@ def test_absorbing_goals_that_move_themselves():
 def test_render_dump_matches_reference(tmp_path):
     """env_render through the CUDA engine: config.json + video_N.txt byte-identical, attack events included"""
     from test_emu_parity_cpu import _render_episode
-    if not os.path.exists(pc.REF_LIB):
-        pytest.skip("the replay dump is only provided by the compiled reference (oracle/_ref)")
     scen = lambda lib: pc.make_battle(lib, 30, 200, 3)
-    a = _render_episode(pc.REF_LIB, str(tmp_path / "ref"), scen)
+    a = _render_episode(checker_lib(), str(tmp_path / "ref"), scen)
     b = _render_episode(pc.CUDA_LIB, str(tmp_path / "gpu"), scen)
     assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
 

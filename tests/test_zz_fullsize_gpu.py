@@ -110,10 +110,8 @@ def test_uncollected_group_reward_survives_reset():
 
 def test_self_kill_feeds_the_corpse(tmp_path):
     """hp of an un-culled corpse in the replay dump after a self-aimed in-group attack (Map.cc:265-273)"""
-    if not os.path.exists(pc.REF_LIB):
-        pytest.skip("needs the compiled reference (replay dump)")
-    act = pc.self_kill_frames(pc.REF_LIB, None)
-    want = pc.self_kill_frames(pc.REF_LIB, str(tmp_path / "ref"), act)
+    act = pc.self_kill_frames(checker_lib(), None)
+    want = pc.self_kill_frames(checker_lib(), str(tmp_path / "ref"), act)
     got = pc.self_kill_frames(ENGINE, str(tmp_path / "b200"), act)
     np.testing.assert_allclose(want[0], got[0], rtol=0, atol=pc.REWARD_TOL)
     assert want[1] == got[1]
