@@ -1133,8 +1133,10 @@ void Engine::get_info(int group, const char *name, void *void_buffer) {        /
         check_group(group, "get_info");
         const AgentTypeDef &t = *group_type_[group];
         for (int i = 0; i < t.view.height * t.view.width; ++i) ib[i] = -1;
-        for (int i = 0; i < t.attack.count; ++i)
-            ib[(t.attack.dy[i] - t.view.y1) * t.view.width + (t.attack.dx[i] - t.view.x1)] = i;
+        for (int i = 0; i < t.attack.count; ++i) {          // attack cells outside the view rectangle are dropped (the
+            const int r = t.attack.dy[i] - t.view.y1, c = t.attack.dx[i] - t.view.x1;   // reference writes out of bounds there)
+            if (r >= 0 && r < t.view.height && c >= 0 && c < t.view.width) ib[r * t.view.width + c] = i;
+        }
     } else if (strequ(name, "attack_base")) {
         check_group(group, "get_info"); ib[0] = group_type_[group]->attack_base;
     } else if (strequ(name, "both_attack")) {

@@ -797,7 +797,10 @@ API int env_get_info(void *game, int g, const char *name, void *buf) {          
     else if (!strcmp(name, "view2attack")) {
         const Type *t = &e->type[e->grp[g].type];
         for (int i = 0; i < t->view.width * t->view.height; i++) ib[i] = -1;
-        for (int i = 0; i < t->attack.count; i++) ib[(t->attack.dy[i] - t->view.y1) * t->view.width + t->attack.dx[i] - t->view.x1] = i;
+        for (int i = 0; i < t->attack.count; i++) {                 /* (cells outside the view: out of bounds in the reference, dropped here) */
+            int r = t->attack.dy[i] - t->view.y1, c = t->attack.dx[i] - t->view.x1;
+            if (r >= 0 && r < t->view.height && c >= 0 && c < t->view.width) ib[r * t->view.width + c] = i;
+        }
     } else if (!strcmp(name, "render_window_info")) {               /* GridWorld.cc:797-834 */
         e->first_render_done = 1;
         int x1 = ib[0], y1 = ib[1], x2 = ib[2], y2 = ib[3], ct = 1;
