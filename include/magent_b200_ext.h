@@ -20,6 +20,8 @@ void *magent_b200_host_alloc(size_t bytes);
 int magent_b200_host_free(void *p);
 
 int magent_b200_sync(EnvHandle game);          /* wait for all queued device work of this game */
+/* env_step(game, done) also accepts a CUDA device pointer for `done`: the flag is written on the device and the call
+ * returns without waiting for the step (device-resident loops; reference src/runtime_api.h:31 takes a host int). */
 /* route the following setup calls (add_agents, seed) to one arena of the batch; -1 = all arenas */
 int magent_b200_select_arena(EnvHandle game, int arena);
 /* set_action with uniform random actions generated on the device (throughput runs; not part of parity).
@@ -35,10 +37,19 @@ int magent_b200_get_observation_f16(EnvHandle game, GroupHandle group, void **bu
 int magent_b200_get_counters(EnvHandle game, long long *out, int capacity);
 
 /* instrumentation: kernels launched by this library in this process; optional CUDA-event timing of the
- * obs-render kernel (total milliseconds and launches since enabled; adds one event sync per launch). */
+ * obs-render kernel of one game (total milliseconds and launches since enabled; read after the fact, no sync added). */
 long long magent_b200_launch_count(void);
-int magent_b200_set_profiling(int on);
-int magent_b200_get_profile(double *obs_ms_total, long long *obs_launches);
+int magent_b200_set_profiling(EnvHandle game, int on);
+int magent_b200_get_profile(EnvHandle game, double *obs_ms_total, long long *obs_launches);
+/* bytes moved by the step-loop calls of this game so far: [0] device->host over PCIe, [1] host->device, [2] written into
+ * caller host buffers by the engine's host threads (env_get_observation with host pointers).  Returns the number written. */
+int magent_b200_get_io_stats(EnvHandle game, long long *out, int capacity);
+/* the cudaStream_t all kernels of this game are launched on (a blocking stream: work on the legacy default stream is
+ * ordered with it both ways, so CUDA-pointer consumers on the default stream need no extra synchronisation) */
+void *magent_b200_stream(EnvHandle game);
+/* host threads env_get_observation uses to write host buffers (MAGENT_B200_HOST_THREADS overrides) */
+int magent_b200_host_threads(void);
+int magent_b200_set_host_threads(int n);       /* 0 = default (usable cores, at most 16) */
 
 #ifdef __cplusplus
 }

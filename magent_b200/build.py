@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libmagent.so")
-SOURCES = ["engine.cc", "shim.cc", "backend_cuda.cu"]
-HEADERS = ["hd.h", "dev_types.h", "step_phases.h", "obs_phases.h", "backend.h", "engine.h",
+SOURCES = ["engine.cc", "shim.cc", "host_expand.cc", "backend_cuda.cu"]
+HEADERS = ["hd.h", "dev_types.h", "step_phases.h", "obs_phases.h", "backend.h", "engine.h", "host_expand.h",
            os.path.join("..", "..", "include", "magent_runtime_api.h"),
            os.path.join("..", "..", "include", "magent_b200_ext.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -21,6 +21,9 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-ccbin", "/usr/bin/g++",
          "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+# host-only sources (.cc) go through g++ directly: no CUDA in them, and host_expand.cc uses per-function ISA targets
+CXX = "/usr/bin/g++"                     # the same host compiler nvcc uses (-ccbin)
+CXXFLAGS = ["-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wno-unused-function", "-pthread"]
 
 
 def up_to_date():
@@ -38,7 +41,10 @@ def build(force=False, verbose=False):
     objs = []
     for src in SOURCES:
         obj = os.path.join(HERE, "lib", src.replace(".", "_") + ".o")
-        cmd = [NVCC] + FLAGS + ["-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
+        if src.endswith(".cu"):
+            cmd = [NVCC] + FLAGS + ["-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
+        else:
+            cmd = [CXX] + CXXFLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or res.returncode != 0:
             sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
@@ -49,7 +55,7 @@ def build(force=False, verbose=False):
             f.write("".join(l for l in res.stderr.splitlines(True) if "Compile time" not in l))
         objs.append(obj)
     cmd = [NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xlinker", "-Bsymbolic", "-o", LIB] + objs
+           "-Xlinker", "-Bsymbolic", "-Xcompiler", "-pthread", "-o", LIB] + objs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)

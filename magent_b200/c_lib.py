@@ -66,8 +66,12 @@ EXT_SIGNATURES = {
     "magent_b200_get_observation_f16": ([_vp, ctypes.c_int, ctypes.POINTER(_vp)], ctypes.c_int),
     "magent_b200_get_counters": ([_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int], ctypes.c_int),
     "magent_b200_last_error": ([], ctypes.c_char_p),
-    "magent_b200_set_profiling": ([ctypes.c_int], ctypes.c_int),
-    "magent_b200_get_profile": ([ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)], ctypes.c_int),
+    "magent_b200_set_profiling": ([_vp, ctypes.c_int], ctypes.c_int),
+    "magent_b200_get_profile": ([_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)], ctypes.c_int),
+    "magent_b200_stream": ([_vp], _vp),
+    "magent_b200_get_io_stats": ([_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int], ctypes.c_int),
+    "magent_b200_host_threads": ([], ctypes.c_int),
+    "magent_b200_set_host_threads": ([ctypes.c_int], ctypes.c_int),
     "magent_b200_launch_count": ([], ctypes.c_longlong),
 }
 

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string>
 #include <string.h>
+#include <atomic>
 #include <vector>
 
 #include "backend.h"
@@ -38,11 +39,48 @@ namespace be {
                                          __FILE__, __LINE__, #expr);                              \
     } while (0)
 
-static int g_device = -1, g_sms = 0;
-static long long g_launches = 0;
-static bool g_profile = false;
-static std::vector<cudaEvent_t> g_events;     // pairs recorded around obs-render launches
-static size_t g_events_used = 0;
+static std::atomic<long long> g_launches{0};       // instrumentation only (magent_b200_launch_count)
+
+// Per-engine device context.  Everything the backend needs to remember between calls lives here, nothing in
+// process-global state: two engines on two devices (or on one) never see each other's scratch.
+struct Ctx {
+    int device = 0, sms = 0;
+    cudaStream_t stream = nullptr;       // every kernel of this engine; created blocking, so work queued on the legacy
+                                         // default stream (torch's default stream) stays ordered with it both ways
+    cudaStream_t copy = nullptr;         // wire / dense DMA traffic (non-blocking; ordered by events)
+    cudaEvent_t ev_wire = nullptr, ev_dense = nullptr, ev_done = nullptr;
+    bool profile = false;
+    std::vector<cudaEvent_t> events;     // pairs recorded around obs-render launches
+    size_t events_used = 0;
+    // products of the last launch_obs_prepare
+    float *mm_pad = nullptr; size_t mm_pad_n = 0; int mm_stride = 0;
+    // per-observer headers of the render kernel
+    int4 *obs_hdr = nullptr; size_t obs_hdr_n = 0;
+    // cudaFuncSetAttribute caches (per device: a context never changes device)
+    size_t step_smem_configured = 0;
+    struct ObsCfg { size_t smem = (size_t)-1; int ctas_per_sm = 1; } obs_cfg[8];
+    int *pin_done = nullptr; size_t pin_done_n = 0;         // pinned read-back of EngineDev::done
+    int *pin_counts = nullptr; size_t pin_counts_n = 0;     // pinned read-back of EngineDev::off (clear_dead)
+    cudaEvent_t ev_counts = nullptr;
+    // wire path (host-buffer observations)
+    WireMark *wire_slots = nullptr; size_t wire_slots_n = 0;         // [n_total][n_in] worst-case slots
+    WireMark *wire_stream = nullptr; size_t wire_stream_n = 0;       // compacted marks
+    WireHdr *wire_hdr = nullptr; size_t wire_hdr_n = 0;
+    long long *wire_base = nullptr; size_t wire_base_n = 0;          // [n_chunks + 1] (device)
+    int *wire_chunk_total = nullptr;
+    // page-locked staging of the above
+    WireHdr *h_wire_hdr = nullptr; size_t h_wire_hdr_n = 0;
+    WireMark *h_wire_marks = nullptr; size_t h_wire_marks_n = 0;
+    long long *h_wire_base = nullptr; size_t h_wire_base_n = 0;
+    float *h_mm = nullptr; size_t h_mm_n = 0;
+    std::vector<cudaEvent_t> wave_events;
+    int waves_queued = 0;
+    std::vector<cudaEvent_t> dma_events; size_t dma_head = 0, dma_tail = 0;
+};
+
+struct DeviceGuard {                     // every entry point runs on its context's device, whatever the caller selected
+    explicit DeviceGuard(const Ctx *c) { int cur = -1; cudaGetDevice(&cur); if (cur != c->device) CUDA_CHECK(cudaSetDevice(c->device)); }
+};
 
 const char *name() { return "cuda-sm_100a"; }
 
@@ -58,32 +96,70 @@ int device_count() {
     return n;
 }
 
-bool init(int device, std::string *err) {
+Ctx *create(int device, std::string *err) {
     int n = device_count();
-    if (n <= 0) { if (err) *err = "cudaGetDeviceCount found no device"; return false; }
+    if (n <= 0) { if (err) *err = "cudaGetDeviceCount found no device"; return nullptr; }
     if (device < 0) {
         if (cudaGetDevice(&device) != cudaSuccess) device = 0;
     }
-    if (device >= n) { if (err) *err = "device_id out of range"; return false; }
+    if (device >= n) { if (err) *err = "device_id out of range"; return nullptr; }
     cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) { if (err) *err = cudaGetErrorString(e); return false; }
+    if (e != cudaSuccess) { if (err) *err = cudaGetErrorString(e); return nullptr; }
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    g_device = device;
-    g_sms = prop.multiProcessorCount;
-    return true;
+    Ctx *c = new Ctx();
+    c->device = device;
+    c->sms = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreate(&c->stream));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_wire, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_dense, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_counts, cudaEventDisableTiming));
+    return c;
 }
-int sm_count() { return g_sms; }
+void destroy(Ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy);
+    for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->wave_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->dma_events) cudaEventDestroy(e);
+    cudaEventDestroy(c->ev_wire); cudaEventDestroy(c->ev_dense); cudaEventDestroy(c->ev_done);
+    cudaFree(c->mm_pad); cudaFree(c->obs_hdr);
+    cudaFree(c->wire_slots); cudaFree(c->wire_stream); cudaFree(c->wire_hdr); cudaFree(c->wire_base); cudaFree(c->wire_chunk_total);
+    cudaEventDestroy(c->ev_counts); cudaFreeHost(c->pin_counts);
+    cudaFreeHost(c->pin_done); cudaFreeHost(c->h_wire_hdr); cudaFreeHost(c->h_wire_marks); cudaFreeHost(c->h_wire_base); cudaFreeHost(c->h_mm);
+    cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy);
+    delete c;
+}
+int device_of(const Ctx *c) { return c->device; }
+int sm_count(const Ctx *c) { return c->sms; }
+void *stream_handle(const Ctx *c) { return (void *)c->stream; }
 
-void *dmalloc(size_t bytes) { void *p = nullptr; CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 16)); return p; }
-void dfree(void *p) { if (p) cudaFree(p); }
-void dmemset(void *p, int byte, size_t bytes) { CUDA_CHECK(cudaMemsetAsync(p, byte, bytes, 0)); }
-void h2d(void *dst, const void *src, size_t bytes) { if (bytes) CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); }
-void d2h(void *dst, const void *src, size_t bytes) { if (bytes) CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); }
-void d2d(void *dst, const void *src, size_t bytes) { if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, 0)); }
+void *dmalloc(Ctx *c, size_t bytes) { DeviceGuard g(c); void *p = nullptr; CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 16)); return p; }
+void dfree(Ctx *c, void *p) { if (p) { DeviceGuard g(c); cudaFree(p); } }
+void dmemset(Ctx *c, void *p, int byte, size_t bytes) { DeviceGuard g(c); CUDA_CHECK(cudaMemsetAsync(p, byte, bytes, c->stream)); }
+void h2d(Ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!bytes) return;
+    DeviceGuard g(c);
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+void d2h(Ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!bytes) return;
+    DeviceGuard g(c);
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+void d2d(Ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!bytes) return;
+    DeviceGuard g(c);
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+}
 void *host_alloc(size_t bytes) {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
 void host_free(void *p) { if (p) cudaFreeHost(p); }
@@ -93,27 +169,34 @@ bool is_device_ptr(const void *p) {
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
-void sync() { CUDA_CHECK(cudaDeviceSynchronize()); }
-long long launch_count() { return g_launches; }
-void profile_enable(bool on) { g_profile = on; g_events_used = 0; }
-static void profile_pair(cudaEvent_t *e0, cudaEvent_t *e1) {
-    if (g_events_used + 2 > g_events.size()) {
-        for (int i = 0; i < 64; ++i) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); g_events.push_back(e); }
+bool is_pinned_host_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+void sync(Ctx *c) { DeviceGuard g(c); CUDA_CHECK(cudaStreamSynchronize(c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->copy)); }
+long long launch_count() { return g_launches.load(); }
+void profile_enable(Ctx *c, bool on) { c->profile = on; c->events_used = 0; }
+static void profile_pair(Ctx *c, cudaEvent_t *e0, cudaEvent_t *e1) {
+    if (c->events_used + 2 > c->events.size()) {
+        for (int i = 0; i < 64; ++i) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); c->events.push_back(e); }
     }
-    *e0 = g_events[g_events_used]; *e1 = g_events[g_events_used + 1];
-    g_events_used += 2;
+    *e0 = c->events[c->events_used]; *e1 = c->events[c->events_used + 1];
+    c->events_used += 2;
 }
 // total device time of the obs-render launches recorded since profile_enable(true); no sync was added
 // to the timed region: the events are read here, after the fact
-void profile_read(double *ms, long long *n) {
+void profile_read(Ctx *c, double *ms, long long *n) {
+    DeviceGuard g(c);
     double total = 0.0;
-    for (size_t i = 0; i + 1 < g_events_used; i += 2) {
-        CUDA_CHECK(cudaEventSynchronize(g_events[i + 1]));
+    for (size_t i = 0; i + 1 < c->events_used; i += 2) {
+        CUDA_CHECK(cudaEventSynchronize(c->events[i + 1]));
         float t = 0;
-        CUDA_CHECK(cudaEventElapsedTime(&t, g_events[i], g_events[i + 1]));
+        CUDA_CHECK(cudaEventElapsedTime(&t, c->events[i], c->events[i + 1]));
         total += t;
     }
-    *ms = total; *n = (long long)(g_events_used / 2);
+    *ms = total; *n = (long long)(c->events_used / 2);
 }
 
 static void post_launch(const char *what) {
@@ -398,26 +481,28 @@ static const int GRID_MODE_THRESHOLD = 32768;    // agents per arena above which
 
 // CTA-per-arena block size: the phases are latency-bound loops over the arena's agents, so with many
 // arenas we want many (small) CTAs resident per SM; with few arenas the single CTA should be wide.
-static int step_block_size(int arenas, int max_agents) {
-    if (arenas >= 2 * g_sms) return 256;
+static int step_block_size(int sms, int arenas, int max_agents) {
+    if (arenas >= 2 * sms) return 256;
     if (max_agents >= 768) return 1024;
     return max_agents >= 384 ? 512 : 256;
 }
 
-static int coop_grid(const void *kernel) {
+static int coop_grid(const Ctx *c, const void *kernel) {
     int per_sm = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GRID_THREADS, 0));
     if (per_sm < 1) mg::fatal("cooperative kernel does not fit on an SM");
-    int g = per_sm * g_sms;
+    int g = per_sm * c->sms;
     return g > 4096 ? 4096 : g;
 }
 
-void launch_step(const EngineDev *dE, const EngineDev &hE, const StepArgs &S, int max_agents) {
+void launch_step(Ctx *c, const EngineDev *dE, const EngineDev &hE, const StepArgs &S, int max_agents) {
+    DeviceGuard guard(c);
+    const int g_sms = c->sms;
     if (max_agents > GRID_MODE_THRESHOLD) {
-        int grid = coop_grid((const void *)step_kernel_grid);
+        int grid = coop_grid(c, (const void *)step_kernel_grid);
         StepArgs s = S;
         void *args[] = {(void *)&dE, (void *)&s};
-        CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)step_kernel_grid, dim3(grid), dim3(GRID_THREADS), args, 0, 0));
+        CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)step_kernel_grid, dim3(grid), dim3(GRID_THREADS), args, 0, c->stream));
         post_launch("step_kernel_grid");
     } else {
         // scratch in shared memory whenever one arena's scratch fits: fewer, wider CTAs (latency per phase drops
@@ -425,16 +510,15 @@ void launch_step(const EngineDev *dE, const EngineDev &hE, const StepArgs &S, in
         const size_t sbytes = step_scratch_bytes(hE.cap_total, hE.max_body);
         static const int smem_pref = getenv("MAGENT_B200_STEP_SMEM") ? atoi(getenv("MAGENT_B200_STEP_SMEM")) : -1;
         const bool in_smem = sbytes <= 200 * 1024 && smem_pref != 0;
-        int threads = step_block_size(hE.A, max_agents);
+        int threads = step_block_size(g_sms, hE.A, max_agents);
         size_t smem = 0;
         if (in_smem) {
             smem = sbytes;
             // few arenas: one wide CTA each; many arenas: narrower CTAs so that two fit on an SM and overlap
             threads = max_agents >= 768 ? (hE.A > g_sms ? 512 : 1024) : (max_agents >= 384 ? 512 : 256);
-            static size_t configured = 0;
-            if (smem > configured) {
+            if (smem > c->step_smem_configured) {
                 CUDA_CHECK(cudaFuncSetAttribute(step_kernel_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured = smem;
+                c->step_smem_configured = smem;
             }
         }
         // measurement knob (profiles/scripts): MAGENT_B200_STEP_THREADS=256..1024 overrides the block size choice above
@@ -444,20 +528,22 @@ void launch_step(const EngineDev *dE, const EngineDev &hE, const StepArgs &S, in
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_cta, threads, smem));
         if (per_sm < 1) per_sm = 1;
         int grid = hE.A < per_sm * g_sms ? hE.A : per_sm * g_sms;
-        step_kernel_cta<<<grid, threads, smem>>>(dE, S, in_smem ? 1 : 0);
+        step_kernel_cta<<<grid, threads, smem, c->stream>>>(dE, S, in_smem ? 1 : 0);
         post_launch("step_kernel_cta");
     }
 }
 
-void launch_cull(const EngineDev *dE, const EngineDev &hE, unsigned curmask, int max_agents) {
+void launch_cull(Ctx *c, const EngineDev *dE, const EngineDev &hE, unsigned curmask, int max_agents) {
+    DeviceGuard guard(c);
+    const int g_sms = c->sms;
     if (max_agents > GRID_MODE_THRESHOLD) {
-        int grid = coop_grid((const void *)cull_kernel_grid);
+        int grid = coop_grid(c, (const void *)cull_kernel_grid);
         void *args[] = {(void *)&dE, (void *)&curmask};
-        CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)cull_kernel_grid, dim3(grid), dim3(GRID_THREADS), args, 0, 0));
+        CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)cull_kernel_grid, dim3(grid), dim3(GRID_THREADS), args, 0, c->stream));
         post_launch("cull_kernel_grid");
     } else {
         int grid = hE.A < 8 * g_sms ? hE.A : 8 * g_sms;
-        cull_kernel_cta<<<grid, step_block_size(hE.A, max_agents)>>>(dE, curmask);
+        cull_kernel_cta<<<grid, step_block_size(g_sms, hE.A, max_agents), 0, c->stream>>>(dE, curmask);
         post_launch("cull_kernel_cta");
     }
 }
@@ -480,8 +566,9 @@ __global__ void __launch_bounds__(1024) offsets_kernel(const EngineDev *gE) {
     if (threadIdx.x == 0) off[A] = running;
 }
 
-void launch_offsets(const EngineDev *dE, const EngineDev &hE) {
-    offsets_kernel<<<hE.G, 1024>>>(dE);
+void launch_offsets(Ctx *c, const EngineDev *dE, const EngineDev &hE) {
+    DeviceGuard guard(c);
+    offsets_kernel<<<hE.G, 1024, 0, c->stream>>>(dE);
     post_launch("offsets_kernel");
 }
 
@@ -500,6 +587,7 @@ __global__ void __launch_bounds__(256) info_kernel(const EngineDev *gE, unsigned
     const EngineDev &E = *gE;
     const int *off = E.off + (size_t)g * (E.A + 1);
     const AgentSoA &s = E.grp[g].soa[(curmask >> g) & 1u];
+    n_total = min(n_total, off[E.A]);         // the host may still hold the counts from before the last cull (upper bounds)
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_total; o += gridDim.x * blockDim.x) {
         int a = E.A == 1 ? 0 : locate_arena(off, E.A, o);
         long gi = (long)a * E.grp[g].cap + (o - off[a]);
@@ -514,10 +602,11 @@ __global__ void __launch_bounds__(256) info_kernel(const EngineDev *gE, unsigned
     }
 }
 
-void launch_info(const EngineDev *dE, const EngineDev &, unsigned curmask, int kind, int group, void *buf, int n_total) {
+void launch_info(Ctx *c, const EngineDev *dE, const EngineDev &, unsigned curmask, int kind, int group, void *buf, int n_total) {
+    DeviceGuard guard(c);
     int grid = (n_total + 255) / 256;
-    if (grid > 8 * g_sms) grid = 8 * g_sms;
-    info_kernel<<<grid, 256>>>(dE, curmask, kind, group, buf, n_total);
+    if (grid > 8 * c->sms) grid = 8 * c->sms;
+    info_kernel<<<grid, 256, 0, c->stream>>>(dE, curmask, kind, group, buf, n_total);
     post_launch("info_kernel");
 }
 
@@ -534,6 +623,7 @@ __global__ void __launch_bounds__(256) random_actions_kernel(const EngineDev *gE
     const int *off = E.off + (size_t)g * (E.A + 1);
     const AgentSoA &s = E.grp[g].soa[(curmask >> g) & 1u];
     const unsigned na = (unsigned)E.grp[g].n_action;
+    n_total = min(n_total, off[E.A]);
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_total; o += gridDim.x * blockDim.x) {
         int a = E.A == 1 ? 0 : locate_arena(off, E.A, o);
         long gi = (long)a * E.grp[g].cap + (o - off[a]);
@@ -541,11 +631,12 @@ __global__ void __launch_bounds__(256) random_actions_kernel(const EngineDev *gE
     }
 }
 
-void launch_random_actions(const EngineDev *dE, const EngineDev &, unsigned curmask, int group,
+void launch_random_actions(Ctx *c, const EngineDev *dE, const EngineDev &, unsigned curmask, int group,
                            unsigned long long seed, int n_total) {
+    DeviceGuard guard(c);
     int grid = (n_total + 255) / 256;
-    if (grid > 8 * g_sms) grid = 8 * g_sms;
-    random_actions_kernel<<<grid, 256>>>(dE, curmask, group, seed, n_total);
+    if (grid > 8 * c->sms) grid = 8 * c->sms;
+    random_actions_kernel<<<grid, 256, 0, c->stream>>>(dE, curmask, group, seed, n_total);
     post_launch("random_actions_kernel");
 }
 
@@ -556,11 +647,6 @@ void launch_random_actions(const EngineDev *dE, const EngineDev &, unsigned curm
 //     render kernel fetches cell code and hp with two independent loads (no position -> plane -> agent chain).
 //     Only living agents own cells (dead ones were cleared in the step), stale values under empty cells are never read;
 //   * minimap (when enabled): counts per (arena, group, coarse cell); value = (float)count / (float)group size
-static float *g_mm_pad = nullptr;             // [A][g_mm_stride] normalised minimap of the last prepare
-static size_t g_mm_pad_n = 0;
-static int g_mm_stride = 0;
-static const EngineDev *g_prepare_owner = nullptr;
-bool obs_prepare_valid(const EngineDev *dE) { return g_prepare_owner == dE; }
 
 // per observation state: (1) the hp_norm plane (hp / max_hp of the occupant, Map.cc:197) at every living agent's
 // body cells -- stale values elsewhere are never read because the kind plane says "empty" there; (2) the minimap
@@ -625,32 +711,33 @@ __global__ void __launch_bounds__(256) minimap_norm_kernel(const EngineDev *gE, 
     }
 }
 
-void launch_obs_prepare(const EngineDev *dE, const EngineDev &hE, unsigned curmask, int og, float *mm_val) {
+void launch_obs_prepare(Ctx *c, const EngineDev *dE, const EngineDev &hE, unsigned curmask, int og, float *mm_val) {
+    DeviceGuard guard(c);
+    const int g_sms = c->sms;
     const int cells = hE.grp[og].view_w * hE.grp[og].view_h;
     const int total = hE.A * hE.G * cells;
     int cap_max = 0;
     for (int g = 0; g < hE.G; ++g) cap_max = cap_max > hE.grp[g].cap ? cap_max : hE.grp[g].cap;
-    g_prepare_owner = dE;
     if (mm_val) {
-        CUDA_CHECK(cudaMemsetAsync(hE.mm_count, 0, (size_t)total * 4, 0));
-        CUDA_CHECK(cudaMemsetAsync(hE.mm_total, 0, (size_t)hE.A * hE.G * 4, 0));
+        CUDA_CHECK(cudaMemsetAsync(hE.mm_count, 0, (size_t)total * 4, c->stream));
+        CUDA_CHECK(cudaMemsetAsync(hE.mm_total, 0, (size_t)hE.A * hE.G * 4, c->stream));
     }
     const int chunk = 4096;
     dim3 grid((cap_max + chunk - 1) / chunk, hE.A * hE.G);
-    obs_prepare_kernel<<<grid, 256, cells * sizeof(int)>>>(dE, curmask, og, chunk, mm_val ? 1 : 0);
+    obs_prepare_kernel<<<grid, 256, cells * sizeof(int), c->stream>>>(dE, curmask, og, chunk, mm_val ? 1 : 0);
     post_launch("obs_prepare_kernel");
     if (mm_val) {
-        g_mm_stride = (hE.G * cells + 3) & ~3;
-        const size_t need = (size_t)hE.A * g_mm_stride;
-        if (need > g_mm_pad_n) {
-            if (g_mm_pad) cudaFree(g_mm_pad);
-            CUDA_CHECK(cudaMalloc(&g_mm_pad, need * sizeof(float)));
-            CUDA_CHECK(cudaMemsetAsync(g_mm_pad, 0, need * sizeof(float), 0));
-            g_mm_pad_n = need;
+        c->mm_stride = (hE.G * cells + 3) & ~3;
+        const size_t need = (size_t)hE.A * c->mm_stride;
+        if (need > c->mm_pad_n) {
+            if (c->mm_pad) { CUDA_CHECK(cudaStreamSynchronize(c->stream)); cudaFree(c->mm_pad); }
+            CUDA_CHECK(cudaMalloc(&c->mm_pad, need * sizeof(float)));
+            CUDA_CHECK(cudaMemsetAsync(c->mm_pad, 0, need * sizeof(float), c->stream));
+            c->mm_pad_n = need;
         }
         int g2 = (total + 255) / 256;
         if (g2 > 8 * g_sms) g2 = 8 * g_sms;
-        minimap_norm_kernel<<<g2, 256>>>(dE, og, g_mm_pad, total, g_mm_stride);
+        minimap_norm_kernel<<<g2, 256, 0, c->stream>>>(dE, og, c->mm_pad, total, c->mm_stride);
         post_launch("minimap_norm_kernel");
     }
 }
@@ -739,11 +826,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 //     zeroed with coalesced 16-byte stores, then each lane writes its observer's handful of non-zeros.
 template <typename T>
 __global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr) {
+    const int n_total = min(P.n_total, P.off[P.A]);           // the host may hold pre-cull counts (upper bounds)
     const int lane = threadIdx.x & 31;
     const int n_warps = gridDim.x * (blockDim.x >> 5);
-    for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < P.n_total; base += n_warps * 32) {
+    for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < n_total; base += n_warps * 32) {
         const int o = base + lane;
-        const int cnt = min(32, P.n_total - base);
+        const int cnt = min(32, n_total - base);
         // the 32 feature rows of this warp are one contiguous block of cnt * F elements: zero it with 16-byte stores (the
         // block starts 16-byte aligned because base % 32 == 0), then every lane drops its own observer's few non-zeros
         T *rows = (T *)P.feature + (size_t)base * P.F;
@@ -756,7 +844,7 @@ __global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr
             for (int q = lane; q < total; q += 32) rows[q] = ObsOut<T>::cv(0.0f);
         }
         __syncwarp();                                          // orders the zero fill before the value stores below
-        if (o < P.n_total) {
+        if (o < n_total) {
             const int a = P.A == 1 ? 0 : locate_arena(P.off, P.A, o);
             const long gi = (long)a * P.cap + (o - P.off[a]);
             const int x = P.x[gi], y = P.y[gi];
@@ -802,6 +890,7 @@ __global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr
 template <typename T, int NIT, bool TURN>
 __global__ void __launch_bounds__(32 * ObsOut<T>::TA, OBS_MIN_CTAS * OBS_TA_N / ObsOut<T>::TA)
 obs_render_kernel(const __grid_constant__ ObsParams P) {
+    const int n_total = min(P.n_total, __ldg(P.off + P.A));   // the host may hold pre-cull counts (upper bounds)
     constexpr int OBS_TA = ObsOut<T>::TA;
     constexpr int OBS_THREADS = 32 * OBS_TA;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -845,7 +934,7 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
     }
     __syncthreads();
     const int n_in = n_in_s;
-    const int n_tiles = (P.n_total + OBS_TA - 1) / OBS_TA;
+    const int n_tiles = (n_total + OBS_TA - 1) / OBS_TA;
     // this lane's slice of the view LUT never changes: small views keep it in registers, large ones re-read smem
     constexpr bool LUT_REGS = NIT <= 4 && !TURN;
     int2 lreg[LUT_REGS ? NIT : 1];
@@ -906,14 +995,14 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
     bool prev_tail = false;                    // the previous observer had cells beyond NIT * 32 marked (large views)
     {
         const int o0 = tile * OBS_TA + warp, o1 = next_tile(tile) * OBS_TA + warp;
-        const bool on0 = tile < tile_end && o0 < P.n_total;
+        const bool on0 = tile < tile_end && o0 < n_total;
         if (on0) hA = P.hdr[o0];
-        if (o1 < P.n_total) hA1 = P.hdr[o1];
+        if (o1 < n_total) hA1 = P.hdr[o1];
         load_kinds(hA, on0, kind);
     }
     for (; tile < tile_end; tile = next_tile(tile)) {
         const int t0 = tile * OBS_TA;
-        const int cnt = min(OBS_TA, P.n_total - t0);
+        const int cnt = min(OBS_TA, n_total - t0);
         const bool active = warp < cnt;
         const int a = hA.z;
         // occupied cells only: the occupant's hp / max_hp (the kinds were loaded one tile ago)
@@ -929,11 +1018,11 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
         int kind1[NIT];
         const int t1 = next_tile(tile);
         const long o1 = (long)t1 * OBS_TA + warp;
-        load_kinds(hA1, o1 < P.n_total, kind1);
+        load_kinds(hA1, o1 < n_total, kind1);
         int4 hA2 = zero4;
         {
             const long o2 = (long)next_tile(t1) * OBS_TA + warp;
-            if (o2 < P.n_total) hA2 = P.hdr[o2];
+            if (o2 < n_total) hA2 = P.hdr[o2];
         }
         // the previous tile's bulk store must have finished READING the buffer before it is touched
         if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -1036,53 +1125,52 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-static int4 *g_obs_hdr = nullptr;
-static size_t g_obs_hdr_n = 0;
-
 template <typename T, int NIT, bool TURN>
-static void launch_obs_typed(const EngineDev &hE, ObsParams &P, int n_total) {
+static void launch_obs_typed(Ctx *c, int cfg_slot, const EngineDev &hE, ObsParams &P, int n_total,
+                             bool with_headers = true, bool headers_only = false) {
+    const int g_sms = c->sms;
     constexpr int TA = ObsOut<T>::TA;
     constexpr int THREADS = 32 * TA;
     const size_t tile_bytes = (size_t)TA * P.rec * sizeof(T);            // multiple of 16 by construction of TA
     const size_t smem = tile_bytes + (size_t)(P.turn ? 4 : 1) * ((P.cells + 1) & ~1) * sizeof(int2);
     if (smem > 227 * 1024) mg::fatal("observation record too large for the render kernel (%zu bytes of shared memory)", smem);
     const int tiles = (n_total + TA - 1) / TA;
-    if ((size_t)n_total > g_obs_hdr_n) {                                 // scratch owned by the backend: per-agent headers
-        if (g_obs_hdr) cudaFree(g_obs_hdr);
-        g_obs_hdr_n = (size_t)n_total + n_total / 4 + 64;
-        CUDA_CHECK(cudaMalloc(&g_obs_hdr, g_obs_hdr_n * sizeof(int4)));
+    if ((size_t)n_total > c->obs_hdr_n) {                                // scratch owned by the context: per-agent headers
+        if (c->obs_hdr) { CUDA_CHECK(cudaStreamSynchronize(c->stream)); cudaFree(c->obs_hdr); }
+        c->obs_hdr_n = (size_t)n_total + n_total / 4 + 64;
+        CUDA_CHECK(cudaMalloc(&c->obs_hdr, c->obs_hdr_n * sizeof(int4)));
     }
-    P.hdr = g_obs_hdr;
-    {
+    P.hdr = c->obs_hdr;
+    if (with_headers) {
         int gt = (n_total + 255) / 256;                                  // one warp per 32 observers
         if (gt > 16 * g_sms) gt = 16 * g_sms;
-        obs_headers_kernel<T><<<gt, 256>>>(P, g_obs_hdr);
+        obs_headers_kernel<T><<<gt, 256, 0, c->stream>>>(P, c->obs_hdr);
         post_launch("obs_headers_kernel");
     }
-    static size_t configured = (size_t)-1;
-    static int ctas_per_sm = 1;
-    if (smem != configured) {
+    if (headers_only) return;
+    Ctx::ObsCfg &cfg = c->obs_cfg[cfg_slot];
+    if (smem != cfg.smem) {
         CUDA_CHECK(cudaFuncSetAttribute(obs_render_kernel<T, NIT, TURN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, obs_render_kernel<T, NIT, TURN>, THREADS, smem));
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-        configured = smem;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.ctas_per_sm, obs_render_kernel<T, NIT, TURN>, THREADS, smem));
+        if (cfg.ctas_per_sm < 1) cfg.ctas_per_sm = 1;
+        cfg.smem = smem;
     }
+    const int ctas_per_sm = cfg.ctas_per_sm;
     const int grid = tiles < ctas_per_sm * g_sms ? tiles : ctas_per_sm * g_sms;
     P.chunk = tiles / (ctas_per_sm * g_sms);                            // keep every CTA busy before lengthening chunks
     if (P.chunk < 1) P.chunk = 1;
     const int max_chunk = sizeof(T) == 2 ? 2 * OBS_CHUNK : OBS_CHUNK;   // f16 tiles are rebuilt for 8 observers at once: longer chunks pay (measured)
     if (P.chunk > max_chunk) P.chunk = max_chunk;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (g_profile) { profile_pair(&e0, &e1); CUDA_CHECK(cudaEventRecord(e0, 0)); }
-    obs_render_kernel<T, NIT, TURN><<<grid, THREADS, smem>>>(P);
+    if (c->profile) { profile_pair(c, &e0, &e1); CUDA_CHECK(cudaEventRecord(e0, c->stream)); }
+    obs_render_kernel<T, NIT, TURN><<<grid, THREADS, smem, c->stream>>>(P);
     post_launch("obs_render_kernel");
-    if (g_profile) CUDA_CHECK(cudaEventRecord(e1, 0));
+    if (c->profile) CUDA_CHECK(cudaEventRecord(e1, c->stream));
 }
 
-void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total) {
+static void fill_obs_params(Ctx *c, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total, ObsParams &P) {
     const int g = O.group;
     const GroupDev &G = hE.grp[g];
-    ObsParams P;
     memset(&P, 0, sizeof P);
     P.A = hE.A; P.W = hE.W; P.H = hE.H; P.G = hE.G; P.C = hE.n_channel;
     P.vw = G.view_w; P.vh = G.view_h; P.cells = G.view_w * G.view_h; P.rec = P.cells * P.C; P.F = G.feature_size;
@@ -1096,7 +1184,7 @@ void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const 
     const AgentSoA &s = G.soa[(O.curmask >> g) & 1u];
     P.x = s.x; P.y = s.y; P.id = s.id; P.act = s.act; P.last_reward = s.last_reward; P.dir = s.dir;
     P.turn = hE.turn_mode; P.body_w = G.body_w; P.body_l = G.body_l;
-    P.mm = mm_val ? g_mm_pad : nullptr; P.mm_stride = mm_val ? g_mm_stride : 0;
+    P.mm = mm_val ? c->mm_pad : nullptr; P.mm_stride = mm_val ? c->mm_stride : 0;
     P.view = O.view; P.feature = O.feature;
     const int stride = 2 + (hE.minimap_mode ? 1 : 0);
     for (int j = 0; j < hE.G; ++j) {
@@ -1105,13 +1193,324 @@ void launch_obs(const EngineDev *, const EngineDev &hE, const ObsArgs &O, const 
         P.mm_ch[j] = ch + 2;
         P.grp_ch[j] = ch;
     }
-    const bool small_view = G.view_count <= 4 * 32;             // in-range view cells held in registers: 4 or 8 per lane
+}
+
+static void launch_obs_dispatch(Ctx *c, const EngineDev &hE, const ObsArgs &O, ObsParams &P, int n_total, bool with_headers, bool headers_only) {
+    const bool small_view = hE.grp[O.group].view_count <= 4 * 32;   // in-range view cells held in registers: 4 or 8 per lane
     if (hE.turn_mode) {                                         // headings: per-heading LUTs in shared memory (NIT = 8 code path)
-        if (O.half) launch_obs_typed<__half, 8, true>(hE, P, n_total); else launch_obs_typed<float, 8, true>(hE, P, n_total);
+        if (O.half) launch_obs_typed<__half, 8, true>(c, 0, hE, P, n_total, with_headers, headers_only);
+        else launch_obs_typed<float, 8, true>(c, 1, hE, P, n_total, with_headers, headers_only);
     } else if (O.half) {
-        if (small_view) launch_obs_typed<__half, 4, false>(hE, P, n_total); else launch_obs_typed<__half, 8, false>(hE, P, n_total);
+        if (small_view) launch_obs_typed<__half, 4, false>(c, 2, hE, P, n_total, with_headers, headers_only);
+        else launch_obs_typed<__half, 8, false>(c, 3, hE, P, n_total, with_headers, headers_only);
     } else {
-        if (small_view) launch_obs_typed<float, 4, false>(hE, P, n_total); else launch_obs_typed<float, 8, false>(hE, P, n_total);
+        if (small_view) launch_obs_typed<float, 4, false>(c, 4, hE, P, n_total, with_headers, headers_only);
+        else launch_obs_typed<float, 8, false>(c, 5, hE, P, n_total, with_headers, headers_only);
+    }
+}
+
+void launch_obs(Ctx *c, const EngineDev *, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total) {
+    DeviceGuard guard(c);
+    ObsParams P;
+    fill_obs_params(c, hE, O, mm_val, n_total, P);
+    launch_obs_dispatch(c, hE, O, P, n_total, true, false);
+}
+
+// ------------------------------------------------------------------------------------------------
+// env_step's done word
+__global__ void __launch_bounds__(256) done_reduce_kernel(const EngineDev *gE, int *out) {
+    __shared__ int all_s;
+    if (threadIdx.x == 0) all_s = 1;
+    __syncthreads();
+    int all = 1;
+    for (int a = threadIdx.x; a < gE->A; a += blockDim.x) all &= gE->done[a] & 1;
+    if (!all) all_s = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) *out = all_s;
+}
+
+void read_done(Ctx *c, const EngineDev &hE, int *done_words) {
+    DeviceGuard guard(c);
+    if ((size_t)hE.A > c->pin_done_n) {
+        if (c->pin_done) cudaFreeHost(c->pin_done);
+        c->pin_done_n = (size_t)hE.A + 64;
+        CUDA_CHECK(cudaHostAlloc((void **)&c->pin_done, c->pin_done_n * sizeof(int), cudaHostAllocDefault));
+    }
+    CUDA_CHECK(cudaMemcpyAsync(c->pin_done, hE.done, (size_t)hE.A * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    memcpy(done_words, c->pin_done, (size_t)hE.A * sizeof(int));
+}
+
+void counts_fetch_begin(Ctx *c, const int *dev_off, size_t n_ints) {
+    DeviceGuard guard(c);
+    if (n_ints > c->pin_counts_n) {
+        if (c->pin_counts) { CUDA_CHECK(cudaStreamSynchronize(c->stream)); cudaFreeHost(c->pin_counts); }
+        c->pin_counts_n = n_ints + 64;
+        CUDA_CHECK(cudaHostAlloc((void **)&c->pin_counts, c->pin_counts_n * sizeof(int), cudaHostAllocDefault));
+    }
+    CUDA_CHECK(cudaMemcpyAsync(c->pin_counts, dev_off, n_ints * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaEventRecord(c->ev_counts, c->stream));
+}
+const int *counts_fetch_wait(Ctx *c) {
+    DeviceGuard guard(c);
+    CUDA_CHECK(cudaEventSynchronize(c->ev_counts));
+    return c->pin_counts;
+}
+
+void launch_done_to_device(Ctx *c, const EngineDev *dE, const EngineDev &, int *dev_done) {
+    DeviceGuard guard(c);
+    done_reduce_kernel<<<1, 256, 0, c->stream>>>(dE, dev_done);
+    post_launch("done_reduce_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-buffer observations: the wire format (backend.h WireHdr / WireMark).
+//
+// The reference ABI wants one dense float32 record per observer in HOST memory (4732 B for battle, 97 % zeros).
+// PCIe moves ~55 GB/s; the host's memory system takes several times that.  So the GPU does the gather -- which cells of
+// the view window show something, and what (Map::extract_view, Map.cc:129-207) -- and ships the answer as a compact
+// record of ~60 B per observer; host threads then write the dense bytes (host_expand.cc).
+//
+// obs_wire_kernel: one warp per observer, ABI order.  Lanes stride over the in-range view cells (same LUT as the render
+// kernel), load the kind byte and, for occupied cells, hp / max_hp; a ballot compacts the non-empty cells into the
+// observer's slot row (worst-case sized, written sparsely).  Lane 0 writes the header and adds the count to the
+// observer's chunk total.  wire_scan_kernel turns chunk totals into chunk bases; wire_compact_kernel copies the slot
+// rows of a chunk into the contiguous mark stream the host reads.
+__global__ void __launch_bounds__(256) obs_wire_kernel(const __grid_constant__ ObsParams P, WireHdr *whdr, WireMark *slots,
+                                                       int slot_stride, int *chunk_total) {
+    extern __shared__ __align__(16) unsigned char wire_smem[];
+    int2 *lut = (int2 *)wire_smem;
+    __shared__ int n_in_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lut_stride = (P.cells + 1) & ~1;
+    if (warp == 0) {                                          // compact the view mask (Range.h:104-189), as obs_render_kernel does
+        int k = 0;
+        for (int base = 0; base < P.cells; base += 32) {
+            const int cell = base + lane;
+            const bool in = cell < P.cells && P.mask[cell];
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const int vy = cell / P.vw, vx = cell - vy * P.vw;
+                const int q = k + __popc(bal & ((1u << lane) - 1u));
+                if (!P.turn) lut[q] = make_int2(cell * P.C, (P.oy + vy) * P.kw + P.ox + vx);
+                else {
+                    for (int d = 0; d < 4; ++d) {                       // one LUT per heading (Map.cc:140-146, 515-560)
+                        int rx = 0, ry = 0, dx, dy;
+                        if (d == DIR_SOUTH) { rx = P.body_w - 1; ry = P.body_l - 1; }
+                        else if (d == DIR_WEST) ry = P.body_w - 1;
+                        else if (d == DIR_EAST) rx = P.body_l - 1;
+                        const int ex = P.ox + vx, ey = P.oy + vy;
+                        if (d == DIR_NORTH) { dx = ex; dy = ey; }
+                        else if (d == DIR_SOUTH) { dx = -ex; dy = -ey; }
+                        else if (d == DIR_WEST) { dx = ey; dy = -ex; }
+                        else { dx = -ey; dy = ex; }
+                        lut[d * lut_stride + q] = make_int2(cell * P.C, (ry + dy) * P.kw + rx + dx);
+                    }
+                }
+            }
+            k += __popc(bal);
+        }
+        if (lane == 0) n_in_s = k;
+    }
+    __syncthreads();
+    const int n_in = n_in_s;
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    for (int o = blockIdx.x * (blockDim.x >> 5) + warp; o < P.n_total; o += warps) {
+        const int4 h = P.hdr[o];                              // {x, y, arena, self cell | heading << 16}
+        const long pb = h.z * P.kplane + (long)(h.y + P.kpad) * P.kw + h.x + P.kpad;
+        const unsigned char *kp = P.kind_plane + pb;
+        const float *hpnp = P.hpn_plane + pb;
+        const int2 *l = lut + (P.turn ? ((h.w >> 16) & 3) * lut_stride : 0);
+        WireMark *row = slots + (size_t)o * slot_stride;
+        int running = 0;
+        for (int base = 0; base < n_in; base += 32) {
+            const int k = base + lane;
+            int t = 0;
+            int2 lk = make_int2(0, 0);
+            if (k < n_in) { lk = l[k]; t = __ldg(kp + lk.y); }
+            const unsigned bal = __ballot_sync(0xffffffffu, t != 0);
+            if (t != 0) {
+                WireMark m;
+                if (t == KIND_WALL) { m.off = (unsigned)lk.x; m.val = 0.0f; }
+                else if (t == KIND_FOOD) { m.off = (unsigned)lk.x + 1u; m.val = 0.0f; }
+                else { m.off = (unsigned)(lk.x + P.grp_ch[t - KIND_GROUP0]) | WIRE_HAS_HP; m.val = __ldg(hpnp + lk.y); }
+                row[running + __popc(bal & ((1u << lane) - 1u))] = m;
+            }
+            running += __popc(bal);
+        }
+        if (lane == 0) {
+            WireHdr w;
+            w.arena = h.z;
+            w.self_cell = (unsigned short)(h.w & 0xffff);
+            w.count = (unsigned short)running;
+            whdr[o] = w;
+            if (running) atomicAdd(&chunk_total[o / WIRE_CHUNK], running);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) wire_scan_kernel(const int *chunk_total, long long *base, int n_chunks) {
+    __shared__ long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int tile = 0; tile < n_chunks; tile += blockDim.x) {
+        const int cidx = tile + threadIdx.x;
+        const int v = cidx < n_chunks ? chunk_total[cidx] : 0;
+        int tot;
+        const int ex = block_excl_scan(v, tot);
+        const long long carry = carry_s;
+        if (cidx < n_chunks) base[cidx] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) base[n_chunks] = carry_s;
+}
+
+__global__ void __launch_bounds__(256) wire_compact_kernel(const WireHdr *whdr, const WireMark *slots, int slot_stride,
+                                                           const long long *base, WireMark *stream, int n_total, int n_chunks) {
+    __shared__ int off_s[WIRE_CHUNK];
+    __shared__ unsigned short cnt_s[WIRE_CHUNK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        const int o0 = ch * WIRE_CHUNK, cnt_obs = min(WIRE_CHUNK, n_total - o0);
+        int running = 0;
+        for (int tile = 0; tile < WIRE_CHUNK; tile += blockDim.x) {
+            const int i = tile + threadIdx.x;
+            const int v = i < cnt_obs ? (int)whdr[o0 + i].count : 0;
+            int tot;
+            const int ex = block_excl_scan(v, tot);
+            off_s[i] = running + ex;
+            cnt_s[i] = (unsigned short)v;
+            running += tot;
+        }
+        __syncthreads();
+        WireMark *dst = stream + base[ch];
+        for (int i = warp; i < cnt_obs; i += nw) {
+            const int n = cnt_s[i], off = off_s[i];
+            const WireMark *src = slots + (size_t)(o0 + i) * slot_stride;
+            for (int k = lane; k < n; k += 32) dst[off + k] = src[k];
+        }
+        __syncthreads();
+    }
+}
+
+template <class T>
+static void grow_dev(Ctx *c, T *&p, size_t &have, size_t need) {
+    if (need <= have) return;
+    if (p) { CUDA_CHECK(cudaStreamSynchronize(c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->copy)); cudaFree(p); }
+    have = need + need / 4 + 64;
+    CUDA_CHECK(cudaMalloc((void **)&p, have * sizeof(T)));
+}
+template <class T>
+static void grow_pinned(Ctx *c, T *&p, size_t &have, size_t need) {
+    if (need <= have) return;
+    if (p) { CUDA_CHECK(cudaStreamSynchronize(c->copy)); cudaFreeHost(p); }
+    have = need + need / 2 + 1024;
+    CUDA_CHECK(cudaHostAlloc((void **)&p, have * sizeof(T), cudaHostAllocDefault));
+}
+
+void obs_wire_begin(Ctx *c, const EngineDev *, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total,
+                    bool want_dense, WireDesc *out) {
+    DeviceGuard guard(c);
+    ObsParams P;
+    fill_obs_params(c, hE, O, mm_val, n_total, P);
+    launch_obs_dispatch(c, hE, O, P, n_total, true, true);               // headers + feature rows (into O.feature)
+    const int n_in = hE.grp[O.group].view_count;
+    const int n_chunks = (n_total + WIRE_CHUNK - 1) / WIRE_CHUNK;
+    grow_dev(c, c->wire_slots, c->wire_slots_n, (size_t)n_total * n_in);
+    grow_dev(c, c->wire_hdr, c->wire_hdr_n, (size_t)n_total);
+    {
+        size_t have = c->wire_base_n;
+        grow_dev(c, c->wire_base, c->wire_base_n, (size_t)n_chunks + 1);
+        if (c->wire_base_n != have) {
+            if (c->wire_chunk_total) cudaFree(c->wire_chunk_total);
+            CUDA_CHECK(cudaMalloc((void **)&c->wire_chunk_total, c->wire_base_n * sizeof(int)));
+        }
+    }
+    CUDA_CHECK(cudaMemsetAsync(c->wire_chunk_total, 0, (size_t)n_chunks * sizeof(int), c->stream));
+    {
+        const size_t smem = (size_t)(P.turn ? 4 : 1) * ((P.cells + 1) & ~1) * sizeof(int2);
+        if (smem > 48 * 1024) mg::fatal("view too large for the wire kernel (%zu bytes of shared memory)", smem);
+        int grid = (n_total + 7) / 8;
+        if (grid > 8 * c->sms) grid = 8 * c->sms;
+        obs_wire_kernel<<<grid, 256, smem, c->stream>>>(P, c->wire_hdr, c->wire_slots, n_in, c->wire_chunk_total);
+        post_launch("obs_wire_kernel");
+        wire_scan_kernel<<<1, 1024, 0, c->stream>>>(c->wire_chunk_total, c->wire_base, n_chunks);
+        post_launch("wire_scan_kernel");
+    }
+    grow_pinned(c, c->h_wire_base, c->h_wire_base_n, (size_t)n_chunks + 1);
+    CUDA_CHECK(cudaMemcpyAsync(c->h_wire_base, c->wire_base, ((size_t)n_chunks + 1) * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaEventRecord(c->ev_done, c->stream));                  // totals on their way
+    if (mm_val) {
+        grow_pinned(c, c->h_mm, c->h_mm_n, (size_t)hE.A * c->mm_stride);
+        CUDA_CHECK(cudaMemcpyAsync(c->h_mm, c->mm_pad, (size_t)hE.A * c->mm_stride * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    grow_pinned(c, c->h_wire_hdr, c->h_wire_hdr_n, (size_t)n_total);
+    // the mark stream cannot be longer than every in-range cell of every observer; it is sized from the real total below
+    CUDA_CHECK(cudaEventSynchronize(c->ev_done));
+    const long long total_marks = c->h_wire_base[n_chunks];
+    grow_dev(c, c->wire_stream, c->wire_stream_n, (size_t)total_marks + 1);
+    grow_pinned(c, c->h_wire_marks, c->h_wire_marks_n, (size_t)total_marks + 1);
+    {
+        int grid = n_chunks < 8 * c->sms ? n_chunks : 8 * c->sms;
+        wire_compact_kernel<<<grid, 256, 0, c->stream>>>(c->wire_hdr, c->wire_slots, n_in, c->wire_base, c->wire_stream, n_total, n_chunks);
+        post_launch("wire_compact_kernel");
+    }
+    CUDA_CHECK(cudaEventRecord(c->ev_wire, c->stream));
+    if (want_dense) {
+        launch_obs_dispatch(c, hE, O, P, n_total, false, false);         // dense records into O.view (device staging)
+        CUDA_CHECK(cudaEventRecord(c->ev_dense, c->stream));
+    }
+    // queue the copies wave by wave on the copy stream
+    CUDA_CHECK(cudaStreamWaitEvent(c->copy, c->ev_wire, 0));
+    int cpw = (n_chunks + 7) / 8;
+    if (cpw < 4) cpw = 4;
+    const int n_waves = (n_chunks + cpw - 1) / cpw;
+    while ((int)c->wave_events.size() < n_waves) {
+        cudaEvent_t e; CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->wave_events.push_back(e);
+    }
+    for (int w = 0; w < n_waves; ++w) {
+        const int c0 = w * cpw, c1 = (c0 + cpw < n_chunks) ? c0 + cpw : n_chunks;
+        const size_t o0 = (size_t)c0 * WIRE_CHUNK, o1 = (size_t)c1 * WIRE_CHUNK < (size_t)n_total ? (size_t)c1 * WIRE_CHUNK : (size_t)n_total;
+        CUDA_CHECK(cudaMemcpyAsync(c->h_wire_hdr + o0, c->wire_hdr + o0, (o1 - o0) * sizeof(WireHdr), cudaMemcpyDeviceToHost, c->copy));
+        const long long m0 = c->h_wire_base[c0], m1 = c->h_wire_base[c1];
+        if (m1 > m0) CUDA_CHECK(cudaMemcpyAsync(c->h_wire_marks + m0, c->wire_stream + m0, (size_t)(m1 - m0) * sizeof(WireMark), cudaMemcpyDeviceToHost, c->copy));
+        CUDA_CHECK(cudaEventRecord(c->wave_events[w], c->copy));
+    }
+    c->waves_queued = n_waves;
+    out->hdr = c->h_wire_hdr; out->marks = c->h_wire_marks; out->chunk_base = c->h_wire_base;
+    out->mm = mm_val ? c->h_mm : nullptr; out->mm_stride = mm_val ? c->mm_stride : 0;
+    out->n_total = n_total; out->n_chunks = n_chunks; out->n_waves = n_waves; out->chunks_per_wave = cpw;
+}
+
+void obs_wire_wait(Ctx *c, int wave) {
+    DeviceGuard guard(c);
+    if (wave == 0) CUDA_CHECK(cudaStreamSynchronize(c->stream) == cudaSuccess ? cudaSuccess : cudaGetLastError());
+    CUDA_CHECK(cudaEventSynchronize(c->wave_events[wave]));
+}
+
+void dense_ready_wait(Ctx *c) { DeviceGuard guard(c); CUDA_CHECK(cudaStreamWaitEvent(c->copy, c->ev_dense, 0)); }
+
+void dma_d2h_async(Ctx *c, void *dst, const void *src, size_t bytes) {
+    DeviceGuard guard(c);
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->copy));
+    if (c->dma_events.size() < 64) {
+        while (c->dma_events.size() < 64) { cudaEvent_t e; CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->dma_events.push_back(e); }
+    }
+    if (c->dma_tail - c->dma_head >= c->dma_events.size()) {             // ring full: retire the oldest
+        CUDA_CHECK(cudaEventSynchronize(c->dma_events[c->dma_head % c->dma_events.size()]));
+        ++c->dma_head;
+    }
+    CUDA_CHECK(cudaEventRecord(c->dma_events[c->dma_tail % c->dma_events.size()], c->copy));
+    ++c->dma_tail;
+}
+
+void dma_wait(Ctx *c, int keep_in_flight) {
+    DeviceGuard guard(c);
+    while ((long long)(c->dma_tail - c->dma_head) > (long long)keep_in_flight) {
+        CUDA_CHECK(cudaEventSynchronize(c->dma_events[c->dma_head % c->dma_events.size()]));
+        ++c->dma_head;
     }
 }
 

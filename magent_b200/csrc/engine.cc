@@ -13,6 +13,7 @@
 #include <sstream>
 
 #include "backend.h"
+#include "host_expand.h"
 
 namespace mg {
 
@@ -109,7 +110,11 @@ Engine::Engine() {
     arenas_[0].rng = minstd_seed(0);                  // GridWorld.cc:29
 }
 
-Engine::~Engine() { free_device(); }
+Engine::~Engine() {
+    free_device();
+    if (h_feat_stage_) be::host_free(h_feat_stage_);
+    if (bx_) be::destroy(bx_);
+}
 
 void Engine::check_group(int g, const char *where) const {
     if (g < 0 || g >= G()) fatal("invalid group handle %d in %s", g, where);
@@ -157,6 +162,7 @@ void Engine::set_config(const char *key, void *p_value) {     // GridWorld.cc:12
         arenas_.assign(A_, HostArena());
         for (int a = 0; a < A_; ++a) arenas_[a].rng = a == 0 ? seed0 : minstd_seed(a);
     } else if (strequ(key, "device_id")) device_id_ = ivalue;
+    else if (strequ(key, "host_path")) host_path_ = ivalue ? 1 : 0;       // 1 wire records + host expansion (default), 0 dense DMA
     else fatal("invalid argument in GridWorld::set_config : %s", key);
 }
 
@@ -413,9 +419,10 @@ void Engine::refresh_host_counts() {
 
 void Engine::reset() {                                // GridWorld.cc:72-118, Map.cc:23-47
     if (W_ <= 2 || H_ <= 2) fatal("map size not configured");
+    settle_counts();
     if (where_ == DEVICE) {                           // keep the RNG streams: they persist across reset
         std::vector<ArenaHdr> hdr(A_);
-        be::d2h(hdr.data(), hE_.hdr, sizeof(ArenaHdr) * A_);
+        be::d2h(bx_, hdr.data(), hE_.hdr, sizeof(ArenaHdr) * A_);
         for (int a = 0; a < A_; ++a) {
             arenas_[a].rng = hdr[a].rng;
             for (int g = 0; g < (int)arenas_[a].groups.size(); ++g) arenas_[a].groups[g].grp_reward = hdr[a].grp_reward[g];
@@ -545,24 +552,28 @@ void Engine::add_agents(int group, int n, const char *method,
 // ---------------------------------------------------------------------------------------------
 // device image
 void Engine::ensure_backend() {
-    if (device_ready_) return;
+    if (bx_) {
+        // one context per engine for its whole life: the device cannot change under allocations that live on it
+        if (device_id_ >= 0 && device_id_ != be::device_of(bx_)) fatal("device_id changed after the engine had started on device %d", be::device_of(bx_));
+        return;
+    }
     std::string err;
-    if (!be::init(device_id_, &err)) fatal("no usable CUDA device for the B200 engine: %s (there is no CPU fallback)", err.c_str());
-    device_ready_ = true;
+    bx_ = be::create(device_id_, &err);
+    if (!bx_) fatal("no usable CUDA device for the B200 engine: %s (there is no CPU fallback)", err.c_str());
 }
 
 void *Engine::dalloc(size_t bytes) {
-    void *p = be::dmalloc(bytes ? bytes : 16);
+    void *p = be::dmalloc(bx_, bytes ? bytes : 16);
     dev_allocs_.push_back(p);
     return p;
 }
 
 void Engine::free_device() {
-    for (void *p : dev_allocs_) be::dfree(p);
+    for (void *p : dev_allocs_) be::dfree(bx_, p);
     dev_allocs_.clear();
-    if (d_view_stage_) be::dfree(d_view_stage_);
-    if (d_feat_stage_) be::dfree(d_feat_stage_);
-    if (d_io_stage_) be::dfree(d_io_stage_);
+    if (d_view_stage_) be::dfree(bx_, d_view_stage_);
+    if (d_feat_stage_) be::dfree(bx_, d_feat_stage_);
+    if (d_io_stage_) be::dfree(bx_, d_io_stage_);
     d_view_stage_ = d_feat_stage_ = nullptr; d_io_stage_ = nullptr;
     view_stage_bytes_ = feat_stage_bytes_ = io_stage_bytes_ = 0;
     dE_ = nullptr;
@@ -571,9 +582,9 @@ void Engine::free_device() {
 
 void *Engine::io_stage(size_t bytes) {
     if (bytes > io_stage_bytes_) {
-        if (d_io_stage_) be::dfree(d_io_stage_);
+        if (d_io_stage_) be::dfree(bx_, d_io_stage_);
         io_stage_bytes_ = bytes + bytes / 4 + 256;
-        d_io_stage_ = be::dmalloc(io_stage_bytes_);
+        d_io_stage_ = be::dmalloc(bx_, io_stage_bytes_);
     }
     return d_io_stage_;
 }
@@ -589,10 +600,10 @@ int Engine::max_agents_per_arena() const {
 }
 
 template <class T>
-static T *upload_vec(Engine *, std::vector<void *> &allocs, const std::vector<T> &v) {
-    T *p = (T *)be::dmalloc(std::max<size_t>(v.size(), 1) * sizeof(T));
+static T *upload_vec(be::Ctx *bx_, std::vector<void *> &allocs, const std::vector<T> &v) {
+    T *p = (T *)be::dmalloc(bx_, std::max<size_t>(v.size(), 1) * sizeof(T));
     allocs.push_back(p);
-    if (!v.empty()) be::h2d(p, v.data(), v.size() * sizeof(T));
+    if (!v.empty()) be::h2d(bx_, p, v.data(), v.size() * sizeof(T));
     return p;
 }
 
@@ -633,9 +644,9 @@ void Engine::to_device() {
             D.n_move = t.move.count; D.attack_base = t.attack_base; D.n_action = t.n_action; D.n_attack = t.attack.count;
             D.channel = group2channel(g);
             D.feature_size = feature_size(g);
-            D.move_dx = upload_vec(this, dev_allocs_, t.move.dx); D.move_dy = upload_vec(this, dev_allocs_, t.move.dy);
-            D.att_dx = upload_vec(this, dev_allocs_, t.attack.dx); D.att_dy = upload_vec(this, dev_allocs_, t.attack.dy);
-            D.view_mask = upload_vec(this, dev_allocs_, t.view.mask);
+            D.move_dx = upload_vec(bx_, dev_allocs_, t.move.dx); D.move_dy = upload_vec(bx_, dev_allocs_, t.move.dy);
+            D.att_dx = upload_vec(bx_, dev_allocs_, t.attack.dx); D.att_dy = upload_vec(bx_, dev_allocs_, t.attack.dy);
+            D.view_mask = upload_vec(bx_, dev_allocs_, t.view.mask);
             D.cap = cap_[g];
             D.foff = foff; foff += cap_[g];
             max_body = std::max(max_body, t.width * t.length);
@@ -670,7 +681,7 @@ void Engine::to_device() {
             hE_.kpad = pad; hE_.kw = W_ + 2 * pad; hE_.kplane = (long)hE_.kw * (H_ + 2 * pad);
             hE_.kind = (unsigned char *)dalloc((size_t)A_ * hE_.kplane + 16);
             hE_.hpn = (float *)dalloc(((size_t)A_ * hE_.kplane + 4) * 4);
-            be::dmemset(hE_.hpn, 0, ((size_t)A_ * hE_.kplane + 4) * 4);
+            be::dmemset(bx_, hE_.hpn, 0, ((size_t)A_ * hE_.kplane + 4) * 4);
         }
         hE_.att_rank = (int *)dalloc(sc * 4); hE_.tgt = (int *)dalloc(sc * 4);
         hE_.in_head = (int *)dalloc(sc * 4); hE_.in_next = (int *)dalloc(sc * 4);
@@ -681,7 +692,7 @@ void Engine::to_device() {
         hE_.sh_first = (int *)dalloc(sc * 4); hE_.att_agent = (int *)dalloc(sc * 4);
         hE_.cl_next = (int *)dalloc(sc * max_body * 4);
         hE_.counters = (long long *)dalloc(sizeof(long long) * MG_N_COUNTERS);
-        be::dmemset(hE_.counters, 0, sizeof(long long) * MG_N_COUNTERS);
+        be::dmemset(bx_, hE_.counters, 0, sizeof(long long) * MG_N_COUNTERS);
         hE_.team_scratch = (int *)dalloc(sizeof(int) * 2 * 4096);
         hE_.mm_count = (int *)dalloc((size_t)A_ * Gn * max_cells * 4);
         hE_.mm_total = (int *)dalloc((size_t)A_ * Gn * 4);
@@ -699,7 +710,7 @@ void Engine::to_device() {
         for (int b = 0; b < 32; ++b) { hE_.pow2[b] = p; p = mulmod31(p, p); }
     }
     hE_.n_rules = (int)compiled_rules_.size();
-    if (hE_.n_rules) be::h2d((void *)hE_.rules, compiled_rules_.data(), sizeof(RuleDev) * compiled_rules_.size());
+    if (hE_.n_rules) be::h2d(bx_, (void *)hE_.rules, compiled_rules_.data(), sizeof(RuleDev) * compiled_rules_.size());
     hE_.n_allq = n_allq_;
     for (int r = 0; r < hE_.n_rules; ++r) {
         const RuleDev &R = compiled_rules_[r];
@@ -734,17 +745,17 @@ void Engine::to_device() {
         auto up_i = [&](int *dst, std::vector<int> HostGroup::*m) {
             ibuf.assign(n, 0);
             for (int a = 0; a < A_; ++a) { const auto &v = arenas_[a].groups[g].*m; std::copy(v.begin(), v.end(), ibuf.begin() + a * cap); }
-            be::h2d(dst, ibuf.data(), n * 4);
+            be::h2d(bx_, dst, ibuf.data(), n * 4);
         };
         auto up_f = [&](float *dst, std::vector<float> HostGroup::*m) {
             fbuf.assign(n, 0);
             for (int a = 0; a < A_; ++a) { const auto &v = arenas_[a].groups[g].*m; std::copy(v.begin(), v.end(), fbuf.begin() + a * cap); }
-            be::h2d(dst, fbuf.data(), n * 4);
+            be::h2d(bx_, dst, fbuf.data(), n * 4);
         };
         auto up_b = [&](unsigned char *dst, std::vector<unsigned char> HostGroup::*m) {
             bbuf.assign(n, 0);
             for (int a = 0; a < A_; ++a) { const auto &v = arenas_[a].groups[g].*m; std::copy(v.begin(), v.end(), bbuf.begin() + a * cap); }
-            be::h2d(dst, bbuf.data(), n);
+            be::h2d(bx_, dst, bbuf.data(), n);
         };
         up_i(s.x, &HostGroup::x); up_i(s.y, &HostGroup::y); up_i(s.act, &HostGroup::act);
         up_i(s.id, &HostGroup::id); up_i(s.op_obj, &HostGroup::op_obj);
@@ -752,11 +763,11 @@ void Engine::to_device() {
         up_b(s.last_op, &HostGroup::last_op); up_b(s.flags, &HostGroup::flags); up_b(s.dir, &HostGroup::dir);
     }
     for (int a = 0; a < A_; ++a)
-        be::h2d(hE_.occ + (size_t)a * W_ * H_, arenas_[a].occ.data(), (size_t)W_ * H_ * 4);
+        be::h2d(bx_, hE_.occ + (size_t)a * W_ * H_, arenas_[a].occ.data(), (size_t)W_ * H_ * 4);
     if (food_mode_)
         for (int a = 0; a < A_; ++a) {
             arenas_[a].food.resize((size_t)W_ * H_, 0.0f);
-            be::h2d(hE_.food + (size_t)a * W_ * H_, arenas_[a].food.data(), (size_t)W_ * H_ * 4);
+            be::h2d(bx_, hE_.food + (size_t)a * W_ * H_, arenas_[a].food.data(), (size_t)W_ * H_ * 4);
         }
     {   // the kind plane mirrors the occupancy image; from here on the step kernels keep it current
         std::vector<unsigned char> kp((size_t)hE_.kplane);
@@ -769,10 +780,10 @@ void Engine::to_device() {
                     kp[(size_t)(y + hE_.kpad) * hE_.kw + x + hE_.kpad] =
                         o == OCC_WALL ? KIND_WALL : o == OCC_FOOD ? KIND_FOOD : o >= 0 ? (unsigned char)(KIND_GROUP0 + code_group(o)) : KIND_EMPTY;
                 }
-            be::h2d(hE_.kind + (size_t)a * hE_.kplane, kp.data(), kp.size());
+            be::h2d(bx_, hE_.kind + (size_t)a * hE_.kplane, kp.data(), kp.size());
         }
     }
-    be::dmemset(hE_.claim_head, 0xff, (size_t)A_ * W_ * H_ * 4);
+    be::dmemset(bx_, hE_.claim_head, 0xff, (size_t)A_ * W_ * H_ * 4);
     {
         std::vector<ArenaHdr> hdr(A_);
         std::vector<int> n((size_t)Gn * A_), dc((size_t)Gn * A_), done(A_);
@@ -787,13 +798,13 @@ void Engine::to_device() {
                 dc[(size_t)g * A_ + a] = arenas_[a].groups[g].dead_ct;
             }
         }
-        be::h2d(hE_.hdr, hdr.data(), sizeof(ArenaHdr) * A_);
-        be::h2d(hE_.n, n.data(), n.size() * 4);
-        be::h2d(hE_.dead_ct, dc.data(), dc.size() * 4);
-        be::h2d(hE_.done, done.data(), done.size() * 4);
-        be::h2d(hE_.off, h_off_.data(), h_off_.size() * 4);
+        be::h2d(bx_, hE_.hdr, hdr.data(), sizeof(ArenaHdr) * A_);
+        be::h2d(bx_, hE_.n, n.data(), n.size() * 4);
+        be::h2d(bx_, hE_.dead_ct, dc.data(), dc.size() * 4);
+        be::h2d(bx_, hE_.done, done.data(), done.size() * 4);
+        be::h2d(bx_, hE_.off, h_off_.data(), h_off_.size() * 4);
     }
-    be::h2d(dE_, &hE_, sizeof(EngineDev));
+    be::h2d(bx_, dE_, &hE_, sizeof(EngineDev));
     ++state_version_;
     may_have_dead_ = true;                            // conservative: the first clear_dead after an upload re-reads the counts
     where_ = DEVICE;
@@ -801,26 +812,27 @@ void Engine::to_device() {
 
 void Engine::to_host(bool keep_device_authoritative) {
     if (where_ == HOST) return;
+    settle_counts();
     const int Gn = G();
     std::vector<int> ibuf; std::vector<float> fbuf; std::vector<unsigned char> bbuf;
     std::vector<int> dc((size_t)Gn * A_);
-    be::d2h(dc.data(), hE_.dead_ct, dc.size() * 4);
+    be::d2h(bx_, dc.data(), hE_.dead_ct, dc.size() * 4);
     std::vector<ArenaHdr> hdr(A_);
-    be::d2h(hdr.data(), hE_.hdr, sizeof(ArenaHdr) * A_);
+    be::d2h(bx_, hdr.data(), hE_.hdr, sizeof(ArenaHdr) * A_);
     for (int g = 0; g < Gn; ++g) {
         const size_t cap = cap_[g], n = (size_t)A_ * cap;
         const AgentSoA &s = hE_.grp[g].soa[(curmask_ >> g) & 1u];
         for (int a = 0; a < A_; ++a) arenas_[a].groups[g].resize(count(g, a));
         auto dn_i = [&](const int *src, std::vector<int> HostGroup::*m) {
-            ibuf.resize(n); be::d2h(ibuf.data(), src, n * 4);
+            ibuf.resize(n); be::d2h(bx_, ibuf.data(), src, n * 4);
             for (int a = 0; a < A_; ++a) { auto &v = arenas_[a].groups[g].*m; std::copy(ibuf.begin() + a * cap, ibuf.begin() + a * cap + v.size(), v.begin()); }
         };
         auto dn_f = [&](const float *src, std::vector<float> HostGroup::*m) {
-            fbuf.resize(n); be::d2h(fbuf.data(), src, n * 4);
+            fbuf.resize(n); be::d2h(bx_, fbuf.data(), src, n * 4);
             for (int a = 0; a < A_; ++a) { auto &v = arenas_[a].groups[g].*m; std::copy(fbuf.begin() + a * cap, fbuf.begin() + a * cap + v.size(), v.begin()); }
         };
         auto dn_b = [&](const unsigned char *src, std::vector<unsigned char> HostGroup::*m) {
-            bbuf.resize(n); be::d2h(bbuf.data(), src, n);
+            bbuf.resize(n); be::d2h(bx_, bbuf.data(), src, n);
             for (int a = 0; a < A_; ++a) { auto &v = arenas_[a].groups[g].*m; std::copy(bbuf.begin() + a * cap, bbuf.begin() + a * cap + v.size(), v.begin()); }
         };
         dn_i(s.x, &HostGroup::x); dn_i(s.y, &HostGroup::y); dn_i(s.act, &HostGroup::act);
@@ -835,10 +847,10 @@ void Engine::to_host(bool keep_device_authoritative) {
     }
     for (int a = 0; a < A_; ++a) {
         arenas_[a].occ.resize((size_t)W_ * H_);
-        be::d2h(arenas_[a].occ.data(), hE_.occ + (size_t)a * W_ * H_, (size_t)W_ * H_ * 4);
+        be::d2h(bx_, arenas_[a].occ.data(), hE_.occ + (size_t)a * W_ * H_, (size_t)W_ * H_ * 4);
         if (food_mode_) {
             arenas_[a].food.resize((size_t)W_ * H_);
-            be::d2h(arenas_[a].food.data(), hE_.food + (size_t)a * W_ * H_, (size_t)W_ * H_ * 4);
+            be::d2h(bx_, arenas_[a].food.data(), hE_.food + (size_t)a * W_ * H_, (size_t)W_ * H_ * 4);
         }
         arenas_[a].rng = hdr[a].rng;
         arenas_[a].done = hdr[a].done;
@@ -848,9 +860,17 @@ void Engine::to_host(bool keep_device_authoritative) {
 
 // ---------------------------------------------------------------------------------------------
 // the step loop
+void Engine::stage_reserve(void *&p, size_t &have, size_t need) {
+    if (need <= have) return;
+    if (p) be::dfree(bx_, p);
+    have = need + need / 8 + 256;
+    p = be::dmalloc(bx_, have);
+}
+
 void Engine::get_observation(int group, void **bufs, int half) {      // GridWorld.cc:292-401
     check_group(group, "GridWorld::get_observation");
     to_device();
+    if (!(be::is_device_ptr(bufs[0]) && be::is_device_ptr(bufs[1]))) settle_counts();    // host copies need exact sizes
     const int n = total(group);
     if (n == 0) return;
     const AgentTypeDef &t = *group_type_[group];
@@ -858,51 +878,89 @@ void Engine::get_observation(int group, void **bufs, int half) {      // GridWor
     const size_t vbytes = (size_t)n * t.view.height * t.view.width * n_channel() * esz;
     const size_t fbytes = (size_t)n * feature_size(group) * esz;
     const bool vdev = be::is_device_ptr(bufs[0]), fdev = be::is_device_ptr(bufs[1]);
-    ObsArgs O;
-    O.curmask = curmask_; O.group = group; O.half = half ? 1 : 0;
-    if (vdev) O.view = bufs[0];
-    else {
-        if (vbytes > view_stage_bytes_) {
-            if (d_view_stage_) be::dfree(d_view_stage_);
-            view_stage_bytes_ = vbytes + vbytes / 8 + 256;
-            d_view_stage_ = be::dmalloc(view_stage_bytes_);
-        }
-        O.view = d_view_stage_;
-    }
-    if (fdev) O.feature = bufs[1];
-    else {
-        if (fbytes > feat_stage_bytes_) {
-            if (d_feat_stage_) be::dfree(d_feat_stage_);
-            feat_stage_bytes_ = fbytes + fbytes / 8 + 256;
-            d_feat_stage_ = be::dmalloc(feat_stage_bytes_);
-        }
-        O.feature = d_feat_stage_;
-    }
     // the pre-pass products depend on the state, on the observer's view size (minimap grid) and on whether the
     // observer's type skips absorbed agents in the minimap (GridWorld.cc:343-347)
     if (prep_version_ != state_version_ || prep_vw_ != t.view.width || prep_vh_ != t.view.height ||
-        prep_skip_absorbed_ != t.can_absorb || !be::obs_prepare_valid(dE_)) {
-        be::launch_obs_prepare(dE_, hE_, curmask_, group, minimap_mode_ ? d_mm_val_ : nullptr);
+        prep_skip_absorbed_ != t.can_absorb) {
+        be::launch_obs_prepare(bx_, dE_, hE_, curmask_, group, minimap_mode_ ? d_mm_val_ : nullptr);
         prep_version_ = state_version_; prep_vw_ = t.view.width; prep_vh_ = t.view.height; prep_skip_absorbed_ = t.can_absorb;
     }
-    be::launch_obs(dE_, hE_, O, minimap_mode_ ? d_mm_val_ : nullptr, n);
-    if (!vdev) be::d2h(bufs[0], d_view_stage_, vbytes);
-    if (!fdev) be::d2h(bufs[1], d_feat_stage_, fbytes);
+    if (host_path_ < 0) {                 // MAGENT_B200_HOST_PATH=dense keeps the round-1 path (dense records over PCIe) for A/B runs
+        const char *e = getenv("MAGENT_B200_HOST_PATH");
+        host_path_ = (e && !strcmp(e, "dense")) ? 0 : 1;
+    }
+    if (!vdev && !fdev && !half && host_path_ == 1 && t.view.height * t.view.width < 0xffff &&
+        (long long)t.view.height * t.view.width * n_channel() < (1ll << 30)) {
+        get_observation_wire(group, bufs);
+        return;
+    }
+    ObsArgs O;
+    O.curmask = curmask_; O.group = group; O.half = half ? 1 : 0;
+    if (vdev) O.view = bufs[0];
+    else { stage_reserve(d_view_stage_, view_stage_bytes_, vbytes); O.view = d_view_stage_; }
+    if (fdev) O.feature = bufs[1];
+    else { stage_reserve(d_feat_stage_, feat_stage_bytes_, fbytes); O.feature = d_feat_stage_; }
+    be::launch_obs(bx_, dE_, hE_, O, minimap_mode_ ? d_mm_val_ : nullptr, n);
+    if (!vdev) { be::d2h(bx_, bufs[0], d_view_stage_, vbytes); io_[IO_D2H] += (long long)vbytes; }
+    if (!fdev) { be::d2h(bx_, bufs[1], d_feat_stage_, fbytes); io_[IO_D2H] += (long long)fbytes; }
+}
+
+// Host buffers (the reference ABI's normal case, python/magent/gridworld.py:221-248): the GPU gathers, PCIe carries the
+// compact wire records, host threads write the dense float32 bytes (host_expand.h).
+void Engine::get_observation_wire(int group, void **bufs) {
+    const int n = total(group);
+    const AgentTypeDef &t = *group_type_[group];
+    const size_t fbytes = (size_t)n * feature_size(group) * 4;
+    ObsArgs O;
+    O.curmask = curmask_; O.group = group; O.half = 0;
+    O.view = nullptr;                                                     // no dense records on the device in this path
+    stage_reserve(d_feat_stage_, feat_stage_bytes_, fbytes);
+    O.feature = d_feat_stage_;
+    be::WireDesc W;
+    be::obs_wire_begin(bx_, dE_, hE_, O, minimap_mode_ ? d_mm_val_ : nullptr, n, false, &W);
+    // feature rows: DMA straight into page-locked caller memory, else through page-locked staging + a threaded copy
+    const bool fpinned = be::is_pinned_host_ptr(bufs[1]);
+    if (!fpinned && fbytes > h_feat_stage_bytes_) {
+        if (h_feat_stage_) be::host_free(h_feat_stage_);
+        h_feat_stage_bytes_ = fbytes + fbytes / 8 + 256;
+        h_feat_stage_ = be::host_alloc(h_feat_stage_bytes_);
+        if (!h_feat_stage_) fatal("cannot allocate %zu bytes of page-locked staging", h_feat_stage_bytes_);
+    }
+    be::dma_d2h_async(bx_, fpinned ? bufs[1] : h_feat_stage_, d_feat_stage_, fbytes);
+    ExpandGeom g;
+    memset(&g, 0, sizeof g);
+    g.C = n_channel(); g.cells = t.view.height * t.view.width; g.rec = g.cells * g.C; g.G = G();
+    g.minimap = minimap_mode_ ? 1 : 0;
+    const int stride = 2 + (minimap_mode_ ? 1 : 0);
+    for (int j = 0; j < G(); ++j) {
+        int rel = j - group; if (rel < 0) rel += G();
+        g.mm_ch[j] = group2channel(0) + rel * stride + 2;                 // make_channel_trans, GridWorld.cc:897-913
+    }
+    be::Ctx *bx = bx_;
+    expand_views(g, W, (float *)bufs[0], [bx](int w) { be::obs_wire_wait(bx, w); });
+    be::dma_wait(bx_, 0);
+    if (!fpinned) parallel_copy(bufs[1], h_feat_stage_, fbytes);
+    // what crossed PCIe: headers, marks, chunk table, minimap rows, feature rows; what the host threads wrote: the views
+    io_[IO_D2H] += (long long)W.n_total * (long long)sizeof(be::WireHdr) + W.chunk_base[W.n_chunks] * (long long)sizeof(be::WireMark) +
+                   (long long)(W.n_chunks + 1) * 8 + (W.mm ? (long long)A_ * W.mm_stride * 4 : 0) + (long long)fbytes;
+    io_[IO_HOST_WRITTEN] += (long long)n * g.rec * 4 + (fpinned ? 0 : (long long)fbytes);
 }
 
 void Engine::set_action(int group, const int *actions) {              // GridWorld.cc:403-454
     check_group(group, "GridWorld::set_action");
     to_device();
+    if (!be::is_device_ptr(actions)) settle_counts();
     const int n = total(group);
     if (std::find(order_.begin(), order_.end(), group) == order_.end()) order_.push_back(group);
     if (n == 0) return;
     const void *src = actions;
     if (!be::is_device_ptr(actions)) {
         void *st = io_stage((size_t)n * 4);
-        be::h2d(st, actions, (size_t)n * 4);
+        be::h2d(bx_, st, actions, (size_t)n * 4);
+        io_[IO_H2D] += (long long)n * 4;
         src = st;
     }
-    be::launch_info(dE_, hE_, curmask_, INFO_ACTION_SCATTER, group, const_cast<void *>(src), n);
+    be::launch_info(bx_, dE_, hE_, curmask_, INFO_ACTION_SCATTER, group, const_cast<void *>(src), n);
 }
 
 void Engine::random_actions(int group, unsigned long long seed) {
@@ -911,7 +969,7 @@ void Engine::random_actions(int group, unsigned long long seed) {
     if (std::find(order_.begin(), order_.end(), group) == order_.end()) order_.push_back(group);
     const int n = total(group);
     if (n == 0) return;
-    be::launch_random_actions(dE_, hE_, curmask_, group, seed * 0x9E3779B97F4A7C15ull + (++rand_calls_), n);
+    be::launch_random_actions(bx_, dE_, hE_, curmask_, group, seed * 0x9E3779B97F4A7C15ull + (++rand_calls_), n);
 }
 
 void Engine::step(int *done) {                                        // GridWorld.cc:456-631
@@ -922,11 +980,22 @@ void Engine::step(int *done) {                                        // GridWor
     S.record_events = first_render_ ? 0 : 1;           // GridWorld.cc:484: only once rendering has started
     S.n_order = (int)order_.size();
     for (int k = 0; k < S.n_order; ++k) S.order[k] = order_[k];
-    be::launch_step(dE_, hE_, S, max_agents_per_arena());
+    be::launch_step(bx_, dE_, hE_, S, max_agents_per_arena());
     ++state_version_;
     order_.clear();
+    if (be::is_device_ptr(done)) {
+        // device-resident caller: the done word goes to its device int, nothing is read back and the host does not
+        // wait for the step.  The host then cannot know whether anybody died: the next clear_dead re-reads the counts.
+        be::launch_done_to_device(bx_, dE_, hE_, done);
+        may_have_dead_ = true;
+        done_stale_ = true;
+        if (!first_render_) collect_attack_events();
+        return;
+    }
     std::vector<int> d(A_);
-    be::d2h(d.data(), hE_.done, (size_t)A_ * 4);
+    be::read_done(bx_, hE_, d.data());
+    io_[IO_D2H] += (long long)A_ * 4;
+    done_stale_ = false;
     int all = 1;
     for (int a = 0; a < A_; ++a) { arenas_[a].done = d[a] & 1; all &= arenas_[a].done; may_have_dead_ |= (d[a] & 2) != 0; }
     *done = all;
@@ -936,23 +1005,37 @@ void Engine::step(int *done) {                                        // GridWor
 void Engine::get_reward(int group, float *buf) {                      // GridWorld.cc:694-704
     check_group(group, "GridWorld::get_reward");
     to_device();
+    if (!be::is_device_ptr(buf)) settle_counts();
     const int n = total(group);
     if (n == 0) return;
-    if (be::is_device_ptr(buf)) { be::launch_info(dE_, hE_, curmask_, INFO_REWARD, group, buf, n); return; }
+    if (be::is_device_ptr(buf)) { be::launch_info(bx_, dE_, hE_, curmask_, INFO_REWARD, group, buf, n); return; }
     void *st = io_stage((size_t)n * 4);
-    be::launch_info(dE_, hE_, curmask_, INFO_REWARD, group, st, n);
-    be::d2h(buf, st, (size_t)n * 4);
+    be::launch_info(bx_, dE_, hE_, curmask_, INFO_REWARD, group, st, n);
+    be::d2h(bx_, buf, st, (size_t)n * 4);
+    io_[IO_D2H] += (long long)n * 4;
 }
 
 void Engine::clear_dead() {                                           // GridWorld.cc:633-665
     to_device();
-    be::launch_cull(dE_, hE_, curmask_, max_agents_per_arena());
+    settle_counts();                                  // a fetch still pending from the previous cull is long finished
+    be::launch_cull(bx_, dE_, hE_, curmask_, max_agents_per_arena());
     ++state_version_;
     curmask_ ^= (1u << G()) - 1u;
     if (!may_have_dead_) return;                      // nobody died since the last cull: counts and offsets stand
     may_have_dead_ = false;
-    be::launch_offsets(dE_, hE_);
-    be::d2h(h_off_.data(), hE_.off, h_off_.size() * 4);
+    // the new counts come back asynchronously: the call does not wait for the cull.  Until somebody needs exact
+    // numbers (settle_counts), h_off_ holds the previous counts -- upper bounds, since a cull only removes agents --
+    // and the kernels clamp to the device-side totals (EngineDev::off).
+    be::launch_offsets(bx_, dE_, hE_);
+    be::counts_fetch_begin(bx_, hE_.off, h_off_.size());
+    counts_pending_ = true;
+}
+
+void Engine::settle_counts() {
+    if (!counts_pending_) return;
+    memcpy(h_off_.data(), be::counts_fetch_wait(bx_), h_off_.size() * sizeof(int));
+    io_[IO_D2H] += (long long)h_off_.size() * 4;
+    counts_pending_ = false;
 }
 
 void Engine::set_goal(int group, const char *method, const int *) {                  // GridWorld.cc:667-679 (deprecated)
@@ -974,6 +1057,7 @@ void Engine::set_goal(int group, const char *method, const int *) {             
 // replay dump for the reference viewer (RenderGenerator.cc:63-185).  Cold path: works on a host snapshot of the
 // selected arena (arena 0 by default); byte-identical files for identical runs.
 void Engine::collect_attack_events() {                // the list GridWorld::step hands to the RenderGenerator (:471-509)
+    settle_counts();
     const int a = sel_arena_ >= 0 ? sel_arena_ : 0;
     struct Ev { int rank, id, x, y; };
     std::vector<Ev> evs;
@@ -984,11 +1068,11 @@ void Engine::collect_attack_events() {                // the list GridWorld::ste
         const AgentSoA &s = hE_.grp[g].soa[(curmask_ >> g) & 1u];
         const size_t base = (size_t)a * cap_[g];
         std::vector<int> rank(n), x(n), y(n), act(n), id(n);
-        be::d2h(rank.data(), hE_.grp[g].ev_rank + base, (size_t)n * 4);
-        be::d2h(x.data(), s.x + base, (size_t)n * 4); be::d2h(y.data(), s.y + base, (size_t)n * 4);
-        be::d2h(act.data(), s.act + base, (size_t)n * 4); be::d2h(id.data(), s.id + base, (size_t)n * 4);
+        be::d2h(bx_, rank.data(), hE_.grp[g].ev_rank + base, (size_t)n * 4);
+        be::d2h(bx_, x.data(), s.x + base, (size_t)n * 4); be::d2h(bx_, y.data(), s.y + base, (size_t)n * 4);
+        be::d2h(bx_, act.data(), s.act + base, (size_t)n * 4); be::d2h(bx_, id.data(), s.id + base, (size_t)n * 4);
         std::vector<unsigned char> dir(n, (unsigned char)DIR_NORTH);
-        if (turn_mode_) be::d2h(dir.data(), s.dir + base, (size_t)n);
+        if (turn_mode_) be::d2h(bx_, dir.data(), s.dir + base, (size_t)n);
         for (int i = 0; i < n; ++i) {
             if (rank[i] < 0) continue;
             const int k = act[i] - t.attack_base;
@@ -1089,18 +1173,23 @@ void Engine::render() {                               // GridWorld.cc:939-949
     if (frame_ct_++ > frame_per_file_) { frame_ct_ = 0; file_ct_++; }
 }
 
-void Engine::sync() { if (device_ready_) be::sync(); }
+void Engine::sync() { if (bx_) be::sync(bx_); }
+void Engine::get_io_stats(long long *out, int cap) { for (int i = 0; i < cap && i < 3; ++i) out[i] = io_[i]; }
+void *Engine::stream() { ensure_backend(); return be::stream_handle(bx_); }
+void Engine::set_profiling(bool on) { ensure_backend(); be::profile_enable(bx_, on); }
+void Engine::get_profile(double *ms, long long *n) { *ms = 0; *n = 0; if (bx_) be::profile_read(bx_, ms, n); }
 
 int Engine::get_counters(long long *out, int cap) {
     int n = std::min<int>(cap, MG_N_COUNTERS);
     if (where_ != DEVICE && dE_ == nullptr) { for (int i = 0; i < n; ++i) out[i] = 0; return n; }
     std::vector<long long> c(MG_N_COUNTERS);
-    be::d2h(c.data(), hE_.counters, sizeof(long long) * MG_N_COUNTERS);
+    be::d2h(bx_, c.data(), hE_.counters, sizeof(long long) * MG_N_COUNTERS);
     for (int i = 0; i < n; ++i) out[i] = c[i];
     return n;
 }
 
 void Engine::get_info(int group, const char *name, void *void_buffer) {        // GridWorld.cc:709-894
+    settle_counts();
     int *ib = (int *)void_buffer;
     float *fb = (float *)void_buffer;
     if (strequ(name, "num")) {
@@ -1113,14 +1202,20 @@ void Engine::get_info(int group, const char *name, void *void_buffer) {        /
         if (n == 0) return;
         int kind = strequ(name, "id") ? INFO_ID : strequ(name, "pos") ? INFO_POS : strequ(name, "alive") ? INFO_ALIVE : INFO_HP;
         size_t bytes = kind == INFO_POS ? (size_t)n * 8 : kind == INFO_ALIVE ? (size_t)n : (size_t)n * 4;
-        if (be::is_device_ptr(void_buffer)) { be::launch_info(dE_, hE_, curmask_, kind, group, void_buffer, n); return; }
+        if (be::is_device_ptr(void_buffer)) { be::launch_info(bx_, dE_, hE_, curmask_, kind, group, void_buffer, n); return; }
         void *st = io_stage(bytes);
-        be::launch_info(dE_, hE_, curmask_, kind, group, st, n);
-        be::d2h(void_buffer, st, bytes);
+        be::launch_info(bx_, dE_, hE_, curmask_, kind, group, st, n);
+        be::d2h(bx_, void_buffer, st, bytes);
     } else if (strequ(name, "arena_num")) {
         check_group(group, "get_info(arena_num)");
         for (int a = 0; a < A_; ++a) ib[a] = count(group, a);
     } else if (strequ(name, "arena_done")) {
+        if (done_stale_ && where_ == DEVICE) {          // the last env_step wrote its result to a device int only
+            std::vector<int> d(A_);
+            be::read_done(bx_, hE_, d.data());
+            for (int a = 0; a < A_; ++a) arenas_[a].done = d[a] & 1;
+            done_stale_ = false;
+        }
         for (int a = 0; a < A_; ++a) ib[a] = arenas_[a].done;
     } else if (strequ(name, "action_space")) {
         check_group(group, "get_info"); ib[0] = group_type_[group]->n_action;

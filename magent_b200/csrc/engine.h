@@ -12,6 +12,7 @@
 #include "dev_types.h"
 
 namespace mg {
+namespace be { struct Ctx; }
 
 [[noreturn]] void fatal(const char *fmt, ...);
 
@@ -97,6 +98,10 @@ public:
     void random_actions(int group, unsigned long long seed);
     int get_counters(long long *out, int cap);
     void sync();
+    void get_io_stats(long long *out, int cap);      // bytes so far: device->host over PCIe, host->device, written by host threads
+    void *stream();                      // cudaStream_t of this engine's kernels (nullptr before the first device call)
+    void set_profiling(bool on);
+    void get_profile(double *ms, long long *n);
 
 private:
     // configuration
@@ -105,7 +110,7 @@ private:
     int embedding_size_ = 0;
     int A_ = 1;
     int device_id_ = -1;
-    bool device_ready_ = false;
+    be::Ctx *bx_ = nullptr;             // this engine's device context (device, streams, scratch): backend.h
     std::map<std::string, AgentTypeDef> types_;
     std::vector<const AgentTypeDef *> group_type_;
     std::vector<SymbolDef> symbols_;
@@ -144,7 +149,11 @@ private:
     float *d_mm_val_ = nullptr;
     size_t view_stage_bytes_ = 0, feat_stage_bytes_ = 0;
     void *d_io_stage_ = nullptr; size_t io_stage_bytes_ = 0;
-    int *pin_small_ = nullptr; size_t pin_small_ints_ = 0;
+    void *h_feat_stage_ = nullptr; size_t h_feat_stage_bytes_ = 0;      // page-locked staging of the feature rows (host path)
+    enum { IO_D2H = 0, IO_H2D = 1, IO_HOST_WRITTEN = 2 };
+    long long io_[3] = {0, 0, 0};       // step-loop traffic (hot calls only)
+    bool done_stale_ = false;           // arenas_[a].done not refreshed by the last step (device-pointer done)
+    int host_path_ = -1;                // env_get_observation into host memory: 1 wire records + host expansion, 0 dense DMA
     unsigned long long rand_calls_ = 0;
     // get_observation pre-pass products (hp_norm plane, minimap) stay valid until the state changes
     unsigned long long state_version_ = 1, prep_version_ = 0;
@@ -158,6 +167,8 @@ private:
     int total(int g) const { return h_off_[(size_t)g * (A_ + 1) + A_]; }
     int count(int g, int a) const { return h_off_[(size_t)g * (A_ + 1) + a + 1] - h_off_[(size_t)g * (A_ + 1) + a]; }
     void refresh_host_counts();
+    bool counts_pending_ = false;       // clear_dead queued a fetch of the new counts; h_off_ still holds the old (upper-bound) ones
+    void settle_counts();
     void check_group(int g, const char *where) const;
 
     void ensure_backend();
@@ -167,6 +178,8 @@ private:
     void free_device();
     void *dalloc(size_t bytes);
     void *io_stage(size_t bytes);
+    void stage_reserve(void *&p, size_t &have, size_t need);
+    void get_observation_wire(int group, void **bufs);
     int max_agents_per_arena() const;
 
     // host-side placement (reference Map.cc:49-115, GridWorld.cc:180-290)

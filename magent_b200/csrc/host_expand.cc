@@ -1,0 +1,294 @@
+// host_expand.cc -- see host_expand.h.  Plain C++: a small persistent thread pool and the wire -> dense expansion.
+#include "host_expand.h"
+
+#include <immintrin.h>
+#include <pthread.h>
+#include <sched.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace mg {
+
+// ---------------------------------------------------------------------------------------------
+// how many host threads
+static int usable_cores() {
+    int n = 1;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) n = CPU_COUNT(&set);
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {                 // cgroup v2: "<quota> <period>" or "max <period>"
+        char q[64]; long period = 0;
+        if (fscanf(f, "%63s %ld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) {
+            long quota = atol(q);
+            if (quota > 0) { int c = (int)(quota / period); if (c < 1) c = 1; if (c < n) n = c; }
+        }
+        fclose(f);
+    } else if (FILE *g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {     // cgroup v1
+        long quota = -1, period = 0;
+        if (fscanf(g, "%ld", &quota) != 1) quota = -1;
+        fclose(g);
+        if (FILE *h = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(h, "%ld", &period) != 1) period = 0; fclose(h); }
+        if (quota > 0 && period > 0) { int c = (int)(quota / period); if (c < 1) c = 1; if (c < n) n = c; }
+    }
+    return n < 1 ? 1 : n;
+}
+
+static std::atomic<int> g_threads_override{0};
+void set_host_threads(int n) { g_threads_override.store(n < 0 ? 0 : (n > 256 ? 256 : n)); }
+
+int host_threads() {
+    const int o = g_threads_override.load(std::memory_order_relaxed);
+    if (o > 0) return o;
+    static const int n = []() {
+        if (const char *e = getenv("MAGENT_B200_HOST_THREADS")) { int v = atoi(e); if (v >= 1) return v > 256 ? 256 : v; }
+        int c = usable_cores();
+        if (const char *w = getenv("LOCAL_WORLD_SIZE")) { int v = atoi(w); if (v > 1) c = c / v; }     // torchrun: ranks share the box
+        if (c > 16) c = 16;                // the memory system saturates well before that (profiles/README.md, round 2)
+        return c < 1 ? 1 : c;
+    }();
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// worker pool: threads are created on first use and live for the life of the process (never joined: the
+// pool object is intentionally leaked so that no destructor races with a worker at exit)
+namespace {
+struct Pool {
+    std::mutex job_mu;                   // one job at a time
+    std::mutex mu;
+    std::condition_variable cv;
+    const std::function<void(int)> *fn = nullptr;
+    int n = 0;                           // threads taking part in the current job (tid < n)
+    unsigned long gen = 0;
+    std::atomic<int> remaining{0};
+    std::vector<std::thread> workers;    // worker k has tid k + 1
+
+    void worker(int tid) {
+        unsigned long seen = 0;
+        for (;;) {
+            const std::function<void(int)> *f = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return gen != seen; });
+                seen = gen;
+                if (tid < n) f = fn;
+            }
+            if (f) {
+                (*f)(tid);
+                remaining.fetch_sub(1, std::memory_order_acq_rel);
+            }
+        }
+    }
+    void run(int want, const std::function<void(int)> &f) {
+        std::lock_guard<std::mutex> job(job_mu);
+        if (want < 1) want = 1;
+        while ((int)workers.size() < want - 1) {
+            const int tid = (int)workers.size() + 1;
+            workers.emplace_back([this, tid] { worker(tid); });
+            workers.back().detach();
+        }
+        if (want > 1) {
+            std::lock_guard<std::mutex> lk(mu);
+            fn = &f; n = want;
+            remaining.store(want - 1, std::memory_order_release);
+            ++gen;
+        }
+        if (want > 1) cv.notify_all();
+        f(0);
+        while (remaining.load(std::memory_order_acquire) > 0) {
+            for (int i = 0; i < 64; ++i) _mm_pause();
+            sched_yield();
+        }
+    }
+};
+std::atomic<Pool *> g_pool{nullptr};
+std::mutex g_pool_mu;
+void forget_pool_in_child() { g_pool.store(nullptr); }      // worker threads do not survive fork()
+Pool *pool() {
+    Pool *p = g_pool.load(std::memory_order_acquire);
+    if (p) return p;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    p = g_pool.load();
+    if (!p) {
+        static bool hooked = false;
+        if (!hooked) { pthread_atfork(nullptr, nullptr, forget_pool_in_child); hooked = true; }
+        p = new Pool();
+        g_pool.store(p, std::memory_order_release);
+    }
+    return p;
+}
+}  // namespace
+
+void host_parallel(int n_threads, const std::function<void(int)> &fn) { pool()->run(n_threads, fn); }
+
+// ---------------------------------------------------------------------------------------------
+// streaming copy: dst gets n bytes of src; full 64-byte lines of dst are written with non-temporal stores (no read for
+// ownership, no cache pollution), the partial lines at either end with ordinary stores
+namespace {
+__attribute__((target("avx512f"))) void stream_body_512(char *d, const char *s, size_t n) {       // d 64-aligned, n % 64 == 0
+    size_t i = 0;
+    for (; i + 256 <= n; i += 256) {
+        const __m512i a = _mm512_loadu_si512((const void *)(s + i)), b = _mm512_loadu_si512((const void *)(s + i + 64));
+        const __m512i c = _mm512_loadu_si512((const void *)(s + i + 128)), e = _mm512_loadu_si512((const void *)(s + i + 192));
+        _mm512_stream_si512((__m512i *)(d + i), a); _mm512_stream_si512((__m512i *)(d + i + 64), b);
+        _mm512_stream_si512((__m512i *)(d + i + 128), c); _mm512_stream_si512((__m512i *)(d + i + 192), e);
+    }
+    for (; i < n; i += 64) _mm512_stream_si512((__m512i *)(d + i), _mm512_loadu_si512((const void *)(s + i)));
+}
+__attribute__((target("avx2"))) void stream_body_256(char *d, const char *s, size_t n) {
+    for (size_t i = 0; i < n; i += 64) {
+        const __m256i a = _mm256_loadu_si256((const __m256i *)(s + i)), b = _mm256_loadu_si256((const __m256i *)(s + i + 32));
+        _mm256_stream_si256((__m256i *)(d + i), a); _mm256_stream_si256((__m256i *)(d + i + 32), b);
+    }
+}
+void stream_body_sse2(char *d, const char *s, size_t n) {
+    for (size_t i = 0; i < n; i += 16) _mm_stream_si128((__m128i *)(d + i), _mm_loadu_si128((const __m128i *)(s + i)));
+}
+typedef void (*StreamFn)(char *, const char *, size_t);
+StreamFn pick_stream() {
+    __builtin_cpu_init();
+    if (getenv("MAGENT_B200_HOST_ISA")) {
+        const char *e = getenv("MAGENT_B200_HOST_ISA");
+        if (!strcmp(e, "sse2")) return stream_body_sse2;
+        if (!strcmp(e, "avx2") && __builtin_cpu_supports("avx2")) return stream_body_256;
+    }
+    if (__builtin_cpu_supports("avx512f")) return stream_body_512;
+    if (__builtin_cpu_supports("avx2")) return stream_body_256;
+    return stream_body_sse2;
+}
+const StreamFn g_stream = pick_stream();
+
+inline void stream_out(char *d, const char *s, size_t n) {
+    size_t head = (size_t)(-(uintptr_t)d) & 63;
+    if (head > n) head = n;
+    if (head) memcpy(d, s, head);
+    const size_t body = (n - head) & ~(size_t)63;
+    if (body) g_stream(d + head, s + head, body);
+    const size_t tail = n - head - body;
+    if (tail) memcpy(d + head + body, s + head + body, tail);
+}
+}  // namespace
+
+void parallel_copy(void *dst, const void *src, size_t bytes) {
+    const size_t piece = (size_t)1 << 20;
+    const size_t n_pieces = (bytes + piece - 1) / piece;
+    int T = host_threads();
+    if ((size_t)T > n_pieces) T = (int)(n_pieces ? n_pieces : 1);
+    std::atomic<size_t> next{0};
+    host_parallel(T, [&](int) {
+        for (;;) {
+            const size_t p = next.fetch_add(1);
+            if (p >= n_pieces) break;
+            const size_t o = p * piece, n = bytes - o < piece ? bytes - o : piece;
+            stream_out((char *)dst + o, (const char *)src + o, n);
+        }
+        _mm_sfence();
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// wire -> dense.  Each thread keeps ONE record in a cache-resident scratch buffer: the zeros and the minimap channels of
+// the arena it is working in.  Per observer it undoes the previous observer's marks and self marker, applies the new
+// ones and streams the record to the caller's buffer; the record is rebuilt only when the arena changes.
+namespace {
+struct Scratch {
+    float *rec = nullptr;
+    int arena = -1;
+    const be::WireMark *prev = nullptr;
+    int prev_n = 0;
+    int prev_self = 0xffff;
+};
+
+inline void rebuild(const ExpandGeom &g, const be::WireDesc &W, Scratch &s, int arena) {
+    memset(s.rec, 0, (size_t)g.rec * sizeof(float));
+    if (g.minimap) {
+        const float *rows = W.mm + (size_t)arena * W.mm_stride;
+        for (int j = 0; j < g.G; ++j) {
+            float *d = s.rec + g.mm_ch[j];
+            const float *r = rows + (size_t)j * g.cells;
+            for (int c = 0; c < g.cells; ++c) d[(size_t)c * g.C] = r[c];           // GridWorld.cc:374-383
+        }
+    }
+    s.arena = arena; s.prev = nullptr; s.prev_n = 0; s.prev_self = 0xffff;
+}
+
+void expand_chunk(const ExpandGeom &g, const be::WireDesc &W, float *out, int chunk, Scratch &s) {
+    const size_t o0 = (size_t)chunk * be::WIRE_CHUNK;
+    const size_t o1 = o0 + be::WIRE_CHUNK < (size_t)W.n_total ? o0 + be::WIRE_CHUNK : (size_t)W.n_total;
+    const be::WireMark *m = W.marks + W.chunk_base[chunk];
+    const size_t rec_bytes = (size_t)g.rec * sizeof(float);
+    char *d = (char *)(out + o0 * (size_t)g.rec);
+    float *rec = s.rec;
+    for (size_t o = o0; o < o1; ++o, d += rec_bytes) {
+        const be::WireHdr h = W.hdr[o];
+        if (h.arena != s.arena) rebuild(g, W, s, h.arena);
+        else {
+            for (int k = 0; k < s.prev_n; ++k) {                                      // undo the previous observer
+                const unsigned off = s.prev[k].off;
+                rec[off & ~be::WIRE_HAS_HP] = 0.0f;
+                if (off & be::WIRE_HAS_HP) rec[(off & ~be::WIRE_HAS_HP) + 1] = 0.0f;
+            }
+            if (g.minimap && s.prev_self != 0xffff) {
+                const float *rows = W.mm + (size_t)s.arena * W.mm_stride;
+                for (int j = 0; j < g.G; ++j) rec[(size_t)s.prev_self * g.C + g.mm_ch[j]] = rows[(size_t)j * g.cells + s.prev_self];
+            }
+        }
+        if (g.minimap && h.self_cell != 0xffff) {                                     // self marker, GridWorld.cc:382
+            const float *rows = W.mm + (size_t)h.arena * W.mm_stride;
+            for (int j = 0; j < g.G; ++j) {
+                const float v = rows[(size_t)j * g.cells + h.self_cell];
+                if (v == v) rec[(size_t)h.self_cell * g.C + g.mm_ch[j]] = v + 1.0f;   // 0/0 of an empty group stays the NaN it is
+            }
+        }
+        for (int k = 0; k < (int)h.count; ++k) {                                      // Map::extract_view, Map.cc:183-199
+            const unsigned off = m[k].off;
+            rec[off & ~be::WIRE_HAS_HP] = 1.0f;
+            if (off & be::WIRE_HAS_HP) rec[(off & ~be::WIRE_HAS_HP) + 1] = m[k].val;
+        }
+        s.prev = m; s.prev_n = h.count; s.prev_self = h.self_cell;
+        m += h.count;
+        stream_out(d, (const char *)rec, rec_bytes);
+    }
+}
+}  // namespace
+
+void expand_views(const ExpandGeom &geom, const be::WireDesc &W, float *out, const std::function<void(int)> &wait_wave) {
+    int T = host_threads();
+    if (T > W.n_chunks) T = W.n_chunks > 0 ? W.n_chunks : 1;
+    std::atomic<int> next{0};
+    std::atomic<int> waves_ready{0};
+    auto work = [&](int tid) {
+        Scratch s;
+        void *mem = nullptr;
+        if (posix_memalign(&mem, 64, (size_t)geom.rec * sizeof(float) + 64) != 0) abort();
+        s.rec = (float *)mem;
+        if (tid == 0 && T == 1) {            // a single thread has to fetch the waves itself, in step with its work
+            for (int c = 0; c < W.n_chunks; ++c) {
+                const int w = c / W.chunks_per_wave;
+                while (waves_ready.load(std::memory_order_relaxed) <= w) { wait_wave(waves_ready.load()); waves_ready.fetch_add(1); }
+                expand_chunk(geom, W, out, c, s);
+            }
+        } else {
+            if (tid == 0)                     // the calling thread owns the CUDA side: it announces the waves as they land
+                for (int w = 0; w < W.n_waves; ++w) { wait_wave(w); waves_ready.store(w + 1, std::memory_order_release); }
+            for (;;) {
+                const int c = next.fetch_add(1);
+                if (c >= W.n_chunks) break;
+                const int w = c / W.chunks_per_wave;
+                while (waves_ready.load(std::memory_order_acquire) <= w) { for (int i = 0; i < 32; ++i) _mm_pause(); }
+                expand_chunk(geom, W, out, c, s);
+            }
+        }
+        _mm_sfence();
+        free(mem);
+    };
+    host_parallel(T, work);
+}
+
+}  // namespace mg

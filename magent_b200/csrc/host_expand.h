@@ -1,0 +1,39 @@
+// host_expand.h -- the host half of env_get_observation for HOST buffers.
+//
+// The reference writes its observations straight into the caller's host memory: one memset of the whole buffer, then a
+// handful of sparse writes per observer (src/gridworld/GridWorld.cc:310-311, 363-397).  The B200 engine does the gather on
+// the GPU; for a host buffer it ships the result as compact wire records (backend.h: WireHdr / WireMark, ~60 B per observer
+// instead of 4732 B) and the threads of this file write the dense float32 records the ABI promises: the arena's minimap
+// channels, the self marker, the marked cells, zeros everywhere else -- every byte of the caller's buffer, exactly the
+// bytes the reference leaves there.  Plain C++ (no CUDA): non-temporal stores out of a cache-resident record.
+#pragma once
+#include <stddef.h>
+#include <functional>
+#include "backend.h"
+
+namespace mg {
+
+struct ExpandGeom {
+    int rec;                             // floats per record = view_h * view_w * n_channel
+    int C, cells, G;
+    int minimap;
+    int mm_ch[MG_MAX_GROUPS];            // observation channel of group j's minimap (GridWorld.cc:897-913)
+};
+
+// number of threads the host side uses (callers included): MAGENT_B200_HOST_THREADS, else the usable cores (affinity
+// mask capped by the cgroup CPU quota) divided by LOCAL_WORLD_SIZE, at most 16
+int host_threads();
+void set_host_threads(int n);           // 0 = back to the default
+
+// Run fn(tid) for tid in [0, n_threads) on the process-wide worker pool; the calling thread is tid 0.  Returns when all
+// have returned.  Jobs of different engines are serialised.
+void host_parallel(int n_threads, const std::function<void(int)> &fn);
+
+// Write the dense records of W into out[n_total][rec].  wait_wave(w) must return once wave w of the wire staging is in
+// host memory; it is called from the calling thread only, for w = 0 .. n_waves-1 in order.
+void expand_views(const ExpandGeom &geom, const be::WireDesc &W, float *out, const std::function<void(int)> &wait_wave);
+
+// dst[0, bytes) = src[0, bytes) with all pool threads (non-temporal stores)
+void parallel_copy(void *dst, const void *src, size_t bytes);
+
+}  // namespace mg

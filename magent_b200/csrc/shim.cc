@@ -7,6 +7,7 @@
 #include "../../include/magent_b200_ext.h"
 #include "backend.h"
 #include "engine.h"
+#include "host_expand.h"
 
 namespace mg { const char *last_error(); void set_last_error(const std::string &s); }
 
@@ -90,5 +91,9 @@ MG_API int magent_b200_get_observation_f16(EnvHandle game, GroupHandle group, vo
 }
 MG_API int magent_b200_get_counters(EnvHandle game, long long *out, int capacity) { return E(game)->get_counters(out, capacity); }
 MG_API long long magent_b200_launch_count(void) { return mg::be::launch_count(); }
-MG_API int magent_b200_set_profiling(int on) { mg::be::profile_enable(on != 0); return 0; }
-MG_API int magent_b200_get_profile(double *ms, long long *n) { mg::be::profile_read(ms, n); return 0; }
+MG_API int magent_b200_set_profiling(EnvHandle game, int on) { E(game)->set_profiling(on != 0); return 0; }
+MG_API int magent_b200_get_profile(EnvHandle game, double *ms, long long *n) { E(game)->get_profile(ms, n); return 0; }
+MG_API int magent_b200_get_io_stats(EnvHandle game, long long *out, int capacity) { E(game)->get_io_stats(out, capacity); return capacity < 3 ? capacity : 3; }
+MG_API void *magent_b200_stream(EnvHandle game) { return E(game)->stream(); }
+MG_API int magent_b200_host_threads(void) { return mg::host_threads(); }
+MG_API int magent_b200_set_host_threads(int n) { mg::set_host_threads(n); return 0; }

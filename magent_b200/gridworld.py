@@ -91,6 +91,7 @@ class GridWorld(Environment):
         self._lib = load_library(kwargs.pop("_lib", None))
         self.num_arenas = int(kwargs.pop("_num_arenas", 1))
         device = kwargs.pop("_device", None)
+        host_path = kwargs.pop("_host_path", None)      # None: engine default (wire); "dense": dense records over PCIe
         self.game = None
 
         if isinstance(config, str):
@@ -119,6 +120,10 @@ class GridWorld(Environment):
             if device is not None:
                 L.env_config_game(game, b"device_id", _cint(device))
             L.env_config_game(game, b"num_arenas", _cint(self.num_arenas))
+        if host_path is not None:
+            if not L.is_b200:
+                raise ValueError("_host_path needs the B200 engine library")
+            L.env_config_game(game, b"host_path", _cint(0 if host_path == "dense" else 1))
 
         for key, value in config.config_dict.items():
             kind = self._CONFIG_TYPES[key]
@@ -457,15 +462,26 @@ class GridWorld(Environment):
     def sync(self):
         self._lib.magent_b200_sync(self.game)
 
+    def get_io_stats(self):
+        """step-loop traffic so far: dict(d2h=PCIe device->host bytes, h2d=..., host_written=bytes the engine's host
+        threads wrote into caller buffers)"""
+        buf = (ctypes.c_longlong * 3)()
+        self._lib.magent_b200_get_io_stats(self.game, buf, 3)
+        return {"d2h": int(buf[0]), "h2d": int(buf[1]), "host_written": int(buf[2])}
+
+    def step_device_done(self, done_ptr):
+        """env_step with a CUDA device int for `done`: returns without waiting for the step (device-resident loops)"""
+        self._lib.env_step(self.game, ctypes.cast(ctypes.c_void_p(int(done_ptr)), ctypes.POINTER(ctypes.c_int)))
+
     def set_profiling(self, on):
         """bracket every obs-render kernel launch with CUDA events (adds a sync per launch)"""
-        self._lib.magent_b200_set_profiling(1 if on else 0)
+        self._lib.magent_b200_set_profiling(self.game, 1 if on else 0)
 
     def get_profile(self):
         """(total obs-render kernel milliseconds, launches) since profiling was enabled"""
         ms = ctypes.c_double(0.0)
         n = ctypes.c_longlong(0)
-        self._lib.magent_b200_get_profile(ctypes.byref(ms), ctypes.byref(n))
+        self._lib.magent_b200_get_profile(self.game, ctypes.byref(ms), ctypes.byref(n))
         return ms.value, n.value
 
     def launch_count(self):

@@ -33,30 +33,43 @@ struct HostCtx {
     }
 };
 
+// the emulation's "device context": the wire staging of the last obs_wire_begin
+struct Ctx {
+    std::vector<WireHdr> hdr;
+    std::vector<WireMark> marks;
+    std::vector<long long> base;
+    std::vector<float> mm;
+    std::vector<int> counts;
+};
+
 const char *name() { return "emu"; }
-bool init(int, std::string *) { return true; }
+Ctx *create(int, std::string *) { return new Ctx(); }
+void destroy(Ctx *c) { delete c; }
+int device_of(const Ctx *) { return 0; }
 int device_count() { return 1; }
-int sm_count() { return 1; }
-void *dmalloc(size_t b) { return calloc(1, b ? b : 1); }
-void dfree(void *p) { free(p); }
-void dmemset(void *p, int byte, size_t n) { memset(p, byte, n); }
-void h2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
-void d2h(void *d, const void *s, size_t n) { memcpy(d, s, n); }
-void d2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
+int sm_count(const Ctx *) { return 1; }
+void *stream_handle(const Ctx *) { return nullptr; }
+void *dmalloc(Ctx *, size_t b) { return calloc(1, b ? b : 1); }
+void dfree(Ctx *, void *p) { free(p); }
+void dmemset(Ctx *, void *p, int byte, size_t n) { memset(p, byte, n); }
+void h2d(Ctx *, void *d, const void *s, size_t n) { memcpy(d, s, n); }
+void d2h(Ctx *, void *d, const void *s, size_t n) { memcpy(d, s, n); }
+void d2d(Ctx *, void *d, const void *s, size_t n) { memcpy(d, s, n); }
 void *host_alloc(size_t b) { return malloc(b ? b : 1); }
 void host_free(void *p) { free(p); }
 bool is_device_ptr(const void *) { return false; }
-void sync() {}
+bool is_pinned_host_ptr(const void *) { return false; }
+void sync(Ctx *) {}
 
-void launch_step(const EngineDev *dE, const EngineDev &, const StepArgs &S, int) {
+void launch_step(Ctx *, const EngineDev *dE, const EngineDev &, const StepArgs &S, int) {
     HostCtx c;
     for (int a = 0; a < dE->A; ++a) run_step(c, *dE, S, a);
 }
-void launch_cull(const EngineDev *dE, const EngineDev &, unsigned curmask, int) {
+void launch_cull(Ctx *, const EngineDev *dE, const EngineDev &, unsigned curmask, int) {
     HostCtx c;
     for (int a = 0; a < dE->A; ++a) run_cull(c, *dE, curmask, a);
 }
-void launch_offsets(const EngineDev *dE, const EngineDev &) {
+void launch_offsets(Ctx *, const EngineDev *dE, const EngineDev &) {
     const EngineDev &E = *dE;
     for (int g = 0; g < E.G; ++g) {
         int *off = E.off + (size_t)g * (E.A + 1);
@@ -64,8 +77,7 @@ void launch_offsets(const EngineDev *dE, const EngineDev &) {
         for (int a = 0; a < E.A; ++a) off[a + 1] = off[a] + E.n[g * E.A + a];
     }
 }
-bool obs_prepare_valid(const EngineDev *) { return true; }
-void launch_obs_prepare(const EngineDev *dE, const EngineDev &, unsigned curmask, int og, float *mm_val) {
+void launch_obs_prepare(Ctx *, const EngineDev *dE, const EngineDev &, unsigned curmask, int og, float *mm_val) {
     if (!mm_val) return;
     const EngineDev &E = *dE;
     const GroupDev &OG = E.grp[og];
@@ -114,7 +126,7 @@ static uint16_t f32_to_f16(float f) {
     if (rem > 0x1000u || (rem == 0x1000u && (r & 1u))) ++r;
     return sign | (uint16_t)r;
 }
-void launch_obs(const EngineDev *dE, const EngineDev &, const ObsArgs &O, const float *mm_val, int) {
+void launch_obs(Ctx *, const EngineDev *dE, const EngineDev &, const ObsArgs &O, const float *mm_val, int) {
     const EngineDev &E = *dE;
     int g = O.group;
     const GroupDev &G = E.grp[g];
@@ -144,7 +156,7 @@ void launch_obs(const EngineDev *dE, const EngineDev &, const ObsArgs &O, const 
         }
     }
 }
-void launch_info(const EngineDev *dE, const EngineDev &, unsigned curmask, int kind, int g, void *buf, int) {
+void launch_info(Ctx *, const EngineDev *dE, const EngineDev &, unsigned curmask, int kind, int g, void *buf, int) {
     const EngineDev &E = *dE;
     const AgentSoA &s = cur_soa(E, curmask, g);
     for (int a = 0; a < E.A; ++a) {
@@ -163,7 +175,7 @@ void launch_info(const EngineDev *dE, const EngineDev &, unsigned curmask, int k
         }
     }
 }
-void launch_random_actions(const EngineDev *dE, const EngineDev &, unsigned curmask, int g,
+void launch_random_actions(Ctx *, const EngineDev *dE, const EngineDev &, unsigned curmask, int g,
                            unsigned long long seed, int) {
     const EngineDev &E = *dE;
     const AgentSoA &s = cur_soa(E, curmask, g);
@@ -175,9 +187,78 @@ void launch_random_actions(const EngineDev *dE, const EngineDev &, unsigned curm
         }
 }
 
+void counts_fetch_begin(Ctx *c, const int *dev_off, size_t n) { c->counts.assign(dev_off, dev_off + n); }
+const int *counts_fetch_wait(Ctx *c) { return c->counts.data(); }
+void read_done(Ctx *, const EngineDev &hE, int *done_words) { memcpy(done_words, hE.done, sizeof(int) * hE.A); }
+void launch_done_to_device(Ctx *, const EngineDev *dE, const EngineDev &, int *dev_done) {
+    int all = 1;
+    for (int a = 0; a < dE->A; ++a) all &= dE->done[a] & 1;
+    *dev_done = all;
+}
+
+// wire records of one observation (backend.h): derived from the same per-cell composition the dense emulation uses, so
+// the engine's host expansion (host_expand.cc) can be checked against the reference without a GPU
+void obs_wire_begin(Ctx *c, const EngineDev *dE, const EngineDev &, const ObsArgs &O, const float *mm_val, int n_total,
+                    bool want_dense, WireDesc *out) {
+    const EngineDev &E = *dE;
+    const int g = O.group;
+    const GroupDev &G = E.grp[g];
+    const int cells = G.view_w * G.view_h, C = E.n_channel;
+    const AgentSoA &s = cur_soa(E, O.curmask, g);
+    const int n_chunks = (n_total + WIRE_CHUNK - 1) / WIRE_CHUNK;
+    c->hdr.assign(n_total, WireHdr());
+    c->marks.clear();
+    c->base.assign(n_chunks + 1, 0);
+    const int mm_stride = (E.G * cells + 3) & ~3;
+    if (mm_val) {
+        c->mm.assign((size_t)E.A * mm_stride, 0.0f);
+        for (int a = 0; a < E.A; ++a) memcpy(&c->mm[(size_t)a * mm_stride], mm_val + (size_t)a * E.G * cells, sizeof(float) * E.G * cells);
+    }
+    std::vector<float> cell(C);
+    for (int a = 0; a < E.A; ++a) {
+        const int n = E.n[g * E.A + a], base = E.off[(size_t)g * (E.A + 1) + a];
+        for (int i = 0; i < n; ++i) {
+            const long gi = gidx(E, a, g, i);
+            const int o = base + i;
+            if (o % WIRE_CHUNK == 0) c->base[o / WIRE_CHUNK] = (long long)c->marks.size();
+            int cx = -1, cy = -1;
+            if (mm_val) minimap_cell(E, G.view_w, G.view_h, s.x[gi], s.y[gi], cx, cy);
+            WireHdr h;
+            h.arena = a;
+            h.self_cell = mm_val ? (unsigned short)(cy * G.view_w + cx) : (unsigned short)0xffff;
+            int count = 0;
+            for (int vy = 0; vy < G.view_h; ++vy)
+                for (int vx = 0; vx < G.view_w; ++vx) {
+                    obs_compose_cell(E, O.curmask, a, g, s.x[gi], s.y[gi], s.dir[gi], -1, -1, vy, vx, nullptr, cell.data());
+                    const int w = (vy * G.view_w + vx) * C;
+                    if (cell[0] != 0.0f) { c->marks.push_back({(unsigned)w, 0.0f}); ++count; }
+                    if (E.food_mode && cell[1] != 0.0f) { c->marks.push_back({(unsigned)(w + 1), 0.0f}); ++count; }
+                    for (int j = 0; j < E.G; ++j) {
+                        const int ch = obs_channel(E, g, j);
+                        if (cell[ch] != 0.0f) { c->marks.push_back({(unsigned)(w + ch) | WIRE_HAS_HP, cell[ch + 1]}); ++count; }
+                    }
+                }
+            h.count = (unsigned short)count;
+            c->hdr[o] = h;
+            obs_feature(E, O.curmask, a, g, i, (float *)O.feature + (size_t)o * G.feature_size);
+        }
+    }
+    c->base[n_chunks] = (long long)c->marks.size();
+    if (want_dense) launch_obs(c, dE, E, O, mm_val, n_total);
+    c->marks.push_back({0u, 0.0f});
+    out->hdr = c->hdr.data(); out->marks = c->marks.data(); out->chunk_base = c->base.data();
+    out->mm = mm_val ? c->mm.data() : nullptr; out->mm_stride = mm_val ? mm_stride : 0;
+    out->n_total = n_total; out->n_chunks = n_chunks;
+    out->chunks_per_wave = 2; out->n_waves = (n_chunks + 1) / 2;
+}
+void obs_wire_wait(Ctx *, int) {}
+void dense_ready_wait(Ctx *) {}
+void dma_d2h_async(Ctx *, void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
+void dma_wait(Ctx *, int) {}
+
 long long launch_count() { return 0; }
-void profile_enable(bool) {}
-void profile_read(double *ms, long long *n) { *ms = 0; *n = 0; }
+void profile_enable(Ctx *, bool) {}
+void profile_read(Ctx *, double *ms, long long *n) { *ms = 0; *n = 0; }
 
 }  // namespace be
 }  // namespace mg

@@ -5,5 +5,5 @@ here="$(cd "$(dirname "$0")" && pwd)"
 src="$here/../../magent_b200/csrc"
 mkdir -p "$here/../_emu"
 /usr/bin/g++ -std=c++17 -O2 -g -fPIC -shared -fvisibility=hidden -Wall -Wno-unused-function \
-    "$src/engine.cc" "$src/shim.cc" "$here/backend_emu.cc" -o "$here/../_emu/libmagent_emu.so"
+    "$src/engine.cc" "$src/shim.cc" "$src/host_expand.cc" "$here/backend_emu.cc" -pthread -o "$here/../_emu/libmagent_emu.so"
 echo "built tests/_emu/libmagent_emu.so"
