@@ -66,6 +66,8 @@ def build_env(wl, lib, arenas, seed0=0):
     kw = {}
     if arenas != 1:
         kw["_num_arenas"] = arenas
+    if wl.get("host_path"):
+        kw["_host_path"] = wl["host_path"]
     if wl["game"] == "battle":
         env = magent.GridWorld("battle", map_size=wl["map_size"], _lib=lib, **kw)
         env.set_seed(seed0)
@@ -261,6 +263,30 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank (and the engine's host threads, which inherit the mask) to the CPUs of the NUMA node its GPU hangs
+    off, BEFORE any page-locked buffer is allocated: the 5 GB of observations per step are then written to local
+    memory.  Returns a short description for the JSON line."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bus = out[-12:] if len(out) >= 12 else out                   # 00000000:9c:00.0 -> 0000:9c:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return "GPU reports no NUMA node"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "node %d has no CPU in the affinity mask" % node
+        os.sched_setaffinity(0, cpus)
+        return "rank bound to NUMA node %d (%d cpus) of GPU %s" % (node, len(cpus), bus)
+    except Exception as e:                                           # noqa: BLE001  (binding is best effort)
+        return "not bound (%s)" % type(e).__name__
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -273,6 +299,10 @@ def main():
     ap.add_argument("--obs-dtype", default="f32", choices=["f32", "f16"],
                     help="f32 = the reference ABI (headline); f16 = the compact hand-off extension (reported separately)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-seconds", type=float, default=1.5, help="the e2e loop runs at least this long (and >= 3 steps)")
+    ap.add_argument("--host-path", default=None, choices=["wire", "dense"],
+                    help="env_get_observation into host memory: wire records + host expansion (default) or the round-1 dense DMA")
+    ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--_cpu-worker", dest="cpu_worker", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=100)
@@ -292,10 +322,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        if not os.path.exists(REF_LIB):
+            # the reference arm is the UNMODIFIED reference or nothing: never silently the C restatement
+            sys.stderr.write("bench.py --impl reference: oracle/_ref/libmagent.so is missing (build it with "
+                             "`make -C oracle ref` where /root/reference exists)\n")
+            sys.exit(3)
         cb = run_cpu_baseline(args.workload, budget_steps=None)
-        if cb is None:
-            print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref nor oracle/_build is built"}))
-            return
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_sample_step"], "higher_is_better": True,
@@ -313,6 +345,7 @@ def main():
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
+    numa = "off" if args.no_numa_bind else bind_to_gpu_numa_node(local_rank)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -324,6 +357,8 @@ def main():
     lib = load_library()
     A = wl["arenas"]
     t_setup = time.time()
+    if args.host_path:
+        wl["host_path"] = args.host_path
     env, act = build_env(wl, lib.path, A, seed0=rank * A)
     handles = env.get_handles()
     spaces = {env._hv(h): (env.get_view_space(h), env.get_feature_space(h)) for h in handles}
@@ -342,6 +377,7 @@ def main():
                    torch.empty((n0,), dtype=torch.float32, device=dev))
 
     import ctypes
+    done_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
 
     def dev_step(seed):
         for h in act:
@@ -351,7 +387,7 @@ def main():
             obs_call(env.game, g, ptrs)
         for h in act:
             env.set_random_actions(h, seed)
-        env.step()
+        env.step_device_done(done_dev.data_ptr())      # `done` to a device int: no read-back, no host wait
         for h in act:
             g = env._hv(h)
             lib.env_get_reward(env.game, g, bufs[g][2].data_ptr())
@@ -408,47 +444,57 @@ def main():
     # ---- end-to-end: host (pinned) buffers through the public API, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        e2e_steps = max(3, args.steps // 4)
         pools = {}
         rs = np.random.RandomState(rank)
         for h in act:
             pools[env._hv(h)] = rs.randint(0, env.get_action_space(h)[0], size=env.get_num(h)).astype(np.int32)
 
         def host_step():
-            h2d = d2h = 0
             for h in act:
-                v, f = env.get_observation_f16(h) if half else env.get_observation(h)
-                d2h += v.nbytes + f.nbytes
+                env.get_observation_f16(h) if half else env.get_observation(h)
             for h in act:
-                a = pools[env._hv(h)][:env.get_num(h)]
-                env.set_action(h, a)
-                h2d += a.nbytes
+                env.set_action(h, pools[env._hv(h)][:env.get_num(h)])
             env.step()
-            d2h += 4
             for h in act:
-                d2h += env.get_reward(h).nbytes
+                env.get_reward(h)
             env.clear_dead()
-            return h2d, d2h
-        host_step()                                     # allocates the pinned receive buffers
+        for _ in range(3):                              # allocates the pinned receive buffers, starts the host threads
+            host_step()
+        barrier()
+        t0 = time.perf_counter()
+        host_step()
+        one = time.perf_counter() - t0
+        e2e_steps = max(3, int(args.e2e_seconds / max(one, 1e-6)) + 1)
+        if world > 1:                                   # every rank must run the same number of steps
+            ts = torch.tensor([e2e_steps], dtype=torch.int64, device=dev)
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            e2e_steps = int(ts.item())
         barrier()
         c0 = env.get_counters()
+        io0 = env.get_io_stats()
         t0 = time.perf_counter()
-        hb = db = 0
         for _ in range(e2e_steps):
-            a, b = host_step()
-            hb += a; db += b
+            host_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         c1 = env.get_counters()
+        io1 = env.get_io_stats()
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        cnt = torch.tensor([c1[0] - c0[0], hb, db], dtype=torch.int64, device=dev)
+        cnt = torch.tensor([c1[0] - c0[0], io1["h2d"] - io0["h2d"], io1["d2h"] - io0["d2h"],
+                            io1["host_written"] - io0["host_written"]], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        e2e = {"value": int(cnt[0].item()) / float(t.item()), "unit": UNIT, "steps": e2e_steps,
+        e2e = {"value": int(cnt[0].item()) / float(t.item()), "unit": UNIT, "steps": e2e_steps, "seconds": float(t.item()),
                "h2d_bytes_per_step": int(cnt[1].item()) // e2e_steps, "d2h_bytes_per_step": int(cnt[2].item()) // e2e_steps,
-               "timing": "host wall clock around the API loop (includes PCIe copies and syncs), max over ranks",
-               "host_buffers": "page-locked numpy arrays owned by the wrapper"}
+               "host_bytes_written_per_step": int(cnt[3].item()) // e2e_steps,
+               "host_threads": int(lib.magent_b200_host_threads()),
+               "path": "observations cross PCIe as compact wire records (headers + marks) and are expanded into the caller's "
+                       "float32 buffers by the engine's host threads; feature rows, rewards and actions are plain copies"
+                       if (args.host_path or "wire") == "wire" and not half else "dense records over PCIe",
+               "bytes_counted": "by the engine (magent_b200_get_io_stats): every byte it copies across PCIe / writes into caller buffers",
+               "timing": "host wall clock around the API loop (includes PCIe copies, host expansion and syncs), max over ranks",
+               "host_buffers": "page-locked numpy arrays owned by the wrapper", "numa": numa}
 
     clocks = sampler.stop() if sampler else None      # sampled across the device-timed and the e2e timed regions
     if rank != 0:

@@ -420,3 +420,91 @@ def test_random_arena_batches_match_independent_checkers(seed):
     tails, empty groups in some arenas)"""
     import fuzz_common as fz
     fz.play_batch(seed, checker_lib(), pc.CUDA_LIB, n_arenas=2 + seed % 5, steps=12)
+
+
+# ---- host-buffer observations: wire records from the CUDA kernels + host expansion (tests/test_host_expand_cpu.py
+# runs the same checks with the emulated producer)
+import test_host_expand_cpu as hx  # noqa: E402
+
+
+@pytest.mark.parametrize("threads", [1, 5])
+@pytest.mark.parametrize("game", sorted(hx.MAKERS))
+def test_wire_records_from_the_gpu_expand_to_the_reference_bytes(game, threads):
+    hx.test_wire_expansion_matches_the_reference(pc.CUDA_LIB, game, threads)
+
+
+def test_wire_path_many_chunks_many_arenas():
+    hx.test_many_chunks_many_arenas(pc.CUDA_LIB)
+
+
+@pytest.mark.parametrize("shift", [4, 36])
+def test_wire_path_into_pageable_unaligned_caller_buffers(shift):
+    """plain numpy memory (what the reference's own wrapper hands over), any alignment"""
+    hx.test_caller_buffers_of_any_alignment(pc.CUDA_LIB, shift)
+
+
+def test_wire_and_dense_host_paths_agree_at_scale():
+    """64 arenas x 2x1000 agents: every record of both groups through both host paths, bit for bit"""
+    import magent_b200 as magent
+    envs = []
+    for path in ("wire", "dense"):
+        env = magent.GridWorld("battle", map_size=200, _lib=pc.CUDA_LIB, _num_arenas=64, _host_path=path)
+        env.set_seed(3)
+        env.reset()
+        for h in env.get_handles():
+            env.add_agents(h, method="random", n=1000)
+        envs.append(env)
+    rs = np.random.RandomState(0)
+    for t in range(4):
+        acts = [rs.randint(0, 21, size=envs[0].get_num(h)).astype(np.int32) for h in envs[0].get_handles()]
+        obs = []
+        for env in envs:
+            hs = env.get_handles()
+            obs.append([tuple(x.copy() for x in env.get_observation(h)) for h in hs])
+            for h, a in zip(hs, acts):
+                env.set_action(h, a)
+            env.step()
+            env.clear_dead()
+        for (v0, f0), (v1, f1) in zip(obs[0], obs[1]):
+            assert np.array_equal(v0.view(np.uint32), v1.view(np.uint32))
+            assert np.array_equal(f0.view(np.uint32), f1.view(np.uint32))
+
+
+def test_device_done_and_deferred_counts():
+    """env_step with a device pointer for `done`, clear_dead without waiting: the host's counts catch up when asked"""
+    import ctypes
+    torch = pytest.importorskip("torch")
+    import magent_b200 as magent
+    from magent_b200.c_lib import load_library
+    L = load_library(pc.CUDA_LIB)
+    env = pc.make_battle(pc.CUDA_LIB, 30, 300, 3)
+    ref = pc.make_battle(checker_lib(), 30, 300, 3)
+    hs, rhs = env.get_handles(), ref.get_handles()
+    done_dev = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    rs = np.random.RandomState(3)
+    for t in range(60):
+        acts = [rs.randint(0, 21, size=ref.get_num(h)).astype(np.int32) for h in rhs]
+        for e, hh in ((env, hs), (ref, rhs)):
+            for h, a in zip(hh, acts):
+                if e is env:
+                    # device-pointer actions: the host may hold pre-cull (larger) counts at this point
+                    ta = torch.from_numpy(a).cuda()
+                    L.env_set_action(e.game, e._hv(h), ta.data_ptr())
+                else:
+                    e.set_action(h, a)
+        env.step_device_done(done_dev.data_ptr())
+        rdone = ref.step()
+        env.clear_dead()
+        ref.clear_dead()
+        assert bool(done_dev.item()) == rdone
+        if t % 7 == 6:                                  # now ask: exact numbers, ids, positions
+            for h, rh in zip(hs, rhs):
+                assert env.get_num(h) == ref.get_num(rh)
+                np.testing.assert_array_equal(env.get_agent_id(h), ref.get_agent_id(rh))
+                np.testing.assert_array_equal(env.get_pos(h), ref.get_pos(rh))
+    assert ref.get_num(rhs[0]) < 300
+    for h, rh in zip(hs, rhs):
+        v, f = env.get_observation(h)
+        rv, rf = ref.get_observation(rh)
+        np.testing.assert_array_equal(v.view(np.uint32), rv.view(np.uint32))
+        np.testing.assert_array_equal(f.view(np.uint32), rf.view(np.uint32))
