@@ -18,6 +18,7 @@
 #include <string>
 #include <string.h>
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "backend.h"
@@ -41,6 +42,20 @@ namespace be {
 
 static std::atomic<long long> g_launches{0};       // instrumentation only (magent_b200_launch_count)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to (function, device), not to an engine: it is only ever raised,
+// under a lock, so that a second engine with a smaller need cannot pull it from under the first
+enum { ATTR_STEP = 0, ATTR_OBS0 = 1, ATTR_N = 1 + 8, ATTR_MAX_DEVICES = 64 };
+static std::mutex g_attr_mu;
+static size_t g_attr_smem[ATTR_MAX_DEVICES][ATTR_N];
+template <class K>
+static void ensure_dynamic_smem(int device, int slot, K kernel, size_t smem) {
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    size_t &have = g_attr_smem[device % ATTR_MAX_DEVICES][slot];
+    if (smem <= have) return;
+    CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    have = smem;
+}
+
 // Per-engine device context.  Everything the backend needs to remember between calls lives here, nothing in
 // process-global state: two engines on two devices (or on one) never see each other's scratch.
 struct Ctx {
@@ -57,7 +72,6 @@ struct Ctx {
     // per-observer headers of the render kernel
     int4 *obs_hdr = nullptr; size_t obs_hdr_n = 0;
     // cudaFuncSetAttribute caches (per device: a context never changes device)
-    size_t step_smem_configured = 0;
     struct ObsCfg { size_t smem = (size_t)-1; int ctas_per_sm = 1; } obs_cfg[8];
     int *pin_done = nullptr; size_t pin_done_n = 0;         // pinned read-back of EngineDev::done
     int *pin_counts = nullptr; size_t pin_counts_n = 0;     // pinned read-back of EngineDev::off (clear_dead)
@@ -516,10 +530,7 @@ void launch_step(Ctx *c, const EngineDev *dE, const EngineDev &hE, const StepArg
             smem = sbytes;
             // few arenas: one wide CTA each; many arenas: narrower CTAs so that two fit on an SM and overlap
             threads = max_agents >= 768 ? (hE.A > g_sms ? 512 : 1024) : (max_agents >= 384 ? 512 : 256);
-            if (smem > c->step_smem_configured) {
-                CUDA_CHECK(cudaFuncSetAttribute(step_kernel_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                c->step_smem_configured = smem;
-            }
+            ensure_dynamic_smem(c->device, ATTR_STEP, step_kernel_cta, smem);
         }
         // measurement knob (profiles/scripts): MAGENT_B200_STEP_THREADS=256..1024 overrides the block size choice above
         static const int threads_pref = getenv("MAGENT_B200_STEP_THREADS") ? atoi(getenv("MAGENT_B200_STEP_THREADS")) : 0;
@@ -1149,8 +1160,8 @@ static void launch_obs_typed(Ctx *c, int cfg_slot, const EngineDev &hE, ObsParam
     }
     if (headers_only) return;
     Ctx::ObsCfg &cfg = c->obs_cfg[cfg_slot];
+    ensure_dynamic_smem(c->device, ATTR_OBS0 + cfg_slot, obs_render_kernel<T, NIT, TURN>, smem);
     if (smem != cfg.smem) {
-        CUDA_CHECK(cudaFuncSetAttribute(obs_render_kernel<T, NIT, TURN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.ctas_per_sm, obs_render_kernel<T, NIT, TURN>, THREADS, smem));
         if (cfg.ctas_per_sm < 1) cfg.ctas_per_sm = 1;
         cfg.smem = smem;
