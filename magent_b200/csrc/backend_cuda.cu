@@ -652,17 +652,48 @@ void launch_random_actions(Ctx *c, const EngineDev *dE, const EngineDev &, unsig
 }
 
 // ------------------------------------------------------------------------------------------------
-// obs_prepare: one pass over every agent of every group per get_observation call:
-//   * hp_norm plane: hpn_plane[cell] = hp / max_hp of the agent standing on the cell -- the f32 divide of Map.cc:197
-//     done ONCE per agent instead of once per observer that sees it, and stored NEXT TO the occupancy plane so the
-//     render kernel fetches cell code and hp with two independent loads (no position -> plane -> agent chain).
-//     Only living agents own cells (dead ones were cleared in the step), stale values under empty cells are never read;
-//   * minimap (when enabled): counts per (arena, group, coarse cell); value = (float)count / (float)group size
+// obs_prepare: the minimap of one observation state (GridWorld.cc:328-357): per (arena, group) the number of agents in
+// every coarse cell of the OBSERVER's view-sized grid, divided by the group's size.  Dead-but-unculled agents count,
+// absorbed ones do not when the observer's type can absorb (:343-347).  (The hp_norm plane the render also needs is
+// kept current by the step kernels, step_phases.h hpn_set.)
+//
+// minimap_small_kernel: one CTA per (arena, group) when a group of an arena is at most a few thousand agents --
+// histogram in shared memory, normalised row written directly.  Larger groups: obs_prepare_kernel histograms chunks of
+// 4096 agents into global counters, minimap_norm_kernel normalises.
+__global__ void __launch_bounds__(256) minimap_small_kernel(const EngineDev *gE, unsigned curmask, int og, float *mm_val, int stride) {
+    extern __shared__ int hist[];
+    __shared__ int counted_s;
+    const EngineDev &E = *gE;
+    const int ag = blockIdx.x;               // a * G + j
+    const int a = ag / E.G, j = ag - a * E.G;
+    const int vw = E.grp[og].view_w, vh = E.grp[og].view_h, cells = vw * vh;
+    const int n = E.n[j * E.A + a];
+    for (int k = threadIdx.x; k < cells; k += blockDim.x) hist[k] = 0;
+    if (threadIdx.x == 0) counted_s = 0;
+    __syncthreads();
+    const GroupDev &G = E.grp[j];
+    const AgentSoA &s = G.soa[(curmask >> j) & 1u];
+    const int scale_h = (E.H + vh - 1) / vh, scale_w = (E.W + vw - 1) / vw;
+    const bool skip_absorbed = E.grp[og].can_absorb != 0;
+    int counted = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const long gi = (long)a * G.cap + i;
+        if (skip_absorbed && (s.flags[gi] & FLAG_ABSORBED)) continue;
+        atomicAdd(&hist[(s.y[gi] / scale_h) * vw + s.x[gi] / scale_w], 1);
+        ++counted;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, d);
+    if ((threadIdx.x & 31) == 0 && counted) atomicAdd(&counted_s, counted);
+    __syncthreads();
+    const int tot = counted_s;
+    float *out = mm_val + (size_t)a * stride + (size_t)j * cells;
+    // an empty (or fully absorbed) group is 0/0 in the reference: x86 divss yields the default quiet NaN 0xFFC00000
+    for (int k = threadIdx.x; k < cells; k += blockDim.x)
+        out[k] = tot ? (float)hist[k] / (float)tot : __int_as_float((int)0xFFC00000u);
+}
 
-// per observation state: (1) the hp_norm plane (hp / max_hp of the occupant, Map.cc:197) at every living agent's
-// body cells -- stale values elsewhere are never read because the kind plane says "empty" there; (2) the minimap
-// histogram of every (arena, group) in the observer's coarse grid.
-__global__ void __launch_bounds__(256) obs_prepare_kernel(const EngineDev *gE, unsigned curmask, int og, int chunk, int do_minimap) {
+__global__ void __launch_bounds__(256) obs_prepare_kernel(const EngineDev *gE, unsigned curmask, int og, int chunk) {
     extern __shared__ int hist[];
     const EngineDev &E = *gE;
     const int ag = blockIdx.y;               // a * G + j
@@ -672,39 +703,24 @@ __global__ void __launch_bounds__(256) obs_prepare_kernel(const EngineDev *gE, u
     const int lo = blockIdx.x * chunk;
     if (lo >= n) return;
     const int hi = min(n, lo + chunk);
-    if (do_minimap) {
-        for (int k = threadIdx.x; k < cells; k += blockDim.x) hist[k] = 0;
-        __syncthreads();
-    }
+    for (int k = threadIdx.x; k < cells; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
     const GroupDev &G = E.grp[j];
     const AgentSoA &s = G.soa[(curmask >> j) & 1u];
     const int scale_h = (E.H + vh - 1) / vh, scale_w = (E.W + vw - 1) / vw;
     const bool skip_absorbed = E.grp[og].can_absorb != 0;     // GridWorld.cc:343-347 (the OBSERVER's type decides)
-    float *plane = E.hpn + a * E.kplane;
     int counted = 0;
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         long gi = (long)a * G.cap + i;
-        const int x = s.x[gi], y = s.y[gi];
-        const unsigned char fl = s.flags[gi];
-        if (!(fl & FLAG_DEAD)) {
-            const float v = s.hp[gi] / G.max_hp;
-            int bw, bh;
-            body_dims(G, agent_dir(E, s, gi), bw, bh);
-            for (int bx = 0; bx < bw; ++bx)
-                for (int by = 0; by < bh; ++by) plane[(long)(y + by + E.kpad) * E.kw + x + bx + E.kpad] = v;
-        }
-        if (do_minimap && !(skip_absorbed && (fl & FLAG_ABSORBED))) {
-            atomicAdd(&hist[(y / scale_h) * vw + x / scale_w], 1);
-            ++counted;
-        }
+        if (skip_absorbed && (s.flags[gi] & FLAG_ABSORBED)) continue;
+        atomicAdd(&hist[(s.y[gi] / scale_h) * vw + s.x[gi] / scale_w], 1);
+        ++counted;
     }
-    if (do_minimap) {
-        if (counted) atomicAdd(&E.mm_total[ag], counted);
-        __syncthreads();
-        int *out = E.mm_count + (size_t)ag * cells;
-        for (int k = threadIdx.x; k < cells; k += blockDim.x)
-            if (hist[k]) atomicAdd(&out[k], hist[k]);
-    }
+    if (counted) atomicAdd(&E.mm_total[ag], counted);
+    __syncthreads();
+    int *out = E.mm_count + (size_t)ag * cells;
+    for (int k = threadIdx.x; k < cells; k += blockDim.x)
+        if (hist[k]) atomicAdd(&out[k], hist[k]);
 }
 
 // normalised minimap, one padded row per arena: mm[a * stride + j * cells + cell]  (stride % 4 == 0 so that a row is a
@@ -723,34 +739,36 @@ __global__ void __launch_bounds__(256) minimap_norm_kernel(const EngineDev *gE, 
 }
 
 void launch_obs_prepare(Ctx *c, const EngineDev *dE, const EngineDev &hE, unsigned curmask, int og, float *mm_val) {
+    if (!mm_val) return;                     // no minimap: nothing to prepare (the planes are kept current by the step)
     DeviceGuard guard(c);
     const int g_sms = c->sms;
     const int cells = hE.grp[og].view_w * hE.grp[og].view_h;
     const int total = hE.A * hE.G * cells;
     int cap_max = 0;
     for (int g = 0; g < hE.G; ++g) cap_max = cap_max > hE.grp[g].cap ? cap_max : hE.grp[g].cap;
-    if (mm_val) {
-        CUDA_CHECK(cudaMemsetAsync(hE.mm_count, 0, (size_t)total * 4, c->stream));
-        CUDA_CHECK(cudaMemsetAsync(hE.mm_total, 0, (size_t)hE.A * hE.G * 4, c->stream));
+    c->mm_stride = (hE.G * cells + 3) & ~3;
+    const size_t need = (size_t)hE.A * c->mm_stride;
+    if (need > c->mm_pad_n) {
+        if (c->mm_pad) { CUDA_CHECK(cudaStreamSynchronize(c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->copy)); cudaFree(c->mm_pad); }
+        CUDA_CHECK(cudaMalloc(&c->mm_pad, need * sizeof(float)));
+        CUDA_CHECK(cudaMemsetAsync(c->mm_pad, 0, need * sizeof(float), c->stream));
+        c->mm_pad_n = need;
     }
+    if (cap_max <= 8192 && (size_t)cells * sizeof(int) <= 48 * 1024) {
+        minimap_small_kernel<<<hE.A * hE.G, 256, cells * sizeof(int), c->stream>>>(dE, curmask, og, c->mm_pad, c->mm_stride);
+        post_launch("minimap_small_kernel");
+        return;
+    }
+    CUDA_CHECK(cudaMemsetAsync(hE.mm_count, 0, (size_t)total * 4, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(hE.mm_total, 0, (size_t)hE.A * hE.G * 4, c->stream));
     const int chunk = 4096;
     dim3 grid((cap_max + chunk - 1) / chunk, hE.A * hE.G);
-    obs_prepare_kernel<<<grid, 256, cells * sizeof(int), c->stream>>>(dE, curmask, og, chunk, mm_val ? 1 : 0);
+    obs_prepare_kernel<<<grid, 256, cells * sizeof(int), c->stream>>>(dE, curmask, og, chunk);
     post_launch("obs_prepare_kernel");
-    if (mm_val) {
-        c->mm_stride = (hE.G * cells + 3) & ~3;
-        const size_t need = (size_t)hE.A * c->mm_stride;
-        if (need > c->mm_pad_n) {
-            if (c->mm_pad) { CUDA_CHECK(cudaStreamSynchronize(c->stream)); cudaFree(c->mm_pad); }
-            CUDA_CHECK(cudaMalloc(&c->mm_pad, need * sizeof(float)));
-            CUDA_CHECK(cudaMemsetAsync(c->mm_pad, 0, need * sizeof(float), c->stream));
-            c->mm_pad_n = need;
-        }
-        int g2 = (total + 255) / 256;
-        if (g2 > 8 * g_sms) g2 = 8 * g_sms;
-        minimap_norm_kernel<<<g2, 256, 0, c->stream>>>(dE, og, c->mm_pad, total, c->mm_stride);
-        post_launch("minimap_norm_kernel");
-    }
+    int g2 = (total + 255) / 256;
+    if (g2 > 8 * g_sms) g2 = 8 * g_sms;
+    minimap_norm_kernel<<<g2, 256, 0, c->stream>>>(dE, og, c->mm_pad, total, c->mm_stride);
+    post_launch("minimap_norm_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -828,58 +846,61 @@ struct ObsParams {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// pre-pass, one warp per 32 observers in ABI order:
+// pre-pass, one thread per observer, CTAs dealt per arena (no search for the arena: blockIdx says it):
 //   * header h = {x, y, arena, self minimap cell | heading << 16}: everything the render kernel needs about the observer itself, so
 //     that its only dependent loads are kind plane -> hp_norm plane;
 //   * the complete non-spatial feature row (GridWorld.cc:386-396): id bits LSB first, one-hot last action, last
 //     reward, and x/W, y/H with the minimap.  A fresh agent's last_action == n_action ("dangerous", GridWorld.h:140)
-//     lands on the reward slot and is overwritten by it -- here the reward simply wins.  The rows of 32 observers are
-//     zeroed with coalesced 16-byte stores, then each lane writes its observer's handful of non-zeros.
+//     lands on the reward slot and is overwritten by it -- here the reward simply wins.  The rows of a CTA's observers are
+//     one contiguous block of the output: composed in shared memory (zero fill, then every thread its own handful of
+//     non-zeros), written out with coalesced stores.
 template <typename T>
-__global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr) {
-    const int n_total = min(P.n_total, P.off[P.A]);           // the host may hold pre-cull counts (upper bounds)
-    const int lane = threadIdx.x & 31;
-    const int n_warps = gridDim.x * (blockDim.x >> 5);
-    for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < n_total; base += n_warps * 32) {
-        const int o = base + lane;
-        const int cnt = min(32, n_total - base);
-        // the 32 feature rows of this warp are one contiguous block of cnt * F elements: zero it with 16-byte stores (the
-        // block starts 16-byte aligned because base % 32 == 0), then every lane drops its own observer's few non-zeros
-        T *rows = (T *)P.feature + (size_t)base * P.F;
-        const int total = cnt * P.F, vec = (int)(16 / sizeof(T));
-        if ((((size_t)rows) & 15) == 0) {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = lane; q < total / vec; q += 32) ((float4 *)rows)[q] = z;
-            for (int q = (total / vec) * vec + lane; q < total; q += 32) rows[q] = ObsOut<T>::cv(0.0f);
-        } else {
-            for (int q = lane; q < total; q += 32) rows[q] = ObsOut<T>::cv(0.0f);
+__global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr, int chunks_per_arena) {
+    extern __shared__ __align__(16) unsigned char hdr_smem[];
+    T *rows = (T *)hdr_smem;                                   // [blockDim.x][F]
+    const int a = blockIdx.x / chunks_per_arena;
+    const int i0 = (blockIdx.x - a * chunks_per_arena) * blockDim.x;
+    const int o0 = P.off[a], n_a = P.off[a + 1] - o0;
+    if (i0 >= n_a) return;
+    int cnt = min((int)blockDim.x, n_a - i0);
+    cnt = min(cnt, P.n_total - (o0 + i0));                     // never beyond the caller's buffers
+    if (cnt <= 0) return;
+    const int total = cnt * P.F;
+    for (int q = threadIdx.x; q < total; q += blockDim.x) rows[q] = ObsOut<T>::cv(0.0f);
+    __syncthreads();
+    if ((int)threadIdx.x < cnt) {
+        const int i = i0 + threadIdx.x;
+        const long gi = (long)a * P.cap + i;
+        const int x = P.x[gi], y = P.y[gi];
+        const int self_cell = P.minimap ? (y / P.scale_h) * P.vw + x / P.scale_w : -1;  // GridWorld.cc:372-373
+        const int heading = P.turn ? (int)P.dir[gi] : 0;
+        hdr[o0 + i] = make_int4(x, y, a, (self_cell & 0xffff) | (heading << 16));
+        T *f = rows + (size_t)threadIdx.x * P.F;
+        unsigned id = (unsigned)P.id[gi];
+        const int nbits = min(P.embedding, 31);
+        id &= nbits >= 32 ? 0xffffffffu : ((1u << nbits) - 1u);
+        while (id) {                                           // embedding: the set bits of the id, LSB first (GridWorld.h:155-164)
+            const int bit = __ffs(id) - 1;
+            f[bit] = ObsOut<T>::cv(1.0f);
+            id &= id - 1;
         }
-        __syncwarp();                                          // orders the zero fill before the value stores below
-        if (o < n_total) {
-            const int a = P.A == 1 ? 0 : locate_arena(P.off, P.A, o);
-            const long gi = (long)a * P.cap + (o - P.off[a]);
-            const int x = P.x[gi], y = P.y[gi];
-            const int self_cell = P.minimap ? (y / P.scale_h) * P.vw + x / P.scale_w : -1;  // GridWorld.cc:372-373
-            const int heading = P.turn ? (int)P.dir[gi] : 0;
-            hdr[o] = make_int4(x, y, a, (self_cell & 0xffff) | (heading << 16));
-            T *f = rows + (size_t)lane * P.F;
-            unsigned id = (unsigned)P.id[gi];
-            const int nbits = min(P.embedding, 31);
-            id &= nbits >= 32 ? 0xffffffffu : ((1u << nbits) - 1u);
-            while (id) {                                       // embedding: the set bits of the id, LSB first (GridWorld.h:155-164)
-                const int bit = __ffs(id) - 1;
-                f[bit] = ObsOut<T>::cv(1.0f);
-                id &= id - 1;
-            }
-            T *g = f + P.embedding;
-            const int act = P.act[gi];
-            if (act >= 0 && act < P.n_action) g[act] = ObsOut<T>::cv(1.0f);
-            g[P.n_action] = ObsOut<T>::cv(P.last_reward[gi]);   // also overwrites the "dangerous" fresh-agent one-hot slot
-            if (P.minimap) {
-                g[P.n_action + 1] = ObsOut<T>::cv((float)x / (float)P.W);                   // GridWorld.cc:394-395
-                g[P.n_action + 2] = ObsOut<T>::cv((float)y / (float)P.H);
-            }
+        T *g = f + P.embedding;
+        const int act = P.act[gi];
+        if (act >= 0 && act < P.n_action) g[act] = ObsOut<T>::cv(1.0f);
+        g[P.n_action] = ObsOut<T>::cv(P.last_reward[gi]);       // also overwrites the "dangerous" fresh-agent one-hot slot
+        if (P.minimap) {
+            g[P.n_action + 1] = ObsOut<T>::cv((float)x / (float)P.W);               // GridWorld.cc:394-395
+            g[P.n_action + 2] = ObsOut<T>::cv((float)y / (float)P.H);
         }
+    }
+    __syncthreads();
+    T *out = (T *)P.feature + (size_t)(o0 + i0) * P.F;
+    if (sizeof(T) == 4 && ((((size_t)out) & 15) == 0)) {       // 16-byte body, scalar tail
+        const int v4 = total >> 2;
+        for (int q = threadIdx.x; q < v4; q += blockDim.x) ((float4 *)out)[q] = ((const float4 *)rows)[q];
+        for (int q = (v4 << 2) + threadIdx.x; q < total; q += blockDim.x) out[q] = rows[q];
+    } else {
+        for (int q = threadIdx.x; q < total; q += blockDim.x) out[q] = rows[q];
     }
 }
 
@@ -1153,9 +1174,12 @@ static void launch_obs_typed(Ctx *c, int cfg_slot, const EngineDev &hE, ObsParam
     }
     P.hdr = c->obs_hdr;
     if (with_headers) {
-        int gt = (n_total + 255) / 256;                                  // one warp per 32 observers
-        if (gt > 16 * g_sms) gt = 16 * g_sms;
-        obs_headers_kernel<T><<<gt, 256, 0, c->stream>>>(P, c->obs_hdr);
+        int threads = 256;                                               // as many observers per CTA as fit 48 KB of rows
+        while (threads > 32 && (size_t)threads * P.F * sizeof(T) > 48 * 1024) threads >>= 1;
+        const size_t hsm = (size_t)threads * P.F * sizeof(T);
+        if (hsm > 48 * 1024) mg::fatal("feature row too long for the header kernel (%d elements)", P.F);
+        const int cpa = (P.cap + threads - 1) / threads;
+        obs_headers_kernel<T><<<(unsigned)((size_t)P.A * cpa), threads, hsm, c->stream>>>(P, c->obs_hdr, cpa);
         post_launch("obs_headers_kernel");
     }
     if (headers_only) return;

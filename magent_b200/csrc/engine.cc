@@ -782,6 +782,25 @@ void Engine::to_device() {
                 }
             be::h2d(bx_, hE_.kind + (size_t)a * hE_.kplane, kp.data(), kp.size());
         }
+        // ... and the hp_norm plane: hp / max_hp (Map.cc:197) under every cell a living agent covers
+        std::vector<float> hp((size_t)hE_.kplane);
+        for (int a = 0; a < A_; ++a) {
+            std::fill(hp.begin(), hp.end(), 0.0f);
+            for (int g = 0; g < Gn; ++g) {
+                const HostGroup &hg = arenas_[a].groups[g];
+                const AgentTypeDef &t = *group_type_[g];
+                for (int i = 0; i < hg.size(); ++i) {
+                    if (hg.flags[i] & FLAG_DEAD) continue;
+                    const bool upright = !turn_mode_ || hg.dir[i] == DIR_NORTH || hg.dir[i] == DIR_SOUTH;
+                    const int bw = upright ? t.width : t.length, bh = upright ? t.length : t.width;
+                    const float v = hg.hp[i] / t.hp;
+                    for (int bx = 0; bx < bw; ++bx)
+                        for (int by = 0; by < bh; ++by)
+                            hp[(size_t)(hg.y[i] + by + hE_.kpad) * hE_.kw + hg.x[i] + bx + hE_.kpad] = v;
+                }
+            }
+            be::h2d(bx_, hE_.hpn + (size_t)a * hE_.kplane, hp.data(), hp.size() * 4);
+        }
     }
     be::dmemset(bx_, hE_.claim_head, 0xff, (size_t)A_ * W_ * H_ * 4);
     {

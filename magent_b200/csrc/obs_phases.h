@@ -57,7 +57,8 @@ MG_HD void obs_compose_cell(const EngineDev &E, unsigned curmask, int a, int g, 
     int tg = code_group(t);
     int ch = obs_channel(E, g, tg);
     out[ch] = 1.0f;
-    out[ch + 1] = cur_soa(E, curmask, tg).hp[gidx(E, a, tg, code_index(t))] / E.grp[tg].max_hp;   // Map.cc:197
+    // hp / max_hp of the occupant (Map.cc:197), from the plane the step phases keep current (step_phases.h hpn_set)
+    out[ch + 1] = E.hpn[a * E.kplane + (long)(y + E.kpad) * E.kw + x + E.kpad];
 }
 
 // non-spatial feature vector of agent (a, g, i)  (GridWorld.cc:386-396, Agent::get_embedding GridWorld.h:155-164)

@@ -61,6 +61,16 @@ MG_HD int node_owner(const EngineDev &E, int node) { return E.max_body == 1 ? no
 MG_HD void kind_set(const EngineDev &E, int a, int x, int y, unsigned char k) {
     E.kind[a * E.kplane + (long)(y + E.kpad) * E.kw + x + E.kpad] = k;
 }
+// ... and so does the hp_norm plane: hp / max_hp of the occupant (Map.cc:197) at every occupied cell, written where an
+// agent's hp changes (attack / starve / absorb) and where it takes new cells (move, turn, placement)
+MG_HD void hpn_set(const EngineDev &E, int a, int x, int y, float v) {
+    E.hpn[a * E.kplane + (long)(y + E.kpad) * E.kw + x + E.kpad] = v;
+}
+MG_HD void hpn_set_body(const EngineDev &E, int a, const GroupDev &G, int x, int y, int bw, int bh, float hp) {
+    const float v = hp / G.max_hp;
+    for (int bx = 0; bx < bw; ++bx)
+        for (int by = 0; by < bh; ++by) hpn_set(E, a, x + bx, y + by, v);
+}
 // ---- directions (turn_mode; reference Map.cc:515-607).  Without turn_mode every agent faces NORTH, for which
 // relative = absolute and the body is width x length.
 MG_HD int agent_dir(const EngineDev &E, const AgentSoA &s, long gi) { return E.turn_mode ? (int)s.dir[gi] : (int)DIR_NORTH; }
@@ -427,6 +437,11 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
             }
         }
         s.hp[gi] = hp;
+        if (!dies && hp != hp0) {                        // keep the hp_norm plane of the observation current
+            int bw, bh;
+            body_dims(G, agent_dir(E, s, gi), bw, bh);
+            hpn_set_body(E, a, G, s.x[gi], s.y[gi], bw, bh, hp);
+        }
         if (dies) {
             s.flags[gi] = fl | FLAG_DEAD;
             R.hdr->any_dead = 1;
@@ -759,7 +774,13 @@ MG_HD void phase_move_collide(Ctx &c, const EngineDev &E, const StepArgs &S, int
             const AgentSoA &so = cur_soa(E, S.curmask, og);
             const long oi = gidx(E, a, og, code_index(obj));
             so.flags[oi] |= FLAG_ABSORBED;
-            so.hp[oi] = so.hp[oi] * 2;
+            const float hp2 = so.hp[oi] * 2;
+            so.hp[oi] = hp2;
+            {                                     // the absorber's cells show its new hp (if it moves, the fill rewrites them)
+                int obw, obh;
+                body_dims(E.grp[og], agent_dir(E, so, oi), obw, obh);
+                hpn_set_body(E, a, E.grp[og], so.x[oi], so.y[oi], obw, obh, hp2);
+            }
             const AgentSoA &s = cur_soa(E, S.curmask, g);
             const long gi = gidx(E, a, g, i);
             s.flags[gi] |= FLAG_DEAD;             // set_dead(true): no dead_penalty, dead_ct untouched (reference quirk)
@@ -832,11 +853,12 @@ MG_HD void phase_move_fill(Ctx &c, const EngineDev &E, const StepArgs &S, int a,
         long gi = gidx(E, a, g, i);
         int bw, bh;
         mover_dims(E, G, s, gi, turn, bw, bh);
+        const float hpv = ok ? s.hp[gi] / G.max_hp : 0.0f;
         for (int bx = 0; bx < bw; ++bx)
             for (int by = 0; by < bh; ++by) {
                 int cell = (ny + by) * E.W + nx + bx;
                 R.claim[cell] = -1;
-                if (ok) { R.occ[cell] = code; kind_set(E, a, nx + bx, ny + by, (unsigned char)(2 + g)); }
+                if (ok) { R.occ[cell] = code; kind_set(E, a, nx + bx, ny + by, (unsigned char)(2 + g)); hpn_set(E, a, nx + bx, ny + by, hpv); }
             }
         if (ok) {
             s.x[gi] = nx; s.y[gi] = ny;
