@@ -33,7 +33,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "agent-steps/sec on battle map at 1/2/4/8 B200 vs ref C++ on host cores"
 UNIT = "agent-steps/s"
@@ -62,7 +61,6 @@ WORKLOADS = {
 
 def build_env(wl, lib, arenas, seed0=0):
     import magent_b200 as magent
-    import parity_common as pc
     kw = {}
     if arenas != 1:
         kw["_num_arenas"] = arenas
@@ -89,7 +87,7 @@ def build_env(wl, lib, arenas, seed0=0):
         env.add_agents(hs[1], method="custom", pos=[[x, y, 0] for x in range(size // 2 + gap, size // 2 + gap + side, 2) for y in ys])
         return env, list(hs)
     if wl["game"] == "gather":
-        env = magent.GridWorld(pc.gather_config(wl["map_size"]), _lib=lib, **kw)
+        env = magent.GridWorld("gather", map_size=wl["map_size"], _lib=lib, **kw)
         env.set_seed(seed0)
         env.reset()
         hs = env.get_handles()
@@ -294,8 +292,12 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="battle512", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="battle512", choices=sorted(WORKLOADS) + ["all"],
+                    help="'all': one JSON line per BASELINE config (battle1, gather64, battle1m, battle1m_sparse, battle512), N=1 only")
     ap.add_argument("--arenas", type=int, default=None, help="override arenas per GPU")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's arenas PER GPU (default); strong: BASELINE configs[4] literally -- 4096 arenas "
+                         "in total (or --arenas), sharded over the ranks (magent_b200.sharding.shard_arenas)")
     ap.add_argument("--obs-dtype", default="f32", choices=["f32", "f16"],
                     help="f32 = the reference ABI (headline); f16 = the compact hand-off extension (reported separately)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -315,9 +317,26 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "all":
+        # one child per workload (a fresh CUDA context each): every BASELINE config in one call
+        for w in ("battle1", "gather64", "battle1m", "battle1m_sparse", "battle512"):
+            cmd = [sys.executable, os.path.abspath(__file__), "--workload", w, "--steps", str(args.steps), "--warmup", str(args.warmup),
+                   "--e2e-seconds", str(args.e2e_seconds)] + (["--no-cpu"] if args.no_cpu or w != "battle512" else []) + \
+                  (["--no-e2e"] if args.no_e2e else [])
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            sys.stdout.write(r.stdout if r.returncode == 0 else json.dumps({"workload": w, "failed": r.stderr[-400:]}) + "\n")
+            sys.stdout.flush()
+        return
     wl = dict(WORKLOADS[args.workload])
     if args.arenas:
         wl["arenas"] = args.arenas
+    first_arena = None
+    if args.scaling == "strong":
+        from magent_b200.sharding import shard_arenas
+        total_arenas = args.arenas or 4096
+        first_arena, wl["arenas"] = shard_arenas(total_arenas, rank, world)
+        wl["desc"] = wl["desc"].replace("512 independent arenas per GPU (per-GPU share of BASELINE configs[4])",
+                                        "%d independent arenas in total (BASELINE configs[4]) sharded over %d GPU(s)" % (total_arenas, world))
 
     if args.impl == "reference":
         if rank != 0:
@@ -359,7 +378,7 @@ def main():
     t_setup = time.time()
     if args.host_path:
         wl["host_path"] = args.host_path
-    env, act = build_env(wl, lib.path, A, seed0=rank * A)
+    env, act = build_env(wl, lib.path, A, seed0=first_arena if first_arena is not None else rank * A)
     handles = env.get_handles()
     spaces = {env._hv(h): (env.get_view_space(h), env.get_feature_space(h)) for h in handles}
 
@@ -432,13 +451,9 @@ def main():
     launches = env.launch_count() - l0
     agent_steps = c1[0] - c0[0]
 
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([agent_steps, launches], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)          # max over ranks of the device time
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)        # NCCL over NVLink: throughput counters only
-    ms_max = float(t.item())
-    total_steps, total_launches = int(cnt[0].item()), int(cnt[1].item())
+    from magent_b200.sharding import reduce_window
+    # NCCL over NVLink: SUM of the throughput counters, MAX over ranks of the device time -- the only collective of the job
+    (total_steps, total_launches), ms_max = reduce_window([agent_steps, launches], ms, device=dev)
     value = total_steps / (ms_max * 1e-3)
 
     # ---- end-to-end: host (pinned) buffers through the public API, copies inside the timed region
@@ -508,11 +523,15 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     achieved = (obs_bytes_per_launch / (obs_ms / obs_launches * 1e-3)) / 1e9 if obs_launches and obs_ms > 0 else None
+    # DRAM bytes per launch of the roofline kernel from the ncu --set full capture (profiles/obs_render_traffic.json); the
+    # capture is tied to the kernel source it was taken from: a changed backend_cuda.cu makes it stale -> null
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "obs_render_traffic.json")
     if os.path.exists(tpath):
+        import hashlib
         tj = json.load(open(tpath))
-        if tj.get("workload") == args.workload and not half:
+        src_sha = hashlib.sha256(open(os.path.join(ROOT, "magent_b200", "csrc", "backend_cuda.cu"), "rb").read()).hexdigest()[:16]
+        if tj.get("workload") == args.workload and not half and tj.get("kernel_source_sha16") == src_sha:
             traffic = tj.get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": "obs_render_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
@@ -529,7 +548,7 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32" if not half else "f32 state, f16 observation hand-off (extension, not the reference ABI)",
         "data": "synthetic",
         "config": {"workload": wl["desc"], "arenas_per_gpu": A, "agents_per_arena_at_start": 2 * wl.get("n", 0) or None,

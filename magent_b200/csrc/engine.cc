@@ -618,9 +618,23 @@ void Engine::to_device() {
         for (int a = 0; a < A_; ++a) need[g] = std::max(need[g], count(g, a));
         need[g] = std::max(64, (need[g] + 63) / 64 * 64);
     }
-    bool realloc = dE_ == nullptr || hE_.A != A_ || hE_.W != W_ || hE_.H != H_ || hE_.G != Gn;
+    // the padded observation planes cover the widest view window of any group, in any heading when agents can turn
+    int pad = 0;
+    for (int g = 0; g < Gn; ++g) {
+        const AgentTypeDef &t = *group_type_[g];
+        const int ox = t.view_x_offset + t.view.x1, oy = t.view_y_offset + t.view.y1;
+        const int ext[4] = {-ox, ox + t.view.width - 1, -oy, oy + t.view.height - 1};
+        for (int e : ext) pad = std::max(pad, e + (turn_mode_ ? std::max(t.width, t.length) : 0));
+    }
+    // env_config_game may change the modes between episodes (as in the reference): everything an allocation's size or
+    // presence depends on is part of the predicate
+    bool realloc = dE_ == nullptr || hE_.A != A_ || hE_.W != W_ || hE_.H != H_ || hE_.G != Gn || hE_.kpad != pad ||
+                   (hE_.food != nullptr) != food_mode_;
     if (!realloc) for (int g = 0; g < Gn; ++g) if (need[g] > cap_[g]) realloc = true;
     if (realloc) {
+        // the event counters are "since construction": they survive a re-allocation (a late add_agents beyond capacity)
+        std::vector<long long> saved_counters;
+        if (dE_ != nullptr) { saved_counters.resize(MG_N_COUNTERS); be::d2h(bx_, saved_counters.data(), hE_.counters, sizeof(long long) * MG_N_COUNTERS); }
         free_device();
         memset(&hE_, 0, sizeof hE_);
         cap_ = need;
@@ -670,14 +684,7 @@ void Engine::to_device() {
         hE_.done = (int *)dalloc((size_t)A_ * 4);
         hE_.occ = (int *)dalloc(cells * 4); hE_.claim_head = (int *)dalloc(cells * 4);
         hE_.food = food_mode_ ? (float *)dalloc(cells * 4) : nullptr;
-        {   // padded observation planes (dev_types.h): the pad covers the widest view window of any group
-            int pad = 0;
-            for (int g = 0; g < Gn; ++g) {
-                const AgentTypeDef &t = *group_type_[g];
-                const int ox = t.view_x_offset + t.view.x1, oy = t.view_y_offset + t.view.y1;
-                const int ext[4] = {-ox, ox + t.view.width - 1, -oy, oy + t.view.height - 1};
-                for (int e : ext) pad = std::max(pad, e + (turn_mode_ ? std::max(t.width, t.length) : 0));   // any heading
-            }
+        {   // padded observation planes (dev_types.h)
             hE_.kpad = pad; hE_.kw = W_ + 2 * pad; hE_.kplane = (long)hE_.kw * (H_ + 2 * pad);
             hE_.kind = (unsigned char *)dalloc((size_t)A_ * hE_.kplane + 16);
             hE_.hpn = (float *)dalloc(((size_t)A_ * hE_.kplane + 4) * 4);
@@ -692,7 +699,8 @@ void Engine::to_device() {
         hE_.sh_first = (int *)dalloc(sc * 4); hE_.att_agent = (int *)dalloc(sc * 4);
         hE_.cl_next = (int *)dalloc(sc * max_body * 4);
         hE_.counters = (long long *)dalloc(sizeof(long long) * MG_N_COUNTERS);
-        be::dmemset(bx_, hE_.counters, 0, sizeof(long long) * MG_N_COUNTERS);
+        if (saved_counters.empty()) be::dmemset(bx_, hE_.counters, 0, sizeof(long long) * MG_N_COUNTERS);
+        else be::h2d(bx_, hE_.counters, saved_counters.data(), sizeof(long long) * MG_N_COUNTERS);
         hE_.team_scratch = (int *)dalloc(sizeof(int) * 2 * 4096);
         hE_.mm_count = (int *)dalloc((size_t)A_ * Gn * max_cells * 4);
         hE_.mm_total = (int *)dalloc((size_t)A_ * Gn * 4);
@@ -1247,9 +1255,14 @@ void Engine::get_info(int group, const char *name, void *void_buffer) {        /
         check_group(group, "get_info");
         const AgentTypeDef &t = *group_type_[group];
         for (int i = 0; i < t.view.height * t.view.width; ++i) ib[i] = -1;
-        for (int i = 0; i < t.attack.count; ++i) {          // attack cells outside the view rectangle are dropped (the
-            const int r = t.attack.dy[i] - t.view.y1, c = t.attack.dx[i] - t.view.x1;   // reference writes out of bounds there)
-            if (r >= 0 && r < t.view.height && c >= 0 && c < t.view.width) ib[r * t.view.width + c] = i;
+        // ret.at(dy - y1, dx - x1) = i is a LINEAR index without a bounds check in the reference (utility.h NDPointer::at,
+        // GridWorld.cc:864-870): an attack cell whose column lies outside the view rectangle lands, wrapped, on a
+        // neighbouring row.  Same here for every index inside the buffer; indices outside it (the reference corrupts the
+        // heap there) are dropped.
+        const int cells = t.view.height * t.view.width;
+        for (int i = 0; i < t.attack.count; ++i) {
+            const long idx = (long)(t.attack.dy[i] - t.view.y1) * t.view.width + (t.attack.dx[i] - t.view.x1);
+            if (idx >= 0 && idx < cells) ib[idx] = i;
         }
     } else if (strequ(name, "attack_base")) {
         check_group(group, "get_info"); ib[0] = group_type_[group]->attack_base;

@@ -797,9 +797,9 @@ API int env_get_info(void *game, int g, const char *name, void *buf) {          
     else if (!strcmp(name, "view2attack")) {
         const Type *t = &e->type[e->grp[g].type];
         for (int i = 0; i < t->view.width * t->view.height; i++) ib[i] = -1;
-        for (int i = 0; i < t->attack.count; i++) {                 /* (cells outside the view: out of bounds in the reference, dropped here) */
-            int r = t->attack.dy[i] - t->view.y1, c = t->attack.dx[i] - t->view.x1;
-            if (r >= 0 && r < t->view.height && c >= 0 && c < t->view.width) ib[r * t->view.width + c] = i;
+        for (int i = 0; i < t->attack.count; i++) {                 /* linear index, no bounds check (NDPointer::at): in-buffer */
+            long idx = (long)(t->attack.dy[i] - t->view.y1) * t->view.width + (t->attack.dx[i] - t->view.x1);   /* indices wrap to the */
+            if (idx >= 0 && idx < (long)t->view.height * t->view.width) ib[idx] = i;                      /* neighbouring row; the rest is dropped */
         }
     } else if (!strcmp(name, "render_window_info")) {               /* GridWorld.cc:797-834 */
         e->first_render_done = 1;
