@@ -44,6 +44,14 @@ int magent_b200_get_profile(EnvHandle game, double *obs_ms_total, long long *obs
 /* bytes moved by the step-loop calls of this game so far: [0] device->host over PCIe, [1] host->device, [2] written into
  * caller host buffers by the engine's host threads (env_get_observation with host pointers).  Returns the number written. */
 int magent_b200_get_io_stats(EnvHandle game, long long *out, int capacity);
+/* CUDA graphs for launch-bound (small) workloads.  Every step-loop call made with CUDA device pointers between begin and
+ * end is recorded instead of executed (actions, rewards, observations and `done` in caller-owned device buffers); the
+ * recorded sequence must contain an even number of gridworld_clear_dead calls (two steps).  graph_launch replays it
+ * `times` times: one launch per replay instead of one per kernel.  The caller refills its action buffers between
+ * replays; counts / ids / positions are read with the usual calls after a replay. */
+int magent_b200_graph_begin(EnvHandle game);
+int magent_b200_graph_end(EnvHandle game);     /* returns the graph id */
+int magent_b200_graph_launch(EnvHandle game, int graph_id, int times);
 /* the cudaStream_t all kernels of this game are launched on (a blocking stream: work on the legacy default stream is
  * ordered with it both ways, so CUDA-pointer consumers on the default stream need no extra synchronisation) */
 void *magent_b200_stream(EnvHandle game);

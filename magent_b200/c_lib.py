@@ -69,6 +69,9 @@ EXT_SIGNATURES = {
     "magent_b200_set_profiling": ([_vp, ctypes.c_int], ctypes.c_int),
     "magent_b200_get_profile": ([_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)], ctypes.c_int),
     "magent_b200_stream": ([_vp], _vp),
+    "magent_b200_graph_begin": ([_vp], ctypes.c_int),
+    "magent_b200_graph_end": ([_vp], ctypes.c_int),
+    "magent_b200_graph_launch": ([_vp, ctypes.c_int, ctypes.c_int], ctypes.c_int),
     "magent_b200_get_io_stats": ([_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int], ctypes.c_int),
     "magent_b200_host_threads": ([], ctypes.c_int),
     "magent_b200_set_host_threads": ([ctypes.c_int], ctypes.c_int),

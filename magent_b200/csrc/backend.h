@@ -94,6 +94,15 @@ void dense_ready_wait(Ctx *);            // copy stream waits for the dense rend
 void dma_d2h_async(Ctx *, void *dst, const void *src, size_t bytes);
 void dma_wait(Ctx *, int keep_in_flight);   // wait until at most `keep_in_flight` of the queued copies are outstanding
 
+// ---- CUDA graphs for launch-bound (small) workloads: everything the engine queues on its stream between begin and end
+// becomes one graph; a replay costs one launch.  While capturing, the backend refuses anything that cannot be captured
+// (allocation growth, host synchronisation).  Returns false when the backend has no graph support (test emulation).
+bool capture_begin(Ctx *);
+int capture_end(Ctx *);                  // instantiates; returns the graph's id (>= 0)
+bool capturing(const Ctx *);
+void graph_launch(Ctx *, int id);
+void graph_destroy_all(Ctx *);
+
 // instrumentation: kernel launch counter and optional CUDA-event timing of the obs-render kernel
 long long launch_count();
 void profile_enable(Ctx *, bool on);

@@ -90,7 +90,15 @@ struct Ctx {
     std::vector<cudaEvent_t> wave_events;
     int waves_queued = 0;
     std::vector<cudaEvent_t> dma_events; size_t dma_head = 0, dma_tail = 0;
+    // CUDA graphs (capture_begin / capture_end / graph_launch)
+    bool capturing = false;
+    std::vector<cudaGraphExec_t> graphs;
 };
+
+static void no_capture(const Ctx *c, const char *what) {
+    if (c->capturing) mg::fatal("%s is not possible while a CUDA graph is being captured (run one un-captured step first so that "
+                                "every buffer has its size)", what);
+}
 
 struct DeviceGuard {                     // every entry point runs on its context's device, whatever the caller selected
     explicit DeviceGuard(const Ctx *c) { int cur = -1; cudaGetDevice(&cur); if (cur != c->device) CUDA_CHECK(cudaSetDevice(c->device)); }
@@ -135,6 +143,7 @@ Ctx *create(int device, std::string *err) {
 void destroy(Ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (cudaGraphExec_t e : c->graphs) if (e) cudaGraphExecDestroy(e);
     cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->wave_events) cudaEventDestroy(e);
@@ -151,17 +160,19 @@ int device_of(const Ctx *c) { return c->device; }
 int sm_count(const Ctx *c) { return c->sms; }
 void *stream_handle(const Ctx *c) { return (void *)c->stream; }
 
-void *dmalloc(Ctx *c, size_t bytes) { DeviceGuard g(c); void *p = nullptr; CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 16)); return p; }
+void *dmalloc(Ctx *c, size_t bytes) { no_capture(c, "a device allocation"); DeviceGuard g(c); void *p = nullptr; CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 16)); return p; }
 void dfree(Ctx *c, void *p) { if (p) { DeviceGuard g(c); cudaFree(p); } }
 void dmemset(Ctx *c, void *p, int byte, size_t bytes) { DeviceGuard g(c); CUDA_CHECK(cudaMemsetAsync(p, byte, bytes, c->stream)); }
 void h2d(Ctx *c, void *dst, const void *src, size_t bytes) {
     if (!bytes) return;
+    no_capture(c, "a blocking host-to-device copy");
     DeviceGuard g(c);
     CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 void d2h(Ctx *c, void *dst, const void *src, size_t bytes) {
     if (!bytes) return;
+    no_capture(c, "a blocking device-to-host copy");
     DeviceGuard g(c);
     CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -189,7 +200,7 @@ bool is_pinned_host_ptr(const void *p) {
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return at.type == cudaMemoryTypeHost;
 }
-void sync(Ctx *c) { DeviceGuard g(c); CUDA_CHECK(cudaStreamSynchronize(c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->copy)); }
+void sync(Ctx *c) { no_capture(c, "a synchronisation"); DeviceGuard g(c); CUDA_CHECK(cudaStreamSynchronize(c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->copy)); }
 long long launch_count() { return g_launches.load(); }
 void profile_enable(Ctx *c, bool on) { c->profile = on; c->events_used = 0; }
 static void profile_pair(Ctx *c, cudaEvent_t *e0, cudaEvent_t *e1) {
@@ -211,6 +222,36 @@ void profile_read(Ctx *c, double *ms, long long *n) {
         total += t;
     }
     *ms = total; *n = (long long)(c->events_used / 2);
+}
+
+bool capture_begin(Ctx *c) {
+    DeviceGuard guard(c);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    c->capturing = true;
+    return true;
+}
+int capture_end(Ctx *c) {
+    DeviceGuard guard(c);
+    cudaGraph_t g = nullptr;
+    c->capturing = false;
+    CUDA_CHECK(cudaStreamEndCapture(c->stream, &g));
+    cudaGraphExec_t exec = nullptr;
+    CUDA_CHECK(cudaGraphInstantiate(&exec, g, 0));
+    CUDA_CHECK(cudaGraphDestroy(g));
+    c->graphs.push_back(exec);
+    return (int)c->graphs.size() - 1;
+}
+bool capturing(const Ctx *c) { return c->capturing; }
+void graph_launch(Ctx *c, int id) {
+    DeviceGuard guard(c);
+    if (id < 0 || id >= (int)c->graphs.size() || !c->graphs[id]) mg::fatal("invalid graph id %d", id);
+    CUDA_CHECK(cudaGraphLaunch(c->graphs[id], c->stream));
+}
+void graph_destroy_all(Ctx *c) {
+    DeviceGuard guard(c);
+    for (cudaGraphExec_t e : c->graphs) if (e) cudaGraphExecDestroy(e);
+    c->graphs.clear();
 }
 
 static void post_launch(const char *what) {
@@ -635,6 +676,8 @@ __global__ void __launch_bounds__(256) random_actions_kernel(const EngineDev *gE
     const AgentSoA &s = E.grp[g].soa[(curmask >> g) & 1u];
     const unsigned na = (unsigned)E.grp[g].n_action;
     n_total = min(n_total, off[E.A]);
+    // the device-side step counter rides in the seed: a replayed CUDA graph (same kernel arguments) still draws fresh actions
+    seed += (unsigned long long)E.counters[CNT_STEPS] * 0xA24BAED4963EE407ull;
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_total; o += gridDim.x * blockDim.x) {
         int a = E.A == 1 ? 0 : locate_arena(off, E.A, o);
         long gi = (long)a * E.grp[g].cap + (o - off[a]);
@@ -749,6 +792,7 @@ void launch_obs_prepare(Ctx *c, const EngineDev *dE, const EngineDev &hE, unsign
     c->mm_stride = (hE.G * cells + 3) & ~3;
     const size_t need = (size_t)hE.A * c->mm_stride;
     if (need > c->mm_pad_n) {
+        no_capture(c, "growing the minimap buffer");
         if (c->mm_pad) { CUDA_CHECK(cudaStreamSynchronize(c->stream)); CUDA_CHECK(cudaStreamSynchronize(c->copy)); cudaFree(c->mm_pad); }
         CUDA_CHECK(cudaMalloc(&c->mm_pad, need * sizeof(float)));
         CUDA_CHECK(cudaMemsetAsync(c->mm_pad, 0, need * sizeof(float), c->stream));
@@ -1250,6 +1294,7 @@ static void launch_obs_typed(Ctx *c, int cfg_slot, const EngineDev &hE, ObsParam
     if (smem > 227 * 1024) mg::fatal("observation record too large for the render kernel (%zu bytes of shared memory)", smem);
     const int tiles = (n_total + TA - 1) / TA;
     if ((size_t)n_total > c->obs_hdr_n) {                                // scratch owned by the context: per-agent headers
+        no_capture(c, "growing the observation header table");
         if (c->obs_hdr) { CUDA_CHECK(cudaStreamSynchronize(c->stream)); cudaFree(c->obs_hdr); }
         c->obs_hdr_n = (size_t)n_total + n_total / 4 + 64;
         CUDA_CHECK(cudaMalloc(&c->obs_hdr, c->obs_hdr_n * sizeof(int4)));
@@ -1279,10 +1324,11 @@ static void launch_obs_typed(Ctx *c, int cfg_slot, const EngineDev &hE, ObsParam
     const int max_chunk = sizeof(T) == 2 ? 2 * OBS_CHUNK : OBS_CHUNK;   // f16 tiles are rebuilt for 8 observers at once: longer chunks pay (measured)
     if (P.chunk > max_chunk) P.chunk = max_chunk;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (c->profile) { profile_pair(c, &e0, &e1); CUDA_CHECK(cudaEventRecord(e0, c->stream)); }
+    const bool timed = c->profile && !c->capturing;
+    if (timed) { profile_pair(c, &e0, &e1); CUDA_CHECK(cudaEventRecord(e0, c->stream)); }
     obs_render_kernel<T, NIT, TURN><<<grid, THREADS, smem, c->stream>>>(P);
     post_launch("obs_render_kernel");
-    if (c->profile) CUDA_CHECK(cudaEventRecord(e1, c->stream));
+    if (timed) CUDA_CHECK(cudaEventRecord(e1, c->stream));
 }
 
 static void fill_obs_params(Ctx *c, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total, ObsParams &P) {
@@ -1347,6 +1393,7 @@ __global__ void __launch_bounds__(256) done_reduce_kernel(const EngineDev *gE, i
 }
 
 void read_done(Ctx *c, const EngineDev &hE, int *done_words) {
+    no_capture(c, "env_step with a host `done`");
     DeviceGuard guard(c);
     if ((size_t)hE.A > c->pin_done_n) {
         if (c->pin_done) cudaFreeHost(c->pin_done);
@@ -1359,6 +1406,7 @@ void read_done(Ctx *c, const EngineDev &hE, int *done_words) {
 }
 
 void counts_fetch_begin(Ctx *c, const int *dev_off, size_t n_ints) {
+    no_capture(c, "the asynchronous count fetch");
     DeviceGuard guard(c);
     if (n_ints > c->pin_counts_n) {
         if (c->pin_counts) { CUDA_CHECK(cudaStreamSynchronize(c->stream)); cudaFreeHost(c->pin_counts); }
@@ -1529,6 +1577,7 @@ static void grow_pinned(Ctx *c, T *&p, size_t &have, size_t need) {
 
 void obs_wire_begin(Ctx *c, const EngineDev *, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total,
                     bool want_dense, WireDesc *out) {
+    no_capture(c, "an observation into host memory");
     DeviceGuard guard(c);
     ObsParams P;
     fill_obs_params(c, hE, O, mm_val, n_total, P);

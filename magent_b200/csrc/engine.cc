@@ -162,7 +162,8 @@ void Engine::set_config(const char *key, void *p_value) {     // GridWorld.cc:12
         arenas_.assign(A_, HostArena());
         for (int a = 0; a < A_; ++a) arenas_[a].rng = a == 0 ? seed0 : minstd_seed(a);
     } else if (strequ(key, "device_id")) device_id_ = ivalue;
-    else if (strequ(key, "host_path")) host_path_ = ivalue ? 1 : 0;       // 1 wire records + host expansion (default), 0 dense DMA
+    else if (strequ(key, "host_path")) host_path_ = ivalue;               // 1 wire records + host expansion (default for large
+                                                                           // observations), 0 dense DMA, 2 wire whatever the size
     else fatal("invalid argument in GridWorld::set_config : %s", key);
 }
 
@@ -916,7 +917,9 @@ void Engine::get_observation(int group, void **bufs, int half) {      // GridWor
         const char *e = getenv("MAGENT_B200_HOST_PATH");
         host_path_ = (e && !strcmp(e, "dense")) ? 0 : 1;
     }
-    if (!vdev && !fdev && !half && host_path_ == 1 && t.view.height * t.view.width < 0xffff &&
+    // small observations (a few MB) are latency-, not bandwidth-bound: one plain copy of the dense records beats the
+    // wire protocol's fixed costs (totals read-back, waves, waking the pool)
+    if (!vdev && !fdev && !half && (host_path_ == 2 || (host_path_ == 1 && vbytes >= ((size_t)16 << 20))) && t.view.height * t.view.width < 0xffff &&
         (long long)t.view.height * t.view.width * n_channel() < (1ll << 30)) {
         get_observation_wire(group, bufs);
         return;
@@ -1054,11 +1057,19 @@ void Engine::clear_dead() {                                           // GridWor
     // numbers (settle_counts), h_off_ holds the previous counts -- upper bounds, since a cull only removes agents --
     // and the kernels clamp to the device-side totals (EngineDev::off).
     be::launch_offsets(bx_, dE_, hE_);
+    if (be::capturing(bx_)) { ++capture_culls_; counts_unknown_ = true; return; }      // no read-back inside a graph
     be::counts_fetch_begin(bx_, hE_.off, h_off_.size());
     counts_pending_ = true;
 }
 
 void Engine::settle_counts() {
+    if (counts_unknown_ && !be::capturing(bx_)) {     // graphs advanced the state: read the offset table the last cull left
+        counts_unknown_ = false;
+        counts_pending_ = false;
+        be::d2h(bx_, h_off_.data(), hE_.off, h_off_.size() * 4);
+        io_[IO_D2H] += (long long)h_off_.size() * 4;
+        return;
+    }
     if (!counts_pending_) return;
     memcpy(h_off_.data(), be::counts_fetch_wait(bx_), h_off_.size() * sizeof(int));
     io_[IO_D2H] += (long long)h_off_.size() * 4;
@@ -1201,6 +1212,25 @@ void Engine::render() {                               // GridWorld.cc:939-949
 }
 
 void Engine::sync() { if (bx_) be::sync(bx_); }
+void Engine::graph_begin() {
+    to_device();
+    settle_counts();
+    if (!first_render_) fatal("graph capture while rendering is not supported");
+    capture_mask_ = curmask_; capture_culls_ = 0;
+    if (!be::capture_begin(bx_)) fatal("this backend has no CUDA graph support");
+}
+int Engine::graph_end() {
+    const int id = be::capture_end(bx_);
+    // kernel arguments are baked into the graph, the ping-pong buffer selector among them: a replay is only right when
+    // the captured sequence leaves the selector where it found it (an even number of clear_dead calls)
+    if (curmask_ != capture_mask_) fatal("a captured step sequence must contain an even number of clear_dead calls (got %d)", capture_culls_);
+    return id;
+}
+void Engine::graph_launch(int id, int times) {
+    to_device();
+    for (int k = 0; k < times; ++k) be::graph_launch(bx_, id);
+    if (times > 0) { ++state_version_; counts_unknown_ = true; counts_pending_ = false; may_have_dead_ = true; done_stale_ = true; }
+}
 void Engine::get_io_stats(long long *out, int cap) { for (int i = 0; i < cap && i < 3; ++i) out[i] = io_[i]; }
 void *Engine::stream() { ensure_backend(); return be::stream_handle(bx_); }
 void Engine::set_profiling(bool on) { ensure_backend(); be::profile_enable(bx_, on); }

@@ -99,6 +99,10 @@ public:
     int get_counters(long long *out, int cap);
     void sync();
     void get_io_stats(long long *out, int cap);      // bytes so far: device->host over PCIe, host->device, written by host threads
+    // CUDA graphs for launch-bound workloads: the device-pointer calls between begin and end become one graph
+    void graph_begin();
+    int graph_end();
+    void graph_launch(int id, int times);
     void *stream();                      // cudaStream_t of this engine's kernels (nullptr before the first device call)
     void set_profiling(bool on);
     void get_profile(double *ms, long long *n);
@@ -167,6 +171,8 @@ private:
     int total(int g) const { return h_off_[(size_t)g * (A_ + 1) + A_]; }
     int count(int g, int a) const { return h_off_[(size_t)g * (A_ + 1) + a + 1] - h_off_[(size_t)g * (A_ + 1) + a]; }
     void refresh_host_counts();
+    bool counts_unknown_ = false;       // steps ran inside replayed graphs: the device's offset table is ahead of h_off_
+    unsigned capture_mask_ = 0; int capture_culls_ = 0;
     bool counts_pending_ = false;       // clear_dead queued a fetch of the new counts; h_off_ still holds the old (upper-bound) ones
     void settle_counts();
     void check_group(int g, const char *where) const;

@@ -123,7 +123,9 @@ class GridWorld(Environment):
         if host_path is not None:
             if not L.is_b200:
                 raise ValueError("_host_path needs the B200 engine library")
-            L.env_config_game(game, b"host_path", _cint(0 if host_path == "dense" else 1))
+            # "dense": dense records over PCIe; "wire": wire records + host expansion whatever the size; default: wire for
+            # observations of 16 MB and more, dense below
+            L.env_config_game(game, b"host_path", _cint({"dense": 0, "wire": 2, "auto": 1}[host_path]))
 
         for key, value in config.config_dict.items():
             kind = self._CONFIG_TYPES[key]
@@ -468,6 +470,16 @@ class GridWorld(Environment):
         buf = (ctypes.c_longlong * 3)()
         self._lib.magent_b200_get_io_stats(self.game, buf, 3)
         return {"d2h": int(buf[0]), "h2d": int(buf[1]), "host_written": int(buf[2])}
+
+    def capture_graph(self, fn):
+        """record the step-loop calls fn() makes (CUDA device pointers only, an even number of clear_dead) into a CUDA
+        graph; returns its id for launch_graph"""
+        self._lib.magent_b200_graph_begin(self.game)
+        fn()
+        return int(self._lib.magent_b200_graph_end(self.game))
+
+    def launch_graph(self, graph_id, times=1):
+        self._lib.magent_b200_graph_launch(self.game, int(graph_id), int(times))
 
     def step_device_done(self, done_ptr):
         """env_step with a CUDA device int for `done`: returns without waiting for the step (device-resident loops)"""

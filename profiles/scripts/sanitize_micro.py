@@ -6,6 +6,8 @@ shuffle / mover storage) at least once.  Usage:
 import os
 import sys
 
+os.environ.setdefault("OMP_NUM_THREADS", "1")      # the compiled reference is deterministic only single-threaded
+
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))

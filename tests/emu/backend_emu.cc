@@ -256,6 +256,12 @@ void dense_ready_wait(Ctx *) {}
 void dma_d2h_async(Ctx *, void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
 void dma_wait(Ctx *, int) {}
 
+bool capture_begin(Ctx *) { return false; }       // no graphs in the emulation
+int capture_end(Ctx *) { return -1; }
+bool capturing(const Ctx *) { return false; }
+void graph_launch(Ctx *, int) {}
+void graph_destroy_all(Ctx *) {}
+
 long long launch_count() { return 0; }
 void profile_enable(Ctx *, bool) {}
 void profile_read(Ctx *, double *ms, long long *n) { *ms = 0; *n = 0; }

@@ -508,3 +508,81 @@ def test_device_done_and_deferred_counts():
         rv, rf = ref.get_observation(rh)
         np.testing.assert_array_equal(v.view(np.uint32), rv.view(np.uint32))
         np.testing.assert_array_equal(f.view(np.uint32), rf.view(np.uint32))
+
+
+def test_replayed_cuda_graph_of_two_steps_matches_the_reference():
+    """magent_b200_graph_*: two whole steps (observations, actions, step, rewards, clear_dead; device buffers only) recorded
+    once and replayed; the caller refills its action buffers between replays.  State after every replay == the reference."""
+    import ctypes
+    torch = pytest.importorskip("torch")
+    from magent_b200.c_lib import load_library
+    L = load_library(pc.CUDA_LIB)
+    env = pc.make_battle(pc.CUDA_LIB, 30, 300, 3)
+    ref = pc.make_battle(checker_lib(), 30, 300, 3)
+    hs, rhs = env.get_handles(), ref.get_handles()
+    dev = "cuda"
+    n0 = [env.get_num(h) for h in hs]
+    obs = [(torch.empty((n,) + env.get_view_space(h), dtype=torch.float32, device=dev),
+            torch.empty((n,) + env.get_feature_space(h), dtype=torch.float32, device=dev)) for h, n in zip(hs, n0)]
+    acts = [[torch.zeros((n,), dtype=torch.int32, device=dev) for n in n0] for _ in range(2)]     # even / odd step
+    rew = [[torch.zeros((n,), dtype=torch.float32, device=dev) for n in n0] for _ in range(2)]
+    done = torch.zeros((2,), dtype=torch.int32, device=dev)
+
+    def one(k):
+        for h, (v, f) in zip(hs, obs):
+            L.env_get_observation(env.game, env._hv(h), (ctypes.c_void_p * 2)(v.data_ptr(), f.data_ptr()))
+        for h, a in zip(hs, acts[k]):
+            L.env_set_action(env.game, env._hv(h), a.data_ptr())
+        env.step_device_done(done.data_ptr() + 4 * k)
+        for h, r in zip(hs, rew[k]):
+            L.env_get_reward(env.game, env._hv(h), r.data_ptr())
+        env.clear_dead()
+
+    rs = np.random.RandomState(7)
+
+    def draw():
+        return [[rs.randint(0, 21, size=n).astype(np.int32) for n in n0] for _ in range(2)]
+
+    a = draw()
+    for k in range(2):                                   # one un-captured pair first: every buffer gets its size
+        for g in range(2):
+            acts[k][g].copy_(torch.from_numpy(a[k][g]))
+
+    def ref_pair(a):
+        out = []
+        for k in range(2):
+            nums = [ref.get_num(h) for h in rhs]
+            for h, x, n in zip(rhs, a[k], nums):
+                ref.set_action(h, np.ascontiguousarray(x[:n]))
+            d = ref.step()
+            out.append((d, [ref.get_reward(h).copy() for h in rhs], nums))
+            ref.clear_dead()
+        return out
+
+    one(0); one(1)
+    want = ref_pair(a)
+    gid = env.capture_graph(lambda: (one(0), one(1)))
+    for rep_i in range(25):
+        a = draw()
+        for k in range(2):
+            for g in range(2):
+                acts[k][g].copy_(torch.from_numpy(a[k][g]))
+        env.launch_graph(gid, 1)
+        want = ref_pair(a)
+        torch.cuda.synchronize()
+        for k in range(2):
+            assert bool(done[k].item()) == want[k][0]
+            for g in range(2):
+                n = want[k][2][g]
+                np.testing.assert_allclose(rew[k][g].cpu().numpy()[:n], want[k][1][g], rtol=0, atol=pc.REWARD_TOL)
+        if rep_i % 6 == 5:
+            for h, rh in zip(hs, rhs):
+                assert env.get_num(h) == ref.get_num(rh)
+                np.testing.assert_array_equal(env.get_agent_id(h), ref.get_agent_id(rh))
+                np.testing.assert_array_equal(env.get_pos(h), ref.get_pos(rh))
+    assert ref.get_num(rhs[0]) < 300                    # agents died and were culled inside the replays
+    for h, rh in zip(hs, rhs):
+        v, f = env.get_observation(h)
+        rv, rf = ref.get_observation(rh)
+        np.testing.assert_array_equal(v.view(np.uint32), rv.view(np.uint32))
+        np.testing.assert_array_equal(f.view(np.uint32), rf.view(np.uint32))
