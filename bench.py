@@ -304,7 +304,9 @@ def main():
     ap.add_argument("--e2e-seconds", type=float, default=1.5, help="the e2e loop runs at least this long (and >= 3 steps)")
     ap.add_argument("--host-path", default=None, choices=["wire", "dense"],
                     help="env_get_observation into host memory: wire records + host expansion (default) or the round-1 dense DMA")
-    ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--numa-bind", action="store_true",
+                    help="pin the rank to the NUMA node of its GPU (default: off -- the engine spreads its host threads and the "
+                         "wrapper's big receive buffers over all nodes, which doubles the host write bandwidth on two sockets)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="device-resident loop as a replayed CUDA graph of two steps (magent_b200_graph_*): auto = for "
                          "launch-bound workloads (fewer than 100k agents per GPU)")
@@ -367,7 +369,7 @@ def main():
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
-    numa = "off" if args.no_numa_bind else bind_to_gpu_numa_node(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if args.numa_bind else None
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -545,7 +547,8 @@ def main():
                        if (args.host_path or "wire") == "wire" and not half else "dense records over PCIe",
                "bytes_counted": "by the engine (magent_b200_get_io_stats): every byte it copies across PCIe / writes into caller buffers",
                "timing": "host wall clock around the API loop (includes PCIe copies, host expansion and syncs), max over ranks",
-               "host_buffers": "page-locked numpy arrays owned by the wrapper", "numa": numa}
+               "host_buffers": "page-locked numpy arrays owned by the wrapper",
+               "numa": numa or "%d node(s): receive buffers split over the nodes, host threads pinned per node" % int(lib.magent_b200_numa_nodes())}
 
     clocks = sampler.stop() if sampler else None      # sampled across the device-timed and the e2e timed regions
     if rank != 0:

@@ -15,9 +15,11 @@ int magent_b200_version(void);                 /* 1000*major + minor */
 const char *magent_b200_last_error(void);
 int magent_b200_device_count(void);            /* 0 when no CUDA device is visible */
 
-/* page-locked host memory for observation / reward receive buffers (PCIe-speed copies) */
+/* page-locked host memory for observation / reward receive buffers.  Blocks of 64 MB and more on a multi-socket host are
+ * split over the NUMA nodes (each part resident on its node and written by that node's threads in env_get_observation). */
 void *magent_b200_host_alloc(size_t bytes);
 int magent_b200_host_free(void *p);
+int magent_b200_numa_nodes(void);              /* NUMA nodes the host threads are spread over (1 = not NUMA) */
 
 int magent_b200_sync(EnvHandle game);          /* wait for all queued device work of this game */
 /* env_step(game, done) also accepts a CUDA device pointer for `done`: the flag is written on the device and the call

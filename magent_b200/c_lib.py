@@ -74,6 +74,7 @@ EXT_SIGNATURES = {
     "magent_b200_graph_launch": ([_vp, ctypes.c_int, ctypes.c_int], ctypes.c_int),
     "magent_b200_get_io_stats": ([_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int], ctypes.c_int),
     "magent_b200_host_threads": ([], ctypes.c_int),
+    "magent_b200_numa_nodes": ([], ctypes.c_int),
     "magent_b200_set_host_threads": ([ctypes.c_int], ctypes.c_int),
     "magent_b200_launch_count": ([], ctypes.c_longlong),
 }

@@ -35,6 +35,8 @@ void d2h(Ctx *, void *dst, const void *src, size_t bytes);          // blocking
 void d2d(Ctx *, void *dst, const void *src, size_t bytes);
 void *host_alloc(size_t bytes);          // page-locked
 void host_free(void *p);
+bool host_register(void *p, size_t bytes);   // page-lock existing host memory (DMA target); false when not possible
+void host_unregister(void *p);
 bool is_device_ptr(const void *p);
 bool is_pinned_host_ptr(const void *p);  // page-locked host memory known to the CUDA driver (DMA target)
 void sync(Ctx *);
@@ -82,13 +84,15 @@ struct WireDesc {
     const float *mm;                     // [A][mm_stride] normalised minimap rows, or nullptr
     int mm_stride;
     int n_total, n_chunks;
-    int n_waves, chunks_per_wave;        // the staging fills wave by wave (obs_wire_wait)
+    int n_waves, chunks_per_wave;        // the staging fills wave by wave (obs_wire_wait): wave w = chunks [w * cpw, (w + 1) * cpw)
+    int wave_order[16];                  // the order the waves were queued in (front and back half alternate, so that the
+                                         // threads of every NUMA part of the caller's buffer find work early)
 };
 // Launch the wire kernels for observation O (O.view = device staging for the dense records, rendered as well when
 // want_dense), read the totals back and queue the device->host copies of headers and marks, wave by wave.
 void obs_wire_begin(Ctx *, const EngineDev *dE, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total,
                     bool want_dense, WireDesc *out);
-void obs_wire_wait(Ctx *, int wave);     // returns once wave `wave` (and all before it) is in host memory
+void obs_wire_wait(Ctx *, int wave);     // returns once wave `wave` is in host memory
 // DMA of finished dense records (device staging -> page-locked caller memory) on the context's copy stream
 void dense_ready_wait(Ctx *);            // copy stream waits for the dense render queued by obs_wire_begin
 void dma_d2h_async(Ctx *, void *dst, const void *src, size_t bytes);

@@ -188,6 +188,11 @@ void *host_alloc(size_t bytes) {
     return p;
 }
 void host_free(void *p) { if (p) cudaFreeHost(p); }
+bool host_register(void *p, size_t bytes) {
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return false; }
+    return true;
+}
+void host_unregister(void *p) { if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError(); }
 bool is_device_ptr(const void *p) {
     if (!p) return false;
     cudaPointerAttributes at;
@@ -1636,7 +1641,10 @@ void obs_wire_begin(Ctx *c, const EngineDev *, const EngineDev &hE, const ObsArg
     while ((int)c->wave_events.size() < n_waves) {
         cudaEvent_t e; CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->wave_events.push_back(e);
     }
-    for (int w = 0; w < n_waves; ++w) {
+    for (int q = 0; q < n_waves; ++q) {
+        const int half = (n_waves + 1) / 2;
+        const int w = (q & 1) ? half + (q >> 1) : (q >> 1);             // 0, half, 1, half + 1, ...
+        out->wave_order[q] = w;
         const int c0 = w * cpw, c1 = (c0 + cpw < n_chunks) ? c0 + cpw : n_chunks;
         const size_t o0 = (size_t)c0 * WIRE_CHUNK, o1 = (size_t)c1 * WIRE_CHUNK < (size_t)n_total ? (size_t)c1 * WIRE_CHUNK : (size_t)n_total;
         CUDA_CHECK(cudaMemcpyAsync(c->h_wire_hdr + o0, c->wire_hdr + o0, (o1 - o0) * sizeof(WireHdr), cudaMemcpyDeviceToHost, c->copy));
@@ -1652,7 +1660,6 @@ void obs_wire_begin(Ctx *c, const EngineDev *, const EngineDev &hE, const ObsArg
 
 void obs_wire_wait(Ctx *c, int wave) {
     DeviceGuard guard(c);
-    if (wave == 0) CUDA_CHECK(cudaStreamSynchronize(c->stream) == cudaSuccess ? cudaSuccess : cudaGetLastError());
     CUDA_CHECK(cudaEventSynchronize(c->wave_events[wave]));
 }
 

@@ -8,6 +8,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <unistd.h>
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <mutex>
@@ -56,6 +59,72 @@ int host_threads() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// NUMA topology from sysfs (no libnuma in the image): the nodes that own CPUs, and their CPU sets
+namespace {
+struct Topo {
+    std::vector<cpu_set_t> node_cpus;    // one entry per node that has CPUs
+    std::vector<int> cpu_node;           // cpu -> index into node_cpus, -1 unknown
+};
+const Topo &topo() {
+    static const Topo t = []() {
+        Topo T;
+        if (const char *e = getenv("MAGENT_B200_NUMA")) { if (!strcmp(e, "off") || !strcmp(e, "0")) return T; }
+        if (const char *e = getenv("MAGENT_B200_NUMA_FAKE")) {       // tests on one-node hosts: n pretend nodes over the same CPUs
+            const int n = atoi(e);
+            if (n >= 2 && n <= 8) {
+                cpu_set_t all; CPU_ZERO(&all);
+                if (sched_getaffinity(0, sizeof all, &all) != 0) return T;
+                for (int k = 0; k < n; ++k) T.node_cpus.push_back(all);
+                for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &all)) { if ((int)T.cpu_node.size() <= c) T.cpu_node.resize(c + 1, -1); T.cpu_node[c] = c % n; }
+                return T;
+            }
+        }
+        for (int node = 0; node < 64; ++node) {
+            char path[96];
+            snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+            FILE *f = fopen(path, "r");
+            if (!f) continue;
+            char buf[4096];
+            cpu_set_t set; CPU_ZERO(&set);
+            int any = 0;
+            if (fgets(buf, sizeof buf, f)) {
+                for (char *tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+                    int lo = 0, hi = 0;
+                    const int k = sscanf(tok, "%d-%d", &lo, &hi);
+                    if (k < 1) continue;
+                    if (k == 1) hi = lo;
+                    for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c) { CPU_SET(c, &set); any = 1; }
+                }
+            }
+            fclose(f);
+            if (!any) continue;
+            const int idx = (int)T.node_cpus.size();
+            T.node_cpus.push_back(set);
+            for (int c = 0; c < CPU_SETSIZE; ++c)
+                if (CPU_ISSET(c, &set)) { if ((int)T.cpu_node.size() <= c) T.cpu_node.resize(c + 1, -1); T.cpu_node[c] = idx; }
+        }
+        if (T.node_cpus.size() < 2) { T.node_cpus.clear(); T.cpu_node.clear(); }
+        return T;
+    }();
+    return t;
+}
+// node a pool thread belongs to: workers alternate over the nodes (and pin themselves there); the calling thread (tid 0)
+// stays wherever the caller put it
+int node_of_tid(int tid) {
+    const Topo &T = topo();
+    const int n = (int)T.node_cpus.size();
+    if (n < 2) return 0;
+    if (tid == 0) {
+        const int cpu = sched_getcpu();
+        return (cpu >= 0 && cpu < (int)T.cpu_node.size() && T.cpu_node[cpu] >= 0) ? T.cpu_node[cpu] : 0;
+    }
+    return tid % n;
+}
+}  // namespace
+
+int numa_nodes() { const int n = (int)topo().node_cpus.size(); return n < 2 ? 1 : n; }
+
+// ---------------------------------------------------------------------------------------------
 // worker pool: threads are created on first use and live for the life of the process (never joined: the
 // pool object is intentionally leaked so that no destructor races with a worker at exit)
 namespace {
@@ -70,6 +139,10 @@ struct Pool {
     std::vector<std::thread> workers;    // worker k has tid k + 1
 
     void worker(int tid) {
+        if (numa_nodes() > 1) {             // stay on one node: the chunks dealt to this thread live in that node's memory
+            const cpu_set_t &set = topo().node_cpus[node_of_tid(tid)];
+            pthread_setaffinity_np(pthread_self(), sizeof(cpu_set_t), &set);      // best effort (a cpuset may forbid it)
+        }
         unsigned long seen = 0;
         for (;;) {
             const std::function<void(int)> *f = nullptr;
@@ -175,6 +248,72 @@ inline void stream_out(char *d, const char *s, size_t n) {
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// NUMA-split blocks
+namespace {
+struct SplitBlock { char *base; size_t bytes; int parts; size_t part_bytes; };
+std::mutex g_split_mu;
+std::vector<SplitBlock> g_split;
+bool split_lookup(const void *p, SplitBlock *out) {
+    std::lock_guard<std::mutex> lk(g_split_mu);
+    for (const SplitBlock &b : g_split)
+        if ((const char *)p >= b.base && (const char *)p < b.base + b.bytes) { *out = b; return true; }
+    return false;
+}
+}  // namespace
+
+void *numa_split_alloc(size_t bytes) {
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    const size_t len = (bytes + page - 1) / page * page;
+    void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return nullptr;
+    const int parts = numa_nodes();
+    SplitBlock b;
+    b.base = (char *)p; b.bytes = len; b.parts = parts;
+    b.part_bytes = parts > 1 ? ((len / parts + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1)) : len;    // 2 MB-aligned parts
+    if (b.part_bytes == 0 || b.part_bytes > len) b.part_bytes = len;
+    // first touch decides where a page lives: every part is zeroed by the pool threads of its node
+    int T = host_threads();
+    if (T < parts) T = parts;
+    const size_t piece = (size_t)4 << 20;
+    std::vector<std::atomic<size_t>> next(parts);
+    for (auto &x : next) x.store(0);
+    host_parallel(T, [&](int tid) {
+        const int node = parts > 1 ? node_of_tid(tid) % parts : 0;
+        const size_t lo = (size_t)node * b.part_bytes, hi = std::min(len, lo + b.part_bytes);
+        for (;;) {
+            const size_t o = lo + next[node].fetch_add(piece);
+            if (o >= hi) break;
+            memset(b.base + o, 0, std::min(piece, hi - o));
+        }
+    });
+    // a node without a thread (very few threads) leaves its part untouched: it is zero anyway (anonymous mapping)
+    {
+        std::lock_guard<std::mutex> lk(g_split_mu);
+        g_split.push_back(b);
+    }
+    return p;
+}
+
+bool numa_split_free(void *p) {
+    SplitBlock b;
+    {
+        std::lock_guard<std::mutex> lk(g_split_mu);
+        auto it = std::find_if(g_split.begin(), g_split.end(), [&](const SplitBlock &x) { return x.base == (char *)p; });
+        if (it == g_split.end()) return false;
+        b = *it;
+        g_split.erase(it);
+    }
+    munmap(b.base, b.bytes);
+    return true;
+}
+
+size_t numa_split_size(const void *p) {
+    std::lock_guard<std::mutex> lk(g_split_mu);
+    for (const SplitBlock &b : g_split) if (b.base == (const char *)p) return b.bytes;
+    return 0;
+}
+
 void parallel_copy(void *dst, const void *src, size_t bytes) {
     const size_t piece = (size_t)1 << 20;
     const size_t n_pieces = (bytes + piece - 1) / piece;
@@ -261,8 +400,30 @@ void expand_chunk(const ExpandGeom &g, const be::WireDesc &W, float *out, int ch
 void expand_views(const ExpandGeom &geom, const be::WireDesc &W, float *out, const std::function<void(int)> &wait_wave) {
     int T = host_threads();
     if (T > W.n_chunks) T = W.n_chunks > 0 ? W.n_chunks : 1;
-    std::atomic<int> next{0};
-    std::atomic<int> waves_ready{0};
+    // chunk ranges per NUMA part of the caller's buffer (one range when the buffer is not a numa_split_alloc block):
+    // part k holds the chunks whose first byte lies in it
+    const size_t rec_bytes = (size_t)geom.rec * sizeof(float), chunk_bytes = rec_bytes * be::WIRE_CHUNK;
+    int n_parts = 1;
+    int part_lo[64], part_hi[64];
+    part_lo[0] = 0; part_hi[0] = W.n_chunks;
+    SplitBlock blk;
+    if (numa_nodes() > 1 && T > 1 && split_lookup(out, &blk) && blk.parts > 1) {
+        n_parts = blk.parts;
+        const size_t off0 = (size_t)((const char *)out - blk.base);
+        int c = 0;
+        for (int k = 0; k < n_parts; ++k) {
+            part_lo[k] = c;
+            const size_t end = (size_t)(k + 1) * blk.part_bytes;              // first byte of the next part
+            while (c < W.n_chunks && off0 + (size_t)c * chunk_bytes < end) ++c;
+            if (k == n_parts - 1) c = W.n_chunks;
+            part_hi[k] = c;
+        }
+    }
+    std::atomic<int> next[64];
+    for (int k = 0; k < n_parts; ++k) next[k].store(part_lo[k]);
+    std::atomic<int> wave_ready[16];
+    for (int w = 0; w < 16; ++w) wave_ready[w].store(0);
+    int fetched = 0;                         // single-thread mode: waves fetched so far (in queue order)
     auto work = [&](int tid) {
         Scratch s;
         void *mem = nullptr;
@@ -271,18 +432,22 @@ void expand_views(const ExpandGeom &geom, const be::WireDesc &W, float *out, con
         if (tid == 0 && T == 1) {            // a single thread has to fetch the waves itself, in step with its work
             for (int c = 0; c < W.n_chunks; ++c) {
                 const int w = c / W.chunks_per_wave;
-                while (waves_ready.load(std::memory_order_relaxed) <= w) { wait_wave(waves_ready.load()); waves_ready.fetch_add(1); }
+                while (!wave_ready[w].load(std::memory_order_relaxed)) { const int q = W.wave_order[fetched++]; wait_wave(q); wave_ready[q].store(1); }
                 expand_chunk(geom, W, out, c, s);
             }
         } else {
             if (tid == 0)                     // the calling thread owns the CUDA side: it announces the waves as they land
-                for (int w = 0; w < W.n_waves; ++w) { wait_wave(w); waves_ready.store(w + 1, std::memory_order_release); }
-            for (;;) {
-                const int c = next.fetch_add(1);
-                if (c >= W.n_chunks) break;
-                const int w = c / W.chunks_per_wave;
-                while (waves_ready.load(std::memory_order_acquire) <= w) { for (int i = 0; i < 32; ++i) _mm_pause(); }
-                expand_chunk(geom, W, out, c, s);
+                for (int q = 0; q < W.n_waves; ++q) { const int w = W.wave_order[q]; wait_wave(w); wave_ready[w].store(1, std::memory_order_release); }
+            const int home = n_parts > 1 ? node_of_tid(tid) % n_parts : 0;
+            for (int turn = 0; turn < n_parts; ++turn) {       // own part first, then help the others (remote writes)
+                const int k = (home + turn) % n_parts;
+                for (;;) {
+                    const int c = next[k].fetch_add(1);
+                    if (c >= part_hi[k]) break;
+                    const int w = c / W.chunks_per_wave;
+                    while (!wave_ready[w].load(std::memory_order_acquire)) { for (int i = 0; i < 32; ++i) _mm_pause(); }
+                    expand_chunk(geom, W, out, c, s);
+                }
             }
         }
         _mm_sfence();

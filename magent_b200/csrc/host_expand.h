@@ -33,6 +33,16 @@ void host_parallel(int n_threads, const std::function<void(int)> &fn);
 // host memory; it is called from the calling thread only, for w = 0 .. n_waves-1 in order.
 void expand_views(const ExpandGeom &geom, const be::WireDesc &W, float *out, const std::function<void(int)> &wait_wave);
 
+// ---- NUMA: one socket's memory controllers take ~200 GB/s of streamed writes; a two-socket host takes twice that if each
+// half of a buffer lives on its own node and is written by threads of that node.
+int numa_nodes();                        // nodes with CPUs this process may use (1 when the host is not NUMA)
+// `bytes` of zeroed, page-aligned host memory whose k-th part (of numa_nodes() equal parts) was first touched -- and is
+// therefore resident -- on node k.  expand_views() recognises pointers into such a block and deals the chunks of a part
+// to the threads pinned to its node.  nullptr when the mapping fails.
+void *numa_split_alloc(size_t bytes);
+bool numa_split_free(void *p);           // false when p is not a block of numa_split_alloc
+size_t numa_split_size(const void *p);   // 0 when p is not the base of such a block
+
 // dst[0, bytes) = src[0, bytes) with all pool threads (non-temporal stores)
 void parallel_copy(void *dst, const void *src, size_t bytes);
 

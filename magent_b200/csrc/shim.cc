@@ -78,8 +78,24 @@ MG_API int discrete_snake_add_object(EnvHandle, int, int, const char *, const in
 MG_API int magent_b200_version(void) { return 1000 * 0 + 1; }
 MG_API const char *magent_b200_last_error(void) { return mg::last_error(); }
 MG_API int magent_b200_device_count(void) { return mg::be::device_count(); }
-MG_API void *magent_b200_host_alloc(size_t bytes) { return mg::be::device_count() > 0 ? mg::be::host_alloc(bytes) : nullptr; }
-MG_API int magent_b200_host_free(void *p) { mg::be::host_free(p); return 0; }
+// Receive buffers for observations.  Large ones on a multi-socket host are split over the NUMA nodes (one part per node,
+// written by that node's threads: host_expand.h) and page-locked in place; everything else is plain page-locked memory.
+MG_API void *magent_b200_host_alloc(size_t bytes) {
+    if (mg::be::device_count() <= 0) return nullptr;
+    if (bytes >= ((size_t)64 << 20) && mg::numa_nodes() > 1) {
+        if (void *p = mg::numa_split_alloc(bytes)) {
+            mg::be::host_register(p, mg::numa_split_size(p));
+            return p;
+        }
+    }
+    return mg::be::host_alloc(bytes);
+}
+MG_API int magent_b200_host_free(void *p) {
+    if (mg::numa_split_size(p)) { mg::be::host_unregister(p); mg::numa_split_free(p); return 0; }
+    mg::be::host_free(p);
+    return 0;
+}
+MG_API int magent_b200_numa_nodes(void) { return mg::numa_nodes(); }
 MG_API int magent_b200_sync(EnvHandle game) { E(game)->sync(); return 0; }
 MG_API int magent_b200_select_arena(EnvHandle game, int arena) { E(game)->select_arena(arena); return 0; }
 MG_API int magent_b200_random_actions(EnvHandle game, GroupHandle group, void *, unsigned long long seed) {

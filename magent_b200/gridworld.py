@@ -50,7 +50,9 @@ class _HostBlock:
 
     def _grow(self, nbytes):
         self.release()
-        cap = int(nbytes * 1.25) + 64
+        # populations only shrink between resets: little slack for the big observation buffers (which a multi-socket host
+        # splits evenly over its NUMA nodes), room to grow for the small ones
+        cap = int(nbytes * (1.02 if nbytes >= (64 << 20) else 1.25)) + 64
         if self._lib.is_b200:
             ptr = self._lib.magent_b200_host_alloc(cap)
             if ptr:

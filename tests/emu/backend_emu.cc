@@ -57,6 +57,8 @@ void d2h(Ctx *, void *d, const void *s, size_t n) { memcpy(d, s, n); }
 void d2d(Ctx *, void *d, const void *s, size_t n) { memcpy(d, s, n); }
 void *host_alloc(size_t b) { return malloc(b ? b : 1); }
 void host_free(void *p) { free(p); }
+bool host_register(void *, size_t) { return false; }
+void host_unregister(void *) {}
 bool is_device_ptr(const void *) { return false; }
 bool is_pinned_host_ptr(const void *) { return false; }
 void sync(Ctx *) {}
@@ -249,7 +251,9 @@ void obs_wire_begin(Ctx *c, const EngineDev *dE, const EngineDev &, const ObsArg
     out->hdr = c->hdr.data(); out->marks = c->marks.data(); out->chunk_base = c->base.data();
     out->mm = mm_val ? c->mm.data() : nullptr; out->mm_stride = mm_val ? mm_stride : 0;
     out->n_total = n_total; out->n_chunks = n_chunks;
-    out->chunks_per_wave = 2; out->n_waves = (n_chunks + 1) / 2;
+    out->chunks_per_wave = (n_chunks + 7) / 8 < 2 ? 2 : (n_chunks + 7) / 8;
+    out->n_waves = (n_chunks + out->chunks_per_wave - 1) / out->chunks_per_wave;
+    for (int q = 0; q < out->n_waves; ++q) { const int half = (out->n_waves + 1) / 2; out->wave_order[q] = (q & 1) ? half + (q >> 1) : (q >> 1); }
 }
 void obs_wire_wait(Ctx *, int) {}
 void dense_ready_wait(Ctx *) {}

@@ -121,3 +121,43 @@ def test_caller_buffers_of_any_alignment(emu, shift):
         assert (raw_f[:base_f] == 0xCD).all() and (raw_f[base_f + nf * 4:] == 0xCD).all()
     finally:
         L.magent_b200_set_host_threads(0)
+
+
+def test_numa_split_buffers_with_pretend_nodes(emu):
+    """MAGENT_B200_NUMA_FAKE=2 (a subprocess: the topology is read once): the wrapper's big receive buffers come from
+    numa_split_alloc, chunks are dealt per part, threads help the other part when theirs is done -- same bytes"""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import magent_b200 as magent
+from magent_b200.c_lib import load_library
+L = load_library(%r)
+assert L.magent_b200_numa_nodes() == 2
+L.magent_b200_set_host_threads(5)
+p = L.magent_b200_host_alloc(80 << 20)
+assert p
+L.magent_b200_host_free(p)
+envs = []
+for path in ("wire", "dense"):
+    env = magent.GridWorld("battle", map_size=40, _lib=L.path, _num_arenas=100, _host_path=path)
+    env.set_seed(2); env.reset()
+    for h in env.get_handles(): env.add_agents(h, method="random", n=150)
+    envs.append(env)
+rs = np.random.RandomState(1)
+for t in range(3):
+    acts = [rs.randint(0, 21, size=envs[0].get_num(h)).astype(np.int32) for h in envs[0].get_handles()]
+    obs = []
+    for env in envs:
+        hs = env.get_handles()
+        obs.append([tuple(x.copy() for x in env.get_observation(h)) for h in hs])
+        for h, a in zip(hs, acts): env.set_action(h, a)
+        env.step(); env.clear_dead()
+    for (v0, f0), (v1, f1) in zip(obs[0], obs[1]):
+        assert v0.nbytes >= (64 << 20) and np.array_equal(v0.view(np.uint32), v1.view(np.uint32)) and np.array_equal(f0.view(np.uint32), f1.view(np.uint32))
+print("OK", obs[0][0][0].nbytes)
+''' % (pc.REPO, os.path.join(pc.REPO, "tests"), emu)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, MAGENT_B200_NUMA_FAKE="2", OMP_NUM_THREADS="1"))
+    assert r.returncode == 0 and "OK" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
