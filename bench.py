@@ -542,6 +542,10 @@ def main():
                "h2d_bytes_per_step": int(cnt[1].item()) // e2e_steps, "d2h_bytes_per_step": int(cnt[2].item()) // e2e_steps,
                "host_bytes_written_per_step": int(cnt[3].item()) // e2e_steps,
                "host_threads": int(lib.magent_b200_host_threads()),
+               "ms_per_step_by_phase": {"wire_records_until_first_copy": (io1["us_wire"] - io0["us_wire"]) / 1e3 / e2e_steps,
+                                        "host_expansion": (io1["us_expand"] - io0["us_expand"]) / 1e3 / e2e_steps,
+                                        "feature_rows": (io1["us_feature"] - io0["us_feature"]) / 1e3 / e2e_steps,
+                                        "whole_step": 1e3 * dt / e2e_steps},
                "path": "observations cross PCIe as compact wire records (headers + marks) and are expanded into the caller's "
                        "float32 buffers by the engine's host threads; feature rows, rewards and actions are plain copies"
                        if (args.host_path or "wire") == "wire" and not half else "dense records over PCIe",

@@ -44,7 +44,9 @@ long long magent_b200_launch_count(void);
 int magent_b200_set_profiling(EnvHandle game, int on);
 int magent_b200_get_profile(EnvHandle game, double *obs_ms_total, long long *obs_launches);
 /* bytes moved by the step-loop calls of this game so far: [0] device->host over PCIe, [1] host->device, [2] written into
- * caller host buffers by the engine's host threads (env_get_observation with host pointers).  Returns the number written. */
+ * caller host buffers by the engine's host threads (env_get_observation with host pointers); [3..5] microseconds the
+ * host-buffer observation calls spent producing wire records / expanding them / finishing the feature rows.
+ * Returns the number written. */
 int magent_b200_get_io_stats(EnvHandle game, long long *out, int capacity);
 /* CUDA graphs for launch-bound (small) workloads.  Every step-loop call made with CUDA device pointers between begin and
  * end is recorded instead of executed (actions, rewards, observations and `done` in caller-owned device buffers); the

@@ -956,6 +956,9 @@ __global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr
 #ifndef OBS_OPT
 #define OBS_OPT 4                    // A/B switches of the round-2 instruction diet: 1 self marker from the tile, 2 division-free
 #endif                               // tile sequence, 4 packed channel table (profiles/README.md)
+#ifndef OBS_STORE_HINT
+#define OBS_STORE_HINT 0             // L2 cache hint on the bulk store: 0 none, 1 evict_first, 2 evict_last
+#endif
 #ifndef OBS_MIN_CTAS
 #define OBS_MIN_CTAS 8
 #endif
@@ -1080,6 +1083,16 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
     // window of grid * OBS_CHUNK tiles (~90 MB), which keeps the output stream inside the TLB reach (blocked
     // assignment -- one 4 MB region per CTA -- measured 20 % slower) and the planes of ~20 arenas L2-hot.
     // Software pipeline: while tile i is composed, the kind loads of tile i+1 and the header load of tile i+2 fly.
+#if OBS_STORE_HINT
+    unsigned long long store_policy;
+#if OBS_STORE_HINT == 1
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(store_policy));
+#elif OBS_STORE_HINT == 2
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(store_policy));
+#else
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(store_policy));
+#endif
+#endif
     const int chunk = P.chunk;                 // 1 when there are too few tiles to keep every CTA busy with longer chunks
     const int chunk_jump = ((int)gridDim.x - 1) * chunk;
     // the tile after t, given t's position inside its chunk (no division in the loop: three positions ride along)
@@ -1272,8 +1285,14 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
         const unsigned bytes = (unsigned)cnt * (unsigned)P.rec * (unsigned)sizeof(T);
         if ((bytes & 15u) == 0 && (((size_t)gout) & 15) == 0) {
             if (threadIdx.x == 0 && !(OBS_ABLATE & 8)) {
+#if OBS_STORE_HINT
+                // the output is a pure stream, never read again by this kernel: tell L2 (A/B switch, profiles/README.md)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                             :: "l"(gout), "r"(smem_u32(buf)), "r"(bytes), "l"(store_policy) : "memory");
+#else
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(gout), "r"(smem_u32(buf)), "r"(bytes) : "memory");
+#endif
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         } else {                                   // ragged last tile / unaligned caller buffer

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <fstream>
 #include <set>
 #include <sstream>
@@ -946,8 +947,10 @@ void Engine::get_observation_wire(int group, void **bufs) {
     O.view = nullptr;                                                     // no dense records on the device in this path
     stage_reserve(d_feat_stage_, feat_stage_bytes_, fbytes);
     O.feature = d_feat_stage_;
+    const auto t0 = std::chrono::steady_clock::now();
     be::WireDesc W;
     be::obs_wire_begin(bx_, dE_, hE_, O, minimap_mode_ ? d_mm_val_ : nullptr, n, false, &W);
+    const auto t1 = std::chrono::steady_clock::now();
     // feature rows: DMA straight into page-locked caller memory, else through page-locked staging + a threaded copy
     const bool fpinned = be::is_pinned_host_ptr(bufs[1]);
     if (!fpinned && fbytes > h_feat_stage_bytes_) {
@@ -968,8 +971,15 @@ void Engine::get_observation_wire(int group, void **bufs) {
     }
     be::Ctx *bx = bx_;
     expand_views(g, W, (float *)bufs[0], [bx](int w) { be::obs_wire_wait(bx, w); });
+    const auto t2 = std::chrono::steady_clock::now();
     be::dma_wait(bx_, 0);
     if (!fpinned) parallel_copy(bufs[1], h_feat_stage_, fbytes);
+    const auto t3 = std::chrono::steady_clock::now();
+    // where the host-buffer call spends its time (microseconds): producing the wire records up to the first queued copy,
+    // expanding, finishing the feature rows
+    io_[IO_US_WIRE] += std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+    io_[IO_US_EXPAND] += std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();
+    io_[IO_US_FEATURE] += std::chrono::duration_cast<std::chrono::microseconds>(t3 - t2).count();
     // what crossed PCIe: headers, marks, chunk table, minimap rows, feature rows; what the host threads wrote: the views
     io_[IO_D2H] += (long long)W.n_total * (long long)sizeof(be::WireHdr) + W.chunk_base[W.n_chunks] * (long long)sizeof(be::WireMark) +
                    (long long)(W.n_chunks + 1) * 8 + (W.mm ? (long long)A_ * W.mm_stride * 4 : 0) + (long long)fbytes;
@@ -1231,7 +1241,7 @@ void Engine::graph_launch(int id, int times) {
     for (int k = 0; k < times; ++k) be::graph_launch(bx_, id);
     if (times > 0) { ++state_version_; counts_unknown_ = true; counts_pending_ = false; may_have_dead_ = true; done_stale_ = true; }
 }
-void Engine::get_io_stats(long long *out, int cap) { for (int i = 0; i < cap && i < 3; ++i) out[i] = io_[i]; }
+void Engine::get_io_stats(long long *out, int cap) { for (int i = 0; i < cap && i < IO_N; ++i) out[i] = io_[i]; }
 void *Engine::stream() { ensure_backend(); return be::stream_handle(bx_); }
 void Engine::set_profiling(bool on) { ensure_backend(); be::profile_enable(bx_, on); }
 void Engine::get_profile(double *ms, long long *n) { *ms = 0; *n = 0; if (bx_) be::profile_read(bx_, ms, n); }

@@ -154,8 +154,8 @@ private:
     size_t view_stage_bytes_ = 0, feat_stage_bytes_ = 0;
     void *d_io_stage_ = nullptr; size_t io_stage_bytes_ = 0;
     void *h_feat_stage_ = nullptr; size_t h_feat_stage_bytes_ = 0;      // page-locked staging of the feature rows (host path)
-    enum { IO_D2H = 0, IO_H2D = 1, IO_HOST_WRITTEN = 2 };
-    long long io_[3] = {0, 0, 0};       // step-loop traffic (hot calls only)
+    enum { IO_D2H = 0, IO_H2D = 1, IO_HOST_WRITTEN = 2, IO_US_WIRE = 3, IO_US_EXPAND = 4, IO_US_FEATURE = 5, IO_N = 6 };
+    long long io_[IO_N] = {0, 0, 0, 0, 0, 0};       // step-loop traffic (hot calls only) and host-path phase times
     bool done_stale_ = false;           // arenas_[a].done not refreshed by the last step (device-pointer done)
     int host_path_ = -1;                // env_get_observation into host memory: 1 wire records + host expansion, 0 dense DMA
     unsigned long long rand_calls_ = 0;

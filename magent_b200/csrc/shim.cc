@@ -109,7 +109,7 @@ MG_API int magent_b200_get_counters(EnvHandle game, long long *out, int capacity
 MG_API long long magent_b200_launch_count(void) { return mg::be::launch_count(); }
 MG_API int magent_b200_set_profiling(EnvHandle game, int on) { E(game)->set_profiling(on != 0); return 0; }
 MG_API int magent_b200_get_profile(EnvHandle game, double *ms, long long *n) { E(game)->get_profile(ms, n); return 0; }
-MG_API int magent_b200_get_io_stats(EnvHandle game, long long *out, int capacity) { E(game)->get_io_stats(out, capacity); return capacity < 3 ? capacity : 3; }
+MG_API int magent_b200_get_io_stats(EnvHandle game, long long *out, int capacity) { E(game)->get_io_stats(out, capacity); return capacity < 6 ? capacity : 6; }
 MG_API int magent_b200_graph_begin(EnvHandle game) { E(game)->graph_begin(); return 0; }
 MG_API int magent_b200_graph_end(EnvHandle game) { return E(game)->graph_end(); }
 MG_API int magent_b200_graph_launch(EnvHandle game, int id, int times) { E(game)->graph_launch(id, times); return 0; }

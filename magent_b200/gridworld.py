@@ -469,9 +469,10 @@ class GridWorld(Environment):
     def get_io_stats(self):
         """step-loop traffic so far: dict(d2h=PCIe device->host bytes, h2d=..., host_written=bytes the engine's host
         threads wrote into caller buffers)"""
-        buf = (ctypes.c_longlong * 3)()
-        self._lib.magent_b200_get_io_stats(self.game, buf, 3)
-        return {"d2h": int(buf[0]), "h2d": int(buf[1]), "host_written": int(buf[2])}
+        buf = (ctypes.c_longlong * 6)()
+        self._lib.magent_b200_get_io_stats(self.game, buf, 6)
+        return {"d2h": int(buf[0]), "h2d": int(buf[1]), "host_written": int(buf[2]),
+                "us_wire": int(buf[3]), "us_expand": int(buf[4]), "us_feature": int(buf[5])}
 
     def capture_graph(self, fn):
         """record the step-loop calls fn() makes (CUDA device pointers only, an even number of clear_dead) into a CUDA

@@ -586,3 +586,10 @@ def test_replayed_cuda_graph_of_two_steps_matches_the_reference():
         rv, rf = ref.get_observation(rh)
         np.testing.assert_array_equal(v.view(np.uint32), rv.view(np.uint32))
         np.testing.assert_array_equal(f.view(np.uint32), rf.view(np.uint32))
+
+
+def test_pinned_divergences_on_the_gpu():
+    """set_action twice in a step: the second call wins; out-of-range action ids: ignored"""
+    import divergence_common as dv
+    dv.second_set_action_wins(pc.CUDA_LIB, checker_lib())
+    dv.invalid_actions_are_ignored(pc.CUDA_LIB, checker_lib())

@@ -299,6 +299,15 @@ def test_battle_one_arena_of_2x400k():
     fs.play_battle_and_check(env, size, size, 2, 23, samples={0: ref}, use_torch_obs=ON_GPU)
 
 
+def test_battle_one_arena_in_the_reference_1m_geometry():
+    """BASELINE configs[3] in the reference's own 1 M-agent geometry (scripts/test/test_1m.py:66-74: map = sqrt(20 N) =
+    4472x4472, 2x500k agents, 16 move bands, boundary buffer): every record of the first steps against the reference"""
+    size, n, seed = 4472, 500000, 5
+    env = batched_battle(1, size, n, seed)
+    ref = pc.make_battle(checker_lib(), size, n, seed)
+    fs.play_battle_and_check(env, size, size, 2, 31, samples={0: ref}, use_torch_obs=ON_GPU)
+
+
 def test_two_huge_arenas_behind_one_handle():
     """arena batch x whole-grid kernels: 2 arenas of 2x20000 agents (more than 32768 per arena, so every arena is
     stepped by the cooperative grid one after the other); both arenas exactly against independent checkers and the
