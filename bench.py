@@ -309,7 +309,7 @@ def main():
                          "wrapper's big receive buffers over all nodes, which doubles the host write bandwidth on two sockets)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="device-resident loop as a replayed CUDA graph of two steps (magent_b200_graph_*): auto = for "
-                         "launch-bound workloads (fewer than 100k agents per GPU)")
+                         "launch-bound workloads (fewer than 250k agents per GPU)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--_cpu-worker", dest="cpu_worker", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=100)
@@ -438,7 +438,7 @@ def main():
     obs_bytes_per_launch = render_bytes / len(act)
 
     n_agents_now = sum(env.get_num(h) for h in handles)
-    use_graph = args.graph == "on" or (args.graph == "auto" and n_agents_now < 100000)
+    use_graph = args.graph == "on" or (args.graph == "auto" and n_agents_now < 250000)
     graph_note = None
     steps_timed = args.steps
     barrier()
@@ -489,6 +489,9 @@ def main():
         launches = env.launch_count() - l0
     agent_steps = c1[0] - c0[0]
 
+    if os.environ.get("MAGENT_B200_BENCH_RANK_REPORT"):
+        sys.stderr.write("rank %d: %.4f ms/step device time, render %.4f ms/launch, %d launches\n"
+                         % (rank, ms / steps_timed, (obs_ms / obs_launches) if obs_launches else 0.0, launches))
     from magent_b200.sharding import reduce_window
     # NCCL over NVLink: SUM of the throughput counters, MAX over ranks of the device time -- the only collective of the job
     (total_steps, total_launches), ms_max = reduce_window([agent_steps, launches], ms, device=dev)

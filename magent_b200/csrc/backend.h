@@ -88,13 +88,12 @@ struct WireDesc {
     int wave_order[16];                  // the order the waves were queued in (front and back half alternate, so that the
                                          // threads of every NUMA part of the caller's buffer find work early)
 };
-// Launch the wire kernels for observation O (O.view = device staging for the dense records, rendered as well when
-// want_dense), read the totals back and queue the device->host copies of headers and marks, wave by wave.
+// Launch the wire kernels for observation O (feature rows into O.feature, device staging), read the totals back and queue
+// the device->host copies of headers and marks, wave by wave.
 void obs_wire_begin(Ctx *, const EngineDev *dE, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total,
-                    bool want_dense, WireDesc *out);
+                    WireDesc *out);
 void obs_wire_wait(Ctx *, int wave);     // returns once wave `wave` is in host memory
-// DMA of finished dense records (device staging -> page-locked caller memory) on the context's copy stream
-void dense_ready_wait(Ctx *);            // copy stream waits for the dense render queued by obs_wire_begin
+// asynchronous device->host copies on the context's copy stream (feature rows of a host-buffer observation)
 void dma_d2h_async(Ctx *, void *dst, const void *src, size_t bytes);
 void dma_wait(Ctx *, int keep_in_flight);   // wait until at most `keep_in_flight` of the queued copies are outstanding
 

@@ -63,7 +63,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;       // every kernel of this engine; created blocking, so work queued on the legacy
                                          // default stream (torch's default stream) stays ordered with it both ways
     cudaStream_t copy = nullptr;         // wire / dense DMA traffic (non-blocking; ordered by events)
-    cudaEvent_t ev_wire = nullptr, ev_dense = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_wire = nullptr, ev_done = nullptr;
     bool profile = false;
     std::vector<cudaEvent_t> events;     // pairs recorded around obs-render launches
     size_t events_used = 0;
@@ -135,7 +135,6 @@ Ctx *create(int device, std::string *err) {
     CUDA_CHECK(cudaStreamCreate(&c->stream));
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_wire, cudaEventDisableTiming));
-    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_dense, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_counts, cudaEventDisableTiming));
     return c;
@@ -148,7 +147,7 @@ void destroy(Ctx *c) {
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->wave_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->dma_events) cudaEventDestroy(e);
-    cudaEventDestroy(c->ev_wire); cudaEventDestroy(c->ev_dense); cudaEventDestroy(c->ev_done);
+    cudaEventDestroy(c->ev_wire); cudaEventDestroy(c->ev_done);
     cudaFree(c->mm_pad); cudaFree(c->obs_hdr);
     cudaFree(c->wire_slots); cudaFree(c->wire_stream); cudaFree(c->wire_hdr); cudaFree(c->wire_base); cudaFree(c->wire_chunk_total);
     cudaEventDestroy(c->ev_counts); cudaFreeHost(c->pin_counts);
@@ -953,12 +952,6 @@ __global__ void __launch_bounds__(256) obs_headers_kernel(ObsParams P, int4 *hdr
     }
 }
 
-#ifndef OBS_OPT
-#define OBS_OPT 4                    // A/B switches of the round-2 instruction diet: 1 self marker from the tile, 2 division-free
-#endif                               // tile sequence, 4 packed channel table (profiles/README.md)
-#ifndef OBS_STORE_HINT
-#define OBS_STORE_HINT 0             // L2 cache hint on the bulk store: 0 none, 1 evict_first, 2 evict_last
-#endif
 #ifndef OBS_MIN_CTAS
 #define OBS_MIN_CTAS 8
 #endif
@@ -1050,32 +1043,14 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
     // write (on = true) or erase what an occupied view cell shows: wall / food flag, or a group's {1, hp / max_hp}
     // channel of every kind, one byte each in two registers (byte k of chpack = channel of group k): no constant-bank
     // lookup and no branch ladder per marked cell
-    const int my_mm_ch = (P.minimap && lane < P.G) ? P.mm_ch[lane < MG_MAX_GROUPS ? lane : 0] : 0;   // this lane's minimap channel
     unsigned long long chpack = 0ull;
 #pragma unroll
     for (int j = 0; j < MG_MAX_GROUPS; ++j) chpack |= (unsigned long long)(P.grp_ch[j] & 0xff) << (8 * j);
     auto mark = [&](T *px, int t, float hp, bool on) {
-#if OBS_OPT & 4
         const bool agent = t >= KIND_GROUP0 && t != KIND_FOOD;
-#if OBS_OPT & 32
-        // byte (t - 2) of the packed table with one PRMT; a wall / food kind selects garbage that the select below discards
-        const int gch = (int)(__byte_perm((unsigned)chpack, (unsigned)(chpack >> 32), (unsigned)(t - KIND_GROUP0) & 7u) & 0xffu);
-        const int ch = agent ? gch : (t == KIND_FOOD ? 1 : 0);
-#else
         const int ch = agent ? (int)((chpack >> (8 * (t - KIND_GROUP0))) & 0xffull) : (t == KIND_FOOD ? 1 : 0);
-#endif
         px[ch] = ObsOut<T>::cv(on ? 1.0f : 0.0f);                          // wall / food flag or the group's 'has' channel
         if (agent) px[ch + 1] = ObsOut<T>::cv(on ? hp : 0.0f);             // hp / max_hp (Map.cc:197)
-#else
-        const T one = ObsOut<T>::cv(on ? 1.0f : 0.0f);
-        if (t == KIND_WALL) px[0] = one;
-        else if (t == KIND_FOOD) px[1] = one;                              // food channel (food_mode)
-        else {
-            const int ch = P.grp_ch[t - KIND_GROUP0];
-            px[ch] = one;
-            px[ch + 1] = ObsOut<T>::cv(on ? hp : 0.0f);                    // hp / max_hp (Map.cc:197)
-        }
-#endif
     };
 
     // tile assignment: chunks of OBS_CHUNK consecutive tiles, dealt round-robin over the CTAs.  Inside a chunk the
@@ -1083,29 +1058,11 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
     // window of grid * OBS_CHUNK tiles (~90 MB), which keeps the output stream inside the TLB reach (blocked
     // assignment -- one 4 MB region per CTA -- measured 20 % slower) and the planes of ~20 arenas L2-hot.
     // Software pipeline: while tile i is composed, the kind loads of tile i+1 and the header load of tile i+2 fly.
-#if OBS_STORE_HINT
-    unsigned long long store_policy;
-#if OBS_STORE_HINT == 1
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(store_policy));
-#elif OBS_STORE_HINT == 2
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(store_policy));
-#else
-    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(store_policy));
-#endif
-#endif
     const int chunk = P.chunk;                 // 1 when there are too few tiles to keep every CTA busy with longer chunks
     const int chunk_jump = ((int)gridDim.x - 1) * chunk;
-    // the tile after t, given t's position inside its chunk (no division in the loop: three positions ride along)
-#if OBS_OPT & 2
-    auto next_tile = [&](int t, int &pos) -> int { if (++pos == chunk) { pos = 0; return t + 1 + chunk_jump; } return t + 1; };
-#else
-    auto next_tile = [&](int t, int &) -> int { return ((t + 1) % chunk) ? t + 1 : t + 1 + chunk_jump; };
-#endif
+    auto next_tile = [&](int t) -> int { return ((t + 1) % chunk) ? t + 1 : t + 1 + chunk_jump; };
     int tile = blockIdx.x * chunk;
-    int pos1 = 0, pos2 = 0;                    // position in chunk of tile i + 1, i + 2
-    int tile1 = next_tile(tile, pos1);
-    pos2 = pos1;
-    int tile2 = next_tile(tile1, pos2);
+    int tile1 = next_tile(tile), tile2 = next_tile(tile1);
     const int tile_end = n_tiles;
     const int4 zero4 = make_int4(0, 0, 0, 0);
     int4 hA = zero4, hA1 = zero4;             // headers of tile i and i+1
@@ -1117,14 +1074,6 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
     unsigned prev_kinds[(NIT + 3) / 4];
 #pragma unroll
     for (int q = 0; q < (NIT + 3) / 4; ++q) prev_kinds[q] = 0u;
-#if OBS_OPT & 64
-    // what the previous observer marked, as record offsets: 15 bits of (word offset + 1) + bit 15 "hp follows", two per
-    // register (records of up to 32766 words; larger ones take the kinds path)
-    unsigned prev_off[(NIT + 1) / 2];
-#pragma unroll
-    for (int q = 0; q < (NIT + 1) / 2; ++q) prev_off[q] = 0u;
-    const bool off_undo = P.rec < 32767;
-#endif
     float self_orig = 0.0f;
     bool prev_tail = false;                    // the previous observer had cells beyond NIT * 32 marked (large views)
     {
@@ -1134,7 +1083,7 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
         if (o1 < n_total) hA1 = P.hdr[o1];
         load_kinds(hA, on0, kind);
     }
-    for (; tile < tile_end; tile = tile1, tile1 = tile2, tile2 = next_tile(tile2, pos2)) {
+    for (; tile < tile_end; tile = tile1, tile1 = tile2, tile2 = next_tile(tile2)) {
         const int t0 = tile * OBS_TA;
         const int cnt = min(OBS_TA, n_total - t0);
         const bool active = warp < cnt;
@@ -1148,10 +1097,6 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
             thp[it] = 0.0f;
             if (kind[it] >= KIND_GROUP0 && kind[it] != KIND_FOOD) thp[it] = __ldg(hpnp + lutv(it, hd).y);
         }
-#if OBS_OPT & 16
-        float self_early = 0.0f;               // the unmarked minimap value under the self marker, requested with the hp loads
-        if (P.minimap && lane < P.G && active) self_early = __ldg(P.mm + (size_t)a * P.mm_stride + lane * P.cells + (int)(short)(hA.w & 0xffff));
-#endif
         // next tile's kinds, next-next tile's header
         int kind1[NIT];
         const long o1 = (long)tile1 * OBS_TA + warp;
@@ -1196,25 +1141,10 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
                 __syncwarp();
             } else {
                 // undo the previous observer: its marked cells and its self marker
-#if OBS_OPT & 64
-                if (off_undo) {
-#pragma unroll
-                    for (int it = 0; it < NIT; ++it) {
-                        const unsigned po = (prev_off[it >> 1] >> ((it & 1) * 16)) & 0xffffu;
-                        if (po != 0u) {
-                            T *px = dst + (po & 0x7fffu) - 1;
-                            px[0] = ObsOut<T>::cv(0.0f);
-                            if (po & 0x8000u) px[1] = ObsOut<T>::cv(0.0f);
-                        }
-                    }
-                } else
-#endif
-                {
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
                     const int t = (prev_kinds[it >> 2] >> ((it & 3) * 8)) & 0xff;
                     if (t != 0) mark(dst + lutv(it, prev_hd).x, t, 0.0f, false);
-                }
                 }
                 if (prev_tail) {                                                   // large views: recompute which tail cells were marked
                     for (int k = NIT * 32 + lane; k < n_in; k += 32) {
@@ -1226,47 +1156,23 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
                         }
                     }
                 }
-                if (P.minimap && lane < P.G && prev_self >= 0) dst[prev_self * P.C + ((OBS_OPT & 8) ? my_mm_ch : P.mm_ch[lane])] = ObsOut<T>::cv(self_orig);
+                if (P.minimap && lane < P.G && prev_self >= 0) dst[prev_self * P.C + P.mm_ch[lane]] = ObsOut<T>::cv(self_orig);
                 __syncwarp();
             }
             // the new observer: self marker (+1 at its coarse cell; NaN + 1 keeps the x86 payload in the reference)
             if (P.minimap && lane < P.G) {
-                // the unmarked value is in the record itself (rebuilt or restored just above by these same lanes): no trip to L2
-                float v;
-                const int mch = (OBS_OPT & 8) ? my_mm_ch : P.mm_ch[lane];
-#if OBS_OPT & 16
-                v = self_early;
-#else
-                if (sizeof(T) == 4 && (OBS_OPT & 1)) v = ((const float *)dst)[self * P.C + mch];
-                else v = __ldg(P.mm + (size_t)a * P.mm_stride + lane * P.cells + self);    // f16 records hold the rounded value
-#endif
+                const float v = __ldg(P.mm + (size_t)a * P.mm_stride + lane * P.cells + self);
                 self_orig = v;
-                if (v == v) dst[self * P.C + mch] = ObsOut<T>::cv(v + 1.0f);
+                if (v == v) dst[self * P.C + P.mm_ch[lane]] = ObsOut<T>::cv(v + 1.0f);
             }
             prev_self = self;
             prev_hd = hd;
 #pragma unroll
             for (int q = 0; q < (NIT + 3) / 4; ++q) prev_kinds[q] = 0u;
-#if OBS_OPT & 64
-#pragma unroll
-            for (int q = 0; q < (NIT + 1) / 2; ++q) prev_off[q] = 0u;
-#endif
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
                 const int t = kind[it];
                 prev_kinds[it >> 2] |= (unsigned)t << ((it & 3) * 8);
-#if OBS_OPT & 64
-                if (off_undo) {
-                    if (t != 0) {
-                        const bool agent = t >= KIND_GROUP0 && t != KIND_FOOD;
-                        const int gch = (int)(__byte_perm((unsigned)chpack, (unsigned)(chpack >> 32), (unsigned)(t - KIND_GROUP0) & 7u) & 0xffu);
-                        const int off = lutv(it, hd).x + (agent ? gch : (t == KIND_FOOD ? 1 : 0));
-                        dst[off] = ObsOut<T>::cv(1.0f);
-                        if (agent) dst[off + 1] = ObsOut<T>::cv(thp[it]);
-                        prev_off[it >> 1] |= ((unsigned)(off + 1) | (agent ? 0x8000u : 0u)) << ((it & 1) * 16);
-                    }
-                } else
-#endif
                 if (t != 0) mark(dst + lutv(it, hd).x, t, thp[it], true);
             }
             prev_tail = false;
@@ -1285,14 +1191,8 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
         const unsigned bytes = (unsigned)cnt * (unsigned)P.rec * (unsigned)sizeof(T);
         if ((bytes & 15u) == 0 && (((size_t)gout) & 15) == 0) {
             if (threadIdx.x == 0 && !(OBS_ABLATE & 8)) {
-#if OBS_STORE_HINT
-                // the output is a pure stream, never read again by this kernel: tell L2 (A/B switch, profiles/README.md)
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                             :: "l"(gout), "r"(smem_u32(buf)), "r"(bytes), "l"(store_policy) : "memory");
-#else
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(gout), "r"(smem_u32(buf)), "r"(bytes) : "memory");
-#endif
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         } else {                                   // ragged last tile / unaligned caller buffer
@@ -1600,7 +1500,7 @@ static void grow_pinned(Ctx *c, T *&p, size_t &have, size_t need) {
 }
 
 void obs_wire_begin(Ctx *c, const EngineDev *, const EngineDev &hE, const ObsArgs &O, const float *mm_val, int n_total,
-                    bool want_dense, WireDesc *out) {
+                    WireDesc *out) {
     no_capture(c, "an observation into host memory");
     DeviceGuard guard(c);
     ObsParams P;
@@ -1648,10 +1548,6 @@ void obs_wire_begin(Ctx *c, const EngineDev *, const EngineDev &hE, const ObsArg
         post_launch("wire_compact_kernel");
     }
     CUDA_CHECK(cudaEventRecord(c->ev_wire, c->stream));
-    if (want_dense) {
-        launch_obs_dispatch(c, hE, O, P, n_total, false, false);         // dense records into O.view (device staging)
-        CUDA_CHECK(cudaEventRecord(c->ev_dense, c->stream));
-    }
     // queue the copies wave by wave on the copy stream
     CUDA_CHECK(cudaStreamWaitEvent(c->copy, c->ev_wire, 0));
     int cpw = (n_chunks + 7) / 8;
@@ -1681,8 +1577,6 @@ void obs_wire_wait(Ctx *c, int wave) {
     DeviceGuard guard(c);
     CUDA_CHECK(cudaEventSynchronize(c->wave_events[wave]));
 }
-
-void dense_ready_wait(Ctx *c) { DeviceGuard guard(c); CUDA_CHECK(cudaStreamWaitEvent(c->copy, c->ev_dense, 0)); }
 
 void dma_d2h_async(Ctx *c, void *dst, const void *src, size_t bytes) {
     DeviceGuard guard(c);

@@ -949,7 +949,7 @@ void Engine::get_observation_wire(int group, void **bufs) {
     O.feature = d_feat_stage_;
     const auto t0 = std::chrono::steady_clock::now();
     be::WireDesc W;
-    be::obs_wire_begin(bx_, dE_, hE_, O, minimap_mode_ ? d_mm_val_ : nullptr, n, false, &W);
+    be::obs_wire_begin(bx_, dE_, hE_, O, minimap_mode_ ? d_mm_val_ : nullptr, n, &W);
     const auto t1 = std::chrono::steady_clock::now();
     // feature rows: DMA straight into page-locked caller memory, else through page-locked staging + a threaded copy
     const bool fpinned = be::is_pinned_host_ptr(bufs[1]);

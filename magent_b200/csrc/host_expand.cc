@@ -118,7 +118,10 @@ int node_of_tid(int tid) {
         const int cpu = sched_getcpu();
         return (cpu >= 0 && cpu < (int)T.cpu_node.size() && T.cpu_node[cpu] >= 0) ? T.cpu_node[cpu] : 0;
     }
-    return tid % n;
+    // ranks of one box (torchrun) start their rotation at different nodes: with few threads per rank the workers of all
+    // ranks would otherwise crowd one node
+    static const int rank_shift = []() { const char *e = getenv("LOCAL_RANK"); return e ? atoi(e) : 0; }();
+    return (tid + rank_shift) % n;
 }
 }  // namespace
 
@@ -251,7 +254,8 @@ inline void stream_out(char *d, const char *s, size_t n) {
 // ---------------------------------------------------------------------------------------------
 // NUMA-split blocks
 namespace {
-struct SplitBlock { char *base; size_t bytes; int parts; size_t part_bytes; };
+// stripes of `stripe` bytes alternate over the nodes, so that any prefix of the block (populations shrink) is balanced
+struct SplitBlock { char *base; size_t bytes; int parts; size_t stripe; };
 std::mutex g_split_mu;
 std::vector<SplitBlock> g_split;
 bool split_lookup(const void *p, SplitBlock *out) {
@@ -270,21 +274,21 @@ void *numa_split_alloc(size_t bytes) {
     const int parts = numa_nodes();
     SplitBlock b;
     b.base = (char *)p; b.bytes = len; b.parts = parts;
-    b.part_bytes = parts > 1 ? ((len / parts + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1)) : len;    // 2 MB-aligned parts
-    if (b.part_bytes == 0 || b.part_bytes > len) b.part_bytes = len;
-    // first touch decides where a page lives: every part is zeroed by the pool threads of its node
+    b.stripe = (size_t)32 << 20;
+    // first touch decides where a page lives: every stripe is zeroed by a pool thread of its node
     int T = host_threads();
     if (T < parts) T = parts;
-    const size_t piece = (size_t)4 << 20;
+    const size_t n_stripes = (len + b.stripe - 1) / b.stripe;
     std::vector<std::atomic<size_t>> next(parts);
     for (auto &x : next) x.store(0);
     host_parallel(T, [&](int tid) {
         const int node = parts > 1 ? node_of_tid(tid) % parts : 0;
-        const size_t lo = (size_t)node * b.part_bytes, hi = std::min(len, lo + b.part_bytes);
         for (;;) {
-            const size_t o = lo + next[node].fetch_add(piece);
-            if (o >= hi) break;
-            memset(b.base + o, 0, std::min(piece, hi - o));
+            const size_t i = next[node].fetch_add(1);                 // i-th stripe of this node
+            const size_t st = i * parts + node;
+            if (st >= n_stripes) break;
+            const size_t o = st * b.stripe;
+            memset(b.base + o, 0, std::min(b.stripe, len - o));
         }
     });
     // a node without a thread (very few threads) leaves its part untouched: it is zero anyway (anonymous mapping)
@@ -404,23 +408,18 @@ void expand_views(const ExpandGeom &geom, const be::WireDesc &W, float *out, con
     // part k holds the chunks whose first byte lies in it
     const size_t rec_bytes = (size_t)geom.rec * sizeof(float), chunk_bytes = rec_bytes * be::WIRE_CHUNK;
     int n_parts = 1;
-    int part_lo[64], part_hi[64];
-    part_lo[0] = 0; part_hi[0] = W.n_chunks;
+    std::vector<int> part_chunks[8];          // chunk ids of every part, ascending
     SplitBlock blk;
-    if (numa_nodes() > 1 && T > 1 && split_lookup(out, &blk) && blk.parts > 1) {
+    if (numa_nodes() > 1 && T > 1 && split_lookup(out, &blk) && blk.parts > 1 && blk.parts <= 8) {
         n_parts = blk.parts;
         const size_t off0 = (size_t)((const char *)out - blk.base);
-        int c = 0;
-        for (int k = 0; k < n_parts; ++k) {
-            part_lo[k] = c;
-            const size_t end = (size_t)(k + 1) * blk.part_bytes;              // first byte of the next part
-            while (c < W.n_chunks && off0 + (size_t)c * chunk_bytes < end) ++c;
-            if (k == n_parts - 1) c = W.n_chunks;
-            part_hi[k] = c;
-        }
+        for (int c = 0; c < W.n_chunks; ++c) part_chunks[((off0 + (size_t)c * chunk_bytes) / blk.stripe) % n_parts].push_back(c);
+    } else {
+        part_chunks[0].resize(W.n_chunks);
+        for (int c = 0; c < W.n_chunks; ++c) part_chunks[0][c] = c;
     }
-    std::atomic<int> next[64];
-    for (int k = 0; k < n_parts; ++k) next[k].store(part_lo[k]);
+    std::atomic<int> next[8];
+    for (int k = 0; k < 8; ++k) next[k].store(0);
     std::atomic<int> wave_ready[16];
     for (int w = 0; w < 16; ++w) wave_ready[w].store(0);
     int fetched = 0;                         // single-thread mode: waves fetched so far (in queue order)
@@ -442,8 +441,9 @@ void expand_views(const ExpandGeom &geom, const be::WireDesc &W, float *out, con
             for (int turn = 0; turn < n_parts; ++turn) {       // own part first, then help the others (remote writes)
                 const int k = (home + turn) % n_parts;
                 for (;;) {
-                    const int c = next[k].fetch_add(1);
-                    if (c >= part_hi[k]) break;
+                    const int i = next[k].fetch_add(1);
+                    if (i >= (int)part_chunks[k].size()) break;
+                    const int c = part_chunks[k][i];
                     const int w = c / W.chunks_per_wave;
                     while (!wave_ready[w].load(std::memory_order_acquire)) { for (int i = 0; i < 32; ++i) _mm_pause(); }
                     expand_chunk(geom, W, out, c, s);

@@ -36,9 +36,10 @@ void expand_views(const ExpandGeom &geom, const be::WireDesc &W, float *out, con
 // ---- NUMA: one socket's memory controllers take ~200 GB/s of streamed writes; a two-socket host takes twice that if each
 // half of a buffer lives on its own node and is written by threads of that node.
 int numa_nodes();                        // nodes with CPUs this process may use (1 when the host is not NUMA)
-// `bytes` of zeroed, page-aligned host memory whose k-th part (of numa_nodes() equal parts) was first touched -- and is
-// therefore resident -- on node k.  expand_views() recognises pointers into such a block and deals the chunks of a part
-// to the threads pinned to its node.  nullptr when the mapping fails.
+// `bytes` of zeroed, page-aligned host memory in 32 MB stripes that alternate over the nodes: every stripe was first touched
+// -- and is therefore resident -- on its node, and any prefix of the block is balanced (populations shrink).  expand_views()
+// recognises pointers into such a block and deals the chunks that start in a node's stripes to the threads pinned to that
+// node.  nullptr when the mapping fails.
 void *numa_split_alloc(size_t bytes);
 bool numa_split_free(void *p);           // false when p is not a block of numa_split_alloc
 size_t numa_split_size(const void *p);   // 0 when p is not the base of such a block

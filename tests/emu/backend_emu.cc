@@ -201,7 +201,7 @@ void launch_done_to_device(Ctx *, const EngineDev *dE, const EngineDev &, int *d
 // wire records of one observation (backend.h): derived from the same per-cell composition the dense emulation uses, so
 // the engine's host expansion (host_expand.cc) can be checked against the reference without a GPU
 void obs_wire_begin(Ctx *c, const EngineDev *dE, const EngineDev &, const ObsArgs &O, const float *mm_val, int n_total,
-                    bool want_dense, WireDesc *out) {
+                    WireDesc *out) {
     const EngineDev &E = *dE;
     const int g = O.group;
     const GroupDev &G = E.grp[g];
@@ -246,7 +246,6 @@ void obs_wire_begin(Ctx *c, const EngineDev *dE, const EngineDev &, const ObsArg
         }
     }
     c->base[n_chunks] = (long long)c->marks.size();
-    if (want_dense) launch_obs(c, dE, E, O, mm_val, n_total);
     c->marks.push_back({0u, 0.0f});
     out->hdr = c->hdr.data(); out->marks = c->marks.data(); out->chunk_base = c->base.data();
     out->mm = mm_val ? c->mm.data() : nullptr; out->mm_stride = mm_val ? mm_stride : 0;
@@ -256,7 +255,6 @@ void obs_wire_begin(Ctx *c, const EngineDev *dE, const EngineDev &, const ObsArg
     for (int q = 0; q < out->n_waves; ++q) { const int half = (out->n_waves + 1) / 2; out->wave_order[q] = (q & 1) ? half + (q >> 1) : (q >> 1); }
 }
 void obs_wire_wait(Ctx *, int) {}
-void dense_ready_wait(Ctx *) {}
 void dma_d2h_async(Ctx *, void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
 void dma_wait(Ctx *, int) {}
 
