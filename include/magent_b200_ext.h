@@ -16,7 +16,8 @@ const char *magent_b200_last_error(void);
 int magent_b200_device_count(void);            /* 0 when no CUDA device is visible */
 
 /* page-locked host memory for observation / reward receive buffers.  Blocks of 64 MB and more on a multi-socket host are
- * split over the NUMA nodes (each part resident on its node and written by that node's threads in env_get_observation). */
+ * striped over the NUMA nodes (32 MB stripes, each resident on its node and written by that node's threads in
+ * env_get_observation). */
 void *magent_b200_host_alloc(size_t bytes);
 int magent_b200_host_free(void *p);
 int magent_b200_numa_nodes(void);              /* NUMA nodes the host threads are spread over (1 = not NUMA) */
