@@ -240,6 +240,45 @@ StreamFn pick_stream() {
 }
 const StreamFn g_stream = pick_stream();
 
+// copies of less than a cache line (record sizes are multiples of 4 bytes): no libc call on the per-record path
+inline void small_copy(char *d, const char *s, size_t n) {
+    if ((n & 3) == 0) { for (size_t i = 0; i < n; i += 4) { uint32_t v; memcpy(&v, s + i, 4); memcpy(d + i, &v, 4); } }
+    else memcpy(d, s, n);
+}
+
+// A sequential byte stream into the caller's buffer.  Records are not multiples of 64 bytes, so the last bytes of one
+// record and the first bytes of the next share a cache line: they are collected in `carry` and leave as ONE full-line
+// non-temporal store -- no partial-line store (read for ownership) and no libc call per record.  Only the first and the
+// last line of a chunk can be partial.
+struct LineWriter {
+    alignas(64) char carry[64];
+    size_t carry_n = 0;
+    char *d = nullptr;                       // next destination byte; 64-byte aligned whenever bytes are carried
+    void begin(char *dst) { d = dst; carry_n = 0; }
+    void put(const char *s, size_t n) {
+        if (carry_n) {
+            size_t need = 64 - carry_n;
+            if (need > n) need = n;
+            small_copy(carry + carry_n, s, need);
+            carry_n += need; s += need; n -= need;
+            if (carry_n == 64) { g_stream(d, carry, 64); d += 64; carry_n = 0; }
+            if (!n) return;
+        } else {
+            size_t head = (size_t)(-(uintptr_t)d) & 63;        // only the first record of a chunk can start off a line
+            if (head) {
+                if (head > n) head = n;
+                memcpy(d, s, head);
+                d += head; s += head; n -= head;
+                if (!n) return;
+            }
+        }
+        const size_t body = n & ~(size_t)63;
+        if (body) { g_stream(d, s, body); d += body; s += body; n -= body; }
+        if (n) { small_copy(carry, s, n); carry_n = n; }
+    }
+    void end() { if (carry_n) { memcpy(d, carry, carry_n); d += carry_n; carry_n = 0; } }
+};
+
 inline void stream_out(char *d, const char *s, size_t n) {
     size_t head = (size_t)(-(uintptr_t)d) & 63;
     if (head > n) head = n;
@@ -361,43 +400,59 @@ inline void rebuild(const ExpandGeom &g, const be::WireDesc &W, Scratch &s, int 
     s.arena = arena; s.prev = nullptr; s.prev_n = 0; s.prev_self = 0xffff;
 }
 
-void expand_chunk(const ExpandGeom &g, const be::WireDesc &W, float *out, int chunk, Scratch &s) {
+// bring scratch record s to show observer o (whose marks start at m): undo what it showed before, apply the new marks
+inline void prepare(const ExpandGeom &g, const be::WireDesc &W, Scratch &s, const be::WireHdr &h, const be::WireMark *m) {
+    float *rec = s.rec;
+    if (h.arena != s.arena) rebuild(g, W, s, h.arena);
+    else {
+        for (int k = 0; k < s.prev_n; ++k) {                                      // undo the previous observer
+            const unsigned off = s.prev[k].off;
+            rec[off & ~be::WIRE_HAS_HP] = 0.0f;
+            if (off & be::WIRE_HAS_HP) rec[(off & ~be::WIRE_HAS_HP) + 1] = 0.0f;
+        }
+        if (g.minimap && s.prev_self != 0xffff) {
+            const float *rows = W.mm + (size_t)s.arena * W.mm_stride;
+            for (int j = 0; j < g.G; ++j) rec[(size_t)s.prev_self * g.C + g.mm_ch[j]] = rows[(size_t)j * g.cells + s.prev_self];
+        }
+    }
+    if (g.minimap && h.self_cell != 0xffff) {                                     // self marker, GridWorld.cc:382
+        const float *rows = W.mm + (size_t)h.arena * W.mm_stride;
+        for (int j = 0; j < g.G; ++j) {
+            const float v = rows[(size_t)j * g.cells + h.self_cell];
+            if (v == v) rec[(size_t)h.self_cell * g.C + g.mm_ch[j]] = v + 1.0f;   // 0/0 of an empty group stays the NaN it is
+        }
+    }
+    for (int k = 0; k < (int)h.count; ++k) {                                      // Map::extract_view, Map.cc:183-199
+        const unsigned off = m[k].off;
+        rec[off & ~be::WIRE_HAS_HP] = 1.0f;
+        if (off & be::WIRE_HAS_HP) rec[(off & ~be::WIRE_HAS_HP) + 1] = m[k].val;
+    }
+    s.prev = m; s.prev_n = h.count; s.prev_self = h.self_cell;
+}
+
+// Two scratch records take turns: while record i streams out of one, record i + 1 is prepared in the other -- the 64-byte
+// loads of the copy never hit a 4-byte store that is still in flight (no failed store-to-load forwarding).
+void expand_chunk(const ExpandGeom &g, const be::WireDesc &W, float *out, int chunk, Scratch (&s)[2]) {
     const size_t o0 = (size_t)chunk * be::WIRE_CHUNK;
     const size_t o1 = o0 + be::WIRE_CHUNK < (size_t)W.n_total ? o0 + be::WIRE_CHUNK : (size_t)W.n_total;
+    if (o0 >= o1) return;
     const be::WireMark *m = W.marks + W.chunk_base[chunk];
     const size_t rec_bytes = (size_t)g.rec * sizeof(float);
-    char *d = (char *)(out + o0 * (size_t)g.rec);
-    float *rec = s.rec;
-    for (size_t o = o0; o < o1; ++o, d += rec_bytes) {
-        const be::WireHdr h = W.hdr[o];
-        if (h.arena != s.arena) rebuild(g, W, s, h.arena);
-        else {
-            for (int k = 0; k < s.prev_n; ++k) {                                      // undo the previous observer
-                const unsigned off = s.prev[k].off;
-                rec[off & ~be::WIRE_HAS_HP] = 0.0f;
-                if (off & be::WIRE_HAS_HP) rec[(off & ~be::WIRE_HAS_HP) + 1] = 0.0f;
-            }
-            if (g.minimap && s.prev_self != 0xffff) {
-                const float *rows = W.mm + (size_t)s.arena * W.mm_stride;
-                for (int j = 0; j < g.G; ++j) rec[(size_t)s.prev_self * g.C + g.mm_ch[j]] = rows[(size_t)j * g.cells + s.prev_self];
-            }
+    LineWriter lw;
+    lw.begin((char *)(out + o0 * (size_t)g.rec));
+    be::WireHdr h = W.hdr[o0];
+    prepare(g, W, s[0], h, m);
+    m += h.count;
+    int cur = 0;
+    for (size_t o = o0; o < o1; ++o, cur ^= 1) {
+        if (o + 1 < o1) {
+            h = W.hdr[o + 1];
+            prepare(g, W, s[cur ^ 1], h, m);
+            m += h.count;
         }
-        if (g.minimap && h.self_cell != 0xffff) {                                     // self marker, GridWorld.cc:382
-            const float *rows = W.mm + (size_t)h.arena * W.mm_stride;
-            for (int j = 0; j < g.G; ++j) {
-                const float v = rows[(size_t)j * g.cells + h.self_cell];
-                if (v == v) rec[(size_t)h.self_cell * g.C + g.mm_ch[j]] = v + 1.0f;   // 0/0 of an empty group stays the NaN it is
-            }
-        }
-        for (int k = 0; k < (int)h.count; ++k) {                                      // Map::extract_view, Map.cc:183-199
-            const unsigned off = m[k].off;
-            rec[off & ~be::WIRE_HAS_HP] = 1.0f;
-            if (off & be::WIRE_HAS_HP) rec[(off & ~be::WIRE_HAS_HP) + 1] = m[k].val;
-        }
-        s.prev = m; s.prev_n = h.count; s.prev_self = h.self_cell;
-        m += h.count;
-        stream_out(d, (const char *)rec, rec_bytes);
+        lw.put((const char *)s[cur].rec, rec_bytes);
     }
+    lw.end();
 }
 }  // namespace
 
@@ -424,10 +479,12 @@ void expand_views(const ExpandGeom &geom, const be::WireDesc &W, float *out, con
     for (int w = 0; w < 16; ++w) wave_ready[w].store(0);
     int fetched = 0;                         // single-thread mode: waves fetched so far (in queue order)
     auto work = [&](int tid) {
-        Scratch s;
+        Scratch s[2];
         void *mem = nullptr;
-        if (posix_memalign(&mem, 64, (size_t)geom.rec * sizeof(float) + 64) != 0) abort();
-        s.rec = (float *)mem;
+        const size_t rec_alloc = ((size_t)geom.rec * sizeof(float) + 127) & ~(size_t)63;
+        if (posix_memalign(&mem, 64, 2 * rec_alloc) != 0) abort();
+        s[0].rec = (float *)mem;
+        s[1].rec = (float *)((char *)mem + rec_alloc);
         if (tid == 0 && T == 1) {            // a single thread has to fetch the waves itself, in step with its work
             for (int c = 0; c < W.n_chunks; ++c) {
                 const int w = c / W.chunks_per_wave;
