@@ -161,3 +161,28 @@ print("OK", obs[0][0][0].nbytes)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, MAGENT_B200_NUMA_FAKE="2", OMP_NUM_THREADS="1"))
     assert r.returncode == 0 and "OK" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+
+
+@pytest.mark.parametrize("isa", ["avx2", "sse2"])
+def test_streaming_stores_without_avx512(emu, isa):
+    """MAGENT_B200_HOST_ISA picks the 32-byte / 16-byte non-temporal store loops (hosts without AVX-512): same bytes"""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import parity_common as pc
+from magent_b200.c_lib import load_library
+L = load_library(%r)
+L.magent_b200_set_host_threads(3)
+w = pc.run_trace(pc.make_battle(L.path, 40, 150, 0, _host_path="wire"), 6, 5, keep_obs=True)
+d = pc.run_trace(pc.make_battle(L.path, 40, 150, 0, _host_path="dense"), 6, 5, keep_obs=True)
+pc.compare_traces(d, w, "isa")
+w = pc.run_trace(pc.make_pursuit(L.path, 40, 0, _host_path="wire"), 6, 5, keep_obs=True)
+d = pc.run_trace(pc.make_pursuit(L.path, 40, 0, _host_path="dense"), 6, 5, keep_obs=True)
+pc.compare_traces(d, w, "isa")
+print("OK")
+''' % (pc.REPO, os.path.join(pc.REPO, "tests"), emu)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, MAGENT_B200_HOST_ISA=isa, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0 and "OK" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
