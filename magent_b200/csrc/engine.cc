@@ -915,8 +915,8 @@ void Engine::get_observation(int group, void **bufs, int half) {      // GridWor
         prep_version_ = state_version_; prep_vw_ = t.view.width; prep_vh_ = t.view.height; prep_skip_absorbed_ = t.can_absorb;
     }
     if (host_path_ < 0) {                 // MAGENT_B200_HOST_PATH=dense keeps the round-1 path (dense records over PCIe) for A/B runs
-        const char *e = getenv("MAGENT_B200_HOST_PATH");
-        host_path_ = (e && !strcmp(e, "dense")) ? 0 : 1;
+        const char *e = getenv("MAGENT_B200_HOST_PATH");                 // dense | wire (whatever the size) | default: by size
+        host_path_ = (e && !strcmp(e, "dense")) ? 0 : (e && !strcmp(e, "wire")) ? 2 : 1;
     }
     // small observations (a few MB) are latency-, not bandwidth-bound: one plain copy of the dense records beats the
     // wire protocol's fixed costs (totals read-back, waves, waking the pool)

@@ -94,3 +94,17 @@ def test_emulated_engine_with_many_groups_and_a_chaotic_caller(emu, seed):
 @pytest.mark.parametrize("seed", list(range(9000, 9006)))
 def test_three_emulated_engines_interleaved_with_chaotic_callers(emu, seed):
     fz.play_interleaved_engines(seed, CHECKER, emu)
+
+
+# the randomised callers again with EVERY host-buffer observation forced through the wire records + host expansion
+# (MAGENT_B200_HOST_PATH=wire; small observations normally take the dense copy): all modes, many groups, late adds, resets
+@pytest.mark.parametrize("seed", list(range(40000, 40010)) + [47002, 110000])
+def test_chaotic_caller_with_wire_records_forced(emu, seed, monkeypatch):
+    monkeypatch.setenv("MAGENT_B200_HOST_PATH", "wire")
+    fz.play_chaotic(seed, CHECKER, emu)
+
+
+@pytest.mark.parametrize("seed", [60000, 60003, 115000])
+def test_chaotic_arena_batch_with_wire_records_forced(emu, seed, monkeypatch):
+    monkeypatch.setenv("MAGENT_B200_HOST_PATH", "wire")
+    fz.play_batch_chaotic(seed, CHECKER, emu, n_arenas=1 + seed % 4)

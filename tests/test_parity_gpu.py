@@ -593,3 +593,18 @@ def test_pinned_divergences_on_the_gpu():
     import divergence_common as dv
     dv.second_set_action_wins(pc.CUDA_LIB, checker_lib())
     dv.invalid_actions_are_ignored(pc.CUDA_LIB, checker_lib())
+
+
+@pytest.mark.parametrize("seed", list(range(40000, 40012)) + [47002, 47170, 70003, 72001, 110000, 113018])
+def test_chaotic_caller_with_wire_records_forced(seed, monkeypatch):
+    """every host-buffer observation of the chaotic caller through the wire kernels + host expansion, whatever its size"""
+    import fuzz_common as fz
+    monkeypatch.setenv("MAGENT_B200_HOST_PATH", "wire")
+    fz.play_chaotic(seed, checker_lib(), pc.CUDA_LIB)
+
+
+@pytest.mark.parametrize("seed", [60000, 60003, 60007, 115000])
+def test_chaotic_arena_batch_with_wire_records_forced(seed, monkeypatch):
+    import fuzz_common as fz
+    monkeypatch.setenv("MAGENT_B200_HOST_PATH", "wire")
+    fz.play_batch_chaotic(seed, checker_lib(), pc.CUDA_LIB, n_arenas=1 + seed % 4)
