@@ -315,7 +315,9 @@ struct CtaCtx {
     MG_HD int *flags(ArenaHdr *) { return flag_smem; }
     int cnt[MG_N_COUNTERS];
     MG_HD void add_count(const EngineDev &, int kind, long long v) { cnt[kind] += (int)v; }
-    // one warp-reduced atomic per counter per warp, once per arena-step
+    // warp-reduced, then one shared-memory add per warp and ONE global atomic per counter per arena-step (the 8 counters
+    // are 8 addresses for the whole GPU: a global atomic per warp made them a hot spot)
+    int *cnt_smem;                      // [MG_N_COUNTERS], zero between arena-steps
     MG_HD void flush_counts(const EngineDev &E) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -324,7 +326,13 @@ struct CtaCtx {
             cnt[k] = 0;
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-            if (v && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&E.counters[k], (unsigned long long)v);
+            if (v && (threadIdx.x & 31) == 0) atomicAdd(&cnt_smem[k], v);
+        }
+        __syncthreads();
+        if (threadIdx.x < MG_N_COUNTERS) {
+            const int v = cnt_smem[threadIdx.x];
+            cnt_smem[threadIdx.x] = 0;
+            if (v) atomicAdd((unsigned long long *)&E.counters[threadIdx.x], (unsigned long long)v);
         }
 #endif
     }
@@ -497,9 +505,12 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_cta(const EngineDev 
         __syncthreads();
     }
     __shared__ int relax_flags[3];
+    __shared__ int counter_sums[MG_N_COUNTERS];
     __shared__ GroupEnum enum_store[2];
+    if (threadIdx.x < MG_N_COUNTERS) counter_sums[threadIdx.x] = 0;
     CtaCtx c;
     c.flag_smem = relax_flags;
+    c.cnt_smem = counter_sums;
     c.enum_smem = enum_store;
     for (int k = 0; k < MG_N_COUNTERS; ++k) c.cnt[k] = 0;
     for (int a = blockIdx.x; a < sE.A; a += gridDim.x) run_step(c, sE, S, a);
@@ -522,6 +533,7 @@ __global__ void __launch_bounds__(STEP_THREADS) cull_kernel_cta(const EngineDev 
     load_engine(&sE, gE);
     CtaCtx c;
     c.flag_smem = nullptr;
+    c.cnt_smem = nullptr;
     c.enum_smem = nullptr;
     for (int a = blockIdx.x; a < sE.A; a += gridDim.x) run_cull(c, sE, curmask, a);
 }
@@ -599,7 +611,13 @@ void launch_cull(Ctx *c, const EngineDev *dE, const EngineDev &hE, unsigned curm
         post_launch("cull_kernel_grid");
     } else {
         int grid = hE.A < 8 * g_sms ? hE.A : 8 * g_sms;
-        cull_kernel_cta<<<grid, step_block_size(g_sms, hE.A, max_agents), 0, c->stream>>>(dE, curmask);
+        // measurement knob (profiles/README.md): MAGENT_B200_CULL_THREADS overrides the block size
+        static const int cull_pref = getenv("MAGENT_B200_CULL_THREADS") ? atoi(getenv("MAGENT_B200_CULL_THREADS")) : 0;
+        // the compaction is a chain of block scans (three barriers per tile of blockDim agents): arenas of ~1000 agents
+        // per group run fastest with 512 threads (measured 256 / 512 / 1024: 1.243 / 1.230 / 1.237 ms per whole step)
+        int threads = max_agents >= 768 ? 512 : step_block_size(g_sms, hE.A, max_agents);
+        if (cull_pref >= 32 && cull_pref <= STEP_THREADS) threads = cull_pref & ~31;
+        cull_kernel_cta<<<grid, threads, 0, c->stream>>>(dE, curmask);
         post_launch("cull_kernel_cta");
     }
 }
@@ -638,15 +656,19 @@ __device__ __forceinline__ int locate_arena(const int *off, int A, int idx) {
     return lo;
 }
 
+// One thread per agent, CTAs dealt per arena (blockIdx says which arena: no search).  `n_total` is the host's count, which
+// may still be the one from before the last cull (an upper bound): the device-side offsets decide.
 __global__ void __launch_bounds__(256) info_kernel(const EngineDev *gE, unsigned curmask, int kind, int g,
-                                                   void *buf, int n_total) {
+                                                   void *buf, int n_total, int chunks_per_arena) {
     const EngineDev &E = *gE;
     const int *off = E.off + (size_t)g * (E.A + 1);
     const AgentSoA &s = E.grp[g].soa[(curmask >> g) & 1u];
-    n_total = min(n_total, off[E.A]);         // the host may still hold the counts from before the last cull (upper bounds)
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_total; o += gridDim.x * blockDim.x) {
-        int a = E.A == 1 ? 0 : locate_arena(off, E.A, o);
-        long gi = (long)a * E.grp[g].cap + (o - off[a]);
+    const int a = blockIdx.x / chunks_per_arena;
+    const int i = (blockIdx.x - a * chunks_per_arena) * blockDim.x + threadIdx.x;
+    const int o0 = off[a];
+    const int o = o0 + i;
+    if (i < off[a + 1] - o0 && o < n_total) {
+        const long gi = (long)a * E.grp[g].cap + i;
         switch (kind) {
             case INFO_ID: ((int *)buf)[o] = s.id[gi]; break;
             case INFO_POS: ((int2 *)buf)[o] = make_int2(s.x[gi], s.y[gi]); break;
@@ -658,11 +680,12 @@ __global__ void __launch_bounds__(256) info_kernel(const EngineDev *gE, unsigned
     }
 }
 
-void launch_info(Ctx *c, const EngineDev *dE, const EngineDev &, unsigned curmask, int kind, int group, void *buf, int n_total) {
+void launch_info(Ctx *c, const EngineDev *dE, const EngineDev &hE, unsigned curmask, int kind, int group, void *buf, int n_total) {
     DeviceGuard guard(c);
-    int grid = (n_total + 255) / 256;
-    if (grid > 8 * c->sms) grid = 8 * c->sms;
-    info_kernel<<<grid, 256, 0, c->stream>>>(dE, curmask, kind, group, buf, n_total);
+    const int cap = hE.grp[group].cap;
+    const int threads = cap >= 256 ? 256 : ((cap + 31) & ~31);
+    const int cpa = (cap + threads - 1) / threads;
+    info_kernel<<<(unsigned)((size_t)hE.A * cpa), threads, 0, c->stream>>>(dE, curmask, kind, group, buf, n_total, cpa);
     post_launch("info_kernel");
 }
 
@@ -674,27 +697,28 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 }
 
 __global__ void __launch_bounds__(256) random_actions_kernel(const EngineDev *gE, unsigned curmask, int g,
-                                                             unsigned long long seed, int n_total) {
+                                                             unsigned long long seed, int n_total, int chunks_per_arena) {
     const EngineDev &E = *gE;
     const int *off = E.off + (size_t)g * (E.A + 1);
     const AgentSoA &s = E.grp[g].soa[(curmask >> g) & 1u];
     const unsigned na = (unsigned)E.grp[g].n_action;
-    n_total = min(n_total, off[E.A]);
     // the device-side step counter rides in the seed: a replayed CUDA graph (same kernel arguments) still draws fresh actions
     seed += (unsigned long long)E.counters[CNT_STEPS] * 0xA24BAED4963EE407ull;
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_total; o += gridDim.x * blockDim.x) {
-        int a = E.A == 1 ? 0 : locate_arena(off, E.A, o);
-        long gi = (long)a * E.grp[g].cap + (o - off[a]);
-        s.act[gi] = (int)((splitmix64(seed ^ ((unsigned long long)o * 0xD1342543DE82EF95ull)) >> 33) % na);
-    }
+    const int a = blockIdx.x / chunks_per_arena;
+    const int i = (blockIdx.x - a * chunks_per_arena) * blockDim.x + threadIdx.x;
+    const int o0 = off[a];
+    const int o = o0 + i;
+    if (i < off[a + 1] - o0 && o < n_total)
+        s.act[(long)a * E.grp[g].cap + i] = (int)((splitmix64(seed ^ ((unsigned long long)o * 0xD1342543DE82EF95ull)) >> 33) % na);
 }
 
-void launch_random_actions(Ctx *c, const EngineDev *dE, const EngineDev &, unsigned curmask, int group,
+void launch_random_actions(Ctx *c, const EngineDev *dE, const EngineDev &hE, unsigned curmask, int group,
                            unsigned long long seed, int n_total) {
     DeviceGuard guard(c);
-    int grid = (n_total + 255) / 256;
-    if (grid > 8 * c->sms) grid = 8 * c->sms;
-    random_actions_kernel<<<grid, 256, 0, c->stream>>>(dE, curmask, group, seed, n_total);
+    const int cap = hE.grp[group].cap;
+    const int threads = cap >= 256 ? 256 : ((cap + 31) & ~31);
+    const int cpa = (cap + threads - 1) / threads;
+    random_actions_kernel<<<(unsigned)((size_t)hE.A * cpa), threads, 0, c->stream>>>(dE, curmask, group, seed, n_total, cpa);
     post_launch("random_actions_kernel");
 }
 
