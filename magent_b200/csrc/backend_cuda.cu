@@ -1071,8 +1071,8 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
 #pragma unroll
     for (int j = 0; j < MG_MAX_GROUPS; ++j) chpack |= (unsigned long long)(P.grp_ch[j] & 0xff) << (8 * j);
     auto mark = [&](T *px, int t, float hp, bool on) {
-        const bool agent = t >= KIND_GROUP0 && t != KIND_FOOD;
-        const int ch = agent ? (int)((chpack >> (8 * (t - KIND_GROUP0))) & 0xffull) : (t == KIND_FOOD ? 1 : 0);
+        const bool agent = kind_is_agent(t);
+        const int ch = agent ? (int)((chpack >> (8 * kind_group(t))) & 0xffull) : (t == KIND_FOOD ? 1 : 0);
         px[ch] = ObsOut<T>::cv(on ? 1.0f : 0.0f);                          // wall / food flag or the group's 'has' channel
         if (agent) px[ch + 1] = ObsOut<T>::cv(on ? hp : 0.0f);             // hp / max_hp (Map.cc:197)
     };
@@ -1119,7 +1119,7 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             thp[it] = 0.0f;
-            if (kind[it] >= KIND_GROUP0 && kind[it] != KIND_FOOD) thp[it] = __ldg(hpnp + lutv(it, hd).y);
+            if (kind_is_agent(kind[it])) thp[it] = (kind[it] & KIND_FULL) ? 1.0f : __ldg(hpnp + lutv(it, hd).y);   // full hp: no load
         }
         // next tile's kinds, next-next tile's header
         int kind1[NIT];
@@ -1204,7 +1204,7 @@ obs_render_kernel(const __grid_constant__ ObsParams P) {
             for (int k = NIT * 32 + lane; k < n_in; k += 32) {                          // views with > NIT * 32 in-range cells
                 const int2 l = lut[(TURN ? hd * lut_stride : 0) + k];
                 const int t = __ldg(kindp + l.y);
-                if (t != 0) { mark(dst + l.x, t, t >= KIND_GROUP0 && t != KIND_FOOD ? __ldg(hpnp + l.y) : 0.0f, true); }
+                if (t != 0) { mark(dst + l.x, t, kind_is_agent(t) ? ((t & KIND_FULL) ? 1.0f : __ldg(hpnp + l.y)) : 0.0f, true); }
                 prev_tail = true;
             }
         }
@@ -1446,7 +1446,7 @@ __global__ void __launch_bounds__(256) obs_wire_kernel(const __grid_constant__ O
                 WireMark m;
                 if (t == KIND_WALL) { m.off = (unsigned)lk.x; m.val = 0.0f; }
                 else if (t == KIND_FOOD) { m.off = (unsigned)lk.x + 1u; m.val = 0.0f; }
-                else { m.off = (unsigned)(lk.x + P.grp_ch[t - KIND_GROUP0]) | WIRE_HAS_HP; m.val = __ldg(hpnp + lk.y); }
+                else { m.off = (unsigned)(lk.x + P.grp_ch[kind_group(t)]) | WIRE_HAS_HP; m.val = (t & KIND_FULL) ? 1.0f : __ldg(hpnp + lk.y); }
                 row[running + __popc(bal & ((1u << lane) - 1u))] = m;
             }
             running += __popc(bal);

@@ -24,6 +24,13 @@ enum Counter { CNT_AGENT_STEPS = 0, CNT_ATTACKS, CNT_HITS, CNT_KILLS, CNT_STARVE
 enum : int { OCC_EMPTY = -1, OCC_WALL = -2, OCC_FOOD = -3 };   // OCC_FOOD: food_mode only (amount in EngineDev::food)
 enum : int { TGT_NONE = -1, TGT_FOOD = -3 };                  // EngineDev::tgt of an attacker: none / an agent code (>= 0) / a food cell
 enum : int { KIND_EMPTY = 0, KIND_WALL = 1, KIND_GROUP0 = 2, KIND_FOOD = 255 };   // EngineDev::kind
+// An agent's kind byte is (KIND_GROUP0 + group) | KIND_FULL when its hp is exactly max_hp: its hp / max_hp is 1.0f by
+// arithmetic, so neither the step has to write nor the render to read the hp_norm plane for it (most agents of a sparse
+// battle).  KIND_FOOD has the bit set too: test for food first.
+enum : int { KIND_FULL = 0x40, KIND_GROUP_MASK = 0x3f };
+MG_HD unsigned char kind_agent(int g, bool full_hp) { return (unsigned char)((KIND_GROUP0 + g) | (full_hp ? KIND_FULL : 0)); }
+MG_HD bool kind_is_agent(int t) { return t >= KIND_GROUP0 && t != KIND_FOOD; }
+MG_HD int kind_group(int t) { return (t & KIND_GROUP_MASK) - KIND_GROUP0; }
 enum : int { RANK_NONE = -1, DEATH_NEVER = 0x7fffffff, DEATH_BEFORE = -1 };
 enum : unsigned { MVKEY_NONE = 0xffffffffu };
 
@@ -169,7 +176,7 @@ struct EngineDev {
     // observation planes, padded by kpad cells on every side so that a view window never needs a bounds check:
     // cell (x, y) of arena a lives at a * kplane + (y + kpad) * kw + x + kpad
     unsigned char *kind;                      // [A][kplane] 0 empty / 1 wall / 2 + group; kept in step with occ
-    float *hpn;                               // [A][kplane] hp / max_hp of the occupant, rebuilt per observation state
+    float *hpn;                               // [A][kplane] hp / max_hp of the occupant where kind lacks KIND_FULL; kept in step with hp
     int kpad, kw;
     long kplane;
     // per-agent step scratch [A][cap_total]

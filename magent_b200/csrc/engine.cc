@@ -788,7 +788,8 @@ void Engine::to_device() {
                 for (int x = 0; x < W_; ++x) {
                     const int o = occ[(size_t)y * W_ + x];
                     kp[(size_t)(y + hE_.kpad) * hE_.kw + x + hE_.kpad] =
-                        o == OCC_WALL ? KIND_WALL : o == OCC_FOOD ? KIND_FOOD : o >= 0 ? (unsigned char)(KIND_GROUP0 + code_group(o)) : KIND_EMPTY;
+                        o == OCC_WALL ? KIND_WALL : o == OCC_FOOD ? KIND_FOOD : o >= 0 ?
+                        kind_agent(code_group(o), arenas_[a].groups[code_group(o)].hp[code_index(o)] == group_type_[code_group(o)]->hp) : KIND_EMPTY;
                 }
             be::h2d(bx_, hE_.kind + (size_t)a * hE_.kplane, kp.data(), kp.size());
         }

@@ -57,8 +57,10 @@ MG_HD void obs_compose_cell(const EngineDev &E, unsigned curmask, int a, int g, 
     int tg = code_group(t);
     int ch = obs_channel(E, g, tg);
     out[ch] = 1.0f;
-    // hp / max_hp of the occupant (Map.cc:197), from the plane the step phases keep current (step_phases.h hpn_set)
-    out[ch + 1] = E.hpn[a * E.kplane + (long)(y + E.kpad) * E.kw + x + E.kpad];
+    // hp / max_hp of the occupant (Map.cc:197), from the planes the step phases keep current (step_phases.h show_body): an
+    // agent at exactly max_hp carries KIND_FULL in its kind byte instead of a value in the hp_norm plane
+    const long pc = a * E.kplane + (long)(y + E.kpad) * E.kw + x + E.kpad;
+    out[ch + 1] = (E.kind[pc] & KIND_FULL) ? 1.0f : E.hpn[pc];
 }
 
 // non-spatial feature vector of agent (a, g, i)  (GridWorld.cc:386-396, Agent::get_embedding GridWorld.h:155-164)

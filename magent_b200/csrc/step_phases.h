@@ -64,12 +64,20 @@ MG_HD void kind_set(const EngineDev &E, int a, int x, int y, unsigned char k) {
 // ... and so does the hp_norm plane: hp / max_hp of the occupant (Map.cc:197) at every occupied cell, written where an
 // agent's hp changes (attack / starve / absorb) and where it takes new cells (move, turn, placement)
 MG_HD void hpn_set(const EngineDev &E, int a, int x, int y, float v) {
+#if !defined(MG_ABLATE_HPN)                          // (profiling variants only: results are WRONG without it)
     E.hpn[a * E.kplane + (long)(y + E.kpad) * E.kw + x + E.kpad] = v;
+#endif
 }
-MG_HD void hpn_set_body(const EngineDev &E, int a, const GroupDev &G, int x, int y, int bw, int bh, float hp) {
+// the cells of a living agent show its group and hp: kind byte (with KIND_FULL when hp == max_hp) and, unless full, hp / max_hp
+MG_HD void show_body(const EngineDev &E, int a, int g, const GroupDev &G, int x, int y, int bw, int bh, float hp) {
+    const bool full = hp == G.max_hp;
+    const unsigned char k = kind_agent(g, full);
     const float v = hp / G.max_hp;
     for (int bx = 0; bx < bw; ++bx)
-        for (int by = 0; by < bh; ++by) hpn_set(E, a, x + bx, y + by, v);
+        for (int by = 0; by < bh; ++by) {
+            kind_set(E, a, x + bx, y + by, k);
+            if (!full) hpn_set(E, a, x + bx, y + by, v);
+        }
 }
 // ---- directions (turn_mode; reference Map.cc:515-607).  Without turn_mode every agent faces NORTH, for which
 // relative = absolute and the body is width x length.
@@ -440,7 +448,7 @@ MG_HD void phase_attack_apply_starve(Ctx &c, const EngineDev &E, const StepArgs 
         if (!dies && hp != hp0) {                        // keep the hp_norm plane of the observation current
             int bw, bh;
             body_dims(G, agent_dir(E, s, gi), bw, bh);
-            hpn_set_body(E, a, G, s.x[gi], s.y[gi], bw, bh, hp);
+            show_body(E, a, g, G, s.x[gi], s.y[gi], bw, bh, hp);
         }
         if (dies) {
             s.flags[gi] = fl | FLAG_DEAD;
@@ -779,7 +787,7 @@ MG_HD void phase_move_collide(Ctx &c, const EngineDev &E, const StepArgs &S, int
             {                                     // the absorber's cells show its new hp (if it moves, the fill rewrites them)
                 int obw, obh;
                 body_dims(E.grp[og], agent_dir(E, so, oi), obw, obh);
-                hpn_set_body(E, a, E.grp[og], so.x[oi], so.y[oi], obw, obh, hp2);
+                show_body(E, a, og, E.grp[og], so.x[oi], so.y[oi], obw, obh, hp2);
             }
             const AgentSoA &s = cur_soa(E, S.curmask, g);
             const long gi = gidx(E, a, g, i);
@@ -853,12 +861,15 @@ MG_HD void phase_move_fill(Ctx &c, const EngineDev &E, const StepArgs &S, int a,
         long gi = gidx(E, a, g, i);
         int bw, bh;
         mover_dims(E, G, s, gi, turn, bw, bh);
-        const float hpv = ok ? s.hp[gi] / G.max_hp : 0.0f;
+        const float hp = ok ? s.hp[gi] : 0.0f;
+        const bool full = hp == G.max_hp;
+        const unsigned char kd = kind_agent(g, full);
+        const float hpv = hp / G.max_hp;
         for (int bx = 0; bx < bw; ++bx)
             for (int by = 0; by < bh; ++by) {
                 int cell = (ny + by) * E.W + nx + bx;
                 R.claim[cell] = -1;
-                if (ok) { R.occ[cell] = code; kind_set(E, a, nx + bx, ny + by, (unsigned char)(2 + g)); hpn_set(E, a, nx + bx, ny + by, hpv); }
+                if (ok) { R.occ[cell] = code; kind_set(E, a, nx + bx, ny + by, kd); if (!full) hpn_set(E, a, nx + bx, ny + by, hpv); }
             }
         if (ok) {
             s.x[gi] = nx; s.y[gi] = ny;
