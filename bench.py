@@ -227,6 +227,9 @@ class ClockSampler:
         except OSError:
             pass
 
+    def sample_now(self):
+        pass
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
@@ -284,6 +287,58 @@ def bind_to_gpu_numa_node(local_rank):
         return "rank bound to NUMA node %d (%d cpus) of GPU %s" % (node, len(cpus), bus)
     except Exception as e:                                           # noqa: BLE001  (binding is best effort)
         return "not bound (%s)" % type(e).__name__
+
+
+class NvmlClockSampler:
+    """SM clock and throttle reasons of one GPU, polled from a thread of this process through NVML (nvidia-ml-py): two
+    cheap queries per sample.  The nvidia-smi poller above asks for more (power draw among it) and was seen to stall
+    the GPU for several milliseconds when a query landed inside the 25 ms timed window (profiles/README.md, round 2)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index, interval=0.05):
+        import threading
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        self.get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.sm, self.bits, self.interval = [], 0, interval
+        self._stop = threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def sample_now(self):
+        try:
+            self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            self.bits |= int(self.get_reasons(self.h))
+        except Exception:                                            # noqa: BLE001
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self.sample_now()
+            self._stop.wait(self.interval)
+
+    def stop(self):
+        self._stop.set()
+        self.t.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": sorted(n for b, n in self.REASONS.items() if self.bits & b),
+               "samples": len(self.sm), "how": "NVML from a thread of the bench process, every %d ms" % int(self.interval * 1e3)}
+        if self.sm:
+            sm = sorted(self.sm)
+            out["sm_mhz"] = sm[len(sm) // 2]
+        return out
+
+
+def make_clock_sampler(index):
+    if os.environ.get("MAGENT_B200_BENCH_SAMPLER") != "smi":
+        try:
+            return NvmlClockSampler(index)
+        except Exception:                                            # noqa: BLE001  (no nvidia-ml-py: fall back to nvidia-smi)
+            pass
+    return ClockSampler(index)
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -426,7 +481,7 @@ def main():
 
     # the clock sampler starts before the warm-up, so that its own start-up (and first query) is over by the time the
     # timed region begins; it keeps sampling through the timed region and the e2e loop
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = make_clock_sampler(local_rank) if rank == 0 else None
     for w in range(args.warmup):
         dev_step(1000 + w)
     setup_s = time.time() - t_setup
@@ -469,6 +524,8 @@ def main():
         ev0.record()
         env.launch_graph(gid, replays)
         ev1.record()
+        if sampler:
+            sampler.sample_now()                        # the host is ahead of the GPU here: a sample inside the timed region
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1)
         barrier()
@@ -483,6 +540,8 @@ def main():
         for s in range(args.steps):
             dev_step(s)
         ev1.record()
+        if sampler:
+            sampler.sample_now()                        # everything is queued, the GPU is mid-way: a sample inside the timed region
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1)
         obs_ms, obs_launches = env.get_profile()
