@@ -295,12 +295,13 @@ class NvmlClockSampler:
     the GPU for several milliseconds when a query landed inside the 25 ms timed window (profiles/README.md, round 2)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index, interval=0.05):
+    def __init__(self, index, interval=0.05, pci_bus_id=None):
         import threading
         import pynvml
         self.nv = pynvml
         pynvml.nvmlInit()
-        self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        # NVML numbers the physical GPUs, CUDA the visible ones (CUDA_VISIBLE_DEVICES): go by PCI bus id when it is known
+        self.h = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode()) if pci_bus_id else pynvml.nvmlDeviceGetHandleByIndex(index)
         self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         self.get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
             pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
@@ -332,13 +333,13 @@ class NvmlClockSampler:
         return out
 
 
-def make_clock_sampler(index):
+def make_clock_sampler(index, pci_bus_id=None):
     if os.environ.get("MAGENT_B200_BENCH_SAMPLER") != "smi":
         try:
-            return NvmlClockSampler(index)
+            return NvmlClockSampler(index, pci_bus_id=pci_bus_id)
         except Exception:                                            # noqa: BLE001  (no nvidia-ml-py: fall back to nvidia-smi)
             pass
-    return ClockSampler(index)
+    return ClockSampler(pci_bus_id or index)
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -481,7 +482,13 @@ def main():
 
     # the clock sampler starts before the warm-up, so that its own start-up (and first query) is over by the time the
     # timed region begins; it keeps sampling through the timed region and the e2e loop
-    sampler = make_clock_sampler(local_rank) if rank == 0 else None
+    bus = None
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:                                                # noqa: BLE001
+        pass
+    sampler = make_clock_sampler(local_rank, bus) if rank == 0 else None
     for w in range(args.warmup):
         dev_step(1000 + w)
     setup_s = time.time() - t_setup
