@@ -62,7 +62,7 @@ int magent_b200_graph_launch(EnvHandle game, int graph_id, int times);
 void *magent_b200_stream(EnvHandle game);
 /* host threads env_get_observation uses to write host buffers (MAGENT_B200_HOST_THREADS overrides) */
 int magent_b200_host_threads(void);
-int magent_b200_set_host_threads(int n);       /* 0 = default (usable cores, at most 16) */
+int magent_b200_set_host_threads(int n);       /* 0 = default (usable cores, at most 16; 24 on hosts with 48+ usable cores) */
 
 #ifdef __cplusplus
 }

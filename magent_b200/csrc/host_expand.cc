@@ -52,7 +52,11 @@ int host_threads() {
         if (const char *e = getenv("MAGENT_B200_HOST_THREADS")) { int v = atoi(e); if (v >= 1) return v > 256 ? 256 : v; }
         int c = usable_cores();
         if (const char *w = getenv("LOCAL_WORLD_SIZE")) { int v = atoi(w); if (v > 1) c = c / v; }     // torchrun: ranks share the box
-        if (c > 16) c = 16;                // the memory system saturates well before that (profiles/README.md, round 2)
+        // the memory system saturates well before the core count of a big host (profiles/README.md, round 2: one socket
+        // takes its ~200 GB/s from 8 streaming threads, the expansion's bookkeeping costs ~20 % on top): 16 threads, 24
+        // when there are cores to spare
+        const int cap = c >= 48 ? 24 : 16;
+        if (c > cap) c = cap;
         return c < 1 ? 1 : c;
     }();
     return n;

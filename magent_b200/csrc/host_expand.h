@@ -21,7 +21,7 @@ struct ExpandGeom {
 };
 
 // number of threads the host side uses (callers included): MAGENT_B200_HOST_THREADS, else the usable cores (affinity
-// mask capped by the cgroup CPU quota) divided by LOCAL_WORLD_SIZE, at most 16
+// mask capped by the cgroup CPU quota) divided by LOCAL_WORLD_SIZE, at most 16 (24 on hosts with 48+ usable cores)
 int host_threads();
 void set_host_threads(int n);           // 0 = back to the default
 
