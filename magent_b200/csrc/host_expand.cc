@@ -473,6 +473,12 @@ void expand_views(const ExpandGeom &geom, const be::WireDesc &W, float *out, con
         n_parts = blk.parts;
         const size_t off0 = (size_t)((const char *)out - blk.base);
         for (int c = 0; c < W.n_chunks; ++c) part_chunks[((off0 + (size_t)c * chunk_bytes) / blk.stripe) % n_parts].push_back(c);
+    } else if (numa_nodes() > 1 && numa_nodes() <= 8 && T > 1) {
+        // somebody else's buffer (plain numpy memory of the reference wrapper, ...): chunk c always goes to the threads of
+        // node c mod n.  Pages nobody has touched yet become resident where they are first written -- on that node -- and
+        // every later call writes them from the same node again
+        n_parts = numa_nodes();
+        for (int c = 0; c < W.n_chunks; ++c) part_chunks[c % n_parts].push_back(c);
     } else {
         part_chunks[0].resize(W.n_chunks);
         for (int c = 0; c < W.n_chunks; ++c) part_chunks[0][c] = c;

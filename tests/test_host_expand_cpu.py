@@ -156,6 +156,14 @@ for t in range(3):
         env.step(); env.clear_dead()
     for (v0, f0), (v1, f1) in zip(obs[0], obs[1]):
         assert v0.nbytes >= (64 << 20) and np.array_equal(v0.view(np.uint32), v1.view(np.uint32)) and np.array_equal(f0.view(np.uint32), f1.view(np.uint32))
+# somebody else's buffers (plain numpy memory): chunks dealt to the nodes round-robin
+import ctypes
+wire, dense = envs
+h = wire.get_handles()[0]; n = wire.get_num(h)
+v = np.empty((n,) + wire.get_view_space(h), np.float32); f = np.empty((n,) + wire.get_feature_space(h), np.float32)
+L.env_get_observation(wire.game, wire._hv(h), (ctypes.c_void_p * 2)(v.ctypes.data, f.ctypes.data))
+dv, df = dense.get_observation(dense.get_handles()[0])
+assert np.array_equal(v.view(np.uint32), dv.view(np.uint32)) and np.array_equal(f.view(np.uint32), df.view(np.uint32))
 print("OK", obs[0][0][0].nbytes)
 ''' % (pc.REPO, os.path.join(pc.REPO, "tests"), emu)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
